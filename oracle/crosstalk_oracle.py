@@ -1,0 +1,339 @@
+"""CPU oracle for the CrosstalkPy hot path.  TEST INFRASTRUCTURE ONLY.
+
+This file is the *checker*, never the product: only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
+``--impl reference`` legs may import it.  The product path
+(``torch-unet_b200/``) must never import anything from ``oracle/``.
+
+It restates, as plain functional PyTorch-on-CPU / NumPy code over a
+``state_dict``, the arithmetic the reference performs on its hot path:
+
+* single-branch CNN forward   -- /root/reference/regression_model.py:5-61
+* double-branch CNN forward   -- /root/reference/two_branch_regression.py:5-100
+* MSE loss                    -- /root/reference/train_model.py:636,421
+* Adam(weight_decay) update   -- /root/reference/train_model.py:637,424
+* per-image Pearson r         -- /root/reference/test-cross-talk-model.py:59-64
+* per-plane min-max normalise -- /root/reference/train_model.py:211-216
+
+The arithmetic itself lives in third-party libraries that are not vendored in
+the reference (PyTorch -- unpinned in requirements.txt:2 -- and SciPy, which is
+not listed at all).  The versions this oracle was pinned against are
+torch 2.11.0 and scipy 1.18.1.  The reference ships no tests and no golden
+vectors, so the pins are created by ``tests/golden/make_golden.py``, which
+imports the *unmodified* reference modules from /root/reference, runs them on
+the reference's own ``Training_Data`` fixtures and records their outputs in
+``tests/golden/golden.json``; ``tests/test_oracle_golden.py`` holds the oracle
+to those numbers.  Parity status: pinned against reference outputs generated
+in the build container (not against reference-owned tests, which do not exist).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+LEAKY_SLOPE = 0.01          # regression_model.py:16,25,38,43 / two_branch_regression.py:12,...
+BN_EPS = 1e-5               # nn.BatchNorm defaults
+BN_MOMENTUM = 0.1
+
+SINGLE_CHANNELS = (2, 128, 256, 512, 512, 512, 512)   # train_model.py:537 (128 filters, 6 blocks, cap 512)
+DOUBLE_CHANNELS = (1, 64, 128, 256, 512)               # train_model.py:535 (64 filters per branch)
+SINGLE_CONV_IDX = (0, 4, 8, 12, 16, 20)
+DOUBLE_CONV_IDX = (0, 4, 8, 12)
+
+
+# --------------------------------------------------------------------------
+# state_dict construction (same keys / shapes / init RNG stream as the reference)
+# --------------------------------------------------------------------------
+def _conv_bn(sd, prefix, idx, cin, cout):
+    conv = torch.nn.Conv2d(cin, cout, kernel_size=3, stride=1, padding=1)
+    bn = torch.nn.BatchNorm2d(cout)
+    sd[f"{prefix}.{idx}.weight"] = conv.weight.detach().clone()
+    sd[f"{prefix}.{idx}.bias"] = conv.bias.detach().clone()
+    for k, v in bn.state_dict().items():
+        sd[f"{prefix}.{idx + 1}.{k}"] = v.detach().clone()
+
+
+def _fc_head(sd, prefix, in_features):
+    for idx, (fi, fo, has_bn) in zip((1, 5, 9), ((in_features, 512, True), (512, 128, True), (128, 1, False))):
+        lin = torch.nn.Linear(fi, fo)
+        sd[f"{prefix}.{idx}.weight"] = lin.weight.detach().clone()
+        sd[f"{prefix}.{idx}.bias"] = lin.bias.detach().clone()
+        if has_bn:
+            bn = torch.nn.BatchNorm1d(fo)
+            for k, v in bn.state_dict().items():
+                sd[f"{prefix}.{idx + 1}.{k}"] = v.detach().clone()
+
+
+def init_single_state_dict(seed: Optional[int] = 0) -> Dict[str, torch.Tensor]:
+    """state_dict of AdvancedRegressionModel(initial_filters=128, num_conv_blocks=6).
+
+    Consumes the RNG exactly like the reference constructor (regression_model.py:6-50:
+    conv/bn pairs in order, then Linear/BatchNorm1d in order) and replays the
+    train-mode dummy pass of ``_get_conv_output`` (regression_model.py:52-56), which
+    leaves every conv-stack BN with num_batches_tracked=1.
+    """
+    if seed is not None:
+        torch.manual_seed(seed)
+    sd: Dict[str, torch.Tensor] = {}
+    ch = SINGLE_CHANNELS
+    for i, idx in enumerate(SINGLE_CONV_IDX):
+        _conv_bn(sd, "conv_layers", idx, ch[i], ch[i + 1])
+    # dummy pass in train mode on zeros(1, 2, 256, 256): updates running stats
+    with torch.no_grad():
+        x = torch.zeros(1, 2, 256, 256)
+        for idx in SINGLE_CONV_IDX:
+            x = _conv_block(sd, "conv_layers", idx, x, training=True, update_stats=True)
+    _fc_head(sd, "fc_layers", 512 * 4 * 4)
+    return sd
+
+
+def init_double_state_dict(seed: Optional[int] = 0) -> Dict[str, torch.Tensor]:
+    """state_dict of SimplifiedTwoBranchRegressionModel(initial_filters_per_branch=64).
+
+    two_branch_regression.py:60-83: bleed branch, source branch, then the head; the
+    dummy pass runs in eval mode so the BN buffers stay pristine.
+    """
+    if seed is not None:
+        torch.manual_seed(seed)
+    sd: Dict[str, torch.Tensor] = {}
+    ch = DOUBLE_CHANNELS
+    for br in ("bleed_branch", "source_branch"):
+        for i, idx in enumerate(DOUBLE_CONV_IDX):
+            _conv_bn(sd, f"{br}.conv_blocks", idx, ch[i], ch[i + 1])
+    _fc_head(sd, "regression_head.fc_layers", 1024 * 16 * 16)
+    return sd
+
+
+def randomize_bn(sd: Dict[str, torch.Tensor], seed: int = 7) -> Dict[str, torch.Tensor]:
+    """Give every BN layer non-trivial gamma (some negative), beta and running stats.
+
+    Random-init eval outputs are nearly constant, which makes an
+    absolute tolerance vacuous; this is fallback weight set (iii) of SURVEY 8c.
+    """
+    g = torch.Generator().manual_seed(seed)
+    out = {k: v.clone() for k, v in sd.items()}
+    for k in list(out.keys()):
+        if k.endswith("running_mean"):
+            base = k[: -len("running_mean")]
+            n = out[k].numel()
+            gamma = 0.5 + torch.rand(n, generator=g)
+            sign = torch.where(torch.rand(n, generator=g) < 0.25, -1.0, 1.0)
+            out[base + "weight"] = gamma * sign
+            out[base + "bias"] = 0.2 * torch.randn(n, generator=g)
+            out[base + "running_mean"] = out[base + "running_mean"] + 0.05 * torch.randn(n, generator=g)
+            out[base + "running_var"] = out[base + "running_var"] * (0.5 + torch.rand(n, generator=g))
+    return out
+
+
+# --------------------------------------------------------------------------
+# forward passes
+# --------------------------------------------------------------------------
+def _batch_norm(sd, key, x, training, update_stats):
+    rm, rv = sd[f"{key}.running_mean"], sd[f"{key}.running_var"]
+    if training and not update_stats:
+        rm, rv = None, None          # batch statistics, buffers untouched
+    y = F.batch_norm(x, rm, rv, sd[f"{key}.weight"], sd[f"{key}.bias"],
+                     training=training, momentum=BN_MOMENTUM, eps=BN_EPS)
+    if training and update_stats:
+        sd[f"{key}.num_batches_tracked"] = sd[f"{key}.num_batches_tracked"] + 1
+    return y
+
+
+def _conv_block(sd, prefix, idx, x, training=False, update_stats=False, taps=None):
+    """Conv3x3(p=1)+bias -> BatchNorm2d -> LeakyReLU(0.01) -> MaxPool2d(2,2).
+
+    regression_model.py:14-17,23-26 / two_branch_regression.py:10-13,...
+    """
+    y = F.conv2d(x, sd[f"{prefix}.{idx}.weight"], sd[f"{prefix}.{idx}.bias"], stride=1, padding=1)
+    if taps is not None:
+        taps[f"{prefix}.{idx}.conv"] = y
+    y = _batch_norm(sd, f"{prefix}.{idx + 1}", y, training, update_stats)
+    y = F.leaky_relu(y, LEAKY_SLOPE)
+    y = F.max_pool2d(y, kernel_size=2, stride=2)
+    if taps is not None:
+        taps[f"{prefix}.{idx}.pool"] = y
+    return y
+
+
+def _head(sd, prefix, x, training, update_stats, dropout_p, dropout_masks, taps):
+    """Flatten -> Linear -> BN1d -> LeakyReLU -> Dropout -> Linear -> BN1d -> LeakyReLU -> Dropout -> Linear.
+
+    regression_model.py:34-50 / two_branch_regression.py:40-54.  ``dropout_masks`` are
+    explicit keep-masks ([N,512], [N,128], 0/1) so both paths can be fed the same
+    Bernoulli draw; ``None`` in training mode means "no dropout" (p forced to 0).
+    """
+    x = torch.flatten(x, 1)                       # NCHW order: c*H*W + h*W + w
+    for j, idx in enumerate((1, 5)):
+        x = F.linear(x, sd[f"{prefix}.{idx}.weight"], sd[f"{prefix}.{idx}.bias"])
+        if taps is not None:
+            taps[f"{prefix}.{idx}.fc"] = x
+        x = _batch_norm(sd, f"{prefix}.{idx + 1}", x, training, update_stats)
+        x = F.leaky_relu(x, LEAKY_SLOPE)
+        if training and dropout_masks is not None:
+            x = x * dropout_masks[j] * (1.0 / (1.0 - dropout_p))
+    x = F.linear(x, sd[f"{prefix}.9.weight"], sd[f"{prefix}.9.bias"])
+    return x
+
+
+def single_forward(sd, x, training=False, update_stats=False, dropout_masks=None, taps=None):
+    """AdvancedRegressionModel.forward -- regression_model.py:58-61 (dropout p=0.1, :39,44)."""
+    for idx in SINGLE_CONV_IDX:
+        x = _conv_block(sd, "conv_layers", idx, x, training, update_stats, taps)
+    return _head(sd, "fc_layers", x, training, update_stats, 0.1, dropout_masks, taps)
+
+
+def double_forward(sd, x, training=False, update_stats=False, dropout_masks=None, taps=None):
+    """SimplifiedTwoBranchRegressionModel.forward -- two_branch_regression.py:85-100 (dropout p=0.5, :45,50)."""
+    feats = []
+    for br, ch in (("bleed_branch", 0), ("source_branch", 1)):
+        y = x[:, ch:ch + 1]                                   # :88-89
+        for idx in DOUBLE_CONV_IDX:
+            y = _conv_block(sd, f"{br}.conv_blocks", idx, y, training, update_stats, taps)
+        feats.append(y)
+    y = torch.cat(feats, dim=1)                                # :96
+    z = _head(sd, "regression_head.fc_layers", y, training, update_stats, 0.5, dropout_masks, taps)
+    return torch.sigmoid(z) * 0.5                              # :53,100
+
+
+FORWARD = {"single": single_forward, "double": double_forward}
+INIT = {"single": init_single_state_dict, "double": init_double_state_dict}
+
+
+def mse_loss(out: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+    """torch.nn.MSELoss() (mean reduction) -- train_model.py:636,421."""
+    return ((out - target) ** 2).mean()
+
+
+# --------------------------------------------------------------------------
+# training step: autograd over the functional forward + restated Adam
+# --------------------------------------------------------------------------
+def is_param(key: str) -> bool:
+    return not (key.endswith("running_mean") or key.endswith("running_var") or key.endswith("num_batches_tracked"))
+
+
+def loss_and_grads(kind, sd, x, y, dropout_masks=None, update_stats=True):
+    """zero_grad -> forward -> MSELoss -> backward (train_model.py:419-422). Returns (loss, out, grads)."""
+    leaves = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items() if is_param(k)}
+    work = dict(sd)
+    work.update(leaves)
+    out = FORWARD[kind](work, x, training=True, update_stats=update_stats, dropout_masks=dropout_masks)
+    loss = mse_loss(out, y)
+    grads = torch.autograd.grad(loss, list(leaves.values()))
+    if update_stats:
+        for k in sd:
+            if not is_param(k):
+                sd[k] = work[k].detach()
+    return loss.detach(), out.detach(), dict(zip(leaves.keys(), grads))
+
+
+def adam_step(p, g, m, v, step, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=1e-4):
+    """One torch.optim.Adam update with coupled L2 on fp32 tensors, in place.
+
+    train_model.py:637: optim.Adam(lr, weight_decay=1e-4); the update follows
+    torch/optim/adam.py ``_single_tensor_adam``: g += wd*p; m.lerp_(g, 1-b1);
+    v = b2*v + (1-b2) g*g; denom = sqrt(v)/sqrt(1-b2^t) + eps; p -= lr/(1-b1^t) * m/denom.
+    """
+    g = g + weight_decay * p
+    m.lerp_(g, 1.0 - beta1)
+    v.mul_(beta2).addcmul_(g, g, value=1.0 - beta2)
+    bc1 = 1.0 - beta1 ** step
+    bc2 = 1.0 - beta2 ** step
+    step_size = lr / bc1
+    denom = (v.sqrt() / math.sqrt(bc2)).add_(eps)
+    p.addcdiv_(m, denom, value=-step_size)
+    return p, m, v
+
+
+class OracleTrainer:
+    """The reference's inner loop (train_model.py:415-426) over a state_dict."""
+
+    def __init__(self, kind, sd, lr=5e-4, weight_decay=1e-4):
+        self.kind, self.sd, self.lr, self.wd = kind, sd, lr, weight_decay
+        self.m = {k: torch.zeros_like(v) for k, v in sd.items() if is_param(k)}
+        self.v = {k: torch.zeros_like(v) for k, v in sd.items() if is_param(k)}
+        self.t = 0
+
+    def step(self, x, y, dropout_masks=None):
+        loss, out, grads = loss_and_grads(self.kind, self.sd, x, y, dropout_masks)
+        self.t += 1
+        for k, g in grads.items():
+            adam_step(self.sd[k], g, self.m[k], self.v[k], self.t, self.lr, weight_decay=self.wd)
+        return float(loss), out
+
+
+# --------------------------------------------------------------------------
+# Pearson r (test-cross-talk-model.py:59-64)
+# --------------------------------------------------------------------------
+def pearson_f32(a: np.ndarray, b: np.ndarray) -> float:
+    """scipy.stats.pearsonr restated for float32 input (dtype preserved).
+
+    xm = x - mean(x); r = dot(xm/||xm||, ym/||ym||) clipped to [-1, 1]; NaN when
+    either plane is constant (the np.std()==0 guard at :61-62 and scipy's own
+    constant-input rule give the same answer).
+    """
+    x = np.asarray(a, dtype=np.float32).ravel()
+    y = np.asarray(b, dtype=np.float32).ravel()
+    if (x == x[0]).all() or (y == y[0]).all() or np.std(x) == 0 or np.std(y) == 0:
+        return float("nan")
+    xm = x - x.mean(dtype=np.float32)
+    ym = y - y.mean(dtype=np.float32)
+    nx = np.float32(np.linalg.norm(xm))
+    ny = np.float32(np.linalg.norm(ym))
+    r = np.dot(xm / nx, ym / ny)
+    return float(max(min(np.float32(r), np.float32(1.0)), np.float32(-1.0)))
+
+
+def pearson_f64(a: np.ndarray, b: np.ndarray) -> float:
+    """Float64 restatement of the same quantity (the tie-breaker the f32 oracle is graded against)."""
+    x = np.asarray(a, dtype=np.float64).ravel()
+    y = np.asarray(b, dtype=np.float64).ravel()
+    if x.min() == x.max() or y.min() == y.max():
+        return float("nan")
+    xm = x - x.mean()
+    ym = y - y.mean()
+    r = float(np.dot(xm, ym) / math.sqrt(np.dot(xm, xm) * np.dot(ym, ym)))
+    return max(min(r, 1.0), -1.0)
+
+
+def pearson_batch(x: torch.Tensor, f64: bool = True) -> np.ndarray:
+    """Per-image r of channel 0 vs channel 1 of an [N,2,H,W] float32 batch."""
+    xs = x.detach().cpu().numpy()
+    fn = pearson_f64 if f64 else pearson_f32
+    return np.array([fn(xs[i, 0], xs[i, 1]) for i in range(xs.shape[0])], dtype=np.float64)
+
+
+# --------------------------------------------------------------------------
+# inputs
+# --------------------------------------------------------------------------
+def normalize_image(img: np.ndarray) -> np.ndarray:
+    """train_model.py:211-216 (float32 arithmetic on a float32 plane)."""
+    lo, hi = img.min(), img.max()
+    if hi > lo:
+        return (img - lo) / (hi - lo)
+    return img
+
+
+def synthetic_batch(n: int, seed: int = 1234, size: int = 256) -> Tuple[torch.Tensor, torch.Tensor]:
+    """SURVEY 8d generator: U[0,1) source plane, ch0 = normalise(alpha*src + (1-alpha)*noise), labels alpha."""
+    g = torch.Generator().manual_seed(seed)
+    src = torch.rand(n, size, size, generator=g)
+    noise = torch.rand(n, size, size, generator=g)
+    alpha = 0.01 + 0.49 * torch.rand(n, generator=g)
+    mixed = alpha[:, None, None] * src + (1.0 - alpha[:, None, None]) * noise
+
+    def norm(t):
+        lo = t.amin(dim=(1, 2), keepdim=True)
+        hi = t.amax(dim=(1, 2), keepdim=True)
+        return (t - lo) / (hi - lo)
+
+    x = torch.stack([norm(mixed), norm(src)], dim=1).contiguous()
+    return x, alpha[:, None].contiguous()
+
+
+def dropout_masks(n: int, p: float, seed: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    g = torch.Generator().manual_seed(seed)
+    return ((torch.rand(n, 512, generator=g) >= p).float(), (torch.rand(n, 128, generator=g) >= p).float())

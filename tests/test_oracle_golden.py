@@ -1,0 +1,83 @@
+"""Pins oracle/crosstalk_oracle.py to what the unmodified reference computed (tests/golden/make_golden.py)."""
+import numpy as np
+import pytest
+import torch
+
+import crosstalk_oracle as orc
+
+
+def _inputs(golden, n=4):
+    tiles = golden["tiles"]
+    xn = np.stack([np.stack([orc.normalize_image(t[0]), orc.normalize_image(t[1])]) for t in tiles])
+    return torch.from_numpy(xn[:n]), torch.from_numpy(golden["labels_np"][:n])[:, None], xn
+
+
+def _close_stats(sd, stats, rtol):
+    for k, (s, a) in stats.items():
+        v = sd[k].double()
+        assert float(v.abs().sum()) == pytest.approx(a, rel=rtol, abs=1e-9), k
+        assert float(v.sum()) == pytest.approx(s, rel=rtol, abs=max(1e-9, rtol * a)), k
+
+
+@pytest.mark.parametrize("kind", ["single", "double"])
+def test_init_matches_reference_constructor(golden, kind):
+    sd = orc.INIT[kind](seed=0)
+    assert set(sd.keys()) == set(golden[kind]["init_stats"].keys())
+    assert len(sd) == (58 if kind == "single" else 72)
+    _close_stats(sd, golden[kind]["init_stats"], 1e-6)
+
+
+@pytest.mark.parametrize("kind", ["single", "double"])
+def test_eval_forward_matches_reference(golden, kind):
+    x, _, _ = _inputs(golden)
+    sd = orc.INIT[kind](seed=0)
+    with torch.no_grad():
+        out = orc.FORWARD[kind](sd, x).flatten().numpy()
+        out_r = orc.FORWARD[kind](orc.randomize_bn(sd, seed=7), x).flatten().numpy()
+    np.testing.assert_allclose(out, golden[kind]["eval_out"], atol=2e-6, rtol=0)
+    # non-vacuous check: randomised BN gives outputs with real spread
+    np.testing.assert_allclose(out_r, golden[kind]["eval_out_randbn"], atol=1e-5, rtol=1e-5)
+
+
+@pytest.mark.parametrize("kind", ["single", "double"])
+def test_train_two_steps_match_reference(golden, kind):
+    x, y, _ = _inputs(golden)
+    sd = orc.INIT[kind](seed=0)
+    tr = orc.OracleTrainer(kind, sd, lr=5e-4, weight_decay=1e-4)
+    loss0, out0, grads = orc.loss_and_grads(kind, {k: v.clone() for k, v in sd.items()}, x, y, update_stats=False)
+    np.testing.assert_allclose(out0.flatten().numpy(), golden[kind]["train_out"], atol=5e-6, rtol=0)
+    for k, gn in golden[kind]["grad_norms"].items():
+        assert float(grads[k].double().norm()) == pytest.approx(gn, rel=2e-3, abs=1e-9), k
+    losses = [tr.step(x, y)[0] for _ in range(2)]
+    np.testing.assert_allclose(losses, golden[kind]["train_losses"], rtol=1e-3)
+    _close_stats(sd, golden[kind]["after2_stats"], 2e-4)
+
+
+def test_pearson_matches_scipy(golden):
+    _, _, xn = _inputs(golden, 5)
+    for i in range(5):
+        r32 = orc.pearson_f32(xn[i, 0], xn[i, 1])
+        r64 = orc.pearson_f64(xn[i, 0], xn[i, 1])
+        assert abs(r32 - golden["pearson_scipy_f32"][i]) <= 1e-6
+        assert abs(r64 - golden["pearson_scipy_f64"][i]) <= 1e-9
+        assert abs(r64 - golden["pearson_scipy_f32"][i]) <= 1e-6     # north_star tolerance
+
+
+def test_pearson_constant_plane_is_nan():
+    a = np.full((256, 256), 0.1, dtype=np.float32)
+    b = np.random.default_rng(0).random((256, 256), dtype=np.float32)
+    assert np.isnan(orc.pearson_f32(a, b)) and np.isnan(orc.pearson_f64(b, a))
+
+
+def test_adam_step_matches_torch_optim():
+    torch.manual_seed(3)
+    p0 = torch.randn(1000)
+    g = torch.randn(1000)
+    p_ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([p_ref], lr=5e-4, weight_decay=1e-4)
+    p, m, v = p0.clone(), torch.zeros(1000), torch.zeros(1000)
+    for t in range(1, 4):
+        p_ref.grad = g.clone() * t
+        opt.step()
+        orc.adam_step(p, g * t, m, v, t, 5e-4)
+    np.testing.assert_allclose(p.numpy(), p_ref.detach().numpy(), rtol=0, atol=1e-7)
