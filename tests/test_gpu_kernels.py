@@ -1,0 +1,220 @@
+"""GPU parity tests, kernel by kernel, through the C ABI (ctypes) against the CPU oracle.
+
+Tolerances (written here, as the task asks):
+  * Pearson r:               |r_gpu - r_oracle_f64| <= 1e-9, and <= 1e-6 against the float32 SciPy golden.
+  * fp32 kernels (first conv -> bf16 store, head, MSE, Adam): a few float32 / bf16 ulps, stated per test.
+  * bf16 tensor-core kernels: operands are rounded to bf16 by construction, accumulation is fp32, the
+    output is rounded to bf16 once: |err| <= 2^-7 * |ref| + small absolute term.
+"""
+import math
+from ctypes import c_float, c_int
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import crosstalk_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctk():
+    import ctk as _ctk
+    _ctk.load()
+    return _ctk
+
+
+def _bf16_close(out, ref, rel=2 ** -7, abs_=2e-2):
+    err = (out.float().cpu() - ref).abs()
+    bound = rel * ref.abs() + abs_
+    bad = (err > bound).float().mean().item()
+    assert bad == 0.0, f"max err {err.max().item():.4g}, frac over bound {bad:.4g}"
+
+
+# ------------------------------------------------------------------ Pearson
+def test_pearson_synthetic_and_golden(ctk, golden):
+    x, _ = orc.synthetic_batch(16, seed=1234)
+    r = ctk.pearson_per_image(x.cuda()).cpu().numpy()
+    ref = orc.pearson_batch(x, f64=True)
+    assert np.abs(r - ref).max() <= 1e-9
+    tiles = golden["tiles"]
+    xn = np.stack([np.stack([orc.normalize_image(t[0]), orc.normalize_image(t[1])]) for t in tiles])
+    r = ctk.pearson_per_image(torch.from_numpy(xn).cuda()).cpu().numpy()
+    assert np.abs(r - np.array(golden["pearson_scipy_f32"])).max() <= 1e-6      # north_star tolerance
+    assert np.abs(r - np.array(golden["pearson_scipy_f64"])).max() <= 1e-9
+
+
+def test_pearson_edge_cases(ctk):
+    x = torch.rand(4, 2, 64, 64)
+    x[1, 0] = 0.25                      # constant plane -> NaN (test-cross-talk-model.py:61-62)
+    x[2, 1] = x[2, 0]                   # identical planes -> exactly 1 after clipping
+    x[3, 1] = 1.0 - x[3, 0]             # anti-correlated -> -1
+    r = ctk.pearson_per_image(x.cuda()).cpu().numpy()
+    assert math.isnan(r[1])
+    assert r[2] == pytest.approx(1.0, abs=1e-12) and r[2] <= 1.0
+    assert r[3] == pytest.approx(-1.0, abs=1e-6) and r[3] >= -1.0
+    assert abs(r[0] - orc.pearson_f64(x[0, 0].numpy(), x[0, 1].numpy())) <= 1e-9
+    assert ctk.pearson_per_image(torch.empty(0, 2, 64, 64).cuda()).numel() == 0
+
+
+def test_pearson_affine_invariance_full_size(ctk):
+    # size-independent property at the bench size: r(a*x+b, c*y+d) == sign(a*c) * r(x, y)
+    x, _ = orc.synthetic_batch(256, seed=5)
+    xd = x.cuda()
+    r0 = ctk.pearson_per_image(xd)
+    y = xd.clone()
+    y[:, 0] = 3.0 * y[:, 0] + 0.5
+    y[:, 1] = -0.25 * y[:, 1] + 2.0
+    r1 = ctk.pearson_per_image(y)
+    assert (r0 + r1).abs().max().item() <= 5e-7
+
+
+# ------------------------------------------------------------------ first conv block
+@pytest.mark.parametrize("cin,cout,c_off", [(1, 64, 0), (1, 64, 1), (2, 128, 0)])
+def test_conv_first_eval(ctk, cin, cout, c_off):
+    from ctk._lib import call, ptr, stream
+    torch.manual_seed(2)
+    n, H, W = 3, 64, 96
+    x = torch.rand(n, 2, H, W)
+    conv = torch.nn.Conv2d(cin, cout, 3, 1, 1)
+    bn = torch.nn.BatchNorm2d(cout)
+    with torch.no_grad():
+        bn.weight.copy_(torch.randn(cout))
+        bn.bias.copy_(0.1 * torch.randn(cout))
+        bn.running_mean.copy_(0.1 * torch.randn(cout))
+        bn.running_var.copy_(0.5 + torch.rand(cout))
+    bn.eval()
+    with torch.no_grad():
+        ref = F.max_pool2d(F.leaky_relu(bn(conv(x[:, c_off:c_off + cin])), 0.01), 2).permute(0, 2, 3, 1).contiguous()
+    conv, bn = conv.cuda(), bn.cuda()
+    scale = torch.empty(cout, device="cuda")
+    shift = torch.empty(cout, device="cuda")
+    call("ctk_fold_bn_eval", ptr(conv.bias), ptr(bn.weight), ptr(bn.bias), ptr(bn.running_mean), ptr(bn.running_var),
+         c_float(bn.eps), c_int(cout), ptr(scale), ptr(shift), stream())
+    wf = torch.empty(cout, cin * 9, device="cuda")
+    call("ctk_pack_first_weight", ptr(conv.weight), ptr(scale), c_int(cout), c_int(cin), ptr(wf), stream())
+    cstride = cout + 64
+    out = torch.zeros(n, H // 2, W // 2, cstride, device="cuda", dtype=torch.bfloat16)
+    call("ctk_conv_first_eval", ptr(x.cuda()), c_int(n), c_int(2), c_int(c_off), c_int(cin), c_int(H), c_int(W), ptr(wf),
+         ptr(shift), c_int(cout), c_float(0.01), ptr(out), c_int(cstride), c_int(64), stream())
+    torch.cuda.synchronize()
+    assert out[..., :64].abs().max().item() == 0.0            # channel offset respected
+    _bf16_close(out[..., 64:], ref, rel=2 ** -8, abs_=1e-4)   # fp32 math, one bf16 rounding
+
+
+# ------------------------------------------------------------------ tensor-core conv block
+def _conv_tc_case(ctk, n, H, W, cin, cout, flags=0, coff=0, extra=0):
+    from ctk._lib import call, ptr, stream
+    torch.manual_seed(3)
+    x = torch.randn(n, H, W, cin).to(torch.bfloat16)
+    w = (torch.randn(cout, cin, 3, 3) / (3.0 * cin ** 0.5)).to(torch.bfloat16).float()
+    scale = 0.5 + torch.rand(cout)
+    scale[::3] *= -1.0                  # negative BN scale: pooling must come after the affine + LeakyReLU
+    shift = 0.1 * torch.randn(cout)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w, padding=1) * scale[None, :, None, None] + shift[None, :, None, None]
+    ref = F.max_pool2d(F.leaky_relu(ref, 0.01), 2).permute(0, 2, 3, 1).contiguous()
+    wp = torch.empty(9, cout, cin, device="cuda", dtype=torch.bfloat16)
+    call("ctk_pack_conv_weight_bf16", ptr(w.cuda()), c_int(cout), c_int(cin), ptr(wp), stream())
+    cstride = cout + extra
+    out = torch.zeros(n, H // 2, W // 2, cstride, device="cuda", dtype=torch.bfloat16)
+    call("ctk_conv3x3_tc_eval", ptr(x.cuda()), c_int(n), c_int(H), c_int(W), c_int(cin), ptr(wp), c_int(cout),
+         ptr(scale.cuda()), ptr(shift.cuda()), c_float(0.01), ptr(out), c_int(cstride), c_int(coff), c_int(flags),
+         stream())
+    torch.cuda.synchronize()
+    _bf16_close(out[..., coff:coff + cout], ref)
+    if extra:
+        rest = torch.cat([out[..., :coff], out[..., coff + cout:]], dim=-1)
+        assert rest.abs().max().item() == 0.0
+
+
+@pytest.mark.parametrize("n,H,W,cin,cout", [
+    (2, 32, 32, 64, 128),     # two tiles per image row band, one K chunk
+    (3, 16, 16, 128, 256),    # two K chunks, two N tiles
+    (1, 8, 8, 512, 512),      # image smaller than the 16-row tile (single-branch block 6)
+    (2, 48, 24, 64, 128),     # ragged: H not a multiple of the tile height
+    (5, 16, 8, 256, 512),     # odd batch
+])
+def test_conv_tc_eval_shapes(ctk, n, H, W, cin, cout):
+    _conv_tc_case(ctk, n, H, W, cin, cout)
+
+
+def test_conv_tc_eval_channel_offset(ctk):
+    _conv_tc_case(ctk, 2, 16, 16, 64, 128, coff=128, extra=256)
+
+
+def test_conv_tc_many_tiles_persistent(ctk):
+    # more tiles than SMs so every CTA loops: exercises barrier phase wrap-around and TMEM double buffering
+    _conv_tc_case(ctk, 8, 64, 64, 64, 128)
+
+
+# ------------------------------------------------------------------ split-K GEMM + head
+def test_gemm_splitk(ctk):
+    from ctk._lib import call, ptr, stream
+    torch.manual_seed(4)
+    M, N, K, splits = 256, 512, 4096, 8
+    a = torch.randn(M, K).to(torch.bfloat16)
+    b = (torch.randn(N, K) / K ** 0.5).to(torch.bfloat16)
+    ref = a.double() @ b.double().t()
+    part = torch.empty(splits, M, N, device="cuda")
+    call("ctk_gemm_bf16_splitk", ptr(a.cuda()), ptr(b.cuda()), c_int(M), c_int(N), c_int(K), c_int(splits), ptr(part),
+         stream())
+    torch.cuda.synchronize()
+    got = part.double().sum(0).cpu()
+    assert (got - ref).abs().max().item() <= 1e-3
+    # each split is the partial sum over its own K range
+    ks = K // splits
+    ref0 = a[:, :ks].double() @ b[:, :ks].double().t()
+    assert (part[0].double().cpu() - ref0).abs().max().item() <= 1e-3
+
+
+def test_head_eval(ctk):
+    from ctk._lib import call, ptr, stream
+    torch.manual_seed(5)
+    n, splits, mstride, f1, f2 = 37, 4, 128, 512, 128
+    part = torch.randn(splits, mstride, f1)
+    s1, h1 = 0.5 + torch.rand(f1), 0.1 * torch.randn(f1)
+    w2 = torch.randn(f2, f1) / f1 ** 0.5
+    s2, h2 = 0.5 + torch.rand(f2), 0.1 * torch.randn(f2)
+    w3, b3 = torch.randn(f2) / f2 ** 0.5, torch.randn(1)
+    a = F.leaky_relu(part.sum(0)[:n] * s1 + h1, 0.01)
+    b = F.leaky_relu((a @ w2.t()) * s2 + h2, 0.01)
+    z = b @ w3 + b3
+    for sig in (0, 1):
+        out = torch.empty(n, device="cuda")
+        call("ctk_head_eval", ptr(part.cuda()), c_int(splits), c_int(mstride), c_int(n), c_int(f1), c_int(f2),
+             ptr(s1.cuda()), ptr(h1.cuda()), ptr(w2.cuda()), ptr(s2.cuda()), ptr(h2.cuda()), ptr(w3.cuda()),
+             ptr(b3.cuda()), c_float(0.01), c_int(sig), ptr(out), stream())
+        ref = 0.5 * torch.sigmoid(z) if sig else z
+        assert (out.cpu() - ref).abs().max().item() <= 2e-5
+
+
+# ------------------------------------------------------------------ MSE + Adam
+def test_mse_loss(ctk):
+    torch.manual_seed(6)
+    o, t = torch.rand(300, 1), torch.rand(300, 1)
+    loss, grad = ctk.mse_loss(o.cuda(), t.cuda(), want_grad=True)
+    assert loss.item() == pytest.approx(orc.mse_loss(o, t).item(), rel=1e-6)
+    np.testing.assert_allclose(grad.cpu().numpy(), (2 * (o - t) / 300).numpy(), rtol=1e-6, atol=1e-9)
+
+
+def test_adam_matches_oracle_and_torch(ctk):
+    torch.manual_seed(7)
+    shapes = [(70000,), (513, 9), (3,), (128, 64, 3, 3)]
+    ps = [torch.randn(s) for s in shapes]
+    dev = [torch.nn.Parameter(p.clone().cuda()) for p in ps]
+    opt = ctk.Adam(dev, lr=5e-4, weight_decay=1e-4)
+    ref = [p.clone() for p in ps]
+    m = [torch.zeros_like(p) for p in ps]
+    v = [torch.zeros_like(p) for p in ps]
+    for t in range(1, 4):
+        gs = [torch.randn(s) * 0.1 for s in shapes]
+        for d, g in zip(dev, gs):
+            d.grad = g.clone().cuda()
+        opt.step()
+        for p, g, mm, vv in zip(ref, gs, m, v):
+            orc.adam_step(p, g, mm, vv, t, 5e-4)
+    for d, p in zip(dev, ref):
+        np.testing.assert_allclose(d.detach().cpu().numpy(), p.numpy(), rtol=0, atol=2e-6)
+    assert opt.param_groups[0]["lr"] == 5e-4 and int(opt.state[dev[0]]["step"]) == 3

@@ -1,0 +1,308 @@
+// 3x3 / stride 1 / pad 1 convolution block as an implicit GEMM on the 5th-generation tensor cores
+// (tcgen05.mma, bf16 operands, fp32 accumulators in TMEM) fed by TMA, with folded BatchNorm, LeakyReLU and
+// the 2x2 max-pool fused into the epilogue.  Replaces nn.Conv2d + nn.BatchNorm2d(eval) + nn.LeakyReLU +
+// nn.MaxPool2d at /root/reference/regression_model.py:23-26 and two_branch_regression.py:16-19,22-25,28-31.
+//
+// GEMM view: D[pixel, cout] = sum_{tap, cin} X[pixel + tap, cin] * Wt[tap][cout][cin].
+//   M tile  = 128 output pixels = a 16-row x 8-column patch of one image (one pixel per TMEM lane)
+//   N tile  = 128 output channels (one fp32 TMEM column each)
+//   K loop  = (cin / 64) chunks x 9 taps x 4 UMMA_K=16 steps
+// A operand: the (16+2) x (8+2) input halo of the patch is loaded ONCE per 64-channel chunk by a single TMA
+// box (out-of-bounds = zero fill gives the conv padding for free) into 128B-swizzled shared memory, one
+// 128-byte row per pixel.  The nine taps are nine *views* of that buffer: the UMMA descriptor for tap
+// (ky,kx) starts (ky*pitch + kx) rows into the halo and strides one halo row per 8-pixel core-matrix group.
+// This cuts L2->SM traffic for A by 9x against a per-tap im2col load.
+// B operand: per (chunk, tap) a [128 cout x 64 cin] K-major tile of the tap-major packed weights.
+//
+// Warp roles (256 threads): warp 0 = B producer, warp 3 = A producer (one elected lane each),
+// warp 1 = MMA issuer (one lane), warp 2 = TMEM allocator, warps 4-7 = epilogue (TMEM -> registers ->
+// scale/shift -> LeakyReLU -> 2x2 max via two butterfly shuffle stages -> 16-byte NHWC stores).
+// Accumulators are double buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include "ctk_common.h"
+#include "ctk_ptx.cuh"
+
+#include <algorithm>
+
+namespace {
+
+using namespace ctk;
+
+constexpr int kTileH = 16;
+constexpr int kTileW = 8;
+constexpr int kHaloH = kTileH + 2;
+constexpr int kBlockN = 128;
+constexpr int kKC = 64;                 // channels per K chunk = one 128-byte swizzle row
+constexpr int kAStages = 2;
+constexpr int kBStages = 6;
+constexpr int kAccStages = 2;
+constexpr int kThreads = 256;
+constexpr int kBStageBytes = kBlockN * 128;                 // 16 KiB
+constexpr int kAStageBytesMax = kHaloH * 16 * 128;          // 36 KiB (pitch 16)
+constexpr int kSmemBytes = 1024 /*align slack*/ + kAStages * kAStageBytesMax + kBStages * kBStageBytes + 2048;
+
+struct ConvParams {
+  int n_img, H, W, cin, cout;
+  int tiles_x, tiles_y, tiles_n, total_tiles;
+  int pitch;            // halo row pitch in pixels (10 = dense, 16 = padded)
+  int use_base_offset;  // descriptor base-offset field = (addr >> 7) & 7
+  int pool, act;
+  float slope;
+  const float* scale;
+  const float* shift;
+  __nv_bfloat16* out;
+  int out_cstride, out_coffset;
+};
+
+struct TileCoord {
+  int img, y0, x0, n0;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int tile) {
+  TileCoord t;
+  const int nt = tile % p.tiles_n;
+  int sp = tile / p.tiles_n;
+  const int tx = sp % p.tiles_x;
+  sp /= p.tiles_x;
+  const int ty = sp % p.tiles_y;
+  t.img = sp / p.tiles_y;
+  t.y0 = ty * kTileH;
+  t.x0 = tx * kTileW;
+  t.n0 = nt * kBlockN;
+  return t;
+}
+
+struct SmemLayout {
+  uint64_t a_full[kAStages], a_empty[kAStages];
+  uint64_t b_full[kBStages], b_empty[kBStages];
+  uint64_t acc_full[kAccStages], acc_empty[kAccStages];
+  uint32_t tmem_base;
+  uint32_t pad[3];
+  alignas(16) float scale[2][kBlockN];
+  alignas(16) float shift[2][kBlockN];
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                  const ConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* a_smem = smem;
+  uint8_t* b_smem = smem + kAStages * kAStageBytesMax;
+  SmemLayout* sl = reinterpret_cast<SmemLayout*>(b_smem + kBStages * kBStageBytes);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int chunks = p.cin / kKC;
+  const uint32_t a_bytes = static_cast<uint32_t>(kHaloH * p.pitch * 128);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kAStages; ++i) { mbar_init(&sl->a_full[i], 1); mbar_init(&sl->a_empty[i], 1); }
+    for (int i = 0; i < kBStages; ++i) { mbar_init(&sl->b_full[i], 1); mbar_init(&sl->b_empty[i], 1); }
+    for (int i = 0; i < kAccStages; ++i) { mbar_init(&sl->acc_full[i], 1); mbar_init(&sl->acc_empty[i], 128); }
+    fence_mbar_init();
+    tma_prefetch_desc(&tm_a);
+    tma_prefetch_desc(&tm_b);
+  }
+  if (warp == 2) tmem_alloc(&sl->tmem_base, kAccStages * kBlockN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = sl->tmem_base;
+
+  if (warp == 3 && lane == 0) {
+    // ---------------- A producer: one halo box per (tile, chunk)
+    int stage = 0, phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(p, tile);
+      for (int c = 0; c < chunks; ++c) {
+        mbar_wait(&sl->a_empty[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&sl->a_full[stage], a_bytes);
+        tma_load_4d(a_smem + stage * kAStageBytesMax, &tm_a, &sl->a_full[stage], c * kKC, t.x0 - 1, t.y0 - 1, t.img);
+        if (++stage == kAStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 0 && lane == 0) {
+    // ---------------- B producer: one weight tile per (tile, chunk, tap)
+    int stage = 0, phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(p, tile);
+      for (int c = 0; c < chunks; ++c) {
+        for (int tap = 0; tap < 9; ++tap) {
+          mbar_wait(&sl->b_empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&sl->b_full[stage], kBStageBytes);
+          tma_load_2d(b_smem + stage * kBStageBytes, &tm_b, &sl->b_full[stage], c * kKC, tap * p.cout + t.n0);
+          if (++stage == kBStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ---------------- MMA issuer
+    constexpr uint32_t idesc = umma_idesc_bf16_f32(128, kBlockN);
+    const uint32_t sbo = static_cast<uint32_t>(p.pitch * 128);
+    int as = 0, aphase = 0, bs = 0, bphase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const int acc_phase = (it >> 1) & 1;
+      mbar_wait(&sl->acc_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * kBlockN);
+      for (int c = 0; c < chunks; ++c) {
+        mbar_wait(&sl->a_full[as], aphase);
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(a_smem + as * kAStageBytesMax);
+        for (int tap = 0; tap < 9; ++tap) {
+          mbar_wait(&sl->b_full[bs], bphase);
+          tc_fence_after();
+          const int ky = tap / 3, kx = tap - 3 * ky;
+          const uint32_t a_tap = a_base + static_cast<uint32_t>((ky * p.pitch + kx) * 128);
+          const uint32_t bo = p.use_base_offset ? ((a_tap >> 7) & 7u) : 0u;
+          const uint32_t b_base = smem_u32(b_smem + bs * kBStageBytes);
+#pragma unroll
+          for (int s = 0; s < kKC / 16; ++s) {
+            const uint64_t adesc = umma_smem_desc_sw128(a_tap + s * 32, sbo, bo);
+            const uint64_t bdesc = umma_smem_desc_sw128(b_base + s * 32, 1024, 0);
+            umma_bf16(d_tmem, adesc, bdesc, idesc, (c | tap | s) != 0 ? 1u : 0u);
+          }
+          umma_commit(&sl->b_empty[bs]);
+          if (++bs == kBStages) { bs = 0; bphase ^= 1; }
+        }
+        umma_commit(&sl->a_empty[as]);
+        if (++as == kAStages) { as = 0; aphase ^= 1; }
+      }
+      umma_commit(&sl->acc_full[acc]);
+    }
+  } else if (warp >= 4) {
+    // ---------------- epilogue: 128 threads, thread <-> TMEM lane <-> output pixel of the tile
+    const int ew = warp - 4;
+    const int m = ew * 32 + lane;
+    const int r = m >> 3, cpx = m & 7;
+    const int et = threadIdx.x - 128;
+    const int Hp = p.H >> 1, Wp = p.W >> 1;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const TileCoord t = decode_tile(p, tile);
+      const int acc = it & 1;
+      const int acc_phase = (it >> 1) & 1;
+      float* s_scale = sl->scale[it & 1];
+      float* s_shift = sl->shift[it & 1];
+      s_scale[et] = __ldg(p.scale + t.n0 + et);
+      s_shift[et] = __ldg(p.shift + t.n0 + et);
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(&sl->acc_full[acc], acc_phase);
+      tc_fence_after();
+      const int y = t.y0 + r, x = t.x0 + cpx;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(acc * kBlockN);
+#pragma unroll 1
+      for (int cb = 0; cb < kBlockN / 32; ++cb) {
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + cb * 32, v);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float f0 = fmaf(__uint_as_float(v[2 * i]), s_scale[cb * 32 + 2 * i], s_shift[cb * 32 + 2 * i]);
+          float f1 = fmaf(__uint_as_float(v[2 * i + 1]), s_scale[cb * 32 + 2 * i + 1], s_shift[cb * 32 + 2 * i + 1]);
+          if (p.act) { f0 = leaky(f0, p.slope); f1 = leaky(f1, p.slope); }
+          pk[i] = pack_bf16x2(f0, f1);
+        }
+        if (p.pool) {
+          // 2x2 max over lanes {l, l^1, l^8}: each butterfly stage halves the channels a lane keeps
+          const bool odd_x = (lane & 1) != 0;
+          uint32_t q[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const uint32_t send = odd_x ? pk[i] : pk[8 + i];
+            const uint32_t keep = odd_x ? pk[8 + i] : pk[i];
+            q[i] = max_bf16x2(keep, __shfl_xor_sync(0xffffffffu, send, 1));
+          }
+          const bool odd_y = (lane & 8) != 0;
+          uint4 o;
+          uint32_t* ov = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint32_t send = odd_y ? q[i] : q[4 + i];
+            const uint32_t keep = odd_y ? q[4 + i] : q[i];
+            ov[i] = max_bf16x2(keep, __shfl_xor_sync(0xffffffffu, send, 8));
+          }
+          if (y < p.H && x < p.W) {
+            const int ch = t.n0 + cb * 32 + (odd_x ? 16 : 0) + (odd_y ? 8 : 0);
+            __nv_bfloat16* dst = p.out +
+                (static_cast<size_t>(t.img) * Hp * Wp + static_cast<size_t>(y >> 1) * Wp + (x >> 1)) * p.out_cstride +
+                p.out_coffset + ch;
+            *reinterpret_cast<uint4*>(dst) = o;
+          }
+        } else if (y < p.H && x < p.W) {
+          __nv_bfloat16* dst = p.out +
+              (static_cast<size_t>(t.img) * p.H * p.W + static_cast<size_t>(y) * p.W + x) * p.out_cstride +
+              p.out_coffset + t.n0 + cb * 32;
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            reinterpret_cast<uint4*>(dst)[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&sl->acc_empty[acc]);
+    }
+  }
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kAccStages * kBlockN);
+  }
+}
+
+}  // namespace
+
+extern "C" int ctk_conv3x3_tc_eval(const void* x_bf16, int n, int H, int W, int cin, const void* w_packed_bf16,
+                                   int cout, const float* scale, const float* shift, float slope, void* out_bf16,
+                                   int out_cstride, int out_coffset, int flags, void* stream) {
+  if (n == 0) return CTK_OK;
+  CTK_REQUIRE(x_bf16 && w_packed_bf16 && scale && shift && out_bf16);
+  CTK_REQUIRE(n > 0 && H > 0 && W > 0 && H % 2 == 0 && W % kTileW == 0 && cin > 0 && cin % kKC == 0 && cout > 0 &&
+              cout % kBlockN == 0);
+  CTK_REQUIRE(out_coffset >= 0 && out_coffset + cout <= out_cstride && out_cstride % 8 == 0 && out_coffset % 8 == 0);
+  CTK_REQUIRE((reinterpret_cast<uintptr_t>(x_bf16) & 15) == 0 && (reinterpret_cast<uintptr_t>(w_packed_bf16) & 15) == 0 &&
+              (reinterpret_cast<uintptr_t>(out_bf16) & 15) == 0);
+
+  ConvParams p;
+  p.n_img = n; p.H = H; p.W = W; p.cin = cin; p.cout = cout;
+  p.tiles_x = W / kTileW;
+  p.tiles_y = (H + kTileH - 1) / kTileH;
+  p.tiles_n = cout / kBlockN;
+  const long long total = static_cast<long long>(n) * p.tiles_x * p.tiles_y * p.tiles_n;
+  CTK_REQUIRE(total < (1ll << 31));
+  p.total_tiles = static_cast<int>(total);
+  p.pitch = (flags & CTK_CONV_HALO_PITCH16) ? 16 : (kTileW + 2);
+  p.use_base_offset = (flags & CTK_CONV_DESC_BASE_OFFSET) ? 1 : 0;
+  p.pool = (flags & CTK_CONV_NO_POOL) ? 0 : 1;
+  p.act = (flags & CTK_CONV_NO_ACT) ? 0 : 1;
+  p.slope = slope;
+  p.scale = scale; p.shift = shift;
+  p.out = static_cast<__nv_bfloat16*>(out_bf16);
+  p.out_cstride = out_cstride; p.out_coffset = out_coffset;
+
+  CUtensorMap tm_a, tm_b;
+  {
+    const uint64_t dims[4] = {static_cast<uint64_t>(cin), static_cast<uint64_t>(W), static_cast<uint64_t>(H),
+                              static_cast<uint64_t>(n)};
+    const uint64_t strides[3] = {static_cast<uint64_t>(cin) * 2, static_cast<uint64_t>(W) * cin * 2,
+                                 static_cast<uint64_t>(H) * W * cin * 2};
+    const uint32_t box[4] = {kKC, static_cast<uint32_t>(p.pitch), kHaloH, 1};
+    int st = ctk::encode_tmap_bf16_sw128(&tm_a, x_bf16, 4, dims, strides, box);
+    if (st != CTK_OK) return st;
+  }
+  {
+    const uint64_t dims[2] = {static_cast<uint64_t>(cin), static_cast<uint64_t>(9) * cout};
+    const uint64_t strides[1] = {static_cast<uint64_t>(cin) * 2};
+    const uint32_t box[2] = {kKC, kBlockN};
+    int st = ctk::encode_tmap_bf16_sw128(&tm_b, w_packed_bf16, 2, dims, strides, box);
+    if (st != CTK_OK) return st;
+  }
+  CTK_CUDA_TRY(cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  const int grid = std::min(p.total_tiles, ctk::num_sms());
+  conv3x3_tc_kernel<<<grid, kThreads, kSmemBytes, ctk::as_stream(stream)>>>(tm_a, tm_b, p);
+  return ctk::check_launch();
+}

@@ -1,0 +1,46 @@
+// Host-side helpers shared by the libctk translation units: status plumbing, launch checks and
+// TMA tensor-map encoding through the driver entry point (no link-time dependency on libcuda).
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "../../include/ctk.h"
+
+namespace ctk {
+
+void set_last_cuda_error(int e);
+
+#define CTK_CUDA_TRY(expr)                                 \
+  do {                                                     \
+    cudaError_t e__ = (expr);                              \
+    if (e__ != cudaSuccess) {                              \
+      ::ctk::set_last_cuda_error(static_cast<int>(e__));   \
+      return CTK_ERR_CUDA;                                 \
+    }                                                      \
+  } while (0)
+
+#define CTK_REQUIRE(cond)              \
+  do {                                 \
+    if (!(cond)) return CTK_ERR_BAD_ARG; \
+  } while (0)
+
+inline int check_launch() {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_last_cuda_error(static_cast<int>(e));
+    return CTK_ERR_CUDA;
+  }
+  return CTK_OK;
+}
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// rank <= 4 bf16 tensor map, 128-byte swizzle.  dims/strides innermost first; strides in bytes for dims 1..rank-1.
+int encode_tmap_bf16_sw128(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                           const uint64_t* strides_bytes, const uint32_t* box);
+
+int num_sms();
+
+}  // namespace ctk

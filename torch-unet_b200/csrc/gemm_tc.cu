@@ -1,0 +1,128 @@
+// Split-K bf16 GEMM on tcgen05 for the first fully connected layer of each regression head
+// (nn.Linear at /root/reference/regression_model.py:36 and two_branch_regression.py:42):
+//   partial[s][m][n] = sum_{k in split s} A[m][k] * B[n][k]
+// A = flattened NHWC activations [batch, K], B = NHWC-column-permuted FC1 weight [512, K]; both K-major, so
+// both operands are plain 128B-swizzled TMA tiles.  The batch is tiny (M = 256) and K is huge (262 144 for
+// the double-branch model), hence split-K: (M/128) x (N/128) x splits CTAs, each streaming its K range
+// through a 6-stage TMA->UMMA pipeline and writing one fp32 partial tile; ctk_head_eval sums the splits.
+#include "ctk_common.h"
+#include "ctk_ptx.cuh"
+
+namespace {
+
+using namespace ctk;
+
+constexpr int kBM = 128, kBN = 128, kBK = 64;
+constexpr int kStages = 6;
+constexpr int kThreads = 192;                         // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2-5 epilogue
+constexpr int kStageBytes = (kBM + kBN) * kBK * 2;    // 32 KiB
+constexpr int kSmemBytes = 1024 + kStages * kStageBytes + 256;
+
+struct GemmSmem {
+  uint64_t full[kStages], empty[kStages], acc_full;
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_splitk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, int M, int N,
+                   int k_per_split, float* __restrict__ partial) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  GemmSmem* sl = reinterpret_cast<GemmSmem*>(smem + kStages * kStageBytes);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * kBM, n0 = blockIdx.y * kBN, split = blockIdx.z;
+  const int k_begin = split * k_per_split;
+  const int k_iters = k_per_split / kBK;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kStages; ++i) { mbar_init(&sl->full[i], 1); mbar_init(&sl->empty[i], 1); }
+    mbar_init(&sl->acc_full, 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&tm_a);
+    tma_prefetch_desc(&tm_b);
+  }
+  if (warp == 1) tmem_alloc(&sl->tmem_base, kBN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = sl->tmem_base;
+
+  if (warp == 0 && lane == 0) {
+    int stage = 0, phase = 0;
+    for (int i = 0; i < k_iters; ++i) {
+      mbar_wait(&sl->empty[stage], phase ^ 1);
+      mbar_arrive_expect_tx(&sl->full[stage], kStageBytes);
+      uint8_t* a_dst = smem + stage * kStageBytes;
+      tma_load_2d(a_dst, &tm_a, &sl->full[stage], k_begin + i * kBK, m0);
+      tma_load_2d(a_dst + kBM * kBK * 2, &tm_b, &sl->full[stage], k_begin + i * kBK, n0);
+      if (++stage == kStages) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp == 1 && lane == 0) {
+    constexpr uint32_t idesc = umma_idesc_bf16_f32(kBM, kBN);
+    int stage = 0, phase = 0;
+    for (int i = 0; i < k_iters; ++i) {
+      mbar_wait(&sl->full[stage], phase);
+      tc_fence_after();
+      const uint32_t a_base = smem_u32(smem + stage * kStageBytes);
+      const uint32_t b_base = a_base + kBM * kBK * 2;
+#pragma unroll
+      for (int s = 0; s < kBK / 16; ++s) {
+        umma_bf16(tmem_base, umma_smem_desc_sw128(a_base + s * 32, 1024, 0),
+                  umma_smem_desc_sw128(b_base + s * 32, 1024, 0), idesc, (i | s) != 0 ? 1u : 0u);
+      }
+      umma_commit(&sl->empty[stage]);
+      if (++stage == kStages) { stage = 0; phase ^= 1; }
+    }
+    umma_commit(&sl->acc_full);
+  } else if (warp >= 2) {
+    const int q = warp & 3;                       // TMEM lane quadrant this warp may read
+    const int row = m0 + q * 32 + lane;
+    mbar_wait(&sl->acc_full, 0);
+    tc_fence_after();
+    float* dst = partial + (static_cast<size_t>(split) * M + row) * N + n0;
+#pragma unroll 1
+    for (int cb = 0; cb < kBN / 32; ++cb) {
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + cb * 32, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        reinterpret_cast<uint4*>(dst + cb * 32)[i] = make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    }
+  }
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kBN);
+  }
+}
+
+}  // namespace
+
+extern "C" int ctk_gemm_bf16_splitk(const void* a_bf16, const void* b_bf16, int M, int N, int K, int splits,
+                                    float* partial, void* stream) {
+  CTK_REQUIRE(a_bf16 && b_bf16 && partial && M > 0 && N > 0 && K > 0 && splits > 0);
+  CTK_REQUIRE(M % kBM == 0 && N % kBN == 0 && K % (kBK * splits) == 0 && splits <= 65535);
+  CTK_REQUIRE((reinterpret_cast<uintptr_t>(a_bf16) & 15) == 0 && (reinterpret_cast<uintptr_t>(b_bf16) & 15) == 0 &&
+              (reinterpret_cast<uintptr_t>(partial) & 15) == 0);
+  CUtensorMap tm_a, tm_b;
+  const uint32_t box[2] = {kBK, kBM};
+  {
+    const uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(M)};
+    const uint64_t strides[1] = {static_cast<uint64_t>(K) * 2};
+    int st = ctk::encode_tmap_bf16_sw128(&tm_a, a_bf16, 2, dims, strides, box);
+    if (st != CTK_OK) return st;
+  }
+  {
+    const uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
+    const uint64_t strides[1] = {static_cast<uint64_t>(K) * 2};
+    int st = ctk::encode_tmap_bf16_sw128(&tm_b, b_bf16, 2, dims, strides, box);
+    if (st != CTK_OK) return st;
+  }
+  CTK_CUDA_TRY(cudaFuncSetAttribute(gemm_splitk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  dim3 grid(M / kBM, N / kBN, splits);
+  gemm_splitk_kernel<<<grid, kThreads, kSmemBytes, ctk::as_stream(stream)>>>(tm_a, tm_b, M, N, K / splits, partial);
+  return ctk::check_launch();
+}

@@ -1,0 +1,17 @@
+"""ctk -- B200-native hot path of CrosstalkPy behind the reference's own Python surface.
+
+    from ctk import AdvancedRegressionModel, SimplifiedTwoBranchRegressionModel, accelerate
+    from ctk import pearson_per_image, mse_loss, Adam
+
+Everything here drives hand-written sm_100a kernels in libctk.so through the C ABI of include/ctk.h.
+"""
+from ._lib import CtkError, EXPORTED_SYMBOLS, LIB_PATH, load
+from .engine import InferenceEngine
+from .metrics import pearson_per_image
+from .models import (AdvancedRegressionModel, SimplifiedFeatureExtractionBranch, SimplifiedRegressionHead,
+                     SimplifiedTwoBranchRegressionModel, accelerate)
+from .optim import Adam, mse_loss
+
+__all__ = ["CtkError", "EXPORTED_SYMBOLS", "LIB_PATH", "load", "InferenceEngine", "pearson_per_image",
+           "AdvancedRegressionModel", "SimplifiedFeatureExtractionBranch", "SimplifiedRegressionHead",
+           "SimplifiedTwoBranchRegressionModel", "accelerate", "Adam", "mse_loss"]

@@ -1,0 +1,99 @@
+"""ctypes binding of libctk.so (the C ABI declared in include/ctk.h).
+
+There is deliberately no fallback: if the shared library is missing or a call fails, the caller gets an
+exception -- never a silent PyTorch/CPU path.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libctk.so")
+
+CONV_HALO_PITCH16 = 1
+CONV_DESC_BASE_OFFSET = 2
+CONV_NO_POOL = 4
+CONV_NO_ACT = 8
+ADAM_CHUNK = 65536
+
+
+class CtkError(RuntimeError):
+    pass
+
+
+# name -> (restype, argtypes); mirrors include/ctk.h one to one
+_SIGNATURES = {
+    "ctk_abi_version": (c_int, []),
+    "ctk_status_string": (c_char_p, [c_int]),
+    "ctk_last_cuda_error": (c_int, []),
+    "ctk_device_check": (c_int, []),
+    "ctk_pearson_workspace_bytes": (c_size_t, [c_int]),
+    "ctk_pearson_f32": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "ctk_fold_bn_eval": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int, c_void_p, c_void_p,
+                                 c_void_p]),
+    "ctk_pack_conv_weight_bf16": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "ctk_pack_first_weight": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "ctk_pack_fc1_weight_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "ctk_conv_first_eval": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
+                                    c_float, c_void_p, c_int, c_int, c_void_p]),
+    "ctk_conv3x3_tc_eval": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_float,
+                                    c_void_p, c_int, c_int, c_int, c_void_p]),
+    "ctk_gemm_bf16_splitk": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "ctk_head_eval": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                              c_void_p, c_void_p, c_void_p, c_float, c_int, c_void_p, c_void_p]),
+    "ctk_mse_loss": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "ctk_adam_multi": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float,
+                               c_float, c_float, c_float, c_float, c_int, c_float, c_void_p]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES.keys())
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    """Load libctk.so (building nothing: run ``python torch-unet_b200/build.py`` or ``__graft_entry__.build()`` first)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise CtkError(f"{LIB_PATH} is missing: build it with `python torch-unet_b200/build.py` "
+                           "(there is no CPU or PyTorch fallback for the CUDA hot path)")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(status: int, what: str = "") -> None:
+    if status != 0:
+        lib = load()
+        msg = lib.ctk_status_string(status).decode()
+        raise CtkError(f"{what}: {msg} (status {status}, cuda error {lib.ctk_last_cuda_error()})")
+
+
+def ptr(t) -> c_void_p:
+    return c_void_p(0) if t is None else c_void_p(t.data_ptr())
+
+
+def stream() -> c_void_p:
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def call(name: str, *args) -> None:
+    check(getattr(load(), name)(*args), name)
+
+
+def require_device(t: torch.Tensor, dtype=None, what: str = "tensor") -> None:
+    if not t.is_cuda:
+        raise CtkError(f"{what} must live on a CUDA device (the ctk hot path has no CPU fallback)")
+    if not t.is_contiguous():
+        raise CtkError(f"{what} must be contiguous")
+    if dtype is not None and t.dtype != dtype:
+        raise CtkError(f"{what} must be {dtype}, got {t.dtype}")

@@ -1,0 +1,30 @@
+"""Per-image comparison metrics on the device (replaces the host loop at test-cross-talk-model.py:52-64)."""
+from __future__ import annotations
+
+from ctypes import c_int, c_size_t
+
+import torch
+
+from . import _lib
+from ._lib import call, ptr, stream
+
+
+def pearson_per_image(inputs: torch.Tensor) -> torch.Tensor:
+    """Pearson r between channel 0 and channel 1 of every [2,H,W] float32 tile of ``inputs`` ([N,2,H,W], CUDA).
+
+    Returns float64 [N]; NaN where either plane is constant (the ``np.std(...) == 0`` guard of
+    test-cross-talk-model.py:61-62); clipped to [-1, 1] like scipy.stats.pearsonr.
+    """
+    _lib.require_device(inputs, torch.float32, "inputs")
+    if inputs.dim() != 4 or inputs.shape[1] != 2:
+        raise _lib.CtkError(f"inputs must be [N,2,H,W], got {tuple(inputs.shape)}")
+    n = inputs.shape[0]
+    plane = inputs.shape[2] * inputs.shape[3]
+    out = torch.empty(n, device=inputs.device, dtype=torch.float64)
+    if n == 0:
+        return out
+    lib = _lib.load()
+    ws_bytes = lib.ctk_pearson_workspace_bytes(c_int(n))
+    ws = torch.empty(ws_bytes // 8, device=inputs.device, dtype=torch.float64)
+    call("ctk_pearson_f32", ptr(inputs), c_int(n), c_int(plane), ptr(out), ptr(ws), c_size_t(ws_bytes), stream())
+    return out
