@@ -1,0 +1,252 @@
+#!/usr/bin/env python
+"""bench.py -- images/sec of the CrosstalkPy hot path on B200 (BASELINE.json metric), one JSON line.
+
+Workload at every N: BASELINE.json configs[1] -- double-branch (-o double) inference of a batch of 256 synthetic
+2-channel 256x256 tiles per GPU plus the per-tile Pearson baseline.  One "step" = Pearson + eval forward over
+one 256-tile batch.  Tiles are independent, so N GPUs shard tiles with no collective ("weak" scaling).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]           # our arm
+    python bench.py --impl reference [...]                         # the reference's CPU path (oracle port)
+
+Under torchrun (N > 1) each rank drives one GPU; rank 0 prints the line.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (os.path.join(ROOT, "torch-unet_b200"), os.path.join(ROOT, "oracle")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import torch  # noqa: E402
+
+METRIC = "infer images/sec (double-branch, 2ch 256x256, batch 256/GPU, + Pearson)"
+BATCH = 256
+GFLOP_PER_IMG = 14.92          # double-branch forward
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "src": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1400.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for line in out.strip().splitlines():
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_rate(n_tiles, steps, warmup):
+    """The reference's CPU path (oracle port: same ATen ops the reference modules call) on the host cores."""
+    import crosstalk_oracle as orc
+    torch.set_num_threads(os.cpu_count() or 1)
+    x, _ = orc.synthetic_batch(n_tiles, seed=1234)
+    sd = orc.init_double_state_dict(0)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            orc.pearson_batch(x, f64=False)                       # scipy-style loop, test-cross-talk-model.py:58-64
+            orc.double_forward(sd, x)
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    return n_tiles / sec, sec, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_tiles = 16
+    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 1))
+    rate, sec, cores = cpu_reference_rate(n_tiles, steps, warmup)
+    sample = f"{n_tiles} of the {BATCH} tiles of one step (pearson loop + double-branch eval forward), fp32, torch CPU"
+    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": "images/sec", "n_gpus": args.gpus,
+            "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "double-branch inference, 256 synthetic 2ch 256x256 tiles + Pearson",
+                       "bounded_sample_tiles": n_tiles},
+            "cpu_baseline": {"value": rate, "unit": "images/sec", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": rate, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ctk", choices=["ctk", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch.distributed as dist
+    import ctk
+    from ctk import _lib
+    import crosstalk_oracle as orc          # cpu_baseline leg + synthetic generator only
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the ctk hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    steps, warmup = args.steps, max(3, args.warmup)
+
+    # ---- model (random init of the reference architecture) and synthetic tiles (SURVEY 8d generator)
+    torch.manual_seed(0)
+    model = ctk.SimplifiedTwoBranchRegressionModel(initial_filters_per_branch=64)
+    model.load_state_dict(orc.randomize_bn(model.state_dict(), seed=7))
+    model = model.to(dev).eval()
+    base, _ = orc.synthetic_batch(32, seed=1234 + rank)
+    n_rot = 3                                   # rotate distinct 134 MB input batches (> 126 MB L2 each)
+    host_batches = [base.roll(shifts=i, dims=0).repeat(BATCH // 32, 1, 1, 1).contiguous().pin_memory() for i in range(n_rot)]
+    dev_batches = [b.to(dev) for b in host_batches]
+    scores = torch.empty(BATCH, 1, device=dev)
+    r_out = torch.empty(BATCH, device=dev, dtype=torch.float64)
+    engine = ctk.models.get_engine(model)
+
+    def step(i):
+        x = dev_batches[i % n_rot]
+        ctk.pearson_per_image(x, out=r_out)
+        engine.forward(x, out=scores)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.no_grad():
+        for i in range(warmup):
+            step(i)
+        barrier()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        launches0 = _lib.launch_count
+        timeline = _lib.start_timeline()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            step(i)
+        e1.record()
+        barrier()
+        _lib.stop_timeline()
+        launches = _lib.launch_count - launches0
+        clocks = sampler.stop() if rank == 0 else None
+        ms = e0.elapsed_time(e1)
+        # ---- end to end: host buffers in, host results out, through the public HostScorer API
+        scorer = ctk.HostScorer(model, slice_tiles=64, device=str(dev))
+        for i in range(2):
+            scorer.score(host_batches[i % n_rot])
+        barrier()
+        t0 = time.perf_counter()
+        e2e_steps = max(3, steps // 2)
+        for i in range(e2e_steps):
+            s_host, r_host = scorer.score(host_batches[i % n_rot])
+        torch.cuda.synchronize()
+        e2e_ms = (time.perf_counter() - t0) * 1e3
+        barrier()
+
+    t = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = t.tolist()
+    value = world * BATCH * steps / (ms / 1e3)
+    e2e_value = world * BATCH * e2e_steps / (e2e_ms / 1e3)
+
+    if rank == 0:
+        pk = peaks()
+        per = {}
+        for name, a, b, meta in timeline:
+            d = per.setdefault(name, {"ms": 0.0, "n": 0, "flops": 0.0})
+            d["ms"] += a.elapsed_time(b)
+            d["n"] += 1
+            d["flops"] += (meta or {}).get("flops", 0.0)
+        conv = per.get("ctk_conv3x3_tc_eval", {"ms": 0.0, "n": 1, "flops": 0.0})
+        conv_tf = conv["flops"] / (conv["ms"] / 1e3) / 1e12 if conv["ms"] > 0 else 0.0
+        roof = {"kernel": "conv3x3_tc_kernel", "bound": "tensor", "achieved": conv_tf, "peak": pk["bf16_tflops"],
+                "unit": "TFLOP/s", "frac": conv_tf / pk["bf16_tflops"], "traffic": None,
+                "peak_source": pk["src"] + " (sustained cuBLAS bf16)",
+                "avg_launch_ms": conv["ms"] / max(1, conv["n"]), "launches": conv["n"],
+                "share_of_step": conv["ms"] / ms if ms > 0 else None,
+                "per_call_ms_per_step": {k: v["ms"] / steps for k, v in per.items()}}
+        line = {"metric": METRIC, "value": value, "unit": "images/sec", "n_gpus": world, "steps": steps, "warmup": warmup,
+                "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": "double-branch inference, batch 256 synthetic 2ch 256x256 tiles per GPU + Pearson "
+                                       "(BASELINE.json configs[1])",
+                           "per_gpu_batch": BATCH, "global_batch": BATCH * world, "parallelism": f"tiles sharded x{world}, no collective",
+                           "l2_policy": "inputs larger than L2 (134 MB per batch), 3 distinct batches rotated",
+                           "weights": "seed-0 random init, randomised BN stats"},
+                "whole_net_tflops": value * GFLOP_PER_IMG / 1e3,
+                "roofline": roof, "clocks": clocks, "gpu_launches": launches,
+                "e2e": {"value": e2e_value, "unit": "images/sec", "h2d_bytes_per_step": scorer.h2d_bytes,
+                        "d2h_bytes_per_step": scorer.d2h_bytes, "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
+                        "api": "ctk.HostScorer.score(pinned host tiles) -> host scores + Pearson r"}}
+        if world == 1 and not args.no_cpu_baseline:
+            rate, sec, cores = cpu_reference_rate(16, 3, 1)
+            line["cpu_baseline"] = {"value": rate, "unit": "images/sec", "cores": cores, "kind": "port",
+                                    "sample": "16 of the 256 tiles of one step (pearson loop + double-branch eval forward), "
+                                              "oracle port = the same ATen CPU ops the reference modules call, fp32"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

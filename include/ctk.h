@@ -89,10 +89,8 @@ int ctk_conv_first_eval(const float* x, int n, int c_total, int c_offset, int ci
  * (torch.cat, two_branch_regression.py:96) without a copy.
  * flags: CTK_CONV_* bits below (0 = default).
  * ------------------------------------------------------------------------------------------ */
-#define CTK_CONV_HALO_PITCH16 1  /* pad halo rows to 16 pixels in shared memory (safe swizzle phase)   */
-#define CTK_CONV_DESC_BASE_OFFSET 2 /* put (addr>>7)&7 into the UMMA descriptor base-offset field        */
-#define CTK_CONV_NO_POOL 4       /* skip the 2x2 max-pool (out is [n,H,W,out_cstride])                 */
-#define CTK_CONV_NO_ACT 8        /* skip LeakyReLU                                                     */
+#define CTK_CONV_NO_POOL 1       /* skip the 2x2 max-pool (out is [n,H,W,out_cstride])                 */
+#define CTK_CONV_NO_ACT 2        /* skip LeakyReLU                                                     */
 int ctk_conv3x3_tc_eval(const void* x_bf16, int n, int H, int W, int cin,
                         const void* w_packed_bf16, int cout, const float* scale, const float* shift, float slope,
                         void* out_bf16, int out_cstride, int out_coffset, int flags, void* stream);

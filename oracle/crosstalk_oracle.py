@@ -129,6 +129,21 @@ def randomize_bn(sd: Dict[str, torch.Tensor], seed: int = 7) -> Dict[str, torch.
     return out
 
 
+def calibrate_bn(kind: str, sd: Dict[str, torch.Tensor], x: torch.Tensor) -> Dict[str, torch.Tensor]:
+    """Weights whose eval outputs have real spread: one train-mode pass over ``x`` with BN momentum 1.0, so every
+    running_mean / running_var becomes that batch's statistics (what nn.BatchNorm does with momentum=1.0).
+    tests/golden/make_golden.py does the same to the reference modules (``bn.momentum = 1.0``)."""
+    global BN_MOMENTUM
+    out = {k: v.clone() for k, v in sd.items()}
+    old, BN_MOMENTUM = BN_MOMENTUM, 1.0
+    try:
+        with torch.no_grad():
+            FORWARD[kind](out, x, training=True, update_stats=True, dropout_masks=None)
+    finally:
+        BN_MOMENTUM = old
+    return out
+
+
 # --------------------------------------------------------------------------
 # forward passes
 # --------------------------------------------------------------------------

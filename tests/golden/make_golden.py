@@ -68,7 +68,7 @@ def tensor_stats(sd):
     return {k: [float(v.double().sum()), float(v.double().abs().sum())] for k, v in sd.items()}
 
 
-def run_model(kind, x, y):
+def run_model(kind, x, y, x5):
     torch.manual_seed(0)
     model = AdvancedRegressionModel(initial_filters=128, num_conv_blocks=6) if kind == "single" \
         else SimplifiedTwoBranchRegressionModel(initial_filters_per_branch=64)
@@ -82,6 +82,22 @@ def run_model(kind, x, y):
     model.load_state_dict(rsd)
     with torch.no_grad():
         res["eval_out_randbn"] = model(x).flatten().tolist()
+    model.load_state_dict(saved)
+    # calibrated BN: one train-mode pass with momentum 1.0 (running stats := batch stats), then eval on the same tiles
+    model.train()
+    for mod in model.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+        if isinstance(mod, (torch.nn.BatchNorm1d, torch.nn.BatchNorm2d)):
+            mod.momentum = 1.0
+    with torch.no_grad():
+        model(x5)
+    model.eval()
+    with torch.no_grad():
+        res["eval_out_calibrated"] = model(x5).flatten().tolist()
+    for mod in model.modules():
+        if isinstance(mod, (torch.nn.BatchNorm1d, torch.nn.BatchNorm2d)):
+            mod.momentum = 0.1
     model.load_state_dict(saved)
     # train mode, dropout p forced to 0
     model.train()
@@ -121,7 +137,7 @@ def main():
     gold["pearson_scipy_f64"] = [float(pearsonr(xn[i, 0].flatten().astype(np.float64),
                                                 xn[i, 1].flatten().astype(np.float64))[0]) for i in range(len(IDS))]
     for kind in ("single", "double"):
-        gold[kind] = run_model(kind, x4, y4)
+        gold[kind] = run_model(kind, x4, y4, torch.from_numpy(xn))
         print(kind, "eval", gold[kind]["eval_out"], "train", gold[kind]["train_out"], gold[kind]["train_losses"])
     with open(os.path.join(HERE, "golden.json"), "w") as f:
         json.dump(gold, f, indent=1)

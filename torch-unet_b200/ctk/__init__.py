@@ -11,7 +11,8 @@ from .metrics import pearson_per_image
 from .models import (AdvancedRegressionModel, SimplifiedFeatureExtractionBranch, SimplifiedRegressionHead,
                      SimplifiedTwoBranchRegressionModel, accelerate)
 from .optim import Adam, mse_loss
+from .pipeline import HostScorer
 
 __all__ = ["CtkError", "EXPORTED_SYMBOLS", "LIB_PATH", "load", "InferenceEngine", "pearson_per_image",
            "AdvancedRegressionModel", "SimplifiedFeatureExtractionBranch", "SimplifiedRegressionHead",
-           "SimplifiedTwoBranchRegressionModel", "accelerate", "Adam", "mse_loss"]
+           "SimplifiedTwoBranchRegressionModel", "accelerate", "Adam", "mse_loss", "HostScorer"]

@@ -14,10 +14,8 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libctk.so")
 
-CONV_HALO_PITCH16 = 1
-CONV_DESC_BASE_OFFSET = 2
-CONV_NO_POOL = 4
-CONV_NO_ACT = 8
+CONV_NO_POOL = 1
+CONV_NO_ACT = 2
 ADAM_CHUNK = 65536
 
 
@@ -86,8 +84,39 @@ def stream() -> c_void_p:
     return c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-def call(name: str, *args) -> None:
-    check(getattr(load(), name)(*args), name)
+# kernels launched per successful call (bench.py reports the sum as "gpu_launches")
+KERNELS_PER_CALL = {"ctk_pearson_f32": 2, "ctk_fold_bn_eval": 1, "ctk_pack_conv_weight_bf16": 1, "ctk_pack_first_weight": 1,
+                    "ctk_pack_fc1_weight_bf16": 1, "ctk_conv_first_eval": 1, "ctk_conv3x3_tc_eval": 1,
+                    "ctk_gemm_bf16_splitk": 1, "ctk_head_eval": 1, "ctk_mse_loss": 1, "ctk_adam_multi": 1}
+launch_count = 0
+_timeline = None      # when a list: (name, start_event, end_event, meta) per call, for per-kernel timing in bench.py
+
+
+def call(name: str, *args, meta=None) -> None:
+    global launch_count
+    fn = getattr(load(), name)
+    if _timeline is not None and name in KERNELS_PER_CALL:
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(fn(*args), name)
+        e1.record()
+        _timeline.append((name, e0, e1, meta))
+    else:
+        check(fn(*args), name)
+    launch_count += KERNELS_PER_CALL.get(name, 0)
+
+
+def start_timeline() -> list:
+    global _timeline
+    _timeline = []
+    return _timeline
+
+
+def stop_timeline() -> list:
+    global _timeline
+    t, _timeline = _timeline, None
+    return t or []
 
 
 def require_device(t: torch.Tensor, dtype=None, what: str = "tensor") -> None:

@@ -156,7 +156,8 @@ class InferenceEngine:
                     call("ctk_conv3x3_tc_eval", ptr(cur), c_int(n), c_int(h), c_int(w), c_int(conv.in_channels),
                          ptr(pk[f"b{bi}.l{li}.w"]), c_int(cout), ptr(pk[f"b{bi}.l{li}.scale"]),
                          ptr(pk[f"b{bi}.l{li}.shift"]), c_float(LEAKY_SLOPE), ptr(dst), c_int(cstride), c_int(coff),
-                         c_int(self.conv_flags), stream())
+                         c_int(self.conv_flags), stream(),
+                         meta={"flops": 2.0 * n * h * w * cout * 9 * conv.in_channels})
                 if taps is not None and not last:
                     taps[f"b{bi}.l{li}"] = dst.clone()
                 cur = dst
@@ -181,14 +182,19 @@ class InferenceEngine:
             taps["fc1_partial"] = partial[:, :n].clone()
 
     @torch.no_grad()
-    def forward(self, x: torch.Tensor, taps: Optional[dict] = None) -> torch.Tensor:
+    def forward(self, x: torch.Tensor, taps: Optional[dict] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         _lib.require_device(x, torch.float32, "input batch")
         if x.dim() != 4 or x.shape[1] != 2 or x.shape[2] % 32 or x.shape[3] % 32:
             raise _lib.CtkError(f"input must be [N,2,H,W] float32 with H, W multiples of 32, got {tuple(x.shape)}")
         call("ctk_device_check")
         self.refresh()
         n = x.shape[0]
-        out = torch.empty(n, 1, device=x.device, dtype=torch.float32)
+        if out is None:
+            out = torch.empty(n, 1, device=x.device, dtype=torch.float32)
+        else:
+            _lib.require_device(out, torch.float32, "out")
+            if out.numel() != n:
+                raise _lib.CtkError("out must hold one float32 per tile")
         for s in range(0, n, MAX_SUB_BATCH):
             e = min(n, s + MAX_SUB_BATCH)
             self._forward_slice(x[s:e], out[s:e], taps)

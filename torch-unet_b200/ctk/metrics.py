@@ -9,7 +9,7 @@ from . import _lib
 from ._lib import call, ptr, stream
 
 
-def pearson_per_image(inputs: torch.Tensor) -> torch.Tensor:
+def pearson_per_image(inputs: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
     """Pearson r between channel 0 and channel 1 of every [2,H,W] float32 tile of ``inputs`` ([N,2,H,W], CUDA).
 
     Returns float64 [N]; NaN where either plane is constant (the ``np.std(...) == 0`` guard of
@@ -20,7 +20,12 @@ def pearson_per_image(inputs: torch.Tensor) -> torch.Tensor:
         raise _lib.CtkError(f"inputs must be [N,2,H,W], got {tuple(inputs.shape)}")
     n = inputs.shape[0]
     plane = inputs.shape[2] * inputs.shape[3]
-    out = torch.empty(n, device=inputs.device, dtype=torch.float64)
+    if out is None:
+        out = torch.empty(n, device=inputs.device, dtype=torch.float64)
+    else:
+        _lib.require_device(out, torch.float64, "out")
+        if out.numel() != n:
+            raise _lib.CtkError("out must hold one float64 per tile")
     if n == 0:
         return out
     lib = _lib.load()

@@ -35,16 +35,21 @@ def _head(in_features: int, p_drop: float, sigmoid: bool) -> nn.Sequential:
     return nn.Sequential(*layers)
 
 
+def get_engine(model) -> InferenceEngine:
+    """The (lazily created) libctk inference engine bound to ``model``."""
+    eng = model.__dict__.get("_ctk_engine")
+    if eng is None:
+        eng = InferenceEngine(model, conv_flags=model.__dict__.get("_ctk_conv_flags", 0))
+        model.__dict__["_ctk_engine"] = eng
+    return eng
+
+
 def _ctk_forward(self, x):
     """forward() shared by the mirrored classes and by accelerate()d reference instances."""
     if self.training:
         raise _lib.CtkError("the ctk training path (train-mode BN, backward) is not built yet; "
                             "call model.eval() and run under torch.no_grad()")
-    eng = self.__dict__.get("_ctk_engine")
-    if eng is None:
-        eng = InferenceEngine(self, conv_flags=self.__dict__.get("_ctk_conv_flags", 0))
-        self.__dict__["_ctk_engine"] = eng
-    return eng.forward(x)
+    return get_engine(self).forward(x)
 
 
 class AdvancedRegressionModel(nn.Module):
