@@ -91,6 +91,7 @@ int ctk_conv_first_eval(const float* x, int n, int c_total, int c_offset, int ci
  * ------------------------------------------------------------------------------------------ */
 #define CTK_CONV_NO_POOL 1       /* skip the 2x2 max-pool (out is [n,H,W,out_cstride])                 */
 #define CTK_CONV_NO_ACT 2        /* skip LeakyReLU                                                     */
+#define CTK_CONV_SINGLE_CTA 4    /* one CTA per tile (cta_group::1, N=128) instead of CTA pairs (cta_group::2) */
 int ctk_conv3x3_tc_eval(const void* x_bf16, int n, int H, int W, int cin,
                         const void* w_packed_bf16, int cout, const float* scale, const float* shift, float slope,
                         void* out_bf16, int out_cstride, int out_coffset, int flags, void* stream);

@@ -135,19 +135,23 @@ def _conv_tc_case(ctk, n, H, W, cin, cout, flags=0, coff=0, extra=0):
     (3, 16, 16, 128, 256),    # two K chunks, two N tiles
     (1, 8, 8, 512, 512),      # image smaller than the 16-row tile (single-branch block 6)
     (2, 48, 24, 64, 128),     # ragged: H not a multiple of the tile height
-    (5, 16, 8, 256, 512),     # odd batch
+    (5, 16, 8, 256, 512),     # odd batch, odd number of spatial tiles (padded CTA pair)
+    (3, 32, 32, 128, 128),    # cout = 128 with two K chunks
 ])
-def test_conv_tc_eval_shapes(ctk, n, H, W, cin, cout):
-    _conv_tc_case(ctk, n, H, W, cin, cout)
+@pytest.mark.parametrize("flags", [0, 4], ids=["cta_pair", "single_cta"])
+def test_conv_tc_eval_shapes(ctk, n, H, W, cin, cout, flags):
+    _conv_tc_case(ctk, n, H, W, cin, cout, flags=flags)
 
 
 def test_conv_tc_eval_channel_offset(ctk):
     _conv_tc_case(ctk, 2, 16, 16, 64, 128, coff=128, extra=256)
 
 
-def test_conv_tc_many_tiles_persistent(ctk):
+@pytest.mark.parametrize("flags", [0, 4], ids=["cta_pair", "single_cta"])
+@pytest.mark.parametrize("cin,cout", [(64, 128), (128, 256)])
+def test_conv_tc_many_tiles_persistent(ctk, cin, cout, flags):
     # more tiles than SMs so every CTA loops: exercises barrier phase wrap-around and TMEM double buffering
-    _conv_tc_case(ctk, 8, 64, 64, 64, 128)
+    _conv_tc_case(ctk, 8, 64, 64, cin, cout, flags=flags)
 
 
 # ------------------------------------------------------------------ split-K GEMM + head

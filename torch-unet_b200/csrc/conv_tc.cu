@@ -4,18 +4,22 @@
 // nn.MaxPool2d at /root/reference/regression_model.py:23-26 and two_branch_regression.py:16-19,22-25,28-31.
 //
 // GEMM view: D[pixel, cout] = sum_{tap, cin} X[pixel + tap, cin] * Wt[tap][cout][cin].
-//   M tile  = 128 output pixels = a 16-row x 8-column patch of one image (one pixel per TMEM lane)
-//   N tile  = 128 output channels (one fp32 TMEM column each)
+//   M tile  = 128 output pixels per CTA = a 16-row x 8-column patch of one image (one pixel per TMEM lane)
+//   N tile  = kBlockN output channels (one fp32 TMEM column each)
 //   K loop  = (cin / 64) chunks x 9 taps x 4 UMMA_K=16 steps
 // A operand: the (16+2) x (8+2) input halo of the patch is loaded ONCE per 64-channel chunk by a single TMA
 // box (out-of-bounds = zero fill gives the conv padding for free) into 128B-swizzled shared memory, one
 // 128-byte row per pixel.  The nine taps are nine *views* of that buffer: the UMMA descriptor for tap
-// (ky,kx) starts (ky*pitch + kx) rows into the halo and strides one halo row per 8-pixel core-matrix group.
-// This cuts L2->SM traffic for A by 9x against a per-tap im2col load.
-// B operand: per (chunk, tap) a [128 cout x 64 cin] K-major tile of the tap-major packed weights.
+// (ky,kx) starts (ky*10 + kx) rows into the halo and strides one halo row (1280 B) per 8-pixel core-matrix
+// group.  This cuts L2->SM traffic for A by 9x against a per-tap im2col load.
+// B operand: per (chunk, tap) a [kBlockN cout x 64 cin] K-major tile of the tap-major packed weights.
 //
-// Warp roles (256 threads): warp 0 = B producer, warp 3 = A producer (one elected lane each),
-// warp 1 = MMA issuer (one lane), warp 2 = TMEM allocator, warps 4-7 = epilogue (TMEM -> registers ->
+// kCtaGroup = 2 runs CTA pairs (cta_group::2): one tcgen05.mma drives both SMs with M = 256 (each CTA owns 128
+// pixels and their accumulators) and every CTA loads only HALF of the B tile, which halves the shared-memory
+// bytes each SM has to read per MMA -- with one CTA and N = 128 the operand reads alone are 128 B/clk/SM.
+//
+// Warp roles (256 threads): warp 0 = B producer, warp 3 = A producer (one lane each), warp 1 = MMA issuer
+// (one lane, pair leader only), warp 2 = TMEM allocator, warps 4-7 = epilogue (TMEM -> registers ->
 // scale/shift -> LeakyReLU -> 2x2 max via two butterfly shuffle stages -> 16-byte NHWC stores).
 // Accumulators are double buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include "ctk_common.h"
@@ -30,20 +34,26 @@ using namespace ctk;
 constexpr int kTileH = 16;
 constexpr int kTileW = 8;
 constexpr int kHaloH = kTileH + 2;
-constexpr int kBlockN = 128;
+constexpr int kHaloW = kTileW + 2;      // dense halo pitch: 10 pixels = 1280 B per row
 constexpr int kKC = 64;                 // channels per K chunk = one 128-byte swizzle row
 constexpr int kAStages = 2;
-constexpr int kBStages = 6;
 constexpr int kAccStages = 2;
 constexpr int kThreads = 256;
-constexpr int kBStageBytes = kBlockN * 128;                 // 16 KiB
-constexpr int kHaloW = kTileW + 2;                          // dense halo pitch: 10 pixels = 1280 B per row
-constexpr int kAStageBytesMax = ((kHaloH * kHaloW * 128 + 1023) / 1024) * 1024;   // 23 KiB
-constexpr int kSmemBytes = 1024 /*align slack*/ + kAStages * kAStageBytesMax + kBStages * kBStageBytes + 2048;
+constexpr uint32_t kABytes = kHaloH * kHaloW * 128;                       // 23040
+constexpr int kAStageBytes = ((kABytes + 1023) / 1024) * 1024;            // 23552
+
+template <int kCtaGroup, int kBlockN>
+struct Cfg {
+  static constexpr int kBRows = kBlockN / kCtaGroup;          // weight rows this CTA loads per (chunk, tap)
+  static constexpr int kBStageBytes = kBRows * 128;
+  static constexpr int kBStages = std::min(12, (200 * 1024 - kAStages * kAStageBytes) / kBStageBytes);
+  static constexpr int kTmemCols = kAccStages * kBlockN;
+  static constexpr int kSmemBytes = 1024 + kAStages * kAStageBytes + kBStages * kBStageBytes + 8192;
+};
 
 struct ConvParams {
   int n_img, H, W, cin, cout;
-  int tiles_x, tiles_y, tiles_n, total_tiles;
+  int tiles_x, tiles_y, tiles_n, spatial_tiles, total_work;
   int pool, act;
   float slope;
   const float* scale;
@@ -56,10 +66,12 @@ struct TileCoord {
   int img, y0, x0, n0;
 };
 
-__device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int tile) {
+// work item -> (pair of spatial tiles, N tile); N tile fastest so that CTAs running together share the halo in L2
+template <int kCtaGroup, int kBlockN>
+__device__ __forceinline__ TileCoord decode_work(const ConvParams& p, int work, int rank) {
   TileCoord t;
-  const int nt = tile % p.tiles_n;
-  int sp = tile / p.tiles_n;
+  const int nt = work % p.tiles_n;
+  int sp = (work / p.tiles_n) * kCtaGroup + rank;     // may be >= spatial_tiles for the padded last pair: img >= n_img
   const int tx = sp % p.tiles_x;
   sp /= p.tiles_x;
   const int ty = sp % p.tiles_y;
@@ -70,9 +82,11 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int tile) 
   return t;
 }
 
+template <int kCtaGroup, int kBlockN>
 struct SmemLayout {
+  using C = Cfg<kCtaGroup, kBlockN>;
   uint64_t a_full[kAStages], a_empty[kAStages];
-  uint64_t b_full[kBStages], b_empty[kBStages];
+  uint64_t b_full[C::kBStages], b_empty[C::kBStages];
   uint64_t acc_full[kAccStages], acc_empty[kAccStages];
   uint32_t tmem_base;
   uint32_t pad[3];
@@ -80,67 +94,87 @@ struct SmemLayout {
   alignas(16) float shift[2][kBlockN];
 };
 
+template <int kCtaGroup, int kBlockN>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                   const ConvParams p) {
+  using C = Cfg<kCtaGroup, kBlockN>;
+  using SL = SmemLayout<kCtaGroup, kBlockN>;
+  static_assert(sizeof(SL) <= 8192, "barrier block too large");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* a_smem = smem;
-  uint8_t* b_smem = smem + kAStages * kAStageBytesMax;
-  SmemLayout* sl = reinterpret_cast<SmemLayout*>(b_smem + kBStages * kBStageBytes);
+  uint8_t* b_smem = smem + kAStages * kAStageBytes;
+  SL* sl = reinterpret_cast<SL*>(b_smem + C::kBStages * C::kBStageBytes);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int chunks = p.cin / kKC;
-  constexpr uint32_t a_bytes = kHaloH * kHaloW * 128;
+  const int rank = kCtaGroup == 2 ? static_cast<int>(cluster_ctarank()) : 0;
+  const int work0 = blockIdx.x / kCtaGroup;
+  const int work_stride = gridDim.x / kCtaGroup;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kAStages; ++i) { mbar_init(&sl->a_full[i], 1); mbar_init(&sl->a_empty[i], 1); }
-    for (int i = 0; i < kBStages; ++i) { mbar_init(&sl->b_full[i], 1); mbar_init(&sl->b_empty[i], 1); }
-    for (int i = 0; i < kAccStages; ++i) { mbar_init(&sl->acc_full[i], 1); mbar_init(&sl->acc_empty[i], 128); }
+    for (int i = 0; i < C::kBStages; ++i) { mbar_init(&sl->b_full[i], 1); mbar_init(&sl->b_empty[i], 1); }
+    for (int i = 0; i < kAccStages; ++i) { mbar_init(&sl->acc_full[i], 1); mbar_init(&sl->acc_empty[i], 4 * kCtaGroup); }
     fence_mbar_init();
     tma_prefetch_desc(&tm_a);
     tma_prefetch_desc(&tm_b);
   }
-  if (warp == 2) tmem_alloc(&sl->tmem_base, kAccStages * kBlockN);
+  if (warp == 2) tmem_alloc<kCtaGroup>(&sl->tmem_base, C::kTmemCols);
   tc_fence_before();
   __syncthreads();
+  if constexpr (kCtaGroup == 2) cluster_sync_all();   // peer barriers / TMEM must exist before anything remote
   tc_fence_after();
   const uint32_t tmem_base = sl->tmem_base;
 
   if (warp == 3 && lane == 0) {
-    // ---------------- A producer: one halo box per (tile, chunk)
+    // ---------------- A producer: one halo box per (work item, chunk); pair members signal the leader's barrier
     int stage = 0, phase = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const TileCoord t = decode_tile(p, tile);
+    for (int work = work0; work < p.total_work; work += work_stride) {
+      const TileCoord t = decode_work<kCtaGroup, kBlockN>(p, work, rank);
       for (int c = 0; c < chunks; ++c) {
         mbar_wait(&sl->a_empty[stage], phase ^ 1);
-        mbar_arrive_expect_tx(&sl->a_full[stage], a_bytes);
-        tma_load_4d(a_smem + stage * kAStageBytesMax, &tm_a, &sl->a_full[stage], c * kKC, t.x0 - 1, t.y0 - 1, t.img);
+        uint8_t* dst = a_smem + stage * kAStageBytes;
+        if constexpr (kCtaGroup == 1) {
+          mbar_arrive_expect_tx(&sl->a_full[stage], kABytes);
+          tma_load_4d(dst, &tm_a, &sl->a_full[stage], c * kKC, t.x0 - 1, t.y0 - 1, t.img);
+        } else {
+          if (rank == 0) mbar_arrive_expect_tx(&sl->a_full[stage], 2 * kABytes);
+          tma_load_4d_pair(dst, &tm_a, mapa_shared(smem_u32(&sl->a_full[stage]), 0), c * kKC, t.x0 - 1, t.y0 - 1, t.img);
+        }
         if (++stage == kAStages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 0 && lane == 0) {
-    // ---------------- B producer: one weight tile per (tile, chunk, tap)
+    // ---------------- B producer: this CTA's share of the weight tile per (work item, chunk, tap)
     int stage = 0, phase = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const TileCoord t = decode_tile(p, tile);
+    for (int work = work0; work < p.total_work; work += work_stride) {
+      const TileCoord t = decode_work<kCtaGroup, kBlockN>(p, work, rank);
       for (int c = 0; c < chunks; ++c) {
         for (int tap = 0; tap < 9; ++tap) {
           mbar_wait(&sl->b_empty[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&sl->b_full[stage], kBStageBytes);
-          tma_load_2d(b_smem + stage * kBStageBytes, &tm_b, &sl->b_full[stage], c * kKC, tap * p.cout + t.n0);
-          if (++stage == kBStages) { stage = 0; phase ^= 1; }
+          uint8_t* dst = b_smem + stage * C::kBStageBytes;
+          const int row = tap * p.cout + t.n0 + rank * C::kBRows;
+          if constexpr (kCtaGroup == 1) {
+            mbar_arrive_expect_tx(&sl->b_full[stage], C::kBStageBytes);
+            tma_load_2d(dst, &tm_b, &sl->b_full[stage], c * kKC, row);
+          } else {
+            if (rank == 0) mbar_arrive_expect_tx(&sl->b_full[stage], 2 * C::kBStageBytes);
+            tma_load_2d_pair(dst, &tm_b, mapa_shared(smem_u32(&sl->b_full[stage]), 0), c * kKC, row);
+          }
+          if (++stage == C::kBStages) { stage = 0; phase ^= 1; }
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ---------------- MMA issuer
-    constexpr uint32_t idesc = umma_idesc_bf16_f32(128, kBlockN);
+  } else if (warp == 1 && lane == 0 && rank == 0) {
+    // ---------------- MMA issuer (pair leader only)
+    constexpr uint32_t idesc = umma_idesc_bf16_f32(128 * kCtaGroup, kBlockN);
     constexpr uint32_t sbo = kHaloW * 128;   // one halo row per 8-pixel core-matrix group
     int as = 0, aphase = 0, bs = 0, bphase = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+    for (int work = work0; work < p.total_work; work += work_stride, ++it) {
       const int acc = it & 1;
       const int acc_phase = (it >> 1) & 1;
       mbar_wait(&sl->acc_empty[acc], acc_phase ^ 1);
@@ -149,7 +183,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       for (int c = 0; c < chunks; ++c) {
         mbar_wait(&sl->a_full[as], aphase);
         tc_fence_after();
-        const uint32_t a_base = smem_u32(a_smem + as * kAStageBytesMax);
+        const uint32_t a_base = smem_u32(a_smem + as * kAStageBytes);
         for (int tap = 0; tap < 9; ++tap) {
           mbar_wait(&sl->b_full[bs], bphase);
           tc_fence_after();
@@ -158,41 +192,49 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
           // base-offset field 0, any 128-byte-aligned start, any multiple-of-128 group stride), so a shifted
           // window of the TMA-written halo is a valid K-major operand as is.
           const uint32_t a_tap = a_base + static_cast<uint32_t>((ky * kHaloW + kx) * 128);
-          const uint32_t b_base = smem_u32(b_smem + bs * kBStageBytes);
+          const uint32_t b_base = smem_u32(b_smem + bs * C::kBStageBytes);
 #pragma unroll
           for (int s = 0; s < kKC / 16; ++s) {
             const uint64_t adesc = umma_smem_desc_sw128(a_tap + s * 32, sbo, 0);
             const uint64_t bdesc = umma_smem_desc_sw128(b_base + s * 32, 1024, 0);
-            umma_bf16(d_tmem, adesc, bdesc, idesc, (c | tap | s) != 0 ? 1u : 0u);
+            const uint32_t accum = (c | tap | s) != 0 ? 1u : 0u;
+            if constexpr (kCtaGroup == 1) umma_bf16(d_tmem, adesc, bdesc, idesc, accum);
+            else umma_bf16_pair(d_tmem, adesc, bdesc, idesc, accum);
           }
-          umma_commit(&sl->b_empty[bs]);
-          if (++bs == kBStages) { bs = 0; bphase ^= 1; }
+          if constexpr (kCtaGroup == 1) umma_commit(&sl->b_empty[bs]);
+          else umma_commit_pair(&sl->b_empty[bs]);
+          if (++bs == C::kBStages) { bs = 0; bphase ^= 1; }
         }
-        umma_commit(&sl->a_empty[as]);
+        if constexpr (kCtaGroup == 1) umma_commit(&sl->a_empty[as]);
+        else umma_commit_pair(&sl->a_empty[as]);
         if (++as == kAStages) { as = 0; aphase ^= 1; }
       }
-      umma_commit(&sl->acc_full[acc]);
+      if constexpr (kCtaGroup == 1) umma_commit(&sl->acc_full[acc]);
+      else umma_commit_pair(&sl->acc_full[acc]);
     }
   } else if (warp >= 4) {
-    // ---------------- epilogue: 128 threads, thread <-> TMEM lane <-> output pixel of the tile
+    // ---------------- epilogue: 128 threads, thread <-> TMEM lane <-> output pixel of this CTA's tile
     const int ew = warp - 4;
     const int m = ew * 32 + lane;
     const int r = m >> 3, cpx = m & 7;
     const int et = threadIdx.x - 128;
     const int Hp = p.H >> 1, Wp = p.W >> 1;
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-      const TileCoord t = decode_tile(p, tile);
+    for (int work = work0; work < p.total_work; work += work_stride, ++it) {
+      const TileCoord t = decode_work<kCtaGroup, kBlockN>(p, work, rank);
       const int acc = it & 1;
       const int acc_phase = (it >> 1) & 1;
       float* s_scale = sl->scale[it & 1];
       float* s_shift = sl->shift[it & 1];
-      s_scale[et] = __ldg(p.scale + t.n0 + et);
-      s_shift[et] = __ldg(p.shift + t.n0 + et);
+      for (int i = et; i < kBlockN; i += 128) {
+        s_scale[i] = __ldg(p.scale + t.n0 + i);
+        s_shift[i] = __ldg(p.shift + t.n0 + i);
+      }
       asm volatile("bar.sync 1, 128;" ::: "memory");
       mbar_wait(&sl->acc_full[acc], acc_phase);
       tc_fence_after();
       const int y = t.y0 + r, x = t.x0 + cpx;
+      const bool valid = t.img < p.n_img && y < p.H && x < p.W;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(acc * kBlockN);
 #pragma unroll 1
       for (int cb = 0; cb < kBlockN / 32; ++cb) {
@@ -226,14 +268,14 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
             const uint32_t keep = odd_y ? q[4 + i] : q[i];
             ov[i] = max_bf16x2(keep, __shfl_xor_sync(0xffffffffu, send, 8));
           }
-          if (y < p.H && x < p.W) {
+          if (valid) {
             const int ch = t.n0 + cb * 32 + (odd_x ? 16 : 0) + (odd_y ? 8 : 0);
             __nv_bfloat16* dst = p.out +
                 (static_cast<size_t>(t.img) * Hp * Wp + static_cast<size_t>(y >> 1) * Wp + (x >> 1)) * p.out_cstride +
                 p.out_coffset + ch;
             *reinterpret_cast<uint4*>(dst) = o;
           }
-        } else if (y < p.H && x < p.W) {
+        } else if (valid) {
           __nv_bfloat16* dst = p.out +
               (static_cast<size_t>(t.img) * p.H * p.W + static_cast<size_t>(y) * p.W + x) * p.out_cstride +
               p.out_coffset + t.n0 + cb * 32;
@@ -242,17 +284,67 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
             reinterpret_cast<uint4*>(dst)[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
         }
       }
+      // this warp has drained its TMEM quadrant: one arrival per warp on the (leader's) accumulator-empty barrier
       tc_fence_before();
-      mbar_arrive(&sl->acc_empty[acc]);
+      __syncwarp();
+      if (lane == 0) {
+        if constexpr (kCtaGroup == 1) mbar_arrive(&sl->acc_empty[acc]);
+        else mbar_arrive_cluster(mapa_shared(smem_u32(&sl->acc_empty[acc]), 0));
+      }
     }
   }
   __syncwarp();
   tc_fence_before();
   __syncthreads();
+  if constexpr (kCtaGroup == 2) cluster_sync_all();   // nobody leaves while the pair still touches its smem / TMEM
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kAccStages * kBlockN);
+    tmem_dealloc<kCtaGroup>(tmem_base, C::kTmemCols);
   }
+}
+
+template <int kCtaGroup, int kBlockN>
+int launch_conv(const void* x_bf16, const void* w_packed_bf16, ConvParams p, cudaStream_t stream) {
+  using C = Cfg<kCtaGroup, kBlockN>;
+  p.tiles_n = p.cout / kBlockN;
+  const long long work = static_cast<long long>((p.spatial_tiles + kCtaGroup - 1) / kCtaGroup) * p.tiles_n;
+  if (work >= (1ll << 31)) return CTK_ERR_BAD_ARG;
+  p.total_work = static_cast<int>(work);
+
+  CUtensorMap tm_a, tm_b;
+  {
+    const uint64_t dims[4] = {static_cast<uint64_t>(p.cin), static_cast<uint64_t>(p.W), static_cast<uint64_t>(p.H),
+                              static_cast<uint64_t>(p.n_img)};
+    const uint64_t strides[3] = {static_cast<uint64_t>(p.cin) * 2, static_cast<uint64_t>(p.W) * p.cin * 2,
+                                 static_cast<uint64_t>(p.H) * p.W * p.cin * 2};
+    const uint32_t box[4] = {kKC, kHaloW, kHaloH, 1};
+    int st = ctk::encode_tmap_bf16_sw128(&tm_a, x_bf16, 4, dims, strides, box);
+    if (st != CTK_OK) return st;
+  }
+  {
+    const uint64_t dims[2] = {static_cast<uint64_t>(p.cin), static_cast<uint64_t>(9) * p.cout};
+    const uint64_t strides[1] = {static_cast<uint64_t>(p.cin) * 2};
+    const uint32_t box[2] = {kKC, static_cast<uint32_t>(C::kBRows)};
+    int st = ctk::encode_tmap_bf16_sw128(&tm_b, w_packed_bf16, 2, dims, strides, box);
+    if (st != CTK_OK) return st;
+  }
+  auto kernel = conv3x3_tc_kernel<kCtaGroup, kBlockN>;
+  CTK_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+  const int clusters = std::min(p.total_work, ctk::num_sms() / kCtaGroup);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(clusters * kCtaGroup);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = C::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCtaGroup;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CTK_CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, tm_a, tm_b, p));
+  return ctk::check_launch();
 }
 
 }  // namespace
@@ -263,45 +355,26 @@ extern "C" int ctk_conv3x3_tc_eval(const void* x_bf16, int n, int H, int W, int 
   if (n == 0) return CTK_OK;
   CTK_REQUIRE(x_bf16 && w_packed_bf16 && scale && shift && out_bf16);
   CTK_REQUIRE(n > 0 && H > 0 && W > 0 && H % 2 == 0 && W % kTileW == 0 && cin > 0 && cin % kKC == 0 && cout > 0 &&
-              cout % kBlockN == 0);
+              cout % 128 == 0);
   CTK_REQUIRE(out_coffset >= 0 && out_coffset + cout <= out_cstride && out_cstride % 8 == 0 && out_coffset % 8 == 0);
   CTK_REQUIRE((reinterpret_cast<uintptr_t>(x_bf16) & 15) == 0 && (reinterpret_cast<uintptr_t>(w_packed_bf16) & 15) == 0 &&
               (reinterpret_cast<uintptr_t>(out_bf16) & 15) == 0);
 
-  ConvParams p;
+  ConvParams p = {};
   p.n_img = n; p.H = H; p.W = W; p.cin = cin; p.cout = cout;
   p.tiles_x = W / kTileW;
   p.tiles_y = (H + kTileH - 1) / kTileH;
-  p.tiles_n = cout / kBlockN;
-  const long long total = static_cast<long long>(n) * p.tiles_x * p.tiles_y * p.tiles_n;
-  CTK_REQUIRE(total < (1ll << 31));
-  p.total_tiles = static_cast<int>(total);
+  const long long spatial = static_cast<long long>(n) * p.tiles_x * p.tiles_y;
+  CTK_REQUIRE(spatial < (1ll << 30));
+  p.spatial_tiles = static_cast<int>(spatial);
   p.pool = (flags & CTK_CONV_NO_POOL) ? 0 : 1;
   p.act = (flags & CTK_CONV_NO_ACT) ? 0 : 1;
   p.slope = slope;
   p.scale = scale; p.shift = shift;
   p.out = static_cast<__nv_bfloat16*>(out_bf16);
   p.out_cstride = out_cstride; p.out_coffset = out_coffset;
-
-  CUtensorMap tm_a, tm_b;
-  {
-    const uint64_t dims[4] = {static_cast<uint64_t>(cin), static_cast<uint64_t>(W), static_cast<uint64_t>(H),
-                              static_cast<uint64_t>(n)};
-    const uint64_t strides[3] = {static_cast<uint64_t>(cin) * 2, static_cast<uint64_t>(W) * cin * 2,
-                                 static_cast<uint64_t>(H) * W * cin * 2};
-    const uint32_t box[4] = {kKC, kHaloW, kHaloH, 1};
-    int st = ctk::encode_tmap_bf16_sw128(&tm_a, x_bf16, 4, dims, strides, box);
-    if (st != CTK_OK) return st;
-  }
-  {
-    const uint64_t dims[2] = {static_cast<uint64_t>(cin), static_cast<uint64_t>(9) * cout};
-    const uint64_t strides[1] = {static_cast<uint64_t>(cin) * 2};
-    const uint32_t box[2] = {kKC, kBlockN};
-    int st = ctk::encode_tmap_bf16_sw128(&tm_b, w_packed_bf16, 2, dims, strides, box);
-    if (st != CTK_OK) return st;
-  }
-  CTK_CUDA_TRY(cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-  const int grid = std::min(p.total_tiles, ctk::num_sms());
-  conv3x3_tc_kernel<<<grid, kThreads, kSmemBytes, ctk::as_stream(stream)>>>(tm_a, tm_b, p);
-  return ctk::check_launch();
+  cudaStream_t s = ctk::as_stream(stream);
+  if (flags & CTK_CONV_SINGLE_CTA) return launch_conv<1, 128>(x_bf16, w_packed_bf16, p, s);
+  if (cout % 256 == 0) return launch_conv<2, 256>(x_bf16, w_packed_bf16, p, s);
+  return launch_conv<2, 128>(x_bf16, w_packed_bf16, p, s);
 }

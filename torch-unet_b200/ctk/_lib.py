@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libctk.so")
 
 CONV_NO_POOL = 1
 CONV_NO_ACT = 2
+CONV_SINGLE_CTA = 4
 ADAM_CHUNK = 65536
 
 
