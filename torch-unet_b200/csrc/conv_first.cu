@@ -1,106 +1,296 @@
 // First conv block, eval mode: Conv2d(cin in {1,2}, cout, 3, 1, 1) + folded BN + LeakyReLU + MaxPool2d(2,2),
 // fp32 NCHW planes in, NHWC bf16 out.  Replaces /root/reference/regression_model.py:14-17 (cin=2, cout=128)
-// and two_branch_regression.py:10-13 (cin=1, cout=64).  K = 9*cin is far too small for a GEMM tile, so
-// this is a direct convolution on the fp32 pipe: each thread keeps the taps of CPT output channels in
-// registers and walks pooled pixels; a pooled pixel's channels are written by consecutive threads so every
-// store instruction of a warp covers whole 128-byte lines of the NHWC output.
+// and two_branch_regression.py:10-13 (cin=1, cout=64).
+//
+// K = 9*cin is tiny, so a direct convolution is bound by the fp32 pipe (576 FMA per pixel for 64 channels).
+// Instead the block runs on the tensor cores as a GEMM whose A operand is built in shared memory by the
+// threads themselves, with split-bf16 operands so the result is fp32-class despite bf16 multiplicands:
+//   x = x_hi + x_lo,  w*bn_scale = w_hi + w_lo   (each half a bf16)
+//   acc = sum_taps  x_hi*w_hi + x_lo*w_hi + x_hi*w_lo                      (dropped term x_lo*w_lo ~ 2^-18)
+// Per input channel that is 14 32-bit K-words: 9 words (x_hi, x_lo)[tap] against (w_hi, w_hi)[tap], then
+// 5 words (x_hi[2u], x_hi[2u+1]) against (w_lo[2u], w_lo[2u+1]).  K is padded to 32 (cin=1) or 64 (cin=2).
+//
+// One CTA = kGroups independent groups of 4 warps.  A group repeatedly takes a 16-row x (8*SUB)-column region of one
+// image plane: stages the (hi|lo)-packed input halo in shared memory, every thread writes the A rows of its pixel
+// (no-swizzle K-major core-matrix layout), one thread issues SUB x K/16 tcgen05.mma (M=128 pixels, N=cout) into the
+// group's TMEM columns, and after the commit the same 128 threads run the epilogue: +shift, LeakyReLU, 2x2 max
+// by butterfly shuffles, 16-byte NHWC stores.  The MMAs are ~100 cycles per region; the kernel is bound by the
+// epilogue instruction stream and the 1 GB of bf16 output it writes, so the groups exist to overlap each other's
+// load / TMEM / store latencies.
 #include "ctk_common.h"
 #include "ctk_ptx.cuh"
 
+#include <algorithm>
+
 namespace {
 
-constexpr int kTileW = 32;   // pooled pixels per block along W
-constexpr int kTileH = 8;    // pooled pixels per block along H
-constexpr int kThreads = 256;
-constexpr int kInW = 2 * kTileW + 2;   // 66
-constexpr int kInH = 2 * kTileH + 2;   // 18
-constexpr int kInPitch = 68;
+using namespace ctk;
 
-template <int CIN, int COUT, int CPT>
-__global__ void __launch_bounds__(kThreads)
-conv_first_eval_kernel(const float* __restrict__ x, int c_total, int c_offset, int H, int W,
-                       const float* __restrict__ w_folded, const float* __restrict__ shift, float slope,
-                       __nv_bfloat16* __restrict__ out, int out_cstride, int out_coffset) {
-  constexpr int G = COUT / CPT;             // threads per pooled pixel
-  constexpr int SLOTS = kThreads / G;       // pooled pixels processed concurrently
-  static_assert(kThreads % G == 0 && (kTileW * kTileH) % SLOTS == 0, "tile/thread mismatch");
-  __shared__ float s_in[CIN][kInH][kInPitch];
+constexpr int kTileH = 16;
+constexpr int kTileW = 8;
+constexpr int kGroups = 4;
+constexpr int kThreads = kGroups * 128;
+constexpr int kTmemCols = 512;
 
-  const int n = blockIdx.z;
-  const int py0 = blockIdx.y * kTileH, px0 = blockIdx.x * kTileW;
-  const int Hp = H / 2, Wp = W / 2;
+template <int CIN, int COUT>
+struct FirstCfg {
+  static constexpr int kK = CIN == 1 ? 32 : 64;                 // padded K (bf16 elements)
+  static constexpr int kKWords = kK / 2;
+  static constexpr int kSub = kTmemCols / (kGroups * COUT);     // 16x8 sub-tiles per group iteration
+  static constexpr int kRegionW = kTileW * kSub;
+  static constexpr int kInW = kRegionW + 2;
+  static constexpr int kInPitch = kInW + 1;
+  static constexpr int kInH = kTileH + 2;
+  static constexpr int kLbo = 128;                              // bytes between core matrices along K
+  static constexpr int kSbo = (kK / 8) * 128;                   // bytes between 8-row groups along M / N
+  static constexpr int kATileBytes = 16 * kSbo;                 // 128 rows
+  static constexpr int kBBytes = (COUT / 8) * kSbo;
+  static constexpr int kGroupBytes = (kSub * kATileBytes + CIN * kInH * kInPitch * 4 + 127) / 128 * 128;
+  static constexpr int kSmemBytes = 1024 + kBBytes + kGroups * kGroupBytes + 256;
+  static_assert(kSub >= 1, "too many output channels for the TMEM split");
+};
 
-  // stage the (2*tile+2)^2 input window, zero padded
-  for (int c = 0; c < CIN; ++c) {
-    const float* plane = x + (static_cast<size_t>(n) * c_total + c_offset + c) * H * W;
-    for (int i = threadIdx.x; i < kInH * kInW; i += kThreads) {
-      const int r = i / kInW, q = i % kInW;
-      const int gy = 2 * py0 - 1 + r, gx = 2 * px0 - 1 + q;
-      float v = 0.f;
-      if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = __ldg(plane + static_cast<size_t>(gy) * W + gx);
-      s_in[c][r][q] = v;
+__device__ __forceinline__ uint32_t split_hi_lo(float x) {
+  const __nv_bfloat16 hi = __float2bfloat16_rn(x);
+  const __nv_bfloat16 lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+  return static_cast<uint32_t>(__bfloat16_as_ushort(hi)) | (static_cast<uint32_t>(__bfloat16_as_ushort(lo)) << 16);
+}
+
+// no-swizzle K-major operand descriptor (layout type 0): LBO = K-direction core-matrix stride, SBO = 8-row group stride
+__device__ __forceinline__ uint64_t umma_smem_desc_nosw(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3fff);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3fff) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3fff) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  return d;
+}
+
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_first_tc_kernel(const float* __restrict__ x, int n_img, int c_total, int c_offset, int H, int W,
+                     const float* __restrict__ w_folded, const float* __restrict__ shift, float slope,
+                     __nv_bfloat16* __restrict__ out, int out_cstride, int out_coffset, int regions_x, int regions_y,
+                     int total_regions) {
+  using C = FirstCfg<CIN, COUT>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* b_smem = smem;
+  uint8_t* groups_smem = smem + C::kBBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(groups_smem + kGroups * C::kGroupBytes);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kGroups);
+  __shared__ float s_shift[COUT];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int group = warp >> 2;
+  const int gt = threadIdx.x & 127;          // thread within group = TMEM lane = pixel of the 16x8 sub-tile
+  const int ew = warp & 3;
+
+  // ---- one-time setup: barriers, TMEM, the B operand (folded weights split into hi/lo bf16)
+  if (threadIdx.x == 0) {
+    for (int g = 0; g < kGroups; ++g) mbar_init(&bars[g], 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc<1>(tmem_slot, kTmemCols);
+  for (int i = threadIdx.x; i < COUT; i += kThreads) s_shift[i] = __ldg(shift + i);
+  for (int i = threadIdx.x; i < COUT * C::kKWords; i += kThreads) {
+    const int n = i / C::kKWords, kw = i % C::kKWords;
+    uint32_t word = 0;
+    const int ch = kw / 14, j = kw % 14;
+    if (ch < CIN) {
+      const float* wr = w_folded + (n * CIN + ch) * 9;
+      if (j < 9) {
+        const uint32_t hl = split_hi_lo(__ldg(wr + j));
+        word = (hl & 0xffffu) | (hl << 16);                               // (w_hi, w_hi)
+      } else {
+        const int t0 = 2 * (j - 9);
+        const uint32_t a = split_hi_lo(__ldg(wr + t0)) >> 16;             // w_lo[t0]
+        const uint32_t b = t0 + 1 < 9 ? (split_hi_lo(__ldg(wr + t0 + 1)) >> 16) : 0u;
+        word = a | (b << 16);
+      }
     }
+    const int k = 2 * kw;                                                 // first bf16 element of this word
+    const uint32_t off = (n >> 3) * C::kSbo + (k >> 3) * C::kLbo + (n & 7) * 16 + (k & 7) * 2;
+    *reinterpret_cast<uint32_t*>(b_smem + off) = word;
   }
-
-  const int cg = threadIdx.x % G;
-  const int slot = threadIdx.x / G;
-  float wr[CPT][CIN * 9];
-  float sh[CPT];
-#pragma unroll
-  for (int j = 0; j < CPT; ++j) {
-    sh[j] = __ldg(shift + cg * CPT + j);
-#pragma unroll
-    for (int k = 0; k < CIN * 9; ++k) wr[j][k] = __ldg(w_folded + (cg * CPT + j) * (CIN * 9) + k);
-  }
+  fence_proxy_async_smem();
+  tc_fence_before();
   __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
 
-  for (int p = slot; p < kTileW * kTileH; p += SLOTS) {
-    const int py = p / kTileW, px = p % kTileW;
-    const int gy = py0 + py, gx = px0 + px;
-    float patch[CIN][4][4];
+  uint8_t* a_smem = groups_smem + group * C::kGroupBytes;
+  uint32_t* in_smem = reinterpret_cast<uint32_t*>(a_smem + C::kSub * C::kATileBytes);
+  const uint32_t tmem_group = tmem_base + static_cast<uint32_t>(group * C::kSub * COUT);
+  const int r = gt >> 3, cpx = gt & 7;
+  const int Hp = H >> 1, Wp = W >> 1;
+  constexpr uint32_t idesc = umma_idesc_bf16_f32(128, COUT);
+  uint32_t parity = 0;
+
+  // input prefetch: the halo of the NEXT region is loaded into registers while this one is being processed
+  constexpr int kPref = (C::kInH * C::kInW + 127) / 128;
+  float pref[CIN][kPref];
+  auto load_region = [&](int region) {
+    const int rx = region % regions_x;
+    const int ry = (region / regions_x) % regions_y;
+    const int img = region / (regions_x * regions_y);
+    const int y0 = ry * kTileH, x0 = rx * C::kRegionW;
+#pragma unroll
+    for (int c = 0; c < CIN; ++c) {
+      const float* plane = x + (static_cast<size_t>(img) * c_total + c_offset + c) * H * W;
+#pragma unroll
+      for (int j = 0; j < kPref; ++j) {
+        const int i = gt + 128 * j;
+        const int rr = i / C::kInW, q = i - rr * C::kInW;
+        const int gy = y0 - 1 + rr, gx = x0 - 1 + q;
+        float v = 0.f;
+        if (i < C::kInH * C::kInW && gy >= 0 && gy < H && gx >= 0 && gx < W)
+          v = __ldg(plane + static_cast<size_t>(gy) * W + gx);
+        pref[c][j] = v;
+      }
+    }
+  };
+  const int region_first = blockIdx.x * kGroups + group;
+  const int region_step = gridDim.x * kGroups;
+  if (region_first < total_regions) load_region(region_first);
+
+  for (int region = region_first; region < total_regions; region += region_step) {
+    const int rx = region % regions_x;
+    const int ry = (region / regions_x) % regions_y;
+    const int img = region / (regions_x * regions_y);
+    const int y0 = ry * kTileH, x0 = rx * C::kRegionW;
+
+    // ---- stage the prefetched input halo as packed (hi | lo << 16) words (zero padded), then prefetch the next one
 #pragma unroll
     for (int c = 0; c < CIN; ++c)
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const float2 a = *reinterpret_cast<const float2*>(&s_in[c][2 * py + r][2 * px]);
-        const float2 b = *reinterpret_cast<const float2*>(&s_in[c][2 * py + r][2 * px + 2]);
-        patch[c][r][0] = a.x; patch[c][r][1] = a.y; patch[c][r][2] = b.x; patch[c][r][3] = b.y;
+      for (int j = 0; j < kPref; ++j) {
+        const int i = gt + 128 * j;
+        const int rr = i / C::kInW, q = i - rr * C::kInW;
+        if (i < C::kInH * C::kInW) in_smem[(c * C::kInH + rr) * C::kInPitch + q] = split_hi_lo(pref[c][j]);
       }
-    float res[CPT];
+    asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory");
+    if (region + region_step < total_regions) load_region(region + region_step);
+
+    // ---- every thread writes the K-words of its pixel for each sub-tile
 #pragma unroll
-    for (int j = 0; j < CPT; ++j) {
-      float acc[4] = {sh[j], sh[j], sh[j], sh[j]};
+    for (int s = 0; s < C::kSub; ++s) {
+      uint32_t kw[C::kKWords];
 #pragma unroll
-      for (int c = 0; c < CIN; ++c)
+      for (int i = 0; i < C::kKWords; ++i) kw[i] = 0;
+#pragma unroll
+      for (int c = 0; c < CIN; ++c) {
+        uint32_t t[9];
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-          for (int kx = 0; kx < 3; ++kx) {
-            const float wv = wr[j][c * 9 + ky * 3 + kx];
-            acc[0] = fmaf(wv, patch[c][ky][kx], acc[0]);
-            acc[1] = fmaf(wv, patch[c][ky][kx + 1], acc[1]);
-            acc[2] = fmaf(wv, patch[c][ky + 1][kx], acc[2]);
-            acc[3] = fmaf(wv, patch[c][ky + 1][kx + 1], acc[3]);
-          }
-      const float m01 = fmaxf(ctk::leaky(acc[0], slope), ctk::leaky(acc[1], slope));
-      const float m23 = fmaxf(ctk::leaky(acc[2], slope), ctk::leaky(acc[3], slope));
-      res[j] = fmaxf(m01, m23);
+          for (int kx = 0; kx < 3; ++kx)
+            t[ky * 3 + kx] = in_smem[(c * C::kInH + r + ky) * C::kInPitch + s * kTileW + cpx + kx];
+#pragma unroll
+        for (int j = 0; j < 9; ++j) kw[c * 14 + j] = t[j];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) kw[c * 14 + 9 + u] = __byte_perm(t[2 * u], t[2 * u + 1], 0x5410);   // (hi, hi)
+        kw[c * 14 + 13] = t[8] & 0xffffu;
+      }
+      uint8_t* tile = a_smem + s * C::kATileBytes + (gt >> 3) * C::kSbo + (gt & 7) * 16;
+#pragma unroll
+      for (int j = 0; j < C::kK / 8; ++j)
+        *reinterpret_cast<uint4*>(tile + j * C::kLbo) = make_uint4(kw[4 * j], kw[4 * j + 1], kw[4 * j + 2], kw[4 * j + 3]);
     }
-    if (gy < Hp && gx < Wp) {
-      __nv_bfloat16* dst =
-          out + (static_cast<size_t>(n) * Hp * Wp + static_cast<size_t>(gy) * Wp + gx) * out_cstride + out_coffset + cg * CPT;
-      if constexpr (CPT == 8) {
-        uint4 v;
-        v.x = ctk::pack_bf16x2(res[0], res[1]); v.y = ctk::pack_bf16x2(res[2], res[3]);
-        v.z = ctk::pack_bf16x2(res[4], res[5]); v.w = ctk::pack_bf16x2(res[6], res[7]);
-        *reinterpret_cast<uint4*>(dst) = v;
-      } else {
-        uint2 v;
-        v.x = ctk::pack_bf16x2(res[0], res[1]); v.y = ctk::pack_bf16x2(res[2], res[3]);
-        *reinterpret_cast<uint2*>(dst) = v;
+    fence_proxy_async_smem();          // generic-proxy writes -> visible to the tensor core's async-proxy reads
+    tc_fence_before();
+    asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory");
+
+    // ---- one thread issues the MMAs of this region and commits to the group's barrier
+    if (gt == 0) {
+      tc_fence_after();
+      const uint32_t b_base = smem_u32(b_smem);
+#pragma unroll
+      for (int s = 0; s < C::kSub; ++s) {
+        const uint32_t a_base = smem_u32(a_smem + s * C::kATileBytes);
+#pragma unroll
+        for (int ks = 0; ks < C::kK / 16; ++ks) {
+          umma_bf16(tmem_group + s * COUT, umma_smem_desc_nosw(a_base + ks * 2 * C::kLbo, C::kLbo, C::kSbo),
+                    umma_smem_desc_nosw(b_base + ks * 2 * C::kLbo, C::kLbo, C::kSbo), idesc, ks != 0 ? 1u : 0u);
+        }
+      }
+      umma_commit(&bars[group]);
+    }
+    mbar_wait(&bars[group], parity);
+    parity ^= 1;
+    tc_fence_after();
+
+    // ---- epilogue per sub-tile: + shift, LeakyReLU, 2x2 max-pool, NHWC bf16 store
+    const int y = y0 + r;
+#pragma unroll 1
+    for (int s = 0; s < C::kSub; ++s) {
+      const int xg = x0 + s * kTileW + cpx;
+      const bool valid = y < H && xg < W;
+#pragma unroll 1
+      for (int cb = 0; cb < COUT / 32; ++cb) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_group + (static_cast<uint32_t>(ew * 32) << 16) + s * COUT + cb * 32, v);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float f0 = leaky(__uint_as_float(v[2 * i]) + s_shift[cb * 32 + 2 * i], slope);
+          const float f1 = leaky(__uint_as_float(v[2 * i + 1]) + s_shift[cb * 32 + 2 * i + 1], slope);
+          pk[i] = pack_bf16x2(f0, f1);
+        }
+        const bool odd_x = (lane & 1) != 0;
+        uint32_t q[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint32_t send = odd_x ? pk[i] : pk[8 + i];
+          const uint32_t keep = odd_x ? pk[8 + i] : pk[i];
+          q[i] = max_bf16x2(keep, __shfl_xor_sync(0xffffffffu, send, 1));
+        }
+        const bool odd_y = (lane & 8) != 0;
+        uint4 o;
+        uint32_t* ov = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t send = odd_y ? q[i] : q[4 + i];
+          const uint32_t keep = odd_y ? q[4 + i] : q[i];
+          ov[i] = max_bf16x2(keep, __shfl_xor_sync(0xffffffffu, send, 8));
+        }
+        if (valid) {
+          const int ch = cb * 32 + (odd_x ? 16 : 0) + (odd_y ? 8 : 0);
+          __nv_bfloat16* dst = out +
+              (static_cast<size_t>(img) * Hp * Wp + static_cast<size_t>(y >> 1) * Wp + (xg >> 1)) * out_cstride +
+              out_coffset + ch;
+          *reinterpret_cast<uint4*>(dst) = o;
+        }
       }
     }
+    tc_fence_before();   // TMEM reads of this iteration are ordered before the barrier the next MMA issue follows
   }
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<1>(tmem_base, kTmemCols);
+  }
+}
+
+template <int CIN, int COUT>
+int launch_first(const float* x, int n, int c_total, int c_offset, int H, int W, const float* w_folded,
+                 const float* shift, float slope, __nv_bfloat16* out, int out_cstride, int out_coffset,
+                 cudaStream_t stream) {
+  using C = FirstCfg<CIN, COUT>;
+  const int regions_x = (W + C::kRegionW - 1) / C::kRegionW;
+  const int regions_y = (H + kTileH - 1) / kTileH;
+  const long long total = static_cast<long long>(n) * regions_x * regions_y;
+  if (total >= (1ll << 31)) return CTK_ERR_BAD_ARG;
+  auto kernel = conv_first_tc_kernel<CIN, COUT>;
+  CTK_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+  const int grid = static_cast<int>(std::min<long long>((total + kGroups - 1) / kGroups, ctk::num_sms()));
+  kernel<<<grid, kThreads, C::kSmemBytes, stream>>>(x, n, c_total, c_offset, H, W, w_folded, shift, slope, out,
+                                                    out_cstride, out_coffset, regions_x, regions_y,
+                                                    static_cast<int>(total));
+  return ctk::check_launch();
 }
 
 }  // namespace
@@ -112,18 +302,11 @@ extern "C" int ctk_conv_first_eval(const float* x, int n, int c_total, int c_off
   CTK_REQUIRE(x && w_folded && shift && out_bf16 && n > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0);
   CTK_REQUIRE(c_offset >= 0 && c_offset + cin <= c_total && out_coffset >= 0 && out_coffset + cout <= out_cstride);
   CTK_REQUIRE(out_cstride % 8 == 0 && out_coffset % 8 == 0 && (reinterpret_cast<uintptr_t>(out_bf16) & 15) == 0);
-  CTK_REQUIRE(n <= 65535);
-  dim3 grid((W / 2 + kTileW - 1) / kTileW, (H / 2 + kTileH - 1) / kTileH, n);
   cudaStream_t s = ctk::as_stream(stream);
   __nv_bfloat16* out = static_cast<__nv_bfloat16*>(out_bf16);
-  if (cin == 1 && cout == 64) {
-    conv_first_eval_kernel<1, 64, 8><<<grid, kThreads, 0, s>>>(x, c_total, c_offset, H, W, w_folded, shift, slope, out,
-                                                               out_cstride, out_coffset);
-  } else if (cin == 2 && cout == 128) {
-    conv_first_eval_kernel<2, 128, 4><<<grid, kThreads, 0, s>>>(x, c_total, c_offset, H, W, w_folded, shift, slope,
-                                                                out, out_cstride, out_coffset);
-  } else {
-    return CTK_ERR_UNSUPPORTED;
-  }
-  return ctk::check_launch();
+  if (cin == 1 && cout == 64)
+    return launch_first<1, 64>(x, n, c_total, c_offset, H, W, w_folded, shift, slope, out, out_cstride, out_coffset, s);
+  if (cin == 2 && cout == 128)
+    return launch_first<2, 128>(x, n, c_total, c_offset, H, W, w_folded, shift, slope, out, out_cstride, out_coffset, s);
+  return CTK_ERR_UNSUPPORTED;
 }
