@@ -127,27 +127,30 @@ conv_first_tc_kernel(const float* __restrict__ x, int n_img, int c_total, int c_
   constexpr uint32_t idesc = umma_idesc_bf16_f32(128, COUT);
   uint32_t parity = 0;
 
-  // input prefetch: the halo of the NEXT region is loaded into registers while this one is being processed
+  // input prefetch: the halo of the NEXT region is loaded into registers while this one is being processed.
+  // Element i = gt + 128*j of the halo is the same (row, column) every iteration, so the index math is hoisted.
   constexpr int kPref = (C::kInH * C::kInW + 127) / 128;
+  int pre_rr[kPref], pre_q[kPref];
+#pragma unroll
+  for (int j = 0; j < kPref; ++j) {
+    const int i = gt + 128 * j;
+    pre_rr[j] = i < C::kInH * C::kInW ? i / C::kInW : -1000000;     // out-of-range slots never pass the bounds test
+    pre_q[j] = i - (i / C::kInW) * C::kInW;
+  }
   float pref[CIN][kPref];
   auto load_region = [&](int region) {
     const int rx = region % regions_x;
     const int ry = (region / regions_x) % regions_y;
     const int img = region / (regions_x * regions_y);
-    const int y0 = ry * kTileH, x0 = rx * C::kRegionW;
+    const int y0 = ry * kTileH - 1, x0 = rx * C::kRegionW - 1;
+    const float* plane0 = x + (static_cast<size_t>(img) * c_total + c_offset) * H * W;
 #pragma unroll
-    for (int c = 0; c < CIN; ++c) {
-      const float* plane = x + (static_cast<size_t>(img) * c_total + c_offset + c) * H * W;
+    for (int j = 0; j < kPref; ++j) {
+      const int gy = y0 + pre_rr[j], gx = x0 + pre_q[j];
+      const bool ok = gy >= 0 && gy < H && gx >= 0 && gx < W;
+      const size_t off = static_cast<size_t>(gy) * W + gx;
 #pragma unroll
-      for (int j = 0; j < kPref; ++j) {
-        const int i = gt + 128 * j;
-        const int rr = i / C::kInW, q = i - rr * C::kInW;
-        const int gy = y0 - 1 + rr, gx = x0 - 1 + q;
-        float v = 0.f;
-        if (i < C::kInH * C::kInW && gy >= 0 && gy < H && gx >= 0 && gx < W)
-          v = __ldg(plane + static_cast<size_t>(gy) * W + gx);
-        pref[c][j] = v;
-      }
+      for (int c = 0; c < CIN; ++c) pref[c][j] = ok ? __ldg(plane0 + static_cast<size_t>(c) * H * W + off) : 0.f;
     }
   };
   const int region_first = blockIdx.x * kGroups + group;
@@ -164,11 +167,8 @@ conv_first_tc_kernel(const float* __restrict__ x, int n_img, int c_total, int c_
 #pragma unroll
     for (int c = 0; c < CIN; ++c)
 #pragma unroll
-      for (int j = 0; j < kPref; ++j) {
-        const int i = gt + 128 * j;
-        const int rr = i / C::kInW, q = i - rr * C::kInW;
-        if (i < C::kInH * C::kInW) in_smem[(c * C::kInH + rr) * C::kInPitch + q] = split_hi_lo(pref[c][j]);
-      }
+      for (int j = 0; j < kPref; ++j)
+        if (pre_rr[j] >= 0) in_smem[(c * C::kInH + pre_rr[j]) * C::kInPitch + pre_q[j]] = split_hi_lo(pref[c][j]);
     asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory");
     if (region + region_step < total_regions) load_region(region + region_step);
 

@@ -18,8 +18,8 @@
 // pixels and their accumulators) and every CTA loads only HALF of the B tile, which halves the shared-memory
 // bytes each SM has to read per MMA -- with one CTA and N = 128 the operand reads alone are 128 B/clk/SM.
 //
-// Warp roles (256 threads): warp 0 = B producer, warp 3 = A producer (one lane each), warp 1 = MMA issuer
-// (one lane, pair leader only), warp 2 = TMEM allocator, warps 4-7 = epilogue (TMEM -> registers ->
+// Warp roles (384 threads): warp 0 = B producer, warp 3 = A producer (one lane each), warp 1 = MMA issuer
+// (one lane, pair leader only), warp 2 = TMEM allocator, warps 4-11 = epilogue (TMEM -> registers ->
 // scale/shift -> LeakyReLU -> 2x2 max via two butterfly shuffle stages -> 16-byte NHWC stores).
 // Accumulators are double buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include "ctk_common.h"
@@ -36,9 +36,10 @@ constexpr int kTileW = 8;
 constexpr int kHaloH = kTileH + 2;
 constexpr int kHaloW = kTileW + 2;      // dense halo pitch: 10 pixels = 1280 B per row
 constexpr int kKC = 64;                 // channels per K chunk = one 128-byte swizzle row
-constexpr int kAStages = 2;
+constexpr int kAStages = 4;
 constexpr int kAccStages = 2;
-constexpr int kThreads = 256;
+constexpr int kEpiWarps = 8;               // two warps per TMEM lane quadrant, interleaved over 32-column blocks
+constexpr int kThreads = 128 + 32 * kEpiWarps;
 constexpr uint32_t kABytes = kHaloH * kHaloW * 128;                       // 23040
 constexpr int kAStageBytes = ((kABytes + 1023) / 1024) * 1024;            // 23552
 
@@ -117,7 +118,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
   if (threadIdx.x == 0) {
     for (int i = 0; i < kAStages; ++i) { mbar_init(&sl->a_full[i], 1); mbar_init(&sl->a_empty[i], 1); }
     for (int i = 0; i < C::kBStages; ++i) { mbar_init(&sl->b_full[i], 1); mbar_init(&sl->b_empty[i], 1); }
-    for (int i = 0; i < kAccStages; ++i) { mbar_init(&sl->acc_full[i], 1); mbar_init(&sl->acc_empty[i], 4 * kCtaGroup); }
+    for (int i = 0; i < kAccStages; ++i) { mbar_init(&sl->acc_full[i], 1); mbar_init(&sl->acc_empty[i], kEpiWarps * kCtaGroup); }
     fence_mbar_init();
     tma_prefetch_desc(&tm_a);
     tma_prefetch_desc(&tm_b);
@@ -129,7 +130,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = sl->tmem_base;
 
-  if (warp == 3 && lane == 0) {
+  // Every role loop below is executed by its WHOLE warp with warp-uniform control flow; only the instruction that
+  // must be issued once (TMA, tcgen05.mma, commit) sits under elect_one().  A loop owned by a single divergent lane
+  // makes the compiler shuttle every descriptor through ELECT / R2UR.BROADCAST / BRA.U.ANY sequences (~130 SASS
+  // instructions per tap, measured 840 clk per tap against 256 clk of MMA work on the 64->128 layer).
+  if (warp == 3) {
     // ---------------- A producer: one halo box per (work item, chunk); pair members signal the leader's barrier
     int stage = 0, phase = 0;
     for (int work = work0; work < p.total_work; work += work_stride) {
@@ -137,17 +142,21 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       for (int c = 0; c < chunks; ++c) {
         mbar_wait(&sl->a_empty[stage], phase ^ 1);
         uint8_t* dst = a_smem + stage * kAStageBytes;
-        if constexpr (kCtaGroup == 1) {
-          mbar_arrive_expect_tx(&sl->a_full[stage], kABytes);
-          tma_load_4d(dst, &tm_a, &sl->a_full[stage], c * kKC, t.x0 - 1, t.y0 - 1, t.img);
-        } else {
-          if (rank == 0) mbar_arrive_expect_tx(&sl->a_full[stage], 2 * kABytes);
-          tma_load_4d_pair(dst, &tm_a, mapa_shared(smem_u32(&sl->a_full[stage]), 0), c * kKC, t.x0 - 1, t.y0 - 1, t.img);
+        if (elect_one()) {
+          if constexpr (kCtaGroup == 1) {
+            mbar_arrive_expect_tx(&sl->a_full[stage], kABytes);
+            tma_load_4d(dst, &tm_a, &sl->a_full[stage], c * kKC, t.x0 - 1, t.y0 - 1, t.img);
+          } else {
+            if (rank == 0) mbar_arrive_expect_tx(&sl->a_full[stage], 2 * kABytes);
+            tma_load_4d_pair(dst, &tm_a, mapa_shared(smem_u32(&sl->a_full[stage]), 0), c * kKC, t.x0 - 1, t.y0 - 1,
+                             t.img);
+          }
         }
+        __syncwarp();
         if (++stage == kAStages) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 0 && lane == 0) {
+  } else if (warp == 0) {
     // ---------------- B producer: this CTA's share of the weight tile per (work item, chunk, tap)
     int stage = 0, phase = 0;
     for (int work = work0; work < p.total_work; work += work_stride) {
@@ -157,21 +166,27 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
           mbar_wait(&sl->b_empty[stage], phase ^ 1);
           uint8_t* dst = b_smem + stage * C::kBStageBytes;
           const int row = tap * p.cout + t.n0 + rank * C::kBRows;
-          if constexpr (kCtaGroup == 1) {
-            mbar_arrive_expect_tx(&sl->b_full[stage], C::kBStageBytes);
-            tma_load_2d(dst, &tm_b, &sl->b_full[stage], c * kKC, row);
-          } else {
-            if (rank == 0) mbar_arrive_expect_tx(&sl->b_full[stage], 2 * C::kBStageBytes);
-            tma_load_2d_pair(dst, &tm_b, mapa_shared(smem_u32(&sl->b_full[stage]), 0), c * kKC, row);
+          if (elect_one()) {
+            if constexpr (kCtaGroup == 1) {
+              mbar_arrive_expect_tx(&sl->b_full[stage], C::kBStageBytes);
+              tma_load_2d(dst, &tm_b, &sl->b_full[stage], c * kKC, row);
+            } else {
+              if (rank == 0) mbar_arrive_expect_tx(&sl->b_full[stage], 2 * C::kBStageBytes);
+              tma_load_2d_pair(dst, &tm_b, mapa_shared(smem_u32(&sl->b_full[stage]), 0), c * kKC, row);
+            }
           }
+          __syncwarp();
           if (++stage == C::kBStages) { stage = 0; phase ^= 1; }
         }
       }
     }
-  } else if (warp == 1 && lane == 0 && rank == 0) {
+  } else if (warp == 1 && rank == 0) {
     // ---------------- MMA issuer (pair leader only)
     constexpr uint32_t idesc = umma_idesc_bf16_f32(128 * kCtaGroup, kBlockN);
     constexpr uint32_t sbo = kHaloW * 128;   // one halo row per 8-pixel core-matrix group
+    // descriptor templates: everything but the 14-bit start-address field is loop invariant
+    const uint64_t adesc0 = umma_smem_desc_sw128(0, sbo, 0);
+    const uint64_t bdesc0 = umma_smem_desc_sw128(0, 1024, 0);
     int as = 0, aphase = 0, bs = 0, bphase = 0;
     int it = 0;
     for (int work = work0; work < p.total_work; work += work_stride, ++it) {
@@ -193,28 +208,38 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
           // window of the TMA-written halo is a valid K-major operand as is.
           const uint32_t a_tap = a_base + static_cast<uint32_t>((ky * kHaloW + kx) * 128);
           const uint32_t b_base = smem_u32(b_smem + bs * C::kBStageBytes);
+          const uint64_t adesc = adesc0 | static_cast<uint64_t>(a_tap >> 4);
+          const uint64_t bdesc = bdesc0 | static_cast<uint64_t>(b_base >> 4);
+          const bool last_tap = tap == 8;
+          if (elect_one()) {
 #pragma unroll
-          for (int s = 0; s < kKC / 16; ++s) {
-            const uint64_t adesc = umma_smem_desc_sw128(a_tap + s * 32, sbo, 0);
-            const uint64_t bdesc = umma_smem_desc_sw128(b_base + s * 32, 1024, 0);
-            const uint32_t accum = (c | tap | s) != 0 ? 1u : 0u;
-            if constexpr (kCtaGroup == 1) umma_bf16(d_tmem, adesc, bdesc, idesc, accum);
-            else umma_bf16_pair(d_tmem, adesc, bdesc, idesc, accum);
+            for (int s = 0; s < kKC / 16; ++s) {
+              const uint32_t accum = (c | tap | s) != 0 ? 1u : 0u;
+              // +32 bytes per UMMA_K step = +2 in the (address >> 4) field; never carries out of it
+              if constexpr (kCtaGroup == 1) umma_bf16(d_tmem, adesc + 2 * s, bdesc + 2 * s, idesc, accum);
+              else umma_bf16_pair(d_tmem, adesc + 2 * s, bdesc + 2 * s, idesc, accum);
+            }
+            if constexpr (kCtaGroup == 1) {
+              umma_commit(&sl->b_empty[bs]);
+              if (last_tap) umma_commit(&sl->a_empty[as]);
+              if (last_tap && c == chunks - 1) umma_commit(&sl->acc_full[acc]);
+            } else {
+              umma_commit_pair(&sl->b_empty[bs]);
+              if (last_tap) umma_commit_pair(&sl->a_empty[as]);
+              if (last_tap && c == chunks - 1) umma_commit_pair(&sl->acc_full[acc]);
+            }
           }
-          if constexpr (kCtaGroup == 1) umma_commit(&sl->b_empty[bs]);
-          else umma_commit_pair(&sl->b_empty[bs]);
+          __syncwarp();
           if (++bs == C::kBStages) { bs = 0; bphase ^= 1; }
         }
-        if constexpr (kCtaGroup == 1) umma_commit(&sl->a_empty[as]);
-        else umma_commit_pair(&sl->a_empty[as]);
         if (++as == kAStages) { as = 0; aphase ^= 1; }
       }
-      if constexpr (kCtaGroup == 1) umma_commit(&sl->acc_full[acc]);
-      else umma_commit_pair(&sl->acc_full[acc]);
     }
   } else if (warp >= 4) {
-    // ---------------- epilogue: 128 threads, thread <-> TMEM lane <-> output pixel of this CTA's tile
-    const int ew = warp - 4;
+    // ---------------- epilogue: thread <-> TMEM lane <-> output pixel of this CTA's tile; the two warps that share a
+    // lane quadrant (warp % 4) take alternate 32-column blocks
+    const int ew = warp & 3;
+    const int half = (warp - 4) >> 2;
     const int m = ew * 32 + lane;
     const int r = m >> 3, cpx = m & 7;
     const int et = threadIdx.x - 128;
@@ -226,18 +251,18 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       const int acc_phase = (it >> 1) & 1;
       float* s_scale = sl->scale[it & 1];
       float* s_shift = sl->shift[it & 1];
-      for (int i = et; i < kBlockN; i += 128) {
+      for (int i = et; i < kBlockN; i += 32 * kEpiWarps) {
         s_scale[i] = __ldg(p.scale + t.n0 + i);
         s_shift[i] = __ldg(p.shift + t.n0 + i);
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
       mbar_wait(&sl->acc_full[acc], acc_phase);
       tc_fence_after();
       const int y = t.y0 + r, x = t.x0 + cpx;
       const bool valid = t.img < p.n_img && y < p.H && x < p.W;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(acc * kBlockN);
 #pragma unroll 1
-      for (int cb = 0; cb < kBlockN / 32; ++cb) {
+      for (int cb = half; cb < kBlockN / 32; cb += kEpiWarps / 4) {
         uint32_t v[32];
         tmem_ld_32x32(taddr + cb * 32, v);
         tmem_ld_wait();
