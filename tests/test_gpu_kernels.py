@@ -102,7 +102,7 @@ def test_conv_first_eval(ctk, cin, cout, c_off):
          ptr(shift), c_int(cout), c_float(0.01), ptr(out), c_int(cstride), c_int(64), stream())
     torch.cuda.synchronize()
     assert out[..., :64].abs().max().item() == 0.0            # channel offset respected
-    _bf16_close(out[..., 64:], ref, rel=2 ** -8, abs_=1e-4)   # fp32 math, one bf16 rounding
+    _bf16_close(out[..., 64:], ref, rel=2 ** -7, abs_=1e-4)   # fp32-class math, bf16 store (negative side rounded twice)
 
 
 # ------------------------------------------------------------------ tensor-core conv block

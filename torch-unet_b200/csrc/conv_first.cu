@@ -79,7 +79,6 @@ conv_first_tc_kernel(const float* __restrict__ x, int n_img, int c_total, int c_
   uint8_t* groups_smem = smem + C::kBBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(groups_smem + kGroups * C::kGroupBytes);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kGroups);
-  __shared__ float s_shift[COUT];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int group = warp >> 2;
@@ -92,12 +91,13 @@ conv_first_tc_kernel(const float* __restrict__ x, int n_img, int c_total, int c_
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc<1>(tmem_slot, kTmemCols);
-  for (int i = threadIdx.x; i < COUT; i += kThreads) s_shift[i] = __ldg(shift + i);
   for (int i = threadIdx.x; i < COUT * C::kKWords; i += kThreads) {
     const int n = i / C::kKWords, kw = i % C::kKWords;
     uint32_t word = 0;
     const int ch = kw / 14, j = kw % 14;
-    if (ch < CIN) {
+    if (kw == 14 * CIN) {
+      word = split_hi_lo(__ldg(shift + n));                               // (shift_hi, shift_lo) against A's (1, 1)
+    } else if (ch < CIN) {
       const float* wr = w_folded + (n * CIN + ch) * 9;
       if (j < 9) {
         const uint32_t hl = split_hi_lo(__ldg(wr + j));
@@ -125,6 +125,7 @@ conv_first_tc_kernel(const float* __restrict__ x, int n_img, int c_total, int c_
   const int r = gt >> 3, cpx = gt & 7;
   const int Hp = H >> 1, Wp = W >> 1;
   constexpr uint32_t idesc = umma_idesc_bf16_f32(128, COUT);
+  const __nv_bfloat162 slope2 = __float2bfloat162_rn(slope);
   uint32_t parity = 0;
 
   // input prefetch: the halo of the NEXT region is loaded into registers while this one is being processed.
@@ -192,6 +193,7 @@ conv_first_tc_kernel(const float* __restrict__ x, int n_img, int c_total, int c_
         for (int u = 0; u < 4; ++u) kw[c * 14 + 9 + u] = __byte_perm(t[2 * u], t[2 * u + 1], 0x5410);   // (hi, hi)
         kw[c * 14 + 13] = t[8] & 0xffffu;
       }
+      kw[14 * CIN] = 0x3f803f80u;                                         // bf16 (1, 1): adds the folded BN shift inside the MMA
       uint8_t* tile = a_smem + s * C::kATileBytes + (gt >> 3) * C::kSbo + (gt & 7) * 16;
 #pragma unroll
       for (int j = 0; j < C::kK / 8; ++j)
@@ -202,19 +204,23 @@ conv_first_tc_kernel(const float* __restrict__ x, int n_img, int c_total, int c_
     asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory");
 
     // ---- one thread issues the MMAs of this region and commits to the group's barrier
-    if (gt == 0) {
+    if (ew == 0) {                      // warp-uniform branch; the single issuing lane is elected inside
       tc_fence_after();
-      const uint32_t b_base = smem_u32(b_smem);
+      const uint64_t desc0 = umma_smem_desc_nosw(0, C::kLbo, C::kSbo);
+      const uint64_t bdesc = desc0 | static_cast<uint64_t>(smem_u32(b_smem) >> 4);
+      const uint64_t adesc = desc0 | static_cast<uint64_t>(smem_u32(a_smem) >> 4);
+      if (elect_one()) {
 #pragma unroll
-      for (int s = 0; s < C::kSub; ++s) {
-        const uint32_t a_base = smem_u32(a_smem + s * C::kATileBytes);
+        for (int s = 0; s < C::kSub; ++s) {
 #pragma unroll
-        for (int ks = 0; ks < C::kK / 16; ++ks) {
-          umma_bf16(tmem_group + s * COUT, umma_smem_desc_nosw(a_base + ks * 2 * C::kLbo, C::kLbo, C::kSbo),
-                    umma_smem_desc_nosw(b_base + ks * 2 * C::kLbo, C::kLbo, C::kSbo), idesc, ks != 0 ? 1u : 0u);
+          for (int ks = 0; ks < C::kK / 16; ++ks) {
+            umma_bf16(tmem_group + s * COUT, adesc + ((s * C::kATileBytes + ks * 2 * C::kLbo) >> 4),
+                      bdesc + ((ks * 2 * C::kLbo) >> 4), idesc, ks != 0 ? 1u : 0u);
+          }
         }
+        umma_commit(&bars[group]);
       }
-      umma_commit(&bars[group]);
+      __syncwarp();
     }
     mbar_wait(&bars[group], parity);
     parity ^= 1;
@@ -233,11 +239,7 @@ conv_first_tc_kernel(const float* __restrict__ x, int n_img, int c_total, int c_
         tmem_ld_wait();
         uint32_t pk[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float f0 = leaky(__uint_as_float(v[2 * i]) + s_shift[cb * 32 + 2 * i], slope);
-          const float f1 = leaky(__uint_as_float(v[2 * i + 1]) + s_shift[cb * 32 + 2 * i + 1], slope);
-          pk[i] = pack_bf16x2(f0, f1);
-        }
+        for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
         const bool odd_x = (lane & 1) != 0;
         uint32_t q[8];
 #pragma unroll
@@ -253,7 +255,7 @@ conv_first_tc_kernel(const float* __restrict__ x, int n_img, int c_total, int c_
         for (int i = 0; i < 4; ++i) {
           const uint32_t send = odd_y ? q[i] : q[4 + i];
           const uint32_t keep = odd_y ? q[4 + i] : q[i];
-          ov[i] = max_bf16x2(keep, __shfl_xor_sync(0xffffffffu, send, 8));
+          ov[i] = leaky_bf16x2(max_bf16x2(keep, __shfl_xor_sync(0xffffffffu, send, 8)), slope2);
         }
         if (valid) {
           const int ch = cb * 32 + (odd_x ? 16 : 0) + (odd_y ? 8 : 0);

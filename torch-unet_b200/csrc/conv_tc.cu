@@ -244,6 +244,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     const int r = m >> 3, cpx = m & 7;
     const int et = threadIdx.x - 128;
     const int Hp = p.H >> 1, Wp = p.W >> 1;
+    const __nv_bfloat162 slope2 = __float2bfloat162_rn(p.slope);
     int it = 0;
     for (int work = work0; work < p.total_work; work += work_stride, ++it) {
       const TileCoord t = decode_work<kCtaGroup, kBlockN>(p, work, rank);
@@ -271,7 +272,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         for (int i = 0; i < 16; ++i) {
           float f0 = fmaf(__uint_as_float(v[2 * i]), s_scale[cb * 32 + 2 * i], s_shift[cb * 32 + 2 * i]);
           float f1 = fmaf(__uint_as_float(v[2 * i + 1]), s_scale[cb * 32 + 2 * i + 1], s_shift[cb * 32 + 2 * i + 1]);
-          if (p.act) { f0 = leaky(f0, p.slope); f1 = leaky(f1, p.slope); }
+          if (p.act && !p.pool) { f0 = leaky(f0, p.slope); f1 = leaky(f1, p.slope); }
           pk[i] = pack_bf16x2(f0, f1);
         }
         if (p.pool) {
@@ -292,6 +293,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
             const uint32_t send = odd_y ? q[i] : q[4 + i];
             const uint32_t keep = odd_y ? q[4 + i] : q[i];
             ov[i] = max_bf16x2(keep, __shfl_xor_sync(0xffffffffu, send, 8));
+            if (p.act) ov[i] = leaky_bf16x2(ov[i], slope2);      // activation after the pool: 4x fewer elements
           }
           if (valid) {
             const int ch = t.n0 + cb * 32 + (odd_x ? 16 : 0) + (odd_y ? 8 : 0);

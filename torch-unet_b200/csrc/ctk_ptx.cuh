@@ -235,5 +235,12 @@ __device__ __forceinline__ uint32_t max_bf16x2(uint32_t a, uint32_t b) {
   return *reinterpret_cast<uint32_t*>(&r);
 }
 __device__ __forceinline__ float leaky(float x, float slope) { return x > 0.f ? x : x * slope; }
+// LeakyReLU on a packed bf16 pair, 0 <= slope <= 1:  max(v, slope*v).  Applied AFTER the max-pool (both are monotone, so
+// they commute) it touches a quarter of the elements; the negative branch is rounded twice (<= 1 bf16 ulp of 0.01*|v|).
+__device__ __forceinline__ uint32_t leaky_bf16x2(uint32_t v, __nv_bfloat162 slope2) {
+  const __nv_bfloat162 x = *reinterpret_cast<__nv_bfloat162*>(&v);
+  const __nv_bfloat162 r = __hmax2(x, __hmul2(x, slope2));
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
 
 }  // namespace ctk
