@@ -139,6 +139,87 @@ int ctk_adam_multi(void* const* params, void* const* grads, void* const* exp_avg
                    float lr, float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
                    void* stream);
 
+/* ==========================================================================================
+ * Training path (train-mode BatchNorm, backward pass).  Replaces loss.backward() (train_model.py:422, a10 in
+ * SURVEY 8a) and the train-mode forward of the layers named at each entry.
+ * ========================================================================================== */
+
+/* Raw convolutions for train mode: y = conv(x) WITHOUT bias (train-mode BatchNorm cancels it; it re-enters the
+ * running mean in ctk_bn_finalize), stored bf16 NHWC at full resolution, plus stats[c] = sum(y), stats[C+c] = sum(y^2)
+ * over all pixels (fp32 accumulators; stats may be NULL for ctk_conv3x3_tc_raw, which is also the dgrad kernel when
+ * fed ctk_pack_conv_weight_dgrad_bf16 weights: dX = conv(dY, rot180(W)^T)).
+ * Replaces: nn.Conv2d forward / aten::convolution_backward (input gradient), regression_model.py:14,23;
+ * two_branch_regression.py:10,16,22,28. */
+int ctk_conv_first_raw(const float* x, int n, int c_total, int c_offset, int cin, int H, int W, const float* w,
+                       int cout, void* y_bf16, float* stats, void* stream);
+int ctk_conv3x3_tc_raw(const void* x_bf16, int n, int H, int W, int cin, const void* w_packed_bf16, int cout,
+                       void* y_bf16, float* stats, void* stream);
+/* conv weight [Cout,Cin,3,3] fp32 -> [9][Cin][Cout] bf16 with the taps rotated by 180 degrees (dgrad operand). */
+int ctk_pack_conv_weight_dgrad_bf16(const float* w, int cout, int cin, void* w_packed_bf16, void* stream);
+
+/* Batch statistics -> normalisation constants; updates running_mean/var (momentum, unbiased variance, conv bias added
+ * to the mean) and num_batches_tracked like nn.BatchNorm in train().  running_* / num_batches_tracked may be NULL.
+ * Replaces: aten::native_batch_norm (training=True), regression_model.py:15,24,37,42. */
+int ctk_bn_finalize(const float* sums, double count, const float* bias, const float* gamma, const float* beta,
+                    float* running_mean, float* running_var, long long* num_batches_tracked, float momentum, float eps,
+                    int channels, float* scale, float* shift, float* mean, float* invstd, void* stream);
+/* out = maxpool2x2(leaky(y*scale + shift)), y bf16 NHWC [n,H,W,C] -> out bf16 NHWC [n,H/2,W/2,out_cstride] @ out_coffset.
+ * Replaces: BatchNorm2d(train) apply + LeakyReLU + MaxPool2d, regression_model.py:15-17,24-26. */
+int ctk_bn_act_pool_fwd(const void* y_bf16, int n, int H, int W, int channels, const float* scale, const float* shift,
+                        float slope, void* out_bf16, int out_cstride, int out_coffset, void* stream);
+/* Backward of MaxPool2d + LeakyReLU + BatchNorm2d(train).  dp = gradient of the pooled output (bf16 NHWC with channel
+ * stride/offset).  reduce: sums[c] = sum(dA) (= dbeta), sums[C+c] = sum(dA*xhat) (= dgamma).  apply: dy (bf16 NHWC,
+ * dense) = gamma*invstd*(dA - mean(dA) - xhat*mean(dA*xhat)).  The pool's argmax is recomputed (first maximum wins). */
+int ctk_bn_bwd_reduce(const void* y_bf16, const void* dp_bf16, int dp_cstride, int dp_coffset, int n, int H, int W,
+                      int channels, const float* scale, const float* shift, const float* mean, const float* invstd,
+                      float slope, float* sums, void* stream);
+int ctk_bn_bwd_apply(const void* y_bf16, const void* dp_bf16, int dp_cstride, int dp_coffset, int n, int H, int W,
+                     int channels, const float* scale, const float* shift, const float* mean, const float* invstd,
+                     const float* sums, float slope, void* dy_bf16, void* stream);
+
+/* Weight gradients.  dw is fp32 in the reference layout [Cout,Cin,3,3] and is overwritten.
+ * ctk_conv3x3_wgrad_tc: tcgen05 GEMM over pixels with MN-major NHWC operands (cin % 64 == 0, cout % 128 == 0).
+ * ctk_conv_first_wgrad: first layer (cin 1 or 2), x = fp32 NCHW input planes.
+ * Replaces: aten::convolution_backward (weight gradient). */
+int ctk_conv3x3_wgrad_tc(const void* dy_bf16, const void* x_bf16, int n, int H, int W, int cin, int cout, float* dw,
+                         void* stream);
+int ctk_conv_first_wgrad(const void* dy_bf16, const float* x, int n, int c_total, int c_offset, int cin, int H, int W,
+                         int cout, float* dw, void* stream);
+
+/* FC1 in training: feature-map transpose out[(c*HW+p)][n] = feat[n][p][c] (zero padded to ld columns), FC1 weight
+ * transposed + permuted w_t[p*C+c][o] = w[o][c*HW+p], and a plain bf16-output GEMM C[M,N] = A[M,K] * B[N,K]^T
+ * (M, N multiples of 128, K of 64).  With ctk_gemm_bf16_splitk they give FC1 forward, dX and dW:
+ *   dfeat[n, p*C+c] = dZ1[n,:] . w_t[p*C+c,:]          dW1[o, c*HW+p] = dZ1^T[o,:] . featT[c*HW+p,:]
+ * Replaces: aten::addmm / mm of nn.Linear, regression_model.py:36; two_branch_regression.py:42. */
+int ctk_feat_transpose_bf16(const void* feat_bf16, int n, int hw, int channels, void* out_bf16, int ld, void* stream);
+int ctk_pack_fc1_weight_t_bf16(const float* w, int out_features, int channels, int hw, void* w_t_bf16, void* stream);
+int ctk_gemm_bf16_out_bf16(const void* a_bf16, const void* b_bf16, int M, int N, int K, void* c_bf16, void* stream);
+
+/* Small fp32 building blocks of the train-mode head and its backward (regression_model.py:37-46,
+ * two_branch_regression.py:43-53,100).
+ *  ctk_colstat:          z[n][f] = sum_s in[s*split_stride + n*row_stride + f] + bias[f]; stats = column sum / sum of squares
+ *  ctk_bn1d_act_drop_fwd: a = leaky(z*scale+shift) * mask/(1-p)   (mask = 0/1 keep mask or NULL)
+ *  ctk_sgemm_strided:    c[i][j] = sum_k a[i*a_i + k*a_k] * b[j*b_j + k*b_k] + bias[j]
+ *  ctk_head_out_fwd/bwd: the last Linear(f,1) [+ Sigmoid*0.5] and its gradients
+ *  ctk_bn1d_bwd_reduce/apply: backward of Dropout + LeakyReLU + BatchNorm1d(train); apply can also emit bf16 copies
+ *                        dz_bf16[n][f] and dzT_bf16[f][n] (row stride ldt) for the FC1 backward GEMMs. */
+int ctk_colstat(const float* in, int splits, long long split_stride, int row_stride, const float* bias, int n_rows,
+                int features, float* z, float* stats, void* stream);
+int ctk_bn1d_act_drop_fwd(const float* z, const float* scale, const float* shift, const float* mask, float drop_p,
+                          float slope, int n_rows, int features, float* a, void* stream);
+int ctk_sgemm_strided(const float* a, long long a_i, long long a_k, const float* b, long long b_j, long long b_k,
+                      const float* bias, int M, int N, int K, float* c, int ldc, void* stream);
+int ctk_head_out_fwd(const float* a2, const float* w3, const float* b3, int n_rows, int features, int sigmoid_half,
+                     float* out, void* stream);
+int ctk_head_out_bwd(const float* dout, const float* out, const float* a2, const float* w3, int n_rows, int features,
+                     int sigmoid_half, float* da2, float* dw3, float* db3, void* stream);
+int ctk_bn1d_bwd_reduce(const float* da, const float* mask, float drop_p, const float* z, const float* scale,
+                        const float* shift, const float* mean, const float* invstd, float slope, int n_rows,
+                        int features, float* dact, float* sums, void* stream);
+int ctk_bn1d_bwd_apply(const float* dact, const float* z, const float* scale, const float* mean, const float* invstd,
+                       const float* sums, int n_rows, int features, float* dz, void* dz_bf16, void* dzT_bf16, int ldt,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif

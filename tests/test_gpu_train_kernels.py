@@ -1,0 +1,196 @@
+"""GPU parity tests of the training-path kernels (through the C ABI) against PyTorch-CPU fp32 autograd of the same op.
+
+Operands are rounded to bf16 up front so the only differences are accumulation order and the final bf16 store:
+tolerances are a few bf16 ulps for bf16 outputs and ~1e-3 relative for fp32 reductions over bf16 products.
+"""
+from ctypes import c_double, c_float, c_int, c_longlong
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def L():
+    from ctk import _lib
+    _lib.load()
+    return _lib
+
+
+def bf(t):
+    return t.to(torch.bfloat16).float()
+
+
+def rel_l2(a, b):
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+@pytest.mark.parametrize("n,H,W,cin,cout", [(2, 32, 32, 64, 128), (3, 16, 16, 128, 256), (2, 16, 24, 128, 64),
+                                             (1, 8, 8, 256, 512)])
+def test_conv_raw_and_stats(L, n, H, W, cin, cout):
+    torch.manual_seed(0)
+    x = bf(torch.randn(n, H, W, cin))
+    w = bf(torch.randn(cout, cin, 3, 3) / (3 * cin ** 0.5))
+    ref = F.conv2d(x.permute(0, 3, 1, 2), w, padding=1).permute(0, 2, 3, 1).contiguous()
+    xd, wd = x.to(torch.bfloat16).cuda(), w.cuda()
+    wp = torch.empty(9, cout, cin, device="cuda", dtype=torch.bfloat16)
+    L.call("ctk_pack_conv_weight_bf16", L.ptr(wd), c_int(cout), c_int(cin), L.ptr(wp), L.stream())
+    y = torch.zeros(n, H, W, cout, device="cuda", dtype=torch.bfloat16)
+    stats = torch.empty(2 * cout, device="cuda")
+    L.call("ctk_conv3x3_tc_raw", L.ptr(xd), c_int(n), c_int(H), c_int(W), c_int(cin), L.ptr(wp), c_int(cout), L.ptr(y),
+           L.ptr(stats), L.stream())
+    torch.cuda.synchronize()
+    assert rel_l2(y.float().cpu(), ref) < 4e-3
+    s = stats.cpu()
+    np.testing.assert_allclose(s[:cout].numpy(), ref.sum((0, 1, 2)).numpy(), rtol=2e-3, atol=2e-2)
+    np.testing.assert_allclose(s[cout:].numpy(), (ref ** 2).sum((0, 1, 2)).numpy(), rtol=2e-3, atol=2e-2)
+
+
+@pytest.mark.parametrize("cin,cout,coff", [(1, 64, 1), (2, 128, 0)])
+def test_conv_first_raw_and_stats(L, cin, cout, coff):
+    torch.manual_seed(1)
+    n, H, W = 2, 32, 48
+    x = torch.rand(n, 2, H, W)
+    w = torch.randn(cout, cin, 3, 3) / 3
+    ref = F.conv2d(x[:, coff:coff + cin], w, padding=1).permute(0, 2, 3, 1).contiguous()
+    xd, wd = x.cuda(), w.cuda()
+    y = torch.zeros(n, H, W, cout, device="cuda", dtype=torch.bfloat16)
+    stats = torch.empty(2 * cout, device="cuda")
+    L.call("ctk_conv_first_raw", L.ptr(xd), c_int(n), c_int(2), c_int(coff), c_int(cin), c_int(H), c_int(W), L.ptr(wd),
+           c_int(cout), L.ptr(y), L.ptr(stats), L.stream())
+    torch.cuda.synchronize()
+    assert rel_l2(y.float().cpu(), ref) < 3e-3          # bf16 store of an fp32-class result
+    s = stats.cpu()
+    np.testing.assert_allclose(s[:cout].numpy(), ref.sum((0, 1, 2)).numpy(), rtol=1e-4, atol=1e-2)
+    np.testing.assert_allclose(s[cout:].numpy(), (ref ** 2).sum((0, 1, 2)).numpy(), rtol=1e-4, atol=1e-2)
+
+
+def _bn_setup(n, H, W, C, seed):
+    torch.manual_seed(seed)
+    y = bf(torch.randn(n, H, W, C) * 0.7 + 0.1)
+    gamma = torch.randn(C)
+    beta = 0.1 * torch.randn(C)
+    bias = 0.05 * torch.randn(C)
+    return y, gamma, beta, bias
+
+
+def test_bn_finalize_act_pool_and_backward(L):
+    n, H, W, C = 3, 16, 24, 64
+    y, gamma, beta, bias = _bn_setup(n, H, W, C, 2)
+    dp = bf(torch.randn(n, H // 2, W // 2, C))
+    # ---- reference: BatchNorm2d(train) on (y + bias) -> LeakyReLU -> MaxPool, autograd for dy / dgamma / dbeta
+    yr = y.permute(0, 3, 1, 2).clone().requires_grad_(True)
+    g = gamma.clone().requires_grad_(True)
+    b = beta.clone().requires_grad_(True)
+    rm, rv = torch.zeros(C), torch.ones(C)
+    z = F.batch_norm(yr + bias[None, :, None, None], rm, rv, g, b, training=True, momentum=0.1, eps=1e-5)
+    pooled = F.max_pool2d(F.leaky_relu(z, 0.01), 2)
+    pooled.backward(dp.permute(0, 3, 1, 2))
+    # ---- device
+    yd = y.to(torch.bfloat16).cuda()
+    sums = torch.stack([y.sum((0, 1, 2)), (y ** 2).sum((0, 1, 2))]).flatten().cuda()
+    dev = lambda t: t.clone().cuda()
+    gd, bd, biasd, rmd, rvd = dev(gamma), dev(beta), dev(bias), torch.zeros(C).cuda(), torch.ones(C).cuda()
+    nbt = torch.zeros((), dtype=torch.int64, device="cuda")
+    scale, shift, mean, invstd = (torch.empty(C, device="cuda") for _ in range(4))
+    L.call("ctk_bn_finalize", L.ptr(sums), c_double(n * H * W), L.ptr(biasd), L.ptr(gd), L.ptr(bd), L.ptr(rmd), L.ptr(rvd),
+           L.ptr(nbt), c_float(0.1), c_float(1e-5), c_int(C), L.ptr(scale), L.ptr(shift), L.ptr(mean), L.ptr(invstd),
+           L.stream())
+    out = torch.zeros(n, H // 2, W // 2, C + 8, device="cuda", dtype=torch.bfloat16)
+    L.call("ctk_bn_act_pool_fwd", L.ptr(yd), c_int(n), c_int(H), c_int(W), c_int(C), L.ptr(scale), L.ptr(shift),
+           c_float(0.01), L.ptr(out), c_int(C + 8), c_int(8), L.stream())
+    dpd = torch.zeros(n, H // 2, W // 2, C + 8, device="cuda", dtype=torch.bfloat16)
+    dpd[..., 8:] = dp.to(torch.bfloat16).cuda()
+    bsum = torch.empty(2 * C, device="cuda")
+    L.call("ctk_bn_bwd_reduce", L.ptr(yd), L.ptr(dpd), c_int(C + 8), c_int(8), c_int(n), c_int(H), c_int(W), c_int(C),
+           L.ptr(scale), L.ptr(shift), L.ptr(mean), L.ptr(invstd), c_float(0.01), L.ptr(bsum), L.stream())
+    dy = torch.empty(n, H, W, C, device="cuda", dtype=torch.bfloat16)
+    L.call("ctk_bn_bwd_apply", L.ptr(yd), L.ptr(dpd), c_int(C + 8), c_int(8), c_int(n), c_int(H), c_int(W), c_int(C),
+           L.ptr(scale), L.ptr(shift), L.ptr(mean), L.ptr(invstd), L.ptr(bsum), c_float(0.01), L.ptr(dy), L.stream())
+    torch.cuda.synchronize()
+    assert int(nbt) == 1
+    np.testing.assert_allclose(rmd.cpu().numpy(), rm.numpy(), rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(rvd.cpu().numpy(), rv.numpy(), rtol=1e-4, atol=1e-6)
+    assert out[..., :8].abs().max().item() == 0
+    assert rel_l2(out[..., 8:].float().cpu(), pooled.detach().permute(0, 2, 3, 1)) < 4e-3
+    np.testing.assert_allclose(bsum[:C].cpu().numpy(), b.grad.numpy(), rtol=1e-3, atol=1e-3)     # dbeta
+    np.testing.assert_allclose(bsum[C:].cpu().numpy(), g.grad.numpy(), rtol=1e-3, atol=1e-3)     # dgamma
+    assert rel_l2(dy.float().cpu(), yr.grad.permute(0, 2, 3, 1)) < 6e-3
+
+
+@pytest.mark.parametrize("n,H,W,cin,cout", [(2, 32, 32, 64, 128), (2, 16, 16, 128, 256), (1, 16, 8, 256, 512)])
+def test_dgrad_and_wgrad(L, n, H, W, cin, cout):
+    torch.manual_seed(3)
+    x = bf(torch.randn(n, H, W, cin)).permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+    w = bf(torch.randn(cout, cin, 3, 3) / (3 * cin ** 0.5)).requires_grad_(True)
+    dy = bf(torch.randn(n, H, W, cout))
+    F.conv2d(x, w, padding=1).backward(dy.permute(0, 3, 1, 2))
+    xd = x.detach().permute(0, 2, 3, 1).contiguous().to(torch.bfloat16).cuda()
+    dyd = dy.to(torch.bfloat16).cuda()
+    wd = w.detach().cuda()
+    # dgrad = conv(dY, rot180(W)^T)
+    wg = torch.empty(9, cin, cout, device="cuda", dtype=torch.bfloat16)
+    L.call("ctk_pack_conv_weight_dgrad_bf16", L.ptr(wd), c_int(cout), c_int(cin), L.ptr(wg), L.stream())
+    dx = torch.zeros(n, H, W, cin, device="cuda", dtype=torch.bfloat16)
+    L.call("ctk_conv3x3_tc_raw", L.ptr(dyd), c_int(n), c_int(H), c_int(W), c_int(cout), L.ptr(wg), c_int(cin), L.ptr(dx),
+           L.ptr(None), L.stream())
+    dw = torch.empty(cout, cin, 3, 3, device="cuda")
+    L.call("ctk_conv3x3_wgrad_tc", L.ptr(dyd), L.ptr(xd), c_int(n), c_int(H), c_int(W), c_int(cin), c_int(cout),
+           L.ptr(dw), L.stream())
+    torch.cuda.synchronize()
+    assert rel_l2(dx.float().cpu(), x.grad.permute(0, 2, 3, 1)) < 4e-3
+    assert rel_l2(dw.cpu(), w.grad) < 1e-3
+
+
+@pytest.mark.parametrize("cin,cout,coff", [(1, 64, 1), (2, 128, 0)])
+def test_first_layer_wgrad(L, cin, cout, coff):
+    torch.manual_seed(4)
+    n, H, W = 2, 24, 40
+    x = torch.rand(n, 2, H, W)
+    w = torch.randn(cout, cin, 3, 3, requires_grad=True)
+    dy = bf(torch.randn(n, H, W, cout))
+    F.conv2d(x[:, coff:coff + cin], w, padding=1).backward(dy.permute(0, 3, 1, 2))
+    xd, dyd = x.cuda(), dy.to(torch.bfloat16).cuda()
+    dw = torch.empty(cout, cin, 3, 3, device="cuda")
+    L.call("ctk_conv_first_wgrad", L.ptr(dyd), L.ptr(xd), c_int(n), c_int(2), c_int(coff), c_int(cin), c_int(H), c_int(W),
+           c_int(cout), L.ptr(dw), L.stream())
+    torch.cuda.synchronize()
+    assert rel_l2(dw.cpu(), w.grad) < 1e-5
+
+
+def test_fc1_training_gemms(L):
+    torch.manual_seed(5)
+    n, hw, C, O = 6, 16, 64, 128            # K = hw*C = 1024
+    K = hw * C
+    npad = 128
+    feat = bf(torch.randn(n, hw, C))
+    w = bf(torch.randn(O, C * hw) / K ** 0.5)                  # reference layout: columns c*hw + p
+    dz = bf(torch.randn(n, O))
+    # references (reference column order)
+    feat_ref = feat.permute(0, 2, 1).reshape(n, C * hw)         # NCHW flatten
+    dfeat_ref = (dz @ w).reshape(n, C, hw).permute(0, 2, 1)     # back to [n, p, c]
+    dw_ref = dz.t() @ feat_ref
+    featd = torch.zeros(npad, hw, C, device="cuda", dtype=torch.bfloat16)
+    featd[:n] = feat.to(torch.bfloat16).cuda()
+    wd = w.cuda()
+    featT = torch.empty(C * hw, 64, device="cuda", dtype=torch.bfloat16)
+    L.call("ctk_feat_transpose_bf16", L.ptr(featd), c_int(n), c_int(hw), c_int(C), L.ptr(featT), c_int(64), L.stream())
+    wT = torch.empty(hw * C, O, device="cuda", dtype=torch.bfloat16)
+    L.call("ctk_pack_fc1_weight_t_bf16", L.ptr(wd), c_int(O), c_int(C), c_int(hw), L.ptr(wT), L.stream())
+    dzd = torch.zeros(npad, O, device="cuda", dtype=torch.bfloat16)
+    dzd[:n] = dz.to(torch.bfloat16).cuda()
+    dzT = torch.zeros(O, 64, device="cuda", dtype=torch.bfloat16)
+    dzT[:, :n] = dz.t().to(torch.bfloat16).cuda()
+    dfeat = torch.empty(npad, hw * C, device="cuda", dtype=torch.bfloat16)
+    L.call("ctk_gemm_bf16_out_bf16", L.ptr(dzd), L.ptr(wT), c_int(npad), c_int(hw * C), c_int(O), L.ptr(dfeat), L.stream())
+    dw = torch.empty(1, O, C * hw, device="cuda")
+    L.call("ctk_gemm_bf16_splitk", L.ptr(dzT), L.ptr(featT), c_int(O), c_int(C * hw), c_int(64), c_int(1), L.ptr(dw),
+           L.stream())
+    torch.cuda.synchronize()
+    assert rel_l2(featT[:, :n].float().cpu().t(), feat_ref) == 0.0
+    assert featT[:, n:].abs().max().item() == 0.0
+    assert rel_l2(dfeat[:n].float().cpu().reshape(n, hw, C), dfeat_ref) < 4e-3
+    assert rel_l2(dw[0].cpu(), dw_ref) < 1e-3

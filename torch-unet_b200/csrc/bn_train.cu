@@ -1,0 +1,273 @@
+// Train-mode BatchNorm2d + LeakyReLU + MaxPool2d(2,2) around the tensor-core convolutions: statistics finalisation,
+// the normalise/activate/pool pass, and the two backward passes (per-channel reductions, then the dense gradient of the
+// raw conv output).  Replaces aten::native_batch_norm(+_backward), leaky_relu(+_backward) and
+// max_pool2d_with_indices(+_backward) for nn.BatchNorm2d / nn.LeakyReLU / nn.MaxPool2d at
+// /root/reference/regression_model.py:15-17,24-26 and two_branch_regression.py:11-13,... in training mode.
+//
+// All four passes are HBM streaming: Y (raw conv output, bf16 NHWC) is read once per pass with 16-byte accesses,
+// one thread per pooled pixel x 8 channels.  No argmax is stored: the backward passes recompute the activations of
+// the 2x2 window from Y and pick the first maximum in scan order, which is what PyTorch's max_pool2d does.
+//   forward : 2 B/elem read + 0.5 B/elem written
+//   reduce  : 2 B/elem + 0.5 B/elem (dP) read
+//   apply   : 2 B/elem + 0.5 B/elem read, 2 B/elem written
+#include "ctk_common.h"
+#include "ctk_ptx.cuh"
+
+namespace {
+
+using namespace ctk;
+
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = __uint_as_float(w[i] << 16);
+    f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+}
+
+// ---------------------------------------------------------------- statistics -> scale/shift (+ running stats)
+__global__ void bn_finalize_kernel(const float* __restrict__ sums, double count, const float* __restrict__ bias,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var,
+                                   long long* __restrict__ num_batches_tracked, float momentum, float eps, int c,
+                                   float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
+                                   float* __restrict__ invstd_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0 && num_batches_tracked) num_batches_tracked[0] += 1;
+  if (i >= c) return;
+  const double m = static_cast<double>(sums[i]) / count;
+  double var = static_cast<double>(sums[c + i]) / count - m * m;      // biased variance normalises the batch
+  var = var > 0.0 ? var : 0.0;
+  const float invstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  const float sc = gamma[i] * invstd;
+  scale[i] = sc;
+  shift[i] = beta[i] - static_cast<float>(m) * sc;
+  mean_out[i] = static_cast<float>(m);
+  invstd_out[i] = invstd;
+  if (running_mean) {
+    const float b = bias ? bias[i] : 0.f;                              // the raw conv output excludes the conv bias
+    const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+    running_mean[i] = (1.f - momentum) * running_mean[i] + momentum * (static_cast<float>(m) + b);
+    running_var[i] = (1.f - momentum) * running_var[i] + momentum * static_cast<float>(unbiased);
+  }
+}
+
+// ---------------------------------------------------------------- forward: normalise + LeakyReLU + 2x2 max-pool
+__global__ void __launch_bounds__(256)
+bn_act_pool_fwd_kernel(const uint4* __restrict__ y, int H, int W, int c8, const float* __restrict__ scale,
+                       const float* __restrict__ shift, float slope, __nv_bfloat16* __restrict__ out, int out_cstride,
+                       int out_coffset, long long total) {
+  const int Hp = H >> 1, Wp = W >> 1;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cg = static_cast<int>(idx % c8);
+    long long pix = idx / c8;
+    const int px = static_cast<int>(pix % Wp);
+    pix /= Wp;
+    const int py = static_cast<int>(pix % Hp);
+    const long long n = pix / Hp;
+    float sc[8], sh[8], best[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { sc[i] = __ldg(scale + cg * 8 + i); sh[i] = __ldg(shift + cg * 8 + i); }
+    const long long base = ((n * H + 2 * py) * W + 2 * px) * c8 + cg;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float f[8];
+      unpack8(__ldcs(y + base + ((j >> 1) * W + (j & 1)) * static_cast<long long>(c8)), f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float a = leaky(fmaf(f[i], sc[i], sh[i]), slope);
+        best[i] = j == 0 ? a : fmaxf(best[i], a);
+      }
+    }
+    *reinterpret_cast<uint4*>(out + ((n * Hp + py) * Wp + px) * static_cast<long long>(out_cstride) + out_coffset + cg * 8) =
+        pack8(best);
+  }
+}
+
+// gradient of the activation output for the four positions of one window (8 channels): routes dP to the first maximum
+__device__ __forceinline__ void window_grads(const uint4* __restrict__ y, long long base, int W, int c8,
+                                             const float (&sc)[8], const float (&sh)[8], float slope,
+                                             const float (&dp)[8], float (&yv)[4][8], float (&da)[4][8]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) unpack8(__ldg(y + base + ((j >> 1) * W + (j & 1)) * static_cast<long long>(c8)), yv[j]);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float z[4], a[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { z[j] = fmaf(yv[j][i], sc[i], sh[i]); a[j] = leaky(z[j], slope); }
+    int arg = 0;
+    float best = a[0];
+#pragma unroll
+    for (int j = 1; j < 4; ++j)
+      if (a[j] > best) { best = a[j]; arg = j; }          // strictly greater: the first maximum wins
+#pragma unroll
+    for (int j = 0; j < 4; ++j) da[j][i] = j == arg ? dp[i] * (z[j] > 0.f ? 1.f : slope) : 0.f;
+  }
+}
+
+// ---------------------------------------------------------------- backward pass 1: sum(dA), sum(dA * xhat) per channel
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce_kernel(const uint4* __restrict__ y, const __nv_bfloat16* __restrict__ dp, int dp_cstride, int dp_coffset,
+                     int H, int W, int c8, const float* __restrict__ scale, const float* __restrict__ shift,
+                     const float* __restrict__ mean, const float* __restrict__ invstd, float slope,
+                     float* __restrict__ sums, long long pooled_pixels) {
+  extern __shared__ float red[];                       // [256][16]
+  const int Hp = H >> 1, Wp = W >> 1;
+  const int cg = threadIdx.x % c8;
+  const int slot = threadIdx.x / c8;
+  const int slots = blockDim.x / c8;
+  float sc[8], sh[8], mu[8], is[8], s1[8], s2[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    sc[i] = __ldg(scale + cg * 8 + i); sh[i] = __ldg(shift + cg * 8 + i);
+    mu[i] = __ldg(mean + cg * 8 + i); is[i] = __ldg(invstd + cg * 8 + i);
+    s1[i] = 0.f; s2[i] = 0.f;
+  }
+  for (long long pix = blockIdx.x * static_cast<long long>(slots) + slot; pix < pooled_pixels;
+       pix += static_cast<long long>(gridDim.x) * slots) {
+    const int px = static_cast<int>(pix % Wp);
+    const long long t = pix / Wp;
+    const int py = static_cast<int>(t % Hp);
+    const long long n = t / Hp;
+    float dpv[8], yv[4][8], da[4][8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(dp + pix * dp_cstride + dp_coffset + cg * 8)), dpv);
+    window_grads(y, ((n * H + 2 * py) * W + 2 * px) * c8 + cg, W, c8, sc, sh, slope, dpv, yv, da);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        s1[i] += da[j][i];
+        s2[i] = fmaf(da[j][i], (yv[j][i] - mu[i]) * is[i], s2[i]);
+      }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { red[threadIdx.x * 16 + i] = s1[i]; red[threadIdx.x * 16 + 8 + i] = s2[i]; }
+  __syncthreads();
+  if (slot == 0) {
+    const int c = c8 * 8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float a = 0.f, b = 0.f;
+      for (int s = 0; s < slots; ++s) { a += red[(s * c8 + cg) * 16 + i]; b += red[(s * c8 + cg) * 16 + 8 + i]; }
+      atomicAdd(sums + cg * 8 + i, a);
+      atomicAdd(sums + c + cg * 8 + i, b);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- backward pass 2: dense gradient of the raw conv output
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(const uint4* __restrict__ y, const __nv_bfloat16* __restrict__ dp, int dp_cstride, int dp_coffset,
+                    int H, int W, int c8, const float* __restrict__ scale, const float* __restrict__ shift,
+                    const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ sums,
+                    float inv_count, float slope, uint4* __restrict__ dy, long long total) {
+  const int Hp = H >> 1, Wp = W >> 1;
+  const int c = c8 * 8;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cg = static_cast<int>(idx % c8);
+    const long long pix = idx / c8;
+    const int px = static_cast<int>(pix % Wp);
+    const long long t = pix / Wp;
+    const int py = static_cast<int>(t % Hp);
+    const long long n = t / Hp;
+    float sc[8], sh[8], mu[8], is[8], m1[8], m2[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      sc[i] = __ldg(scale + cg * 8 + i); sh[i] = __ldg(shift + cg * 8 + i);
+      mu[i] = __ldg(mean + cg * 8 + i); is[i] = __ldg(invstd + cg * 8 + i);
+      m1[i] = __ldg(sums + cg * 8 + i) * inv_count;
+      m2[i] = __ldg(sums + c + cg * 8 + i) * inv_count;
+    }
+    float dpv[8], yv[4][8], da[4][8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(dp + pix * dp_cstride + dp_coffset + cg * 8)), dpv);
+    const long long base = ((n * H + 2 * py) * W + 2 * px) * c8 + cg;
+    window_grads(y, base, W, c8, sc, sh, slope, dpv, yv, da);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float g[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float xhat = (yv[j][i] - mu[i]) * is[i];
+        g[i] = sc[i] * (da[j][i] - m1[i] - xhat * m2[i]);     // sc = gamma * invstd
+      }
+      dy[base + ((j >> 1) * W + (j & 1)) * static_cast<long long>(c8)] = pack8(g);
+    }
+  }
+}
+
+inline int grid_for(long long total, int threads) {
+  const long long blocks = (total + threads - 1) / threads;
+  const long long cap = static_cast<long long>(ctk::num_sms()) * 16;
+  return static_cast<int>(blocks < cap ? blocks : cap);
+}
+
+}  // namespace
+
+extern "C" {
+
+int ctk_bn_finalize(const float* sums, double count, const float* bias, const float* gamma, const float* beta,
+                    float* running_mean, float* running_var, long long* num_batches_tracked, float momentum, float eps,
+                    int channels, float* scale, float* shift, float* mean, float* invstd, void* stream) {
+  CTK_REQUIRE(sums && gamma && beta && scale && shift && mean && invstd && channels > 0 && count >= 1.0);
+  CTK_REQUIRE((running_mean == nullptr) == (running_var == nullptr));
+  bn_finalize_kernel<<<(channels + 127) / 128, 128, 0, ctk::as_stream(stream)>>>(
+      sums, count, bias, gamma, beta, running_mean, running_var, num_batches_tracked, momentum, eps, channels, scale,
+      shift, mean, invstd);
+  return ctk::check_launch();
+}
+
+int ctk_bn_act_pool_fwd(const void* y_bf16, int n, int H, int W, int channels, const float* scale, const float* shift,
+                        float slope, void* out_bf16, int out_cstride, int out_coffset, void* stream) {
+  if (n == 0) return CTK_OK;
+  CTK_REQUIRE(y_bf16 && scale && shift && out_bf16 && n > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0);
+  CTK_REQUIRE(channels > 0 && channels % 8 == 0 && out_cstride % 8 == 0 && out_coffset % 8 == 0 &&
+              out_coffset + channels <= out_cstride);
+  const long long total = static_cast<long long>(n) * (H / 2) * (W / 2) * (channels / 8);
+  bn_act_pool_fwd_kernel<<<grid_for(total, 256), 256, 0, ctk::as_stream(stream)>>>(
+      static_cast<const uint4*>(y_bf16), H, W, channels / 8, scale, shift, slope, static_cast<__nv_bfloat16*>(out_bf16),
+      out_cstride, out_coffset, total);
+  return ctk::check_launch();
+}
+
+int ctk_bn_bwd_reduce(const void* y_bf16, const void* dp_bf16, int dp_cstride, int dp_coffset, int n, int H, int W,
+                      int channels, const float* scale, const float* shift, const float* mean, const float* invstd,
+                      float slope, float* sums, void* stream) {
+  if (n == 0) return CTK_OK;
+  CTK_REQUIRE(y_bf16 && dp_bf16 && scale && shift && mean && invstd && sums && n > 0 && H % 2 == 0 && W % 2 == 0);
+  CTK_REQUIRE(channels > 0 && channels % 8 == 0 && channels <= 2048 && 256 % (channels / 8) == 0 &&
+              dp_cstride % 8 == 0 && dp_coffset % 8 == 0 && dp_coffset + channels <= dp_cstride);
+  cudaStream_t s = ctk::as_stream(stream);
+  CTK_CUDA_TRY(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * channels, s));
+  const long long pooled = static_cast<long long>(n) * (H / 2) * (W / 2);
+  const int slots = 256 / (channels / 8);
+  const long long blocks = (pooled + slots - 1) / slots;
+  const int grid = static_cast<int>(blocks < ctk::num_sms() * 8 ? blocks : ctk::num_sms() * 8);
+  bn_bwd_reduce_kernel<<<grid, 256, 256 * 16 * sizeof(float), s>>>(
+      static_cast<const uint4*>(y_bf16), static_cast<const __nv_bfloat16*>(dp_bf16), dp_cstride, dp_coffset, H, W,
+      channels / 8, scale, shift, mean, invstd, slope, sums, pooled);
+  return ctk::check_launch();
+}
+
+int ctk_bn_bwd_apply(const void* y_bf16, const void* dp_bf16, int dp_cstride, int dp_coffset, int n, int H, int W,
+                     int channels, const float* scale, const float* shift, const float* mean, const float* invstd,
+                     const float* sums, float slope, void* dy_bf16, void* stream) {
+  if (n == 0) return CTK_OK;
+  CTK_REQUIRE(y_bf16 && dp_bf16 && scale && shift && mean && invstd && sums && dy_bf16 && n > 0 && H % 2 == 0 &&
+              W % 2 == 0);
+  CTK_REQUIRE(channels > 0 && channels % 8 == 0 && dp_cstride % 8 == 0 && dp_coffset % 8 == 0 &&
+              dp_coffset + channels <= dp_cstride);
+  const long long total = static_cast<long long>(n) * (H / 2) * (W / 2) * (channels / 8);
+  const float inv_count = 1.f / (static_cast<float>(n) * H * W);
+  bn_bwd_apply_kernel<<<grid_for(total, 256), 256, 0, ctk::as_stream(stream)>>>(
+      static_cast<const uint4*>(y_bf16), static_cast<const __nv_bfloat16*>(dp_bf16), dp_cstride, dp_coffset, H, W,
+      channels / 8, scale, shift, mean, invstd, sums, inv_count, slope, static_cast<uint4*>(dy_bf16), total);
+  return ctk::check_launch();
+}
+
+}  // extern "C"

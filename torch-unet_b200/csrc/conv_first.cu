@@ -66,13 +66,19 @@ __device__ __forceinline__ uint64_t umma_smem_desc_nosw(uint32_t smem_addr, uint
   return d;
 }
 
-template <int CIN, int COUT>
+// kTrain = false: folded BN shift + LeakyReLU + 2x2 max-pool, pooled NHWC output (eval mode).
+// kTrain = true : raw conv output (no bias, no BN) stored at full resolution plus per-channel sum / sum of squares
+//                 of the fp32 accumulators into stats[2*COUT] (train-mode BatchNorm needs batch statistics first).
+template <int CIN, int COUT, bool kTrain>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_first_tc_kernel(const float* __restrict__ x, int n_img, int c_total, int c_offset, int H, int W,
                      const float* __restrict__ w_folded, const float* __restrict__ shift, float slope,
                      __nv_bfloat16* __restrict__ out, int out_cstride, int out_coffset, int regions_x, int regions_y,
-                     int total_regions) {
+                     int total_regions, float* __restrict__ stats) {
   using C = FirstCfg<CIN, COUT>;
+  __shared__ float s_stat[kTrain ? 2 * COUT : 1];
+  if constexpr (kTrain)
+    for (int i = threadIdx.x; i < 2 * COUT; i += kThreads) s_stat[i] = 0.f;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* b_smem = smem;
@@ -96,7 +102,7 @@ conv_first_tc_kernel(const float* __restrict__ x, int n_img, int c_total, int c_
     uint32_t word = 0;
     const int ch = kw / 14, j = kw % 14;
     if (kw == 14 * CIN) {
-      word = split_hi_lo(__ldg(shift + n));                               // (shift_hi, shift_lo) against A's (1, 1)
+      word = shift ? split_hi_lo(__ldg(shift + n)) : 0u;                  // (shift_hi, shift_lo) against A's (1, 1)
     } else if (ch < CIN) {
       const float* wr = w_folded + (n * CIN + ch) * 9;
       if (j < 9) {
@@ -237,6 +243,30 @@ conv_first_tc_kernel(const float* __restrict__ x, int n_img, int c_total, int c_
         uint32_t v[32];
         tmem_ld_32x32(tmem_group + (static_cast<uint32_t>(ew * 32) << 16) + s * COUT + cb * 32, v);
         tmem_ld_wait();
+        if constexpr (kTrain) {
+          float f[32], sq[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            f[i] = valid ? __uint_as_float(v[i]) : 0.f;
+            sq[i] = f[i] * f[i];
+          }
+          const float tot = warp_transpose_sum32(f, lane);
+          const float tot2 = warp_transpose_sum32(sq, lane);
+          atomicAdd(&s_stat[cb * 32 + lane], tot);
+          atomicAdd(&s_stat[COUT + cb * 32 + lane], tot2);
+          if (valid) {
+            __nv_bfloat16* dst = out + (static_cast<size_t>(img) * H * W + static_cast<size_t>(y) * W + xg) * out_cstride +
+                                 out_coffset + cb * 32;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              reinterpret_cast<uint4*>(dst)[i] =
+                  make_uint4(pack_bf16x2(__uint_as_float(v[8 * i]), __uint_as_float(v[8 * i + 1])),
+                             pack_bf16x2(__uint_as_float(v[8 * i + 2]), __uint_as_float(v[8 * i + 3])),
+                             pack_bf16x2(__uint_as_float(v[8 * i + 4]), __uint_as_float(v[8 * i + 5])),
+                             pack_bf16x2(__uint_as_float(v[8 * i + 6]), __uint_as_float(v[8 * i + 7])));
+          }
+          continue;
+        }
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
@@ -271,27 +301,30 @@ conv_first_tc_kernel(const float* __restrict__ x, int n_img, int c_total, int c_
   __syncwarp();
   tc_fence_before();
   __syncthreads();
+  if constexpr (kTrain)
+    for (int i = threadIdx.x; i < 2 * COUT; i += kThreads) atomicAdd(stats + i, s_stat[i]);
   if (warp == 0) {
     tc_fence_after();
     tmem_dealloc<1>(tmem_base, kTmemCols);
   }
 }
 
-template <int CIN, int COUT>
+template <int CIN, int COUT, bool kTrain>
 int launch_first(const float* x, int n, int c_total, int c_offset, int H, int W, const float* w_folded,
-                 const float* shift, float slope, __nv_bfloat16* out, int out_cstride, int out_coffset,
+                 const float* shift, float slope, __nv_bfloat16* out, int out_cstride, int out_coffset, float* stats,
                  cudaStream_t stream) {
   using C = FirstCfg<CIN, COUT>;
   const int regions_x = (W + C::kRegionW - 1) / C::kRegionW;
   const int regions_y = (H + kTileH - 1) / kTileH;
   const long long total = static_cast<long long>(n) * regions_x * regions_y;
   if (total >= (1ll << 31)) return CTK_ERR_BAD_ARG;
-  auto kernel = conv_first_tc_kernel<CIN, COUT>;
+  auto kernel = conv_first_tc_kernel<CIN, COUT, kTrain>;
+  if (kTrain) CTK_CUDA_TRY(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * COUT, stream));
   CTK_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
   const int grid = static_cast<int>(std::min<long long>((total + kGroups - 1) / kGroups, ctk::num_sms()));
   kernel<<<grid, kThreads, C::kSmemBytes, stream>>>(x, n, c_total, c_offset, H, W, w_folded, shift, slope, out,
                                                     out_cstride, out_coffset, regions_x, regions_y,
-                                                    static_cast<int>(total));
+                                                    static_cast<int>(total), stats);
   return ctk::check_launch();
 }
 
@@ -307,8 +340,24 @@ extern "C" int ctk_conv_first_eval(const float* x, int n, int c_total, int c_off
   cudaStream_t s = ctk::as_stream(stream);
   __nv_bfloat16* out = static_cast<__nv_bfloat16*>(out_bf16);
   if (cin == 1 && cout == 64)
-    return launch_first<1, 64>(x, n, c_total, c_offset, H, W, w_folded, shift, slope, out, out_cstride, out_coffset, s);
+    return launch_first<1, 64, false>(x, n, c_total, c_offset, H, W, w_folded, shift, slope, out, out_cstride,
+                                      out_coffset, nullptr, s);
   if (cin == 2 && cout == 128)
-    return launch_first<2, 128>(x, n, c_total, c_offset, H, W, w_folded, shift, slope, out, out_cstride, out_coffset, s);
+    return launch_first<2, 128, false>(x, n, c_total, c_offset, H, W, w_folded, shift, slope, out, out_cstride,
+                                       out_coffset, nullptr, s);
+  return CTK_ERR_UNSUPPORTED;
+}
+
+extern "C" int ctk_conv_first_raw(const float* x, int n, int c_total, int c_offset, int cin, int H, int W,
+                                  const float* w, int cout, void* y_bf16, float* stats, void* stream) {
+  if (n == 0) return CTK_OK;
+  CTK_REQUIRE(x && w && y_bf16 && stats && n > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0);
+  CTK_REQUIRE(c_offset >= 0 && c_offset + cin <= c_total && (reinterpret_cast<uintptr_t>(y_bf16) & 15) == 0);
+  cudaStream_t s = ctk::as_stream(stream);
+  __nv_bfloat16* out = static_cast<__nv_bfloat16*>(y_bf16);
+  if (cin == 1 && cout == 64)
+    return launch_first<1, 64, true>(x, n, c_total, c_offset, H, W, w, nullptr, 0.f, out, cout, 0, stats, s);
+  if (cin == 2 && cout == 128)
+    return launch_first<2, 128, true>(x, n, c_total, c_offset, H, W, w, nullptr, 0.f, out, cout, 0, stats, s);
   return CTK_ERR_UNSUPPORTED;
 }

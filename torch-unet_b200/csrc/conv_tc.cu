@@ -49,7 +49,7 @@ struct Cfg {
   static constexpr int kBStageBytes = kBRows * 128;
   static constexpr int kBStages = std::min(12, (200 * 1024 - kAStages * kAStageBytes) / kBStageBytes);
   static constexpr int kTmemCols = kAccStages * kBlockN;
-  static constexpr int kSmemBytes = 1024 + kAStages * kAStageBytes + kBStages * kBStageBytes + 8192;
+  static constexpr int kSmemBytes = 1024 + kAStages * kAStageBytes + kBStages * kBStageBytes + 12288;
 };
 
 struct ConvParams {
@@ -57,8 +57,9 @@ struct ConvParams {
   int tiles_x, tiles_y, tiles_n, spatial_tiles, total_work;
   int pool, act;
   float slope;
-  const float* scale;
+  const float* scale;   // nullptr = identity (raw conv output)
   const float* shift;
+  float* stats;         // nullptr, or [2*cout]: per-channel sum and sum of squares of the raw fp32 accumulators
   __nv_bfloat16* out;
   int out_cstride, out_coffset;
 };
@@ -93,6 +94,8 @@ struct SmemLayout {
   uint32_t pad[3];
   alignas(16) float scale[2][kBlockN];
   alignas(16) float shift[2][kBlockN];
+  float stat_sum[512];      // per-CTA partial statistics (train mode), flushed once at the end
+  float stat_sq[512];
 };
 
 template <int kCtaGroup, int kBlockN>
@@ -101,7 +104,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                   const ConvParams p) {
   using C = Cfg<kCtaGroup, kBlockN>;
   using SL = SmemLayout<kCtaGroup, kBlockN>;
-  static_assert(sizeof(SL) <= 8192, "barrier block too large");
+  static_assert(sizeof(SL) <= 12288, "barrier block too large");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* a_smem = smem;
@@ -124,6 +127,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     tma_prefetch_desc(&tm_b);
   }
   if (warp == 2) tmem_alloc<kCtaGroup>(&sl->tmem_base, C::kTmemCols);
+  if (p.stats != nullptr)
+    for (int i = threadIdx.x; i < 512; i += kThreads) { sl->stat_sum[i] = 0.f; sl->stat_sq[i] = 0.f; }
   tc_fence_before();
   __syncthreads();
   if constexpr (kCtaGroup == 2) cluster_sync_all();   // peer barriers / TMEM must exist before anything remote
@@ -253,8 +258,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       float* s_scale = sl->scale[it & 1];
       float* s_shift = sl->shift[it & 1];
       for (int i = et; i < kBlockN; i += 32 * kEpiWarps) {
-        s_scale[i] = __ldg(p.scale + t.n0 + i);
-        s_shift[i] = __ldg(p.shift + t.n0 + i);
+        s_scale[i] = p.scale ? __ldg(p.scale + t.n0 + i) : 1.f;
+        s_shift[i] = p.scale ? __ldg(p.shift + t.n0 + i) : 0.f;
       }
       asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
       mbar_wait(&sl->acc_full[acc], acc_phase);
@@ -267,6 +272,19 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         uint32_t v[32];
         tmem_ld_32x32(taddr + cb * 32, v);
         tmem_ld_wait();
+        if (p.stats != nullptr) {
+          // train mode: batch statistics of the raw conv output, reduced over this warp's 32 pixels
+          float f[32], sq[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            f[i] = valid ? __uint_as_float(v[i]) : 0.f;
+            sq[i] = f[i] * f[i];
+          }
+          const float tot = warp_transpose_sum32(f, lane);
+          const float tot2 = warp_transpose_sum32(sq, lane);
+          atomicAdd(&sl->stat_sum[t.n0 + cb * 32 + lane], tot);
+          atomicAdd(&sl->stat_sq[t.n0 + cb * 32 + lane], tot2);
+        }
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
@@ -317,6 +335,13 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       if (lane == 0) {
         if constexpr (kCtaGroup == 1) mbar_arrive(&sl->acc_empty[acc]);
         else mbar_arrive_cluster(mapa_shared(smem_u32(&sl->acc_empty[acc]), 0));
+      }
+    }
+    if (p.stats != nullptr) {
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+      for (int i = et; i < p.cout; i += 32 * kEpiWarps) {
+        atomicAdd(p.stats + i, sl->stat_sum[i]);
+        atomicAdd(p.stats + p.cout + i, sl->stat_sq[i]);
       }
     }
   }
@@ -376,13 +401,13 @@ int launch_conv(const void* x_bf16, const void* w_packed_bf16, ConvParams p, cud
 
 }  // namespace
 
-extern "C" int ctk_conv3x3_tc_eval(const void* x_bf16, int n, int H, int W, int cin, const void* w_packed_bf16,
-                                   int cout, const float* scale, const float* shift, float slope, void* out_bf16,
-                                   int out_cstride, int out_coffset, int flags, void* stream) {
+static int conv_dispatch(const void* x_bf16, int n, int H, int W, int cin, const void* w_packed_bf16, int cout,
+                         const float* scale, const float* shift, float* stats, float slope, void* out_bf16,
+                         int out_cstride, int out_coffset, int flags, void* stream) {
   if (n == 0) return CTK_OK;
-  CTK_REQUIRE(x_bf16 && w_packed_bf16 && scale && shift && out_bf16);
+  CTK_REQUIRE(x_bf16 && w_packed_bf16 && out_bf16 && (scale == nullptr) == (shift == nullptr));
   CTK_REQUIRE(n > 0 && H > 0 && W > 0 && H % 2 == 0 && W % kTileW == 0 && cin > 0 && cin % kKC == 0 && cout > 0 &&
-              cout % 128 == 0);
+              cout % 64 == 0 && cout <= 512);
   CTK_REQUIRE(out_coffset >= 0 && out_coffset + cout <= out_cstride && out_cstride % 8 == 0 && out_coffset % 8 == 0);
   CTK_REQUIRE((reinterpret_cast<uintptr_t>(x_bf16) & 15) == 0 && (reinterpret_cast<uintptr_t>(w_packed_bf16) & 15) == 0 &&
               (reinterpret_cast<uintptr_t>(out_bf16) & 15) == 0);
@@ -397,11 +422,27 @@ extern "C" int ctk_conv3x3_tc_eval(const void* x_bf16, int n, int H, int W, int 
   p.pool = (flags & CTK_CONV_NO_POOL) ? 0 : 1;
   p.act = (flags & CTK_CONV_NO_ACT) ? 0 : 1;
   p.slope = slope;
-  p.scale = scale; p.shift = shift;
+  p.scale = scale; p.shift = shift; p.stats = stats;
   p.out = static_cast<__nv_bfloat16*>(out_bf16);
   p.out_cstride = out_cstride; p.out_coffset = out_coffset;
   cudaStream_t s = ctk::as_stream(stream);
-  if (flags & CTK_CONV_SINGLE_CTA) return launch_conv<1, 128>(x_bf16, w_packed_bf16, p, s);
+  if (stats != nullptr) CTK_CUDA_TRY(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * cout, s));
+  if ((flags & CTK_CONV_SINGLE_CTA) && cout % 128 == 0) return launch_conv<1, 128>(x_bf16, w_packed_bf16, p, s);
   if (cout % 256 == 0) return launch_conv<2, 256>(x_bf16, w_packed_bf16, p, s);
-  return launch_conv<2, 128>(x_bf16, w_packed_bf16, p, s);
+  if (cout % 128 == 0) return launch_conv<2, 128>(x_bf16, w_packed_bf16, p, s);
+  return launch_conv<2, 64>(x_bf16, w_packed_bf16, p, s);
+}
+
+extern "C" int ctk_conv3x3_tc_eval(const void* x_bf16, int n, int H, int W, int cin, const void* w_packed_bf16,
+                                   int cout, const float* scale, const float* shift, float slope, void* out_bf16,
+                                   int out_cstride, int out_coffset, int flags, void* stream) {
+  CTK_REQUIRE(scale && shift);
+  return conv_dispatch(x_bf16, n, H, W, cin, w_packed_bf16, cout, scale, shift, nullptr, slope, out_bf16, out_cstride,
+                       out_coffset, flags, stream);
+}
+
+extern "C" int ctk_conv3x3_tc_raw(const void* x_bf16, int n, int H, int W, int cin, const void* w_packed_bf16,
+                                  int cout, void* y_bf16, float* stats, void* stream) {
+  return conv_dispatch(x_bf16, n, H, W, cin, w_packed_bf16, cout, nullptr, nullptr, stats, 0.f, y_bf16, cout, 0,
+                       CTK_CONV_NO_POOL | CTK_CONV_NO_ACT, stream);
 }

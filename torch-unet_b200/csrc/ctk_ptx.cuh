@@ -243,4 +243,50 @@ __device__ __forceinline__ uint32_t leaky_bf16x2(uint32_t v, __nv_bfloat162 slop
   return *reinterpret_cast<const uint32_t*>(&r);
 }
 
+// Sum each of 32 per-lane values across the 32 lanes of a warp: afterwards lane l holds the total of element l.
+// Five butterfly steps; each halves the number of elements a lane still carries (16+8+4+2+1 = 31 shuffles).
+__device__ __forceinline__ float warp_transpose_sum32(const float (&v)[32], int lane) {
+  float a16[16], a8[8], a4[4], a2[2];
+  {
+    const bool up = (lane & 16) != 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float send = up ? v[i] : v[i + 16];
+      const float keep = up ? v[i + 16] : v[i];
+      a16[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+  }
+  {
+    const bool up = (lane & 8) != 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float send = up ? a16[i] : a16[i + 8];
+      const float keep = up ? a16[i + 8] : a16[i];
+      a8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+  }
+  {
+    const bool up = (lane & 4) != 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float send = up ? a8[i] : a8[i + 4];
+      const float keep = up ? a8[i + 4] : a8[i];
+      a4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+  }
+  {
+    const bool up = (lane & 2) != 0;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float send = up ? a4[i] : a4[i + 2];
+      const float keep = up ? a4[i + 2] : a4[i];
+      a2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+  }
+  const bool up = (lane & 1) != 0;
+  const float send = up ? a2[0] : a2[1];
+  const float keep = up ? a2[1] : a2[0];
+  return keep + __shfl_xor_sync(0xffffffffu, send, 1);
+}
+
 }  // namespace ctk

@@ -25,7 +25,7 @@ struct GemmSmem {
 
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_splitk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, int M, int N,
-                   int k_per_split, float* __restrict__ partial) {
+                   int k_per_split, float* __restrict__ partial, __nv_bfloat16* __restrict__ out_bf16) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   GemmSmem* sl = reinterpret_cast<GemmSmem*>(smem + kStages * kStageBytes);
@@ -79,15 +79,26 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
     const int row = m0 + q * 32 + lane;
     mbar_wait(&sl->acc_full, 0);
     tc_fence_after();
-    float* dst = partial + (static_cast<size_t>(split) * M + row) * N + n0;
+    float* dst = partial ? partial + (static_cast<size_t>(split) * M + row) * N + n0 : nullptr;
+    __nv_bfloat16* dst16 = out_bf16 ? out_bf16 + static_cast<size_t>(row) * N + n0 : nullptr;
 #pragma unroll 1
     for (int cb = 0; cb < kBN / 32; ++cb) {
       uint32_t v[32];
       tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + cb * 32, v);
       tmem_ld_wait();
+      if (dst) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        reinterpret_cast<uint4*>(dst + cb * 32)[i] = make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        for (int i = 0; i < 8; ++i)
+          reinterpret_cast<uint4*>(dst + cb * 32)[i] = make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          reinterpret_cast<uint4*>(dst16 + cb * 32)[i] =
+              make_uint4(pack_bf16x2(__uint_as_float(v[8 * i]), __uint_as_float(v[8 * i + 1])),
+                         pack_bf16x2(__uint_as_float(v[8 * i + 2]), __uint_as_float(v[8 * i + 3])),
+                         pack_bf16x2(__uint_as_float(v[8 * i + 4]), __uint_as_float(v[8 * i + 5])),
+                         pack_bf16x2(__uint_as_float(v[8 * i + 6]), __uint_as_float(v[8 * i + 7])));
+      }
     }
   }
   __syncwarp();
@@ -101,12 +112,13 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
 
 }  // namespace
 
-extern "C" int ctk_gemm_bf16_splitk(const void* a_bf16, const void* b_bf16, int M, int N, int K, int splits,
-                                    float* partial, void* stream) {
-  CTK_REQUIRE(a_bf16 && b_bf16 && partial && M > 0 && N > 0 && K > 0 && splits > 0);
-  CTK_REQUIRE(M % kBM == 0 && N % kBN == 0 && K % (kBK * splits) == 0 && splits <= 65535);
+static int gemm_launch(const void* a_bf16, const void* b_bf16, int M, int N, int K, int splits, float* partial,
+                       void* out_bf16, void* stream) {
+  CTK_REQUIRE(a_bf16 && b_bf16 && (partial != nullptr) != (out_bf16 != nullptr) && M > 0 && N > 0 && K > 0 && splits > 0);
+  CTK_REQUIRE(M % kBM == 0 && N % kBN == 0 && K % (kBK * splits) == 0 && splits <= 65535 && N / kBN <= 65535);
+  CTK_REQUIRE(out_bf16 == nullptr || splits == 1);
   CTK_REQUIRE((reinterpret_cast<uintptr_t>(a_bf16) & 15) == 0 && (reinterpret_cast<uintptr_t>(b_bf16) & 15) == 0 &&
-              (reinterpret_cast<uintptr_t>(partial) & 15) == 0);
+              (reinterpret_cast<uintptr_t>(partial) & 15) == 0 && (reinterpret_cast<uintptr_t>(out_bf16) & 15) == 0);
   CUtensorMap tm_a, tm_b;
   const uint32_t box[2] = {kBK, kBM};
   {
@@ -123,6 +135,17 @@ extern "C" int ctk_gemm_bf16_splitk(const void* a_bf16, const void* b_bf16, int 
   }
   CTK_CUDA_TRY(cudaFuncSetAttribute(gemm_splitk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   dim3 grid(M / kBM, N / kBN, splits);
-  gemm_splitk_kernel<<<grid, kThreads, kSmemBytes, ctk::as_stream(stream)>>>(tm_a, tm_b, M, N, K / splits, partial);
+  gemm_splitk_kernel<<<grid, kThreads, kSmemBytes, ctk::as_stream(stream)>>>(
+      tm_a, tm_b, M, N, K / splits, partial, static_cast<__nv_bfloat16*>(out_bf16));
   return ctk::check_launch();
+}
+
+extern "C" int ctk_gemm_bf16_splitk(const void* a_bf16, const void* b_bf16, int M, int N, int K, int splits,
+                                    float* partial, void* stream) {
+  return gemm_launch(a_bf16, b_bf16, M, N, K, splits, partial, nullptr, stream);
+}
+
+extern "C" int ctk_gemm_bf16_out_bf16(const void* a_bf16, const void* b_bf16, int M, int N, int K, void* c_bf16,
+                                      void* stream) {
+  return gemm_launch(a_bf16, b_bf16, M, N, K, 1, nullptr, c_bf16, stream);
 }

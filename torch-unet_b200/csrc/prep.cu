@@ -33,11 +33,59 @@ __global__ void pack_conv_kernel(const float* __restrict__ w, int cout, int cin,
   }
 }
 
+// dgrad operand: out[tap'][ci][co] = w[co][ci][8 - tap']  (weights rotated by 180 degrees, Cin/Cout swapped)
+__global__ void pack_conv_dgrad_kernel(const float* __restrict__ w, int cout, int cin, __nv_bfloat16* __restrict__ out) {
+  const size_t total = static_cast<size_t>(9) * cout * cin;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int co = static_cast<int>(i % cout);
+    const int ci = static_cast<int>((i / cout) % cin);
+    const int tap = static_cast<int>(i / (static_cast<size_t>(cin) * cout));
+    out[i] = __float2bfloat16_rn(w[(static_cast<size_t>(co) * cin + ci) * 9 + (8 - tap)]);
+  }
+}
+
+// out[(c*HW + p)][n] = feat[n][p*cstride + c]   (NHWC activations -> NCHW-flatten rows, batch contiguous, zero padded to ld)
+__global__ void feat_transpose_kernel(const __nv_bfloat16* __restrict__ feat, int n, int hw, int channels,
+                                      __nv_bfloat16* __restrict__ out, int ld) {
+  __shared__ __nv_bfloat16 tile[32][34];
+  const int p = blockIdx.z;
+  const int c0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int nn = n0 + j, c = c0 + threadIdx.x;
+    tile[j][threadIdx.x] = (nn < n && c < channels)
+        ? feat[(static_cast<size_t>(nn) * hw + p) * channels + c] : __float2bfloat16_rn(0.f);
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int c = c0 + j, nn = n0 + threadIdx.x;
+    if (c < channels && nn < ld) out[(static_cast<size_t>(c) * hw + p) * ld + nn] = tile[threadIdx.x][j];
+  }
+}
+
+// w_t[p*C + c][o] = w[o][c*HW + p]  (FC1 weight, NHWC-ordered rows, output features contiguous: K-major B operand of dfeat)
+__global__ void pack_fc1_t_kernel(const float* __restrict__ w, int out_features, int channels, int hw,
+                                  __nv_bfloat16* __restrict__ out) {
+  __shared__ float tile[32][33];
+  const int c = blockIdx.z;
+  const int p0 = blockIdx.x * 32, o0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int o = o0 + j, p = p0 + threadIdx.x;
+    tile[j][threadIdx.x] = (o < out_features && p < hw) ? w[(static_cast<size_t>(o) * channels + c) * hw + p] : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int p = p0 + j, o = o0 + threadIdx.x;
+    if (p < hw && o < out_features)
+      out[(static_cast<size_t>(p) * channels + c) * out_features + o] = __float2bfloat16_rn(tile[threadIdx.x][j]);
+  }
+}
+
 __global__ void pack_first_kernel(const float* __restrict__ w, const float* __restrict__ scale, int cout, int k,
                                   float* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= cout * k) return;
-  out[i] = w[i] * scale[i / k];
+  out[i] = scale ? w[i] * scale[i / k] : w[i];
 }
 
 // out[o][p*C + c] = w[o][c*HW + p]; one block per (row o, 32-pixel x 32-channel tile), transposed through smem
@@ -79,8 +127,33 @@ int ctk_pack_conv_weight_bf16(const float* w, int cout, int cin, void* w_packed_
   return ctk::check_launch();
 }
 
+int ctk_pack_conv_weight_dgrad_bf16(const float* w, int cout, int cin, void* w_packed_bf16, void* stream) {
+  CTK_REQUIRE(w && w_packed_bf16 && cout > 0 && cin > 0);
+  const size_t total = static_cast<size_t>(9) * cout * cin;
+  const int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, 4096));
+  pack_conv_dgrad_kernel<<<blocks, 256, 0, ctk::as_stream(stream)>>>(w, cout, cin,
+                                                                     static_cast<__nv_bfloat16*>(w_packed_bf16));
+  return ctk::check_launch();
+}
+
+int ctk_feat_transpose_bf16(const void* feat_bf16, int n, int hw, int channels, void* out_bf16, int ld, void* stream) {
+  CTK_REQUIRE(feat_bf16 && out_bf16 && n > 0 && hw > 0 && hw <= 65535 && channels > 0 && ld >= n);
+  dim3 grid((channels + 31) / 32, (ld + 31) / 32, hw);
+  feat_transpose_kernel<<<grid, dim3(32, 8), 0, ctk::as_stream(stream)>>>(
+      static_cast<const __nv_bfloat16*>(feat_bf16), n, hw, channels, static_cast<__nv_bfloat16*>(out_bf16), ld);
+  return ctk::check_launch();
+}
+
+int ctk_pack_fc1_weight_t_bf16(const float* w, int out_features, int channels, int hw, void* w_t_bf16, void* stream) {
+  CTK_REQUIRE(w && w_t_bf16 && out_features > 0 && channels > 0 && channels <= 65535 && hw > 0);
+  dim3 grid((hw + 31) / 32, (out_features + 31) / 32, channels);
+  pack_fc1_t_kernel<<<grid, dim3(32, 8), 0, ctk::as_stream(stream)>>>(w, out_features, channels, hw,
+                                                                      static_cast<__nv_bfloat16*>(w_t_bf16));
+  return ctk::check_launch();
+}
+
 int ctk_pack_first_weight(const float* w, const float* scale, int cout, int cin, float* w_folded, void* stream) {
-  CTK_REQUIRE(w && scale && w_folded && cout > 0 && cin > 0);
+  CTK_REQUIRE(w && w_folded && cout > 0 && cin > 0);
   const int total = cout * cin * 9;
   pack_first_kernel<<<(total + 255) / 256, 256, 0, ctk::as_stream(stream)>>>(w, scale, cout, cin * 9, w_folded);
   return ctk::check_launch();

@@ -1,0 +1,313 @@
+// Weight gradient of the 3x3 convolutions on tcgen05 (replaces the wgrad half of aten::convolution_backward for
+// nn.Conv2d at /root/reference/regression_model.py:23 and two_branch_regression.py:16,22,28):
+//   dW[co][ci][ky][kx] = sum_{n,y,x} dY[n,y,x,co] * X[n, y+ky-1, x+kx-1, ci]
+// GEMM view per CTA: D[co (M=128), ci (N<=128)] for the three taps of one kernel row ky, reduced over K = pixels.
+// Both operands are NHWC, i.e. contiguous along their M/N dimension: they are consumed as MN-major 128B-swizzled
+// tiles exactly as TMA lands them (one 128-byte row of 64 channels per pixel, 8-pixel swizzle atoms):
+//   A = dY patch  : 16x8 pixels x 128 co  -> two boxes {64 co, 8, 16}; K atom = one image row of the patch (SBO 1024),
+//                   second 64-co block at LBO = 16 KiB
+//   B = X halo    : 16 rows x 10 columns x nci ci for row offset ky; the three taps kx are three shifted views of
+//                   it (start (2*ks*10 + kx) rows in, SBO = 1280 = one halo row), second ci block at LBO = 20 KiB
+// A CTA owns (co block, ci block, ky, slice) and walks every `slices`-th patch, accumulating 3 x nci fp32 columns in
+// TMEM with no epilogue in between; at the end the accumulators are added to dW (reference layout) with atomics.
+#include "ctk_common.h"
+#include "ctk_ptx.cuh"
+
+#include <algorithm>
+
+namespace {
+
+using namespace ctk;
+
+constexpr int kTileH = 16, kTileW = 8, kHaloW = 10;
+constexpr int kThreads = 192;                 // warp 0 = TMA producer, warp 1 = MMA issuer + TMEM, warps 2-5 = epilogue
+constexpr int kABlockBytes = 128 * 128;       // one 64-channel block of the dY patch
+constexpr int kBBlockBytes = kTileH * kHaloW * 128;   // one 64-channel block of the X halo rows (20480)
+constexpr int kTmemCols = 512;
+
+struct WgradParams {
+  int n_img, H, W, cin, cout, nci;            // nci = ci columns per CTA (64 or 128)
+  int tiles_x, tiles_y, total_tiles;
+  int co_blocks, ci_blocks, slices;
+  float* dw;                                  // [cout][cin][3][3] fp32, pre-zeroed
+};
+
+struct WgradSmem {
+  uint64_t full[4], empty[4], done;
+  uint32_t tmem_base;
+};
+
+// instruction descriptor: bf16 x bf16 -> f32, both operands MN-major
+__host__ __device__ constexpr uint32_t idesc_mn(uint32_t M, uint32_t N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+// MN-major SW128 shared-memory descriptor: LBO = stride between 64-element MN blocks, SBO = stride between 8-row K atoms
+__device__ __forceinline__ uint64_t desc_mn_sw128(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((addr >> 4) & 0x3fff);
+  d |= static_cast<uint64_t>((lbo >> 4) & 0x3fff) << 16;
+  d |= static_cast<uint64_t>((sbo >> 4) & 0x3fff) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+template <int kStages>
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ CUtensorMap tm_x,
+                const WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int b_blocks = p.nci / 64;
+  const int stage_bytes = 2 * kABlockBytes + b_blocks * kBBlockBytes;       // multiple of 1024
+  WgradSmem* sl = reinterpret_cast<WgradSmem*>(smem + kStages * stage_bytes);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // unit decode: blockIdx.x = ((co_blk * ci_blocks + ci_blk) * 3 + ky) * slices + slice
+  int u = blockIdx.x;
+  const int slice = u % p.slices; u /= p.slices;
+  const int ky = u % 3; u /= 3;
+  const int ci_blk = u % p.ci_blocks;
+  const int co_blk = u / p.ci_blocks;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kStages; ++i) { mbar_init(&sl->full[i], 1); mbar_init(&sl->empty[i], 1); }
+    mbar_init(&sl->done, 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&tm_dy);
+    tma_prefetch_desc(&tm_x);
+  }
+  if (warp == 1) tmem_alloc<1>(&sl->tmem_base, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = sl->tmem_base;
+
+  if (warp == 0) {
+    int stage = 0, phase = 0;
+    for (int tile = slice; tile < p.total_tiles; tile += p.slices) {
+      const int tx = tile % p.tiles_x;
+      const int ty = (tile / p.tiles_x) % p.tiles_y;
+      const int img = tile / (p.tiles_x * p.tiles_y);
+      mbar_wait(&sl->empty[stage], phase ^ 1);
+      if (elect_one()) {
+        uint8_t* dst = smem + stage * stage_bytes;
+        mbar_arrive_expect_tx(&sl->full[stage], static_cast<uint32_t>(stage_bytes));
+        for (int b = 0; b < 2; ++b)
+          tma_load_4d(dst + b * kABlockBytes, &tm_dy, &sl->full[stage], co_blk * 128 + b * 64, tx * kTileW,
+                      ty * kTileH, img);
+        for (int b = 0; b < b_blocks; ++b)
+          tma_load_4d(dst + 2 * kABlockBytes + b * kBBlockBytes, &tm_x, &sl->full[stage], ci_blk * p.nci + b * 64,
+                      tx * kTileW - 1, ty * kTileH + ky - 1, img);
+      }
+      __syncwarp();
+      if (++stage == kStages) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = idesc_mn(128, static_cast<uint32_t>(p.nci));
+    const uint64_t adesc0 = desc_mn_sw128(0, kABlockBytes, 1024);
+    const uint64_t bdesc0 = desc_mn_sw128(0, kBBlockBytes, kHaloW * 128);
+    int stage = 0, phase = 0;
+    bool first = true;
+    for (int tile = slice; tile < p.total_tiles; tile += p.slices) {
+      mbar_wait(&sl->full[stage], phase);
+      tc_fence_after();
+      const uint32_t a_base = smem_u32(smem + stage * stage_bytes);
+      const uint32_t b_base = a_base + 2 * kABlockBytes;
+      if (elect_one()) {
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {                       // 16 pixels = image rows 2ks, 2ks+1 of the patch
+            const uint64_t adesc = adesc0 | static_cast<uint64_t>((a_base + ks * 2048) >> 4);
+            const uint64_t bdesc = bdesc0 | static_cast<uint64_t>((b_base + (ks * 2 * kHaloW + kx) * 128) >> 4);
+            umma_bf16(tmem_base + static_cast<uint32_t>(kx * p.nci), adesc, bdesc, idesc, (first && ks == 0) ? 0u : 1u);
+          }
+        }
+        umma_commit(&sl->empty[stage]);
+      }
+      __syncwarp();
+      first = false;
+      if (++stage == kStages) { stage = 0; phase ^= 1; }
+    }
+    if (elect_one()) umma_commit(&sl->done);
+    __syncwarp();
+  } else {
+    // epilogue: lane quadrant q of TMEM = co rows q*32 .. q*32+31 of this CTA's co block
+    const int q = warp & 3;
+    const int co = co_blk * 128 + q * 32 + lane;
+    const bool any = slice < p.total_tiles;
+    if (any) {
+      mbar_wait(&sl->done, 0);
+      tc_fence_after();
+      for (int kx = 0; kx < 3; ++kx) {
+        for (int cb = 0; cb < p.nci / 32; ++cb) {
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + kx * p.nci + cb * 32, v);
+          tmem_ld_wait();
+          float* dst = p.dw + (static_cast<size_t>(co) * p.cin + ci_blk * p.nci + cb * 32) * 9 + ky * 3 + kx;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) atomicAdd(dst + i * 9, __uint_as_float(v[i]));
+        }
+      }
+    }
+  }
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<1>(tmem_base, kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// First layer (Cin = 1 or 2): K = pixels, N = 9*Cin is too narrow for the tensor cores -> fp32 CUDA-core reduction.
+// dW[co][ci][tap] = sum dY[n,y,x,co] * x[n,ci,y+ky-1,x+kx-1];  x is the fp32 NCHW input, dY is bf16 NHWC.
+// Persistent blocks; thread = (4 output channels, pixel slot); the input window is staged in shared memory.
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(256)
+wgrad_first_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x, int n_img, int c_total,
+                   int c_offset, int H, int W, float* __restrict__ dw) {
+  constexpr int G = COUT / 4;                  // channel groups
+  constexpr int SLOTS = 256 / G;               // pixels processed concurrently
+  constexpr int TW = 32, TH = 8;               // pixel tile per iteration
+  __shared__ float s_in[CIN][TH + 2][TW + 2 + 1];
+  __shared__ float s_red[256];
+  const int cg = threadIdx.x % G, slot = threadIdx.x / G;
+  float acc[4][CIN * 9];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int k = 0; k < CIN * 9; ++k) acc[j][k] = 0.f;
+  const int tiles_x = (W + TW - 1) / TW, tiles_y = (H + TH - 1) / TH;
+  const long long total = static_cast<long long>(n_img) * tiles_x * tiles_y;
+  for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    const int tx = static_cast<int>(tile % tiles_x);
+    const int ty = static_cast<int>((tile / tiles_x) % tiles_y);
+    const int img = static_cast<int>(tile / (static_cast<long long>(tiles_x) * tiles_y));
+    __syncthreads();
+    for (int c = 0; c < CIN; ++c) {
+      const float* plane = x + (static_cast<size_t>(img) * c_total + c_offset + c) * H * W;
+      for (int i = threadIdx.x; i < (TH + 2) * (TW + 2); i += 256) {
+        const int r = i / (TW + 2), q = i % (TW + 2);
+        const int gy = ty * TH - 1 + r, gx = tx * TW - 1 + q;
+        s_in[c][r][q] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? __ldg(plane + static_cast<size_t>(gy) * W + gx) : 0.f;
+      }
+    }
+    __syncthreads();
+    for (int pix = slot; pix < TW * TH; pix += SLOTS) {
+      const int py = pix / TW, px = pix % TW;
+      const int gy = ty * TH + py, gx = tx * TW + px;
+      if (gy >= H || gx >= W) continue;
+      const uint2 raw = __ldg(reinterpret_cast<const uint2*>(
+          dy + ((static_cast<size_t>(img) * H + gy) * W + gx) * COUT + cg * 4));
+      const float g[4] = {__uint_as_float(raw.x << 16), __uint_as_float(raw.x & 0xffff0000u),
+                          __uint_as_float(raw.y << 16), __uint_as_float(raw.y & 0xffff0000u)};
+#pragma unroll
+      for (int c = 0; c < CIN; ++c)
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            const float xv = s_in[c][py + ky][px + kx];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[j][c * 9 + ky * 3 + kx] = fmaf(g[j], xv, acc[j][c * 9 + ky * 3 + kx]);
+          }
+    }
+  }
+  // reduce the SLOTS partial sums of every (channel, tap) through shared memory, one (j, k) plane at a time
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int k = 0; k < CIN * 9; ++k) {
+      __syncthreads();
+      s_red[threadIdx.x] = acc[j][k];
+      __syncthreads();
+      if (slot == 0) {
+        float s = 0.f;
+        for (int t = 0; t < SLOTS; ++t) s += s_red[t * G + cg];
+        atomicAdd(dw + (cg * 4 + j) * (CIN * 9) + k, s);
+      }
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int ctk_conv3x3_wgrad_tc(const void* dy_bf16, const void* x_bf16, int n, int H, int W, int cin, int cout, float* dw,
+                         void* stream) {
+  if (n == 0) return CTK_OK;
+  CTK_REQUIRE(dy_bf16 && x_bf16 && dw && n > 0 && H > 0 && W > 0 && W % kTileW == 0 && cin % 64 == 0 && cout % 128 == 0);
+  CTK_REQUIRE((reinterpret_cast<uintptr_t>(dy_bf16) & 15) == 0 && (reinterpret_cast<uintptr_t>(x_bf16) & 15) == 0);
+  cudaStream_t s = ctk::as_stream(stream);
+  CTK_CUDA_TRY(cudaMemsetAsync(dw, 0, sizeof(float) * 9 * cin * cout, s));
+  WgradParams p = {};
+  p.n_img = n; p.H = H; p.W = W; p.cin = cin; p.cout = cout;
+  p.nci = cin % 128 == 0 ? 128 : 64;
+  p.tiles_x = W / kTileW;
+  p.tiles_y = (H + kTileH - 1) / kTileH;
+  const long long tiles = static_cast<long long>(n) * p.tiles_x * p.tiles_y;
+  CTK_REQUIRE(tiles < (1ll << 30));
+  p.total_tiles = static_cast<int>(tiles);
+  p.co_blocks = cout / 128;
+  p.ci_blocks = cin / p.nci;
+  const int units = p.co_blocks * p.ci_blocks * 3;
+  p.slices = std::max(1, std::min(p.total_tiles, (2 * ctk::num_sms()) / units));
+  p.dw = dw;
+
+  CUtensorMap tm_dy, tm_x;
+  {
+    const uint64_t dims[4] = {static_cast<uint64_t>(cout), static_cast<uint64_t>(W), static_cast<uint64_t>(H),
+                              static_cast<uint64_t>(n)};
+    const uint64_t strides[3] = {static_cast<uint64_t>(cout) * 2, static_cast<uint64_t>(W) * cout * 2,
+                                 static_cast<uint64_t>(H) * W * cout * 2};
+    const uint32_t box[4] = {64, kTileW, kTileH, 1};
+    int st = ctk::encode_tmap_bf16_sw128(&tm_dy, dy_bf16, 4, dims, strides, box);
+    if (st != CTK_OK) return st;
+  }
+  {
+    const uint64_t dims[4] = {static_cast<uint64_t>(cin), static_cast<uint64_t>(W), static_cast<uint64_t>(H),
+                              static_cast<uint64_t>(n)};
+    const uint64_t strides[3] = {static_cast<uint64_t>(cin) * 2, static_cast<uint64_t>(W) * cin * 2,
+                                 static_cast<uint64_t>(H) * W * cin * 2};
+    const uint32_t box[4] = {64, kHaloW, kTileH, 1};
+    int st = ctk::encode_tmap_bf16_sw128(&tm_x, x_bf16, 4, dims, strides, box);
+    if (st != CTK_OK) return st;
+  }
+  const int stage_bytes = 2 * kABlockBytes + (p.nci / 64) * kBBlockBytes;
+  const int grid = units * p.slices;
+  if (p.nci == 128) {
+    constexpr int kStages = 2;
+    const int smem_bytes = 1024 + kStages * stage_bytes + 256;
+    CTK_CUDA_TRY(cudaFuncSetAttribute(wgrad_tc_kernel<kStages>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    wgrad_tc_kernel<kStages><<<grid, kThreads, smem_bytes, s>>>(tm_dy, tm_x, p);
+  } else {
+    constexpr int kStages = 3;
+    const int smem_bytes = 1024 + kStages * stage_bytes + 256;
+    CTK_CUDA_TRY(cudaFuncSetAttribute(wgrad_tc_kernel<kStages>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    wgrad_tc_kernel<kStages><<<grid, kThreads, smem_bytes, s>>>(tm_dy, tm_x, p);
+  }
+  return ctk::check_launch();
+}
+
+int ctk_conv_first_wgrad(const void* dy_bf16, const float* x, int n, int c_total, int c_offset, int cin, int H, int W,
+                         int cout, float* dw, void* stream) {
+  if (n == 0) return CTK_OK;
+  CTK_REQUIRE(dy_bf16 && x && dw && n > 0 && H > 0 && W > 0 && c_offset >= 0 && c_offset + cin <= c_total);
+  cudaStream_t s = ctk::as_stream(stream);
+  CTK_CUDA_TRY(cudaMemsetAsync(dw, 0, sizeof(float) * 9 * cin * cout, s));
+  const int grid = ctk::num_sms() * 4;
+  const __nv_bfloat16* dy = static_cast<const __nv_bfloat16*>(dy_bf16);
+  if (cin == 1 && cout == 64) {
+    wgrad_first_kernel<1, 64><<<grid, 256, 0, s>>>(dy, x, n, c_total, c_offset, H, W, dw);
+  } else if (cin == 2 && cout == 128) {
+    wgrad_first_kernel<2, 128><<<grid, 256, 0, s>>>(dy, x, n, c_total, c_offset, H, W, dw);
+  } else {
+    return CTK_ERR_UNSUPPORTED;
+  }
+  return ctk::check_launch();
+}
+
+}  // extern "C"
