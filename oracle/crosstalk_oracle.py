@@ -145,6 +145,57 @@ def calibrate_bn(kind: str, sd: Dict[str, torch.Tensor], x: torch.Tensor) -> Dic
 
 
 # --------------------------------------------------------------------------
+# optional bf16-rounding restatement of the GPU path (precision model, not the reference)
+# --------------------------------------------------------------------------
+# The CUDA path keeps conv operands (weights of blocks 2+, block inputs/outputs, FC1 operands and the gradients that
+# flow between blocks) in bf16 and accumulates in fp32.  With EMULATE_BF16 = True the same roundings are applied here,
+# everything else staying fp32, so tests can separate "kernel is wrong" from "bf16 operands lose this much".
+EMULATE_BF16 = False
+
+
+class _RoundBoth(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return x.to(torch.bfloat16).float()
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.bfloat16).float()
+
+
+class _RoundFwd(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return x.to(torch.bfloat16).float()
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+class _RoundBwd(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.bfloat16).float()
+
+
+class emulate_bf16:
+    """Context manager: ``with orc.emulate_bf16(): ...`` runs the forward/backward with the GPU path's roundings."""
+
+    def __enter__(self):
+        global EMULATE_BF16
+        self.old, EMULATE_BF16 = EMULATE_BF16, True
+
+    def __exit__(self, *a):
+        global EMULATE_BF16
+        EMULATE_BF16 = self.old
+
+
+# --------------------------------------------------------------------------
 # forward passes
 # --------------------------------------------------------------------------
 def _batch_norm(sd, key, x, training, update_stats):
@@ -163,12 +214,19 @@ def _conv_block(sd, prefix, idx, x, training=False, update_stats=False, taps=Non
 
     regression_model.py:14-17,23-26 / two_branch_regression.py:10-13,...
     """
-    y = F.conv2d(x, sd[f"{prefix}.{idx}.weight"], sd[f"{prefix}.{idx}.bias"], stride=1, padding=1)
+    w = sd[f"{prefix}.{idx}.weight"]
+    if EMULATE_BF16 and idx != 0:            # the first block runs split-bf16 (fp32-class) on the GPU
+        w = _RoundFwd.apply(w)
+    y = F.conv2d(x, w, sd[f"{prefix}.{idx}.bias"], stride=1, padding=1)
+    if EMULATE_BF16 and training:            # train mode stores the raw conv output in bf16
+        y = _RoundBoth.apply(y)
     if taps is not None:
         taps[f"{prefix}.{idx}.conv"] = y
     y = _batch_norm(sd, f"{prefix}.{idx + 1}", y, training, update_stats)
     y = F.leaky_relu(y, LEAKY_SLOPE)
     y = F.max_pool2d(y, kernel_size=2, stride=2)
+    if EMULATE_BF16:
+        y = _RoundBoth.apply(y)
     if taps is not None:
         taps[f"{prefix}.{idx}.pool"] = y
     return y
@@ -183,7 +241,12 @@ def _head(sd, prefix, x, training, update_stats, dropout_p, dropout_masks, taps)
     """
     x = torch.flatten(x, 1)                       # NCHW order: c*H*W + h*W + w
     for j, idx in enumerate((1, 5)):
-        x = F.linear(x, sd[f"{prefix}.{idx}.weight"], sd[f"{prefix}.{idx}.bias"])
+        w = sd[f"{prefix}.{idx}.weight"]
+        if EMULATE_BF16 and idx == 1:
+            w = _RoundFwd.apply(w)
+        x = F.linear(x, w, sd[f"{prefix}.{idx}.bias"])
+        if EMULATE_BF16 and idx == 1:
+            x = _RoundBwd.apply(x)           # dZ1 feeds the FC1 backward GEMMs as bf16
         if taps is not None:
             taps[f"{prefix}.{idx}.fc"] = x
         x = _batch_norm(sd, f"{prefix}.{idx + 1}", x, training, update_stats)

@@ -1,0 +1,140 @@
+"""End-to-end training parity on the GPU: train-mode forward, loss, every parameter gradient, BatchNorm running
+statistics and a short Adam loss curve against the CPU oracle (which is pinned to the reference's own train-mode
+outputs / gradient norms / losses by tests/test_oracle_golden.py).
+
+Tolerances.  The GPU path rounds conv / FC1 operands and the activations / gradients stored between blocks to bf16
+(fp32 accumulation).  On these random, untrained weights with BatchNorm statistics over 8 tiles that rounding alone
+moves per-tensor gradients by 3-30 % (relative L2): ``orc.emulate_bf16()`` applies the same roundings to the fp32
+oracle on the CPU and lands at the same distance from fp32, tensor by tensor.  The kernels themselves are held to
+tight bounds in test_gpu_train_kernels.py; here the end-to-end bound is therefore "no worse than the bf16 rounding
+model": err(gpu, fp32) <= 1.6 * err(bf16-emulation, fp32) + 2e-2 per tensor, and the step-0 loss within 1 % (double)
+/ 5 % (single) of the fp32 oracle.
+"""
+import numpy as np
+import pytest
+import torch
+
+import crosstalk_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+GRAD_SLACK, GRAD_FLOOR = 1.6, 2e-2
+# north_star loss bound (1 %) holds for the sigmoid-bounded double-branch model; the single-branch model with random
+# weights and batch statistics over 8 tiles amplifies bf16 operand rounding (see DESIGN.md "Precision")
+LOSS_REL = {"double": 1e-2, "single": 5e-2}
+
+
+import os
+
+
+def _data(golden, n_syn=int(os.environ.get("CTK_TEST_NSYN", "3"))):
+    tiles = golden["tiles"]
+    xn = np.stack([np.stack([orc.normalize_image(t[0]), orc.normalize_image(t[1])]) for t in tiles])
+    xs, ys = orc.synthetic_batch(n_syn, seed=99)
+    x = torch.cat([torch.from_numpy(xn), xs], dim=0)
+    y = torch.cat([torch.from_numpy(golden["labels_np"])[:, None], ys], dim=0)
+    return x, y
+
+
+def _build(kind):
+    import ctk
+    torch.manual_seed(0)
+    if kind == "single":
+        return ctk.AdvancedRegressionModel(initial_filters=128, num_conv_blocks=6)
+    return ctk.SimplifiedTwoBranchRegressionModel(initial_filters_per_branch=64)
+
+
+@pytest.mark.parametrize("kind", ["single", "double"])
+def test_forward_loss_and_gradients_match_oracle(golden, kind):
+    import ctk
+    x, y = _data(golden)
+    n = x.shape[0]
+    model = _build(kind)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    p_drop = 0.1 if kind == "single" else 0.5
+    masks = orc.dropout_masks(n, p_drop, seed=5)
+    with orc.emulate_bf16():
+        loss_emu, out_emu, grads_emu = orc.loss_and_grads(kind, {k: v.clone() for k, v in sd.items()}, x, y,
+                                                          dropout_masks=masks, update_stats=False)
+    loss_ref, out_ref, grads_ref = orc.loss_and_grads(kind, sd, x, y, dropout_masks=masks, update_stats=True)
+
+    model = model.cuda().train()
+    eng = ctk.models.get_train_engine(model)
+    eng.forced_masks = tuple(m.cuda() for m in masks)
+    out = model(x.cuda())
+    loss = torch.nn.functional.mse_loss(out, y.cuda())          # the reference's criterion (train_model.py:636)
+    loss.backward()
+    torch.cuda.synchronize()
+    print(kind, "train out max err", (out.detach().cpu() - out_ref).abs().max().item(), "loss", loss.item(), float(loss_ref),
+          "| vs bf16 emulation: out err", (out.detach().cpu() - out_emu).abs().max().item(), "loss", float(loss_emu))
+    assert abs(loss.item() - float(loss_ref)) <= LOSS_REL[kind] * abs(float(loss_ref))
+    worst = 0.0
+    bad = []
+    for name, p in model.named_parameters():
+        g, r = p.grad.detach().cpu(), grads_ref[name]
+        assert g.shape == r.shape, name
+        if name.endswith("bias") and r.norm().item() < 1e-6 * (1 + p.detach().norm().item()):
+            # biases in front of a train-mode BatchNorm: the exact gradient is 0 (autograd leaves ~1e-9 of noise)
+            assert g.abs().max().item() <= 1e-5, name
+            continue
+        rel = ((g - r).norm() / (r.norm() + 1e-30)).item()
+        e = grads_emu[name]
+        rel_emu = ((g - e).norm() / (e.norm() + 1e-30)).item()
+        emu_vs_ref = ((e - r).norm() / (r.norm() + 1e-30)).item()
+        worst = max(worst, rel)
+        print(f"  {name:45s} rel L2 {rel:.3e}  |ref| {r.norm().item():.3e}   gpu-vs-bf16emu {rel_emu:.3e}  emu-vs-fp32 {emu_vs_ref:.3e}")
+        if rel > GRAD_SLACK * emu_vs_ref + GRAD_FLOOR:
+            bad.append((name, rel, emu_vs_ref))
+    print(kind, "worst gradient rel L2", worst)
+    assert not bad, bad
+    # BatchNorm running statistics were advanced exactly once, like nn.BatchNorm in train()
+    msd = model.state_dict()
+    for k, v in sd.items():
+        if k.endswith("running_mean") or k.endswith("running_var"):
+            np.testing.assert_allclose(msd[k].cpu().numpy(), v.numpy(), rtol=2e-2, atol=2e-3, err_msg=k)
+        if k.endswith("num_batches_tracked"):
+            assert int(msd[k]) == int(v), k
+
+
+@pytest.mark.parametrize("kind", ["double", "single"])
+def test_short_adam_loss_curve_matches_oracle(golden, kind):
+    import ctk
+    x, y = _data(golden)
+    n = x.shape[0]
+    steps = 6
+    model = _build(kind)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    p_drop = 0.1 if kind == "single" else 0.5
+    masks = [orc.dropout_masks(n, p_drop, seed=100 + t) for t in range(steps)]
+    tr = orc.OracleTrainer(kind, {k: v.clone() for k, v in sd.items()}, lr=5e-4, weight_decay=1e-4)
+    ref_losses = [tr.step(x, y, dropout_masks=masks[t])[0] for t in range(steps)]
+    with orc.emulate_bf16():
+        tre = orc.OracleTrainer(kind, {k: v.clone() for k, v in sd.items()}, lr=5e-4, weight_decay=1e-4)
+        emu_losses = [tre.step(x, y, dropout_masks=masks[t])[0] for t in range(steps)]
+
+    model = model.cuda().train()
+    eng = ctk.models.get_train_engine(model)
+    opt = ctk.Adam(model.parameters(), lr=5e-4, weight_decay=1e-4)            # train_model.py:637
+    crit = torch.nn.MSELoss()
+    xd, yd = x.cuda(), y.cuda()
+    losses = []
+    for t in range(steps):
+        eng.forced_masks = tuple(m.cuda() for m in masks[t])
+        opt.zero_grad()
+        out = model(xd)
+        loss = crit(out, yd)
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    print(kind, "gpu", [f"{v:.5f}" for v in losses])
+    print(kind, "ref", [f"{v:.5f}" for v in ref_losses])
+    print(kind, "emu", [f"{v:.5f}" for v in emu_losses])
+    rel = [abs(a - b) / abs(b) for a, b in zip(losses, ref_losses)]
+    rel_emu = [abs(a - b) / abs(b) for a, b in zip(emu_losses, ref_losses)]
+    print(kind, "rel gpu-vs-fp32", [f"{v:.4f}" for v in rel])
+    print(kind, "rel emu-vs-fp32", [f"{v:.4f}" for v in rel_emu])
+    assert rel[0] <= LOSS_REL[kind]
+    # a bf16 trajectory on 8 tiles drifts chaotically from the fp32 one; the GPU must not drift more than the CPU
+    # bf16-rounding model of the same path does
+    assert max(rel) <= 2.5 * max(rel_emu) + 0.05
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0]

@@ -44,11 +44,25 @@ def get_engine(model) -> InferenceEngine:
     return eng
 
 
+def get_train_engine(model):
+    """The (lazily created) libctk training engine bound to ``model``."""
+    from .train import TrainEngine
+    eng = model.__dict__.get("_ctk_train_engine")
+    if eng is None:
+        eng = TrainEngine(model)
+        model.__dict__["_ctk_train_engine"] = eng
+    return eng
+
+
 def _ctk_forward(self, x):
-    """forward() shared by the mirrored classes and by accelerate()d reference instances."""
+    """forward() shared by the mirrored classes and by accelerate()d reference instances.
+
+    train(): batch-statistics BatchNorm, Dropout, and an autograd edge whose backward runs the ctk dgrad / wgrad /
+    BN-backward kernels.  eval(): folded-BN inference path.
+    """
     if self.training:
-        raise _lib.CtkError("the ctk training path (train-mode BN, backward) is not built yet; "
-                            "call model.eval() and run under torch.no_grad()")
+        from .train import train_forward
+        return train_forward(get_train_engine(self), x)
     return get_engine(self).forward(x)
 
 

@@ -1,0 +1,312 @@
+"""Train-mode forward and backward of both reference models through libctk.
+
+``TrainEngine.forward`` runs conv (raw + batch statistics) -> BN finalise -> normalise/LeakyReLU/pool per block, the
+FC1 split-K GEMM and the small fp32 head; ``TrainEngine.backward`` walks the same graph in reverse with the dedicated
+kernels (BN backward reduce/apply, tcgen05 dgrad and wgrad, FC1 dX/dW GEMMs).  ``_CtkTrainFunction`` plugs the pair into
+``torch.autograd`` so the reference loop (train_model.py:419-424: zero_grad / model(x) / criterion / backward / step)
+runs unchanged; PyTorch only owns the tensors and the graph edge.
+"""
+from __future__ import annotations
+
+from ctypes import c_double, c_float, c_int, c_longlong
+from typing import Callable, Dict, List, Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import call, ptr, stream
+from .engine import LEAKY_SLOPE, _Branch, _conv_bn_pairs, _head_layers
+
+
+def _pad(n: int, m: int) -> int:
+    return (n + m - 1) // m * m
+
+
+class TrainEngine:
+    def __init__(self, model: torch.nn.Module):
+        self.model = model
+        if hasattr(model, "conv_layers") and hasattr(model, "fc_layers"):
+            self.kind = "single"
+            self.branches = [_Branch(_conv_bn_pairs(model.conv_layers), 0)]
+            seq = model.fc_layers
+            self.sigmoid_half = 0
+        elif hasattr(model, "bleed_branch") and hasattr(model, "source_branch"):
+            self.kind = "double"
+            self.branches = [_Branch(_conv_bn_pairs(model.bleed_branch.conv_blocks), 0),
+                             _Branch(_conv_bn_pairs(model.source_branch.conv_blocks), 1)]
+            seq = model.regression_head.fc_layers
+            self.sigmoid_half = 1
+        else:
+            raise _lib.CtkError(f"{type(model).__name__} is not one of the two crosstalk regression models")
+        self.lin, self.bns = _head_layers(seq)
+        self.drop_p = [m.p for m in seq if isinstance(m, torch.nn.Dropout)]
+        if len(self.drop_p) != 2:
+            raise _lib.CtkError("head layout differs from the reference (2 Dropout layers expected)")
+        self.feat_channels = sum(b.channels[-1] for b in self.branches)
+        self.params: List[torch.nn.Parameter] = list(model.parameters())
+        self.forced_masks: Optional[Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]] = None
+        self.on_grad_ready: Optional[Callable[[torch.nn.Parameter, torch.Tensor], None]] = None
+        self._saved: Optional[dict] = None
+
+    # ------------------------------------------------------------------ helpers
+    @staticmethod
+    def _new(shape, dtype, dev):
+        return torch.empty(shape, device=dev, dtype=dtype)
+
+    def _bn_finalize(self, sums, count, bias, bn, dev):
+        c = bn.num_features
+        scale, shift, mean, invstd = (self._new((c,), torch.float32, dev) for _ in range(4))
+        mom = 0.1 if bn.momentum is None else bn.momentum
+        track = bn.track_running_stats and bn.running_mean is not None
+        call("ctk_bn_finalize", ptr(sums), c_double(count), ptr(bias), ptr(bn.weight), ptr(bn.bias),
+             ptr(bn.running_mean if track else None), ptr(bn.running_var if track else None),
+             ptr(bn.num_batches_tracked if track else None), c_float(mom), c_float(bn.eps), c_int(c), ptr(scale), ptr(shift),
+             ptr(mean), ptr(invstd), stream())
+        return scale, shift, mean, invstd
+
+    def _colsum(self, t, n, f):
+        st = self._new((2 * f,), torch.float32, t.device)
+        call("ctk_colstat", ptr(t), c_int(1), c_longlong(0), c_int(f), ptr(None), c_int(n), c_int(f), ptr(None), ptr(st), stream())
+        return st[:f]
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        _lib.require_device(x, torch.float32, "input batch")
+        if x.dim() != 4 or x.shape[1] != 2 or x.shape[2] % 32 or x.shape[3] % 32:
+            raise _lib.CtkError(f"input must be [N,2,H,W] float32 with H, W multiples of 32, got {tuple(x.shape)}")
+        call("ctk_device_check")
+        for p in self.params:
+            _lib.require_device(p, torch.float32, "parameter")
+        n, c_total, H, W = x.shape
+        dev = x.device
+        depth = len(self.branches[0].pairs)
+        hf, wf = H >> depth, W >> depth
+        fc1, fc2, fc3 = self.lin
+        K = fc1.in_features
+        if K != hf * wf * self.feat_channels:
+            raise _lib.CtkError("input size does not match the model's first Linear layer")
+        m_pad = _pad(n, 128)
+        sv = {"x": x, "n": n, "H": H, "W": W, "m_pad": m_pad, "blocks": []}
+        feat = torch.zeros((m_pad, hf, wf, self.feat_channels), device=dev, dtype=torch.bfloat16)
+        c_off = 0
+        for br in self.branches:
+            h, w = H, W
+            cur = None
+            blocks = []
+            for li, (conv, bn) in enumerate(br.pairs):
+                cout, cin = conv.out_channels, conv.in_channels
+                y = self._new((n, h, w, cout), torch.bfloat16, dev)
+                stats = self._new((2 * cout,), torch.float32, dev)
+                if li == 0:
+                    call("ctk_conv_first_raw", ptr(x), c_int(n), c_int(c_total), c_int(br.c_offset), c_int(cin), c_int(h),
+                         c_int(w), ptr(conv.weight), c_int(cout), ptr(y), ptr(stats), stream())
+                else:
+                    wp = self._new((9, cout, cin), torch.bfloat16, dev)
+                    call("ctk_pack_conv_weight_bf16", ptr(conv.weight), c_int(cout), c_int(cin), ptr(wp), stream())
+                    call("ctk_conv3x3_tc_raw", ptr(cur), c_int(n), c_int(h), c_int(w), c_int(cin), ptr(wp), c_int(cout),
+                         ptr(y), ptr(stats), stream(), meta={"flops": 2.0 * n * h * w * cout * 9 * cin})
+                scale, shift, mean, invstd = self._bn_finalize(stats, float(n) * h * w, conv.bias, bn, dev)
+                last = li == len(br.pairs) - 1
+                if last:
+                    dst, cstride, coff = feat, self.feat_channels, c_off
+                else:
+                    dst, cstride, coff = self._new((n, h // 2, w // 2, cout), torch.bfloat16, dev), cout, 0
+                call("ctk_bn_act_pool_fwd", ptr(y), c_int(n), c_int(h), c_int(w), c_int(cout), ptr(scale), ptr(shift),
+                     c_float(LEAKY_SLOPE), ptr(dst), c_int(cstride), c_int(coff), stream())
+                blocks.append({"y": y, "x_in": cur, "scale": scale, "shift": shift, "mean": mean, "invstd": invstd,
+                               "h": h, "w": w, "conv": conv, "bn": bn})
+                cur = dst
+                h, w = h // 2, w // 2
+            sv["blocks"].append({"branch": br, "blocks": blocks, "c_off": c_off})
+            c_off += br.channels[-1]
+        sv["feat"], sv["hf"], sv["wf"] = feat, hf, wf
+
+        # ---- FC1 (tcgen05 split-K) + fp32 head
+        f1, f2 = fc1.out_features, fc2.out_features
+        hw = hf * wf
+        w1p = self._new((f1, K), torch.bfloat16, dev)
+        call("ctk_pack_fc1_weight_bf16", ptr(fc1.weight), c_int(f1), c_int(self.feat_channels), c_int(hw), ptr(w1p), stream())
+        tiles = (m_pad // 128) * (f1 // 128)
+        splits = 1
+        while splits * 2 * tiles <= 160 and (K // 64) % (splits * 2) == 0 and K // (splits * 2) >= 512:
+            splits *= 2
+        partial = self._new((splits, m_pad, f1), torch.float32, dev)
+        call("ctk_gemm_bf16_splitk", ptr(feat), ptr(w1p), c_int(m_pad), c_int(f1), c_int(K), c_int(splits), ptr(partial),
+             stream(), meta={"flops": 2.0 * m_pad * f1 * K})
+        z1 = self._new((n, f1), torch.float32, dev)
+        st1 = self._new((2 * f1,), torch.float32, dev)
+        call("ctk_colstat", ptr(partial), c_int(splits), c_longlong(m_pad * f1), c_int(f1), ptr(fc1.bias), c_int(n), c_int(f1),
+             ptr(z1), ptr(st1), stream())
+        bn1 = self._bn_finalize(st1, float(n), None, self.bns[0], dev)
+        masks = self._masks(n, f1, f2, dev)
+        a1 = self._new((n, f1), torch.float32, dev)
+        call("ctk_bn1d_act_drop_fwd", ptr(z1), ptr(bn1[0]), ptr(bn1[1]), ptr(masks[0]), c_float(self.drop_p[0]),
+             c_float(LEAKY_SLOPE), c_int(n), c_int(f1), ptr(a1), stream())
+        z2 = self._new((n, f2), torch.float32, dev)
+        call("ctk_sgemm_strided", ptr(a1), c_longlong(f1), c_longlong(1), ptr(fc2.weight), c_longlong(f1), c_longlong(1),
+             ptr(fc2.bias), c_int(n), c_int(f2), c_int(f1), ptr(z2), c_int(f2), stream())
+        st2 = self._new((2 * f2,), torch.float32, dev)
+        call("ctk_colstat", ptr(z2), c_int(1), c_longlong(0), c_int(f2), ptr(None), c_int(n), c_int(f2), ptr(None), ptr(st2),
+             stream())
+        bn2 = self._bn_finalize(st2, float(n), None, self.bns[1], dev)
+        a2 = self._new((n, f2), torch.float32, dev)
+        call("ctk_bn1d_act_drop_fwd", ptr(z2), ptr(bn2[0]), ptr(bn2[1]), ptr(masks[1]), c_float(self.drop_p[1]),
+             c_float(LEAKY_SLOPE), c_int(n), c_int(f2), ptr(a2), stream())
+        out = self._new((n, 1), torch.float32, dev)
+        call("ctk_head_out_fwd", ptr(a2), ptr(fc3.weight), ptr(fc3.bias), c_int(n), c_int(f2), c_int(self.sigmoid_half),
+             ptr(out), stream())
+        sv.update(z1=z1, bn1=bn1, a1=a1, z2=z2, bn2=bn2, a2=a2, out=out, masks=masks)
+        self._saved = sv
+        return out
+
+    def _masks(self, n, f1, f2, dev):
+        if self.forced_masks is not None:
+            ms = []
+            for m, f in zip(self.forced_masks, (f1, f2)):
+                if m is not None:
+                    _lib.require_device(m, torch.float32, "dropout mask")
+                    if tuple(m.shape) != (n, f):
+                        raise _lib.CtkError("dropout mask has the wrong shape")
+                ms.append(m)
+            return tuple(ms)
+        out = []
+        for p, f in zip(self.drop_p, (f1, f2)):
+            out.append(None if p == 0.0 else (torch.rand(n, f, device=dev) >= p).float())
+        return tuple(out)
+
+    # ------------------------------------------------------------------ backward
+    def backward(self, dout: torch.Tensor) -> Dict[torch.nn.Parameter, torch.Tensor]:
+        sv = self._saved
+        if sv is None:
+            raise _lib.CtkError("backward called without a matching train-mode forward")
+        self._saved = None
+        dout = dout.contiguous().float()
+        _lib.require_device(dout, torch.float32, "output gradient")
+        grads: Dict[torch.nn.Parameter, torch.Tensor] = {}
+
+        def done(p, g):
+            grads[p] = g
+            if self.on_grad_ready is not None:
+                self.on_grad_ready(p, g)
+
+        n, dev = sv["n"], dout.device
+        fc1, fc2, fc3 = self.lin
+        f1, f2 = fc1.out_features, fc2.out_features
+        K = fc1.in_features
+        m_pad = sv["m_pad"]
+        k_pad = _pad(n, 64)
+        masks = sv["masks"]
+        # ---- head
+        da2 = self._new((n, f2), torch.float32, dev)
+        dw3 = self._new((1, f2), torch.float32, dev)
+        db3 = self._new((1,), torch.float32, dev)
+        call("ctk_head_out_bwd", ptr(dout), ptr(sv["out"]), ptr(sv["a2"]), ptr(fc3.weight), c_int(n), c_int(f2),
+             c_int(self.sigmoid_half), ptr(da2), ptr(dw3), ptr(db3), stream())
+        done(fc3.weight, dw3)
+        done(fc3.bias, db3)
+        sc2, sh2, mu2, is2 = sv["bn2"]
+        dact2 = self._new((n, f2), torch.float32, dev)
+        sums2 = self._new((2 * f2,), torch.float32, dev)
+        call("ctk_bn1d_bwd_reduce", ptr(da2), ptr(masks[1]), c_float(self.drop_p[1]), ptr(sv["z2"]), ptr(sc2), ptr(sh2),
+             ptr(mu2), ptr(is2), c_float(LEAKY_SLOPE), c_int(n), c_int(f2), ptr(dact2), ptr(sums2), stream())
+        done(self.bns[1].bias, sums2[:f2])
+        done(self.bns[1].weight, sums2[f2:])
+        dz2 = self._new((n, f2), torch.float32, dev)
+        call("ctk_bn1d_bwd_apply", ptr(dact2), ptr(sv["z2"]), ptr(sc2), ptr(mu2), ptr(is2), ptr(sums2), c_int(n), c_int(f2),
+             ptr(dz2), ptr(None), ptr(None), c_int(0), stream())
+        dw2 = self._new((f2, f1), torch.float32, dev)
+        call("ctk_sgemm_strided", ptr(dz2), c_longlong(1), c_longlong(f2), ptr(sv["a1"]), c_longlong(1), c_longlong(f1),
+             ptr(None), c_int(f2), c_int(f1), c_int(n), ptr(dw2), c_int(f1), stream())
+        done(fc2.weight, dw2)
+        done(fc2.bias, self._colsum(dz2, n, f2))
+        da1 = self._new((n, f1), torch.float32, dev)
+        call("ctk_sgemm_strided", ptr(dz2), c_longlong(f2), c_longlong(1), ptr(fc2.weight), c_longlong(1), c_longlong(f1),
+             ptr(None), c_int(n), c_int(f1), c_int(f2), ptr(da1), c_int(f1), stream())
+        sc1, sh1, mu1, is1 = sv["bn1"]
+        dact1 = self._new((n, f1), torch.float32, dev)
+        sums1 = self._new((2 * f1,), torch.float32, dev)
+        call("ctk_bn1d_bwd_reduce", ptr(da1), ptr(masks[0]), c_float(self.drop_p[0]), ptr(sv["z1"]), ptr(sc1), ptr(sh1),
+             ptr(mu1), ptr(is1), c_float(LEAKY_SLOPE), c_int(n), c_int(f1), ptr(dact1), ptr(sums1), stream())
+        done(self.bns[0].bias, sums1[:f1])
+        done(self.bns[0].weight, sums1[f1:])
+        dz1 = self._new((n, f1), torch.float32, dev)
+        dz1_bf = torch.zeros((m_pad, f1), device=dev, dtype=torch.bfloat16)
+        dz1t_bf = torch.zeros((f1, k_pad), device=dev, dtype=torch.bfloat16)
+        call("ctk_bn1d_bwd_apply", ptr(dact1), ptr(sv["z1"]), ptr(sc1), ptr(mu1), ptr(is1), ptr(sums1), c_int(n), c_int(f1),
+             ptr(dz1), ptr(dz1_bf), ptr(dz1t_bf), c_int(k_pad), stream())
+        done(fc1.bias, self._colsum(dz1, n, f1))
+        # ---- FC1: dW1 (reference column order) and dfeat (NHWC order)
+        hf, wf = sv["hf"], sv["wf"]
+        hw = hf * wf
+        featT = self._new((K, k_pad), torch.bfloat16, dev)
+        call("ctk_feat_transpose_bf16", ptr(sv["feat"]), c_int(n), c_int(hw), c_int(self.feat_channels), ptr(featT),
+             c_int(k_pad), stream())
+        dw1 = self._new((f1, K), torch.float32, dev)
+        call("ctk_gemm_bf16_splitk", ptr(dz1t_bf), ptr(featT), c_int(f1), c_int(K), c_int(k_pad), c_int(1), ptr(dw1), stream(),
+             meta={"flops": 2.0 * f1 * K * k_pad})
+        done(fc1.weight, dw1)
+        del featT
+        w1t = self._new((K, f1), torch.bfloat16, dev)
+        call("ctk_pack_fc1_weight_t_bf16", ptr(fc1.weight), c_int(f1), c_int(self.feat_channels), c_int(hw), ptr(w1t), stream())
+        dfeat = self._new((m_pad, hf, wf, self.feat_channels), torch.bfloat16, dev)
+        call("ctk_gemm_bf16_out_bf16", ptr(dz1_bf), ptr(w1t), c_int(m_pad), c_int(K), c_int(f1), ptr(dfeat), stream(),
+             meta={"flops": 2.0 * m_pad * f1 * K})
+        del w1t
+        # ---- conv stacks, last block first
+        x = sv["x"]
+        for entry in sv["blocks"]:
+            br, blocks = entry["branch"], entry["blocks"]
+            dp, dp_cstride, dp_coff = dfeat, self.feat_channels, entry["c_off"]
+            for li in range(len(blocks) - 1, -1, -1):
+                b = blocks[li]
+                conv, bn, h, w = b["conv"], b["bn"], b["h"], b["w"]
+                cout, cin = conv.out_channels, conv.in_channels
+                sums = self._new((2 * cout,), torch.float32, dev)
+                call("ctk_bn_bwd_reduce", ptr(b["y"]), ptr(dp), c_int(dp_cstride), c_int(dp_coff), c_int(n), c_int(h), c_int(w),
+                     c_int(cout), ptr(b["scale"]), ptr(b["shift"]), ptr(b["mean"]), ptr(b["invstd"]), c_float(LEAKY_SLOPE),
+                     ptr(sums), stream())
+                done(bn.bias, sums[:cout])
+                done(bn.weight, sums[cout:])
+                dy = self._new((n, h, w, cout), torch.bfloat16, dev)
+                call("ctk_bn_bwd_apply", ptr(b["y"]), ptr(dp), c_int(dp_cstride), c_int(dp_coff), c_int(n), c_int(h), c_int(w),
+                     c_int(cout), ptr(b["scale"]), ptr(b["shift"]), ptr(b["mean"]), ptr(b["invstd"]), ptr(sums),
+                     c_float(LEAKY_SLOPE), ptr(dy), stream())
+                b["y"] = None
+                dw = self._new(tuple(conv.weight.shape), torch.float32, dev)
+                if li == 0:
+                    call("ctk_conv_first_wgrad", ptr(dy), ptr(x), c_int(n), c_int(x.shape[1]), c_int(br.c_offset), c_int(cin),
+                         c_int(h), c_int(w), c_int(cout), ptr(dw), stream())
+                else:
+                    call("ctk_conv3x3_wgrad_tc", ptr(dy), ptr(b["x_in"]), c_int(n), c_int(h), c_int(w), c_int(cin), c_int(cout),
+                         ptr(dw), stream(), meta={"flops": 2.0 * n * h * w * cout * 9 * cin})
+                done(conv.weight, dw)
+                # the conv bias feeds a train-mode BatchNorm, so its gradient is sum(dY) = 0 identically
+                done(conv.bias, torch.zeros_like(conv.bias))
+                if li > 0:
+                    wg = self._new((9, cin, cout), torch.bfloat16, dev)
+                    call("ctk_pack_conv_weight_dgrad_bf16", ptr(conv.weight), c_int(cout), c_int(cin), ptr(wg), stream())
+                    dx = self._new((n, h, w, cin), torch.bfloat16, dev)
+                    call("ctk_conv3x3_tc_raw", ptr(dy), c_int(n), c_int(h), c_int(w), c_int(cout), ptr(wg), c_int(cin), ptr(dx),
+                         ptr(None), stream(), meta={"flops": 2.0 * n * h * w * cout * 9 * cin})
+                    dp, dp_cstride, dp_coff = dx, cin, 0
+                del dy
+        return grads
+
+
+class _CtkTrainFunction(torch.autograd.Function):
+    """Graph edge for the whole network: forward = TrainEngine.forward, backward hands every parameter its gradient."""
+
+    @staticmethod
+    def forward(ctx, engine, x, *params):
+        ctx.engine = engine
+        return engine.forward(x)
+
+    @staticmethod
+    def backward(ctx, dout):
+        engine = ctx.engine
+        grads = engine.backward(dout)
+        return (None, None) + tuple(grads.get(p) for p in engine.params)
+
+
+def train_forward(engine: TrainEngine, x: torch.Tensor) -> torch.Tensor:
+    return _CtkTrainFunction.apply(engine, x, *engine.params)
