@@ -120,6 +120,158 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def cpu_train_rate(kind, n_tiles, steps, warmup):
+    """Reference training step (forward + MSE + backward + Adam) on the host cores: oracle port of train_model.py:419-424."""
+    import crosstalk_oracle as orc
+    torch.set_num_threads(os.cpu_count() or 1)
+    x, y = orc.synthetic_batch(n_tiles, seed=1234)
+    tr = orc.OracleTrainer(kind, orc.INIT[kind](0), lr=5e-4, weight_decay=1e-4)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        tr.step(x, y)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    return n_tiles / sec, sec, torch.get_num_threads()
+
+
+def run_train(args):
+    """Training throughput: zero_grad -> forward -> MSELoss -> backward -> Adam.step -> loss.item() (train_model.py:419-426),
+    per-GPU batch fixed (weak scaling), gradients averaged across ranks by the bucketed NCCL all-reduce."""
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    kind, batch = args.model, args.batch
+    if args.impl == "reference":
+        if rank == 0:
+            rate, sec, cores = cpu_train_rate(kind, 8, max(1, min(args.steps, 3)), 1)
+            print(json.dumps({"impl": "reference", "metric": f"train images/sec ({kind}-branch, 2ch 256x256)", "value": rate,
+                              "unit": "images/sec", "n_gpus": args.gpus, "steps": max(1, min(args.steps, 3)), "warmup": 1,
+                              "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                              "dtype": "f32", "data": "synthetic",
+                              "config": {"workload": f"{kind}-branch training step", "bounded_sample_tiles": 8},
+                              "cpu_baseline": {"value": rate, "unit": "images/sec", "cores": cores, "kind": "port",
+                                               "sample": "8-tile batches, fwd+MSE+bwd+Adam, fp32, torch CPU"},
+                              "e2e": {"value": rate, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}),
+                  flush=True)
+        return
+    import ctk
+    from ctk import _lib
+    import crosstalk_oracle as orc
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the ctk hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    steps, warmup = args.steps, max(3, args.warmup)
+    torch.manual_seed(0)
+    model = (ctk.SimplifiedTwoBranchRegressionModel(initial_filters_per_branch=64) if kind == "double"
+             else ctk.AdvancedRegressionModel(initial_filters=128, num_conv_blocks=6)).to(dev).train()
+    sync = None
+    if world > 1:
+        ctk.parallel.broadcast_parameters(model)
+        sync = ctk.parallel.attach(model)
+    opt = ctk.Adam(model.parameters(), lr=5e-4, weight_decay=1e-4)
+    crit = torch.nn.MSELoss()
+    base_x, base_y = orc.synthetic_batch(32, seed=1234 + rank)
+    reps = (batch + 31) // 32
+    host = [(base_x.roll(i, 0).repeat(reps, 1, 1, 1)[:batch].contiguous().pin_memory(),
+             base_y.roll(i, 0).repeat(reps, 1)[:batch].contiguous().pin_memory()) for i in range(2)]
+    devb = [(a.to(dev), b.to(dev)) for a, b in host]
+
+    def step(xb, yb):
+        opt.zero_grad()
+        out = model(xb)
+        loss = crit(out, yb)
+        loss.backward()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(warmup):
+        step(*devb[i % 2]).item()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.launch_count
+    timeline = _lib.start_timeline()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        last = step(*devb[i % 2]).item()            # loss.item() every step, like train_model.py:426
+    e1.record()
+    barrier()
+    _lib.stop_timeline()
+    launches = _lib.launch_count - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms = e0.elapsed_time(e1)
+    # end to end: the batch starts in pinned host memory every step (the DataLoader's pin_memory=True path, :607-614)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(2, steps // 2)
+    for i in range(e2e_steps):
+        xb = host[i % 2][0].to(dev, non_blocking=True)
+        yb = host[i % 2][1].to(dev, non_blocking=True)
+        step(xb, yb).item()
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    barrier()
+    t = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = t.tolist()
+    if rank == 0:
+        pk = peaks()
+        per = {}
+        for name, a, b, meta in timeline:
+            d = per.setdefault(name, {"ms": 0.0, "n": 0, "flops": 0.0})
+            d["ms"] += a.elapsed_time(b)
+            d["n"] += 1
+            d["flops"] += (meta or {}).get("flops", 0.0)
+        tc = {k: per[k] for k in ("ctk_conv3x3_tc_raw", "ctk_conv3x3_wgrad_tc") if k in per}
+        tc_flops = sum(v["flops"] for v in tc.values())
+        tc_ms = sum(v["ms"] for v in tc.values())
+        tf = tc_flops / (tc_ms / 1e3) / 1e12 if tc_ms > 0 else 0.0
+        gflop_img = {"double": 44.6, "single": 77.6}[kind]
+        line = {"metric": f"train images/sec ({kind}-branch, 2ch 256x256, batch {batch}/GPU)", "value": world * batch * steps / (ms / 1e3),
+                "unit": "images/sec", "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms / steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": f"{kind}-branch training step (fwd + MSE + bwd + Adam lr 5e-4 wd 1e-4), batch {batch} per GPU",
+                           "per_gpu_batch": batch, "global_batch": batch * world,
+                           "parallelism": f"dp{world}: bucketed NCCL all-reduce (AVG) overlapped with backward" if world > 1 else "single GPU",
+                           "l2_policy": "inputs larger than L2 (134 MB per batch), 2 distinct batches rotated"},
+                "whole_net_tflops": world * batch * steps / (ms / 1e3) * gflop_img / 1e3,
+                "roofline": {"kernel": "conv3x3_tc_kernel (fwd+dgrad) + wgrad_tc_kernel", "bound": "tensor", "achieved": tf,
+                             "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": tf / pk["bf16_tflops"], "traffic": None,
+                             "peak_source": pk["src"] + " (sustained cuBLAS bf16)",
+                             "share_of_step": tc_ms / ms if ms > 0 else None,
+                             "per_call_ms_per_step": {k: round(v["ms"] / steps, 4) for k, v in sorted(per.items())},
+                             "per_call_tflops": {k: (v["flops"] / (v["ms"] / 1e3) / 1e12 if v["ms"] > 0 and v["flops"] > 0 else None)
+                                                 for k, v in sorted(per.items())}},
+                "clocks": clocks, "gpu_launches": launches, "last_loss": last,
+                "e2e": {"value": world * batch * e2e_steps / (e2e_ms / 1e3), "unit": "images/sec",
+                        "h2d_bytes_per_step": batch * (2 * 256 * 256 + 1) * 4, "d2h_bytes_per_step": 4, "steps": e2e_steps,
+                        "ms_per_step": e2e_ms / e2e_steps, "api": "model(x); MSELoss; backward; ctk.Adam.step; loss.item()"}}
+        if sync is not None:
+            line["allreduce"] = {"collectives_per_step": sync.collectives / (warmup + steps + e2e_steps),
+                                 "bytes_per_step": sync.bytes_reduced / (warmup + steps + e2e_steps)}
+        if world == 1 and not args.no_cpu_baseline:
+            rate, sec, cores = cpu_train_rate(kind, 8, 2, 1)
+            line["cpu_baseline"] = {"value": rate, "unit": "images/sec", "cores": cores, "kind": "port",
+                                    "sample": "8-tile batches, fwd+MSE+bwd+Adam, oracle port (same ATen CPU ops as the reference), fp32"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -127,7 +279,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ctk", choices=["ctk", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="infer", choices=["infer", "train"],
+                    help="infer = BASELINE configs[1] (default, the headline line); train = configs[2]/[3] training step")
+    ap.add_argument("--model", default="double", choices=["double", "single"])
+    ap.add_argument("--batch", type=int, default=BATCH, help="per-GPU batch (train mode)")
     args = ap.parse_args()
+    if args.mode == "train":
+        return run_train(args)
     if args.impl == "reference":
         return run_reference(args)
 

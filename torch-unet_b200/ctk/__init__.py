@@ -12,7 +12,8 @@ from .models import (AdvancedRegressionModel, SimplifiedFeatureExtractionBranch,
                      SimplifiedTwoBranchRegressionModel, accelerate)
 from .optim import Adam, mse_loss
 from .pipeline import HostScorer
+from . import parallel
 
 __all__ = ["CtkError", "EXPORTED_SYMBOLS", "LIB_PATH", "load", "InferenceEngine", "pearson_per_image",
            "AdvancedRegressionModel", "SimplifiedFeatureExtractionBranch", "SimplifiedRegressionHead",
-           "SimplifiedTwoBranchRegressionModel", "accelerate", "Adam", "mse_loss", "HostScorer"]
+           "SimplifiedTwoBranchRegressionModel", "accelerate", "Adam", "mse_loss", "HostScorer", "parallel"]

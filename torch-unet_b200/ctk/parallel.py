@@ -1,0 +1,98 @@
+"""Data-parallel gradient exchange for the ctk training path.
+
+One process per GPU; the global batch is split evenly and the only data-path exchange is the gradient all-reduce.
+``GradSynchronizer`` hooks ``TrainEngine.on_grad_ready``: gradients arrive in backward order (head first, then the
+conv blocks last-to-first), large tensors (FC1's 537 MB weight gradient is the first big one out) are reduced in
+place as soon as their wgrad kernel has been enqueued, small ones are packed into ~25 MB buckets.  Every collective is
+launched asynchronously -- NCCL runs it on its own stream behind the producing kernel -- so the exchange overlaps the
+remaining dgrad / wgrad work, and the compute stream only waits for it at the end of ``backward``.
+The result is the MEAN over ranks (matching ``MSELoss(reduction='mean')`` over the global batch); with NCCL that is a
+single ``ReduceOp.AVG``.  torch.distributed is plumbing here: communicator setup, stream ordering, the collective.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+BIG_TENSOR_BYTES = 8 << 20
+BUCKET_BYTES = 25 << 20
+
+
+class GradSynchronizer:
+    def __init__(self, process_group=None, bucket_bytes: int = BUCKET_BYTES, big_tensor_bytes: int = BIG_TENSOR_BYTES):
+        if not dist.is_initialized():
+            raise RuntimeError("torch.distributed is not initialised")
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group)
+        self.bucket_bytes = bucket_bytes
+        self.big_bytes = big_tensor_bytes
+        self.use_avg = dist.get_backend(process_group) == "nccl"
+        self._pending: List[Tuple[object, torch.Tensor]] = []      # (work, tensor to divide when not AVG)
+        self._bucket: List[Tuple[object, torch.Tensor]] = []       # (key, grad)
+        self._bucket_bytes = 0
+        self._replaced: Dict[object, torch.Tensor] = {}
+        self.collectives = 0
+        self.bytes_reduced = 0
+
+    # ------------------------------------------------------------------ called by TrainEngine.backward
+    def on_grad_ready(self, key, grad: torch.Tensor) -> None:
+        nbytes = grad.numel() * grad.element_size()
+        if nbytes >= self.big_bytes and grad.is_contiguous():
+            self._launch(grad)
+            return
+        self._bucket.append((key, grad))
+        self._bucket_bytes += nbytes
+        if self._bucket_bytes >= self.bucket_bytes:
+            self._flush()
+
+    def finalize(self, grads: Dict[object, torch.Tensor]) -> Dict[object, torch.Tensor]:
+        """Flush the last bucket, make the current stream wait for every collective, hand back the reduced gradients."""
+        self._flush()
+        for work, t in self._pending:
+            work.wait()
+            if not self.use_avg:
+                t.div_(self.world)
+        self._pending.clear()
+        out = dict(grads)
+        out.update(self._replaced)
+        self._replaced = {}
+        return out
+
+    # ------------------------------------------------------------------ internals
+    def _launch(self, t: torch.Tensor) -> None:
+        op = dist.ReduceOp.AVG if self.use_avg else dist.ReduceOp.SUM
+        work = dist.all_reduce(t, op=op, group=self.pg, async_op=True)
+        self._pending.append((work, t))
+        self.collectives += 1
+        self.bytes_reduced += t.numel() * t.element_size()
+
+    def _flush(self) -> None:
+        if not self._bucket:
+            return
+        flat = torch.cat([g.reshape(-1) for _, g in self._bucket])
+        self._launch(flat)
+        off = 0
+        for key, g in self._bucket:
+            n = g.numel()
+            self._replaced[key] = flat[off:off + n].view(g.shape)     # gradients become views of the reduced bucket
+            off += n
+        self._bucket = []
+        self._bucket_bytes = 0
+
+
+def attach(model: torch.nn.Module, process_group=None, **kw) -> GradSynchronizer:
+    """Make ``loss.backward()`` of a ctk model all-reduce (average) its gradients across the process group."""
+    from .models import get_train_engine
+    sync = GradSynchronizer(process_group, **kw)
+    eng = get_train_engine(model)
+    eng.on_grad_ready = sync.on_grad_ready
+    eng.finalize_grads = sync.finalize
+    return sync
+
+
+def broadcast_parameters(model: torch.nn.Module, src: int = 0, process_group=None) -> None:
+    """All ranks start from rank ``src``'s parameters and buffers (what DDP does at construction)."""
+    for t in list(model.parameters()) + list(model.buffers()):
+        dist.broadcast(t.data, src=src, group=process_group)

@@ -46,6 +46,7 @@ class TrainEngine:
         self.params: List[torch.nn.Parameter] = list(model.parameters())
         self.forced_masks: Optional[Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]] = None
         self.on_grad_ready: Optional[Callable[[torch.nn.Parameter, torch.Tensor], None]] = None
+        self.finalize_grads: Optional[Callable[[dict], dict]] = None      # e.g. parallel.GradSynchronizer.finalize
         self._saved: Optional[dict] = None
 
     # ------------------------------------------------------------------ helpers
@@ -290,6 +291,8 @@ class TrainEngine:
                          ptr(None), stream(), meta={"flops": 2.0 * n * h * w * cout * 9 * cin})
                     dp, dp_cstride, dp_coff = dx, cin, 0
                 del dy
+        if self.finalize_grads is not None:
+            grads = self.finalize_grads(grads)
         return grads
 
 
