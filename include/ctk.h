@@ -173,6 +173,12 @@ int ctk_bn_act_pool_fwd(const void* y_bf16, int n, int H, int W, int channels, c
 int ctk_bn_bwd_reduce(const void* y_bf16, const void* dp_bf16, int dp_cstride, int dp_coffset, int n, int H, int W,
                       int channels, const float* scale, const float* shift, const float* mean, const float* invstd,
                       float slope, float* sums, void* stream);
+/* Same sums from the pooled activation P (the block's stored output) and dP alone: dA lives only at each window's
+ * argmax, where the activation equals P, so f'(P) and xhat(P) = (leaky^-1(P) - beta)/gamma are recoverable.  Reads
+ * 1 B per element of Y instead of 2.5 B.  gamma == 0 channels get dgamma = 0. */
+int ctk_bn_bwd_reduce_pooled(const void* pooled_bf16, int p_cstride, int p_coffset, const void* dp_bf16, int dp_cstride,
+                             int dp_coffset, long long pooled_pixels, int channels, const float* gamma,
+                             const float* beta, float slope, float* sums, void* stream);
 int ctk_bn_bwd_apply(const void* y_bf16, const void* dp_bf16, int dp_cstride, int dp_coffset, int n, int H, int W,
                      int channels, const float* scale, const float* shift, const float* mean, const float* invstd,
                      const float* sums, float slope, void* dy_bf16, void* stream);

@@ -107,6 +107,9 @@ def test_bn_finalize_act_pool_and_backward(L):
     bsum = torch.empty(2 * C, device="cuda")
     L.call("ctk_bn_bwd_reduce", L.ptr(yd), L.ptr(dpd), c_int(C + 8), c_int(8), c_int(n), c_int(H), c_int(W), c_int(C),
            L.ptr(scale), L.ptr(shift), L.ptr(mean), L.ptr(invstd), c_float(0.01), L.ptr(bsum), L.stream())
+    bsum_p = torch.empty(2 * C, device="cuda")
+    L.call("ctk_bn_bwd_reduce_pooled", L.ptr(out), c_int(C + 8), c_int(8), L.ptr(dpd), c_int(C + 8), c_int(8),
+           c_longlong(n * (H // 2) * (W // 2)), c_int(C), L.ptr(gd), L.ptr(bd), c_float(0.01), L.ptr(bsum_p), L.stream())
     dy = torch.empty(n, H, W, C, device="cuda", dtype=torch.bfloat16)
     L.call("ctk_bn_bwd_apply", L.ptr(yd), L.ptr(dpd), c_int(C + 8), c_int(8), c_int(n), c_int(H), c_int(W), c_int(C),
            L.ptr(scale), L.ptr(shift), L.ptr(mean), L.ptr(invstd), L.ptr(bsum), c_float(0.01), L.ptr(dy), L.stream())
@@ -118,6 +121,9 @@ def test_bn_finalize_act_pool_and_backward(L):
     assert rel_l2(out[..., 8:].float().cpu(), pooled.detach().permute(0, 2, 3, 1)) < 4e-3
     np.testing.assert_allclose(bsum[:C].cpu().numpy(), b.grad.numpy(), rtol=1e-3, atol=1e-3)     # dbeta
     np.testing.assert_allclose(bsum[C:].cpu().numpy(), g.grad.numpy(), rtol=1e-3, atol=1e-3)     # dgamma
+    # the pooled-tensor variant reconstructs xhat from the bf16-rounded pooled activation: a few bf16 ulps looser
+    np.testing.assert_allclose(bsum_p[:C].cpu().numpy(), b.grad.numpy(), rtol=1e-3, atol=1e-3)
+    np.testing.assert_allclose(bsum_p[C:].cpu().numpy(), g.grad.numpy(), rtol=2e-2, atol=3e-2)
     assert rel_l2(dy.float().cpu(), yr.grad.permute(0, 2, 3, 1)) < 6e-3
 
 

@@ -160,6 +160,58 @@ bn_bwd_reduce_kernel(const uint4* __restrict__ y, const __nv_bfloat16* __restric
   }
 }
 
+// ---------------------------------------------------------------- backward pass 1 from the POOLED tensors only
+// dA is non-zero only at each window's argmax, where the activation equals the stored pooled output P.  So
+//   sum(dA)       = sum_w dP * f'(P)            f'(P) = P > 0 ? 1 : slope
+//   sum(dA*xhat)  = sum_w dP * f'(P) * xhat(P)  xhat(P) = (leaky^-1(P) - beta) / gamma
+// needs 1 B per element of Y (P and dP, both quarter size) instead of 2.5 B.
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce_pooled_kernel(const __nv_bfloat16* __restrict__ pooled, int p_cstride, int p_coffset,
+                            const __nv_bfloat16* __restrict__ dp, int dp_cstride, int dp_coffset, int c8,
+                            const float* __restrict__ gamma, const float* __restrict__ beta, float slope,
+                            float* __restrict__ sums, long long pooled_pixels) {
+  extern __shared__ float red[];                       // [256][16]
+  const int cg = threadIdx.x % c8;
+  const int slot = threadIdx.x / c8;
+  const int slots = blockDim.x / c8;
+  float ig[8], be[8], s1[8], s2[8];
+  const float inv_slope = 1.f / slope;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float g = __ldg(gamma + cg * 8 + i);
+    ig[i] = g != 0.f ? 1.f / g : 0.f;
+    be[i] = __ldg(beta + cg * 8 + i);
+    s1[i] = 0.f; s2[i] = 0.f;
+  }
+  for (long long pix = blockIdx.x * static_cast<long long>(slots) + slot; pix < pooled_pixels;
+       pix += static_cast<long long>(gridDim.x) * slots) {
+    float pv[8], dv[8];
+    unpack8(__ldcs(reinterpret_cast<const uint4*>(pooled + pix * p_cstride + p_coffset + cg * 8)), pv);
+    unpack8(__ldcs(reinterpret_cast<const uint4*>(dp + pix * dp_cstride + dp_coffset + cg * 8)), dv);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const bool pos = pv[i] > 0.f;
+      const float da = pos ? dv[i] : dv[i] * slope;
+      const float z = pos ? pv[i] : pv[i] * inv_slope;
+      s1[i] += da;
+      s2[i] = fmaf(da, (z - be[i]) * ig[i], s2[i]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { red[threadIdx.x * 16 + i] = s1[i]; red[threadIdx.x * 16 + 8 + i] = s2[i]; }
+  __syncthreads();
+  if (slot == 0) {
+    const int c = c8 * 8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float a = 0.f, b = 0.f;
+      for (int s = 0; s < slots; ++s) { a += red[(s * c8 + cg) * 16 + i]; b += red[(s * c8 + cg) * 16 + 8 + i]; }
+      atomicAdd(sums + cg * 8 + i, a);
+      atomicAdd(sums + c + cg * 8 + i, b);
+    }
+  }
+}
+
 // ---------------------------------------------------------------- backward pass 2: dense gradient of the raw conv output
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const uint4* __restrict__ y, const __nv_bfloat16* __restrict__ dp, int dp_cstride, int dp_coffset,
@@ -251,6 +303,25 @@ int ctk_bn_bwd_reduce(const void* y_bf16, const void* dp_bf16, int dp_cstride, i
   bn_bwd_reduce_kernel<<<grid, 256, 256 * 16 * sizeof(float), s>>>(
       static_cast<const uint4*>(y_bf16), static_cast<const __nv_bfloat16*>(dp_bf16), dp_cstride, dp_coffset, H, W,
       channels / 8, scale, shift, mean, invstd, slope, sums, pooled);
+  return ctk::check_launch();
+}
+
+int ctk_bn_bwd_reduce_pooled(const void* pooled_bf16, int p_cstride, int p_coffset, const void* dp_bf16, int dp_cstride,
+                             int dp_coffset, long long pooled_pixels, int channels, const float* gamma,
+                             const float* beta, float slope, float* sums, void* stream) {
+  if (pooled_pixels == 0) return CTK_OK;
+  CTK_REQUIRE(pooled_bf16 && dp_bf16 && gamma && beta && sums && pooled_pixels > 0 && slope > 0.f);
+  CTK_REQUIRE(channels > 0 && channels % 8 == 0 && channels <= 2048 && 256 % (channels / 8) == 0);
+  CTK_REQUIRE(dp_cstride % 8 == 0 && dp_coffset % 8 == 0 && dp_coffset + channels <= dp_cstride && p_cstride % 8 == 0 &&
+              p_coffset % 8 == 0 && p_coffset + channels <= p_cstride);
+  cudaStream_t s = ctk::as_stream(stream);
+  CTK_CUDA_TRY(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * channels, s));
+  const int slots = 256 / (channels / 8);
+  const long long blocks = (pooled_pixels + slots - 1) / slots;
+  const int grid = static_cast<int>(blocks < ctk::num_sms() * 8 ? blocks : ctk::num_sms() * 8);
+  bn_bwd_reduce_pooled_kernel<<<grid, 256, 256 * 16 * sizeof(float), s>>>(
+      static_cast<const __nv_bfloat16*>(pooled_bf16), p_cstride, p_coffset, static_cast<const __nv_bfloat16*>(dp_bf16),
+      dp_cstride, dp_coffset, channels / 8, gamma, beta, slope, sums, pooled_pixels);
   return ctk::check_launch();
 }
 

@@ -114,7 +114,7 @@ class TrainEngine:
                     dst, cstride, coff = self._new((n, h // 2, w // 2, cout), torch.bfloat16, dev), cout, 0
                 call("ctk_bn_act_pool_fwd", ptr(y), c_int(n), c_int(h), c_int(w), c_int(cout), ptr(scale), ptr(shift),
                      c_float(LEAKY_SLOPE), ptr(dst), c_int(cstride), c_int(coff), stream())
-                blocks.append({"y": y, "x_in": cur, "scale": scale, "shift": shift, "mean": mean, "invstd": invstd,
+                blocks.append({"y": y, "x_in": cur, "pooled": (dst, cstride, coff), "scale": scale, "shift": shift, "mean": mean, "invstd": invstd,
                                "h": h, "w": w, "conv": conv, "bn": bn})
                 cur = dst
                 h, w = h // 2, w // 2
@@ -263,9 +263,10 @@ class TrainEngine:
                 conv, bn, h, w = b["conv"], b["bn"], b["h"], b["w"]
                 cout, cin = conv.out_channels, conv.in_channels
                 sums = self._new((2 * cout,), torch.float32, dev)
-                call("ctk_bn_bwd_reduce", ptr(b["y"]), ptr(dp), c_int(dp_cstride), c_int(dp_coff), c_int(n), c_int(h), c_int(w),
-                     c_int(cout), ptr(b["scale"]), ptr(b["shift"]), ptr(b["mean"]), ptr(b["invstd"]), c_float(LEAKY_SLOPE),
-                     ptr(sums), stream())
+                pooled, p_cstride, p_coff = b["pooled"]
+                call("ctk_bn_bwd_reduce_pooled", ptr(pooled), c_int(p_cstride), c_int(p_coff), ptr(dp), c_int(dp_cstride),
+                     c_int(dp_coff), c_longlong(n * (h // 2) * (w // 2)), c_int(cout), ptr(bn.weight), ptr(bn.bias),
+                     c_float(LEAKY_SLOPE), ptr(sums), stream())
                 done(bn.bias, sums[:cout])
                 done(bn.weight, sums[cout:])
                 dy = self._new((n, h, w, cout), torch.bfloat16, dev)
