@@ -163,6 +163,32 @@ int ctk_pack_conv_weight_dgrad_bf16(const float* w, int cout, int cin, void* w_p
 int ctk_bn_finalize(const float* sums, double count, const float* bias, const float* gamma, const float* beta,
                     float* running_mean, float* running_var, long long* num_batches_tracked, float momentum, float eps,
                     int channels, float* scale, float* shift, float* mean, float* invstd, void* stream);
+/* Same, from per-channel [mean, biased variance] instead of sums (first block: moments come from the patch Gram matrix). */
+int ctk_bn_finalize_moments(const float* moments, double count, const float* bias, const float* gamma, const float* beta,
+                            float* running_mean, float* running_var, long long* num_batches_tracked, float momentum,
+                            float eps, int channels, float* scale, float* shift, float* mean, float* invstd,
+                            void* stream);
+
+/* First conv block in training without materialising its full-resolution output.  With T = 9*cin taps,
+ * gram = [S (T doubles) | G (T*T doubles)], S[t] = sum_p x[p+t], G[t][t'] = sum_p x[p+t] x[p+t'] (zero padded):
+ *   ctk_first_patch_gram     gram of the input planes (overwrites gram)
+ *   ctk_first_moments        moments[c] = batch mean, moments[cout+c] = biased batch variance of conv(x, w)[.,c] (no bias)
+ *   (then ctk_bn_finalize_moments, ctk_pack_first_weight(w, scale) and ctk_conv_first_eval give the pooled output)
+ *   ctk_first_wgrad_fused    t1[c][t] = sum_windows dP[w,c] * f'(z*) * x[argmax(w,c) + t]; recomputes the 2x2 window's
+ *                            activations from x with the folded weights (first maximum wins); dp is dense bf16 NHWC
+ *   ctk_first_wgrad_finalize dw[c][t] = scale_c (t1 - m1_c S_t - m2_c invstd_c ((G w_c)[t] - mean_c S_t)),
+ *                            sums = [sum dA, sum dA*xhat] from ctk_bn_bwd_reduce_pooled, count = n*H*W
+ * Replaces (train mode): nn.Conv2d + nn.BatchNorm2d statistics and their backward for regression_model.py:14-15,
+ * two_branch_regression.py:10-11. */
+int ctk_first_patch_gram(const float* x, int n, int c_total, int c_offset, int cin, int H, int W, double* gram,
+                         void* stream);
+int ctk_first_moments(const double* gram, const float* w, int cout, int cin, double count, float* moments, void* stream);
+int ctk_first_wgrad_fused(const float* x, int n, int c_total, int c_offset, int cin, int H, int W, const float* w_folded,
+                          const float* shift, float slope, const void* dp_bf16, int cout, float* t1, void* stream);
+int ctk_first_wgrad_finalize(const float* t1, const double* gram, const float* w, const float* scale, const float* mean,
+                             const float* invstd, const float* sums, double count, int cout, int cin, float* dw,
+                             void* stream);
+
 /* out = maxpool2x2(leaky(y*scale + shift)), y bf16 NHWC [n,H,W,C] -> out bf16 NHWC [n,H/2,W/2,out_cstride] @ out_coffset.
  * Replaces: BatchNorm2d(train) apply + LeakyReLU + MaxPool2d, regression_model.py:15-17,24-26. */
 int ctk_bn_act_pool_fwd(const void* y_bf16, int n, int H, int W, int channels, const float* scale, const float* shift,

@@ -30,7 +30,8 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 }
 
 // ---------------------------------------------------------------- statistics -> scale/shift (+ running stats)
-__global__ void bn_finalize_kernel(const float* __restrict__ sums, double count, const float* __restrict__ bias,
+// moments == 0: sums = [sum(y), sum(y^2)];  moments == 1: sums = [mean, biased variance] (first block, from the Gram matrix)
+__global__ void bn_finalize_kernel(const float* __restrict__ sums, int moments, double count, const float* __restrict__ bias,
                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                    float* __restrict__ running_mean, float* __restrict__ running_var,
                                    long long* __restrict__ num_batches_tracked, float momentum, float eps, int c,
@@ -39,8 +40,9 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sums, double count,
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i == 0 && num_batches_tracked) num_batches_tracked[0] += 1;
   if (i >= c) return;
-  const double m = static_cast<double>(sums[i]) / count;
-  double var = static_cast<double>(sums[c + i]) / count - m * m;      // biased variance normalises the batch
+  const double m = moments ? static_cast<double>(sums[i]) : static_cast<double>(sums[i]) / count;
+  double var = moments ? static_cast<double>(sums[c + i])
+                       : static_cast<double>(sums[c + i]) / count - m * m;      // biased variance normalises the batch
   var = var > 0.0 ? var : 0.0;
   const float invstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
   const float sc = gamma[i] * invstd;
@@ -263,15 +265,31 @@ inline int grid_for(long long total, int threads) {
 
 extern "C" {
 
-int ctk_bn_finalize(const float* sums, double count, const float* bias, const float* gamma, const float* beta,
-                    float* running_mean, float* running_var, long long* num_batches_tracked, float momentum, float eps,
-                    int channels, float* scale, float* shift, float* mean, float* invstd, void* stream) {
+static int bn_finalize_impl(const float* sums, int moments, double count, const float* bias, const float* gamma,
+                            const float* beta, float* running_mean, float* running_var, long long* num_batches_tracked,
+                            float momentum, float eps, int channels, float* scale, float* shift, float* mean,
+                            float* invstd, void* stream) {
   CTK_REQUIRE(sums && gamma && beta && scale && shift && mean && invstd && channels > 0 && count >= 1.0);
   CTK_REQUIRE((running_mean == nullptr) == (running_var == nullptr));
   bn_finalize_kernel<<<(channels + 127) / 128, 128, 0, ctk::as_stream(stream)>>>(
-      sums, count, bias, gamma, beta, running_mean, running_var, num_batches_tracked, momentum, eps, channels, scale,
-      shift, mean, invstd);
+      sums, moments, count, bias, gamma, beta, running_mean, running_var, num_batches_tracked, momentum, eps, channels,
+      scale, shift, mean, invstd);
   return ctk::check_launch();
+}
+
+int ctk_bn_finalize(const float* sums, double count, const float* bias, const float* gamma, const float* beta,
+                    float* running_mean, float* running_var, long long* num_batches_tracked, float momentum, float eps,
+                    int channels, float* scale, float* shift, float* mean, float* invstd, void* stream) {
+  return bn_finalize_impl(sums, 0, count, bias, gamma, beta, running_mean, running_var, num_batches_tracked, momentum, eps,
+                          channels, scale, shift, mean, invstd, stream);
+}
+
+int ctk_bn_finalize_moments(const float* moments, double count, const float* bias, const float* gamma, const float* beta,
+                            float* running_mean, float* running_var, long long* num_batches_tracked, float momentum,
+                            float eps, int channels, float* scale, float* shift, float* mean, float* invstd,
+                            void* stream) {
+  return bn_finalize_impl(moments, 1, count, bias, gamma, beta, running_mean, running_var, num_batches_tracked, momentum,
+                          eps, channels, scale, shift, mean, invstd, stream);
 }
 
 int ctk_bn_act_pool_fwd(const void* y_bf16, int n, int H, int W, int channels, const float* scale, const float* shift,

@@ -1,0 +1,305 @@
+// Train-mode forward statistics and weight gradient of the FIRST conv block without ever materialising its
+// full-resolution output (1 G elements per branch at batch 256 -- more than half of all pre-pool activations).
+//
+// The first conv has only T = 9*Cin taps, so everything that is linear or quadratic in its output follows from the
+// patch Gram matrix of the input,  S[t] = sum_p x[p+t],  G[t][t'] = sum_p x[p+t] x[p+t']  (zero padded like the conv):
+//   batch mean / variance of channel c :  mean = w_c.S / M,   var = w_c^T (G/M - s s^T) w_c            (exact, fp64)
+//   sum_p Y[p,c] x[p+t]                :  (G w_c)[t]
+// Forward therefore is: Gram -> moments -> BN constants -> the fused eval-style kernel (conv + scale/shift + LeakyReLU +
+// pool) that writes only the pooled output.  Backward needs dW[c,t] = sum_p dY[p,c] x[p+t] with
+//   dY = scale_c (dA - m1_c - xhat m2_c)   =>   dW[c,t] = scale_c [ T1[c,t] - m1_c S_t - m2_c invstd_c ((G w_c)[t] - mu_c S_t) ]
+// where only T1[c,t] = sum_windows dP[w,c] f'(z*) x[p*(w,c)+t] touches the data: the kernel below recomputes the four
+// conv outputs of each 2x2 window on the fp32 pipe to find the arg-max position p* (first maximum, like PyTorch).
+// Replaces (train mode) nn.Conv2d + nn.BatchNorm2d statistics + their backward for the first block:
+// /root/reference/regression_model.py:14-15 and two_branch_regression.py:10-11.
+#include "ctk_common.h"
+#include "ctk_ptx.cuh"
+
+namespace {
+
+using namespace ctk;
+
+// ------------------------------------------------------------------------------------------------ patch Gram matrix
+// gram layout (double): [0, T) = S, [T, T + T*T) = G row-major (full, symmetric).
+template <int CIN>
+__global__ void __launch_bounds__(256)
+patch_gram_kernel(const float* __restrict__ x, int n_img, int c_total, int c_offset, int H, int W,
+                  double* __restrict__ gram) {
+  constexpr int T = 9 * CIN;
+  constexpr int ITEMS = T + T * (T + 1) / 2;          // sums + upper triangle
+  constexpr int ROLES = 8;
+  constexpr int PER = (ITEMS + ROLES - 1) / ROLES;
+  constexpr int TW = 32, TH = 8;
+  __shared__ float s_in[CIN][TH + 2][TW + 2 + 1];
+  const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
+  // fp32 partial sums over the 8 pixels a lane sees per tile, folded into fp64 running sums after every tile:
+  // the variance w^T (G/M - s s^T) w cancels one or two digits, so the Gram entries need more than fp32
+  float acc[PER];
+  double dacc[PER];
+#pragma unroll
+  for (int i = 0; i < PER; ++i) { acc[i] = 0.f; dacc[i] = 0.0; }
+  const int tiles_x = (W + TW - 1) / TW, tiles_y = (H + TH - 1) / TH;
+  const long long total = static_cast<long long>(n_img) * tiles_x * tiles_y;
+  for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    const int tx = static_cast<int>(tile % tiles_x);
+    const int ty = static_cast<int>((tile / tiles_x) % tiles_y);
+    const int img = static_cast<int>(tile / (static_cast<long long>(tiles_x) * tiles_y));
+    __syncthreads();
+    for (int c = 0; c < CIN; ++c) {
+      const float* plane = x + (static_cast<size_t>(img) * c_total + c_offset + c) * H * W;
+      for (int i = threadIdx.x; i < (TH + 2) * (TW + 2); i += 256) {
+        const int r = i / (TW + 2), q = i % (TW + 2);
+        const int gy = ty * TH - 1 + r, gx = tx * TW - 1 + q;
+        s_in[c][r][q] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? __ldg(plane + static_cast<size_t>(gy) * W + gx) : 0.f;
+      }
+    }
+    __syncthreads();
+    for (int py = 0; py < TH; ++py) {
+      const int gy = ty * TH + py, gx = tx * TW + lane;
+      if (gy >= H || gx >= W) continue;
+      float v[T];
+#pragma unroll
+      for (int c = 0; c < CIN; ++c)
+#pragma unroll
+        for (int k = 0; k < 9; ++k) v[c * 9 + k] = s_in[c][py + k / 3][lane + k % 3];
+      // item index -> (sum t) or (pair a <= b); role r owns items r, r + ROLES, ...; all indices are compile time
+      int item = 0, slot = 0;
+#pragma unroll
+      for (int a = 0; a < T; ++a, ++item)
+        if (item % ROLES == role) { acc[item / ROLES] += v[a]; }
+#pragma unroll
+      for (int a = 0; a < T; ++a)
+#pragma unroll
+        for (int b = a; b < T; ++b, ++item)
+          if (item % ROLES == role) { acc[item / ROLES] = fmaf(v[a], v[b], acc[item / ROLES]); }
+      (void)slot;
+    }
+#pragma unroll
+    for (int i = 0; i < PER; ++i) { dacc[i] += static_cast<double>(acc[i]); acc[i] = 0.f; }
+  }
+  // warp reduce over lanes, then one fp64 atomic per item per warp
+  int item = 0;
+#pragma unroll
+  for (int a = 0; a < T; ++a, ++item) {
+    if (item % ROLES == role) {
+      double s = dacc[item / ROLES];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0) atomicAdd(gram + a, s);
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < T; ++a)
+#pragma unroll
+    for (int b = a; b < T; ++b, ++item) {
+      if (item % ROLES == role) {
+        double s = dacc[item / ROLES];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) {
+          atomicAdd(gram + T + a * T + b, s);
+          if (a != b) atomicAdd(gram + T + b * T + a, s);
+        }
+      }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ moments from the Gram matrix
+__global__ void first_moments_kernel(const double* __restrict__ gram, const float* __restrict__ w, int cout, int T,
+                                     double count, float* __restrict__ moments) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cout) return;
+  const double* S = gram;
+  const double* G = gram + T;
+  double mean = 0.0;
+  for (int t = 0; t < T; ++t) mean += static_cast<double>(w[c * T + t]) * S[t];
+  mean /= count;
+  double var = 0.0;
+  for (int a = 0; a < T; ++a) {
+    double row = 0.0;
+    for (int b = 0; b < T; ++b)
+      row += static_cast<double>(w[c * T + b]) * (G[a * T + b] / count - (S[a] / count) * (S[b] / count));
+    var += static_cast<double>(w[c * T + a]) * row;
+  }
+  moments[c] = static_cast<float>(mean);
+  moments[cout + c] = static_cast<float>(var > 0.0 ? var : 0.0);
+}
+
+// ------------------------------------------------------------------------------------------------ T1 = sum_w dP f'(z*) x[p* + t]
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(256)
+first_wgrad_fused_kernel(const float* __restrict__ x, int n_img, int c_total, int c_offset, int H, int W,
+                         const float* __restrict__ w_folded, const float* __restrict__ shift, float slope,
+                         const __nv_bfloat16* __restrict__ dp, float* __restrict__ t1) {
+  constexpr int T = 9 * CIN;
+  constexpr int G = COUT / 4;                  // channel groups of 4
+  constexpr int SLOTS = 256 / G;               // windows processed concurrently
+  constexpr int TWW = 16, TWH = 8;             // pooled-pixel (window) tile per iteration
+  __shared__ float s_in[CIN][2 * TWH + 2][2 * TWW + 2 + 1];
+  __shared__ float s_red[256];
+  const int cg = threadIdx.x % G, slot = threadIdx.x / G;
+  float wr[4][T], sh[4], acc[4][T];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    sh[j] = __ldg(shift + cg * 4 + j);
+#pragma unroll
+    for (int k = 0; k < T; ++k) { wr[j][k] = __ldg(w_folded + (cg * 4 + j) * T + k); acc[j][k] = 0.f; }
+  }
+  const int Hp = H >> 1, Wp = W >> 1;
+  const int tiles_x = (Wp + TWW - 1) / TWW, tiles_y = (Hp + TWH - 1) / TWH;
+  const long long total = static_cast<long long>(n_img) * tiles_x * tiles_y;
+  for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    const int tx = static_cast<int>(tile % tiles_x);
+    const int ty = static_cast<int>((tile / tiles_x) % tiles_y);
+    const int img = static_cast<int>(tile / (static_cast<long long>(tiles_x) * tiles_y));
+    __syncthreads();
+    for (int c = 0; c < CIN; ++c) {
+      const float* plane = x + (static_cast<size_t>(img) * c_total + c_offset + c) * H * W;
+      for (int i = threadIdx.x; i < (2 * TWH + 2) * (2 * TWW + 2); i += 256) {
+        const int r = i / (2 * TWW + 2), q = i % (2 * TWW + 2);
+        const int gy = 2 * ty * TWH - 1 + r, gx = 2 * tx * TWW - 1 + q;
+        s_in[c][r][q] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? __ldg(plane + static_cast<size_t>(gy) * W + gx) : 0.f;
+      }
+    }
+    __syncthreads();
+    for (int win = slot; win < TWW * TWH; win += SLOTS) {
+      const int wy = win / TWW, wx = win % TWW;
+      const int py = ty * TWH + wy, px = tx * TWW + wx;
+      if (py >= Hp || px >= Wp) continue;
+      const uint2 raw = __ldg(reinterpret_cast<const uint2*>(
+          dp + ((static_cast<size_t>(img) * Hp + py) * Wp + px) * COUT + cg * 4));
+      const float g[4] = {__uint_as_float(raw.x << 16), __uint_as_float(raw.x & 0xffff0000u),
+                          __uint_as_float(raw.y << 16), __uint_as_float(raw.y & 0xffff0000u)};
+      float patch[CIN][4][4];
+#pragma unroll
+      for (int c = 0; c < CIN; ++c)
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) patch[c][r][q] = s_in[c][2 * wy + r][2 * wx + q];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float z[4] = {sh[j], sh[j], sh[j], sh[j]};
+#pragma unroll
+        for (int c = 0; c < CIN; ++c)
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+              const float wv = wr[j][c * 9 + ky * 3 + kx];
+              z[0] = fmaf(wv, patch[c][ky][kx], z[0]);
+              z[1] = fmaf(wv, patch[c][ky][kx + 1], z[1]);
+              z[2] = fmaf(wv, patch[c][ky + 1][kx], z[2]);
+              z[3] = fmaf(wv, patch[c][ky + 1][kx + 1], z[3]);
+            }
+        int arg = 0;
+        float best = leaky(z[0], slope), zbest = z[0];
+#pragma unroll
+        for (int q = 1; q < 4; ++q) {
+          const float a = leaky(z[q], slope);
+          if (a > best) { best = a; arg = q; zbest = z[q]; }
+        }
+        const float gg = g[j] * (zbest > 0.f ? 1.f : slope);
+        const int dy = arg >> 1, dx = arg & 1;
+#pragma unroll
+        for (int c = 0; c < CIN; ++c)
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+              // patch[c][dy+ky][dx+kx] with a run-time (dy, dx): select among the four compile-time candidates
+              const float x00 = patch[c][ky][kx], x01 = patch[c][ky][kx + 1];
+              const float x10 = patch[c][ky + 1][kx], x11 = patch[c][ky + 1][kx + 1];
+              const float xv = dy ? (dx ? x11 : x10) : (dx ? x01 : x00);
+              acc[j][c * 9 + ky * 3 + kx] = fmaf(gg, xv, acc[j][c * 9 + ky * 3 + kx]);
+            }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int k = 0; k < T; ++k) {
+      __syncthreads();
+      s_red[threadIdx.x] = acc[j][k];
+      __syncthreads();
+      if (slot == 0) {
+        float s = 0.f;
+        for (int t = 0; t < SLOTS; ++t) s += s_red[t * G + cg];
+        atomicAdd(t1 + (cg * 4 + j) * T + k, s);
+      }
+    }
+}
+
+// dW[c,t] = scale_c [ T1 - m1 S_t - m2 invstd ((G w_c)[t] - mu S_t) ]
+__global__ void first_wgrad_finalize_kernel(const float* __restrict__ t1, const double* __restrict__ gram,
+                                            const float* __restrict__ w, const float* __restrict__ scale,
+                                            const float* __restrict__ mean, const float* __restrict__ invstd,
+                                            const float* __restrict__ sums, double count, int cout, int T,
+                                            float* __restrict__ dw) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cout * T) return;
+  const int c = i / T, t = i % T;
+  const double* S = gram;
+  const double* G = gram + T;
+  double gw = 0.0;
+  for (int b = 0; b < T; ++b) gw += G[t * T + b] * static_cast<double>(w[c * T + b]);
+  const double m1 = static_cast<double>(sums[c]) / count;
+  const double m2 = static_cast<double>(sums[cout + c]) / count;
+  const double v = static_cast<double>(t1[i]) - m1 * S[t] -
+                   m2 * static_cast<double>(invstd[c]) * (gw - static_cast<double>(mean[c]) * S[t]);
+  dw[i] = static_cast<float>(static_cast<double>(scale[c]) * v);
+}
+
+}  // namespace
+
+extern "C" {
+
+int ctk_first_patch_gram(const float* x, int n, int c_total, int c_offset, int cin, int H, int W, double* gram,
+                         void* stream) {
+  CTK_REQUIRE(x && gram && n > 0 && H > 0 && W > 0 && c_offset >= 0 && c_offset + cin <= c_total);
+  const int T = 9 * cin;
+  cudaStream_t s = ctk::as_stream(stream);
+  CTK_CUDA_TRY(cudaMemsetAsync(gram, 0, sizeof(double) * (T + T * T), s));
+  const int grid = ctk::num_sms() * 4;
+  if (cin == 1) patch_gram_kernel<1><<<grid, 256, 0, s>>>(x, n, c_total, c_offset, H, W, gram);
+  else if (cin == 2) patch_gram_kernel<2><<<grid, 256, 0, s>>>(x, n, c_total, c_offset, H, W, gram);
+  else return CTK_ERR_UNSUPPORTED;
+  return ctk::check_launch();
+}
+
+int ctk_first_moments(const double* gram, const float* w, int cout, int cin, double count, float* moments,
+                      void* stream) {
+  CTK_REQUIRE(gram && w && moments && cout > 0 && cin > 0 && count >= 1.0);
+  first_moments_kernel<<<(cout + 63) / 64, 64, 0, ctk::as_stream(stream)>>>(gram, w, cout, 9 * cin, count, moments);
+  return ctk::check_launch();
+}
+
+int ctk_first_wgrad_fused(const float* x, int n, int c_total, int c_offset, int cin, int H, int W, const float* w_folded,
+                          const float* shift, float slope, const void* dp_bf16, int cout, float* t1, void* stream) {
+  CTK_REQUIRE(x && w_folded && shift && dp_bf16 && t1 && n > 0 && H % 2 == 0 && W % 2 == 0);
+  CTK_REQUIRE(c_offset >= 0 && c_offset + cin <= c_total);
+  cudaStream_t s = ctk::as_stream(stream);
+  CTK_CUDA_TRY(cudaMemsetAsync(t1, 0, sizeof(float) * 9 * cin * cout, s));
+  const int grid = ctk::num_sms() * 4;
+  const __nv_bfloat16* dp = static_cast<const __nv_bfloat16*>(dp_bf16);
+  if (cin == 1 && cout == 64)
+    first_wgrad_fused_kernel<1, 64><<<grid, 256, 0, s>>>(x, n, c_total, c_offset, H, W, w_folded, shift, slope, dp, t1);
+  else if (cin == 2 && cout == 128)
+    first_wgrad_fused_kernel<2, 128><<<grid, 256, 0, s>>>(x, n, c_total, c_offset, H, W, w_folded, shift, slope, dp, t1);
+  else
+    return CTK_ERR_UNSUPPORTED;
+  return ctk::check_launch();
+}
+
+int ctk_first_wgrad_finalize(const float* t1, const double* gram, const float* w, const float* scale, const float* mean,
+                             const float* invstd, const float* sums, double count, int cout, int cin, float* dw,
+                             void* stream) {
+  CTK_REQUIRE(t1 && gram && w && scale && mean && invstd && sums && dw && cout > 0 && cin > 0 && count >= 1.0);
+  const int total = cout * 9 * cin;
+  first_wgrad_finalize_kernel<<<(total + 127) / 128, 128, 0, ctk::as_stream(stream)>>>(t1, gram, w, scale, mean, invstd,
+                                                                                       sums, count, cout, 9 * cin, dw);
+  return ctk::check_launch();
+}
+
+}  // extern "C"

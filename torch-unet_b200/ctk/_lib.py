@@ -54,6 +54,14 @@ _SIGNATURES = {
     "ctk_pack_conv_weight_dgrad_bf16": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "ctk_bn_finalize": (c_int, [c_void_p, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
                                 c_float, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "ctk_bn_finalize_moments": (c_int, [c_void_p, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                        c_float, c_float, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "ctk_first_patch_gram": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "ctk_first_moments": (c_int, [c_void_p, c_void_p, c_int, c_int, c_double, c_void_p, c_void_p]),
+    "ctk_first_wgrad_fused": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_float,
+                                      c_void_p, c_int, c_void_p, c_void_p]),
+    "ctk_first_wgrad_finalize": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_double,
+                                         c_int, c_int, c_void_p, c_void_p]),
     "ctk_bn_act_pool_fwd": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p, c_int,
                                     c_int, c_void_p]),
     "ctk_bn_bwd_reduce": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
@@ -123,7 +131,8 @@ KERNELS_PER_CALL = {"ctk_pearson_f32": 2, "ctk_fold_bn_eval": 1, "ctk_pack_conv_
                     "ctk_pack_fc1_weight_bf16": 1, "ctk_conv_first_eval": 1, "ctk_conv3x3_tc_eval": 1,
                     "ctk_gemm_bf16_splitk": 1, "ctk_head_eval": 1, "ctk_mse_loss": 1, "ctk_adam_multi": 1,
                     "ctk_conv_first_raw": 1, "ctk_conv3x3_tc_raw": 1, "ctk_pack_conv_weight_dgrad_bf16": 1,
-                    "ctk_bn_finalize": 1, "ctk_bn_act_pool_fwd": 1, "ctk_bn_bwd_reduce": 1, "ctk_bn_bwd_reduce_pooled": 1, "ctk_bn_bwd_apply": 1,
+                    "ctk_bn_finalize": 1, "ctk_bn_finalize_moments": 1, "ctk_first_patch_gram": 1,
+                    "ctk_first_moments": 1, "ctk_first_wgrad_fused": 1, "ctk_first_wgrad_finalize": 1, "ctk_bn_act_pool_fwd": 1, "ctk_bn_bwd_reduce": 1, "ctk_bn_bwd_reduce_pooled": 1, "ctk_bn_bwd_apply": 1,
                     "ctk_conv3x3_wgrad_tc": 1, "ctk_conv_first_wgrad": 1, "ctk_feat_transpose_bf16": 1,
                     "ctk_pack_fc1_weight_t_bf16": 1, "ctk_gemm_bf16_out_bf16": 1, "ctk_colstat": 1,
                     "ctk_bn1d_act_drop_fwd": 1, "ctk_sgemm_strided": 1, "ctk_head_out_fwd": 1, "ctk_head_out_bwd": 1,

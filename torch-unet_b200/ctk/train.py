@@ -44,6 +44,9 @@ class TrainEngine:
             raise _lib.CtkError("head layout differs from the reference (2 Dropout layers expected)")
         self.feat_channels = sum(b.channels[-1] for b in self.branches)
         self.params: List[torch.nn.Parameter] = list(model.parameters())
+        # "gram": first block's BN statistics and weight gradient from the input's patch Gram matrix (no full-resolution
+        # activation is stored); "stored": the generic path (raw conv output kept, generic BN backward + wgrad)
+        self.first_block_mode = "gram"
         self.forced_masks: Optional[Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]] = None
         self.on_grad_ready: Optional[Callable[[torch.nn.Parameter, torch.Tensor], None]] = None
         self.finalize_grads: Optional[Callable[[dict], dict]] = None      # e.g. parallel.GradSynchronizer.finalize
@@ -54,12 +57,12 @@ class TrainEngine:
     def _new(shape, dtype, dev):
         return torch.empty(shape, device=dev, dtype=dtype)
 
-    def _bn_finalize(self, sums, count, bias, bn, dev):
+    def _bn_finalize(self, sums, count, bias, bn, dev, moments=False):
         c = bn.num_features
         scale, shift, mean, invstd = (self._new((c,), torch.float32, dev) for _ in range(4))
         mom = 0.1 if bn.momentum is None else bn.momentum
         track = bn.track_running_stats and bn.running_mean is not None
-        call("ctk_bn_finalize", ptr(sums), c_double(count), ptr(bias), ptr(bn.weight), ptr(bn.bias),
+        call("ctk_bn_finalize_moments" if moments else "ctk_bn_finalize", ptr(sums), c_double(count), ptr(bias), ptr(bn.weight), ptr(bn.bias),
              ptr(bn.running_mean if track else None), ptr(bn.running_var if track else None),
              ptr(bn.num_batches_tracked if track else None), c_float(mom), c_float(bn.eps), c_int(c), ptr(scale), ptr(shift),
              ptr(mean), ptr(invstd), stream())
@@ -96,6 +99,33 @@ class TrainEngine:
             blocks = []
             for li, (conv, bn) in enumerate(br.pairs):
                 cout, cin = conv.out_channels, conv.in_channels
+                last = li == len(br.pairs) - 1
+                if last:
+                    dst, cstride, coff = feat, self.feat_channels, c_off
+                else:
+                    dst, cstride, coff = self._new((n, h // 2, w // 2, cout), torch.bfloat16, dev), cout, 0
+                if li == 0 and self.first_block_mode == "gram":
+                    # first block: statistics from the input's patch Gram matrix, then the fused eval-style kernel;
+                    # the full-resolution conv output is never written
+                    T = 9 * cin
+                    gram = self._new((T + T * T,), torch.float64, dev)
+                    call("ctk_first_patch_gram", ptr(x), c_int(n), c_int(c_total), c_int(br.c_offset), c_int(cin), c_int(h),
+                         c_int(w), ptr(gram), stream())
+                    mom = self._new((2 * cout,), torch.float32, dev)
+                    call("ctk_first_moments", ptr(gram), ptr(conv.weight), c_int(cout), c_int(cin), c_double(float(n) * h * w),
+                         ptr(mom), stream())
+                    scale, shift, mean, invstd = self._bn_finalize(mom, float(n) * h * w, conv.bias, bn, dev, moments=True)
+                    wfold = self._new((cout, T), torch.float32, dev)
+                    call("ctk_pack_first_weight", ptr(conv.weight), ptr(scale), c_int(cout), c_int(cin), ptr(wfold), stream())
+                    call("ctk_conv_first_eval", ptr(x), c_int(n), c_int(c_total), c_int(br.c_offset), c_int(cin), c_int(h),
+                         c_int(w), ptr(wfold), ptr(shift), c_int(cout), c_float(LEAKY_SLOPE), ptr(dst), c_int(cstride),
+                         c_int(coff), stream())
+                    blocks.append({"y": None, "x_in": None, "pooled": (dst, cstride, coff), "scale": scale, "shift": shift,
+                                   "mean": mean, "invstd": invstd, "h": h, "w": w, "conv": conv, "bn": bn, "gram": gram,
+                                   "wf": wfold})
+                    cur = dst
+                    h, w = h // 2, w // 2
+                    continue
                 y = self._new((n, h, w, cout), torch.bfloat16, dev)
                 stats = self._new((2 * cout,), torch.float32, dev)
                 if li == 0:
@@ -107,11 +137,6 @@ class TrainEngine:
                     call("ctk_conv3x3_tc_raw", ptr(cur), c_int(n), c_int(h), c_int(w), c_int(cin), ptr(wp), c_int(cout),
                          ptr(y), ptr(stats), stream(), meta={"flops": 2.0 * n * h * w * cout * 9 * cin})
                 scale, shift, mean, invstd = self._bn_finalize(stats, float(n) * h * w, conv.bias, bn, dev)
-                last = li == len(br.pairs) - 1
-                if last:
-                    dst, cstride, coff = feat, self.feat_channels, c_off
-                else:
-                    dst, cstride, coff = self._new((n, h // 2, w // 2, cout), torch.bfloat16, dev), cout, 0
                 call("ctk_bn_act_pool_fwd", ptr(y), c_int(n), c_int(h), c_int(w), c_int(cout), ptr(scale), ptr(shift),
                      c_float(LEAKY_SLOPE), ptr(dst), c_int(cstride), c_int(coff), stream())
                 blocks.append({"y": y, "x_in": cur, "pooled": (dst, cstride, coff), "scale": scale, "shift": shift, "mean": mean, "invstd": invstd,
@@ -269,6 +294,19 @@ class TrainEngine:
                      c_float(LEAKY_SLOPE), ptr(sums), stream())
                 done(bn.bias, sums[:cout])
                 done(bn.weight, sums[cout:])
+                if b.get("gram") is not None:
+                    if dp_cstride != cout or dp_coff != 0:
+                        raise _lib.CtkError("the first block's output gradient must be dense")
+                    T = 9 * cin
+                    t1 = self._new((cout, T), torch.float32, dev)
+                    call("ctk_first_wgrad_fused", ptr(x), c_int(n), c_int(x.shape[1]), c_int(br.c_offset), c_int(cin), c_int(h),
+                         c_int(w), ptr(b["wf"]), ptr(b["shift"]), c_float(LEAKY_SLOPE), ptr(dp), c_int(cout), ptr(t1), stream())
+                    dw = self._new(tuple(conv.weight.shape), torch.float32, dev)
+                    call("ctk_first_wgrad_finalize", ptr(t1), ptr(b["gram"]), ptr(conv.weight), ptr(b["scale"]), ptr(b["mean"]),
+                         ptr(b["invstd"]), ptr(sums), c_double(float(n) * h * w), c_int(cout), c_int(cin), ptr(dw), stream())
+                    done(conv.weight, dw)
+                    done(conv.bias, torch.zeros_like(conv.bias))
+                    continue
                 dy = self._new((n, h, w, cout), torch.bfloat16, dev)
                 call("ctk_bn_bwd_apply", ptr(b["y"]), ptr(dp), c_int(dp_cstride), c_int(dp_coff), c_int(n), c_int(h), c_int(w),
                      c_int(cout), ptr(b["scale"]), ptr(b["shift"]), ptr(b["mean"]), ptr(b["invstd"]), ptr(sums),
