@@ -175,16 +175,19 @@ int ctk_bn_finalize_moments(const float* moments, double count, const float* bia
  *   ctk_first_moments        moments[c] = batch mean, moments[cout+c] = biased batch variance of conv(x, w)[.,c] (no bias)
  *   (then ctk_bn_finalize_moments, ctk_pack_first_weight(w, scale) and ctk_conv_first_eval give the pooled output)
  *   ctk_first_wgrad_fused    t1[c][t] = sum_windows dP[w,c] * f'(z*) * x[argmax(w,c) + t]; recomputes the 2x2 window's
- *                            activations from x with the folded weights (first maximum wins); dp is dense bf16 NHWC
+ *                            activations from x with the folded weights (first maximum wins); dp is dense bf16 NHWC.
+ *                            Also sums[c] = sum dA (= d beta) and sums[cout+c] = sum dA*xhat (= d gamma), xhat taken
+ *                            from the recomputed fp32 z* (no bf16 round trip through the pooled tensor)
  *   ctk_first_wgrad_finalize dw[c][t] = scale_c (t1 - m1_c S_t - m2_c invstd_c ((G w_c)[t] - mean_c S_t)),
- *                            sums = [sum dA, sum dA*xhat] from ctk_bn_bwd_reduce_pooled, count = n*H*W
+ *                            m1 = sums[c]/count, m2 = sums[cout+c]/count, count = n*H*W
  * Replaces (train mode): nn.Conv2d + nn.BatchNorm2d statistics and their backward for regression_model.py:14-15,
  * two_branch_regression.py:10-11. */
 int ctk_first_patch_gram(const float* x, int n, int c_total, int c_offset, int cin, int H, int W, double* gram,
                          void* stream);
 int ctk_first_moments(const double* gram, const float* w, int cout, int cin, double count, float* moments, void* stream);
 int ctk_first_wgrad_fused(const float* x, int n, int c_total, int c_offset, int cin, int H, int W, const float* w_folded,
-                          const float* shift, float slope, const void* dp_bf16, int cout, float* t1, void* stream);
+                          const float* shift, const float* gamma, const float* beta, float slope, const void* dp_bf16,
+                          int cout, float* t1, float* sums, void* stream);
 int ctk_first_wgrad_finalize(const float* t1, const double* gram, const float* w, const float* scale, const float* mean,
                              const float* invstd, const float* sums, double count, int cout, int cin, float* dw,
                              void* stream);

@@ -165,3 +165,31 @@ def test_cpu_tensor_is_rejected():
     model = _build("single").eval()
     with pytest.raises(ctk.CtkError):
         model(torch.zeros(1, 2, 256, 256))
+
+
+def test_host_scorer_one_shot_and_stream(golden):
+    """Host-buffer API (pipeline.HostScorer): sliced one-shot call and the double-buffered stream give exactly what the
+    device-tensor path gives, for full, ragged and single-tile batches, and in order."""
+    import ctk
+    x = _inputs(golden)
+    model = _build("double")
+    model.load_state_dict(orc.randomize_bn(model.state_dict(), seed=7))
+    model = model.cuda().eval()
+    with torch.no_grad():
+        ref = model(x.cuda()).flatten().cpu()
+        r_ref = ctk.pearson_per_image(x.cuda()).cpu()
+    scorer = ctk.HostScorer(model, slice_tiles=3)
+    s, r = scorer.score(x.pin_memory())
+    assert torch.equal(s, ref) and torch.equal(r, r_ref)
+    # stream: batches of different sizes, results must come back in submission order
+    cuts = [(0, 4), (4, 5), (5, x.shape[0]), (0, 4)]
+    outs = list(scorer.score_stream(x[a:b].contiguous().pin_memory() for a, b in cuts))
+    assert len(outs) == len(cuts)
+    for (a, b), (s, r) in zip(cuts, outs):
+        assert torch.equal(s, ref[a:b]) and torch.equal(r, r_ref[a:b])
+    assert list(scorer.score_stream([])) == []
+    with pytest.raises(ctk.CtkError):
+        scorer.score(x.cuda())
+    model.train()
+    with pytest.raises(ctk.CtkError):
+        scorer.score(x)

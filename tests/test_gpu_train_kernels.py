@@ -258,11 +258,9 @@ def test_first_block_gram_path(L, cin, cout, coff):
            L.ptr(shift), c_int(cout), c_float(0.01), L.ptr(out), c_int(cout), c_int(0), L.stream())
     dpd = dp.to(torch.bfloat16).cuda()
     sums = torch.empty(2 * cout, device="cuda")
-    L.call("ctk_bn_bwd_reduce_pooled", L.ptr(out), c_int(cout), c_int(0), L.ptr(dpd), c_int(cout), c_int(0),
-           c_longlong(n * (H // 2) * (W // 2)), c_int(cout), L.ptr(gd), L.ptr(bd), c_float(0.01), L.ptr(sums), L.stream())
     t1 = torch.empty(cout, T, device="cuda")
     L.call("ctk_first_wgrad_fused", L.ptr(xd), c_int(n), c_int(2), c_int(coff), c_int(cin), c_int(H), c_int(W), L.ptr(wf),
-           L.ptr(shift), c_float(0.01), L.ptr(dpd), c_int(cout), L.ptr(t1), L.stream())
+           L.ptr(shift), L.ptr(gd), L.ptr(bd), c_float(0.01), L.ptr(dpd), c_int(cout), L.ptr(t1), L.ptr(sums), L.stream())
     dw = torch.empty(cout, cin, 3, 3, device="cuda")
     L.call("ctk_first_wgrad_finalize", L.ptr(t1), L.ptr(gram), L.ptr(wd), L.ptr(scale), L.ptr(mean), L.ptr(invstd),
            L.ptr(sums), c_double(count), c_int(cout), c_int(cin), L.ptr(dw), L.stream())
@@ -272,7 +270,6 @@ def test_first_block_gram_path(L, cin, cout, coff):
     np.testing.assert_allclose(rvd.cpu().numpy(), rv.numpy(), rtol=1e-4, atol=1e-6)
     assert rel_l2(out.float().cpu(), pooled.detach().permute(0, 2, 3, 1)) < 4e-3
     np.testing.assert_allclose(sums[:cout].cpu().numpy(), beta.grad.numpy(), rtol=1e-3, atol=1e-3)
-    np.testing.assert_allclose(sums[cout:].cpu().numpy(), gamma.grad.numpy(), rtol=2e-2, atol=0.2)
-    # dW is a small difference of large terms (BN removes the mean and the xhat component); sum-level error is set by
-    # the bf16-reconstructed dgamma above
-    assert rel_l2(dw.cpu(), w.grad) < 2e-2
+    np.testing.assert_allclose(sums[cout:].cpu().numpy(), gamma.grad.numpy(), rtol=1e-3, atol=2e-3)
+    # dW is a small difference of large terms (BN removes the mean and the xhat component of the gradient)
+    assert rel_l2(dw.cpu(), w.grad) < 2e-3

@@ -59,44 +59,63 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sums, int moments, 
 }
 
 // ---------------------------------------------------------------- forward: normalise + LeakyReLU + 2x2 max-pool
+// A thread keeps ONE 8-channel group for its whole grid-stride walk (the stride is a multiple of c8), so the per-channel
+// constants are loaded once, and it handles two pooled pixels per iteration with all eight 16-byte loads issued up front.
 __global__ void __launch_bounds__(256)
 bn_act_pool_fwd_kernel(const uint4* __restrict__ y, int H, int W, int c8, const float* __restrict__ scale,
                        const float* __restrict__ shift, float slope, __nv_bfloat16* __restrict__ out, int out_cstride,
-                       int out_coffset, long long total) {
+                       int out_coffset, long long pooled_pixels) {
   const int Hp = H >> 1, Wp = W >> 1;
-  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int cg = static_cast<int>(idx % c8);
-    long long pix = idx / c8;
-    const int px = static_cast<int>(pix % Wp);
-    pix /= Wp;
-    const int py = static_cast<int>(pix % Hp);
-    const long long n = pix / Hp;
-    float sc[8], sh[8], best[8];
+  const int slots = blockDim.x / c8;
+  const int cg = threadIdx.x % c8, slot = threadIdx.x / c8;
+  float sc[8], sh[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { sc[i] = __ldg(scale + cg * 8 + i); sh[i] = __ldg(shift + cg * 8 + i); }
-    const long long base = ((n * H + 2 * py) * W + 2 * px) * c8 + cg;
+  for (int i = 0; i < 8; ++i) { sc[i] = __ldg(scale + cg * 8 + i); sh[i] = __ldg(shift + cg * 8 + i); }
+  const long long stride = static_cast<long long>(gridDim.x) * slots;
+  for (long long pix0 = blockIdx.x * static_cast<long long>(slots) + slot; pix0 < pooled_pixels; pix0 += 2 * stride) {
+    uint4 raw[2][4];
+    long long obase[2];
+    bool on[2];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float f[8];
-      unpack8(__ldcs(y + base + ((j >> 1) * W + (j & 1)) * static_cast<long long>(c8)), f);
+    for (int u = 0; u < 2; ++u) {
+      const long long pix = pix0 + u * stride;
+      on[u] = pix < pooled_pixels;
+      const long long q = on[u] ? pix : pix0;
+      const int px = static_cast<int>(q % Wp);
+      const long long t = q / Wp;
+      const int py = static_cast<int>(t % Hp);
+      const long long n = t / Hp;
+      const long long base = ((n * H + 2 * py) * W + 2 * px) * c8 + cg;
+      obase[u] = q * static_cast<long long>(out_cstride) + out_coffset + cg * 8;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float a = leaky(fmaf(f[i], sc[i], sh[i]), slope);
-        best[i] = j == 0 ? a : fmaxf(best[i], a);
-      }
+      for (int j = 0; j < 4; ++j) raw[u][j] = __ldcs(y + base + ((j >> 1) * W + (j & 1)) * static_cast<long long>(c8));
     }
-    *reinterpret_cast<uint4*>(out + ((n * Hp + py) * Wp + px) * static_cast<long long>(out_cstride) + out_coffset + cg * 8) =
-        pack8(best);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      float best[8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float f[8];
+        unpack8(raw[u][j], f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float a = fmaf(f[i], sc[i], sh[i]);
+          best[i] = j == 0 ? a : fmaxf(best[i], a);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) best[i] = leaky(best[i], slope);     // monotone: activation after the max
+      if (on[u]) *reinterpret_cast<uint4*>(out + obase[u]) = pack8(best);
+    }
   }
 }
 
 // gradient of the activation output for the four positions of one window (8 channels): routes dP to the first maximum
-__device__ __forceinline__ void window_grads(const uint4* __restrict__ y, long long base, int W, int c8,
-                                             const float (&sc)[8], const float (&sh)[8], float slope,
-                                             const float (&dp)[8], float (&yv)[4][8], float (&da)[4][8]) {
+__device__ __forceinline__ void window_grads_raw(const uint4 (&raw)[4], const float (&sc)[8], const float (&sh)[8],
+                                                 float slope, const float (&dp)[8], float (&yv)[4][8],
+                                                 float (&da)[4][8]) {
 #pragma unroll
-  for (int j = 0; j < 4; ++j) unpack8(__ldg(y + base + ((j >> 1) * W + (j & 1)) * static_cast<long long>(c8)), yv[j]);
+  for (int j = 0; j < 4; ++j) unpack8(raw[j], yv[j]);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     float z[4], a[4];
@@ -110,6 +129,14 @@ __device__ __forceinline__ void window_grads(const uint4* __restrict__ y, long l
 #pragma unroll
     for (int j = 0; j < 4; ++j) da[j][i] = j == arg ? dp[i] * (z[j] > 0.f ? 1.f : slope) : 0.f;
   }
+}
+__device__ __forceinline__ void window_grads(const uint4* __restrict__ y, long long base, int W, int c8,
+                                             const float (&sc)[8], const float (&sh)[8], float slope,
+                                             const float (&dp)[8], float (&yv)[4][8], float (&da)[4][8]) {
+  uint4 raw[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) raw[j] = __ldg(y + base + ((j >> 1) * W + (j & 1)) * static_cast<long long>(c8));
+  window_grads_raw(raw, sc, sh, slope, dp, yv, da);
 }
 
 // ---------------------------------------------------------------- backward pass 1: sum(dA), sum(dA * xhat) per channel
@@ -185,18 +212,30 @@ bn_bwd_reduce_pooled_kernel(const __nv_bfloat16* __restrict__ pooled, int p_cstr
     be[i] = __ldg(beta + cg * 8 + i);
     s1[i] = 0.f; s2[i] = 0.f;
   }
-  for (long long pix = blockIdx.x * static_cast<long long>(slots) + slot; pix < pooled_pixels;
-       pix += static_cast<long long>(gridDim.x) * slots) {
-    float pv[8], dv[8];
-    unpack8(__ldcs(reinterpret_cast<const uint4*>(pooled + pix * p_cstride + p_coffset + cg * 8)), pv);
-    unpack8(__ldcs(reinterpret_cast<const uint4*>(dp + pix * dp_cstride + dp_coffset + cg * 8)), dv);
+  const long long stride = static_cast<long long>(gridDim.x) * slots;
+  for (long long pix0 = blockIdx.x * static_cast<long long>(slots) + slot; pix0 < pooled_pixels; pix0 += 4 * stride) {
+    uint4 rp[4], rd[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const bool pos = pv[i] > 0.f;
-      const float da = pos ? dv[i] : dv[i] * slope;
-      const float z = pos ? pv[i] : pv[i] * inv_slope;
-      s1[i] += da;
-      s2[i] = fmaf(da, (z - be[i]) * ig[i], s2[i]);
+    for (int u = 0; u < 4; ++u) {                      // eight independent 16-byte loads in flight per thread
+      const long long pix = pix0 + u * stride;
+      const long long q = pix < pooled_pixels ? pix : pix0;
+      rp[u] = __ldcs(reinterpret_cast<const uint4*>(pooled + q * p_cstride + p_coffset + cg * 8));
+      rd[u] = __ldcs(reinterpret_cast<const uint4*>(dp + q * dp_cstride + dp_coffset + cg * 8));
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (pix0 + u * stride >= pooled_pixels) break;
+      float pv[8], dv[8];
+      unpack8(rp[u], pv);
+      unpack8(rd[u], dv);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const bool pos = pv[i] > 0.f;
+        const float da = pos ? dv[i] : dv[i] * slope;
+        const float z = pos ? pv[i] : pv[i] * inv_slope;
+        s1[i] += da;
+        s2[i] = fmaf(da, (z - be[i]) * ig[i], s2[i]);
+      }
     }
   }
 #pragma unroll
@@ -215,50 +254,90 @@ bn_bwd_reduce_pooled_kernel(const __nv_bfloat16* __restrict__ pooled, int p_cstr
 }
 
 // ---------------------------------------------------------------- backward pass 2: dense gradient of the raw conv output
-__global__ void __launch_bounds__(256)
+// dY = sc (dA - m1 - xhat m2) with xhat = (y - mu) invstd  ==  sc dA + A y + B,  A = -sc invstd m2,  B = -sc m1 - A mu.
+// Same thread <-> channel-group mapping as the forward pass: constants live in registers for the whole walk.
+__global__ void __launch_bounds__(256, 2)
 bn_bwd_apply_kernel(const uint4* __restrict__ y, const __nv_bfloat16* __restrict__ dp, int dp_cstride, int dp_coffset,
                     int H, int W, int c8, const float* __restrict__ scale, const float* __restrict__ shift,
                     const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ sums,
-                    float inv_count, float slope, uint4* __restrict__ dy, long long total) {
+                    float inv_count, float slope, uint4* __restrict__ dy, long long pooled_pixels) {
   const int Hp = H >> 1, Wp = W >> 1;
   const int c = c8 * 8;
-  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int cg = static_cast<int>(idx % c8);
-    const long long pix = idx / c8;
-    const int px = static_cast<int>(pix % Wp);
-    const long long t = pix / Wp;
-    const int py = static_cast<int>(t % Hp);
-    const long long n = t / Hp;
-    float sc[8], sh[8], mu[8], is[8], m1[8], m2[8];
+  const int slots = blockDim.x / c8;
+  const int cg = threadIdx.x % c8, slot = threadIdx.x / c8;
+  float sc[8], sh[8], ca[8], cb[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      sc[i] = __ldg(scale + cg * 8 + i); sh[i] = __ldg(shift + cg * 8 + i);
-      mu[i] = __ldg(mean + cg * 8 + i); is[i] = __ldg(invstd + cg * 8 + i);
-      m1[i] = __ldg(sums + cg * 8 + i) * inv_count;
-      m2[i] = __ldg(sums + c + cg * 8 + i) * inv_count;
+  for (int i = 0; i < 8; ++i) {
+    sc[i] = __ldg(scale + cg * 8 + i); sh[i] = __ldg(shift + cg * 8 + i);
+    const float mu = __ldg(mean + cg * 8 + i), is = __ldg(invstd + cg * 8 + i);
+    const float m1 = __ldg(sums + cg * 8 + i) * inv_count, m2 = __ldg(sums + c + cg * 8 + i) * inv_count;
+    ca[i] = -sc[i] * is * m2;
+    cb[i] = -sc[i] * m1 - ca[i] * mu;
+  }
+  const long long stride = static_cast<long long>(gridDim.x) * slots;
+  for (long long pix0 = blockIdx.x * static_cast<long long>(slots) + slot; pix0 < pooled_pixels; pix0 += 2 * stride) {
+    uint4 raw[2][4], rdp[2];
+    long long base[2];
+    bool on[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const long long pix = pix0 + u * stride;
+      on[u] = pix < pooled_pixels;
+      const long long q = on[u] ? pix : pix0;
+      const int px = static_cast<int>(q % Wp);
+      const long long t = q / Wp;
+      const int py = static_cast<int>(t % Hp);
+      const long long n = t / Hp;
+      base[u] = ((n * H + 2 * py) * W + 2 * px) * c8 + cg;
+      rdp[u] = __ldcs(reinterpret_cast<const uint4*>(dp + q * dp_cstride + dp_coffset + cg * 8));
+#pragma unroll
+      for (int j = 0; j < 4; ++j) raw[u][j] = __ldcs(y + base[u] + ((j >> 1) * W + (j & 1)) * static_cast<long long>(c8));
     }
-    float dpv[8], yv[4][8], da[4][8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(dp + pix * dp_cstride + dp_coffset + cg * 8)), dpv);
-    const long long base = ((n * H + 2 * py) * W + 2 * px) * c8 + cg;
-    window_grads(y, base, W, c8, sc, sh, slope, dpv, yv, da);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float g[8];
+    for (int u = 0; u < 2; ++u) {
+      if (!on[u]) break;
+      // one 32-bit word (two channels) of the four window positions at a time keeps the live set small
+      uint32_t o[4][4];
+      const uint32_t dw[4] = {rdp[u].x, rdp[u].y, rdp[u].z, rdp[u].w};
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float xhat = (yv[j][i] - mu[i]) * is[i];
-        g[i] = sc[i] * (da[j][i] - m1[i] - xhat * m2[i]);     // sc = gamma * invstd
+      for (int k = 0; k < 4; ++k) {
+        float g[4][2];
+#pragma unroll
+        for (int hsel = 0; hsel < 2; ++hsel) {
+          const int i = 2 * k + hsel;
+          const float dpi = hsel ? __uint_as_float(dw[k] & 0xffff0000u) : __uint_as_float(dw[k] << 16);
+          float yv[4], z[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t w = k == 0 ? raw[u][j].x : k == 1 ? raw[u][j].y : k == 2 ? raw[u][j].z : raw[u][j].w;
+            yv[j] = hsel ? __uint_as_float(w & 0xffff0000u) : __uint_as_float(w << 16);
+            z[j] = fmaf(yv[j], sc[i], sh[i]);
+          }
+          // LeakyReLU is monotone, so the first maximum of the activations is the first maximum of z
+          int arg = 0;
+          float best = z[0];
+#pragma unroll
+          for (int j = 1; j < 4; ++j)
+            if (z[j] > best) { best = z[j]; arg = j; }
+          const float top = sc[i] * dpi * (best > 0.f ? 1.f : slope);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) g[j][hsel] = fmaf(ca[i], yv[j], cb[i]) + (j == arg ? top : 0.f);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j][k] = pack_bf16x2(g[j][0], g[j][1]);
       }
-      dy[base + ((j >> 1) * W + (j & 1)) * static_cast<long long>(c8)] = pack8(g);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        dy[base[u] + ((j >> 1) * W + (j & 1)) * static_cast<long long>(c8)] = make_uint4(o[j][0], o[j][1], o[j][2], o[j][3]);
     }
   }
 }
 
-inline int grid_for(long long total, int threads) {
-  const long long blocks = (total + threads - 1) / threads;
-  const long long cap = static_cast<long long>(ctk::num_sms()) * 16;
-  return static_cast<int>(blocks < cap ? blocks : cap);
+// grid for the pooled-pixel walks: `slots` pooled pixels per CTA pass, a few CTAs per SM
+inline int grid_for_pixels(long long pooled_pixels, int slots, int per_iter) {
+  const long long blocks = (pooled_pixels + static_cast<long long>(slots) * per_iter - 1) / (static_cast<long long>(slots) * per_iter);
+  const long long cap = static_cast<long long>(ctk::num_sms()) * 8;
+  return static_cast<int>(blocks < 1 ? 1 : (blocks < cap ? blocks : cap));
 }
 
 }  // namespace
@@ -298,10 +377,13 @@ int ctk_bn_act_pool_fwd(const void* y_bf16, int n, int H, int W, int channels, c
   CTK_REQUIRE(y_bf16 && scale && shift && out_bf16 && n > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0);
   CTK_REQUIRE(channels > 0 && channels % 8 == 0 && out_cstride % 8 == 0 && out_coffset % 8 == 0 &&
               out_coffset + channels <= out_cstride);
-  const long long total = static_cast<long long>(n) * (H / 2) * (W / 2) * (channels / 8);
-  bn_act_pool_fwd_kernel<<<grid_for(total, 256), 256, 0, ctk::as_stream(stream)>>>(
-      static_cast<const uint4*>(y_bf16), H, W, channels / 8, scale, shift, slope, static_cast<__nv_bfloat16*>(out_bf16),
-      out_cstride, out_coffset, total);
+  CTK_REQUIRE(channels <= 2048);
+  const int c8 = channels / 8;
+  const int threads = (256 / c8) * c8;                 // a whole number of channel groups per CTA
+  const long long pooled = static_cast<long long>(n) * (H / 2) * (W / 2);
+  bn_act_pool_fwd_kernel<<<grid_for_pixels(pooled, threads / c8, 2), threads, 0, ctk::as_stream(stream)>>>(
+      static_cast<const uint4*>(y_bf16), H, W, c8, scale, shift, slope, static_cast<__nv_bfloat16*>(out_bf16),
+      out_cstride, out_coffset, pooled);
   return ctk::check_launch();
 }
 
@@ -351,11 +433,14 @@ int ctk_bn_bwd_apply(const void* y_bf16, const void* dp_bf16, int dp_cstride, in
               W % 2 == 0);
   CTK_REQUIRE(channels > 0 && channels % 8 == 0 && dp_cstride % 8 == 0 && dp_coffset % 8 == 0 &&
               dp_coffset + channels <= dp_cstride);
-  const long long total = static_cast<long long>(n) * (H / 2) * (W / 2) * (channels / 8);
+  CTK_REQUIRE(channels <= 2048);
+  const int c8 = channels / 8;
+  const int threads = (256 / c8) * c8;
+  const long long pooled = static_cast<long long>(n) * (H / 2) * (W / 2);
   const float inv_count = 1.f / (static_cast<float>(n) * H * W);
-  bn_bwd_apply_kernel<<<grid_for(total, 256), 256, 0, ctk::as_stream(stream)>>>(
+  bn_bwd_apply_kernel<<<grid_for_pixels(pooled, threads / c8, 2), threads, 0, ctk::as_stream(stream)>>>(
       static_cast<const uint4*>(y_bf16), static_cast<const __nv_bfloat16*>(dp_bf16), dp_cstride, dp_coffset, H, W,
-      channels / 8, scale, shift, mean, invstd, sums, inv_count, slope, static_cast<uint4*>(dy_bf16), total);
+      c8, scale, shift, mean, invstd, sums, inv_count, slope, static_cast<uint4*>(dy_bf16), pooled);
   return ctk::check_launch();
 }
 

@@ -20,7 +20,8 @@
 //
 // Warp roles (384 threads): warp 0 = B producer, warp 3 = A producer (one lane each), warp 1 = MMA issuer
 // (one lane, pair leader only), warp 2 = TMEM allocator, warps 4-11 = epilogue (TMEM -> registers ->
-// scale/shift -> LeakyReLU -> 2x2 max via two butterfly shuffle stages -> 16-byte NHWC stores).
+// scale/shift -> 2x2 max via two butterfly shuffle stages -> LeakyReLU -> 16-byte NHWC stores), compiled per
+// epilogue flavour (eval / raw / raw + batch statistics).
 // Accumulators are double buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include "ctk_common.h"
 #include "ctk_ptx.cuh"
@@ -43,18 +44,51 @@ constexpr int kThreads = 128 + 32 * kEpiWarps;
 constexpr uint32_t kABytes = kHaloH * kHaloW * 128;                       // 23040
 constexpr int kAStageBytes = ((kABytes + 1023) / 1024) * 1024;            // 23552
 
-template <int kCtaGroup, int kBlockN>
+// Epilogue flavours (compile time, so the hot loop carries no run-time mode predicates):
+enum : int {
+  kEpiEvalPool = 0,   // folded BN -> 2x2 max-pool -> LeakyReLU, pooled bf16 store (the inference block)
+  kEpiEvalAny = 1,    // folded BN with run-time pool / activation switches (CTK_CONV_NO_POOL / CTK_CONV_NO_ACT)
+  kEpiRaw = 2,        // bf16 store of the raw accumulators (dgrad)
+  kEpiRawStats = 3    // raw store + per-channel sum / sum of squares of the fp32 accumulators (train-mode forward)
+};
+constexpr int kScratchPitch = 36;                                  // floats; 16-byte aligned rows, conflict-free both ways
+constexpr int kScratchBytes = kEpiWarps * 32 * kScratchPitch * 4;  // per-warp transpose tile for the statistics
+constexpr int kCtrlBytes = 8192;
+
+template <int kCtaGroup, int kBlockN, int kEpi>
 struct Cfg {
   static constexpr int kBRows = kBlockN / kCtaGroup;          // weight rows this CTA loads per (chunk, tap)
   static constexpr int kBStageBytes = kBRows * 128;
-  static constexpr int kBStages = std::min(12, (200 * 1024 - kAStages * kAStageBytes) / kBStageBytes);
+  static constexpr int kExtra = kEpi == kEpiRawStats ? kScratchBytes : 0;
+  static constexpr int kBStages =
+      std::min(12, (227 * 1024 - 1024 - kCtrlBytes - kExtra - kAStages * kAStageBytes) / kBStageBytes);
   static constexpr int kTmemCols = kAccStages * kBlockN;
-  static constexpr int kSmemBytes = 1024 + kAStages * kAStageBytes + kBStages * kBStageBytes + 12288;
+  static constexpr int kSmemBytes = 1024 + kAStages * kAStageBytes + kBStages * kBStageBytes + kCtrlBytes + kExtra;
 };
+
+// n / d for 0 <= n < 2^31 by multiply-high (Granlund-Montgomery, 31-bit dividend): the role loops decode a work index
+// per tile, and a run-time integer division costs ~45 instructions each in every one of the 11 warps
+struct FastDiv {
+  uint32_t d, mul, shr;
+};
+inline FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f = {d, 0u, 0u};
+  if (d > 1) {
+    uint32_t l = 0;
+    while ((1u << l) < d) ++l;
+    f.mul = static_cast<uint32_t>(((1ull << (31 + l)) + d - 1) / d);
+    f.shr = l - 1;
+  }
+  return f;
+}
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) {
+  return f.d == 1 ? n : (__umulhi(n, f.mul) >> f.shr);
+}
 
 struct ConvParams {
   int n_img, H, W, cin, cout;
   int tiles_x, tiles_y, tiles_n, spatial_tiles, total_work;
+  FastDiv div_n, div_x, div_y;
   int pool, act;
   float slope;
   const float* scale;   // nullptr = identity (raw conv output)
@@ -72,39 +106,162 @@ struct TileCoord {
 template <int kCtaGroup, int kBlockN>
 __device__ __forceinline__ TileCoord decode_work(const ConvParams& p, int work, int rank) {
   TileCoord t;
-  const int nt = work % p.tiles_n;
-  int sp = (work / p.tiles_n) * kCtaGroup + rank;     // may be >= spatial_tiles for the padded last pair: img >= n_img
-  const int tx = sp % p.tiles_x;
-  sp /= p.tiles_x;
-  const int ty = sp % p.tiles_y;
-  t.img = sp / p.tiles_y;
+  const uint32_t wq = fdiv(static_cast<uint32_t>(work), p.div_n);
+  const int nt = work - static_cast<int>(wq) * p.tiles_n;
+  const uint32_t sp = wq * kCtaGroup + rank;          // may be >= spatial_tiles for the padded last pair: img >= n_img
+  const uint32_t q1 = fdiv(sp, p.div_x);
+  const int tx = static_cast<int>(sp - q1 * p.tiles_x);
+  const uint32_t q2 = fdiv(q1, p.div_y);
+  const int ty = static_cast<int>(q1 - q2 * p.tiles_y);
+  t.img = static_cast<int>(q2);
   t.y0 = ty * kTileH;
   t.x0 = tx * kTileW;
   t.n0 = nt * kBlockN;
   return t;
 }
 
-template <int kCtaGroup, int kBlockN>
+template <int kCtaGroup, int kBlockN, int kEpi>
 struct SmemLayout {
-  using C = Cfg<kCtaGroup, kBlockN>;
+  using C = Cfg<kCtaGroup, kBlockN, kEpi>;
   uint64_t a_full[kAStages], a_empty[kAStages];
   uint64_t b_full[C::kBStages], b_empty[C::kBStages];
   uint64_t acc_full[kAccStages], acc_empty[kAccStages];
   uint32_t tmem_base;
   uint32_t pad[3];
-  alignas(16) float scale[2][kBlockN];
-  alignas(16) float shift[2][kBlockN];
-  float stat_sum[512];      // per-CTA partial statistics (train mode), flushed once at the end
-  float stat_sq[512];
+  // eval: folded-BN scale / shift of ALL output channels (cout <= 512), staged once per CTA;
+  // train (raw + statistics): the same arrays hold the per-CTA partial sum / sum of squares, flushed once at the end
+  alignas(16) float ch_a[512];
+  alignas(16) float ch_b[512];
 };
 
-template <int kCtaGroup, int kBlockN>
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float lds32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__device__ __forceinline__ void red_shared_add(uint32_t addr, float v) {
+  asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+
+struct EpiCtx {
+  int lane, y, x, Hp, Wp;
+  bool valid;
+  uint32_t sc_addr, sh_addr;      // shared-space addresses of ch_a / ch_b
+  uint32_t scratch_addr;          // this warp's transpose tile (statistics)
+  __nv_bfloat162 slope2;
+};
+
+// One 32-lane x 32-column block of fp32 accumulators (lane = output pixel, v[i] = channel ch0 + i of the tile).
+template <int kEpi>
+__device__ __forceinline__ void epilogue_block(const ConvParams& p, const EpiCtx& e, const TileCoord& t, int ch0,
+                                               const uint32_t (&v)[32]) {
+  const int lane = e.lane;
+  uint32_t pk[16];
+  if constexpr (kEpi == kEpiRaw || kEpi == kEpiRawStats) {
+    if constexpr (kEpi == kEpiRawStats) {
+      // batch statistics of the raw conv output: transpose the 32 x 32 block through this warp's scratch tile so that
+      // lane c can sum channel c over the warp's 32 pixels (8 STS.128 + 32 LDS + 64 math instead of a 31-shuffle
+      // butterfly per moment)
+      const uint32_t row = e.scratch_addr + static_cast<uint32_t>(lane * kScratchPitch * 4);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float a = e.valid ? __uint_as_float(v[4 * j]) : 0.f, b = e.valid ? __uint_as_float(v[4 * j + 1]) : 0.f;
+        const float c = e.valid ? __uint_as_float(v[4 * j + 2]) : 0.f, d = e.valid ? __uint_as_float(v[4 * j + 3]) : 0.f;
+        sts128(row + j * 16, a, b, c, d);
+      }
+      __syncwarp();
+      float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+      const uint32_t col = e.scratch_addr + static_cast<uint32_t>(lane * 4);
+#pragma unroll
+      for (int l = 0; l < 32; l += 2) {
+        const float x0 = lds32(col + l * kScratchPitch * 4);
+        const float x1 = lds32(col + (l + 1) * kScratchPitch * 4);
+        s0 += x0; q0 = fmaf(x0, x0, q0);
+        s1 += x1; q1 = fmaf(x1, x1, q1);
+      }
+      __syncwarp();
+      red_shared_add(e.sc_addr + static_cast<uint32_t>((t.n0 + ch0 + lane) * 4), s0 + s1);
+      red_shared_add(e.sh_addr + static_cast<uint32_t>((t.n0 + ch0 + lane) * 4), q0 + q1);
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+    if (e.valid) {
+      __nv_bfloat16* dst = p.out +
+          (static_cast<size_t>(t.img) * p.H * p.W + static_cast<size_t>(e.y) * p.W + e.x) * p.out_cstride +
+          p.out_coffset + t.n0 + ch0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        reinterpret_cast<uint4*>(dst)[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+    }
+    return;
+  } else {
+    const uint32_t sc = e.sc_addr + static_cast<uint32_t>((t.n0 + ch0) * 4);
+    const uint32_t sh = e.sh_addr + static_cast<uint32_t>((t.n0 + ch0) * 4);
+    const bool act_first = kEpi == kEpiEvalAny && p.act && !p.pool;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 a = lds128(sc + j * 16), b = lds128(sh + j * 16);
+      float f0 = fmaf(__uint_as_float(v[4 * j]), a.x, b.x), f1 = fmaf(__uint_as_float(v[4 * j + 1]), a.y, b.y);
+      float f2 = fmaf(__uint_as_float(v[4 * j + 2]), a.z, b.z), f3 = fmaf(__uint_as_float(v[4 * j + 3]), a.w, b.w);
+      if (act_first) { f0 = leaky(f0, p.slope); f1 = leaky(f1, p.slope); f2 = leaky(f2, p.slope); f3 = leaky(f3, p.slope); }
+      pk[2 * j] = pack_bf16x2(f0, f1);
+      pk[2 * j + 1] = pack_bf16x2(f2, f3);
+    }
+    if (kEpi == kEpiEvalPool || p.pool) {
+      // 2x2 max over lanes {l, l^1, l^8}: each butterfly stage halves the channels a lane keeps
+      const bool odd_x = (lane & 1) != 0;
+      uint32_t q[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t send = odd_x ? pk[i] : pk[8 + i];
+        const uint32_t keep = odd_x ? pk[8 + i] : pk[i];
+        q[i] = max_bf16x2(keep, __shfl_xor_sync(0xffffffffu, send, 1));
+      }
+      const bool odd_y = (lane & 8) != 0;
+      uint4 o;
+      uint32_t* ov = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t send = odd_y ? q[i] : q[4 + i];
+        const uint32_t keep = odd_y ? q[4 + i] : q[i];
+        ov[i] = max_bf16x2(keep, __shfl_xor_sync(0xffffffffu, send, 8));
+        if (kEpi == kEpiEvalPool || p.act) ov[i] = leaky_bf16x2(ov[i], e.slope2);   // after the pool: 4x fewer elements
+      }
+      if (e.valid) {
+        const int ch = t.n0 + ch0 + (odd_x ? 16 : 0) + (odd_y ? 8 : 0);
+        __nv_bfloat16* dst = p.out +
+            (static_cast<size_t>(t.img) * e.Hp * e.Wp + static_cast<size_t>(e.y >> 1) * e.Wp + (e.x >> 1)) * p.out_cstride +
+            p.out_coffset + ch;
+        *reinterpret_cast<uint4*>(dst) = o;
+      }
+    } else if (e.valid) {
+      __nv_bfloat16* dst = p.out +
+          (static_cast<size_t>(t.img) * p.H * p.W + static_cast<size_t>(e.y) * p.W + e.x) * p.out_cstride +
+          p.out_coffset + t.n0 + ch0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        reinterpret_cast<uint4*>(dst)[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+    }
+  }
+}
+
+template <int kCtaGroup, int kBlockN, int kEpi>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                   const ConvParams p) {
-  using C = Cfg<kCtaGroup, kBlockN>;
-  using SL = SmemLayout<kCtaGroup, kBlockN>;
-  static_assert(sizeof(SL) <= 12288, "barrier block too large");
+  using C = Cfg<kCtaGroup, kBlockN, kEpi>;
+  using SL = SmemLayout<kCtaGroup, kBlockN, kEpi>;
+  static_assert(sizeof(SL) <= kCtrlBytes, "barrier block too large");
+  static_assert(C::kBStages >= 4, "too few weight stages");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* a_smem = smem;
@@ -127,8 +284,15 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     tma_prefetch_desc(&tm_b);
   }
   if (warp == 2) tmem_alloc<kCtaGroup>(&sl->tmem_base, C::kTmemCols);
-  if (p.stats != nullptr)
-    for (int i = threadIdx.x; i < 512; i += kThreads) { sl->stat_sum[i] = 0.f; sl->stat_sq[i] = 0.f; }
+  for (int i = threadIdx.x; i < 512; i += kThreads) {
+    if constexpr (kEpi == kEpiEvalPool || kEpi == kEpiEvalAny) {
+      sl->ch_a[i] = i < p.cout ? __ldg(p.scale + i) : 0.f;
+      sl->ch_b[i] = i < p.cout ? __ldg(p.shift + i) : 0.f;
+    } else {
+      sl->ch_a[i] = 0.f;
+      sl->ch_b[i] = 0.f;
+    }
+  }
   tc_fence_before();
   __syncthreads();
   if constexpr (kCtaGroup == 2) cluster_sync_all();   // peer barriers / TMEM must exist before anything remote
@@ -242,106 +406,65 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     }
   } else if (warp >= 4) {
     // ---------------- epilogue: thread <-> TMEM lane <-> output pixel of this CTA's tile; the two warps that share a
-    // lane quadrant (warp % 4) take alternate 32-column blocks
+    // lane quadrant (warp % 4) take alternate 32-column blocks.  TMEM loads are software pipelined: the block after the
+    // one being processed is already in flight, and the accumulator stage is released as soon as the last load landed.
     const int ew = warp & 3;
     const int half = (warp - 4) >> 2;
     const int m = ew * 32 + lane;
     const int r = m >> 3, cpx = m & 7;
     const int et = threadIdx.x - 128;
-    const int Hp = p.H >> 1, Wp = p.W >> 1;
-    const __nv_bfloat162 slope2 = __float2bfloat162_rn(p.slope);
+    constexpr int kBlocks = kBlockN / 32;
+    constexpr int kPerWarp = kBlocks / 2;
+    static_assert(kBlocks % 2 == 0 && kEpiWarps == 8, "two epilogue warps per lane quadrant");
+    EpiCtx e;
+    e.lane = lane;
+    e.Hp = p.H >> 1;
+    e.Wp = p.W >> 1;
+    e.sc_addr = smem_u32(sl->ch_a);
+    e.sh_addr = smem_u32(sl->ch_b);
+    e.scratch_addr = smem_u32(reinterpret_cast<uint8_t*>(sl) + kCtrlBytes) + static_cast<uint32_t>((warp - 4) * 32 * kScratchPitch * 4);
+    e.slope2 = __float2bfloat162_rn(p.slope);
     int it = 0;
     for (int work = work0; work < p.total_work; work += work_stride, ++it) {
       const TileCoord t = decode_work<kCtaGroup, kBlockN>(p, work, rank);
       const int acc = it & 1;
       const int acc_phase = (it >> 1) & 1;
-      float* s_scale = sl->scale[it & 1];
-      float* s_shift = sl->shift[it & 1];
-      for (int i = et; i < kBlockN; i += 32 * kEpiWarps) {
-        s_scale[i] = p.scale ? __ldg(p.scale + t.n0 + i) : 1.f;
-        s_shift[i] = p.scale ? __ldg(p.shift + t.n0 + i) : 0.f;
-      }
-      asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+      e.y = t.y0 + r;
+      e.x = t.x0 + cpx;
+      e.valid = t.img < p.n_img && e.y < p.H && e.x < p.W;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(acc * kBlockN);
       mbar_wait(&sl->acc_full[acc], acc_phase);
       tc_fence_after();
-      const int y = t.y0 + r, x = t.x0 + cpx;
-      const bool valid = t.img < p.n_img && y < p.H && x < p.W;
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(acc * kBlockN);
-#pragma unroll 1
-      for (int cb = half; cb < kBlockN / 32; cb += kEpiWarps / 4) {
-        uint32_t v[32];
-        tmem_ld_32x32(taddr + cb * 32, v);
+      auto release = [&]() {
+        // every TMEM read of this warp for the tile has completed: one arrival per warp on the (leader's) barrier
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (kCtaGroup == 1) mbar_arrive(&sl->acc_empty[acc]);
+          else mbar_arrive_cluster(mapa_shared(smem_u32(&sl->acc_empty[acc]), 0));
+        }
+      };
+      uint32_t va[32], vb[32];
+      tmem_ld_32x32(taddr + half * 32, va);
+#pragma unroll
+      for (int i = 0; i < kPerWarp; i += 2) {
         tmem_ld_wait();
-        if (p.stats != nullptr) {
-          // train mode: batch statistics of the raw conv output, reduced over this warp's 32 pixels
-          float f[32], sq[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            f[i] = valid ? __uint_as_float(v[i]) : 0.f;
-            sq[i] = f[i] * f[i];
-          }
-          const float tot = warp_transpose_sum32(f, lane);
-          const float tot2 = warp_transpose_sum32(sq, lane);
-          atomicAdd(&sl->stat_sum[t.n0 + cb * 32 + lane], tot);
-          atomicAdd(&sl->stat_sq[t.n0 + cb * 32 + lane], tot2);
+        if (i + 1 < kPerWarp) tmem_ld_32x32(taddr + (half + 2 * (i + 1)) * 32, vb);
+        else release();
+        epilogue_block<kEpi>(p, e, t, (half + 2 * i) * 32, va);
+        if (i + 1 < kPerWarp) {
+          tmem_ld_wait();
+          if (i + 2 < kPerWarp) tmem_ld_32x32(taddr + (half + 2 * (i + 2)) * 32, va);
+          else release();
+          epilogue_block<kEpi>(p, e, t, (half + 2 * (i + 1)) * 32, vb);
         }
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float f0 = fmaf(__uint_as_float(v[2 * i]), s_scale[cb * 32 + 2 * i], s_shift[cb * 32 + 2 * i]);
-          float f1 = fmaf(__uint_as_float(v[2 * i + 1]), s_scale[cb * 32 + 2 * i + 1], s_shift[cb * 32 + 2 * i + 1]);
-          if (p.act && !p.pool) { f0 = leaky(f0, p.slope); f1 = leaky(f1, p.slope); }
-          pk[i] = pack_bf16x2(f0, f1);
-        }
-        if (p.pool) {
-          // 2x2 max over lanes {l, l^1, l^8}: each butterfly stage halves the channels a lane keeps
-          const bool odd_x = (lane & 1) != 0;
-          uint32_t q[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const uint32_t send = odd_x ? pk[i] : pk[8 + i];
-            const uint32_t keep = odd_x ? pk[8 + i] : pk[i];
-            q[i] = max_bf16x2(keep, __shfl_xor_sync(0xffffffffu, send, 1));
-          }
-          const bool odd_y = (lane & 8) != 0;
-          uint4 o;
-          uint32_t* ov = reinterpret_cast<uint32_t*>(&o);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const uint32_t send = odd_y ? q[i] : q[4 + i];
-            const uint32_t keep = odd_y ? q[4 + i] : q[i];
-            ov[i] = max_bf16x2(keep, __shfl_xor_sync(0xffffffffu, send, 8));
-            if (p.act) ov[i] = leaky_bf16x2(ov[i], slope2);      // activation after the pool: 4x fewer elements
-          }
-          if (valid) {
-            const int ch = t.n0 + cb * 32 + (odd_x ? 16 : 0) + (odd_y ? 8 : 0);
-            __nv_bfloat16* dst = p.out +
-                (static_cast<size_t>(t.img) * Hp * Wp + static_cast<size_t>(y >> 1) * Wp + (x >> 1)) * p.out_cstride +
-                p.out_coffset + ch;
-            *reinterpret_cast<uint4*>(dst) = o;
-          }
-        } else if (valid) {
-          __nv_bfloat16* dst = p.out +
-              (static_cast<size_t>(t.img) * p.H * p.W + static_cast<size_t>(y) * p.W + x) * p.out_cstride +
-              p.out_coffset + t.n0 + cb * 32;
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            reinterpret_cast<uint4*>(dst)[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
-        }
-      }
-      // this warp has drained its TMEM quadrant: one arrival per warp on the (leader's) accumulator-empty barrier
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if constexpr (kCtaGroup == 1) mbar_arrive(&sl->acc_empty[acc]);
-        else mbar_arrive_cluster(mapa_shared(smem_u32(&sl->acc_empty[acc]), 0));
       }
     }
-    if (p.stats != nullptr) {
+    if constexpr (kEpi == kEpiRawStats) {
       asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
       for (int i = et; i < p.cout; i += 32 * kEpiWarps) {
-        atomicAdd(p.stats + i, sl->stat_sum[i]);
-        atomicAdd(p.stats + p.cout + i, sl->stat_sq[i]);
+        atomicAdd(p.stats + i, sl->ch_a[i]);
+        atomicAdd(p.stats + p.cout + i, sl->ch_b[i]);
       }
     }
   }
@@ -355,10 +478,13 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
   }
 }
 
-template <int kCtaGroup, int kBlockN>
+template <int kCtaGroup, int kBlockN, int kEpi>
 int launch_conv(const void* x_bf16, const void* w_packed_bf16, ConvParams p, cudaStream_t stream) {
-  using C = Cfg<kCtaGroup, kBlockN>;
+  using C = Cfg<kCtaGroup, kBlockN, kEpi>;
   p.tiles_n = p.cout / kBlockN;
+  p.div_n = make_fastdiv(static_cast<uint32_t>(p.tiles_n));
+  p.div_x = make_fastdiv(static_cast<uint32_t>(p.tiles_x));
+  p.div_y = make_fastdiv(static_cast<uint32_t>(p.tiles_y));
   const long long work = static_cast<long long>((p.spatial_tiles + kCtaGroup - 1) / kCtaGroup) * p.tiles_n;
   if (work >= (1ll << 31)) return CTK_ERR_BAD_ARG;
   p.total_work = static_cast<int>(work);
@@ -380,7 +506,7 @@ int launch_conv(const void* x_bf16, const void* w_packed_bf16, ConvParams p, cud
     int st = ctk::encode_tmap_bf16_sw128(&tm_b, w_packed_bf16, 2, dims, strides, box);
     if (st != CTK_OK) return st;
   }
-  auto kernel = conv3x3_tc_kernel<kCtaGroup, kBlockN>;
+  auto kernel = conv3x3_tc_kernel<kCtaGroup, kBlockN, kEpi>;
   CTK_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
   const int clusters = std::min(p.total_work, ctk::num_sms() / kCtaGroup);
   cudaLaunchConfig_t cfg = {};
@@ -427,10 +553,20 @@ static int conv_dispatch(const void* x_bf16, int n, int H, int W, int cin, const
   p.out_cstride = out_cstride; p.out_coffset = out_coffset;
   cudaStream_t s = ctk::as_stream(stream);
   if (stats != nullptr) CTK_CUDA_TRY(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * cout, s));
-  if ((flags & CTK_CONV_SINGLE_CTA) && cout % 128 == 0) return launch_conv<1, 128>(x_bf16, w_packed_bf16, p, s);
-  if (cout % 256 == 0) return launch_conv<2, 256>(x_bf16, w_packed_bf16, p, s);
-  if (cout % 128 == 0) return launch_conv<2, 128>(x_bf16, w_packed_bf16, p, s);
-  return launch_conv<2, 64>(x_bf16, w_packed_bf16, p, s);
+  const int epi = scale == nullptr ? (stats != nullptr ? kEpiRawStats : kEpiRaw)
+                                   : (p.pool && p.act ? kEpiEvalPool : kEpiEvalAny);
+#define CTK_CONV_LAUNCH(G, N)                                                                             \
+  switch (epi) {                                                                                          \
+    case kEpiEvalPool: return launch_conv<G, N, kEpiEvalPool>(x_bf16, w_packed_bf16, p, s);               \
+    case kEpiEvalAny: return launch_conv<G, N, kEpiEvalAny>(x_bf16, w_packed_bf16, p, s);                 \
+    case kEpiRaw: return launch_conv<G, N, kEpiRaw>(x_bf16, w_packed_bf16, p, s);                         \
+    default: return launch_conv<G, N, kEpiRawStats>(x_bf16, w_packed_bf16, p, s);                         \
+  }
+  if ((flags & CTK_CONV_SINGLE_CTA) && cout % 128 == 0) { CTK_CONV_LAUNCH(1, 128) }
+  if (cout % 256 == 0) { CTK_CONV_LAUNCH(2, 256) }
+  if (cout % 128 == 0) { CTK_CONV_LAUNCH(2, 128) }
+  CTK_CONV_LAUNCH(2, 64)
+#undef CTK_CONV_LAUNCH
 }
 
 extern "C" int ctk_conv3x3_tc_eval(const void* x_bf16, int n, int H, int W, int cin, const void* w_packed_bf16,

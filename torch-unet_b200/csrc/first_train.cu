@@ -21,87 +21,147 @@ using namespace ctk;
 
 // ------------------------------------------------------------------------------------------------ patch Gram matrix
 // gram layout (double): [0, T) = S, [T, T + T*T) = G row-major (full, symmetric).
+// Items = T sums + T(T+1)/2 upper-triangle products.  A warp owns one row of a 32 x 8 pixel tile at a time (lane = pixel)
+// and a compile-time slice ("role") of the items, so every FFMA is unconditional: 9*CIN LDS feed ITEMS/ROLES FFMAs.
+template <int CIN>
+struct GramCfg {
+  static constexpr int T = 9 * CIN;
+  static constexpr int ITEMS = T + T * (T + 1) / 2;
+  static constexpr int ROLES = CIN == 1 ? 1 : 4;
+  static constexpr int PER = (ITEMS + ROLES - 1) / ROLES;
+  static constexpr int ROWG = 8 / ROLES;             // warps that share a role split the tile's rows
+  static constexpr int TW = 32, TH = 64;             // pixel tile per iteration: long enough to hide the next tile's loads
+  static constexpr int SLOTS = ((TH + 2) * (TW + 2) + 255) / 256;   // staging elements per thread and channel
+};
+
+template <int CIN, int ROLE>
+__device__ __forceinline__ void gram_accumulate(const float (&v)[9 * CIN], float (&acc)[GramCfg<CIN>::PER]) {
+  using C = GramCfg<CIN>;
+  int item = 0;
+#pragma unroll
+  for (int a = 0; a < C::T; ++a, ++item)
+    if (item % C::ROLES == ROLE) acc[item / C::ROLES] += v[a];
+#pragma unroll
+  for (int a = 0; a < C::T; ++a)
+#pragma unroll
+    for (int b = a; b < C::T; ++b, ++item)
+      if (item % C::ROLES == ROLE) acc[item / C::ROLES] = fmaf(v[a], v[b], acc[item / C::ROLES]);
+}
+
+template <int CIN, int ROLE>
+__device__ __forceinline__ void gram_role(const float* __restrict__ x, int n_img, int c_total, int c_offset, int H, int W,
+                                          double* __restrict__ gram, float (*s_in)[GramCfg<CIN>::TH + 2][35],
+                                          double* s_red) {
+  using C = GramCfg<CIN>;
+  constexpr int T = C::T, TW = C::TW, TH = C::TH, SLOTS = C::SLOTS;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int rowg = warp / C::ROLES;
+  // fp32 partial sums (<= TH / ROWG adds each), folded into fp64 running sums after every tile: the variance
+  // w^T (G/M - s s^T) w cancels one or two digits, so the Gram entries need more than fp32 over 10^7 pixels
+  float acc[C::PER];
+  double dacc[C::PER];
+#pragma unroll
+  for (int i = 0; i < C::PER; ++i) { acc[i] = 0.f; dacc[i] = 0.0; }
+  const int tiles_x = (W + TW - 1) / TW, tiles_y = (H + TH - 1) / TH;
+  const long long total = static_cast<long long>(n_img) * tiles_x * tiles_y;
+  // this thread's staging slots of the (TH+2) x (TW+2) halo
+  int sr[SLOTS], sq[SLOTS];
+#pragma unroll
+  for (int k = 0; k < SLOTS; ++k) {
+    const int i = threadIdx.x + 256 * k;
+    sr[k] = i / (TW + 2);
+    sq[k] = i - sr[k] * (TW + 2);
+  }
+  // the next tile's halo is fetched into registers while the current one is being multiplied
+  float pf[CIN][SLOTS];
+  auto fetch = [&](long long tile) {
+    const int tx = static_cast<int>(tile % tiles_x);
+    const int ty = static_cast<int>((tile / tiles_x) % tiles_y);
+    const int img = static_cast<int>(tile / (static_cast<long long>(tiles_x) * tiles_y));
+#pragma unroll
+    for (int c = 0; c < CIN; ++c) {
+      const float* plane = x + (static_cast<size_t>(img) * c_total + c_offset + c) * H * W;
+#pragma unroll
+      for (int k = 0; k < SLOTS; ++k) {
+        const int gy = ty * TH - 1 + sr[k], gx = tx * TW - 1 + sq[k];
+        pf[c][k] = (sr[k] < TH + 2 && gy >= 0 && gy < H && gx >= 0 && gx < W)
+                       ? __ldg(plane + static_cast<size_t>(gy) * W + gx) : 0.f;
+      }
+    }
+  };
+  if (blockIdx.x < total) fetch(blockIdx.x);
+  for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    const int tx = static_cast<int>(tile % tiles_x);
+    const int ty = static_cast<int>((tile / tiles_x) % tiles_y);
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < CIN; ++c)
+#pragma unroll
+      for (int k = 0; k < SLOTS; ++k)
+        if (sr[k] < TH + 2) s_in[c][sr[k]][sq[k]] = pf[c][k];
+    __syncthreads();
+    if (tile + gridDim.x < total) fetch(tile + gridDim.x);
+#pragma unroll 2
+    for (int py = rowg; py < TH; py += C::ROWG) {
+      const int gy = ty * TH + py, gx = tx * TW + lane;
+      float v[T];
+      const bool in = gy < H && gx < W;
+#pragma unroll
+      for (int c = 0; c < CIN; ++c)
+#pragma unroll
+        for (int k = 0; k < 9; ++k) v[c * 9 + k] = in ? s_in[c][py + k / 3][lane + k % 3] : 0.f;
+      gram_accumulate<CIN, ROLE>(v, acc);
+    }
+#pragma unroll
+    for (int i = 0; i < C::PER; ++i) { dacc[i] += static_cast<double>(acc[i]); acc[i] = 0.f; }
+  }
+  // lanes -> warp total, the ROWG warps of a role -> CTA total (shared memory), one fp64 atomic per item per CTA
+#pragma unroll
+  for (int i = 0; i < C::PER; ++i) {
+    double sres = dacc[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sres += __shfl_xor_sync(0xffffffffu, sres, o);
+    if (lane == 0) s_red[warp * C::PER + i] = sres;
+  }
+  __syncthreads();
+  if (rowg == 0) {
+    for (int i = lane; i < C::PER; i += 32) {
+      const int item = i * C::ROLES + ROLE;
+      if (item >= C::ITEMS) continue;
+      double tot = 0.0;
+      for (int g = 0; g < C::ROWG; ++g) tot += s_red[(g * C::ROLES + ROLE) * C::PER + i];
+      if (item < T) {
+        atomicAdd(gram + item, tot);
+      } else {
+        // upper-triangle index -> (a, b), a <= b
+        int rem = item - T, a = 0;
+        while (rem >= T - a) { rem -= T - a; ++a; }
+        const int b = a + rem;
+        atomicAdd(gram + T + a * T + b, tot);
+        if (a != b) atomicAdd(gram + T + b * T + a, tot);
+      }
+    }
+  }
+}
+
 template <int CIN>
 __global__ void __launch_bounds__(256)
 patch_gram_kernel(const float* __restrict__ x, int n_img, int c_total, int c_offset, int H, int W,
                   double* __restrict__ gram) {
-  constexpr int T = 9 * CIN;
-  constexpr int ITEMS = T + T * (T + 1) / 2;          // sums + upper triangle
-  constexpr int ROLES = 8;
-  constexpr int PER = (ITEMS + ROLES - 1) / ROLES;
-  constexpr int TW = 32, TH = 8;
-  __shared__ float s_in[CIN][TH + 2][TW + 2 + 1];
-  const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
-  // fp32 partial sums over the 8 pixels a lane sees per tile, folded into fp64 running sums after every tile:
-  // the variance w^T (G/M - s s^T) w cancels one or two digits, so the Gram entries need more than fp32
-  float acc[PER];
-  double dacc[PER];
-#pragma unroll
-  for (int i = 0; i < PER; ++i) { acc[i] = 0.f; dacc[i] = 0.0; }
-  const int tiles_x = (W + TW - 1) / TW, tiles_y = (H + TH - 1) / TH;
-  const long long total = static_cast<long long>(n_img) * tiles_x * tiles_y;
-  for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
-    const int tx = static_cast<int>(tile % tiles_x);
-    const int ty = static_cast<int>((tile / tiles_x) % tiles_y);
-    const int img = static_cast<int>(tile / (static_cast<long long>(tiles_x) * tiles_y));
-    __syncthreads();
-    for (int c = 0; c < CIN; ++c) {
-      const float* plane = x + (static_cast<size_t>(img) * c_total + c_offset + c) * H * W;
-      for (int i = threadIdx.x; i < (TH + 2) * (TW + 2); i += 256) {
-        const int r = i / (TW + 2), q = i % (TW + 2);
-        const int gy = ty * TH - 1 + r, gx = tx * TW - 1 + q;
-        s_in[c][r][q] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? __ldg(plane + static_cast<size_t>(gy) * W + gx) : 0.f;
-      }
-    }
-    __syncthreads();
-    for (int py = 0; py < TH; ++py) {
-      const int gy = ty * TH + py, gx = tx * TW + lane;
-      if (gy >= H || gx >= W) continue;
-      float v[T];
-#pragma unroll
-      for (int c = 0; c < CIN; ++c)
-#pragma unroll
-        for (int k = 0; k < 9; ++k) v[c * 9 + k] = s_in[c][py + k / 3][lane + k % 3];
-      // item index -> (sum t) or (pair a <= b); role r owns items r, r + ROLES, ...; all indices are compile time
-      int item = 0, slot = 0;
-#pragma unroll
-      for (int a = 0; a < T; ++a, ++item)
-        if (item % ROLES == role) { acc[item / ROLES] += v[a]; }
-#pragma unroll
-      for (int a = 0; a < T; ++a)
-#pragma unroll
-        for (int b = a; b < T; ++b, ++item)
-          if (item % ROLES == role) { acc[item / ROLES] = fmaf(v[a], v[b], acc[item / ROLES]); }
-      (void)slot;
-    }
-#pragma unroll
-    for (int i = 0; i < PER; ++i) { dacc[i] += static_cast<double>(acc[i]); acc[i] = 0.f; }
-  }
-  // warp reduce over lanes, then one fp64 atomic per item per warp
-  int item = 0;
-#pragma unroll
-  for (int a = 0; a < T; ++a, ++item) {
-    if (item % ROLES == role) {
-      double s = dacc[item / ROLES];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (lane == 0) atomicAdd(gram + a, s);
+  using C = GramCfg<CIN>;
+  __shared__ float s_in[CIN][C::TH + 2][35];
+  __shared__ double s_red[8 * C::PER];
+  const int role = (threadIdx.x >> 5) % C::ROLES;
+  if constexpr (C::ROLES == 1) {
+    gram_role<CIN, 0>(x, n_img, c_total, c_offset, H, W, gram, s_in, s_red);
+  } else {
+    switch (role) {          // warp-uniform
+      case 0: gram_role<CIN, 0>(x, n_img, c_total, c_offset, H, W, gram, s_in, s_red); break;
+      case 1: gram_role<CIN, 1>(x, n_img, c_total, c_offset, H, W, gram, s_in, s_red); break;
+      case 2: gram_role<CIN, 2>(x, n_img, c_total, c_offset, H, W, gram, s_in, s_red); break;
+      default: gram_role<CIN, 3>(x, n_img, c_total, c_offset, H, W, gram, s_in, s_red); break;
     }
   }
-#pragma unroll
-  for (int a = 0; a < T; ++a)
-#pragma unroll
-    for (int b = a; b < T; ++b, ++item) {
-      if (item % ROLES == role) {
-        double s = dacc[item / ROLES];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) {
-          atomicAdd(gram + T + a * T + b, s);
-          if (a != b) atomicAdd(gram + T + b * T + a, s);
-        }
-      }
-    }
 }
 
 // ------------------------------------------------------------------------------------------------ moments from the Gram matrix
@@ -129,8 +189,9 @@ __global__ void first_moments_kernel(const double* __restrict__ gram, const floa
 template <int CIN, int COUT>
 __global__ void __launch_bounds__(256)
 first_wgrad_fused_kernel(const float* __restrict__ x, int n_img, int c_total, int c_offset, int H, int W,
-                         const float* __restrict__ w_folded, const float* __restrict__ shift, float slope,
-                         const __nv_bfloat16* __restrict__ dp, float* __restrict__ t1) {
+                         const float* __restrict__ w_folded, const float* __restrict__ shift,
+                         const float* __restrict__ gamma, const float* __restrict__ beta, float slope,
+                         const __nv_bfloat16* __restrict__ dp, float* __restrict__ t1, float* __restrict__ sums) {
   constexpr int T = 9 * CIN;
   constexpr int G = COUT / 4;                  // channel groups of 4
   constexpr int SLOTS = 256 / G;               // windows processed concurrently
@@ -138,10 +199,14 @@ first_wgrad_fused_kernel(const float* __restrict__ x, int n_img, int c_total, in
   __shared__ float s_in[CIN][2 * TWH + 2][2 * TWW + 2 + 1];
   __shared__ float s_red[256];
   const int cg = threadIdx.x % G, slot = threadIdx.x / G;
-  float wr[4][T], sh[4], acc[4][T];
+  float wr[4][T], sh[4], acc[4][T], be[4], ig[4], s1[4], s2[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     sh[j] = __ldg(shift + cg * 4 + j);
+    be[j] = __ldg(beta + cg * 4 + j);
+    const float g0 = __ldg(gamma + cg * 4 + j);
+    ig[j] = g0 != 0.f ? 1.f / g0 : 0.f;
+    s1[j] = 0.f; s2[j] = 0.f;
 #pragma unroll
     for (int k = 0; k < T; ++k) { wr[j][k] = __ldg(w_folded + (cg * 4 + j) * T + k); acc[j][k] = 0.f; }
   }
@@ -200,6 +265,8 @@ first_wgrad_fused_kernel(const float* __restrict__ x, int n_img, int c_total, in
           if (a > best) { best = a; arg = q; zbest = z[q]; }
         }
         const float gg = g[j] * (zbest > 0.f ? 1.f : slope);
+        s1[j] += gg;                                        // sum dA          (= dbeta)
+        s2[j] = fmaf(gg, (zbest - be[j]) * ig[j], s2[j]);   // sum dA * xhat   (= dgamma), xhat = (z - beta) / gamma in fp32
         const int dy = arg >> 1, dx = arg & 1;
 #pragma unroll
         for (int c = 0; c < CIN; ++c)
@@ -227,6 +294,19 @@ first_wgrad_fused_kernel(const float* __restrict__ x, int n_img, int c_total, in
         float s = 0.f;
         for (int t = 0; t < SLOTS; ++t) s += s_red[t * G + cg];
         atomicAdd(t1 + (cg * 4 + j) * T + k, s);
+      }
+    }
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      __syncthreads();
+      s_red[threadIdx.x] = k == 0 ? s1[j] : s2[j];
+      __syncthreads();
+      if (slot == 0) {
+        float s = 0.f;
+        for (int t = 0; t < SLOTS; ++t) s += s_red[t * G + cg];
+        atomicAdd(sums + k * COUT + cg * 4 + j, s);
       }
     }
 }
@@ -261,7 +341,7 @@ int ctk_first_patch_gram(const float* x, int n, int c_total, int c_offset, int c
   const int T = 9 * cin;
   cudaStream_t s = ctk::as_stream(stream);
   CTK_CUDA_TRY(cudaMemsetAsync(gram, 0, sizeof(double) * (T + T * T), s));
-  const int grid = ctk::num_sms() * 4;
+  const int grid = ctk::num_sms();          // ~240 registers per thread: one resident CTA per SM
   if (cin == 1) patch_gram_kernel<1><<<grid, 256, 0, s>>>(x, n, c_total, c_offset, H, W, gram);
   else if (cin == 2) patch_gram_kernel<2><<<grid, 256, 0, s>>>(x, n, c_total, c_offset, H, W, gram);
   else return CTK_ERR_UNSUPPORTED;
@@ -276,17 +356,19 @@ int ctk_first_moments(const double* gram, const float* w, int cout, int cin, dou
 }
 
 int ctk_first_wgrad_fused(const float* x, int n, int c_total, int c_offset, int cin, int H, int W, const float* w_folded,
-                          const float* shift, float slope, const void* dp_bf16, int cout, float* t1, void* stream) {
-  CTK_REQUIRE(x && w_folded && shift && dp_bf16 && t1 && n > 0 && H % 2 == 0 && W % 2 == 0);
+                          const float* shift, const float* gamma, const float* beta, float slope, const void* dp_bf16,
+                          int cout, float* t1, float* sums, void* stream) {
+  CTK_REQUIRE(x && w_folded && shift && gamma && beta && dp_bf16 && t1 && sums && n > 0 && H % 2 == 0 && W % 2 == 0);
   CTK_REQUIRE(c_offset >= 0 && c_offset + cin <= c_total);
   cudaStream_t s = ctk::as_stream(stream);
   CTK_CUDA_TRY(cudaMemsetAsync(t1, 0, sizeof(float) * 9 * cin * cout, s));
+  CTK_CUDA_TRY(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * cout, s));
   const int grid = ctk::num_sms() * 4;
   const __nv_bfloat16* dp = static_cast<const __nv_bfloat16*>(dp_bf16);
   if (cin == 1 && cout == 64)
-    first_wgrad_fused_kernel<1, 64><<<grid, 256, 0, s>>>(x, n, c_total, c_offset, H, W, w_folded, shift, slope, dp, t1);
+    first_wgrad_fused_kernel<1, 64><<<grid, 256, 0, s>>>(x, n, c_total, c_offset, H, W, w_folded, shift, gamma, beta, slope, dp, t1, sums);
   else if (cin == 2 && cout == 128)
-    first_wgrad_fused_kernel<2, 128><<<grid, 256, 0, s>>>(x, n, c_total, c_offset, H, W, w_folded, shift, slope, dp, t1);
+    first_wgrad_fused_kernel<2, 128><<<grid, 256, 0, s>>>(x, n, c_total, c_offset, H, W, w_folded, shift, gamma, beta, slope, dp, t1, sums);
   else
     return CTK_ERR_UNSUPPORTED;
   return ctk::check_launch();

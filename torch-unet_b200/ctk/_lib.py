@@ -58,8 +58,8 @@ _SIGNATURES = {
                                         c_float, c_float, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "ctk_first_patch_gram": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "ctk_first_moments": (c_int, [c_void_p, c_void_p, c_int, c_int, c_double, c_void_p, c_void_p]),
-    "ctk_first_wgrad_fused": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_float,
-                                      c_void_p, c_int, c_void_p, c_void_p]),
+    "ctk_first_wgrad_fused": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                      c_void_p, c_float, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "ctk_first_wgrad_finalize": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_double,
                                          c_int, c_int, c_void_p, c_void_p]),
     "ctk_bn_act_pool_fwd": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p, c_int,

@@ -288,25 +288,30 @@ class TrainEngine:
                 conv, bn, h, w = b["conv"], b["bn"], b["h"], b["w"]
                 cout, cin = conv.out_channels, conv.in_channels
                 sums = self._new((2 * cout,), torch.float32, dev)
-                pooled, p_cstride, p_coff = b["pooled"]
-                call("ctk_bn_bwd_reduce_pooled", ptr(pooled), c_int(p_cstride), c_int(p_coff), ptr(dp), c_int(dp_cstride),
-                     c_int(dp_coff), c_longlong(n * (h // 2) * (w // 2)), c_int(cout), ptr(bn.weight), ptr(bn.bias),
-                     c_float(LEAKY_SLOPE), ptr(sums), stream())
-                done(bn.bias, sums[:cout])
-                done(bn.weight, sums[cout:])
                 if b.get("gram") is not None:
+                    # first block: the fused kernel recomputes each window's pre-activations from the input, which gives
+                    # the BN reductions (exactly, in fp32) together with the data term of the weight gradient
                     if dp_cstride != cout or dp_coff != 0:
                         raise _lib.CtkError("the first block's output gradient must be dense")
                     T = 9 * cin
                     t1 = self._new((cout, T), torch.float32, dev)
                     call("ctk_first_wgrad_fused", ptr(x), c_int(n), c_int(x.shape[1]), c_int(br.c_offset), c_int(cin), c_int(h),
-                         c_int(w), ptr(b["wf"]), ptr(b["shift"]), c_float(LEAKY_SLOPE), ptr(dp), c_int(cout), ptr(t1), stream())
+                         c_int(w), ptr(b["wf"]), ptr(b["shift"]), ptr(bn.weight), ptr(bn.bias), c_float(LEAKY_SLOPE), ptr(dp),
+                         c_int(cout), ptr(t1), ptr(sums), stream())
+                    done(bn.bias, sums[:cout])
+                    done(bn.weight, sums[cout:])
                     dw = self._new(tuple(conv.weight.shape), torch.float32, dev)
                     call("ctk_first_wgrad_finalize", ptr(t1), ptr(b["gram"]), ptr(conv.weight), ptr(b["scale"]), ptr(b["mean"]),
                          ptr(b["invstd"]), ptr(sums), c_double(float(n) * h * w), c_int(cout), c_int(cin), ptr(dw), stream())
                     done(conv.weight, dw)
                     done(conv.bias, torch.zeros_like(conv.bias))
                     continue
+                pooled, p_cstride, p_coff = b["pooled"]
+                call("ctk_bn_bwd_reduce_pooled", ptr(pooled), c_int(p_cstride), c_int(p_coff), ptr(dp), c_int(dp_cstride),
+                     c_int(dp_coff), c_longlong(n * (h // 2) * (w // 2)), c_int(cout), ptr(bn.weight), ptr(bn.bias),
+                     c_float(LEAKY_SLOPE), ptr(sums), stream())
+                done(bn.bias, sums[:cout])
+                done(bn.weight, sums[cout:])
                 dy = self._new((n, h, w, cout), torch.bfloat16, dev)
                 call("ctk_bn_bwd_apply", ptr(b["y"]), ptr(dp), c_int(dp_cstride), c_int(dp_coff), c_int(n), c_int(h), c_int(w),
                      c_int(cout), ptr(b["scale"]), ptr(b["shift"]), ptr(b["mean"]), ptr(b["invstd"]), ptr(sums),
