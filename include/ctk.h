@@ -78,6 +78,13 @@ int ctk_pack_fc1_weight_bf16(const float* w, int out_features, int channels, int
 int ctk_conv_first_eval(const float* x, int n, int c_total, int c_offset, int cin, int H, int W,
                         const float* w_folded, const float* shift, int cout, float slope,
                         void* out_bf16, int out_cstride, int out_coffset, void* stream);
+/* Same block, additionally storing what the training backward needs to route gradients through the max-pool and the
+ * LeakyReLU without recomputing the convolution: codes_u32 is [n, H/2, W/2, cout/8] uint32, 4 bits per pooled element
+ * (channel c of a pixel in bits [4*(c%8), 4*(c%8)+4) of word c/8): bits 0-1 = arg-max position 2*dy+dx inside the 2x2
+ * window (aten::max_pool2d_with_indices), bit 2 = 1 if the pre-activation at the arg-max is negative (LeakyReLU branch). */
+int ctk_conv_first_pool_codes(const float* x, int n, int c_total, int c_offset, int cin, int H, int W,
+                              const float* w_folded, const float* shift, int cout, float slope,
+                              void* out_bf16, int out_cstride, int out_coffset, void* codes_u32, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Tensor-core conv block, eval mode (implicit GEMM on tcgen05, accumulators in TMEM, operands by TMA):
@@ -173,23 +180,22 @@ int ctk_bn_finalize_moments(const float* moments, double count, const float* bia
  * gram = [S (T doubles) | G (T*T doubles)], S[t] = sum_p x[p+t], G[t][t'] = sum_p x[p+t] x[p+t'] (zero padded):
  *   ctk_first_patch_gram     gram of the input planes (overwrites gram)
  *   ctk_first_moments        moments[c] = batch mean, moments[cout+c] = biased batch variance of conv(x, w)[.,c] (no bias)
- *   (then ctk_bn_finalize_moments, ctk_pack_first_weight(w, scale) and ctk_conv_first_eval give the pooled output)
- *   ctk_first_wgrad_fused    t1[c][t] = sum_windows dP[w,c] * f'(z*) * x[argmax(w,c) + t]; recomputes the 2x2 window's
- *                            activations from x with the folded weights (first maximum wins); dp is dense bf16 NHWC.
- *                            Also sums[c] = sum dA (= d beta) and sums[cout+c] = sum dA*xhat (= d gamma), xhat taken
- *                            from the recomputed fp32 z* (no bf16 round trip through the pooled tensor)
- *   ctk_first_wgrad_finalize dw[c][t] = scale_c (t1 - m1_c S_t - m2_c invstd_c ((G w_c)[t] - mean_c S_t)),
+ *   (then ctk_bn_finalize_moments, ctk_pack_first_weight(w, scale) and ctk_conv_first_pool_codes give the pooled output)
+ *   ctk_first_wgrad_codes    t1[c][t] = sum_windows g[w,c] * x[argmax(w,c) + t] and sums[c] = sum_windows g[w,c] (= d beta),
+ *                            g = dP * f'(z*), arg-max position and sign of z* from the codes ctk_conv_first_pool_codes
+ *                            stored in the forward pass; dp is dense bf16 NHWC
+ *   ctk_first_wgrad_finalize sums[cout+c] = sum dA*xhat (= d gamma) = invstd_c (w_c . t1_c - mean_c sums[c]), then
+ *                            dw[c][t] = scale_c (t1 - m1_c S_t - m2_c invstd_c ((G w_c)[t] - mean_c S_t)),
  *                            m1 = sums[c]/count, m2 = sums[cout+c]/count, count = n*H*W
  * Replaces (train mode): nn.Conv2d + nn.BatchNorm2d statistics and their backward for regression_model.py:14-15,
  * two_branch_regression.py:10-11. */
 int ctk_first_patch_gram(const float* x, int n, int c_total, int c_offset, int cin, int H, int W, double* gram,
                          void* stream);
 int ctk_first_moments(const double* gram, const float* w, int cout, int cin, double count, float* moments, void* stream);
-int ctk_first_wgrad_fused(const float* x, int n, int c_total, int c_offset, int cin, int H, int W, const float* w_folded,
-                          const float* shift, const float* gamma, const float* beta, float slope, const void* dp_bf16,
-                          int cout, float* t1, float* sums, void* stream);
+int ctk_first_wgrad_codes(const float* x, int n, int c_total, int c_offset, int cin, int H, int W, const void* codes_u32,
+                          const void* dp_bf16, int cout, float slope, float* t1, float* sums, void* stream);
 int ctk_first_wgrad_finalize(const float* t1, const double* gram, const float* w, const float* scale, const float* mean,
-                             const float* invstd, const float* sums, double count, int cout, int cin, float* dw,
+                             const float* invstd, float* sums, double count, int cout, int cin, float* dw,
                              void* stream);
 
 /* out = maxpool2x2(leaky(y*scale + shift)), y bf16 NHWC [n,H,W,C] -> out bf16 NHWC [n,H/2,W/2,out_cstride] @ out_coffset.

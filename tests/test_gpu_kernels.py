@@ -105,6 +105,45 @@ def test_conv_first_eval(ctk, cin, cout, c_off):
     _bf16_close(out[..., 64:], ref, rel=2 ** -7, abs_=1e-4)   # fp32-class math, bf16 store (negative side rounded twice)
 
 
+@pytest.mark.parametrize("cin,cout,c_off,H,W", [(1, 64, 1, 64, 96), (2, 128, 0, 32, 32), (1, 64, 0, 36, 20)])
+def test_conv_first_pool_codes(ctk, cin, cout, c_off, H, W):
+    """Pooled first block + 4-bit arg-max / sign codes (what the training backward consumes) against
+    F.max_pool2d(return_indices=True) of the fp32 reference; windows whose top two entries (or whose maximum and 0)
+    are closer than the bf16-operand-split accuracy are left out of the code comparison."""
+    from ctk._lib import call, ptr, stream
+    torch.manual_seed(3)
+    n = 2
+    x = torch.rand(n, 2, H, W)
+    w = torch.randn(cout, cin, 3, 3) / 3
+    scale = torch.randn(cout) * 0.5 + 1.0
+    shift = 0.2 * torch.randn(cout)
+    z = F.conv2d(x[:, c_off:c_off + cin], w * scale[:, None, None, None], padding=1) + shift[None, :, None, None]
+    pooled, idx = F.max_pool2d(F.leaky_relu(z, 0.01), 2, return_indices=True)
+    zmax = F.max_pool2d(z, 2)
+    wd, sd, hd, xd = w.cuda(), scale.cuda(), shift.cuda(), x.cuda()
+    wf = torch.empty(cout, cin * 9, device="cuda")
+    call("ctk_pack_first_weight", ptr(wd), ptr(sd), c_int(cout), c_int(cin), ptr(wf), stream())
+    out = torch.zeros(n, H // 2, W // 2, cout, device="cuda", dtype=torch.bfloat16)
+    codes = torch.zeros(n, H // 2, W // 2, cout // 8, device="cuda", dtype=torch.int32)
+    call("ctk_conv_first_pool_codes", ptr(xd), c_int(n), c_int(2), c_int(c_off), c_int(cin), c_int(H), c_int(W), ptr(wf),
+         ptr(hd), c_int(cout), c_float(0.01), ptr(out), c_int(cout), c_int(0), ptr(codes), stream())
+    torch.cuda.synchronize()
+    _bf16_close(out, pooled.permute(0, 2, 3, 1).contiguous(), rel=2 ** -7, abs_=1e-4)
+    cw = codes.cpu().to(torch.int64) & 0xFFFFFFFF
+    nib = torch.stack([(cw >> (4 * i)) & 0xF for i in range(8)], dim=-1).reshape(n, H // 2, W // 2, cout)
+    pos_gpu, neg_gpu = nib & 3, (nib >> 2) & 1
+    iy, ix = idx // W, idx % W
+    pos_ref = ((iy % 2) * 2 + (ix % 2)).permute(0, 2, 3, 1)
+    neg_ref = (zmax < 0).long().permute(0, 2, 3, 1)
+    win = z.unfold(2, 2, 2).unfold(3, 2, 2).reshape(n, cout, H // 2, W // 2, 4)
+    top2 = win.topk(2, dim=-1).values
+    clear_arg = ((top2[..., 0] - top2[..., 1]) > 1e-4).permute(0, 2, 3, 1)
+    clear_sign = (top2[..., 0].abs() > 1e-4).permute(0, 2, 3, 1)
+    assert clear_arg.float().mean() > 0.99
+    assert torch.equal(pos_gpu[clear_arg], pos_ref[clear_arg])
+    assert torch.equal(neg_gpu[clear_sign], neg_ref[clear_sign])
+
+
 # ------------------------------------------------------------------ tensor-core conv block
 def _conv_tc_case(ctk, n, H, W, cin, cout, flags=0, coff=0, extra=0):
     from ctk._lib import call, ptr, stream

@@ -254,13 +254,14 @@ def test_first_block_gram_path(L, cin, cout, coff):
     wf = torch.empty(cout, T, device="cuda")
     L.call("ctk_pack_first_weight", L.ptr(wd), L.ptr(scale), c_int(cout), c_int(cin), L.ptr(wf), L.stream())
     out = torch.zeros(n, H // 2, W // 2, cout, device="cuda", dtype=torch.bfloat16)
-    L.call("ctk_conv_first_eval", L.ptr(xd), c_int(n), c_int(2), c_int(coff), c_int(cin), c_int(H), c_int(W), L.ptr(wf),
-           L.ptr(shift), c_int(cout), c_float(0.01), L.ptr(out), c_int(cout), c_int(0), L.stream())
+    codes = torch.zeros(n, H // 2, W // 2, cout // 8, device="cuda", dtype=torch.int32)
+    L.call("ctk_conv_first_pool_codes", L.ptr(xd), c_int(n), c_int(2), c_int(coff), c_int(cin), c_int(H), c_int(W), L.ptr(wf),
+           L.ptr(shift), c_int(cout), c_float(0.01), L.ptr(out), c_int(cout), c_int(0), L.ptr(codes), L.stream())
     dpd = dp.to(torch.bfloat16).cuda()
     sums = torch.empty(2 * cout, device="cuda")
     t1 = torch.empty(cout, T, device="cuda")
-    L.call("ctk_first_wgrad_fused", L.ptr(xd), c_int(n), c_int(2), c_int(coff), c_int(cin), c_int(H), c_int(W), L.ptr(wf),
-           L.ptr(shift), L.ptr(gd), L.ptr(bd), c_float(0.01), L.ptr(dpd), c_int(cout), L.ptr(t1), L.ptr(sums), L.stream())
+    L.call("ctk_first_wgrad_codes", L.ptr(xd), c_int(n), c_int(2), c_int(coff), c_int(cin), c_int(H), c_int(W),
+           L.ptr(codes), L.ptr(dpd), c_int(cout), c_float(0.01), L.ptr(t1), L.ptr(sums), L.stream())
     dw = torch.empty(cout, cin, 3, 3, device="cuda")
     L.call("ctk_first_wgrad_finalize", L.ptr(t1), L.ptr(gram), L.ptr(wd), L.ptr(scale), L.ptr(mean), L.ptr(invstd),
            L.ptr(sums), c_double(count), c_int(cout), c_int(cin), L.ptr(dw), L.stream())

@@ -309,6 +309,289 @@ conv_first_tc_kernel(const float* __restrict__ x, int n_img, int c_total, int c_
   }
 }
 
+// ======================================================================================================================
+// Pooled variant (the block as the models use it): one TMEM lane per 2x2 WINDOW.
+//
+// The four pixels of a pooling window are four separate A tiles (same 128 windows, window position q = (dy, dx)); the MMA
+// of position q accumulates into TMEM columns [32q, 32q+32) of the group, 32 output channels per round.  The thread that
+// owns a window then reads its four positions from its own lane and takes the max in registers: no cross-lane
+// shuffles, no selects, the bf16 pack and the LeakyReLU run on the pooled quarter of the data, and the window's patch
+// (4 x 4 inputs per channel) is read from shared memory once for all four A rows.  ~430 instructions per window and
+// 64 channels against ~1600 for the pixel-per-lane version above (measured with ncu, profiles/r1_infer_full_*).
+//
+// kCodes: also store, per pooled element, the arg-max position and the sign of the pre-activation (4-bit code, eight
+// channels per 32-bit word) -- what the training backward needs to route gradients without recomputing the conv.
+// The position rides in the two low mantissa bits of the fp32 accumulators through the max (<= 3 fp32 ulp).
+template <int CIN>
+struct WinCfg {
+  static constexpr int kGroups = CIN == 1 ? 4 : 2;              // 4 A tiles of 16 KB per group at K = 64: two groups fit
+  static constexpr int kThreads = kGroups * 128;
+  static constexpr int kK = CIN == 1 ? 32 : 64;
+  static constexpr int kKWords = kK / 2;
+  static constexpr int kWinH = 16, kWinW = 8;                   // windows per region (one per TMEM lane)
+  static constexpr int kInH = 2 * kWinH + 2, kInW = 2 * kWinW + 2;
+  static constexpr int kInPitch = 24;                           // words; 8-byte patch loads are bank-conflict free
+  static constexpr int kLbo = 128;
+  static constexpr int kSbo = (kK / 8) * 128;
+  static constexpr int kATileBytes = 16 * kSbo;                 // 128 rows
+  static constexpr int kGroupBytes = 4 * kATileBytes + CIN * kInH * kInPitch * 4;
+  static constexpr int kPref = (kInH * kInW + 127) / 128;
+  static constexpr int smem_bytes(int cout) { return 1024 + (cout / 8) * kSbo + kGroups * kGroupBytes + 256; }
+};
+
+template <int CIN, bool kCodes>
+__global__ void __launch_bounds__(WinCfg<CIN>::kThreads, 1)
+conv_first_win_kernel(const float* __restrict__ x, int n_img, int c_total, int c_offset, int H, int W,
+                      const float* __restrict__ w_folded, const float* __restrict__ shift, float slope, int cout,
+                      __nv_bfloat16* __restrict__ out, int out_cstride, int out_coffset, uint32_t* __restrict__ codes,
+                      FastDiv div_rx, FastDiv div_ry, int total_regions) {
+  using C = WinCfg<CIN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* b_smem = smem;
+  uint8_t* groups_smem = smem + (cout / 8) * C::kSbo;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(groups_smem + C::kGroups * C::kGroupBytes);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + C::kGroups);
+
+  const int warp = threadIdx.x >> 5;
+  const int group = warp >> 2;
+  const int gt = threadIdx.x & 127;          // thread within group = TMEM lane = window of the 16 x 8 region
+  const int ew = warp & 3;
+
+  if (threadIdx.x == 0) {
+    for (int g = 0; g < C::kGroups; ++g) mbar_init(&bars[g], 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc<1>(tmem_slot, 512);
+  // B operand: folded weights split into hi/lo bf16 (same K-word layout as the kernel above), built once per CTA
+  for (int i = threadIdx.x; i < cout * C::kKWords; i += C::kThreads) {
+    const int n = i / C::kKWords, kw = i % C::kKWords;
+    uint32_t word = 0;
+    const int ch = kw / 14, j = kw % 14;
+    if (kw == 14 * CIN) {
+      word = split_hi_lo(__ldg(shift + n));                               // (shift_hi, shift_lo) against A's (1, 1)
+    } else if (ch < CIN) {
+      const float* wr = w_folded + (n * CIN + ch) * 9;
+      if (j < 9) {
+        const uint32_t hl = split_hi_lo(__ldg(wr + j));
+        word = (hl & 0xffffu) | (hl << 16);                               // (w_hi, w_hi)
+      } else {
+        const int t0 = 2 * (j - 9);
+        const uint32_t a = split_hi_lo(__ldg(wr + t0)) >> 16;             // w_lo[t0]
+        const uint32_t b = t0 + 1 < 9 ? (split_hi_lo(__ldg(wr + t0 + 1)) >> 16) : 0u;
+        word = a | (b << 16);
+      }
+    }
+    const int k = 2 * kw;
+    const uint32_t off = (n >> 3) * C::kSbo + (k >> 3) * C::kLbo + (n & 7) * 16 + (k & 7) * 2;
+    *reinterpret_cast<uint32_t*>(b_smem + off) = word;
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  uint8_t* a_smem = groups_smem + group * C::kGroupBytes;
+  uint32_t* in_smem = reinterpret_cast<uint32_t*>(a_smem + 4 * C::kATileBytes);
+  const uint32_t tmem_group = tmem_base + static_cast<uint32_t>(group * 128);
+  const int wy = gt >> 3, wx = gt & 7;
+  const int Hp = H >> 1, Wp = W >> 1;
+  constexpr uint32_t idesc = umma_idesc_bf16_f32(128, 32);
+  const __nv_bfloat162 slope2 = __float2bfloat162_rn(slope);
+  uint32_t parity = 0;
+  const int rounds = cout >> 5;
+
+  // input prefetch: the halo of the NEXT region is loaded into registers while this one is being processed
+  int pre_rr[C::kPref], pre_q[C::kPref];
+#pragma unroll
+  for (int j = 0; j < C::kPref; ++j) {
+    const int i = gt + 128 * j;
+    pre_rr[j] = i < C::kInH * C::kInW ? i / C::kInW : -1000000;
+    pre_q[j] = i - (i / C::kInW) * C::kInW;
+  }
+  float pref[CIN][C::kPref];
+  auto decode = [&](int region, int& img, int& ry, int& rx) {
+    const uint32_t q1 = fdiv(static_cast<uint32_t>(region), div_rx);
+    rx = region - static_cast<int>(q1 * div_rx.d);
+    const uint32_t q2 = fdiv(q1, div_ry);
+    ry = static_cast<int>(q1 - q2 * div_ry.d);
+    img = static_cast<int>(q2);
+  };
+  auto load_region = [&](int region) {
+    int img, ry, rx;
+    decode(region, img, ry, rx);
+    const int y0 = ry * 2 * C::kWinH - 1, x0 = rx * 2 * C::kWinW - 1;
+    const float* plane0 = x + (static_cast<size_t>(img) * c_total + c_offset) * H * W;
+#pragma unroll
+    for (int j = 0; j < C::kPref; ++j) {
+      const int gy = y0 + pre_rr[j], gx = x0 + pre_q[j];
+      const bool ok = gy >= 0 && gy < H && gx >= 0 && gx < W;
+      const size_t off = static_cast<size_t>(gy) * W + gx;
+#pragma unroll
+      for (int c = 0; c < CIN; ++c) pref[c][j] = ok ? __ldg(plane0 + static_cast<size_t>(c) * H * W + off) : 0.f;
+    }
+  };
+  const int region_first = blockIdx.x * C::kGroups + group;
+  const int region_step = gridDim.x * C::kGroups;
+  if (region_first < total_regions) load_region(region_first);
+
+  for (int region = region_first; region < total_regions; region += region_step) {
+    int img, ry, rx;
+    decode(region, img, ry, rx);
+    // ---- stage the prefetched halo as packed (hi | lo << 16) words, then prefetch the next region
+#pragma unroll
+    for (int c = 0; c < CIN; ++c)
+#pragma unroll
+      for (int j = 0; j < C::kPref; ++j)
+        if (pre_rr[j] >= 0) in_smem[(c * C::kInH + pre_rr[j]) * C::kInPitch + pre_q[j]] = split_hi_lo(pref[c][j]);
+    asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory");
+    if (region + region_step < total_regions) load_region(region + region_step);
+
+    // ---- this window's 4 x 4 patch per channel -> the A rows of its four pixels
+    {
+      uint32_t pt[CIN][4][4];
+#pragma unroll
+      for (int c = 0; c < CIN; ++c)
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {
+          const uint2* row = reinterpret_cast<const uint2*>(in_smem + (c * C::kInH + 2 * wy + rr) * C::kInPitch + 2 * wx);
+          const uint2 a = row[0], b = row[1];
+          pt[c][rr][0] = a.x; pt[c][rr][1] = a.y; pt[c][rr][2] = b.x; pt[c][rr][3] = b.y;
+        }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int dy = q >> 1, dx = q & 1;
+        uint32_t kw[C::kKWords];
+#pragma unroll
+        for (int i = 0; i < C::kKWords; ++i) kw[i] = 0;
+#pragma unroll
+        for (int c = 0; c < CIN; ++c) {
+          uint32_t t[9];
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) t[ky * 3 + kx] = pt[c][dy + ky][dx + kx];
+#pragma unroll
+          for (int j = 0; j < 9; ++j) kw[c * 14 + j] = t[j];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) kw[c * 14 + 9 + u] = __byte_perm(t[2 * u], t[2 * u + 1], 0x5410);   // (hi, hi)
+          kw[c * 14 + 13] = t[8] & 0xffffu;
+        }
+        kw[14 * CIN] = 0x3f803f80u;                                       // bf16 (1, 1): adds the folded BN shift inside the MMA
+        uint8_t* tile = a_smem + q * C::kATileBytes + (gt >> 3) * C::kSbo + (gt & 7) * 16;
+#pragma unroll
+        for (int j = 0; j < C::kK / 8; ++j)
+          *reinterpret_cast<uint4*>(tile + j * C::kLbo) = make_uint4(kw[4 * j], kw[4 * j + 1], kw[4 * j + 2], kw[4 * j + 3]);
+      }
+    }
+    fence_proxy_async_smem();          // generic-proxy writes -> visible to the tensor core's async-proxy reads
+    tc_fence_before();
+    asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory");
+
+    const int py = ry * C::kWinH + wy, px = rx * C::kWinW + wx;
+    const bool valid = py < Hp && px < Wp;
+    const size_t pooled_pix = (static_cast<size_t>(img) * Hp + py) * Wp + px;
+#pragma unroll 1
+    for (int cr = 0; cr < rounds; ++cr) {
+      // ---- one thread issues the 4 x K/16 MMAs of this channel round and commits to the group's barrier
+      if (ew == 0) {
+        tc_fence_after();
+        const uint64_t desc0 = umma_smem_desc_nosw(0, C::kLbo, C::kSbo);
+        const uint64_t bdesc = desc0 | static_cast<uint64_t>((smem_u32(b_smem) + cr * 4 * C::kSbo) >> 4);
+        const uint64_t adesc = desc0 | static_cast<uint64_t>(smem_u32(a_smem) >> 4);
+        if (elect_one()) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+#pragma unroll
+            for (int ks = 0; ks < C::kK / 16; ++ks) {
+              umma_bf16(tmem_group + q * 32, adesc + ((q * C::kATileBytes + ks * 2 * C::kLbo) >> 4),
+                        bdesc + ((ks * 2 * C::kLbo) >> 4), idesc, ks != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(&bars[group]);
+        }
+        __syncwarp();
+      }
+      mbar_wait(&bars[group], parity);
+      parity ^= 1;
+      tc_fence_after();
+      // ---- epilogue: max over the window's four positions in registers, LeakyReLU, bf16, 2 x 32 bytes per thread
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        uint32_t v[4][16];
+        const uint32_t taddr = tmem_group + (static_cast<uint32_t>(ew * 32) << 16) + hf * 16;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) tmem_ld_32x16(taddr + q * 32, v[q]);
+        tmem_ld_wait();
+        float best[16];
+        if constexpr (kCodes) {
+          // position q in the two low mantissa bits (3 - q: the first position wins ties among non-negative values)
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float m = __uint_as_float((v[0][i] & ~3u) | 3u);
+            m = fmaxf(m, __uint_as_float((v[1][i] & ~3u) | 2u));
+            m = fmaxf(m, __uint_as_float((v[2][i] & ~3u) | 1u));
+            best[i] = fmaxf(m, __uint_as_float(v[3][i] & ~3u));
+          }
+          uint32_t cw[2] = {0u, 0u};
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const uint32_t b = __float_as_uint(best[i]);
+            const uint32_t nib = (3u - (b & 3u)) | ((b >> 29) & 4u);        // arg-max position | sign << 2
+            cw[i >> 3] |= nib << (4 * (i & 7));
+          }
+          if (valid) {
+            uint32_t* cdst = codes + pooled_pix * (cout >> 3) + cr * 4 + hf * 2;
+            *reinterpret_cast<uint2*>(cdst) = make_uint2(cw[0], cw[1]);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            best[i] = fmaxf(fmaxf(__uint_as_float(v[0][i]), __uint_as_float(v[1][i])),
+                            fmaxf(__uint_as_float(v[2][i]), __uint_as_float(v[3][i])));
+        }
+        uint32_t o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = leaky_bf16x2(pack_bf16x2(best[2 * i], best[2 * i + 1]), slope2);
+        if (valid) {
+          __nv_bfloat16* dst = out + pooled_pix * out_cstride + out_coffset + cr * 32 + hf * 16;
+          reinterpret_cast<uint4*>(dst)[0] = make_uint4(o[0], o[1], o[2], o[3]);
+          reinterpret_cast<uint4*>(dst)[1] = make_uint4(o[4], o[5], o[6], o[7]);
+        }
+      }
+      tc_fence_before();   // TMEM reads of this round are ordered before the barrier the next MMA issue follows
+      asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory");
+    }
+  }
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<1>(tmem_base, 512);
+  }
+}
+
+template <int CIN, bool kCodes>
+int launch_first_win(const float* x, int n, int c_total, int c_offset, int H, int W, const float* w_folded,
+                     const float* shift, float slope, int cout, __nv_bfloat16* out, int out_cstride, int out_coffset,
+                     uint32_t* codes, cudaStream_t stream) {
+  using C = WinCfg<CIN>;
+  const int regions_x = (W / 2 + C::kWinW - 1) / C::kWinW;
+  const int regions_y = (H / 2 + C::kWinH - 1) / C::kWinH;
+  const long long total = static_cast<long long>(n) * regions_x * regions_y;
+  if (total >= (1ll << 30)) return CTK_ERR_BAD_ARG;
+  auto kernel = conv_first_win_kernel<CIN, kCodes>;
+  const int smem = C::smem_bytes(cout);
+  CTK_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int grid = static_cast<int>(std::min<long long>((total + C::kGroups - 1) / C::kGroups, ctk::num_sms()));
+  kernel<<<grid, C::kThreads, smem, stream>>>(x, n, c_total, c_offset, H, W, w_folded, shift, slope, cout, out, out_cstride,
+                                              out_coffset, codes, make_fastdiv(regions_x), make_fastdiv(regions_y),
+                                              static_cast<int>(total));
+  return ctk::check_launch();
+}
+
 template <int CIN, int COUT, bool kTrain>
 int launch_first(const float* x, int n, int c_total, int c_offset, int H, int W, const float* w_folded,
                  const float* shift, float slope, __nv_bfloat16* out, int out_cstride, int out_coffset, float* stats,
@@ -330,22 +613,44 @@ int launch_first(const float* x, int n, int c_total, int c_offset, int H, int W,
 
 }  // namespace
 
-extern "C" int ctk_conv_first_eval(const float* x, int n, int c_total, int c_offset, int cin, int H, int W,
-                                   const float* w_folded, const float* shift, int cout, float slope, void* out_bf16,
-                                   int out_cstride, int out_coffset, void* stream) {
+static int first_pool_dispatch(const float* x, int n, int c_total, int c_offset, int cin, int H, int W,
+                               const float* w_folded, const float* shift, int cout, float slope, void* out_bf16,
+                               int out_cstride, int out_coffset, void* codes, void* stream) {
   if (n == 0) return CTK_OK;
   CTK_REQUIRE(x && w_folded && shift && out_bf16 && n > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0);
   CTK_REQUIRE(c_offset >= 0 && c_offset + cin <= c_total && out_coffset >= 0 && out_coffset + cout <= out_cstride);
   CTK_REQUIRE(out_cstride % 8 == 0 && out_coffset % 8 == 0 && (reinterpret_cast<uintptr_t>(out_bf16) & 15) == 0);
+  CTK_REQUIRE(cout > 0 && cout % 32 == 0 && cout <= 256 && (reinterpret_cast<uintptr_t>(codes) & 7) == 0);
   cudaStream_t s = ctk::as_stream(stream);
   __nv_bfloat16* out = static_cast<__nv_bfloat16*>(out_bf16);
-  if (cin == 1 && cout == 64)
-    return launch_first<1, 64, false>(x, n, c_total, c_offset, H, W, w_folded, shift, slope, out, out_cstride,
-                                      out_coffset, nullptr, s);
-  if (cin == 2 && cout == 128)
-    return launch_first<2, 128, false>(x, n, c_total, c_offset, H, W, w_folded, shift, slope, out, out_cstride,
-                                       out_coffset, nullptr, s);
+  uint32_t* cd = static_cast<uint32_t*>(codes);
+  if (cin == 1)
+    return cd ? launch_first_win<1, true>(x, n, c_total, c_offset, H, W, w_folded, shift, slope, cout, out, out_cstride,
+                                          out_coffset, cd, s)
+              : launch_first_win<1, false>(x, n, c_total, c_offset, H, W, w_folded, shift, slope, cout, out, out_cstride,
+                                           out_coffset, cd, s);
+  if (cin == 2)
+    return cd ? launch_first_win<2, true>(x, n, c_total, c_offset, H, W, w_folded, shift, slope, cout, out, out_cstride,
+                                          out_coffset, cd, s)
+              : launch_first_win<2, false>(x, n, c_total, c_offset, H, W, w_folded, shift, slope, cout, out, out_cstride,
+                                           out_coffset, cd, s);
   return CTK_ERR_UNSUPPORTED;
+}
+
+extern "C" int ctk_conv_first_eval(const float* x, int n, int c_total, int c_offset, int cin, int H, int W,
+                                   const float* w_folded, const float* shift, int cout, float slope, void* out_bf16,
+                                   int out_cstride, int out_coffset, void* stream) {
+  return first_pool_dispatch(x, n, c_total, c_offset, cin, H, W, w_folded, shift, cout, slope, out_bf16, out_cstride,
+                             out_coffset, nullptr, stream);
+}
+
+extern "C" int ctk_conv_first_pool_codes(const float* x, int n, int c_total, int c_offset, int cin, int H, int W,
+                                         const float* w_folded, const float* shift, int cout, float slope,
+                                         void* out_bf16, int out_cstride, int out_coffset, void* codes_u32,
+                                         void* stream) {
+  CTK_REQUIRE(codes_u32 != nullptr);
+  return first_pool_dispatch(x, n, c_total, c_offset, cin, H, W, w_folded, shift, cout, slope, out_bf16, out_cstride,
+                             out_coffset, codes_u32, stream);
 }
 
 extern "C" int ctk_conv_first_raw(const float* x, int n, int c_total, int c_offset, int cin, int H, int W,

@@ -66,25 +66,6 @@ struct Cfg {
   static constexpr int kSmemBytes = 1024 + kAStages * kAStageBytes + kBStages * kBStageBytes + kCtrlBytes + kExtra;
 };
 
-// n / d for 0 <= n < 2^31 by multiply-high (Granlund-Montgomery, 31-bit dividend): the role loops decode a work index
-// per tile, and a run-time integer division costs ~45 instructions each in every one of the 11 warps
-struct FastDiv {
-  uint32_t d, mul, shr;
-};
-inline FastDiv make_fastdiv(uint32_t d) {
-  FastDiv f = {d, 0u, 0u};
-  if (d > 1) {
-    uint32_t l = 0;
-    while ((1u << l) < d) ++l;
-    f.mul = static_cast<uint32_t>(((1ull << (31 + l)) + d - 1) / d);
-    f.shr = l - 1;
-  }
-  return f;
-}
-__device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) {
-  return f.d == 1 ? n : (__umulhi(n, f.mul) >> f.shr);
-}
-
 struct ConvParams {
   int n_img, H, W, cin, cout;
   int tiles_x, tiles_y, tiles_n, spatial_tiles, total_work;

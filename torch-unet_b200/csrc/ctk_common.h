@@ -43,4 +43,25 @@ int encode_tmap_bf16_sw128(CUtensorMap* map, const void* base, int rank, const u
 
 int num_sms();
 
+// n / d for 0 <= n < 2^31 by multiply-high (Granlund-Montgomery, 31-bit dividend): the role loops decode a work index
+// per tile, and a run-time integer division costs ~45 instructions each in every one of the 11 warps
+struct FastDiv {
+  uint32_t d, mul, shr;
+};
+inline FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f = {d, 0u, 0u};
+  if (d > 1) {
+    uint32_t l = 0;
+    while ((1u << l) < d) ++l;
+    f.mul = static_cast<uint32_t>(((1ull << (31 + l)) + d - 1) / d);
+    f.shr = l - 1;
+  }
+  return f;
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) {
+  return f.d == 1 ? n : (__umulhi(n, f.mul) >> f.shr);
+}
+#endif
+
 }  // namespace ctk

@@ -8,8 +8,8 @@
 // Forward therefore is: Gram -> moments -> BN constants -> the fused eval-style kernel (conv + scale/shift + LeakyReLU +
 // pool) that writes only the pooled output.  Backward needs dW[c,t] = sum_p dY[p,c] x[p+t] with
 //   dY = scale_c (dA - m1_c - xhat m2_c)   =>   dW[c,t] = scale_c [ T1[c,t] - m1_c S_t - m2_c invstd_c ((G w_c)[t] - mu_c S_t) ]
-// where only T1[c,t] = sum_windows dP[w,c] f'(z*) x[p*(w,c)+t] touches the data: the kernel below recomputes the four
-// conv outputs of each 2x2 window on the fp32 pipe to find the arg-max position p* (first maximum, like PyTorch).
+// where only T1[c,t] = sum_windows dP[w,c] f'(z*) x[p*(w,c)+t] touches the data: a gather driven by the 4-bit
+// arg-max / sign codes the forward kernel stored per pooled element.
 // Replaces (train mode) nn.Conv2d + nn.BatchNorm2d statistics + their backward for the first block:
 // /root/reference/regression_model.py:14-15 and two_branch_regression.py:10-11.
 #include "ctk_common.h"
@@ -186,146 +186,135 @@ __global__ void first_moments_kernel(const double* __restrict__ gram, const floa
 }
 
 // ------------------------------------------------------------------------------------------------ T1 = sum_w dP f'(z*) x[p* + t]
+// The forward pass (ctk_conv_first_pool_codes) left a 4-bit code per pooled element: arg-max position p* inside the 2x2
+// window and the sign of the pre-activation there.  The data term of the weight gradient is then a gather:
+// 9*CIN shared-memory loads and FMAs per (window, channel), no recomputation of the convolution.
+//   t1[c][t] = sum_w g[w,c] x[p*(w,c) + t],   s1[c] = sum_w g[w,c],   g = dP * (sign ? slope : 1)
+// (sum_w g * xhat, the BatchNorm weight gradient, follows from t1 and s1 in the finalize kernel:
+//  sum_w g conv(x)[p*] = sum_t w[c][t] t1[c][t].)
 template <int CIN, int COUT>
 __global__ void __launch_bounds__(256)
-first_wgrad_fused_kernel(const float* __restrict__ x, int n_img, int c_total, int c_offset, int H, int W,
-                         const float* __restrict__ w_folded, const float* __restrict__ shift,
-                         const float* __restrict__ gamma, const float* __restrict__ beta, float slope,
-                         const __nv_bfloat16* __restrict__ dp, float* __restrict__ t1, float* __restrict__ sums) {
+first_wgrad_codes_kernel(const float* __restrict__ x, int n_img, int c_total, int c_offset, int H, int W,
+                         const uint32_t* __restrict__ codes, const __nv_bfloat16* __restrict__ dp, float slope,
+                         float* __restrict__ t1, float* __restrict__ s1_out) {
   constexpr int T = 9 * CIN;
   constexpr int G = COUT / 4;                  // channel groups of 4
   constexpr int SLOTS = 256 / G;               // windows processed concurrently
-  constexpr int TWW = 16, TWH = 8;             // pooled-pixel (window) tile per iteration
-  __shared__ float s_in[CIN][2 * TWH + 2][2 * TWW + 2 + 1];
+  constexpr int TWW = 16, TWH = 16;            // pooled-pixel (window) tile per iteration
+  constexpr int PITCH = 36;                    // == 4 (mod 32): the <= 8 distinct addresses of a warp hit distinct banks
+  constexpr int ROWS = 2 * TWH + 2, COLS = 2 * TWW + 2;
+  constexpr int PRE = (ROWS * COLS + 255) / 256;
+  __shared__ float s_in[CIN][ROWS][PITCH];
   __shared__ float s_red[256];
   const int cg = threadIdx.x % G, slot = threadIdx.x / G;
-  float wr[4][T], sh[4], acc[4][T], be[4], ig[4], s1[4], s2[4];
+  float acc[4][T], s1[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    sh[j] = __ldg(shift + cg * 4 + j);
-    be[j] = __ldg(beta + cg * 4 + j);
-    const float g0 = __ldg(gamma + cg * 4 + j);
-    ig[j] = g0 != 0.f ? 1.f / g0 : 0.f;
-    s1[j] = 0.f; s2[j] = 0.f;
+    s1[j] = 0.f;
 #pragma unroll
-    for (int k = 0; k < T; ++k) { wr[j][k] = __ldg(w_folded + (cg * 4 + j) * T + k); acc[j][k] = 0.f; }
+    for (int k = 0; k < T; ++k) acc[j][k] = 0.f;
   }
   const int Hp = H >> 1, Wp = W >> 1;
   const int tiles_x = (Wp + TWW - 1) / TWW, tiles_y = (Hp + TWH - 1) / TWH;
   const long long total = static_cast<long long>(n_img) * tiles_x * tiles_y;
+  int sr[PRE], sq[PRE];
+#pragma unroll
+  for (int k = 0; k < PRE; ++k) {
+    const int i = threadIdx.x + 256 * k;
+    sr[k] = i < ROWS * COLS ? i / COLS : -1000000;
+    sq[k] = i - (i / COLS) * COLS;
+  }
+  float pf[CIN][PRE];
+  auto fetch = [&](long long tile) {
+    const int tx = static_cast<int>(tile % tiles_x);
+    const int ty = static_cast<int>((tile / tiles_x) % tiles_y);
+    const int img = static_cast<int>(tile / (static_cast<long long>(tiles_x) * tiles_y));
+#pragma unroll
+    for (int c = 0; c < CIN; ++c) {
+      const float* plane = x + (static_cast<size_t>(img) * c_total + c_offset + c) * H * W;
+#pragma unroll
+      for (int k = 0; k < PRE; ++k) {
+        const int gy = 2 * ty * TWH - 1 + sr[k], gx = 2 * tx * TWW - 1 + sq[k];
+        pf[c][k] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? __ldg(plane + static_cast<size_t>(gy) * W + gx) : 0.f;
+      }
+    }
+  };
+  if (blockIdx.x < total) fetch(blockIdx.x);
   for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
     const int tx = static_cast<int>(tile % tiles_x);
     const int ty = static_cast<int>((tile / tiles_x) % tiles_y);
     const int img = static_cast<int>(tile / (static_cast<long long>(tiles_x) * tiles_y));
     __syncthreads();
-    for (int c = 0; c < CIN; ++c) {
-      const float* plane = x + (static_cast<size_t>(img) * c_total + c_offset + c) * H * W;
-      for (int i = threadIdx.x; i < (2 * TWH + 2) * (2 * TWW + 2); i += 256) {
-        const int r = i / (2 * TWW + 2), q = i % (2 * TWW + 2);
-        const int gy = 2 * ty * TWH - 1 + r, gx = 2 * tx * TWW - 1 + q;
-        s_in[c][r][q] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? __ldg(plane + static_cast<size_t>(gy) * W + gx) : 0.f;
-      }
-    }
+#pragma unroll
+    for (int c = 0; c < CIN; ++c)
+#pragma unroll
+      for (int k = 0; k < PRE; ++k)
+        if (sr[k] >= 0) s_in[c][sr[k]][sq[k]] = pf[c][k];
     __syncthreads();
+    if (tile + gridDim.x < total) fetch(tile + gridDim.x);
+#pragma unroll 2
     for (int win = slot; win < TWW * TWH; win += SLOTS) {
       const int wy = win / TWW, wx = win % TWW;
       const int py = ty * TWH + wy, px = tx * TWW + wx;
       if (py >= Hp || px >= Wp) continue;
-      const uint2 raw = __ldg(reinterpret_cast<const uint2*>(
-          dp + ((static_cast<size_t>(img) * Hp + py) * Wp + px) * COUT + cg * 4));
+      const size_t pix = (static_cast<size_t>(img) * Hp + py) * Wp + px;
+      const uint2 raw = __ldcs(reinterpret_cast<const uint2*>(dp + pix * COUT + cg * 4));
+      const uint32_t cw = __ldcs(codes + pix * (COUT / 8) + (cg >> 1)) >> ((cg & 1) * 16);
       const float g[4] = {__uint_as_float(raw.x << 16), __uint_as_float(raw.x & 0xffff0000u),
                           __uint_as_float(raw.y << 16), __uint_as_float(raw.y & 0xffff0000u)};
-      float patch[CIN][4][4];
-#pragma unroll
-      for (int c = 0; c < CIN; ++c)
-#pragma unroll
-        for (int r = 0; r < 4; ++r)
-#pragma unroll
-          for (int q = 0; q < 4; ++q) patch[c][r][q] = s_in[c][2 * wy + r][2 * wx + q];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        float z[4] = {sh[j], sh[j], sh[j], sh[j]};
+        const uint32_t nib = (cw >> (4 * j)) & 0xfu;
+        const float gg = (nib & 4u) ? g[j] * slope : g[j];
+        s1[j] += gg;
+        const float* base = &s_in[0][2 * wy + ((nib >> 1) & 1u)][2 * wx + (nib & 1u)];
 #pragma unroll
         for (int c = 0; c < CIN; ++c)
 #pragma unroll
           for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-              const float wv = wr[j][c * 9 + ky * 3 + kx];
-              z[0] = fmaf(wv, patch[c][ky][kx], z[0]);
-              z[1] = fmaf(wv, patch[c][ky][kx + 1], z[1]);
-              z[2] = fmaf(wv, patch[c][ky + 1][kx], z[2]);
-              z[3] = fmaf(wv, patch[c][ky + 1][kx + 1], z[3]);
-            }
-        int arg = 0;
-        float best = leaky(z[0], slope), zbest = z[0];
-#pragma unroll
-        for (int q = 1; q < 4; ++q) {
-          const float a = leaky(z[q], slope);
-          if (a > best) { best = a; arg = q; zbest = z[q]; }
-        }
-        const float gg = g[j] * (zbest > 0.f ? 1.f : slope);
-        s1[j] += gg;                                        // sum dA          (= dbeta)
-        s2[j] = fmaf(gg, (zbest - be[j]) * ig[j], s2[j]);   // sum dA * xhat   (= dgamma), xhat = (z - beta) / gamma in fp32
-        const int dy = arg >> 1, dx = arg & 1;
-#pragma unroll
-        for (int c = 0; c < CIN; ++c)
-#pragma unroll
-          for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-              // patch[c][dy+ky][dx+kx] with a run-time (dy, dx): select among the four compile-time candidates
-              const float x00 = patch[c][ky][kx], x01 = patch[c][ky][kx + 1];
-              const float x10 = patch[c][ky + 1][kx], x11 = patch[c][ky + 1][kx + 1];
-              const float xv = dy ? (dx ? x11 : x10) : (dx ? x01 : x00);
-              acc[j][c * 9 + ky * 3 + kx] = fmaf(gg, xv, acc[j][c * 9 + ky * 3 + kx]);
-            }
+            for (int kx = 0; kx < 3; ++kx)
+              acc[j][c * 9 + ky * 3 + kx] = fmaf(gg, base[(c * ROWS + ky) * PITCH + kx], acc[j][c * 9 + ky * 3 + kx]);
       }
     }
   }
 #pragma unroll
   for (int j = 0; j < 4; ++j)
 #pragma unroll
-    for (int k = 0; k < T; ++k) {
+    for (int k = 0; k <= T; ++k) {
       __syncthreads();
-      s_red[threadIdx.x] = acc[j][k];
-      __syncthreads();
-      if (slot == 0) {
-        float s = 0.f;
-        for (int t = 0; t < SLOTS; ++t) s += s_red[t * G + cg];
-        atomicAdd(t1 + (cg * 4 + j) * T + k, s);
-      }
-    }
-#pragma unroll
-  for (int j = 0; j < 4; ++j)
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      __syncthreads();
-      s_red[threadIdx.x] = k == 0 ? s1[j] : s2[j];
+      s_red[threadIdx.x] = k < T ? acc[j][k < T ? k : 0] : s1[j];
       __syncthreads();
       if (slot == 0) {
         float s = 0.f;
         for (int t = 0; t < SLOTS; ++t) s += s_red[t * G + cg];
-        atomicAdd(sums + k * COUT + cg * 4 + j, s);
+        if (k < T) atomicAdd(t1 + (cg * 4 + j) * T + k, s);
+        else atomicAdd(s1_out + cg * 4 + j, s);
       }
     }
 }
 
-// dW[c,t] = scale_c [ T1 - m1 S_t - m2 invstd ((G w_c)[t] - mu S_t) ]
+// dW[c,t] = scale_c [ T1 - m1 S_t - m2 invstd ((G w_c)[t] - mu S_t) ],  m1 = s1 / count,  m2 = s2 / count with
+// s2[c] = sum dA * xhat = invstd_c (sum_t w[c][t] T1[c][t] - mu_c s1[c]);  sums = [s1 (in) | s2 (out)] = [d beta | d gamma]
 __global__ void first_wgrad_finalize_kernel(const float* __restrict__ t1, const double* __restrict__ gram,
                                             const float* __restrict__ w, const float* __restrict__ scale,
                                             const float* __restrict__ mean, const float* __restrict__ invstd,
-                                            const float* __restrict__ sums, double count, int cout, int T,
+                                            float* __restrict__ sums, double count, int cout, int T,
                                             float* __restrict__ dw) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= cout * T) return;
   const int c = i / T, t = i % T;
   const double* S = gram;
   const double* G = gram + T;
-  double gw = 0.0;
-  for (int b = 0; b < T; ++b) gw += G[t * T + b] * static_cast<double>(w[c * T + b]);
-  const double m1 = static_cast<double>(sums[c]) / count;
-  const double m2 = static_cast<double>(sums[cout + c]) / count;
+  double gw = 0.0, wt1 = 0.0;
+  for (int b = 0; b < T; ++b) {
+    gw += G[t * T + b] * static_cast<double>(w[c * T + b]);
+    wt1 += static_cast<double>(w[c * T + b]) * static_cast<double>(t1[c * T + b]);
+  }
+  const double s1 = static_cast<double>(sums[c]);
+  const double s2 = static_cast<double>(invstd[c]) * (wt1 - static_cast<double>(mean[c]) * s1);
+  if (t == 0) sums[cout + c] = static_cast<float>(s2);
+  const double m1 = s1 / count, m2 = s2 / count;
   const double v = static_cast<double>(t1[i]) - m1 * S[t] -
                    m2 * static_cast<double>(invstd[c]) * (gw - static_cast<double>(mean[c]) * S[t]);
   dw[i] = static_cast<float>(static_cast<double>(scale[c]) * v);
@@ -355,27 +344,27 @@ int ctk_first_moments(const double* gram, const float* w, int cout, int cin, dou
   return ctk::check_launch();
 }
 
-int ctk_first_wgrad_fused(const float* x, int n, int c_total, int c_offset, int cin, int H, int W, const float* w_folded,
-                          const float* shift, const float* gamma, const float* beta, float slope, const void* dp_bf16,
-                          int cout, float* t1, float* sums, void* stream) {
-  CTK_REQUIRE(x && w_folded && shift && gamma && beta && dp_bf16 && t1 && sums && n > 0 && H % 2 == 0 && W % 2 == 0);
+int ctk_first_wgrad_codes(const float* x, int n, int c_total, int c_offset, int cin, int H, int W, const void* codes_u32,
+                          const void* dp_bf16, int cout, float slope, float* t1, float* sums, void* stream) {
+  CTK_REQUIRE(x && codes_u32 && dp_bf16 && t1 && sums && n > 0 && H % 2 == 0 && W % 2 == 0);
   CTK_REQUIRE(c_offset >= 0 && c_offset + cin <= c_total);
   cudaStream_t s = ctk::as_stream(stream);
   CTK_CUDA_TRY(cudaMemsetAsync(t1, 0, sizeof(float) * 9 * cin * cout, s));
   CTK_CUDA_TRY(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * cout, s));
-  const int grid = ctk::num_sms() * 4;
+  const int grid = ctk::num_sms() * 2;
   const __nv_bfloat16* dp = static_cast<const __nv_bfloat16*>(dp_bf16);
+  const uint32_t* cd = static_cast<const uint32_t*>(codes_u32);
   if (cin == 1 && cout == 64)
-    first_wgrad_fused_kernel<1, 64><<<grid, 256, 0, s>>>(x, n, c_total, c_offset, H, W, w_folded, shift, gamma, beta, slope, dp, t1, sums);
+    first_wgrad_codes_kernel<1, 64><<<grid, 256, 0, s>>>(x, n, c_total, c_offset, H, W, cd, dp, slope, t1, sums);
   else if (cin == 2 && cout == 128)
-    first_wgrad_fused_kernel<2, 128><<<grid, 256, 0, s>>>(x, n, c_total, c_offset, H, W, w_folded, shift, gamma, beta, slope, dp, t1, sums);
+    first_wgrad_codes_kernel<2, 128><<<grid, 256, 0, s>>>(x, n, c_total, c_offset, H, W, cd, dp, slope, t1, sums);
   else
     return CTK_ERR_UNSUPPORTED;
   return ctk::check_launch();
 }
 
 int ctk_first_wgrad_finalize(const float* t1, const double* gram, const float* w, const float* scale, const float* mean,
-                             const float* invstd, const float* sums, double count, int cout, int cin, float* dw,
+                             const float* invstd, float* sums, double count, int cout, int cin, float* dw,
                              void* stream) {
   CTK_REQUIRE(t1 && gram && w && scale && mean && invstd && sums && dw && cout > 0 && cin > 0 && count >= 1.0);
   const int total = cout * 9 * cin;

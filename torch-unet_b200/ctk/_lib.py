@@ -39,6 +39,8 @@ _SIGNATURES = {
     "ctk_pack_fc1_weight_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "ctk_conv_first_eval": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
                                     c_float, c_void_p, c_int, c_int, c_void_p]),
+    "ctk_conv_first_pool_codes": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
+                                          c_float, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "ctk_conv3x3_tc_eval": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_float,
                                     c_void_p, c_int, c_int, c_int, c_void_p]),
     "ctk_gemm_bf16_splitk": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
@@ -58,8 +60,8 @@ _SIGNATURES = {
                                         c_float, c_float, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "ctk_first_patch_gram": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "ctk_first_moments": (c_int, [c_void_p, c_void_p, c_int, c_int, c_double, c_void_p, c_void_p]),
-    "ctk_first_wgrad_fused": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
-                                      c_void_p, c_float, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "ctk_first_wgrad_codes": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
+                                      c_float, c_void_p, c_void_p, c_void_p]),
     "ctk_first_wgrad_finalize": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_double,
                                          c_int, c_int, c_void_p, c_void_p]),
     "ctk_bn_act_pool_fwd": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p, c_int,
@@ -128,11 +130,11 @@ def stream() -> c_void_p:
 
 # kernels launched per successful call (bench.py reports the sum as "gpu_launches")
 KERNELS_PER_CALL = {"ctk_pearson_f32": 2, "ctk_fold_bn_eval": 1, "ctk_pack_conv_weight_bf16": 1, "ctk_pack_first_weight": 1,
-                    "ctk_pack_fc1_weight_bf16": 1, "ctk_conv_first_eval": 1, "ctk_conv3x3_tc_eval": 1,
+                    "ctk_pack_fc1_weight_bf16": 1, "ctk_conv_first_eval": 1, "ctk_conv_first_pool_codes": 1, "ctk_conv3x3_tc_eval": 1,
                     "ctk_gemm_bf16_splitk": 1, "ctk_head_eval": 1, "ctk_mse_loss": 1, "ctk_adam_multi": 1,
                     "ctk_conv_first_raw": 1, "ctk_conv3x3_tc_raw": 1, "ctk_pack_conv_weight_dgrad_bf16": 1,
                     "ctk_bn_finalize": 1, "ctk_bn_finalize_moments": 1, "ctk_first_patch_gram": 1,
-                    "ctk_first_moments": 1, "ctk_first_wgrad_fused": 1, "ctk_first_wgrad_finalize": 1, "ctk_bn_act_pool_fwd": 1, "ctk_bn_bwd_reduce": 1, "ctk_bn_bwd_reduce_pooled": 1, "ctk_bn_bwd_apply": 1,
+                    "ctk_first_moments": 1, "ctk_first_wgrad_codes": 1, "ctk_first_wgrad_finalize": 1, "ctk_bn_act_pool_fwd": 1, "ctk_bn_bwd_reduce": 1, "ctk_bn_bwd_reduce_pooled": 1, "ctk_bn_bwd_apply": 1,
                     "ctk_conv3x3_wgrad_tc": 1, "ctk_conv_first_wgrad": 1, "ctk_feat_transpose_bf16": 1,
                     "ctk_pack_fc1_weight_t_bf16": 1, "ctk_gemm_bf16_out_bf16": 1, "ctk_colstat": 1,
                     "ctk_bn1d_act_drop_fwd": 1, "ctk_sgemm_strided": 1, "ctk_head_out_fwd": 1, "ctk_head_out_bwd": 1,

@@ -117,12 +117,13 @@ class TrainEngine:
                     scale, shift, mean, invstd = self._bn_finalize(mom, float(n) * h * w, conv.bias, bn, dev, moments=True)
                     wfold = self._new((cout, T), torch.float32, dev)
                     call("ctk_pack_first_weight", ptr(conv.weight), ptr(scale), c_int(cout), c_int(cin), ptr(wfold), stream())
-                    call("ctk_conv_first_eval", ptr(x), c_int(n), c_int(c_total), c_int(br.c_offset), c_int(cin), c_int(h),
+                    codes = self._new((n, h // 2, w // 2, cout // 8), torch.int32, dev)
+                    call("ctk_conv_first_pool_codes", ptr(x), c_int(n), c_int(c_total), c_int(br.c_offset), c_int(cin), c_int(h),
                          c_int(w), ptr(wfold), ptr(shift), c_int(cout), c_float(LEAKY_SLOPE), ptr(dst), c_int(cstride),
-                         c_int(coff), stream())
+                         c_int(coff), ptr(codes), stream())
                     blocks.append({"y": None, "x_in": None, "pooled": (dst, cstride, coff), "scale": scale, "shift": shift,
                                    "mean": mean, "invstd": invstd, "h": h, "w": w, "conv": conv, "bn": bn, "gram": gram,
-                                   "wf": wfold})
+                                   "codes": codes})
                     cur = dst
                     h, w = h // 2, w // 2
                     continue
@@ -289,20 +290,19 @@ class TrainEngine:
                 cout, cin = conv.out_channels, conv.in_channels
                 sums = self._new((2 * cout,), torch.float32, dev)
                 if b.get("gram") is not None:
-                    # first block: the fused kernel recomputes each window's pre-activations from the input, which gives
-                    # the BN reductions (exactly, in fp32) together with the data term of the weight gradient
+                    # first block: the forward pass stored arg-max / sign codes, so the data term of the weight gradient and
+                    # sum(dA) are one gather over the input; sum(dA * xhat) follows from them in the finalize kernel
                     if dp_cstride != cout or dp_coff != 0:
                         raise _lib.CtkError("the first block's output gradient must be dense")
                     T = 9 * cin
                     t1 = self._new((cout, T), torch.float32, dev)
-                    call("ctk_first_wgrad_fused", ptr(x), c_int(n), c_int(x.shape[1]), c_int(br.c_offset), c_int(cin), c_int(h),
-                         c_int(w), ptr(b["wf"]), ptr(b["shift"]), ptr(bn.weight), ptr(bn.bias), c_float(LEAKY_SLOPE), ptr(dp),
-                         c_int(cout), ptr(t1), ptr(sums), stream())
-                    done(bn.bias, sums[:cout])
-                    done(bn.weight, sums[cout:])
+                    call("ctk_first_wgrad_codes", ptr(x), c_int(n), c_int(x.shape[1]), c_int(br.c_offset), c_int(cin), c_int(h),
+                         c_int(w), ptr(b["codes"]), ptr(dp), c_int(cout), c_float(LEAKY_SLOPE), ptr(t1), ptr(sums), stream())
                     dw = self._new(tuple(conv.weight.shape), torch.float32, dev)
                     call("ctk_first_wgrad_finalize", ptr(t1), ptr(b["gram"]), ptr(conv.weight), ptr(b["scale"]), ptr(b["mean"]),
                          ptr(b["invstd"]), ptr(sums), c_double(float(n) * h * w), c_int(cout), c_int(cin), ptr(dw), stream())
+                    done(bn.bias, sums[:cout])
+                    done(bn.weight, sums[cout:])
                     done(conv.weight, dw)
                     done(conv.bias, torch.zeros_like(conv.bias))
                     continue
