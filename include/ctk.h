@@ -127,6 +127,29 @@ int ctk_head_eval(const float* fc1_partial, int splits, int m_stride, int n, int
                   float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * fp32-class inference ("precision = fp32", north_star: score within 1e-5 of the fp32 reference).
+ * The tensor cores only multiply bf16, so every fp32 operand is carried as a pair of bf16 numbers, v = hi + lo with
+ * hi = bf16(v), lo = bf16(v - hi) (16 significant bits), and every product is three MMAs,
+ *     x*w ~= x_hi*w_hi + x_lo*w_hi + x_hi*w_lo        (dropped x_lo*w_lo ~ 2^-17 relative),
+ * accumulated in fp32 in TMEM.  Activations between blocks are NHWC bf16 tensors with 2C channels [hi(C) | lo(C)]
+ * (written through the out_hi / out_lo pointers, which share pixel stride and channel offset), conv weights are
+ * [9][Cout][3*Cin] = [w_hi | w_hi | w_lo] so that the SAME implicit-GEMM pipeline runs with K = 3*Cin over
+ * [x_hi | x_lo | x_hi]; BatchNorm, max-pool and LeakyReLU run on the fp32 accumulators.  FC1 is three split-K GEMMs
+ * (feat_hi*W_hi, feat_lo*W_hi, feat_hi*W_lo) whose partial sums ctk_head_eval adds up (splits = 3 * splits).
+ * Same reference lines as the bf16 entry points above.
+ * ------------------------------------------------------------------------------------------ */
+int ctk_pack_conv_weight_split_bf16(const float* w, int cout, int cin, void* w_split_bf16, void* stream);
+int ctk_pack_fc1_weight_split_bf16(const float* w, int out_features, int channels, int hw, void* w_hi_bf16,
+                                   void* w_lo_bf16, void* stream);
+int ctk_conv_first_eval_split(const float* x, int n, int c_total, int c_offset, int cin, int H, int W,
+                              const float* w_folded, const float* shift, int cout, float slope,
+                              void* out_hi_bf16, void* out_lo_bf16, int out_cstride, int out_coffset, void* stream);
+/* x_split: [n,H,W,2*cin] bf16 = [hi | lo]; cin = logical input channels (multiple of 64), cout % 128 == 0. */
+int ctk_conv3x3_tc_eval_split(const void* x_split_bf16, int n, int H, int W, int cin, const void* w_split_bf16,
+                              int cout, const float* scale, const float* shift, float slope, void* out_hi_bf16,
+                              void* out_lo_bf16, int out_cstride, int out_coffset, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * MSE loss (mean reduction) and its gradient.  Replaces: torch.nn.MSELoss(), train_model.py:636,421.
  * loss_out: [1] fp32; grad_out (may be NULL): [n] fp32 = 2*(out-target)/n.
  * ------------------------------------------------------------------------------------------ */

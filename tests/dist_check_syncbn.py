@@ -1,0 +1,93 @@
+"""Run under torchrun on >= 2 GPUs: data-parallel training with sync_bn=True over shards of a batch must reproduce the
+single-process step on the whole batch (what the reference's one-process loop computes, train_model.py:415-426):
+same loss, same gradients, same BatchNorm running statistics -- up to fp32 summation order and the bf16 rounding flips
+that follow from it.  Prints one line per check and exits non-zero on failure.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29611 \
+        tests/dist_check_syncbn.py [single|double]
+"""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (os.path.join(ROOT, "torch-unet_b200"), os.path.join(ROOT, "oracle")):
+    sys.path.insert(0, p)
+
+import ctk                       # noqa: E402
+import crosstalk_oracle as orc   # noqa: E402  (synthetic data + dropout masks only)
+
+
+def build(kind):
+    torch.manual_seed(0)
+    m = (ctk.AdvancedRegressionModel(initial_filters=128, num_conv_blocks=6) if kind == "single"
+         else ctk.SimplifiedTwoBranchRegressionModel(initial_filters_per_branch=64))
+    return m.cuda().train()
+
+
+def step(model, x, y, masks):
+    eng = ctk.models.get_train_engine(model)
+    eng.forced_masks = masks
+    for p in model.parameters():
+        p.grad = None
+    loss = torch.nn.functional.mse_loss(model(x), y)
+    loss.backward()
+    return loss.detach(), {k: p.grad.detach().clone() for k, p in model.named_parameters()}
+
+
+def main():
+    kind = sys.argv[1] if len(sys.argv) > 1 else "double"
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    per = 4
+    n = per * world
+    x, y = orc.synthetic_batch(n, seed=77)
+    p_drop = 0.1 if kind == "single" else 0.5
+    m1, m2 = orc.dropout_masks(n, p_drop, seed=5)
+    x, y, m1, m2 = x.cuda(), y.cuda(), m1.cuda(), m2.cuda()
+    # single process, whole batch
+    full = build(kind)
+    loss_full, g_full = step(full, x, y, (m1, m2))
+    # data parallel with global BatchNorm statistics
+    dp = build(kind)
+    ctk.parallel.broadcast_parameters(dp)
+    ctk.parallel.attach(dp, sync_bn=True)
+    sl = slice(rank * per, (rank + 1) * per)
+    loss_local, g_dp = step(dp, x[sl].contiguous(), y[sl].contiguous(), (m1[sl].contiguous(), m2[sl].contiguous()))
+    loss_dp = loss_local.clone()
+    dist.all_reduce(loss_dp, op=dist.ReduceOp.AVG)
+    ok = True
+    rel_loss = abs(loss_dp.item() - loss_full.item()) / abs(loss_full.item())
+    ok &= rel_loss < 2e-3
+    worst, worst_name = 0.0, ""
+    num = den = 0.0
+    for k in g_full:
+        a, b = g_dp[k].float(), g_full[k].float()
+        if b.norm().item() < 1e-7:
+            continue
+        rel = ((a - b).norm() / b.norm()).item()
+        num += ((a - b) ** 2).sum().item()
+        den += (b ** 2).sum().item()
+        if rel > worst:
+            worst, worst_name = rel, k
+    whole = (num / den) ** 0.5
+    ok &= whole < 2e-2 and worst < 0.15
+    sd_f, sd_d = full.state_dict(), dp.state_dict()
+    stat_err = max(((sd_d[k].float() - sd_f[k].float()).abs().max() / (sd_f[k].float().abs().max() + 1e-12)).item()
+                   for k in sd_f if "running_" in k)
+    ok &= stat_err < 1e-3
+    flag = torch.tensor([1.0 if ok else 0.0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print(f"syncbn {kind} world {world}: loss full {loss_full.item():.6f} dp {loss_dp.item():.6f} (rel {rel_loss:.2e}); "
+              f"whole-gradient rel L2 {whole:.2e}; worst tensor {worst_name} {worst:.2e}; running-stat rel err {stat_err:.2e}; "
+              f"{'OK' if flag.item() == 1.0 else 'FAIL'}", flush=True)
+    dist.destroy_process_group()
+    sys.exit(0 if flag.item() == 1.0 else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -143,3 +143,18 @@ def test_short_adam_loss_curve_matches_oracle(golden, kind):
     # bf16-rounding model of the same path does
     assert max(rel) <= 2.5 * max(rel_emu) + 0.05
     assert all(np.isfinite(losses)) and losses[-1] < losses[0]
+
+
+@pytest.mark.parametrize("kind", ["double"])
+def test_syncbn_data_parallel_matches_single_process(kind):
+    """2 ranks x 4 tiles with sync_bn=True == 1 process x 8 tiles (the reference's single-process semantics)."""
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run tests/dist_check_syncbn.py under torchrun on a multi-GPU box)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(29600 + os.getpid() % 300), os.path.join(root, "tests", "dist_check_syncbn.py"), kind]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    print(r.stdout[-2000:], r.stderr[-2000:])
+    assert r.returncode == 0

@@ -339,13 +339,15 @@ struct WinCfg {
   static constexpr int smem_bytes(int cout) { return 1024 + (cout / 8) * kSbo + kGroups * kGroupBytes + 256; }
 };
 
-template <int CIN, bool kCodes>
+// kMode: 0 = pooled bf16 output, 1 = + arg-max / sign codes, 2 = fp32-class output as bf16 (hi, lo) pairs (out, out_lo)
+template <int CIN, int kMode>
 __global__ void __launch_bounds__(WinCfg<CIN>::kThreads, 1)
 conv_first_win_kernel(const float* __restrict__ x, int n_img, int c_total, int c_offset, int H, int W,
                       const float* __restrict__ w_folded, const float* __restrict__ shift, float slope, int cout,
                       __nv_bfloat16* __restrict__ out, int out_cstride, int out_coffset, uint32_t* __restrict__ codes,
-                      FastDiv div_rx, FastDiv div_ry, int total_regions) {
+                      __nv_bfloat16* __restrict__ out_lo, FastDiv div_rx, FastDiv div_ry, int total_regions) {
   using C = WinCfg<CIN>;
+  constexpr bool kCodes = kMode == 1;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* b_smem = smem;
@@ -551,13 +553,31 @@ conv_first_win_kernel(const float* __restrict__ x, int n_img, int c_total, int c
             best[i] = fmaxf(fmaxf(__uint_as_float(v[0][i]), __uint_as_float(v[1][i])),
                             fmaxf(__uint_as_float(v[2][i]), __uint_as_float(v[3][i])));
         }
-        uint32_t o[8];
+        if constexpr (kMode == 2) {
+          uint32_t oh[8], ol[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = leaky_bf16x2(pack_bf16x2(best[2 * i], best[2 * i + 1]), slope2);
-        if (valid) {
-          __nv_bfloat16* dst = out + pooled_pix * out_cstride + out_coffset + cr * 32 + hf * 16;
-          reinterpret_cast<uint4*>(dst)[0] = make_uint4(o[0], o[1], o[2], o[3]);
-          reinterpret_cast<uint4*>(dst)[1] = make_uint4(o[4], o[5], o[6], o[7]);
+          for (int i = 0; i < 8; ++i) {
+            const float a0 = leaky(best[2 * i], slope), a1 = leaky(best[2 * i + 1], slope);
+            const uint32_t s0 = split_hi_lo(a0), s1 = split_hi_lo(a1);
+            oh[i] = (s0 & 0xffffu) | (s1 << 16);
+            ol[i] = (s0 >> 16) | (s1 & 0xffff0000u);
+          }
+          if (valid) {
+            const size_t off = pooled_pix * out_cstride + out_coffset + cr * 32 + hf * 16;
+            reinterpret_cast<uint4*>(out + off)[0] = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+            reinterpret_cast<uint4*>(out + off)[1] = make_uint4(oh[4], oh[5], oh[6], oh[7]);
+            reinterpret_cast<uint4*>(out_lo + off)[0] = make_uint4(ol[0], ol[1], ol[2], ol[3]);
+            reinterpret_cast<uint4*>(out_lo + off)[1] = make_uint4(ol[4], ol[5], ol[6], ol[7]);
+          }
+        } else {
+          uint32_t o[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] = leaky_bf16x2(pack_bf16x2(best[2 * i], best[2 * i + 1]), slope2);
+          if (valid) {
+            __nv_bfloat16* dst = out + pooled_pix * out_cstride + out_coffset + cr * 32 + hf * 16;
+            reinterpret_cast<uint4*>(dst)[0] = make_uint4(o[0], o[1], o[2], o[3]);
+            reinterpret_cast<uint4*>(dst)[1] = make_uint4(o[4], o[5], o[6], o[7]);
+          }
         }
       }
       tc_fence_before();   // TMEM reads of this round are ordered before the barrier the next MMA issue follows
@@ -573,21 +593,21 @@ conv_first_win_kernel(const float* __restrict__ x, int n_img, int c_total, int c
   }
 }
 
-template <int CIN, bool kCodes>
+template <int CIN, int kMode>
 int launch_first_win(const float* x, int n, int c_total, int c_offset, int H, int W, const float* w_folded,
                      const float* shift, float slope, int cout, __nv_bfloat16* out, int out_cstride, int out_coffset,
-                     uint32_t* codes, cudaStream_t stream) {
+                     uint32_t* codes, __nv_bfloat16* out_lo, cudaStream_t stream) {
   using C = WinCfg<CIN>;
   const int regions_x = (W / 2 + C::kWinW - 1) / C::kWinW;
   const int regions_y = (H / 2 + C::kWinH - 1) / C::kWinH;
   const long long total = static_cast<long long>(n) * regions_x * regions_y;
   if (total >= (1ll << 30)) return CTK_ERR_BAD_ARG;
-  auto kernel = conv_first_win_kernel<CIN, kCodes>;
+  auto kernel = conv_first_win_kernel<CIN, kMode>;
   const int smem = C::smem_bytes(cout);
   CTK_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int grid = static_cast<int>(std::min<long long>((total + C::kGroups - 1) / C::kGroups, ctk::num_sms()));
   kernel<<<grid, C::kThreads, smem, stream>>>(x, n, c_total, c_offset, H, W, w_folded, shift, slope, cout, out, out_cstride,
-                                              out_coffset, codes, make_fastdiv(regions_x), make_fastdiv(regions_y),
+                                              out_coffset, codes, out_lo, make_fastdiv(regions_x), make_fastdiv(regions_y),
                                               static_cast<int>(total));
   return ctk::check_launch();
 }
@@ -615,25 +635,32 @@ int launch_first(const float* x, int n, int c_total, int c_offset, int H, int W,
 
 static int first_pool_dispatch(const float* x, int n, int c_total, int c_offset, int cin, int H, int W,
                                const float* w_folded, const float* shift, int cout, float slope, void* out_bf16,
-                               int out_cstride, int out_coffset, void* codes, void* stream) {
+                               int out_cstride, int out_coffset, void* codes, void* out_lo_bf16, void* stream) {
   if (n == 0) return CTK_OK;
   CTK_REQUIRE(x && w_folded && shift && out_bf16 && n > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0);
   CTK_REQUIRE(c_offset >= 0 && c_offset + cin <= c_total && out_coffset >= 0 && out_coffset + cout <= out_cstride);
   CTK_REQUIRE(out_cstride % 8 == 0 && out_coffset % 8 == 0 && (reinterpret_cast<uintptr_t>(out_bf16) & 15) == 0);
   CTK_REQUIRE(cout > 0 && cout % 32 == 0 && cout <= 256 && (reinterpret_cast<uintptr_t>(codes) & 7) == 0);
+  CTK_REQUIRE((reinterpret_cast<uintptr_t>(out_lo_bf16) & 15) == 0 && !(codes && out_lo_bf16));
   cudaStream_t s = ctk::as_stream(stream);
   __nv_bfloat16* out = static_cast<__nv_bfloat16*>(out_bf16);
+  __nv_bfloat16* out_lo = static_cast<__nv_bfloat16*>(out_lo_bf16);
   uint32_t* cd = static_cast<uint32_t*>(codes);
-  if (cin == 1)
-    return cd ? launch_first_win<1, true>(x, n, c_total, c_offset, H, W, w_folded, shift, slope, cout, out, out_cstride,
-                                          out_coffset, cd, s)
-              : launch_first_win<1, false>(x, n, c_total, c_offset, H, W, w_folded, shift, slope, cout, out, out_cstride,
-                                           out_coffset, cd, s);
-  if (cin == 2)
-    return cd ? launch_first_win<2, true>(x, n, c_total, c_offset, H, W, w_folded, shift, slope, cout, out, out_cstride,
-                                          out_coffset, cd, s)
-              : launch_first_win<2, false>(x, n, c_total, c_offset, H, W, w_folded, shift, slope, cout, out, out_cstride,
-                                           out_coffset, cd, s);
+  const int mode = cd ? 1 : (out_lo ? 2 : 0);
+#define CTK_FIRST_LAUNCH(CIN, MODE)                                                                                  \
+  return launch_first_win<CIN, MODE>(x, n, c_total, c_offset, H, W, w_folded, shift, slope, cout, out, out_cstride, \
+                                     out_coffset, cd, out_lo, s)
+  if (cin == 1) {
+    if (mode == 0) { CTK_FIRST_LAUNCH(1, 0); }
+    if (mode == 1) { CTK_FIRST_LAUNCH(1, 1); }
+    CTK_FIRST_LAUNCH(1, 2);
+  }
+  if (cin == 2) {
+    if (mode == 0) { CTK_FIRST_LAUNCH(2, 0); }
+    if (mode == 1) { CTK_FIRST_LAUNCH(2, 1); }
+    CTK_FIRST_LAUNCH(2, 2);
+  }
+#undef CTK_FIRST_LAUNCH
   return CTK_ERR_UNSUPPORTED;
 }
 
@@ -641,7 +668,16 @@ extern "C" int ctk_conv_first_eval(const float* x, int n, int c_total, int c_off
                                    const float* w_folded, const float* shift, int cout, float slope, void* out_bf16,
                                    int out_cstride, int out_coffset, void* stream) {
   return first_pool_dispatch(x, n, c_total, c_offset, cin, H, W, w_folded, shift, cout, slope, out_bf16, out_cstride,
-                             out_coffset, nullptr, stream);
+                             out_coffset, nullptr, nullptr, stream);
+}
+
+extern "C" int ctk_conv_first_eval_split(const float* x, int n, int c_total, int c_offset, int cin, int H, int W,
+                                         const float* w_folded, const float* shift, int cout, float slope,
+                                         void* out_hi_bf16, void* out_lo_bf16, int out_cstride, int out_coffset,
+                                         void* stream) {
+  CTK_REQUIRE(out_lo_bf16 != nullptr);
+  return first_pool_dispatch(x, n, c_total, c_offset, cin, H, W, w_folded, shift, cout, slope, out_hi_bf16, out_cstride,
+                             out_coffset, nullptr, out_lo_bf16, stream);
 }
 
 extern "C" int ctk_conv_first_pool_codes(const float* x, int n, int c_total, int c_offset, int cin, int H, int W,
@@ -650,7 +686,7 @@ extern "C" int ctk_conv_first_pool_codes(const float* x, int n, int c_total, int
                                          void* stream) {
   CTK_REQUIRE(codes_u32 != nullptr);
   return first_pool_dispatch(x, n, c_total, c_offset, cin, H, W, w_folded, shift, cout, slope, out_bf16, out_cstride,
-                             out_coffset, codes_u32, stream);
+                             out_coffset, codes_u32, nullptr, stream);
 }
 
 extern "C" int ctk_conv_first_raw(const float* x, int n, int c_total, int c_offset, int cin, int H, int W,

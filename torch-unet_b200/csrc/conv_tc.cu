@@ -49,7 +49,8 @@ enum : int {
   kEpiEvalPool = 0,   // folded BN -> 2x2 max-pool -> LeakyReLU, pooled bf16 store (the inference block)
   kEpiEvalAny = 1,    // folded BN with run-time pool / activation switches (CTK_CONV_NO_POOL / CTK_CONV_NO_ACT)
   kEpiRaw = 2,        // bf16 store of the raw accumulators (dgrad)
-  kEpiRawStats = 3    // raw store + per-channel sum / sum of squares of the fp32 accumulators (train-mode forward)
+  kEpiRawStats = 3,   // raw store + per-channel sum / sum of squares of the fp32 accumulators (train-mode forward)
+  kEpiEvalPoolSplit = 4   // fp32-class inference: BN, pool and LeakyReLU in fp32, output stored as bf16 (hi, lo) pairs
 };
 constexpr int kScratchPitch = 36;                                  // floats; 16-byte aligned rows, conflict-free both ways
 constexpr int kScratchBytes = kEpiWarps * 32 * kScratchPitch * 4;  // per-warp transpose tile for the statistics
@@ -76,7 +77,10 @@ struct ConvParams {
   const float* shift;
   float* stats;         // nullptr, or [2*cout]: per-channel sum and sum of squares of the raw fp32 accumulators
   __nv_bfloat16* out;
+  __nv_bfloat16* out_lo;   // kEpiEvalPoolSplit: low halves, same pixel / channel addressing as `out`
   int out_cstride, out_coffset;
+  int cin_phys;         // channels of the activation tensor in memory (= cin, or 2/3 cin for the split layout)
+  int a_wrap;           // split layout: K chunk c >= a_wrap re-reads physical chunk c - a_wrap ([hi | lo | hi] from [hi | lo])
 };
 
 struct TileCoord {
@@ -184,6 +188,48 @@ __device__ __forceinline__ void epilogue_block(const ConvParams& p, const EpiCtx
         reinterpret_cast<uint4*>(dst)[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
     }
     return;
+  } else if constexpr (kEpi == kEpiEvalPoolSplit) {
+    const uint32_t sc = e.sc_addr + static_cast<uint32_t>((t.n0 + ch0) * 4);
+    const uint32_t sh = e.sh_addr + static_cast<uint32_t>((t.n0 + ch0) * 4);
+    float f[32];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 a = lds128(sc + j * 16), b = lds128(sh + j * 16);
+      f[4 * j] = fmaf(__uint_as_float(v[4 * j]), a.x, b.x);
+      f[4 * j + 1] = fmaf(__uint_as_float(v[4 * j + 1]), a.y, b.y);
+      f[4 * j + 2] = fmaf(__uint_as_float(v[4 * j + 2]), a.z, b.z);
+      f[4 * j + 3] = fmaf(__uint_as_float(v[4 * j + 3]), a.w, b.w);
+    }
+    const bool odd_x = (lane & 1) != 0, odd_y = (lane & 8) != 0;
+    float q[16], r[8];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float send = odd_x ? f[i] : f[16 + i];
+      const float keep = odd_x ? f[16 + i] : f[i];
+      q[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 1));
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float send = odd_y ? q[i] : q[8 + i];
+      const float keep = odd_y ? q[8 + i] : q[i];
+      r[i] = leaky(fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 8)), p.slope);
+    }
+    if (e.valid) {
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(r[2 * i]), h1 = __float2bfloat16_rn(r[2 * i + 1]);
+        hi[i] = static_cast<uint32_t>(__bfloat16_as_ushort(h0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(h1)) << 16);
+        lo[i] = pack_bf16x2(r[2 * i] - __bfloat162float(h0), r[2 * i + 1] - __bfloat162float(h1));
+      }
+      const int ch = t.n0 + ch0 + (odd_x ? 16 : 0) + (odd_y ? 8 : 0);
+      const size_t off =
+          (static_cast<size_t>(t.img) * e.Hp * e.Wp + static_cast<size_t>(e.y >> 1) * e.Wp + (e.x >> 1)) * p.out_cstride +
+          p.out_coffset + ch;
+      *reinterpret_cast<uint4*>(p.out + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(p.out_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+    return;
   } else {
     const uint32_t sc = e.sc_addr + static_cast<uint32_t>((t.n0 + ch0) * 4);
     const uint32_t sh = e.sh_addr + static_cast<uint32_t>((t.n0 + ch0) * 4);
@@ -266,7 +312,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
   }
   if (warp == 2) tmem_alloc<kCtaGroup>(&sl->tmem_base, C::kTmemCols);
   for (int i = threadIdx.x; i < 512; i += kThreads) {
-    if constexpr (kEpi == kEpiEvalPool || kEpi == kEpiEvalAny) {
+    if constexpr (kEpi == kEpiEvalPool || kEpi == kEpiEvalAny || kEpi == kEpiEvalPoolSplit) {
       sl->ch_a[i] = i < p.cout ? __ldg(p.scale + i) : 0.f;
       sl->ch_b[i] = i < p.cout ? __ldg(p.shift + i) : 0.f;
     } else {
@@ -292,13 +338,14 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       for (int c = 0; c < chunks; ++c) {
         mbar_wait(&sl->a_empty[stage], phase ^ 1);
         uint8_t* dst = a_smem + stage * kAStageBytes;
+        const int cc = (p.a_wrap > 0 && c >= p.a_wrap) ? c - p.a_wrap : c;
         if (elect_one()) {
           if constexpr (kCtaGroup == 1) {
             mbar_arrive_expect_tx(&sl->a_full[stage], kABytes);
-            tma_load_4d(dst, &tm_a, &sl->a_full[stage], c * kKC, t.x0 - 1, t.y0 - 1, t.img);
+            tma_load_4d(dst, &tm_a, &sl->a_full[stage], cc * kKC, t.x0 - 1, t.y0 - 1, t.img);
           } else {
             if (rank == 0) mbar_arrive_expect_tx(&sl->a_full[stage], 2 * kABytes);
-            tma_load_4d_pair(dst, &tm_a, mapa_shared(smem_u32(&sl->a_full[stage]), 0), c * kKC, t.x0 - 1, t.y0 - 1,
+            tma_load_4d_pair(dst, &tm_a, mapa_shared(smem_u32(&sl->a_full[stage]), 0), cc * kKC, t.x0 - 1, t.y0 - 1,
                              t.img);
           }
         }
@@ -472,10 +519,9 @@ int launch_conv(const void* x_bf16, const void* w_packed_bf16, ConvParams p, cud
 
   CUtensorMap tm_a, tm_b;
   {
-    const uint64_t dims[4] = {static_cast<uint64_t>(p.cin), static_cast<uint64_t>(p.W), static_cast<uint64_t>(p.H),
-                              static_cast<uint64_t>(p.n_img)};
-    const uint64_t strides[3] = {static_cast<uint64_t>(p.cin) * 2, static_cast<uint64_t>(p.W) * p.cin * 2,
-                                 static_cast<uint64_t>(p.H) * p.W * p.cin * 2};
+    const uint64_t cp = static_cast<uint64_t>(p.cin_phys);
+    const uint64_t dims[4] = {cp, static_cast<uint64_t>(p.W), static_cast<uint64_t>(p.H), static_cast<uint64_t>(p.n_img)};
+    const uint64_t strides[3] = {cp * 2, static_cast<uint64_t>(p.W) * cp * 2, static_cast<uint64_t>(p.H) * p.W * cp * 2};
     const uint32_t box[4] = {kKC, kHaloW, kHaloH, 1};
     int st = ctk::encode_tmap_bf16_sw128(&tm_a, x_bf16, 4, dims, strides, box);
     if (st != CTK_OK) return st;
@@ -510,7 +556,7 @@ int launch_conv(const void* x_bf16, const void* w_packed_bf16, ConvParams p, cud
 
 static int conv_dispatch(const void* x_bf16, int n, int H, int W, int cin, const void* w_packed_bf16, int cout,
                          const float* scale, const float* shift, float* stats, float slope, void* out_bf16,
-                         int out_cstride, int out_coffset, int flags, void* stream) {
+                         int out_cstride, int out_coffset, int flags, void* stream, void* out_lo_bf16 = nullptr) {
   if (n == 0) return CTK_OK;
   CTK_REQUIRE(x_bf16 && w_packed_bf16 && out_bf16 && (scale == nullptr) == (shift == nullptr));
   CTK_REQUIRE(n > 0 && H > 0 && W > 0 && H % 2 == 0 && W % kTileW == 0 && cin > 0 && cin % kKC == 0 && cout > 0 &&
@@ -531,8 +577,19 @@ static int conv_dispatch(const void* x_bf16, int n, int H, int W, int cin, const
   p.slope = slope;
   p.scale = scale; p.shift = shift; p.stats = stats;
   p.out = static_cast<__nv_bfloat16*>(out_bf16);
+  p.out_lo = static_cast<__nv_bfloat16*>(out_lo_bf16);
   p.out_cstride = out_cstride; p.out_coffset = out_coffset;
+  p.cin_phys = cin; p.a_wrap = 0;
   cudaStream_t s = ctk::as_stream(stream);
+  if (out_lo_bf16 != nullptr) {
+    // fp32-class: the activation tensor holds [hi | lo] (2/3 of the logical K), K runs over [hi | lo | hi]
+    CTK_REQUIRE(cin % 3 == 0 && (cin / 3) % kKC == 0 && scale != nullptr && p.pool && p.act);
+    p.cin_phys = cin / 3 * 2;
+    p.a_wrap = p.cin_phys / kKC;
+    if (cout % 256 == 0) return launch_conv<2, 256, kEpiEvalPoolSplit>(x_bf16, w_packed_bf16, p, s);
+    if (cout % 128 == 0) return launch_conv<2, 128, kEpiEvalPoolSplit>(x_bf16, w_packed_bf16, p, s);
+    return CTK_ERR_UNSUPPORTED;
+  }
   if (stats != nullptr) CTK_CUDA_TRY(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * cout, s));
   const int epi = scale == nullptr ? (stats != nullptr ? kEpiRawStats : kEpiRaw)
                                    : (p.pool && p.act ? kEpiEvalPool : kEpiEvalAny);
@@ -556,6 +613,15 @@ extern "C" int ctk_conv3x3_tc_eval(const void* x_bf16, int n, int H, int W, int 
   CTK_REQUIRE(scale && shift);
   return conv_dispatch(x_bf16, n, H, W, cin, w_packed_bf16, cout, scale, shift, nullptr, slope, out_bf16, out_cstride,
                        out_coffset, flags, stream);
+}
+
+extern "C" int ctk_conv3x3_tc_eval_split(const void* x_split_bf16, int n, int H, int W, int cin,
+                                         const void* w_split_bf16, int cout, const float* scale, const float* shift,
+                                         float slope, void* out_hi_bf16, void* out_lo_bf16, int out_cstride,
+                                         int out_coffset, void* stream) {
+  CTK_REQUIRE(scale && shift && out_lo_bf16 && (reinterpret_cast<uintptr_t>(out_lo_bf16) & 15) == 0);
+  return conv_dispatch(x_split_bf16, n, H, W, 3 * cin, w_split_bf16, cout, scale, shift, nullptr, slope, out_hi_bf16,
+                       out_cstride, out_coffset, 0, stream, out_lo_bf16);
 }
 
 extern "C" int ctk_conv3x3_tc_raw(const void* x_bf16, int n, int H, int W, int cin, const void* w_packed_bf16,

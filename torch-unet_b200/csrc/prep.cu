@@ -33,6 +33,25 @@ __global__ void pack_conv_kernel(const float* __restrict__ w, int cout, int cin,
   }
 }
 
+// fp32-class operand: out[tap][co][3*cin] = [ hi(w) | hi(w) | lo(w) ] along K, to be multiplied with activations laid out
+// [ hi(x) | lo(x) | hi(x) ]: x*w ~ hi*hi + lo*hi + hi*lo (the dropped lo*lo term is ~2^-17 relative)
+__global__ void pack_conv_split_kernel(const float* __restrict__ w, int cout, int cin, __nv_bfloat16* __restrict__ out) {
+  const size_t total = static_cast<size_t>(9) * cout * cin;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int ci = static_cast<int>(i % cin);
+    const int co = static_cast<int>((i / cin) % cout);
+    const int tap = static_cast<int>(i / (static_cast<size_t>(cin) * cout));
+    const float v = w[(static_cast<size_t>(co) * cin + ci) * 9 + tap];
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+    __nv_bfloat16* row = out + (static_cast<size_t>(tap) * cout + co) * 3 * cin;
+    row[ci] = hi;
+    row[cin + ci] = hi;
+    row[2 * cin + ci] = lo;
+  }
+}
+
 // dgrad operand: out[tap'][ci][co] = w[co][ci][8 - tap']  (weights rotated by 180 degrees, Cin/Cout swapped)
 __global__ void pack_conv_dgrad_kernel(const float* __restrict__ w, int cout, int cin, __nv_bfloat16* __restrict__ out) {
   const size_t total = static_cast<size_t>(9) * cout * cin;
@@ -89,12 +108,14 @@ __global__ void pack_first_kernel(const float* __restrict__ w, const float* __re
 }
 
 // out[o][p*C + c] = w[o][c*HW + p]; one block per (row o, 32-pixel x 32-channel tile), transposed through smem
-__global__ void pack_fc1_kernel(const float* __restrict__ w, int channels, int hw, __nv_bfloat16* __restrict__ out) {
+__global__ void pack_fc1_kernel(const float* __restrict__ w, int channels, int hw, __nv_bfloat16* __restrict__ out,
+                                __nv_bfloat16* __restrict__ out_lo) {
   __shared__ float tile[32][33];
   const size_t row = blockIdx.z;
   const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
   const float* src = w + row * static_cast<size_t>(channels) * hw;
   __nv_bfloat16* dst = out + row * static_cast<size_t>(channels) * hw;
+  __nv_bfloat16* dst_lo = out_lo ? out_lo + row * static_cast<size_t>(channels) * hw : nullptr;
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
     const int c = c0 + j, p = p0 + threadIdx.x;
     tile[j][threadIdx.x] = (c < channels && p < hw) ? src[static_cast<size_t>(c) * hw + p] : 0.f;
@@ -102,7 +123,12 @@ __global__ void pack_fc1_kernel(const float* __restrict__ w, int channels, int h
   __syncthreads();
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
     const int p = p0 + j, c = c0 + threadIdx.x;
-    if (c < channels && p < hw) dst[static_cast<size_t>(p) * channels + c] = __float2bfloat16_rn(tile[threadIdx.x][j]);
+    if (c < channels && p < hw) {
+      const float v = tile[threadIdx.x][j];
+      const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+      dst[static_cast<size_t>(p) * channels + c] = hi;
+      if (dst_lo) dst_lo[static_cast<size_t>(p) * channels + c] = __float2bfloat16_rn(v - __bfloat162float(hi));
+    }
   }
 }
 
@@ -164,7 +190,25 @@ int ctk_pack_fc1_weight_bf16(const float* w, int out_features, int channels, int
   CTK_REQUIRE(w && w_packed_bf16 && out_features > 0 && out_features <= 65535 && channels > 0 && hw > 0);
   dim3 grid((hw + 31) / 32, (channels + 31) / 32, out_features);
   pack_fc1_kernel<<<grid, dim3(32, 8), 0, ctk::as_stream(stream)>>>(w, channels, hw,
-                                                                    static_cast<__nv_bfloat16*>(w_packed_bf16));
+                                                                    static_cast<__nv_bfloat16*>(w_packed_bf16), nullptr);
+  return ctk::check_launch();
+}
+
+int ctk_pack_fc1_weight_split_bf16(const float* w, int out_features, int channels, int hw, void* w_hi_bf16,
+                                   void* w_lo_bf16, void* stream) {
+  CTK_REQUIRE(w && w_hi_bf16 && w_lo_bf16 && out_features > 0 && out_features <= 65535 && channels > 0 && hw > 0);
+  dim3 grid((hw + 31) / 32, (channels + 31) / 32, out_features);
+  pack_fc1_kernel<<<grid, dim3(32, 8), 0, ctk::as_stream(stream)>>>(
+      w, channels, hw, static_cast<__nv_bfloat16*>(w_hi_bf16), static_cast<__nv_bfloat16*>(w_lo_bf16));
+  return ctk::check_launch();
+}
+
+int ctk_pack_conv_weight_split_bf16(const float* w, int cout, int cin, void* w_packed_bf16, void* stream) {
+  CTK_REQUIRE(w && w_packed_bf16 && cout > 0 && cin > 0);
+  const size_t total = static_cast<size_t>(9) * cout * cin;
+  const int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, 4096));
+  pack_conv_split_kernel<<<blocks, 256, 0, ctk::as_stream(stream)>>>(w, cout, cin,
+                                                                     static_cast<__nv_bfloat16*>(w_packed_bf16));
   return ctk::check_launch();
 }
 

@@ -9,11 +9,11 @@ from ._lib import CtkError, EXPORTED_SYMBOLS, LIB_PATH, load
 from .engine import InferenceEngine
 from .metrics import pearson_per_image
 from .models import (AdvancedRegressionModel, SimplifiedFeatureExtractionBranch, SimplifiedRegressionHead,
-                     SimplifiedTwoBranchRegressionModel, accelerate)
+                     SimplifiedTwoBranchRegressionModel, accelerate, set_precision)
 from .optim import Adam, mse_loss
 from .pipeline import HostScorer
 from . import parallel
 
 __all__ = ["CtkError", "EXPORTED_SYMBOLS", "LIB_PATH", "load", "InferenceEngine", "pearson_per_image",
            "AdvancedRegressionModel", "SimplifiedFeatureExtractionBranch", "SimplifiedRegressionHead",
-           "SimplifiedTwoBranchRegressionModel", "accelerate", "Adam", "mse_loss", "HostScorer", "parallel"]
+           "SimplifiedTwoBranchRegressionModel", "accelerate", "set_precision", "Adam", "mse_loss", "HostScorer", "parallel"]

@@ -39,6 +39,12 @@ _SIGNATURES = {
     "ctk_pack_fc1_weight_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "ctk_conv_first_eval": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
                                     c_float, c_void_p, c_int, c_int, c_void_p]),
+    "ctk_pack_conv_weight_split_bf16": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "ctk_pack_fc1_weight_split_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "ctk_conv_first_eval_split": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
+                                          c_float, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "ctk_conv3x3_tc_eval_split": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p,
+                                          c_float, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "ctk_conv_first_pool_codes": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
                                           c_float, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "ctk_conv3x3_tc_eval": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_float,
@@ -130,7 +136,8 @@ def stream() -> c_void_p:
 
 # kernels launched per successful call (bench.py reports the sum as "gpu_launches")
 KERNELS_PER_CALL = {"ctk_pearson_f32": 2, "ctk_fold_bn_eval": 1, "ctk_pack_conv_weight_bf16": 1, "ctk_pack_first_weight": 1,
-                    "ctk_pack_fc1_weight_bf16": 1, "ctk_conv_first_eval": 1, "ctk_conv_first_pool_codes": 1, "ctk_conv3x3_tc_eval": 1,
+                    "ctk_pack_fc1_weight_bf16": 1, "ctk_conv_first_eval": 1, "ctk_conv_first_pool_codes": 1, "ctk_pack_conv_weight_split_bf16": 1,
+                    "ctk_pack_fc1_weight_split_bf16": 1, "ctk_conv_first_eval_split": 1, "ctk_conv3x3_tc_eval_split": 1, "ctk_conv3x3_tc_eval": 1,
                     "ctk_gemm_bf16_splitk": 1, "ctk_head_eval": 1, "ctk_mse_loss": 1, "ctk_adam_multi": 1,
                     "ctk_conv_first_raw": 1, "ctk_conv3x3_tc_raw": 1, "ctk_pack_conv_weight_dgrad_bf16": 1,
                     "ctk_bn_finalize": 1, "ctk_bn_finalize_moments": 1, "ctk_first_patch_gram": 1,

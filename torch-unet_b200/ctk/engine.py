@@ -54,9 +54,12 @@ class _Branch:
 class InferenceEngine:
     """Eval-mode forward of either reference model through libctk."""
 
-    def __init__(self, model: torch.nn.Module, conv_flags: int = 0):
+    def __init__(self, model: torch.nn.Module, conv_flags: int = 0, precision: str = "bf16"):
+        if precision not in ("bf16", "fp32"):
+            raise _lib.CtkError("precision must be 'bf16' (bf16 operands, fp32 accumulate) or 'fp32' (split-bf16, fp32-class)")
         self.model = model
         self.conv_flags = conv_flags
+        self.precision = precision
         name = type(model).__name__
         if hasattr(model, "conv_layers") and hasattr(model, "fc_layers"):
             self.kind = "single"
@@ -103,6 +106,10 @@ class InferenceEngine:
                     w = torch.empty(conv.out_channels, conv.in_channels * 9, device=dev, dtype=torch.float32)
                     call("ctk_pack_first_weight", ptr(conv.weight), ptr(scale), c_int(conv.out_channels),
                          c_int(conv.in_channels), ptr(w), stream())
+                elif self.precision == "fp32":
+                    w = torch.empty(9, conv.out_channels, 3 * conv.in_channels, device=dev, dtype=torch.bfloat16)
+                    call("ctk_pack_conv_weight_split_bf16", ptr(conv.weight), c_int(conv.out_channels),
+                         c_int(conv.in_channels), ptr(w), stream())
                 else:
                     w = torch.empty(9, conv.out_channels, conv.in_channels, device=dev, dtype=torch.bfloat16)
                     call("ctk_pack_conv_weight_bf16", ptr(conv.weight), c_int(conv.out_channels),
@@ -111,8 +118,14 @@ class InferenceEngine:
         fc1, fc2, fc3 = self.lin
         hw = fc1.in_features // self.feat_channels
         w1 = torch.empty(fc1.out_features, fc1.in_features, device=dev, dtype=torch.bfloat16)
-        call("ctk_pack_fc1_weight_bf16", ptr(fc1.weight), c_int(fc1.out_features), c_int(self.feat_channels), c_int(hw),
-             ptr(w1), stream())
+        if self.precision == "fp32":
+            w1_lo = torch.empty_like(w1)
+            call("ctk_pack_fc1_weight_split_bf16", ptr(fc1.weight), c_int(fc1.out_features), c_int(self.feat_channels),
+                 c_int(hw), ptr(w1), ptr(w1_lo), stream())
+            pk["fc1.w_lo"] = w1_lo
+        else:
+            call("ctk_pack_fc1_weight_bf16", ptr(fc1.weight), c_int(fc1.out_features), c_int(self.feat_channels), c_int(hw),
+                 ptr(w1), stream())
         pk["fc1.w"] = w1
         pk["fc1.scale"], pk["fc1.shift"] = self._fold(fc1.bias, self.bns[0])
         pk["fc2.scale"], pk["fc2.shift"] = self._fold(fc2.bias, self.bns[1])
@@ -129,7 +142,61 @@ class InferenceEngine:
         return b
 
     # ------------------------------------------------------------------ forward
+    def _forward_slice_fp32(self, x: torch.Tensor, out: torch.Tensor, taps: Optional[dict]) -> None:
+        """fp32-class pass: activations as bf16 (hi, lo) pairs, three MMAs per product (include/ctk.h, split entry points)."""
+        n, c_total, H, W = x.shape
+        dev = x.device
+        pk = self._packed
+        depth = len(self.branches[0].pairs)
+        hf, wf = H >> depth, W >> depth
+        m_pad = (n + 127) // 128 * 128
+        feat = self._buf("feat_split", (2, m_pad, hf, wf, self.feat_channels), torch.bfloat16, dev)
+        c_out_off = 0
+        for bi, br in enumerate(self.branches):
+            h, w = H, W
+            cur = None
+            for li, (conv, bn) in enumerate(br.pairs):
+                cout = conv.out_channels
+                last = li == len(br.pairs) - 1
+                if last:
+                    hi, lo, cstride, coff = feat[0], feat[1], self.feat_channels, c_out_off
+                else:
+                    dst = self._buf(f"act_split{li}", (n, h // 2, w // 2, 2 * cout), torch.bfloat16, dev)
+                    hi, lo, cstride, coff = dst, dst[..., cout:], 2 * cout, 0
+                if li == 0:
+                    call("ctk_conv_first_eval_split", ptr(x), c_int(n), c_int(c_total), c_int(br.c_offset), c_int(br.cin),
+                         c_int(h), c_int(w), ptr(pk[f"b{bi}.l0.w"]), ptr(pk[f"b{bi}.l0.shift"]), c_int(cout),
+                         c_float(LEAKY_SLOPE), ptr(hi), ptr(lo), c_int(cstride), c_int(coff), stream())
+                else:
+                    call("ctk_conv3x3_tc_eval_split", ptr(cur), c_int(n), c_int(h), c_int(w), c_int(conv.in_channels),
+                         ptr(pk[f"b{bi}.l{li}.w"]), c_int(cout), ptr(pk[f"b{bi}.l{li}.scale"]),
+                         ptr(pk[f"b{bi}.l{li}.shift"]), c_float(LEAKY_SLOPE), ptr(hi), ptr(lo), c_int(cstride), c_int(coff),
+                         stream(), meta={"flops": 3 * 2.0 * n * h * w * cout * 9 * conv.in_channels})
+                if taps is not None and not last:
+                    taps[f"b{bi}.l{li}"] = dst[..., :cout].float() + dst[..., cout:].float()
+                cur = None if last else dst
+                h, w = h // 2, w // 2
+            c_out_off += br.channels[-1]
+        if taps is not None:
+            taps["feat"] = feat[0, :n].float() + feat[1, :n].float()
+        fc1, fc2, fc3 = self.lin
+        K = fc1.in_features
+        tiles = (m_pad // 128) * (fc1.out_features // 128)
+        splits = 1
+        while splits * 2 * tiles <= 160 and (K // 64) % (splits * 2) == 0 and K // (splits * 2) >= 512:
+            splits *= 2
+        partial = self._buf("fc1p_split", (3 * splits, m_pad, fc1.out_features), torch.float32, dev)
+        for j, (a, b) in enumerate(((feat[0], pk["fc1.w"]), (feat[1], pk["fc1.w"]), (feat[0], pk["fc1.w_lo"]))):
+            call("ctk_gemm_bf16_splitk", ptr(a), ptr(b), c_int(m_pad), c_int(fc1.out_features), c_int(K), c_int(splits),
+                 ptr(partial[j * splits:]), stream())
+        call("ctk_head_eval", ptr(partial), c_int(3 * splits), c_int(m_pad), c_int(n), c_int(fc1.out_features),
+             c_int(fc2.out_features), ptr(pk["fc1.scale"]), ptr(pk["fc1.shift"]), ptr(fc2.weight), ptr(pk["fc2.scale"]),
+             ptr(pk["fc2.shift"]), ptr(fc3.weight), ptr(fc3.bias), c_float(LEAKY_SLOPE), c_int(self.sigmoid_half),
+             ptr(out), stream())
+
     def _forward_slice(self, x: torch.Tensor, out: torch.Tensor, taps: Optional[dict]) -> None:
+        if self.precision == "fp32":
+            return self._forward_slice_fp32(x, out, taps)
         n, c_total, H, W = x.shape
         dev = x.device
         pk = self._packed

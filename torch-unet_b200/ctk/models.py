@@ -39,9 +39,20 @@ def get_engine(model) -> InferenceEngine:
     """The (lazily created) libctk inference engine bound to ``model``."""
     eng = model.__dict__.get("_ctk_engine")
     if eng is None:
-        eng = InferenceEngine(model, conv_flags=model.__dict__.get("_ctk_conv_flags", 0))
+        eng = InferenceEngine(model, conv_flags=model.__dict__.get("_ctk_conv_flags", 0),
+                              precision=model.__dict__.get("_ctk_precision", "bf16"))
         model.__dict__["_ctk_engine"] = eng
     return eng
+
+
+def set_precision(model, precision: str):
+    """Select the arithmetic of the eval-mode path: "bf16" (default: bf16 operands, fp32 accumulation; north_star bound
+    1e-3 on the score) or "fp32" (every operand carried as a bf16 hi/lo pair, three MMAs per product; bound 1e-5)."""
+    if precision not in ("bf16", "fp32"):
+        raise _lib.CtkError("precision must be 'bf16' or 'fp32'")
+    model.__dict__["_ctk_precision"] = precision
+    model.__dict__.pop("_ctk_engine", None)
+    return model
 
 
 def get_train_engine(model):
@@ -123,7 +134,7 @@ class SimplifiedTwoBranchRegressionModel(nn.Module):
     forward = _ctk_forward
 
 
-def accelerate(model: nn.Module, conv_flags: int = 0) -> nn.Module:
+def accelerate(model: nn.Module, conv_flags: int = 0, precision: str = "bf16") -> nn.Module:
     """Route ``model(inputs)`` of a reference-built instance through libctk, in place.
 
     Parameters, buffers, ``state_dict()``, ``str(model)`` and optimizers attached to the parameters are
@@ -131,6 +142,6 @@ def accelerate(model: nn.Module, conv_flags: int = 0) -> nn.Module:
     """
     InferenceEngine(model)            # validates the architecture now, loudly
     model.__dict__["_ctk_conv_flags"] = conv_flags
-    model.__dict__.pop("_ctk_engine", None)
+    set_precision(model, precision)
     model.forward = types.MethodType(_ctk_forward, model)
     return model

@@ -82,13 +82,22 @@ class GradSynchronizer:
         self._bucket_bytes = 0
 
 
-def attach(model: torch.nn.Module, process_group=None, **kw) -> GradSynchronizer:
-    """Make ``loss.backward()`` of a ctk model all-reduce (average) its gradients across the process group."""
+def attach(model: torch.nn.Module, process_group=None, sync_bn: bool = False, **kw) -> GradSynchronizer:
+    """Make ``loss.backward()`` of a ctk model all-reduce (average) its gradients across the process group.
+
+    ``sync_bn=True`` additionally sums every BatchNorm's batch statistics (and the matching backward reductions) over the
+    ranks, so that normalisation uses the GLOBAL batch like the single-process reference does (train_model.py runs one
+    process; its BatchNorm sees all of ``-b``).  These are a few KB per layer: ~20 small blocking all-reduces per step.
+    Without it the statistics are per rank, which is what torch's DistributedDataParallel does by default."""
     from .models import get_train_engine
     sync = GradSynchronizer(process_group, **kw)
     eng = get_train_engine(model)
     eng.on_grad_ready = sync.on_grad_ready
     eng.finalize_grads = sync.finalize
+    if sync_bn and sync.world > 1:
+        pg = process_group
+        eng.stat_allreduce = lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM, group=pg)
+        eng.stat_world = sync.world
     return sync
 
 

@@ -50,6 +50,11 @@ class TrainEngine:
         self.forced_masks: Optional[Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]] = None
         self.on_grad_ready: Optional[Callable[[torch.nn.Parameter, torch.Tensor], None]] = None
         self.finalize_grads: Optional[Callable[[dict], dict]] = None      # e.g. parallel.GradSynchronizer.finalize
+        # SyncBN (parallel.attach(..., sync_bn=True)): in-place SUM over ranks of a small statistics tensor, and the number
+        # of ranks.  The reference is one process, so its BatchNorm statistics span the whole global batch; with this
+        # hook the data-parallel path reproduces that instead of per-rank statistics.
+        self.stat_allreduce: Optional[Callable[[torch.Tensor], None]] = None
+        self.stat_world: int = 1
         self._saved: Optional[dict] = None
 
     # ------------------------------------------------------------------ helpers
@@ -67,6 +72,21 @@ class TrainEngine:
              ptr(bn.num_batches_tracked if track else None), c_float(mom), c_float(bn.eps), c_int(c), ptr(scale), ptr(shift),
              ptr(mean), ptr(invstd), stream())
         return scale, shift, mean, invstd
+
+    def _sync_stats(self, t: torch.Tensor) -> torch.Tensor:
+        if self.stat_allreduce is not None:
+            self.stat_allreduce(t)
+        return t
+
+    def _global_sums(self, sums: torch.Tensor) -> torch.Tensor:
+        """BN-backward reductions for the apply pass.  The kernels divide by the LOCAL element count, so under SyncBN they
+        are handed (sum over ranks) / world: that is the mean over the global batch.  The local sums stay the parameter
+        gradients (the gradient exchange averages them like every other gradient)."""
+        if self.stat_allreduce is None:
+            return sums
+        g = sums.clone()
+        self.stat_allreduce(g)
+        return g.div_(self.stat_world)
 
     def _colsum(self, t, n, f):
         st = self._new((2 * f,), torch.float32, t.device)
@@ -111,10 +131,12 @@ class TrainEngine:
                     gram = self._new((T + T * T,), torch.float64, dev)
                     call("ctk_first_patch_gram", ptr(x), c_int(n), c_int(c_total), c_int(br.c_offset), c_int(cin), c_int(h),
                          c_int(w), ptr(gram), stream())
+                    self._sync_stats(gram)
+                    count = float(n) * h * w * self.stat_world
                     mom = self._new((2 * cout,), torch.float32, dev)
-                    call("ctk_first_moments", ptr(gram), ptr(conv.weight), c_int(cout), c_int(cin), c_double(float(n) * h * w),
+                    call("ctk_first_moments", ptr(gram), ptr(conv.weight), c_int(cout), c_int(cin), c_double(count),
                          ptr(mom), stream())
-                    scale, shift, mean, invstd = self._bn_finalize(mom, float(n) * h * w, conv.bias, bn, dev, moments=True)
+                    scale, shift, mean, invstd = self._bn_finalize(mom, count, conv.bias, bn, dev, moments=True)
                     wfold = self._new((cout, T), torch.float32, dev)
                     call("ctk_pack_first_weight", ptr(conv.weight), ptr(scale), c_int(cout), c_int(cin), ptr(wfold), stream())
                     codes = self._new((n, h // 2, w // 2, cout // 8), torch.int32, dev)
@@ -137,7 +159,8 @@ class TrainEngine:
                     call("ctk_pack_conv_weight_bf16", ptr(conv.weight), c_int(cout), c_int(cin), ptr(wp), stream())
                     call("ctk_conv3x3_tc_raw", ptr(cur), c_int(n), c_int(h), c_int(w), c_int(cin), ptr(wp), c_int(cout),
                          ptr(y), ptr(stats), stream(), meta={"flops": 2.0 * n * h * w * cout * 9 * cin})
-                scale, shift, mean, invstd = self._bn_finalize(stats, float(n) * h * w, conv.bias, bn, dev)
+                self._sync_stats(stats)
+                scale, shift, mean, invstd = self._bn_finalize(stats, float(n) * h * w * self.stat_world, conv.bias, bn, dev)
                 call("ctk_bn_act_pool_fwd", ptr(y), c_int(n), c_int(h), c_int(w), c_int(cout), ptr(scale), ptr(shift),
                      c_float(LEAKY_SLOPE), ptr(dst), c_int(cstride), c_int(coff), stream())
                 blocks.append({"y": y, "x_in": cur, "pooled": (dst, cstride, coff), "scale": scale, "shift": shift, "mean": mean, "invstd": invstd,
@@ -164,7 +187,8 @@ class TrainEngine:
         st1 = self._new((2 * f1,), torch.float32, dev)
         call("ctk_colstat", ptr(partial), c_int(splits), c_longlong(m_pad * f1), c_int(f1), ptr(fc1.bias), c_int(n), c_int(f1),
              ptr(z1), ptr(st1), stream())
-        bn1 = self._bn_finalize(st1, float(n), None, self.bns[0], dev)
+        self._sync_stats(st1)
+        bn1 = self._bn_finalize(st1, float(n) * self.stat_world, None, self.bns[0], dev)
         masks = self._masks(n, f1, f2, dev)
         a1 = self._new((n, f1), torch.float32, dev)
         call("ctk_bn1d_act_drop_fwd", ptr(z1), ptr(bn1[0]), ptr(bn1[1]), ptr(masks[0]), c_float(self.drop_p[0]),
@@ -175,7 +199,8 @@ class TrainEngine:
         st2 = self._new((2 * f2,), torch.float32, dev)
         call("ctk_colstat", ptr(z2), c_int(1), c_longlong(0), c_int(f2), ptr(None), c_int(n), c_int(f2), ptr(None), ptr(st2),
              stream())
-        bn2 = self._bn_finalize(st2, float(n), None, self.bns[1], dev)
+        self._sync_stats(st2)
+        bn2 = self._bn_finalize(st2, float(n) * self.stat_world, None, self.bns[1], dev)
         a2 = self._new((n, f2), torch.float32, dev)
         call("ctk_bn1d_act_drop_fwd", ptr(z2), ptr(bn2[0]), ptr(bn2[1]), ptr(masks[1]), c_float(self.drop_p[1]),
              c_float(LEAKY_SLOPE), c_int(n), c_int(f2), ptr(a2), stream())
@@ -239,8 +264,8 @@ class TrainEngine:
         done(self.bns[1].bias, sums2[:f2])
         done(self.bns[1].weight, sums2[f2:])
         dz2 = self._new((n, f2), torch.float32, dev)
-        call("ctk_bn1d_bwd_apply", ptr(dact2), ptr(sv["z2"]), ptr(sc2), ptr(mu2), ptr(is2), ptr(sums2), c_int(n), c_int(f2),
-             ptr(dz2), ptr(None), ptr(None), c_int(0), stream())
+        call("ctk_bn1d_bwd_apply", ptr(dact2), ptr(sv["z2"]), ptr(sc2), ptr(mu2), ptr(is2), ptr(self._global_sums(sums2)),
+             c_int(n), c_int(f2), ptr(dz2), ptr(None), ptr(None), c_int(0), stream())
         dw2 = self._new((f2, f1), torch.float32, dev)
         call("ctk_sgemm_strided", ptr(dz2), c_longlong(1), c_longlong(f2), ptr(sv["a1"]), c_longlong(1), c_longlong(f1),
              ptr(None), c_int(f2), c_int(f1), c_int(n), ptr(dw2), c_int(f1), stream())
@@ -259,8 +284,8 @@ class TrainEngine:
         dz1 = self._new((n, f1), torch.float32, dev)
         dz1_bf = torch.zeros((m_pad, f1), device=dev, dtype=torch.bfloat16)
         dz1t_bf = torch.zeros((f1, k_pad), device=dev, dtype=torch.bfloat16)
-        call("ctk_bn1d_bwd_apply", ptr(dact1), ptr(sv["z1"]), ptr(sc1), ptr(mu1), ptr(is1), ptr(sums1), c_int(n), c_int(f1),
-             ptr(dz1), ptr(dz1_bf), ptr(dz1t_bf), c_int(k_pad), stream())
+        call("ctk_bn1d_bwd_apply", ptr(dact1), ptr(sv["z1"]), ptr(sc1), ptr(mu1), ptr(is1), ptr(self._global_sums(sums1)),
+             c_int(n), c_int(f1), ptr(dz1), ptr(dz1_bf), ptr(dz1t_bf), c_int(k_pad), stream())
         done(fc1.bias, self._colsum(dz1, n, f1))
         # ---- FC1: dW1 (reference column order) and dfeat (NHWC order)
         hf, wf = sv["hf"], sv["wf"]
@@ -299,8 +324,16 @@ class TrainEngine:
                     call("ctk_first_wgrad_codes", ptr(x), c_int(n), c_int(x.shape[1]), c_int(br.c_offset), c_int(cin), c_int(h),
                          c_int(w), ptr(b["codes"]), ptr(dp), c_int(cout), c_float(LEAKY_SLOPE), ptr(t1), ptr(sums), stream())
                     dw = self._new(tuple(conv.weight.shape), torch.float32, dev)
+                    # SyncBN: the saved Gram matrix is already the global one, so reduce t1 / sum(dA) too and form the
+                    # global gradient on every rank; dividing by the world size makes the exchange's mean leave it as is
+                    self._sync_stats(t1)
+                    self._sync_stats(sums)
                     call("ctk_first_wgrad_finalize", ptr(t1), ptr(b["gram"]), ptr(conv.weight), ptr(b["scale"]), ptr(b["mean"]),
-                         ptr(b["invstd"]), ptr(sums), c_double(float(n) * h * w), c_int(cout), c_int(cin), ptr(dw), stream())
+                         ptr(b["invstd"]), ptr(sums), c_double(float(n) * h * w * self.stat_world), c_int(cout), c_int(cin),
+                         ptr(dw), stream())
+                    if self.stat_world > 1:
+                        dw.div_(self.stat_world)
+                        sums.div_(self.stat_world)
                     done(bn.bias, sums[:cout])
                     done(bn.weight, sums[cout:])
                     done(conv.weight, dw)
@@ -314,7 +347,7 @@ class TrainEngine:
                 done(bn.weight, sums[cout:])
                 dy = self._new((n, h, w, cout), torch.bfloat16, dev)
                 call("ctk_bn_bwd_apply", ptr(b["y"]), ptr(dp), c_int(dp_cstride), c_int(dp_coff), c_int(n), c_int(h), c_int(w),
-                     c_int(cout), ptr(b["scale"]), ptr(b["shift"]), ptr(b["mean"]), ptr(b["invstd"]), ptr(sums),
+                     c_int(cout), ptr(b["scale"]), ptr(b["shift"]), ptr(b["mean"]), ptr(b["invstd"]), ptr(self._global_sums(sums)),
                      c_float(LEAKY_SLOPE), ptr(dy), stream())
                 b["y"] = None
                 dw = self._new(tuple(conv.weight.shape), torch.float32, dev)
