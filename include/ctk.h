@@ -53,6 +53,20 @@ int ctk_pearson_f32(const float* tiles, int n_tiles, int plane_elems, double* r_
                     void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Fused per-tile comparison metrics (the next metrics of the same host loop, test-cross-talk-model.py:59-79):
+ *   pearson_out[n]   f64  as ctk_pearson_f32                                                   (:59-64)
+ *   rmse_out[n]      f32  np.sqrt(np.mean((img0 - img1) ** 2))                                  (:79)
+ *   hist_out[n][2][256] u32  np.histogram(plane.flatten(), bins=256)[0] of both planes -- bit-exact counts (:65-66)
+ *   hist_corr_out[n] f64  pearsonr(hist0, hist1), NaN if either histogram is flat               (:67-70)
+ * Any output pointer may be NULL (hist_corr_out needs hist_out).  One read of the tiles from HBM plus one re-read
+ * (L2 resident) for the histograms.
+ * ------------------------------------------------------------------------------------------ */
+size_t ctk_tile_metrics_workspace_bytes(int n_tiles);
+int ctk_tile_metrics_f32(const float* tiles, int n_tiles, int plane_elems, double* pearson_out, float* rmse_out,
+                         double* hist_corr_out, unsigned int* hist_out, void* workspace, size_t workspace_bytes,
+                         void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Parameter re-packing (derived cache; redo after every optimizer step / load_state_dict).
  * ------------------------------------------------------------------------------------------ */
 /* Eval-mode BatchNorm folded with the conv/linear bias:  y = acc*scale + shift  where

@@ -385,6 +385,60 @@ def pearson_batch(x: torch.Tensor, f64: bool = True) -> np.ndarray:
 
 
 # --------------------------------------------------------------------------
+# RMSE and histogram correlation (test-cross-talk-model.py:65-70,79) -- SURVEY 8f row 1
+# --------------------------------------------------------------------------
+def rmse_f32(a: np.ndarray, b: np.ndarray) -> float:
+    """``np.sqrt(np.mean((img0 - img1) ** 2))`` on float32 planes (test-cross-talk-model.py:79)."""
+    a = np.asarray(a, dtype=np.float32)
+    b = np.asarray(b, dtype=np.float32)
+    return float(np.sqrt(np.mean((a - b) ** 2)))
+
+
+def histogram256_f32(a: np.ndarray) -> np.ndarray:
+    """``np.histogram(plane.flatten(), bins=256)[0]`` restated for a float32 plane (test-cross-talk-model.py:65-66).
+
+    NumPy >= 2 (numpy/lib/_histograms_impl.py, uniform-bin path) keeps everything in the array's dtype:
+    edges = float32(arange(257) * float32((max-min)/256) + min) with the last edge set to max; a first guess
+    ``int(((x - min) / (max - min)) * 256)`` (float32 ops, truncation), clamped from 256 to 255, is then corrected by at
+    most one bin against the float32 edges (left-closed bins, the last bin closed on both sides).  A constant plane uses
+    the range [v - 0.5, v + 0.5].  The CUDA kernel repeats exactly these float32 operations, so counts are bit-exact.
+    """
+    x = np.asarray(a, dtype=np.float32).ravel()
+    first, last = x.min(), x.max()
+    if first == last:
+        first, last = np.float32(first - np.float32(0.5)), np.float32(last + np.float32(0.5))
+    step = np.float32((last - first) / np.float32(256))
+    edges = (np.arange(257, dtype=np.float32) * step + first).astype(np.float32)
+    edges[-1] = last
+    denom = np.float32(last - first)
+    idx = (((x - first) / denom) * np.float32(256)).astype(np.int64)
+    idx[idx == 256] -= 1
+    idx[x < edges[idx]] -= 1
+    inc = (x >= edges[idx + 1]) & (idx != 255)
+    idx[inc] += 1
+    return np.bincount(idx, minlength=256).astype(np.int64)
+
+
+def hist_correlation(a: np.ndarray, b: np.ndarray) -> float:
+    """Pearson r of the two 256-bin histograms, NaN if either histogram is flat (test-cross-talk-model.py:65-70)."""
+    h1, h2 = histogram256_f32(a), histogram256_f32(b)
+    if np.std(h1) == 0 or np.std(h2) == 0:
+        return float("nan")
+    return pearson_f64(h1.astype(np.float64), h2.astype(np.float64))
+
+
+def tile_metrics_batch(x: torch.Tensor) -> Dict[str, np.ndarray]:
+    """Per-image Pearson r, RMSE and histogram correlation of channel 0 vs channel 1 of an [N,2,H,W] float32 batch."""
+    xs = x.detach().cpu().numpy()
+    n = xs.shape[0]
+    return {"pearson": np.array([pearson_f64(xs[i, 0], xs[i, 1]) for i in range(n)]),
+            "rmse": np.array([rmse_f32(xs[i, 0], xs[i, 1]) for i in range(n)]),
+            "hist_corr": np.array([hist_correlation(xs[i, 0], xs[i, 1]) for i in range(n)]),
+            "hist": np.stack([np.stack([histogram256_f32(xs[i, 0]), histogram256_f32(xs[i, 1])]) for i in range(n)])
+            if n else np.zeros((0, 2, 256), dtype=np.int64)}
+
+
+# --------------------------------------------------------------------------
 # inputs
 # --------------------------------------------------------------------------
 def normalize_image(img: np.ndarray) -> np.ndarray:

@@ -72,6 +72,46 @@ def test_pearson_affine_invariance_full_size(ctk):
 
 
 # ------------------------------------------------------------------ first conv block
+def test_tile_metrics_fused(ctk, golden):
+    """Pearson + RMSE + 256-bin histograms + histogram correlation in one fused pass against the oracle
+    restatement, the reference-call goldens, and np.histogram bit for bit -- on fixture tiles (normalised and raw),
+    synthetic tiles, a constant plane, flat histograms and a ragged plane size."""
+    import json
+    import os
+    tiles = torch.from_numpy(golden["tiles"].astype(np.float32))
+    xn = torch.stack([torch.stack([torch.from_numpy(orc.normalize_image(t[0].numpy())),
+                                   torch.from_numpy(orc.normalize_image(t[1].numpy()))]) for t in tiles])
+    xs, _ = orc.synthetic_batch(3, seed=5)
+    const = xs[:1].clone()
+    const[0, 1] = 0.25                                     # constant plane: Pearson NaN, histogram all in one bin
+    x = torch.cat([xn, tiles, xs, const], dim=0).contiguous()
+    got = ctk.tile_metrics(x.cuda())
+    ref = orc.tile_metrics_batch(x)
+    hist = got["hist"].cpu().numpy().astype(np.int64)
+    assert np.array_equal(hist, ref["hist"])                                              # integer work: bit-exact
+    for i in range(x.shape[0]):
+        for c in range(2):
+            assert np.array_equal(hist[i, c], np.histogram(x[i, c].numpy().flatten(), bins=256)[0])
+    np.testing.assert_allclose(got["pearson"].cpu().numpy(), ref["pearson"], atol=1e-9, equal_nan=True)
+    np.testing.assert_allclose(got["hist_corr"].cpu().numpy(), ref["hist_corr"], atol=1e-12, equal_nan=True)
+    np.testing.assert_allclose(got["rmse"].cpu().numpy(), ref["rmse"], rtol=2e-6)          # fp32 pairwise mean vs fp64 sum
+    assert np.isnan(got["pearson"][-1].item()) and not np.isnan(got["hist_corr"][-1].item())
+    m = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "metrics.json")))
+    np.testing.assert_allclose(got["hist_corr"][:5].cpu().numpy(), m["normalised"]["hist_corr"], atol=1e-12)
+    np.testing.assert_allclose(got["hist_corr"][5:10].cpu().numpy(), m["raw"]["hist_corr"], atol=1e-12)
+    np.testing.assert_allclose(got["rmse"][:5].cpu().numpy(), m["normalised"]["rmse"], rtol=2e-6)
+    # flat histograms (every bin hit equally often) -> NaN like np.std(hist) == 0; ragged plane (48 x 40)
+    ramp = (torch.arange(256, dtype=torch.float32) / 255).repeat(8).reshape(1, 1, 32, 64).repeat(1, 2, 1, 1).contiguous()
+    assert np.isnan(ctk.tile_metrics(ramp.cuda())["hist_corr"].item()) and np.isnan(orc.hist_correlation(ramp[0, 0].numpy(), ramp[0, 1].numpy()))
+    rag = torch.rand(2, 2, 48, 40)
+    g2, r2 = ctk.tile_metrics(rag.cuda()), orc.tile_metrics_batch(rag)
+    assert np.array_equal(g2["hist"].cpu().numpy().astype(np.int64), r2["hist"])
+    np.testing.assert_allclose(g2["hist_corr"].cpu().numpy(), r2["hist_corr"], atol=1e-12)
+    assert ctk.tile_metrics(torch.empty(0, 2, 32, 32).cuda())["pearson"].numel() == 0
+    # same Pearson as the stand-alone kernel
+    np.testing.assert_allclose(got["pearson"].cpu().numpy(), ctk.pearson_per_image(x.cuda()).cpu().numpy(), atol=1e-12, equal_nan=True)
+
+
 @pytest.mark.parametrize("cin,cout,c_off", [(1, 64, 0), (1, 64, 1), (2, 128, 0)])
 def test_conv_first_eval(ctk, cin, cout, c_off):
     from ctk._lib import call, ptr, stream

@@ -94,3 +94,29 @@ def test_adam_step_matches_torch_optim():
         opt.step()
         orc.adam_step(p, g * t, m, v, t, 5e-4)
     np.testing.assert_allclose(p.numpy(), p_ref.detach().numpy(), rtol=0, atol=1e-7)
+
+
+def test_metrics_restatement_matches_reference_calls(golden):
+    """RMSE / 256-bin histogram / histogram correlation restatements against the reference's own numpy + scipy calls
+    (tests/golden/metrics.json, written by make_metrics_golden.py with the expressions of test-cross-talk-model.py:65-79)
+    and against np.histogram directly on awkward inputs."""
+    import json
+    import os
+    m = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "metrics.json")))
+    tiles = golden["tiles"].astype(np.float32)
+    xn = np.stack([np.stack([orc.normalize_image(t[0]), orc.normalize_image(t[1])]) for t in tiles])
+    for name, imgs in (("normalised", xn), ("raw", tiles)):
+        g = m[name]
+        for j in range(imgs.shape[0]):
+            h0, h1 = orc.histogram256_f32(imgs[j, 0]), orc.histogram256_f32(imgs[j, 1])
+            assert [int(v) for v in h0[:16]] == g["hist0_head"][j] and [int(v) for v in h1[:16]] == g["hist1_head"][j]
+            assert int((h0 ** 2).sum()) == g["hist0_sum_sq"][j] and int((h1 ** 2).sum()) == g["hist1_sum_sq"][j]
+            assert abs(orc.hist_correlation(imgs[j, 0], imgs[j, 1]) - g["hist_corr"][j]) <= 1e-12
+            assert abs(orc.rmse_f32(imgs[j, 0], imgs[j, 1]) - g["rmse"][j]) <= 1e-7 * g["rmse"][j]
+    rng = np.random.default_rng(0)
+    awkward = [np.full(4096, 0.3, np.float32), (rng.standard_normal(65536) * 1e-3 + 5).astype(np.float32),
+               (rng.random(65536) ** 3 * 7 - 2).astype(np.float32), np.arange(257, dtype=np.float32) / 256,
+               np.array([0, 1, 1, 1, 0.5, 0.00390625, 0.99609375] * 8, np.float32)]
+    for a in awkward:
+        assert np.array_equal(orc.histogram256_f32(a), np.histogram(a, bins=256)[0])
+    assert np.isnan(orc.hist_correlation(np.arange(256, dtype=np.float32), np.arange(256, dtype=np.float32)))   # flat histograms

@@ -61,8 +61,10 @@ struct Cfg {
   static constexpr int kBRows = kBlockN / kCtaGroup;          // weight rows this CTA loads per (chunk, tap)
   static constexpr int kBStageBytes = kBRows * 128;
   static constexpr int kExtra = kEpi == kEpiRawStats ? kScratchBytes : 0;
+  // ring of weight stages; when the whole layer's share (chunks x 9 stages) fits, the weights are loaded ONCE and stay
+  // resident (b_resident): 64-channel layers otherwise re-stream 74 KB per tile per CTA from L2 and stall on it
   static constexpr int kBStages =
-      std::min(12, (227 * 1024 - 1024 - kCtrlBytes - kExtra - kAStages * kAStageBytes) / kBStageBytes);
+      std::min(18, (227 * 1024 - 1024 - kCtrlBytes - kExtra - kAStages * kAStageBytes) / kBStageBytes);
   static constexpr int kTmemCols = kAccStages * kBlockN;
   static constexpr int kSmemBytes = 1024 + kAStages * kAStageBytes + kBStages * kBStageBytes + kCtrlBytes + kExtra;
 };
@@ -79,6 +81,7 @@ struct ConvParams {
   __nv_bfloat16* out;
   __nv_bfloat16* out_lo;   // kEpiEvalPoolSplit: low halves, same pixel / channel addressing as `out`
   int out_cstride, out_coffset;
+  int b_resident;       // chunks * 9 <= kBStages: every (chunk, tap) weight stage is loaded once and never recycled
   int cin_phys;         // channels of the activation tensor in memory (= cin, or 2/3 cin for the split layout)
   int a_wrap;           // split layout: K chunk c >= a_wrap re-reads physical chunk c - a_wrap ([hi | lo | hi] from [hi | lo])
 };
@@ -360,7 +363,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       const TileCoord t = decode_work<kCtaGroup, kBlockN>(p, work, rank);
       for (int c = 0; c < chunks; ++c) {
         for (int tap = 0; tap < 9; ++tap) {
-          mbar_wait(&sl->b_empty[stage], phase ^ 1);
+          if (!p.b_resident) mbar_wait(&sl->b_empty[stage], phase ^ 1);
           uint8_t* dst = b_smem + stage * C::kBStageBytes;
           const int row = tap * p.cout + t.n0 + rank * C::kBRows;
           if (elect_one()) {
@@ -376,6 +379,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
           if (++stage == C::kBStages) { stage = 0; phase ^= 1; }
         }
       }
+      if (p.b_resident) break;      // resident weights (one N tile): loaded with the first work item, reused by all
     }
   } else if (warp == 1 && rank == 0) {
     // ---------------- MMA issuer (pair leader only)
@@ -397,8 +401,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         tc_fence_after();
         const uint32_t a_base = smem_u32(a_smem + as * kAStageBytes);
         for (int tap = 0; tap < 9; ++tap) {
-          mbar_wait(&sl->b_full[bs], bphase);
-          tc_fence_after();
+          if (p.b_resident) bs = c * 9 + tap;
+          if (!p.b_resident || it == 0) {
+            mbar_wait(&sl->b_full[bs], bphase);
+            tc_fence_after();
+          }
           const int ky = tap / 3, kx = tap - 3 * ky;
           // The 128B swizzle is a function of the absolute shared-memory address bits (verified on B200:
           // base-offset field 0, any 128-byte-aligned start, any multiple-of-128 group stride), so a shifted
@@ -417,17 +424,17 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
               else umma_bf16_pair(d_tmem, adesc + 2 * s, bdesc + 2 * s, idesc, accum);
             }
             if constexpr (kCtaGroup == 1) {
-              umma_commit(&sl->b_empty[bs]);
+              if (!p.b_resident) umma_commit(&sl->b_empty[bs]);
               if (last_tap) umma_commit(&sl->a_empty[as]);
               if (last_tap && c == chunks - 1) umma_commit(&sl->acc_full[acc]);
             } else {
-              umma_commit_pair(&sl->b_empty[bs]);
+              if (!p.b_resident) umma_commit_pair(&sl->b_empty[bs]);
               if (last_tap) umma_commit_pair(&sl->a_empty[as]);
               if (last_tap && c == chunks - 1) umma_commit_pair(&sl->acc_full[acc]);
             }
           }
           __syncwarp();
-          if (++bs == C::kBStages) { bs = 0; bphase ^= 1; }
+          if (!p.b_resident && ++bs == C::kBStages) { bs = 0; bphase ^= 1; }
         }
         if (++as == kAStages) { as = 0; aphase ^= 1; }
       }
@@ -513,6 +520,7 @@ int launch_conv(const void* x_bf16, const void* w_packed_bf16, ConvParams p, cud
   p.div_n = make_fastdiv(static_cast<uint32_t>(p.tiles_n));
   p.div_x = make_fastdiv(static_cast<uint32_t>(p.tiles_x));
   p.div_y = make_fastdiv(static_cast<uint32_t>(p.tiles_y));
+  p.b_resident = (p.tiles_n == 1 && (p.cin / kKC) * 9 <= C::kBStages) ? 1 : 0;
   const long long work = static_cast<long long>((p.spatial_tiles + kCtaGroup - 1) / kCtaGroup) * p.tiles_n;
   if (work >= (1ll << 31)) return CTK_ERR_BAD_ARG;
   p.total_work = static_cast<int>(work);

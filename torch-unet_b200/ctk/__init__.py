@@ -7,13 +7,13 @@ Everything here drives hand-written sm_100a kernels in libctk.so through the C A
 """
 from ._lib import CtkError, EXPORTED_SYMBOLS, LIB_PATH, load
 from .engine import InferenceEngine
-from .metrics import pearson_per_image
+from .metrics import pearson_per_image, tile_metrics
 from .models import (AdvancedRegressionModel, SimplifiedFeatureExtractionBranch, SimplifiedRegressionHead,
                      SimplifiedTwoBranchRegressionModel, accelerate, set_precision)
 from .optim import Adam, mse_loss
 from .pipeline import HostScorer
 from . import parallel
 
-__all__ = ["CtkError", "EXPORTED_SYMBOLS", "LIB_PATH", "load", "InferenceEngine", "pearson_per_image",
+__all__ = ["CtkError", "EXPORTED_SYMBOLS", "LIB_PATH", "load", "InferenceEngine", "pearson_per_image", "tile_metrics",
            "AdvancedRegressionModel", "SimplifiedFeatureExtractionBranch", "SimplifiedRegressionHead",
            "SimplifiedTwoBranchRegressionModel", "accelerate", "set_precision", "Adam", "mse_loss", "HostScorer", "parallel"]

@@ -33,3 +33,29 @@ def pearson_per_image(inputs: torch.Tensor, out: torch.Tensor = None) -> torch.T
     ws = torch.empty(ws_bytes // 8, device=inputs.device, dtype=torch.float64)
     call("ctk_pearson_f32", ptr(inputs), c_int(n), c_int(plane), ptr(out), ptr(ws), c_size_t(ws_bytes), stream())
     return out
+
+
+def tile_metrics(inputs: torch.Tensor, histograms: bool = True) -> dict:
+    """Pearson r, RMSE and 256-bin histogram correlation of channel 0 vs channel 1 for every tile of ``inputs``
+    ([N,2,H,W] float32, CUDA) in one fused pass -- test-cross-talk-model.py:59-70,79 without the device->host copy of the
+    inputs (:52).  Returns {"pearson": f64[N], "rmse": f32[N], "hist_corr": f64[N], "hist": i32[N,2,256]} on the device
+    (the last two only with ``histograms=True``); histogram counts equal ``np.histogram(plane, bins=256)[0]`` exactly.
+    """
+    _lib.require_device(inputs, torch.float32, "inputs")
+    if inputs.dim() != 4 or inputs.shape[1] != 2:
+        raise _lib.CtkError(f"inputs must be [N,2,H,W], got {tuple(inputs.shape)}")
+    n = inputs.shape[0]
+    plane = inputs.shape[2] * inputs.shape[3]
+    dev = inputs.device
+    out = {"pearson": torch.empty(n, device=dev, dtype=torch.float64), "rmse": torch.empty(n, device=dev, dtype=torch.float32)}
+    if histograms:
+        out["hist_corr"] = torch.empty(n, device=dev, dtype=torch.float64)
+        out["hist"] = torch.empty(n, 2, 256, device=dev, dtype=torch.int32)
+    if n == 0:
+        return out
+    lib = _lib.load()
+    ws_bytes = lib.ctk_tile_metrics_workspace_bytes(c_int(n))
+    ws = torch.empty((ws_bytes + 7) // 8, device=dev, dtype=torch.float64)
+    call("ctk_tile_metrics_f32", ptr(inputs), c_int(n), c_int(plane), ptr(out["pearson"]), ptr(out["rmse"]),
+         ptr(out.get("hist_corr")), ptr(out.get("hist")), ptr(ws), c_size_t(ws_bytes), stream())
+    return out
