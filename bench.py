@@ -136,9 +136,10 @@ def cpu_train_rate(kind, n_tiles, steps, warmup):
     return n_tiles / sec, sec, torch.get_num_threads()
 
 
-def run_train(args):
+def run_train(args, shared_pg=False):
     """Training throughput: zero_grad -> forward -> MSELoss -> backward -> Adam.step -> loss.item() (train_model.py:419-426),
-    per-GPU batch fixed (weak scaling), gradients averaged across ranks by the bucketed NCCL all-reduce."""
+    per-GPU batch fixed (weak scaling), gradients averaged across ranks by the bucketed NCCL all-reduce.
+    Prints its own JSON line (--mode train) or, with shared_pg=True, returns it for the "train" key of the default line."""
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -164,16 +165,16 @@ def run_train(args):
         raise SystemExit("bench.py needs a CUDA device: the ctk hot path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
+    if world > 1 and not shared_pg:
         dist.init_process_group("nccl", device_id=dev)
-    steps, warmup = args.steps, max(3, args.warmup)
+    steps, warmup = (min(args.steps, 10), 3) if shared_pg else (args.steps, max(3, args.warmup))
     torch.manual_seed(0)
     model = (ctk.SimplifiedTwoBranchRegressionModel(initial_filters_per_branch=64) if kind == "double"
              else ctk.AdvancedRegressionModel(initial_filters=128, num_conv_blocks=6)).to(dev).train()
     sync = None
     if world > 1:
         ctk.parallel.broadcast_parameters(model)
-        sync = ctk.parallel.attach(model)
+        sync = ctk.parallel.attach(model, sync_bn=args.sync_bn)
     opt = ctk.Adam(model.parameters(), lr=5e-4, weight_decay=1e-4)
     crit = torch.nn.MSELoss()
     base_x, base_y = orc.synthetic_batch(32, seed=1234 + rank)
@@ -205,6 +206,7 @@ def run_train(args):
     timeline = _lib.start_timeline()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    last = float("nan")
     for i in range(steps):
         last = step(*devb[i % 2]).item()            # loss.item() every step, like train_model.py:426
     e1.record()
@@ -246,7 +248,8 @@ def run_train(args):
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": f"{kind}-branch training step (fwd + MSE + bwd + Adam lr 5e-4 wd 1e-4), batch {batch} per GPU",
                            "per_gpu_batch": batch, "global_batch": batch * world,
-                           "parallelism": f"dp{world}: bucketed NCCL all-reduce (AVG) overlapped with backward" if world > 1 else "single GPU",
+                           "parallelism": (f"dp{world}: bucketed NCCL all-reduce (AVG) overlapped with backward"
+                                           + (", SyncBN" if args.sync_bn else ", per-rank BatchNorm statistics")) if world > 1 else "single GPU",
                            "l2_policy": "inputs larger than L2 (134 MB per batch), 2 distinct batches rotated"},
                 "whole_net_tflops": world * batch * steps / (ms / 1e3) * gflop_img / 1e3,
                 "roofline": {"kernel": "conv3x3_tc_kernel (fwd+dgrad) + wgrad_tc_kernel", "bound": "tensor", "achieved": tf,
@@ -254,8 +257,8 @@ def run_train(args):
                              "peak_source": pk["src"] + " (sustained cuBLAS bf16)",
                              "share_of_step": tc_ms / ms if ms > 0 else None,
                              "per_call_ms_per_step": {k: round(v["ms"] / steps, 4) for k, v in sorted(per.items())},
-                             "per_call_tflops": {k: (v["flops"] / (v["ms"] / 1e3) / 1e12 if v["ms"] > 0 and v["flops"] > 0 else None)
-                                                 for k, v in sorted(per.items())}},
+                             "per_call_tflops": {k: round(v["flops"] / (v["ms"] / 1e3) / 1e12, 1)
+                                                 for k, v in sorted(per.items()) if v["ms"] > 0 and v["flops"] > 0}},
                 "clocks": clocks, "gpu_launches": launches, "last_loss": last,
                 "e2e": {"value": world * batch * e2e_steps / (e2e_ms / 1e3), "unit": "images/sec",
                         "h2d_bytes_per_step": batch * (2 * 256 * 256 + 1) * 4, "d2h_bytes_per_step": 4, "steps": e2e_steps,
@@ -267,9 +270,14 @@ def run_train(args):
             rate, sec, cores = cpu_train_rate(kind, 8, 2, 1)
             line["cpu_baseline"] = {"value": rate, "unit": "images/sec", "cores": cores, "kind": "port",
                                     "sample": "8-tile batches, fwd+MSE+bwd+Adam, oracle port (same ATen CPU ops as the reference), fp32"}
+        if shared_pg:
+            return line
         print(json.dumps(line), flush=True)
-    if world > 1:
+    del model, opt, devb
+    torch.cuda.empty_cache()
+    if world > 1 and not shared_pg:
         dist.destroy_process_group()
+    return None
 
 
 def main():
@@ -279,6 +287,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ctk", choices=["ctk", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="default mode: skip the attached training measurement")
+    ap.add_argument("--sync-bn", action="store_true", help="train mode, N > 1: BatchNorm statistics over the global batch")
     ap.add_argument("--mode", default="infer", choices=["infer", "train"],
                     help="infer = BASELINE configs[1] (default, the headline line); train = configs[2]/[3] training step")
     ap.add_argument("--model", default="double", choices=["double", "single"])
@@ -412,6 +422,21 @@ def main():
             line["cpu_baseline"] = {"value": rate, "unit": "images/sec", "cores": cores, "kind": "port",
                                     "sample": "16 of the 256 tiles of one step (pearson loop + double-branch eval forward), "
                                               "oracle port = the same ATen CPU ops the reference modules call, fp32"}
+    # the metric is "train & infer images/sec": the double-branch training step (BASELINE configs[2]/[3] shape, batch 256 per
+    # GPU) is measured in the same run and attached under "train" (its own value / e2e / roofline / clocks)
+    train_line = None
+    if not args.no_train:
+        del model, engine, dev_batches, scorer
+        torch.cuda.empty_cache()
+        targs = argparse.Namespace(**vars(args))
+        targs.no_cpu_baseline = True
+        train_line = run_train(targs, shared_pg=True)
+    if rank == 0:
+        if train_line is not None:
+            line["train"] = {k: train_line[k] for k in ("metric", "value", "unit", "steps", "warmup", "ms_per_step", "config",
+                                                        "whole_net_tflops", "roofline", "clocks", "gpu_launches", "e2e")}
+            if "allreduce" in train_line:
+                line["train"]["allreduce"] = train_line["allreduce"]
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -164,6 +164,17 @@ int ctk_conv3x3_tc_eval_split(const void* x_split_bf16, int n, int H, int W, int
                               void* out_lo_bf16, int out_cstride, int out_coffset, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Input pipeline on the device (the caller side of the path):
+ *   raw pixel payloads [n][2][H*W] (float64 as the reference's TIFFs store them, or float32) ->
+ *   astype(float32) -> per-plane (img - min) / (max - min), constant planes unchanged -> optional flips -> out [n,2,H,W] f32
+ * Replaces: train_model.py:166-167 (imread(...).astype(np.float32)), :211-216 (normalize_image), :225-232 (TF.hflip /
+ * TF.vflip on both planes).  flip_flags: NULL or [n] bytes, bit 0 = horizontal flip, bit 1 = vertical flip (the caller
+ * draws them: `torch.rand(1) < 0.5` twice per sample in the reference).  Bit-identical to the NumPy float32 arithmetic.
+ * ------------------------------------------------------------------------------------------ */
+int ctk_prepare_tiles(const void* raw, int raw_is_f64, const unsigned char* flip_flags, int n, int H, int W, float* out,
+                      void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * MSE loss (mean reduction) and its gradient.  Replaces: torch.nn.MSELoss(), train_model.py:636,421.
  * loss_out: [1] fp32; grad_out (may be NULL): [n] fp32 = 2*(out-target)/n.
  * ------------------------------------------------------------------------------------------ */

@@ -449,6 +449,23 @@ def normalize_image(img: np.ndarray) -> np.ndarray:
     return img
 
 
+def prepare_tiles(raw: np.ndarray, flips: Optional[np.ndarray] = None) -> np.ndarray:
+    """The reference's per-sample input path restated over a batch: raw [N,2,H,W] (float64 as stored in the TIFFs, or
+    float32) -> ``.astype(np.float32)`` (train_model.py:166-167) -> normalize_image per plane (:211-216) -> hflip if
+    ``flips[i] & 1``, vflip if ``flips[i] & 2`` on both planes (TF.hflip / TF.vflip, :225-232)."""
+    x = np.asarray(raw).astype(np.float32)
+    out = np.empty_like(x)
+    for i in range(x.shape[0]):
+        for c in range(2):
+            p = normalize_image(x[i, c])
+            if flips is not None and flips[i] & 1:
+                p = p[:, ::-1]
+            if flips is not None and flips[i] & 2:
+                p = p[::-1, :]
+            out[i, c] = p
+    return out
+
+
 def synthetic_batch(n: int, seed: int = 1234, size: int = 256) -> Tuple[torch.Tensor, torch.Tensor]:
     """SURVEY 8d generator: U[0,1) source plane, ch0 = normalise(alpha*src + (1-alpha)*noise), labels alpha."""
     g = torch.Generator().manual_seed(seed)

@@ -72,6 +72,32 @@ def test_pearson_affine_invariance_full_size(ctk):
 
 
 # ------------------------------------------------------------------ first conv block
+def test_prepare_tiles_bit_exact(ctk, golden):
+    """Device input pipeline (float64 / float32 payload -> cast -> per-plane min-max normalise -> flips) against the
+    oracle restatement of train_model.py:166-167, 211-232: float32 arithmetic, so equality is exact.  Covers the
+    256 x 256 cluster kernel, the generic kernel (ragged 40 x 24), constant planes, all four flip states, empty batches."""
+    rng = np.random.default_rng(1)
+    tiles = golden["tiles"].astype(np.float64)
+    synth = rng.random((4, 2, 256, 256)) * 3.7 - 1.2
+    synth[1, 0] = 0.625                                                    # constant plane: left unchanged
+    raw = np.concatenate([tiles, synth], axis=0)
+    flips = np.array([0, 1, 2, 3, 0, 3, 1, 2, 0], dtype=np.uint8)
+    for dtype in (np.float64, np.float32):
+        r = raw.astype(dtype)
+        ref = orc.prepare_tiles(r, flips)
+        got = ctk.prepare_tiles(torch.from_numpy(r).cuda(), torch.from_numpy(flips).cuda()).cpu().numpy()
+        assert np.array_equal(got, ref)
+        got0 = ctk.prepare_tiles(torch.from_numpy(r).cuda()).cpu().numpy()
+        assert np.array_equal(got0, orc.prepare_tiles(r))
+    small = rng.random((3, 2, 40, 24))
+    fl = np.array([3, 0, 1], dtype=np.uint8)
+    assert np.array_equal(ctk.prepare_tiles(torch.from_numpy(small).cuda(), torch.from_numpy(fl).cuda()).cpu().numpy(),
+                          orc.prepare_tiles(small, fl))
+    assert ctk.prepare_tiles(torch.empty(0, 2, 256, 256, dtype=torch.float64).cuda()).shape == (0, 2, 256, 256)
+    with pytest.raises(ctk.CtkError):
+        ctk.prepare_tiles(torch.zeros(1, 2, 8, 8, dtype=torch.float64))      # host tensor: no CPU fallback
+
+
 def test_tile_metrics_fused(ctk, golden):
     """Pearson + RMSE + 256-bin histograms + histogram correlation in one fused pass against the oracle
     restatement, the reference-call goldens, and np.histogram bit for bit -- on fixture tiles (normalised and raw),

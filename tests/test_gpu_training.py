@@ -209,3 +209,50 @@ def test_200_step_loss_curve_against_reference_golden():
     print("mean loss over the last 100 steps: reference %.5f gpu %.5f" % (tail_ref, tail_gpu))
     assert abs(tail_gpu - tail_ref) / tail_ref <= 0.25
     assert gpu[steps // 2:].mean() < 0.5 * gpu[:10].mean()     # and it trained
+
+
+def test_lr_schedulers_and_checkpoint_resume_drive_ctk_adam():
+    """the reference's schedulers (train_model.py:376-387: ReduceLROnPlateau / OneCycleLR, which also
+    cycles beta1) are torch objects acting on ``optimizer.param_groups``; ctk.Adam is a torch Optimizer, so they must
+    drive it exactly like torch.optim.Adam, and optimizer + scheduler state must survive a state_dict round trip."""
+    import ctk
+    torch.manual_seed(0)
+    shapes = [(300, 17), (64,), (5, 3, 3, 3)]
+    p0 = [torch.randn(s) for s in shapes]
+    grads = [[torch.randn(s) for s in shapes] for _ in range(12)]
+
+    def run(make_opt, device, resume_at=None):
+        params = [torch.nn.Parameter(p.clone().to(device)) for p in p0]
+        opt = make_opt(params)
+        sched = torch.optim.lr_scheduler.OneCycleLR(opt, max_lr=1e-3, pct_start=0.3, anneal_strategy="cos", div_factor=25.0,
+                                                    final_div_factor=1e4, epochs=3, steps_per_epoch=4)
+        lrs = []
+        for t, gs in enumerate(grads):
+            if resume_at is not None and t == resume_at:                   # checkpoint -> fresh objects -> resume
+                osd, ssd = opt.state_dict(), sched.state_dict()
+                opt = make_opt(params)
+                sched = torch.optim.lr_scheduler.OneCycleLR(opt, max_lr=1e-3, pct_start=0.3, anneal_strategy="cos",
+                                                            div_factor=25.0, final_div_factor=1e4, epochs=3, steps_per_epoch=4)
+                opt.load_state_dict(osd)
+                sched.load_state_dict(ssd)
+            for p, g in zip(params, gs):
+                p.grad = g.clone().to(device)
+            opt.step()
+            sched.step()
+            lrs.append(opt.param_groups[0]["lr"])
+        return [p.detach().cpu() for p in params], lrs
+
+    ref, lr_ref = run(lambda ps: torch.optim.Adam(ps, lr=5e-4, weight_decay=1e-4), "cpu")
+    got, lr_got = run(lambda ps: ctk.Adam(ps, lr=5e-4, weight_decay=1e-4), "cuda")
+    res, lr_res = run(lambda ps: ctk.Adam(ps, lr=5e-4, weight_decay=1e-4), "cuda", resume_at=5)
+    assert lr_got == lr_ref and lr_res == lr_ref
+    for a, b, c in zip(ref, got, res):
+        assert torch.allclose(a, b, rtol=2e-5, atol=2e-7)
+        assert torch.equal(b, c)                                           # resume is bit-identical to the uninterrupted run
+    # ReduceLROnPlateau lowers ctk.Adam's lr exactly like torch's
+    prm = [torch.nn.Parameter(torch.zeros(4, device="cuda"))]
+    opt = ctk.Adam(prm, lr=5e-4, weight_decay=1e-4)
+    plateau = torch.optim.lr_scheduler.ReduceLROnPlateau(opt, factor=0.3, patience=3, threshold=5e-5, min_lr=1e-8)
+    for _ in range(6):
+        plateau.step(1.0)
+    assert abs(opt.param_groups[0]["lr"] - 5e-4 * 0.3) < 1e-12

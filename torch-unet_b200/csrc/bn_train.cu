@@ -417,8 +417,10 @@ int ctk_bn_bwd_reduce_pooled(const void* pooled_bf16, int p_cstride, int p_coffs
   cudaStream_t s = ctk::as_stream(stream);
   CTK_CUDA_TRY(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * channels, s));
   const int slots = 256 / (channels / 8);
-  const long long blocks = (pooled_pixels + slots - 1) / slots;
-  const int grid = static_cast<int>(blocks < ctk::num_sms() * 8 ? blocks : ctk::num_sms() * 8);
+  // every CTA ends with 2 * channels global atomics on the same addresses: few, long-running CTAs (>= 64 pixels per slot)
+  const long long blocks = (pooled_pixels + static_cast<long long>(slots) * 64 - 1) / (static_cast<long long>(slots) * 64);
+  const long long cap = static_cast<long long>(ctk::num_sms()) * 3;
+  const int grid = static_cast<int>(blocks < 1 ? 1 : (blocks < cap ? blocks : cap));
   bn_bwd_reduce_pooled_kernel<<<grid, 256, 256 * 16 * sizeof(float), s>>>(
       static_cast<const __nv_bfloat16*>(pooled_bf16), p_cstride, p_coffset, static_cast<const __nv_bfloat16*>(dp_bf16),
       dp_cstride, dp_coffset, channels / 8, gamma, beta, slope, sums, pooled_pixels);

@@ -13,22 +13,27 @@ namespace {
 using namespace ctk;
 
 constexpr int kBM = 128, kBN = 128, kBK = 64;
-constexpr int kStages = 6;
 constexpr int kThreads = 192;                         // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2-5 epilogue
 constexpr int kStageBytes = (kBM + kBN) * kBK * 2;    // 32 KiB
-constexpr int kSmemBytes = 1024 + kStages * kStageBytes + 256;
+// kStages = 6: long K ranges (FC1 forward), one CTA per SM.  kStages = 2: the FC1 backward GEMMs have K = 256 / 512 and
+// thousands of output tiles, so a CTA is mostly prologue + epilogue; 66 KB of shared memory lets three of them share an SM
+// and overlap each other's TMEM allocation, pipeline fill and 64 KB fp32 tile store.
+template <int kStages>
+constexpr int smem_bytes() { return 1024 + kStages * kStageBytes + 256; }
 
+template <int kStages>
 struct GemmSmem {
   uint64_t full[kStages], empty[kStages], acc_full;
   uint32_t tmem_base;
 };
 
-__global__ void __launch_bounds__(kThreads, 1)
+template <int kStages>
+__global__ void __launch_bounds__(kThreads, kStages <= 2 ? 3 : 1)
 gemm_splitk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, int M, int N,
                    int k_per_split, float* __restrict__ partial, __nv_bfloat16* __restrict__ out_bf16) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  GemmSmem* sl = reinterpret_cast<GemmSmem*>(smem + kStages * kStageBytes);
+  GemmSmem<kStages>* sl = reinterpret_cast<GemmSmem<kStages>*>(smem + kStages * kStageBytes);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * kBM, n0 = blockIdx.y * kBN, split = blockIdx.z;
   const int k_begin = split * k_per_split;
@@ -133,10 +138,16 @@ static int gemm_launch(const void* a_bf16, const void* b_bf16, int M, int N, int
     int st = ctk::encode_tmap_bf16_sw128(&tm_b, b_bf16, 2, dims, strides, box);
     if (st != CTK_OK) return st;
   }
-  CTK_CUDA_TRY(cudaFuncSetAttribute(gemm_splitk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   dim3 grid(M / kBM, N / kBN, splits);
-  gemm_splitk_kernel<<<grid, kThreads, kSmemBytes, ctk::as_stream(stream)>>>(
-      tm_a, tm_b, M, N, K / splits, partial, static_cast<__nv_bfloat16*>(out_bf16));
+  if (K / splits / kBK <= 8) {
+    CTK_CUDA_TRY(cudaFuncSetAttribute(gemm_splitk_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<2>()));
+    gemm_splitk_kernel<2><<<grid, kThreads, smem_bytes<2>(), ctk::as_stream(stream)>>>(
+        tm_a, tm_b, M, N, K / splits, partial, static_cast<__nv_bfloat16*>(out_bf16));
+  } else {
+    CTK_CUDA_TRY(cudaFuncSetAttribute(gemm_splitk_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<6>()));
+    gemm_splitk_kernel<6><<<grid, kThreads, smem_bytes<6>(), ctk::as_stream(stream)>>>(
+        tm_a, tm_b, M, N, K / splits, partial, static_cast<__nv_bfloat16*>(out_bf16));
+  }
   return ctk::check_launch();
 }
 

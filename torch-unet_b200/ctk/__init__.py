@@ -12,8 +12,9 @@ from .models import (AdvancedRegressionModel, SimplifiedFeatureExtractionBranch,
                      SimplifiedTwoBranchRegressionModel, accelerate, set_precision)
 from .optim import Adam, mse_loss
 from .pipeline import HostScorer
-from . import parallel
+from . import io, parallel
+from .io import prepare_tiles
 
 __all__ = ["CtkError", "EXPORTED_SYMBOLS", "LIB_PATH", "load", "InferenceEngine", "pearson_per_image", "tile_metrics",
            "AdvancedRegressionModel", "SimplifiedFeatureExtractionBranch", "SimplifiedRegressionHead",
-           "SimplifiedTwoBranchRegressionModel", "accelerate", "set_precision", "Adam", "mse_loss", "HostScorer", "parallel"]
+           "SimplifiedTwoBranchRegressionModel", "accelerate", "set_precision", "Adam", "mse_loss", "HostScorer", "parallel", "io", "prepare_tiles"]
