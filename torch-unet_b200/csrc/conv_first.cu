@@ -1,6 +1,6 @@
-// First conv block, eval mode: Conv2d(cin in {1,2}, cout, 3, 1, 1) + folded BN + LeakyReLU + MaxPool2d(2,2),
-// fp32 NCHW planes in, NHWC bf16 out.  Replaces /root/reference/regression_model.py:14-17 (cin=2, cout=128)
-// and two_branch_regression.py:10-13 (cin=1, cout=64).
+// First conv block: Conv2d(cin in {1,2}, cout, 3, 1, 1) + BN + LeakyReLU + MaxPool2d(2,2), fp32 NCHW planes in, NHWC
+// bf16 out.  Replaces /root/reference/regression_model.py:14-17 (cin=2, cout=128) and two_branch_regression.py:10-13
+// (cin=1, cout=64).
 //
 // K = 9*cin is tiny, so a direct convolution is bound by the fp32 pipe (576 FMA per pixel for 64 channels).
 // Instead the block runs on the tensor cores as a GEMM whose A operand is built in shared memory by the
@@ -10,13 +10,11 @@
 // Per input channel that is 14 32-bit K-words: 9 words (x_hi, x_lo)[tap] against (w_hi, w_hi)[tap], then
 // 5 words (x_hi[2u], x_hi[2u+1]) against (w_lo[2u], w_lo[2u+1]).  K is padded to 32 (cin=1) or 64 (cin=2).
 //
-// One CTA = kGroups independent groups of 4 warps.  A group repeatedly takes a 16-row x (8*SUB)-column region of one
-// image plane: stages the (hi|lo)-packed input halo in shared memory, every thread writes the A rows of its pixel
-// (no-swizzle K-major core-matrix layout), one thread issues SUB x K/16 tcgen05.mma (M=128 pixels, N=cout) into the
-// group's TMEM columns, and after the commit the same 128 threads run the epilogue: +shift, LeakyReLU, 2x2 max
-// by butterfly shuffles, 16-byte NHWC stores.  The MMAs are ~100 cycles per region; the kernel is bound by the
-// epilogue instruction stream and the 1 GB of bf16 output it writes, so the groups exist to overlap each other's
-// load / TMEM / store latencies.
+// Two kernels:
+//  * conv_first_tc_kernel  -- raw, full-resolution conv output + batch statistics (one TMEM lane per PIXEL; the
+//    "stored" training path and ctk_conv_first_raw)
+//  * conv_first_ws_kernel  -- the pooled block as the models use it (one TMEM lane per 2x2 WINDOW, warp specialised,
+//    TMA-store epilogue): eval, train (arg-max / sign codes) and fp32-class (hi, lo) outputs
 #include "ctk_common.h"
 #include "ctk_ptx.cuh"
 
@@ -129,9 +127,7 @@ conv_first_tc_kernel(const float* __restrict__ x, int n_img, int c_total, int c_
   uint32_t* in_smem = reinterpret_cast<uint32_t*>(a_smem + C::kSub * C::kATileBytes);
   const uint32_t tmem_group = tmem_base + static_cast<uint32_t>(group * C::kSub * COUT);
   const int r = gt >> 3, cpx = gt & 7;
-  const int Hp = H >> 1, Wp = W >> 1;
   constexpr uint32_t idesc = umma_idesc_bf16_f32(128, COUT);
-  const __nv_bfloat162 slope2 = __float2bfloat162_rn(slope);
   uint32_t parity = 0;
 
   // input prefetch: the halo of the NEXT region is loaded into registers while this one is being processed.
@@ -232,7 +228,7 @@ conv_first_tc_kernel(const float* __restrict__ x, int n_img, int c_total, int c_
     parity ^= 1;
     tc_fence_after();
 
-    // ---- epilogue per sub-tile: + shift, LeakyReLU, 2x2 max-pool, NHWC bf16 store
+    // ---- epilogue per sub-tile: raw bf16 store + per-channel statistics
     const int y = y0 + r;
 #pragma unroll 1
     for (int s = 0; s < C::kSub; ++s) {
@@ -267,33 +263,6 @@ conv_first_tc_kernel(const float* __restrict__ x, int n_img, int c_total, int c_
           }
           continue;
         }
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
-        const bool odd_x = (lane & 1) != 0;
-        uint32_t q[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const uint32_t send = odd_x ? pk[i] : pk[8 + i];
-          const uint32_t keep = odd_x ? pk[8 + i] : pk[i];
-          q[i] = max_bf16x2(keep, __shfl_xor_sync(0xffffffffu, send, 1));
-        }
-        const bool odd_y = (lane & 8) != 0;
-        uint4 o;
-        uint32_t* ov = reinterpret_cast<uint32_t*>(&o);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const uint32_t send = odd_y ? q[i] : q[4 + i];
-          const uint32_t keep = odd_y ? q[4 + i] : q[i];
-          ov[i] = leaky_bf16x2(max_bf16x2(keep, __shfl_xor_sync(0xffffffffu, send, 8)), slope2);
-        }
-        if (valid) {
-          const int ch = cb * 32 + (odd_x ? 16 : 0) + (odd_y ? 8 : 0);
-          __nv_bfloat16* dst = out +
-              (static_cast<size_t>(img) * Hp * Wp + static_cast<size_t>(y >> 1) * Wp + (xg >> 1)) * out_cstride +
-              out_coffset + ch;
-          *reinterpret_cast<uint4*>(dst) = o;
-        }
       }
     }
     tc_fence_before();   // TMEM reads of this iteration are ordered before the barrier the next MMA issue follows
@@ -310,68 +279,85 @@ conv_first_tc_kernel(const float* __restrict__ x, int n_img, int c_total, int c_
 }
 
 // ======================================================================================================================
-// Pooled variant (the block as the models use it): one TMEM lane per 2x2 WINDOW.
+// Pooled variant (the block as the models use it): one TMEM lane per 2x2 WINDOW, warp specialised.
 //
 // The four pixels of a pooling window are four separate A tiles (same 128 windows, window position q = (dy, dx)); the MMA
-// of position q accumulates into TMEM columns [32q, 32q+32) of the group, 32 output channels per round.  The thread that
-// owns a window then reads its four positions from its own lane and takes the max in registers: no cross-lane
-// shuffles, no selects, the bf16 pack and the LeakyReLU run on the pooled quarter of the data, and the window's patch
-// (4 x 4 inputs per channel) is read from shared memory once for all four A rows.  ~430 instructions per window and
-// 64 channels against ~1600 for the pixel-per-lane version above (measured with ncu, profiles/r1_infer_full_*).
-//
-// kCodes: also store, per pooled element, the arg-max position and the sign of the pre-activation (4-bit code, eight
-// channels per 32-bit word) -- what the training backward needs to route gradients without recomputing the conv.
-// The position rides in the two low mantissa bits of the fp32 accumulators through the max (<= 3 fp32 ulp).
+// of position q accumulates into its own 64 TMEM columns.  The thread that owns a window then reads its four positions
+// from its own lane and takes the max in registers: no cross-lane shuffles, no selects, the bf16 pack and the LeakyReLU
+// run on the pooled quarter of the data, and the window's patch (4 x 4 inputs per channel) is read from shared memory
+// once for all four A rows (~430 instructions per window and 64 channels against ~1600 for a pixel-per-lane epilogue).
+// kMode 1 also stores, per pooled element, the arg-max position and the sign of the pre-activation (4-bit code, eight
+// channels per 32-bit word) -- what the training backward needs to route gradients without recomputing the conv; the
+// position rides in the two low mantissa bits of the fp32 accumulators through the max (<= 3 fp32 ulp).
+// kMode 2 stores fp32-class results as bf16 (hi, lo) pairs.
+// Three concurrent roles, so that each one's latencies hide behind the others':
+//   warps 8-15  two producer groups (128 threads = 128 windows each) take alternate regions: input halo -> (hi|lo) words
+//               in shared memory -> the four A tiles of the region into a ring slot            [a_empty -> a_full]
+//   warp 16     one thread issues, per 64-channel pass, 4 positions x K/16 MMAs (M = 128 windows, N = 64) into one of
+//               two 256-column TMEM buffers, commits acc_full, and a_empty after the region's last pass
+//   warps 0-7   two epilogue groups (one per TMEM buffer, warp % 4 = lane quadrant): max over the four positions in
+//               registers -> LeakyReLU -> bf16 -> 32-byte stores (+ codes / (hi, lo) pairs)     [acc_full -> acc_empty]
 template <int CIN>
-struct WinCfg {
-  static constexpr int kGroups = CIN == 1 ? 4 : 2;              // 4 A tiles of 16 KB per group at K = 64: two groups fit
-  static constexpr int kThreads = kGroups * 128;
+struct WsCfg {
   static constexpr int kK = CIN == 1 ? 32 : 64;
   static constexpr int kKWords = kK / 2;
-  static constexpr int kWinH = 16, kWinW = 8;                   // windows per region (one per TMEM lane)
+  static constexpr int kWinH = 16, kWinW = 8;
   static constexpr int kInH = 2 * kWinH + 2, kInW = 2 * kWinW + 2;
-  static constexpr int kInPitch = 24;                           // words; 8-byte patch loads are bank-conflict free
+  static constexpr int kInPitch = 24;
   static constexpr int kLbo = 128;
   static constexpr int kSbo = (kK / 8) * 128;
-  static constexpr int kATileBytes = 16 * kSbo;                 // 128 rows
-  static constexpr int kGroupBytes = 4 * kATileBytes + CIN * kInH * kInPitch * 4;
+  static constexpr int kATileBytes = 16 * kSbo;
+  static constexpr int kSlotBytes = 4 * kATileBytes;             // 32 KB (CIN 1) / 64 KB (CIN 2)
+  static constexpr int kSlots = CIN == 1 ? 4 : 2;
+  static constexpr int kInBytes = CIN * kInH * kInPitch * 4;
   static constexpr int kPref = (kInH * kInW + 127) / 128;
-  static constexpr int smem_bytes(int cout) { return 1024 + (cout / 8) * kSbo + kGroups * kGroupBytes + 256; }
+  static constexpr int kThreads = 17 * 32;
+  static constexpr int kStageBytes = 8 * 2 * 4096;              // output staging: 8 epilogue warps x 2 x (32 windows x 128 B)
+  static constexpr int smem_bytes(int cout) {
+    return 1024 + ((cout / 8) * kSbo + 1023) / 1024 * 1024 + kSlots * kSlotBytes + kStageBytes + 2 * kInBytes + 256;
+  }
 };
 
-// kMode: 0 = pooled bf16 output, 1 = + arg-max / sign codes, 2 = fp32-class output as bf16 (hi, lo) pairs (out, out_lo)
 template <int CIN, int kMode>
-__global__ void __launch_bounds__(WinCfg<CIN>::kThreads, 1)
-conv_first_win_kernel(const float* __restrict__ x, int n_img, int c_total, int c_offset, int H, int W,
-                      const float* __restrict__ w_folded, const float* __restrict__ shift, float slope, int cout,
-                      __nv_bfloat16* __restrict__ out, int out_cstride, int out_coffset, uint32_t* __restrict__ codes,
-                      __nv_bfloat16* __restrict__ out_lo, FastDiv div_rx, FastDiv div_ry, int total_regions) {
-  using C = WinCfg<CIN>;
+__global__ void __launch_bounds__(WsCfg<CIN>::kThreads, 1)
+conv_first_ws_kernel(const __grid_constant__ CUtensorMap tm_out, const float* __restrict__ x, int n_img, int c_total,
+                     int c_offset, int H, int W, const float* __restrict__ w_folded, const float* __restrict__ shift,
+                     float slope, int cout,
+                     __nv_bfloat16* __restrict__ out, int out_cstride, int out_coffset, uint32_t* __restrict__ codes,
+                     __nv_bfloat16* __restrict__ out_lo, FastDiv div_rx, FastDiv div_ry, int total_regions) {
+  using C = WsCfg<CIN>;
   constexpr bool kCodes = kMode == 1;
+  constexpr int kPosCols = 64;                 // TMEM columns per window position (64 channels)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* b_smem = smem;
-  uint8_t* groups_smem = smem + (cout / 8) * C::kSbo;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(groups_smem + C::kGroups * C::kGroupBytes);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + C::kGroups);
+  uint8_t* slots = smem + ((cout / 8) * C::kSbo + 1023) / 1024 * 1024;
+  uint8_t* stage_base = slots + C::kSlots * C::kSlotBytes;       // 1024-byte aligned: SWIZZLE_128B tiles for the TMA stores
+  uint8_t* in_base = stage_base + C::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(in_base + 2 * C::kInBytes);
+  uint64_t* a_full = bars;                       // [kSlots], 4 producer-warp arrivals
+  uint64_t* a_empty = bars + C::kSlots;          // [kSlots], one MMA commit
+  uint64_t* acc_full = bars + 2 * C::kSlots;     // [2], one MMA commit
+  uint64_t* acc_empty = acc_full + 2;            // [2], 4 epilogue-warp arrivals
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
-  const int warp = threadIdx.x >> 5;
-  const int group = warp >> 2;
-  const int gt = threadIdx.x & 127;          // thread within group = TMEM lane = window of the 16 x 8 region
-  const int ew = warp & 3;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int passes = cout >> 6;                  // 64 output channels per TMEM buffer
 
   if (threadIdx.x == 0) {
-    for (int g = 0; g < C::kGroups; ++g) mbar_init(&bars[g], 1);
+    for (int i = 0; i < C::kSlots; ++i) { mbar_init(&a_full[i], 4); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
     fence_mbar_init();
+    tma_prefetch_desc(&tm_out);
   }
-  if (warp == 0) tmem_alloc<1>(tmem_slot, 512);
-  // B operand: folded weights split into hi/lo bf16 (same K-word layout as the kernel above), built once per CTA
+  if (warp == 16) tmem_alloc<1>(tmem_slot, 512);
+  // B operand (folded weights split into hi/lo bf16), built once per CTA by everybody
   for (int i = threadIdx.x; i < cout * C::kKWords; i += C::kThreads) {
     const int n = i / C::kKWords, kw = i % C::kKWords;
     uint32_t word = 0;
     const int ch = kw / 14, j = kw % 14;
     if (kw == 14 * CIN) {
-      word = split_hi_lo(__ldg(shift + n));                               // (shift_hi, shift_lo) against A's (1, 1)
+      word = split_hi_lo(__ldg(shift + n));                          // (shift_hi, shift_lo) against A's (1, 1)
     } else if (ch < CIN) {
       const float* wr = w_folded + (n * CIN + ch) * 9;
       if (j < 9) {
@@ -379,7 +365,7 @@ conv_first_win_kernel(const float* __restrict__ x, int n_img, int c_total, int c
         word = (hl & 0xffffu) | (hl << 16);                               // (w_hi, w_hi)
       } else {
         const int t0 = 2 * (j - 9);
-        const uint32_t a = split_hi_lo(__ldg(wr + t0)) >> 16;             // w_lo[t0]
+        const uint32_t a = split_hi_lo(__ldg(wr + t0)) >> 16;        // w_lo[t0]
         const uint32_t b = t0 + 1 < 9 ? (split_hi_lo(__ldg(wr + t0 + 1)) >> 16) : 0u;
         word = a | (b << 16);
       }
@@ -393,26 +379,8 @@ conv_first_win_kernel(const float* __restrict__ x, int n_img, int c_total, int c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-
-  uint8_t* a_smem = groups_smem + group * C::kGroupBytes;
-  uint32_t* in_smem = reinterpret_cast<uint32_t*>(a_smem + 4 * C::kATileBytes);
-  const uint32_t tmem_group = tmem_base + static_cast<uint32_t>(group * 128);
-  const int wy = gt >> 3, wx = gt & 7;
   const int Hp = H >> 1, Wp = W >> 1;
-  constexpr uint32_t idesc = umma_idesc_bf16_f32(128, 32);
-  const __nv_bfloat162 slope2 = __float2bfloat162_rn(slope);
-  uint32_t parity = 0;
-  const int rounds = cout >> 5;
 
-  // input prefetch: the halo of the NEXT region is loaded into registers while this one is being processed
-  int pre_rr[C::kPref], pre_q[C::kPref];
-#pragma unroll
-  for (int j = 0; j < C::kPref; ++j) {
-    const int i = gt + 128 * j;
-    pre_rr[j] = i < C::kInH * C::kInW ? i / C::kInW : -1000000;
-    pre_q[j] = i - (i / C::kInW) * C::kInW;
-  }
-  float pref[CIN][C::kPref];
   auto decode = [&](int region, int& img, int& ry, int& rx) {
     const uint32_t q1 = fdiv(static_cast<uint32_t>(region), div_rx);
     rx = region - static_cast<int>(q1 * div_rx.d);
@@ -420,38 +388,49 @@ conv_first_win_kernel(const float* __restrict__ x, int n_img, int c_total, int c
     ry = static_cast<int>(q1 - q2 * div_ry.d);
     img = static_cast<int>(q2);
   };
-  auto load_region = [&](int region) {
-    int img, ry, rx;
-    decode(region, img, ry, rx);
-    const int y0 = ry * 2 * C::kWinH - 1, x0 = rx * 2 * C::kWinW - 1;
-    const float* plane0 = x + (static_cast<size_t>(img) * c_total + c_offset) * H * W;
+
+  if (warp >= 8 && warp < 16) {
+    // ------------------------------------------------------------------ producers
+    const int pg = (warp - 8) >> 2;
+    const int gt = threadIdx.x & 127;            // window of the region this thread builds
+    const int wy = gt >> 3, wx = gt & 7;
+    uint32_t* in_smem = reinterpret_cast<uint32_t*>(in_base + pg * C::kInBytes);
+    int pre_rr[C::kPref], pre_q[C::kPref];
 #pragma unroll
     for (int j = 0; j < C::kPref; ++j) {
-      const int gy = y0 + pre_rr[j], gx = x0 + pre_q[j];
-      const bool ok = gy >= 0 && gy < H && gx >= 0 && gx < W;
-      const size_t off = static_cast<size_t>(gy) * W + gx;
-#pragma unroll
-      for (int c = 0; c < CIN; ++c) pref[c][j] = ok ? __ldg(plane0 + static_cast<size_t>(c) * H * W + off) : 0.f;
+      const int i = gt + 128 * j;
+      pre_rr[j] = i < C::kInH * C::kInW ? i / C::kInW : -1000000;
+      pre_q[j] = i - (i / C::kInW) * C::kInW;
     }
-  };
-  const int region_first = blockIdx.x * C::kGroups + group;
-  const int region_step = gridDim.x * C::kGroups;
-  if (region_first < total_regions) load_region(region_first);
-
-  for (int region = region_first; region < total_regions; region += region_step) {
-    int img, ry, rx;
-    decode(region, img, ry, rx);
-    // ---- stage the prefetched halo as packed (hi | lo << 16) words, then prefetch the next region
+    float pref[CIN][C::kPref];
+    auto load_region = [&](int region) {
+      int img, ry, rx;
+      decode(region, img, ry, rx);
+      const int y0 = ry * 2 * C::kWinH - 1, x0 = rx * 2 * C::kWinW - 1;
+      const float* plane0 = x + (static_cast<size_t>(img) * c_total + c_offset) * H * W;
 #pragma unroll
-    for (int c = 0; c < CIN; ++c)
+      for (int j = 0; j < C::kPref; ++j) {
+        const int gy = y0 + pre_rr[j], gx = x0 + pre_q[j];
+        const bool ok = gy >= 0 && gy < H && gx >= 0 && gx < W;
+        const size_t off = static_cast<size_t>(gy) * W + gx;
 #pragma unroll
-      for (int j = 0; j < C::kPref; ++j)
-        if (pre_rr[j] >= 0) in_smem[(c * C::kInH + pre_rr[j]) * C::kInPitch + pre_q[j]] = split_hi_lo(pref[c][j]);
-    asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory");
-    if (region + region_step < total_regions) load_region(region + region_step);
-
-    // ---- this window's 4 x 4 patch per channel -> the A rows of its four pixels
-    {
+        for (int c = 0; c < CIN; ++c) pref[c][j] = ok ? __ldg(plane0 + static_cast<size_t>(c) * H * W + off) : 0.f;
+      }
+    };
+    const int k_step = 2;
+    int k = pg;
+    int region = blockIdx.x + k * gridDim.x;
+    if (region < total_regions) load_region(region);
+    for (; region < total_regions; k += k_step, region = blockIdx.x + k * gridDim.x) {
+      // halo -> packed (hi | lo << 16) words; the next region of this group is prefetched into registers meanwhile
+#pragma unroll
+      for (int c = 0; c < CIN; ++c)
+#pragma unroll
+        for (int j = 0; j < C::kPref; ++j)
+          if (pre_rr[j] >= 0) in_smem[(c * C::kInH + pre_rr[j]) * C::kInPitch + pre_q[j]] = split_hi_lo(pref[c][j]);
+      asm volatile("bar.sync %0, 128;" ::"r"(pg + 1) : "memory");
+      const int next = blockIdx.x + (k + k_step) * gridDim.x;
+      if (next < total_regions) load_region(next);
       uint32_t pt[CIN][4][4];
 #pragma unroll
       for (int c = 0; c < CIN; ++c)
@@ -461,6 +440,10 @@ conv_first_win_kernel(const float* __restrict__ x, int n_img, int c_total, int c
           const uint2 a = row[0], b = row[1];
           pt[c][rr][0] = a.x; pt[c][rr][1] = a.y; pt[c][rr][2] = b.x; pt[c][rr][3] = b.y;
         }
+      asm volatile("bar.sync %0, 128;" ::"r"(pg + 1) : "memory");      // everybody has its patch: in_smem may be restaged
+      const int slot = k % C::kSlots;
+      mbar_wait(&a_empty[slot], ((k / C::kSlots) & 1) ^ 1);
+      uint8_t* a_smem = slots + slot * C::kSlotBytes;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const int dy = q >> 1, dx = q & 1;
@@ -486,108 +469,160 @@ conv_first_win_kernel(const float* __restrict__ x, int n_img, int c_total, int c
         for (int j = 0; j < C::kK / 8; ++j)
           *reinterpret_cast<uint4*>(tile + j * C::kLbo) = make_uint4(kw[4 * j], kw[4 * j + 1], kw[4 * j + 2], kw[4 * j + 3]);
       }
+      fence_proxy_async_smem();          // generic-proxy writes -> visible to the tensor core's async-proxy reads
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&a_full[slot]);
     }
-    fence_proxy_async_smem();          // generic-proxy writes -> visible to the tensor core's async-proxy reads
-    tc_fence_before();
-    asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory");
-
-    const int py = ry * C::kWinH + wy, px = rx * C::kWinW + wx;
-    const bool valid = py < Hp && px < Wp;
-    const size_t pooled_pix = (static_cast<size_t>(img) * Hp + py) * Wp + px;
-#pragma unroll 1
-    for (int cr = 0; cr < rounds; ++cr) {
-      // ---- one thread issues the 4 x K/16 MMAs of this channel round and commits to the group's barrier
-      if (ew == 0) {
+  } else if (warp == 16) {
+    // ------------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = umma_idesc_bf16_f32(128, 64);
+    const uint64_t desc0 = umma_smem_desc_nosw(0, C::kLbo, C::kSbo);
+    int u = 0;
+    for (int k = 0, region = blockIdx.x; region < total_regions; ++k, region += gridDim.x) {
+      const int slot = k % C::kSlots;
+      mbar_wait(&a_full[slot], (k / C::kSlots) & 1);
+      tc_fence_after();
+      const uint64_t adesc = desc0 | static_cast<uint64_t>(smem_u32(slots + slot * C::kSlotBytes) >> 4);
+      for (int p = 0; p < passes; ++p, ++u) {
+        const int buf = u & 1;
+        mbar_wait(&acc_empty[buf], ((u >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint64_t desc0 = umma_smem_desc_nosw(0, C::kLbo, C::kSbo);
-        const uint64_t bdesc = desc0 | static_cast<uint64_t>((smem_u32(b_smem) + cr * 4 * C::kSbo) >> 4);
-        const uint64_t adesc = desc0 | static_cast<uint64_t>(smem_u32(a_smem) >> 4);
+        const uint64_t bdesc = desc0 | static_cast<uint64_t>((smem_u32(b_smem) + p * 8 * C::kSbo) >> 4);
         if (elect_one()) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
+          for (int q = 0; q < 4; ++q)
 #pragma unroll
-            for (int ks = 0; ks < C::kK / 16; ++ks) {
-              umma_bf16(tmem_group + q * 32, adesc + ((q * C::kATileBytes + ks * 2 * C::kLbo) >> 4),
+            for (int ks = 0; ks < C::kK / 16; ++ks)
+              umma_bf16(tmem_base + buf * 256 + q * kPosCols, adesc + ((q * C::kATileBytes + ks * 2 * C::kLbo) >> 4),
                         bdesc + ((ks * 2 * C::kLbo) >> 4), idesc, ks != 0 ? 1u : 0u);
-            }
-          }
-          umma_commit(&bars[group]);
+          umma_commit(&acc_full[buf]);
+          if (p == passes - 1) umma_commit(&a_empty[slot]);
         }
         __syncwarp();
       }
-      mbar_wait(&bars[group], parity);
-      parity ^= 1;
-      tc_fence_after();
-      // ---- epilogue: max over the window's four positions in registers, LeakyReLU, bf16, 2 x 32 bytes per thread
-#pragma unroll
-      for (int hf = 0; hf < 2; ++hf) {
-        uint32_t v[4][16];
-        const uint32_t taddr = tmem_group + (static_cast<uint32_t>(ew * 32) << 16) + hf * 16;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) tmem_ld_32x16(taddr + q * 32, v[q]);
-        tmem_ld_wait();
-        float best[16];
-        if constexpr (kCodes) {
-          // position q in the two low mantissa bits (3 - q: the first position wins ties among non-negative values)
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float m = __uint_as_float((v[0][i] & ~3u) | 3u);
-            m = fmaxf(m, __uint_as_float((v[1][i] & ~3u) | 2u));
-            m = fmaxf(m, __uint_as_float((v[2][i] & ~3u) | 1u));
-            best[i] = fmaxf(m, __uint_as_float(v[3][i] & ~3u));
-          }
-          uint32_t cw[2] = {0u, 0u};
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const uint32_t b = __float_as_uint(best[i]);
-            const uint32_t nib = (3u - (b & 3u)) | ((b >> 29) & 4u);        // arg-max position | sign << 2
-            cw[i >> 3] |= nib << (4 * (i & 7));
-          }
-          if (valid) {
-            uint32_t* cdst = codes + pooled_pix * (cout >> 3) + cr * 4 + hf * 2;
-            *reinterpret_cast<uint2*>(cdst) = make_uint2(cw[0], cw[1]);
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 16; ++i)
-            best[i] = fmaxf(fmaxf(__uint_as_float(v[0][i]), __uint_as_float(v[1][i])),
-                            fmaxf(__uint_as_float(v[2][i]), __uint_as_float(v[3][i])));
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue: group eg drains TMEM buffer eg
+    const int eg = warp >> 2, ew = warp & 3;
+    const int gt = ew * 32 + lane;               // TMEM lane = window
+    const int wy = gt >> 3, wx = gt & 7;
+    const __nv_bfloat162 slope2 = __float2bfloat162_rn(slope);
+    int u = 0;
+    int stage_turn = 0;
+    for (int k = 0, region = blockIdx.x; region < total_regions; ++k, region += gridDim.x) {
+      int img, ry, rx;
+      decode(region, img, ry, rx);
+      const int py = ry * C::kWinH + wy, px = rx * C::kWinW + wx;
+      const bool valid = py < Hp && px < Wp;
+      const size_t pooled_pix = (static_cast<size_t>(img) * Hp + py) * Wp + px;
+      for (int p = 0; p < passes; ++p, ++u) {
+        if ((u & 1) != eg) continue;
+        uint32_t code_words[8];
+        uint32_t stage_addr = 0;
+        if constexpr (kMode != 2) {
+          stage_addr = smem_u32(stage_base) + static_cast<uint32_t>((warp * 2 + stage_turn) * 4096);
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the store that last read this tile
+          __syncwarp();
         }
-        if constexpr (kMode == 2) {
-          uint32_t oh[8], ol[8];
+        mbar_wait(&acc_full[eg], (u >> 1) & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + eg * 256;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float a0 = leaky(best[2 * i], slope), a1 = leaky(best[2 * i + 1], slope);
-            const uint32_t s0 = split_hi_lo(a0), s1 = split_hi_lo(a1);
-            oh[i] = (s0 & 0xffffu) | (s1 << 16);
-            ol[i] = (s0 >> 16) | (s1 & 0xffff0000u);
-          }
-          if (valid) {
-            const size_t off = pooled_pix * out_cstride + out_coffset + cr * 32 + hf * 16;
-            reinterpret_cast<uint4*>(out + off)[0] = make_uint4(oh[0], oh[1], oh[2], oh[3]);
-            reinterpret_cast<uint4*>(out + off)[1] = make_uint4(oh[4], oh[5], oh[6], oh[7]);
-            reinterpret_cast<uint4*>(out_lo + off)[0] = make_uint4(ol[0], ol[1], ol[2], ol[3]);
-            reinterpret_cast<uint4*>(out_lo + off)[1] = make_uint4(ol[4], ol[5], ol[6], ol[7]);
-          }
-        } else {
-          uint32_t o[8];
+        for (int hf = 0; hf < 4; ++hf) {
+          uint32_t v[4][16];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) o[i] = leaky_bf16x2(pack_bf16x2(best[2 * i], best[2 * i + 1]), slope2);
-          if (valid) {
-            __nv_bfloat16* dst = out + pooled_pix * out_cstride + out_coffset + cr * 32 + hf * 16;
-            reinterpret_cast<uint4*>(dst)[0] = make_uint4(o[0], o[1], o[2], o[3]);
-            reinterpret_cast<uint4*>(dst)[1] = make_uint4(o[4], o[5], o[6], o[7]);
+          for (int q = 0; q < 4; ++q) tmem_ld_32x16(taddr + q * 64 + hf * 16, v[q]);
+          tmem_ld_wait();
+          if (hf == 3) {                          // all TMEM reads of this unit are done: hand the buffer back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[eg]);
           }
+          float best[16];
+          const int ch = p * 64 + hf * 16;
+          if constexpr (kCodes) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              float m = __uint_as_float((v[0][i] & ~3u) | 3u);
+              m = fmaxf(m, __uint_as_float((v[1][i] & ~3u) | 2u));
+              m = fmaxf(m, __uint_as_float((v[2][i] & ~3u) | 1u));
+              best[i] = fmaxf(m, __uint_as_float(v[3][i] & ~3u));
+            }
+            uint32_t cw[2] = {0u, 0u};
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const uint32_t b = __float_as_uint(best[i]);
+              const uint32_t nib = (3u - (b & 3u)) | ((b >> 29) & 4u);      // arg-max position | sign << 2
+              cw[i >> 3] |= nib << (4 * (i & 7));
+            }
+            code_words[2 * hf] = cw[0];
+            code_words[2 * hf + 1] = cw[1];
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              best[i] = fmaxf(fmaxf(__uint_as_float(v[0][i]), __uint_as_float(v[1][i])),
+                              fmaxf(__uint_as_float(v[2][i]), __uint_as_float(v[3][i])));
+          }
+          if constexpr (kMode == 2) {
+            uint32_t oh[8], ol[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const uint32_t s0 = split_hi_lo(leaky(best[2 * i], slope)), s1 = split_hi_lo(leaky(best[2 * i + 1], slope));
+              oh[i] = (s0 & 0xffffu) | (s1 << 16);
+              ol[i] = (s0 >> 16) | (s1 & 0xffff0000u);
+            }
+            if (valid) {
+              const size_t off = pooled_pix * out_cstride + out_coffset + ch;
+              reinterpret_cast<uint4*>(out + off)[0] = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+              reinterpret_cast<uint4*>(out + off)[1] = make_uint4(oh[4], oh[5], oh[6], oh[7]);
+              reinterpret_cast<uint4*>(out_lo + off)[0] = make_uint4(ol[0], ol[1], ol[2], ol[3]);
+              reinterpret_cast<uint4*>(out_lo + off)[1] = make_uint4(ol[4], ol[5], ol[6], ol[7]);
+            }
+          } else {
+            // pooled bf16 output: staged as a 128B-swizzled [32 windows][64 channels] tile, stored by one TMA instruction
+            // per warp and pass -- registers are free again after the shared-memory store, every global write is a full
+            // 128-byte line, and ragged edges are clipped by the tensor map
+            uint32_t o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = leaky_bf16x2(pack_bf16x2(best[2 * i], best[2 * i + 1]), slope2);
+            const uint32_t row = stage_addr + static_cast<uint32_t>(lane * 128);
+            const uint32_t c0 = static_cast<uint32_t>(((2 * hf) ^ (lane & 7)) * 16);
+            const uint32_t c1 = static_cast<uint32_t>(((2 * hf + 1) ^ (lane & 7)) * 16);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + c0), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + c1), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]) : "memory");
+          }
+        }
+        if constexpr (kCodes) {
+          if (valid) {                                      // the window's 64 codes of this pass: one full 32-byte sector
+            uint4* cdst = reinterpret_cast<uint4*>(codes + pooled_pix * (cout >> 3) + p * 8);
+            cdst[0] = make_uint4(code_words[0], code_words[1], code_words[2], code_words[3]);
+            cdst[1] = make_uint4(code_words[4], code_words[5], code_words[6], code_words[7]);
+          }
+        }
+        if constexpr (kMode != 2) {
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            asm volatile(
+                "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                    reinterpret_cast<uint64_t>(&tm_out)),
+                "r"(stage_addr), "r"(out_coffset + p * 64), "r"(rx * C::kWinW), "r"(ry * C::kWinH + ew * 4), "r"(img)
+                : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+          stage_turn ^= 1;
         }
       }
-      tc_fence_before();   // TMEM reads of this round are ordered before the barrier the next MMA issue follows
-      asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory");
+    }
+    if constexpr (kMode != 2) {
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores must land before the CTA exits
+      __syncwarp();
     }
   }
   __syncwarp();
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) {
+  if (warp == 16) {
     tc_fence_after();
     tmem_dealloc<1>(tmem_base, 512);
   }
@@ -597,18 +632,27 @@ template <int CIN, int kMode>
 int launch_first_win(const float* x, int n, int c_total, int c_offset, int H, int W, const float* w_folded,
                      const float* shift, float slope, int cout, __nv_bfloat16* out, int out_cstride, int out_coffset,
                      uint32_t* codes, __nv_bfloat16* out_lo, cudaStream_t stream) {
-  using C = WinCfg<CIN>;
-  const int regions_x = (W / 2 + C::kWinW - 1) / C::kWinW;
-  const int regions_y = (H / 2 + C::kWinH - 1) / C::kWinH;
+  using WS = WsCfg<CIN>;
+  const int regions_x = (W / 2 + WS::kWinW - 1) / WS::kWinW;
+  const int regions_y = (H / 2 + WS::kWinH - 1) / WS::kWinH;
   const long long total = static_cast<long long>(n) * regions_x * regions_y;
   if (total >= (1ll << 30)) return CTK_ERR_BAD_ARG;
-  auto kernel = conv_first_win_kernel<CIN, kMode>;
-  const int smem = C::smem_bytes(cout);
-  CTK_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  const int grid = static_cast<int>(std::min<long long>((total + C::kGroups - 1) / C::kGroups, ctk::num_sms()));
-  kernel<<<grid, C::kThreads, smem, stream>>>(x, n, c_total, c_offset, H, W, w_folded, shift, slope, cout, out, out_cstride,
-                                              out_coffset, codes, out_lo, make_fastdiv(regions_x), make_fastdiv(regions_y),
-                                              static_cast<int>(total));
+  auto ws = conv_first_ws_kernel<CIN, kMode>;
+  const int ws_smem = WS::smem_bytes(cout);
+  CTK_CUDA_TRY(cudaFuncSetAttribute(ws, cudaFuncAttributeMaxDynamicSharedMemorySize, ws_smem));
+  const int ws_grid = static_cast<int>(std::min<long long>(total, ctk::num_sms()));
+  CUtensorMap tm_out;
+  {
+    const uint64_t cs = static_cast<uint64_t>(out_cstride);
+    const uint64_t dims[4] = {cs, static_cast<uint64_t>(W / 2), static_cast<uint64_t>(H / 2), static_cast<uint64_t>(n)};
+    const uint64_t strides[3] = {cs * 2, static_cast<uint64_t>(W / 2) * cs * 2, static_cast<uint64_t>(H / 2) * (W / 2) * cs * 2};
+    const uint32_t box[4] = {64, 8, 4, 1};
+    int st = ctk::encode_tmap_bf16_sw128(&tm_out, out, 4, dims, strides, box);
+    if (st != CTK_OK) return st;
+  }
+  ws<<<ws_grid, WS::kThreads, ws_smem, stream>>>(tm_out, x, n, c_total, c_offset, H, W, w_folded, shift, slope, cout, out,
+                                                 out_cstride, out_coffset, codes, out_lo, make_fastdiv(regions_x),
+                                                 make_fastdiv(regions_y), static_cast<int>(total));
   return ctk::check_launch();
 }
 
@@ -640,7 +684,7 @@ static int first_pool_dispatch(const float* x, int n, int c_total, int c_offset,
   CTK_REQUIRE(x && w_folded && shift && out_bf16 && n > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0);
   CTK_REQUIRE(c_offset >= 0 && c_offset + cin <= c_total && out_coffset >= 0 && out_coffset + cout <= out_cstride);
   CTK_REQUIRE(out_cstride % 8 == 0 && out_coffset % 8 == 0 && (reinterpret_cast<uintptr_t>(out_bf16) & 15) == 0);
-  CTK_REQUIRE(cout > 0 && cout % 32 == 0 && cout <= 256 && (reinterpret_cast<uintptr_t>(codes) & 7) == 0);
+  CTK_REQUIRE(cout > 0 && cout % 64 == 0 && cout <= 256 && (reinterpret_cast<uintptr_t>(codes) & 15) == 0);
   CTK_REQUIRE((reinterpret_cast<uintptr_t>(out_lo_bf16) & 15) == 0 && !(codes && out_lo_bf16));
   cudaStream_t s = ctk::as_stream(stream);
   __nv_bfloat16* out = static_cast<__nv_bfloat16*>(out_bf16);
