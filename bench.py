@@ -34,8 +34,12 @@ def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         p = json.load(open(path))
-        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "src": "measured"}
-    return {"hbm_gbs": 6650.0, "bf16_tflops": 1400.0, "src": "fallback"}
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                "bf16_tflops_burst": p["bf16_tflops"], "src": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1400.0, "bf16_tflops_burst": 1400.0, "src": "fallback"}
+
+
+NOMINAL_BF16_TFLOPS = 2250.0     # B200 dense bf16 (B200_PROFILING.md)
 
 
 class ClockSampler:
@@ -255,6 +259,7 @@ def run_train(args, shared_pg=False):
                 "roofline": {"kernel": "conv3x3_tc_kernel (fwd+dgrad) + wgrad_tc_kernel", "bound": "tensor", "achieved": tf,
                              "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": tf / pk["bf16_tflops"], "traffic": None,
                              "peak_source": pk["src"] + " (sustained cuBLAS bf16)",
+                             "frac_of_burst_cublas": tf / pk["bf16_tflops_burst"], "frac_of_nominal_dense": tf / NOMINAL_BF16_TFLOPS,
                              "share_of_step": tc_ms / ms if ms > 0 else None,
                              "per_call_ms_per_step": {k: round(v["ms"] / steps, 4) for k, v in sorted(per.items())},
                              "per_call_tflops": {k: round(v["flops"] / (v["ms"] / 1e3) / 1e12, 1)
@@ -398,7 +403,8 @@ def main():
         conv_tf = conv["flops"] / (conv["ms"] / 1e3) / 1e12 if conv["ms"] > 0 else 0.0
         roof = {"kernel": "conv3x3_tc_kernel", "bound": "tensor", "achieved": conv_tf, "peak": pk["bf16_tflops"],
                 "unit": "TFLOP/s", "frac": conv_tf / pk["bf16_tflops"], "traffic": None,
-                "peak_source": pk["src"] + " (sustained cuBLAS bf16)",
+                "peak_source": pk["src"] + " (sustained cuBLAS bf16: the kernel is timed inside a long step)",
+                "frac_of_burst_cublas": conv_tf / pk["bf16_tflops_burst"], "frac_of_nominal_dense": conv_tf / NOMINAL_BF16_TFLOPS,
                 "avg_launch_ms": conv["ms"] / max(1, conv["n"]), "launches": conv["n"],
                 "share_of_step": conv["ms"] / ms if ms > 0 else None,
                 "per_call_ms_per_step": {k: v["ms"] / steps for k, v in per.items()}}

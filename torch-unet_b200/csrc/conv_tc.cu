@@ -383,13 +383,28 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     }
   } else if (warp == 1 && rank == 0) {
     // ---------------- MMA issuer (pair leader only)
+    // The issue loop is on the critical path of the narrow layers: a (256 x 64 x 16) MMA retires in 32 clocks, so the ~80
+    // instructions a rolled per-tap iteration used to spend on run-time tap arithmetic, constant-bank reloads and
+    // descriptor moves (measured: 300+ clk per 4 MMAs) starved the tensor pipe.  Taps and K steps are fully unrolled
+    // (descriptors differ by compile-time constants), and with resident weights a whole chunk -- 36 MMAs and its commits
+    // -- is issued under a single elect.
     constexpr uint32_t idesc = umma_idesc_bf16_f32(128 * kCtaGroup, kBlockN);
     constexpr uint32_t sbo = kHaloW * 128;   // one halo row per 8-pixel core-matrix group
     // descriptor templates: everything but the 14-bit start-address field is loop invariant
     const uint64_t adesc0 = umma_smem_desc_sw128(0, sbo, 0);
     const uint64_t bdesc0 = umma_smem_desc_sw128(0, 1024, 0);
+    const uint32_t b_smem_addr = smem_u32(b_smem);
+    auto mma = [&](uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accum) {
+      if constexpr (kCtaGroup == 1) umma_bf16(d_tmem, adesc, bdesc, idesc, accum);
+      else umma_bf16_pair(d_tmem, adesc, bdesc, idesc, accum);
+    };
+    auto commit = [&](uint64_t* bar) {
+      if constexpr (kCtaGroup == 1) umma_commit(bar);
+      else umma_commit_pair(bar);
+    };
     int as = 0, aphase = 0, bs = 0, bphase = 0;
     int it = 0;
+    const bool resident = p.b_resident != 0;
     for (int work = work0; work < p.total_work; work += work_stride, ++it) {
       const int acc = it & 1;
       const int acc_phase = (it >> 1) & 1;
@@ -399,42 +414,59 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       for (int c = 0; c < chunks; ++c) {
         mbar_wait(&sl->a_full[as], aphase);
         tc_fence_after();
-        const uint32_t a_base = smem_u32(a_smem + as * kAStageBytes);
-        for (int tap = 0; tap < 9; ++tap) {
-          if (p.b_resident) bs = c * 9 + tap;
-          if (!p.b_resident || it == 0) {
-            mbar_wait(&sl->b_full[bs], bphase);
-            tc_fence_after();
-          }
-          const int ky = tap / 3, kx = tap - 3 * ky;
-          // The 128B swizzle is a function of the absolute shared-memory address bits (verified on B200:
-          // base-offset field 0, any 128-byte-aligned start, any multiple-of-128 group stride), so a shifted
-          // window of the TMA-written halo is a valid K-major operand as is.
-          const uint32_t a_tap = a_base + static_cast<uint32_t>((ky * kHaloW + kx) * 128);
-          const uint32_t b_base = smem_u32(b_smem + bs * C::kBStageBytes);
-          const uint64_t adesc = adesc0 | static_cast<uint64_t>(a_tap >> 4);
-          const uint64_t bdesc = bdesc0 | static_cast<uint64_t>(b_base >> 4);
-          const bool last_tap = tap == 8;
+        // The 128B swizzle is a function of the absolute shared-memory address bits (verified on B200: base-offset
+        // field 0, any 128-byte-aligned start, any multiple-of-128 group stride), so a shifted window of the
+        // TMA-written halo is a valid K-major operand as is.  Stage bases are 1024-byte aligned and every offset below
+        // stays inside the stage, so adding (offset >> 4) never carries out of the descriptor's address field.
+        const uint64_t adesc_c = adesc0 | static_cast<uint64_t>(smem_u32(a_smem + as * kAStageBytes) >> 4);
+        const bool last_chunk = c == chunks - 1;
+        if (resident && it > 0) {
+          // weights of every (chunk, tap) are in place since the first tile: one straight-line burst per chunk
+          const uint64_t bdesc_c = bdesc0 | static_cast<uint64_t>((b_smem_addr + c * 9 * C::kBStageBytes) >> 4);
           if (elect_one()) {
 #pragma unroll
-            for (int s = 0; s < kKC / 16; ++s) {
-              const uint32_t accum = (c | tap | s) != 0 ? 1u : 0u;
-              // +32 bytes per UMMA_K step = +2 in the (address >> 4) field; never carries out of it
-              if constexpr (kCtaGroup == 1) umma_bf16(d_tmem, adesc + 2 * s, bdesc + 2 * s, idesc, accum);
-              else umma_bf16_pair(d_tmem, adesc + 2 * s, bdesc + 2 * s, idesc, accum);
+            for (int tap = 0; tap < 9; ++tap) {
+#pragma unroll
+              for (int s = 0; s < kKC / 16; ++s) {
+                const uint32_t accum = (tap | s) != 0 ? 1u : (c != 0 ? 1u : 0u);
+                mma(d_tmem, adesc_c + (((tap / 3) * kHaloW + tap % 3) * 128 + s * 32) / 16,
+                    bdesc_c + (tap * C::kBStageBytes + s * 32) / 16, accum);
+              }
             }
-            if constexpr (kCtaGroup == 1) {
-              if (!p.b_resident) umma_commit(&sl->b_empty[bs]);
-              if (last_tap) umma_commit(&sl->a_empty[as]);
-              if (last_tap && c == chunks - 1) umma_commit(&sl->acc_full[acc]);
-            } else {
-              if (!p.b_resident) umma_commit_pair(&sl->b_empty[bs]);
-              if (last_tap) umma_commit_pair(&sl->a_empty[as]);
-              if (last_tap && c == chunks - 1) umma_commit_pair(&sl->acc_full[acc]);
-            }
+            commit(&sl->a_empty[as]);
+            if (last_chunk) commit(&sl->acc_full[acc]);
           }
           __syncwarp();
-          if (!p.b_resident && ++bs == C::kBStages) { bs = 0; bphase ^= 1; }
+        } else {
+          // streamed weights (or the first tile of a resident layer): one kernel row -- three taps, 12 MMAs -- per elect
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky) {
+            int st[3];
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+              if (resident) bs = c * 9 + ky * 3 + kx;
+              st[kx] = bs;
+              mbar_wait(&sl->b_full[bs], bphase);
+              if (!resident && ++bs == C::kBStages) { bs = 0; bphase ^= 1; }
+            }
+            tc_fence_after();
+            if (elect_one()) {
+#pragma unroll
+              for (int kx = 0; kx < 3; ++kx) {
+                const uint64_t adesc = adesc_c + ((ky * kHaloW + kx) * 128) / 16;
+                const uint64_t bdesc = bdesc0 | static_cast<uint64_t>((b_smem_addr + st[kx] * C::kBStageBytes) >> 4);
+#pragma unroll
+                for (int s = 0; s < kKC / 16; ++s) {
+                  const uint32_t accum = (ky | kx | s) != 0 ? 1u : (c != 0 ? 1u : 0u);
+                  mma(d_tmem, adesc + 2 * s, bdesc + 2 * s, accum);      // +32 bytes per UMMA_K step
+                }
+                if (!resident) commit(&sl->b_empty[st[kx]]);
+              }
+              if (ky == 2) commit(&sl->a_empty[as]);
+              if (ky == 2 && last_chunk) commit(&sl->acc_full[acc]);
+            }
+            __syncwarp();
+          }
         }
         if (++as == kAStages) { as = 0; aphase ^= 1; }
       }

@@ -252,29 +252,47 @@ first_wgrad_codes_kernel(const float* __restrict__ x, int n_img, int c_total, in
         if (sr[k] >= 0) s_in[c][sr[k]][sq[k]] = pf[c][k];
     __syncthreads();
     if (tile + gridDim.x < total) fetch(tile + gridDim.x);
-#pragma unroll 2
-    for (int win = slot; win < TWW * TWH; win += SLOTS) {
-      const int wy = win / TWW, wx = win % TWW;
-      const int py = ty * TWH + wy, px = tx * TWW + wx;
-      if (py >= Hp || px >= Wp) continue;
-      const size_t pix = (static_cast<size_t>(img) * Hp + py) * Wp + px;
-      const uint2 raw = __ldcs(reinterpret_cast<const uint2*>(dp + pix * COUT + cg * 4));
-      const uint32_t cw = __ldcs(codes + pix * (COUT / 8) + (cg >> 1)) >> ((cg & 1) * 16);
-      const float g[4] = {__uint_as_float(raw.x << 16), __uint_as_float(raw.x & 0xffff0000u),
-                          __uint_as_float(raw.y << 16), __uint_as_float(raw.y & 0xffff0000u)};
+    // this thread's windows of the tile, eight at a time: all their gradient / code loads are issued before the first
+    // one is used (the gather itself only touches shared memory, so these global loads are the kernel's latency)
+    constexpr int PER_THREAD = TWW * TWH / SLOTS;
+    constexpr int BATCH = PER_THREAD < 8 ? PER_THREAD : 8;
+    static_assert(PER_THREAD % BATCH == 0, "window batches");
+#pragma unroll 1
+    for (int w0 = 0; w0 < PER_THREAD; w0 += BATCH) {
+      uint2 raws[BATCH];
+      uint32_t cws[BATCH];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const uint32_t nib = (cw >> (4 * j)) & 0xfu;
-        const float gg = (nib & 4u) ? g[j] * slope : g[j];
-        s1[j] += gg;
-        const float* base = &s_in[0][2 * wy + ((nib >> 1) & 1u)][2 * wx + (nib & 1u)];
+      for (int b = 0; b < BATCH; ++b) {
+        const int win = slot + (w0 + b) * SLOTS;
+        const int wy = win / TWW, wx = win % TWW;
+        const int py = ty * TWH + wy, px = tx * TWW + wx;
+        const bool ok = py < Hp && px < Wp;
+        const size_t pix = ok ? (static_cast<size_t>(img) * Hp + py) * Wp + px : 0;
+        raws[b] = ok ? __ldcs(reinterpret_cast<const uint2*>(dp + pix * COUT + cg * 4)) : make_uint2(0u, 0u);
+        cws[b] = ok ? __ldcs(codes + pix * (COUT / 8) + (cg >> 1)) : 0u;
+      }
 #pragma unroll
-        for (int c = 0; c < CIN; ++c)
+      for (int b = 0; b < BATCH; ++b) {
+        const int win = slot + (w0 + b) * SLOTS;
+        const int wy = win / TWW, wx = win % TWW;
+        const uint2 raw = raws[b];
+        const uint32_t cw = cws[b] >> ((cg & 1) * 16);
+        const float g[4] = {__uint_as_float(raw.x << 16), __uint_as_float(raw.x & 0xffff0000u),
+                            __uint_as_float(raw.y << 16), __uint_as_float(raw.y & 0xffff0000u)};
 #pragma unroll
-          for (int ky = 0; ky < 3; ++ky)
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t nib = (cw >> (4 * j)) & 0xfu;
+          const float gg = (nib & 4u) ? g[j] * slope : g[j];     // out-of-range windows carry g = 0
+          s1[j] += gg;
+          const float* base = &s_in[0][2 * wy + ((nib >> 1) & 1u)][2 * wx + (nib & 1u)];
 #pragma unroll
-            for (int kx = 0; kx < 3; ++kx)
-              acc[j][c * 9 + ky * 3 + kx] = fmaf(gg, base[(c * ROWS + ky) * PITCH + kx], acc[j][c * 9 + ky * 3 + kx]);
+          for (int c = 0; c < CIN; ++c)
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+              for (int kx = 0; kx < 3; ++kx)
+                acc[j][c * 9 + ky * 3 + kx] = fmaf(gg, base[(c * ROWS + ky) * PITCH + kx], acc[j][c * 9 + ky * 3 + kx]);
+        }
       }
     }
   }
