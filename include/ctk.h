@@ -65,6 +65,12 @@ size_t ctk_tile_metrics_workspace_bytes(int n_tiles);
 int ctk_tile_metrics_f32(const float* tiles, int n_tiles, int plane_elems, double* pearson_out, float* rmse_out,
                          double* hist_corr_out, unsigned int* hist_out, void* workspace, size_t workspace_bytes,
                          void* stream);
+/* nmi_out[n] f64 = sklearn.metrics.normalized_mutual_info_score(np.digitize(img0, linspace(min, max, 256)),
+ * np.digitize(img1, ...)) -- test-cross-talk-model.py:71-74,84.  The 256 x 256 contingency table of every tile is built in
+ * the workspace with the exact float32 digitisation rule of NumPy >= 2; MI and entropies in fp64. */
+size_t ctk_tile_nmi_workspace_bytes(int n_tiles);
+int ctk_tile_nmi_f32(const float* tiles, int n_tiles, int plane_elems, double* nmi_out, void* workspace,
+                     size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Parameter re-packing (derived cache; redo after every optimizer step / load_state_dict).

@@ -427,6 +427,60 @@ def hist_correlation(a: np.ndarray, b: np.ndarray) -> float:
     return pearson_f64(h1.astype(np.float64), h2.astype(np.float64))
 
 
+def digitize256_f32(a: np.ndarray) -> np.ndarray:
+    """``np.digitize(plane.flatten(), bins=np.linspace(plane.min(), plane.max(), 256))`` restated for a float32 plane
+    (test-cross-talk-model.py:71-74): label = number of float32 edges ``k * step + min`` (last edge = max) that are <= x,
+    i.e. 1..256.  NumPy >= 2 keeps the edges in float32 (step = float32((max - min) / 255))."""
+    x = np.asarray(a, dtype=np.float32).ravel()
+    lo, hi = x.min(), x.max()
+    step = np.float32((hi - lo) / np.float32(255))
+    edges = (np.arange(256, dtype=np.float32) * step + lo).astype(np.float32)
+    edges[-1] = hi
+    k = np.clip(((x - lo) / step).astype(np.int64) if step > 0 else np.full(x.shape, 255, np.int64), 0, 255)
+    k[edges[k] > x] -= 1
+    up = (k < 255)
+    up[up] &= edges[k[up] + 1] <= x[up]
+    k[up] += 1
+    return k + 1
+
+
+def nmi_from_joint(joint: np.ndarray) -> float:
+    """sklearn.metrics.normalized_mutual_info_score (average_method='arithmetic') from a contingency table:
+    MI = sum_ij n_ij/N (log n_ij - log N - log a_i - log b_j + log A + log B), entropies -sum p (log n - log N), all in
+    float64 with natural logs; 1.0 if both labelings are constant, 0.0 if |MI| < eps (sklearn/metrics/cluster/_supervised.py)."""
+    joint = np.asarray(joint, dtype=np.int64)
+    pi, pj = joint.sum(1), joint.sum(0)
+    if (pi > 0).sum() == 1 and (pj > 0).sum() == 1:
+        return 1.0
+    if (pi > 0).sum() == 1 or (pj > 0).sum() == 1:
+        return 0.0
+    n = float(joint.sum())
+    nzx, nzy = np.nonzero(joint)
+    nz = joint[nzx, nzy].astype(np.float64)
+    outer = pi[nzx].astype(np.int64) * pj[nzy].astype(np.int64)
+    log_outer = -np.log(outer) + math.log(pi.sum()) + math.log(pj.sum())
+    mi = (nz / n) * (np.log(nz) - math.log(n)) + (nz / n) * log_outer
+    mi = np.where(np.abs(mi) < np.finfo(np.float64).eps, 0.0, mi)
+    mi = float(np.clip(mi.sum(), 0.0, None))
+    if abs(mi) < np.finfo(np.float64).eps:
+        return 0.0
+
+    def entropy(c):
+        c = c[c > 0].astype(np.float64)
+        if c.size == 1:
+            return 0.0
+        return float(-np.sum((c / c.sum()) * (np.log(c) - math.log(c.sum()))))
+    return mi / (0.5 * (entropy(pi) + entropy(pj)))
+
+
+def nmi_digitized(a: np.ndarray, b: np.ndarray) -> float:
+    """normalized_mutual_info_score(digitize(img0), digitize(img1)) -- test-cross-talk-model.py:71-74,84."""
+    la, lb = digitize256_f32(a), digitize256_f32(b)
+    joint = np.zeros((256, 256), dtype=np.int64)
+    np.add.at(joint, (la - 1, lb - 1), 1)
+    return nmi_from_joint(joint)
+
+
 def tile_metrics_batch(x: torch.Tensor) -> Dict[str, np.ndarray]:
     """Per-image Pearson r, RMSE and histogram correlation of channel 0 vs channel 1 of an [N,2,H,W] float32 batch."""
     xs = x.detach().cpu().numpy()
@@ -434,6 +488,7 @@ def tile_metrics_batch(x: torch.Tensor) -> Dict[str, np.ndarray]:
     return {"pearson": np.array([pearson_f64(xs[i, 0], xs[i, 1]) for i in range(n)]),
             "rmse": np.array([rmse_f32(xs[i, 0], xs[i, 1]) for i in range(n)]),
             "hist_corr": np.array([hist_correlation(xs[i, 0], xs[i, 1]) for i in range(n)]),
+            "nmi": np.array([nmi_digitized(xs[i, 0], xs[i, 1]) for i in range(n)]),
             "hist": np.stack([np.stack([histogram256_f32(xs[i, 0]), histogram256_f32(xs[i, 1])]) for i in range(n)])
             if n else np.zeros((0, 2, 256), dtype=np.int64)}
 

@@ -134,6 +134,15 @@ def test_tile_metrics_fused(ctk, golden):
     assert np.array_equal(g2["hist"].cpu().numpy().astype(np.int64), r2["hist"])
     np.testing.assert_allclose(g2["hist_corr"].cpu().numpy(), r2["hist_corr"], atol=1e-12)
     assert ctk.tile_metrics(torch.empty(0, 2, 32, 32).cuda())["pearson"].numel() == 0
+    # NMI of the digitised planes (sklearn's formula on NumPy's digitisation): fixture goldens and the oracle restatement
+    nmi = ctk.nmi_per_image(x.cuda()).cpu().numpy()
+    np.testing.assert_allclose(nmi, ref["nmi"], atol=1e-12)
+    np.testing.assert_allclose(nmi[:5], m["normalised"]["nmi"], atol=1e-12)
+    np.testing.assert_allclose(nmi[5:10], m["raw"]["nmi"], atol=1e-12)
+    assert nmi[-1] == 0.0                                                   # one constant plane
+    both_const = torch.full((1, 2, 32, 32), 0.5)
+    assert ctk.nmi_per_image(both_const.cuda()).item() == 1.0
+    np.testing.assert_allclose(ctk.nmi_per_image(rag.cuda()).cpu().numpy(), r2["nmi"], atol=1e-12)
     # same Pearson as the stand-alone kernel
     np.testing.assert_allclose(got["pearson"].cpu().numpy(), ctk.pearson_per_image(x.cuda()).cpu().numpy(), atol=1e-12, equal_nan=True)
 

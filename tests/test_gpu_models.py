@@ -188,6 +188,13 @@ def test_host_scorer_one_shot_and_stream(golden):
     for (a, b), (s, r) in zip(cuts, outs):
         assert torch.equal(s, ref[a:b]) and torch.equal(r, r_ref[a:b])
     assert list(scorer.score_stream([])) == []
+    # every device-computable comparison metric of the reference's evaluate loop in the same call
+    s_all, m_all = ctk.HostScorer(model, slice_tiles=3, metrics="all").score(x.pin_memory())
+    ref_m = orc.tile_metrics_batch(x)
+    assert torch.equal(s_all, ref) and torch.equal(m_all["pearson"], r_ref)
+    np.testing.assert_allclose(m_all["rmse"].numpy(), ref_m["rmse"], rtol=2e-6)
+    np.testing.assert_allclose(m_all["hist_corr"].numpy(), ref_m["hist_corr"], atol=1e-12, equal_nan=True)
+    np.testing.assert_allclose(m_all["nmi"].numpy(), ref_m["nmi"], atol=1e-12)
     with pytest.raises(ctk.CtkError):
         scorer.score(x.cuda())
     model.train()

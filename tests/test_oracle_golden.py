@@ -113,6 +113,7 @@ def test_metrics_restatement_matches_reference_calls(golden):
             assert int((h0 ** 2).sum()) == g["hist0_sum_sq"][j] and int((h1 ** 2).sum()) == g["hist1_sum_sq"][j]
             assert abs(orc.hist_correlation(imgs[j, 0], imgs[j, 1]) - g["hist_corr"][j]) <= 1e-12
             assert abs(orc.rmse_f32(imgs[j, 0], imgs[j, 1]) - g["rmse"][j]) <= 1e-7 * g["rmse"][j]
+            assert abs(orc.nmi_digitized(imgs[j, 0], imgs[j, 1]) - g["nmi"][j]) <= 1e-13
     rng = np.random.default_rng(0)
     awkward = [np.full(4096, 0.3, np.float32), (rng.standard_normal(65536) * 1e-3 + 5).astype(np.float32),
                (rng.random(65536) ** 3 * 7 - 2).astype(np.float32), np.arange(257, dtype=np.float32) / 256,
@@ -120,3 +121,7 @@ def test_metrics_restatement_matches_reference_calls(golden):
     for a in awkward:
         assert np.array_equal(orc.histogram256_f32(a), np.histogram(a, bins=256)[0])
     assert np.isnan(orc.hist_correlation(np.arange(256, dtype=np.float32), np.arange(256, dtype=np.float32)))   # flat histograms
+    for a in awkward[1:]:
+        assert np.array_equal(orc.digitize256_f32(a), np.digitize(a, bins=np.linspace(a.min(), a.max(), 256)))
+    const = np.full(1024, 0.5, np.float32)
+    assert orc.nmi_digitized(const, const) == 1.0 and orc.nmi_digitized(const, awkward[1][:1024]) == 0.0

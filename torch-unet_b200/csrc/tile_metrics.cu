@@ -230,6 +230,117 @@ __global__ void __launch_bounds__(128) tile_hist_corr_kernel(const unsigned int*
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Normalised mutual information of the two planes after np.digitize into 256 levels (test-cross-talk-model.py:71-74,84;
+// sklearn.metrics.normalized_mutual_info_score).  label(x) = number of float32 edges k*step + min (last edge = max) that
+// are <= x, exactly as np.digitize(x, np.linspace(min, max, 256)) computes it in NumPy >= 2.
+struct DigitRule {
+  float lo, hi, step;
+};
+__device__ __forceinline__ DigitRule make_digit_rule(float mn, float mx) {
+  DigitRule d;
+  d.lo = mn; d.hi = mx;
+  d.step = __fdiv_rn(__fsub_rn(mx, mn), 255.0f);
+  return d;
+}
+__device__ __forceinline__ float digit_edge(const DigitRule& d, int k) {
+  return k == 255 ? d.hi : __fadd_rn(__fmul_rn(static_cast<float>(k), d.step), d.lo);
+}
+__device__ __forceinline__ int digit_of(const DigitRule& d, float x) {      // 0-based label (NumPy's minus one)
+  int k = 255;
+  if (d.step > 0.f) {
+    k = static_cast<int>(__fdiv_rn(__fsub_rn(x, d.lo), d.step));
+    k = min(max(k, 0), 255);
+  }
+  if (digit_edge(d, k) > x) k -= 1;
+  if (k < 255 && digit_edge(d, k + 1) <= x) k += 1;
+  return k;
+}
+
+__global__ void __launch_bounds__(kThreads) tile_joint_kernel(const float* __restrict__ tiles, int plane_elems,
+                                                              const float* __restrict__ minmax,
+                                                              unsigned int* __restrict__ joint) {
+  const int tile = blockIdx.x / kSlices;
+  const int slice = blockIdx.x % kSlices;
+  const DigitRule r0 = make_digit_rule(minmax[tile * 4 + 0], minmax[tile * 4 + 1]);
+  const DigitRule r1 = make_digit_rule(minmax[tile * 4 + 2], minmax[tile * 4 + 3]);
+  const float4* p0 = reinterpret_cast<const float4*>(tiles + static_cast<size_t>(tile) * 2 * plane_elems);
+  const float4* p1 = p0 + plane_elems / 4;
+  unsigned int* jt = joint + static_cast<size_t>(tile) * kBins * kBins;
+  const int nvec = plane_elems / 4;
+  const int per_slice = (nvec + kSlices - 1) / kSlices;
+  const int begin = slice * per_slice;
+  const int end = min(nvec, begin + per_slice);
+  for (int i = begin + threadIdx.x; i < end; i += kThreads) {
+    const float4 x = __ldcs(p0 + i), y = __ldcs(p1 + i);
+    atomicAdd(jt + digit_of(r0, x.x) * kBins + digit_of(r1, y.x), 1u);
+    atomicAdd(jt + digit_of(r0, x.y) * kBins + digit_of(r1, y.y), 1u);
+    atomicAdd(jt + digit_of(r0, x.z) * kBins + digit_of(r1, y.z), 1u);
+    atomicAdd(jt + digit_of(r0, x.w) * kBins + digit_of(r1, y.w), 1u);
+  }
+}
+
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0.0;
+  for (int w = 0; w < kThreads / 32; ++w) t += sh[w];
+  return t;
+}
+
+// one CTA per tile: marginals, MI and the two entropies from the 256 x 256 contingency table (fp64, natural logs)
+__global__ void __launch_bounds__(kThreads) tile_nmi_kernel(const unsigned int* __restrict__ joint, int plane_elems,
+                                                            double* __restrict__ out) {
+  __shared__ unsigned int row_sum[kBins], col_sum[kBins];
+  __shared__ double sh[kThreads / 32];
+  const int tile = blockIdx.x;
+  const unsigned int* jt = joint + static_cast<size_t>(tile) * kBins * kBins;
+  for (int i = threadIdx.x; i < kBins; i += kThreads) { row_sum[i] = 0u; col_sum[i] = 0u; }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kBins; i += kThreads) {          // thread i sums row i and column i
+    unsigned int r = 0u, c = 0u;
+    for (int j = 0; j < kBins; ++j) { r += jt[i * kBins + j]; c += jt[j * kBins + i]; }
+    row_sum[i] = r; col_sum[i] = c;
+  }
+  __syncthreads();
+  const double n = static_cast<double>(plane_elems);
+  const double log_n = log(n);
+  double mi = 0.0;
+  for (int idx = threadIdx.x; idx < kBins * kBins; idx += kThreads) {
+    const unsigned int c = jt[idx];
+    if (c == 0u) continue;
+    const int i = idx / kBins, j = idx % kBins;
+    const double nz = static_cast<double>(c);
+    const double outer = static_cast<double>(static_cast<unsigned long long>(row_sum[i]) * col_sum[j]);
+    const double log_outer = -log(outer) + log_n + log_n;
+    double t = (nz / n) * (log(nz) - log_n) + (nz / n) * log_outer;
+    if (fabs(t) < 2.220446049250313e-16) t = 0.0;
+    mi += t;
+  }
+  mi = block_sum(mi, sh);
+  double hr = 0.0, hc = 0.0;
+  int nr = 0, nc = 0;
+  for (int i = threadIdx.x; i < kBins; i += kThreads) {
+    if (row_sum[i]) { const double c = static_cast<double>(row_sum[i]); hr -= (c / n) * (log(c) - log_n); nr = 1; }
+    if (col_sum[i]) { const double c = static_cast<double>(col_sum[i]); hc -= (c / n) * (log(c) - log_n); nc = 1; }
+  }
+  hr = block_sum(hr, sh);
+  hc = block_sum(hc, sh);
+  const int rows_used = __syncthreads_count(nr), cols_used = __syncthreads_count(nc);
+  if (threadIdx.x == 0) {
+    double r;
+    if (rows_used == 1 && cols_used == 1) r = 1.0;                  // both labelings constant
+    else if (rows_used == 1 || cols_used == 1) r = 0.0;
+    else {
+      mi = fmax(mi, 0.0);
+      r = fabs(mi) < 2.220446049250313e-16 ? 0.0 : mi / (0.5 * (hr + hc));
+    }
+    out[tile] = r;
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -261,6 +372,35 @@ int ctk_tile_metrics_f32(const float* tiles, int n_tiles, int plane_elems, doubl
   st = ctk::check_launch();
   if (st != CTK_OK || hist_corr_out == nullptr) return st;
   tile_hist_corr_kernel<<<(n_tiles + 3) / 4, 128, 0, s>>>(hist_out, n_tiles, hist_corr_out);
+  return ctk::check_launch();
+}
+
+size_t ctk_tile_nmi_workspace_bytes(int n_tiles) {
+  if (n_tiles <= 0) return 0;
+  return ctk_tile_metrics_workspace_bytes(n_tiles) + static_cast<size_t>(n_tiles) * kBins * kBins * sizeof(unsigned int);
+}
+
+int ctk_tile_nmi_f32(const float* tiles, int n_tiles, int plane_elems, double* nmi_out, void* workspace,
+                     size_t workspace_bytes, void* stream) {
+  if (n_tiles == 0) return CTK_OK;
+  CTK_REQUIRE(tiles && nmi_out && workspace && n_tiles > 0 && plane_elems > 0 && plane_elems % 4 == 0);
+  CTK_REQUIRE((reinterpret_cast<uintptr_t>(tiles) & 15) == 0 && (reinterpret_cast<uintptr_t>(workspace) & 7) == 0);
+  if (workspace_bytes < ctk_tile_nmi_workspace_bytes(n_tiles)) return CTK_ERR_WORKSPACE;
+  cudaStream_t s = ctk::as_stream(stream);
+  double* partial = static_cast<double*>(workspace);
+  float* minmax = reinterpret_cast<float*>(partial + static_cast<size_t>(n_tiles) * kSlices * kPartial);
+  unsigned int* joint = reinterpret_cast<unsigned int*>(static_cast<char*>(workspace) + ctk_tile_metrics_workspace_bytes(n_tiles));
+  tile_sums_kernel<<<static_cast<unsigned>(n_tiles) * kSlices, kThreads, 0, s>>>(tiles, plane_elems, partial);
+  int st = ctk::check_launch();
+  if (st != CTK_OK) return st;
+  tile_finalize_kernel<<<(n_tiles + 127) / 128, 128, 0, s>>>(partial, n_tiles, plane_elems, nullptr, nullptr, minmax);
+  st = ctk::check_launch();
+  if (st != CTK_OK) return st;
+  CTK_CUDA_TRY(cudaMemsetAsync(joint, 0, sizeof(unsigned int) * kBins * kBins * static_cast<size_t>(n_tiles), s));
+  tile_joint_kernel<<<static_cast<unsigned>(n_tiles) * kSlices, kThreads, 0, s>>>(tiles, plane_elems, minmax, joint);
+  st = ctk::check_launch();
+  if (st != CTK_OK) return st;
+  tile_nmi_kernel<<<static_cast<unsigned>(n_tiles), kThreads, 0, s>>>(joint, plane_elems, nmi_out);
   return ctk::check_launch();
 }
 

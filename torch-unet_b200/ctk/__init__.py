@@ -7,7 +7,7 @@ Everything here drives hand-written sm_100a kernels in libctk.so through the C A
 """
 from ._lib import CtkError, EXPORTED_SYMBOLS, LIB_PATH, load
 from .engine import InferenceEngine
-from .metrics import pearson_per_image, tile_metrics
+from .metrics import nmi_per_image, pearson_per_image, tile_metrics
 from .models import (AdvancedRegressionModel, SimplifiedFeatureExtractionBranch, SimplifiedRegressionHead,
                      SimplifiedTwoBranchRegressionModel, accelerate, set_precision)
 from .optim import Adam, mse_loss
@@ -15,6 +15,6 @@ from .pipeline import HostScorer
 from . import io, parallel
 from .io import prepare_tiles
 
-__all__ = ["CtkError", "EXPORTED_SYMBOLS", "LIB_PATH", "load", "InferenceEngine", "pearson_per_image", "tile_metrics",
+__all__ = ["CtkError", "EXPORTED_SYMBOLS", "LIB_PATH", "load", "InferenceEngine", "pearson_per_image", "tile_metrics", "nmi_per_image",
            "AdvancedRegressionModel", "SimplifiedFeatureExtractionBranch", "SimplifiedRegressionHead",
            "SimplifiedTwoBranchRegressionModel", "accelerate", "set_precision", "Adam", "mse_loss", "HostScorer", "parallel", "io", "prepare_tiles"]

@@ -35,6 +35,24 @@ def pearson_per_image(inputs: torch.Tensor, out: torch.Tensor = None) -> torch.T
     return out
 
 
+def nmi_per_image(inputs: torch.Tensor) -> torch.Tensor:
+    """Normalised mutual information of channel 0 vs channel 1 of every tile after np.digitize into 256 levels
+    (test-cross-talk-model.py:71-74,84).  ``inputs``: [N,2,H,W] float32 CUDA; returns float64 [N]."""
+    _lib.require_device(inputs, torch.float32, "inputs")
+    if inputs.dim() != 4 or inputs.shape[1] != 2:
+        raise _lib.CtkError(f"inputs must be [N,2,H,W], got {tuple(inputs.shape)}")
+    n = inputs.shape[0]
+    out = torch.empty(n, device=inputs.device, dtype=torch.float64)
+    if n == 0:
+        return out
+    lib = _lib.load()
+    ws_bytes = lib.ctk_tile_nmi_workspace_bytes(c_int(n))
+    ws = torch.empty((ws_bytes + 7) // 8, device=inputs.device, dtype=torch.float64)
+    call("ctk_tile_nmi_f32", ptr(inputs), c_int(n), c_int(inputs.shape[2] * inputs.shape[3]), ptr(out), ptr(ws),
+         c_size_t(ws_bytes), stream())
+    return out
+
+
 def tile_metrics(inputs: torch.Tensor, histograms: bool = True) -> dict:
     """Pearson r, RMSE and 256-bin histogram correlation of channel 0 vs channel 1 for every tile of ``inputs``
     ([N,2,H,W] float32, CUDA) in one fused pass -- test-cross-talk-model.py:59-70,79 without the device->host copy of the

@@ -20,12 +20,17 @@ from typing import Iterable, Iterator, Tuple
 import torch
 
 from . import _lib
-from .metrics import pearson_per_image
+from .metrics import nmi_per_image, pearson_per_image, tile_metrics
 from .models import get_engine
 
 
 class HostScorer:
-    def __init__(self, model: torch.nn.Module, slice_tiles: int = 64, device: str = "cuda"):
+    def __init__(self, model: torch.nn.Module, slice_tiles: int = 64, device: str = "cuda", metrics: str = "pearson"):
+        """``metrics``: "pearson" -> results are (scores, r);  "all" -> (scores, {"pearson", "rmse", "hist_corr", "nmi"}),
+        the device-computable comparison metrics of test-cross-talk-model.py:59-84 for every tile."""
+        if metrics not in ("pearson", "all"):
+            raise _lib.CtkError("metrics must be 'pearson' or 'all'")
+        self.metrics = metrics
         self.model = model
         self.slice = slice_tiles
         self.dev = torch.device(device)
@@ -49,8 +54,10 @@ class HostScorer:
                   "x": torch.empty((n, *tiles_host.shape[1:]), device=self.dev, dtype=tiles_host.dtype),
                   "scores": torch.empty(n, 1, device=self.dev, dtype=torch.float32),
                   "r": torch.empty(n, device=self.dev, dtype=torch.float64),
+                  "extra": torch.empty(3, n, device=self.dev, dtype=torch.float64),      # rmse, hist_corr, nmi
                   "scores_h": torch.empty(n, dtype=torch.float32, pin_memory=True),
                   "r_h": torch.empty(n, dtype=torch.float64, pin_memory=True),
+                  "extra_h": torch.empty(3, n, dtype=torch.float64, pin_memory=True),
                   "free": None, "done": None}
             self._slots[i] = sl
         return sl
@@ -83,22 +90,36 @@ class HostScorer:
             if e - done_to < compute_tiles and e < n:
                 continue
             main.wait_event(ev)
-            pearson_per_image(sl["x"][done_to:e], out=sl["r"][done_to:e])
-            engine.forward(sl["x"][done_to:e], out=sl["scores"][done_to:e])
+            part = sl["x"][done_to:e]
+            if self.metrics == "all":
+                m = tile_metrics(part)
+                sl["r"][done_to:e] = m["pearson"]
+                sl["extra"][0, done_to:e] = m["rmse"].double()
+                sl["extra"][1, done_to:e] = m["hist_corr"]
+                sl["extra"][2, done_to:e] = nmi_per_image(part)
+            else:
+                pearson_per_image(part, out=sl["r"][done_to:e])
+            engine.forward(part, out=sl["scores"][done_to:e])
             done_to = e
         sl["free"] = torch.cuda.Event()
         sl["free"].record(main)
         sl["scores_h"].copy_(sl["scores"].flatten(), non_blocking=True)
         sl["r_h"].copy_(sl["r"], non_blocking=True)
+        if self.metrics == "all":
+            sl["extra_h"].copy_(sl["extra"], non_blocking=True)
+        sl["all"] = self.metrics == "all"
         sl["done"] = torch.cuda.Event()
         sl["done"].record(main)
         self.h2d_bytes = tiles_host.numel() * tiles_host.element_size()
-        self.d2h_bytes = n * 4 + n * 8
+        self.d2h_bytes = n * 4 + n * 8 + (3 * n * 8 if self.metrics == "all" else 0)
         return sl
 
     @staticmethod
-    def _finish(sl) -> Tuple[torch.Tensor, torch.Tensor]:
+    def _finish(sl):
         sl["done"].synchronize()
+        if sl["all"]:
+            ex = sl["extra_h"].clone()
+            return sl["scores_h"].clone(), {"pearson": sl["r_h"].clone(), "rmse": ex[0].float(), "hist_corr": ex[1], "nmi": ex[2]}
         return sl["scores_h"].clone(), sl["r_h"].clone()
 
     # ------------------------------------------------------------------ public API
