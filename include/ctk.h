@@ -289,6 +289,8 @@ int ctk_conv_first_wgrad(const void* dy_bf16, const float* x, int n, int c_total
 int ctk_feat_transpose_bf16(const void* feat_bf16, int n, int hw, int channels, void* out_bf16, int ld, void* stream);
 int ctk_pack_fc1_weight_t_bf16(const float* w, int out_features, int channels, int hw, void* w_t_bf16, void* stream);
 int ctk_gemm_bf16_out_bf16(const void* a_bf16, const void* b_bf16, int M, int N, int K, void* c_bf16, void* stream);
+/* same product with B given as [K][N] (N contiguous): FC1's dX reads the forward pass's packed weight [f1][HW*C] directly */
+int ctk_gemm_bf16_bt_out_bf16(const void* a_bf16, const void* b_kn_bf16, int M, int N, int K, void* c_bf16, void* stream);
 
 /* Small fp32 building blocks of the train-mode head and its backward (regression_model.py:37-46,
  * two_branch_regression.py:43-53,100).

@@ -196,7 +196,13 @@ def test_fc1_training_gemms(L):
     dw = torch.empty(1, O, C * hw, device="cuda")
     L.call("ctk_gemm_bf16_splitk", L.ptr(dzT), L.ptr(featT), c_int(O), c_int(C * hw), c_int(64), c_int(1), L.ptr(dw),
            L.stream())
+    # the same dX product reading the forward-layout packed weight [O][hw*C] as an MN-major operand
+    wP = torch.empty(O, hw * C, device="cuda", dtype=torch.bfloat16)
+    L.call("ctk_pack_fc1_weight_bf16", L.ptr(wd), c_int(O), c_int(C), c_int(hw), L.ptr(wP), L.stream())
+    dfeat2 = torch.empty(npad, hw * C, device="cuda", dtype=torch.bfloat16)
+    L.call("ctk_gemm_bf16_bt_out_bf16", L.ptr(dzd), L.ptr(wP), c_int(npad), c_int(hw * C), c_int(O), L.ptr(dfeat2), L.stream())
     torch.cuda.synchronize()
+    assert torch.equal(dfeat2[:n], dfeat[:n])
     assert rel_l2(featT[:, :n].float().cpu().t(), feat_ref) == 0.0
     assert featT[:, n:].abs().max().item() == 0.0
     assert rel_l2(dfeat[:n].float().cpu().reshape(n, hw, C), dfeat_ref) < 4e-3

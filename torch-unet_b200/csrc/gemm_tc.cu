@@ -27,7 +27,23 @@ struct GemmSmem {
   uint32_t tmem_base;
 };
 
-template <int kStages>
+// kBMn: B is given as [K][N] (N contiguous) instead of [N][K]: consumed as an MN-major 128B-swizzled operand -- two TMA
+// boxes of 64 N-elements x 64 K-rows per stage (LBO = 8 KiB between them, SBO = 1 KiB between 8-row K atoms), 2 KiB per
+// UMMA_K step.  This is how FC1's dX GEMM reads the forward pass's packed weight without a transposed copy.
+__host__ __device__ constexpr uint32_t gemm_idesc(bool b_mn) {
+  return umma_idesc_bf16_f32(kBM, kBN) | (b_mn ? (1u << 16) : 0u);
+}
+__device__ __forceinline__ uint64_t gemm_desc_mn_sw128(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((addr >> 4) & 0x3fff);
+  d |= static_cast<uint64_t>((lbo >> 4) & 0x3fff) << 16;
+  d |= static_cast<uint64_t>((sbo >> 4) & 0x3fff) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+template <int kStages, bool kBMn>
 __global__ void __launch_bounds__(kThreads, kStages <= 2 ? 3 : 1)
 gemm_splitk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, int M, int N,
                    int k_per_split, float* __restrict__ partial, __nv_bfloat16* __restrict__ out_bf16) {
@@ -59,11 +75,16 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
       mbar_arrive_expect_tx(&sl->full[stage], kStageBytes);
       uint8_t* a_dst = smem + stage * kStageBytes;
       tma_load_2d(a_dst, &tm_a, &sl->full[stage], k_begin + i * kBK, m0);
-      tma_load_2d(a_dst + kBM * kBK * 2, &tm_b, &sl->full[stage], k_begin + i * kBK, n0);
+      if constexpr (kBMn) {
+        tma_load_2d(a_dst + kBM * kBK * 2, &tm_b, &sl->full[stage], n0, k_begin + i * kBK);
+        tma_load_2d(a_dst + kBM * kBK * 2 + 64 * kBK * 2, &tm_b, &sl->full[stage], n0 + 64, k_begin + i * kBK);
+      } else {
+        tma_load_2d(a_dst + kBM * kBK * 2, &tm_b, &sl->full[stage], k_begin + i * kBK, n0);
+      }
       if (++stage == kStages) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1 && lane == 0) {
-    constexpr uint32_t idesc = umma_idesc_bf16_f32(kBM, kBN);
+    constexpr uint32_t idesc = gemm_idesc(kBMn);
     int stage = 0, phase = 0;
     for (int i = 0; i < k_iters; ++i) {
       mbar_wait(&sl->full[stage], phase);
@@ -72,8 +93,9 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
       const uint32_t b_base = a_base + kBM * kBK * 2;
 #pragma unroll
       for (int s = 0; s < kBK / 16; ++s) {
-        umma_bf16(tmem_base, umma_smem_desc_sw128(a_base + s * 32, 1024, 0),
-                  umma_smem_desc_sw128(b_base + s * 32, 1024, 0), idesc, (i | s) != 0 ? 1u : 0u);
+        const uint64_t bdesc = kBMn ? gemm_desc_mn_sw128(b_base + s * 2048, 64 * kBK * 2, 1024)
+                                    : umma_smem_desc_sw128(b_base + s * 32, 1024, 0);
+        umma_bf16(tmem_base, umma_smem_desc_sw128(a_base + s * 32, 1024, 0), bdesc, idesc, (i | s) != 0 ? 1u : 0u);
       }
       umma_commit(&sl->empty[stage]);
       if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -117,8 +139,18 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
 
 }  // namespace
 
+template <int kStages, bool kBMn>
+static int gemm_run(const CUtensorMap& tm_a, const CUtensorMap& tm_b, dim3 grid, int M, int N, int k_per_split, float* partial,
+                    void* out_bf16, void* stream) {
+  auto kernel = gemm_splitk_kernel<kStages, kBMn>;
+  CTK_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<kStages>()));
+  kernel<<<grid, kThreads, smem_bytes<kStages>(), ctk::as_stream(stream)>>>(tm_a, tm_b, M, N, k_per_split, partial,
+                                                                           static_cast<__nv_bfloat16*>(out_bf16));
+  return ctk::check_launch();
+}
+
 static int gemm_launch(const void* a_bf16, const void* b_bf16, int M, int N, int K, int splits, float* partial,
-                       void* out_bf16, void* stream) {
+                       void* out_bf16, void* stream, bool b_mn = false) {
   CTK_REQUIRE(a_bf16 && b_bf16 && (partial != nullptr) != (out_bf16 != nullptr) && M > 0 && N > 0 && K > 0 && splits > 0);
   CTK_REQUIRE(M % kBM == 0 && N % kBN == 0 && K % (kBK * splits) == 0 && splits <= 65535 && N / kBN <= 65535);
   CTK_REQUIRE(out_bf16 == nullptr || splits == 1);
@@ -132,23 +164,24 @@ static int gemm_launch(const void* a_bf16, const void* b_bf16, int M, int N, int
     int st = ctk::encode_tmap_bf16_sw128(&tm_a, a_bf16, 2, dims, strides, box);
     if (st != CTK_OK) return st;
   }
-  {
+  if (b_mn) {
+    const uint64_t dims[2] = {static_cast<uint64_t>(N), static_cast<uint64_t>(K)};
+    const uint64_t strides[1] = {static_cast<uint64_t>(N) * 2};
+    const uint32_t box_mn[2] = {64, kBK};
+    int st = ctk::encode_tmap_bf16_sw128(&tm_b, b_bf16, 2, dims, strides, box_mn);
+    if (st != CTK_OK) return st;
+  } else {
     const uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
     const uint64_t strides[1] = {static_cast<uint64_t>(K) * 2};
     int st = ctk::encode_tmap_bf16_sw128(&tm_b, b_bf16, 2, dims, strides, box);
     if (st != CTK_OK) return st;
   }
   dim3 grid(M / kBM, N / kBN, splits);
-  if (K / splits / kBK <= 8) {
-    CTK_CUDA_TRY(cudaFuncSetAttribute(gemm_splitk_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<2>()));
-    gemm_splitk_kernel<2><<<grid, kThreads, smem_bytes<2>(), ctk::as_stream(stream)>>>(
-        tm_a, tm_b, M, N, K / splits, partial, static_cast<__nv_bfloat16*>(out_bf16));
-  } else {
-    CTK_CUDA_TRY(cudaFuncSetAttribute(gemm_splitk_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<6>()));
-    gemm_splitk_kernel<6><<<grid, kThreads, smem_bytes<6>(), ctk::as_stream(stream)>>>(
-        tm_a, tm_b, M, N, K / splits, partial, static_cast<__nv_bfloat16*>(out_bf16));
-  }
-  return ctk::check_launch();
+  const bool short_k = K / splits / kBK <= 8;
+  if (b_mn) return short_k ? gemm_run<2, true>(tm_a, tm_b, grid, M, N, K / splits, partial, out_bf16, stream)
+                           : gemm_run<6, true>(tm_a, tm_b, grid, M, N, K / splits, partial, out_bf16, stream);
+  return short_k ? gemm_run<2, false>(tm_a, tm_b, grid, M, N, K / splits, partial, out_bf16, stream)
+                 : gemm_run<6, false>(tm_a, tm_b, grid, M, N, K / splits, partial, out_bf16, stream);
 }
 
 extern "C" int ctk_gemm_bf16_splitk(const void* a_bf16, const void* b_bf16, int M, int N, int K, int splits,
@@ -159,4 +192,10 @@ extern "C" int ctk_gemm_bf16_splitk(const void* a_bf16, const void* b_bf16, int 
 extern "C" int ctk_gemm_bf16_out_bf16(const void* a_bf16, const void* b_bf16, int M, int N, int K, void* c_bf16,
                                       void* stream) {
   return gemm_launch(a_bf16, b_bf16, M, N, K, 1, nullptr, c_bf16, stream);
+}
+
+/* C[M,N] (bf16) = A[M,K] * B[K,N]: B row-major with N contiguous (an MN-major tensor-core operand, no transposed copy). */
+extern "C" int ctk_gemm_bf16_bt_out_bf16(const void* a_bf16, const void* b_kn_bf16, int M, int N, int K, void* c_bf16,
+                                         void* stream) {
+  return gemm_launch(a_bf16, b_kn_bf16, M, N, K, 1, nullptr, c_bf16, stream, true);
 }

@@ -107,27 +107,64 @@ __global__ void pack_first_kernel(const float* __restrict__ w, const float* __re
   out[i] = scale ? w[i] * scale[i / k] : w[i];
 }
 
-// out[o][p*C + c] = w[o][c*HW + p]; one block per (row o, 32-pixel x 32-channel tile), transposed through smem
-__global__ void pack_fc1_kernel(const float* __restrict__ w, int channels, int hw, __nv_bfloat16* __restrict__ out,
-                                __nv_bfloat16* __restrict__ out_lo) {
-  __shared__ float tile[32][33];
+// out[o][p*C + c] = w[o][c*HW + p]; one block per (row o, 64-pixel x 64-channel tile), transposed through smem:
+// 256-byte fp32 row reads (float4 per thread), 128-byte bf16 row writes (four channels per thread)
+__global__ void __launch_bounds__(256)
+pack_fc1_kernel(const float* __restrict__ w, int channels, int hw, __nv_bfloat16* __restrict__ out,
+                __nv_bfloat16* __restrict__ out_lo) {
+  __shared__ float tile[64][65];                               // [channel][pixel]
   const size_t row = blockIdx.z;
-  const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  const int c0 = blockIdx.y * 64, p0 = blockIdx.x * 64;
   const float* src = w + row * static_cast<size_t>(channels) * hw;
   __nv_bfloat16* dst = out + row * static_cast<size_t>(channels) * hw;
   __nv_bfloat16* dst_lo = out_lo ? out_lo + row * static_cast<size_t>(channels) * hw : nullptr;
-  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
-    const int c = c0 + j, p = p0 + threadIdx.x;
-    tile[j][threadIdx.x] = (c < channels && p < hw) ? src[static_cast<size_t>(c) * hw + p] : 0.f;
+  const int t = threadIdx.x;
+  const bool vec = (hw % 4 == 0) && p0 + 64 <= hw;
+#pragma unroll
+  for (int pass = 0; pass < 4; ++pass) {
+    const int j = pass * 16 + (t >> 4), q = (t & 15) * 4;      // channel row j, pixels q..q+3
+    const int c = c0 + j;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < channels) {
+      if (vec) {
+        v = __ldcs(reinterpret_cast<const float4*>(src + static_cast<size_t>(c) * hw + p0 + q));
+      } else {
+        const float* s0 = src + static_cast<size_t>(c) * hw;
+        if (p0 + q < hw) v.x = s0[p0 + q];
+        if (p0 + q + 1 < hw) v.y = s0[p0 + q + 1];
+        if (p0 + q + 2 < hw) v.z = s0[p0 + q + 2];
+        if (p0 + q + 3 < hw) v.w = s0[p0 + q + 3];
+      }
+    }
+    tile[j][q] = v.x; tile[j][q + 1] = v.y; tile[j][q + 2] = v.z; tile[j][q + 3] = v.w;
   }
   __syncthreads();
-  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
-    const int p = p0 + j, c = c0 + threadIdx.x;
-    if (c < channels && p < hw) {
-      const float v = tile[threadIdx.x][j];
-      const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-      dst[static_cast<size_t>(p) * channels + c] = hi;
-      if (dst_lo) dst_lo[static_cast<size_t>(p) * channels + c] = __float2bfloat16_rn(v - __bfloat162float(hi));
+  const bool cvec = (channels % 4 == 0) && c0 + 64 <= channels;
+#pragma unroll
+  for (int pass = 0; pass < 4; ++pass) {
+    const int j = pass * 16 + (t >> 4), q = (t & 15) * 4;      // pixel row j, channels q..q+3
+    const int p = p0 + j;
+    if (p >= hw) continue;
+    float v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = tile[q + k][j];
+    __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      hi[k] = __float2bfloat16_rn(v[k]);
+      lo[k] = __float2bfloat16_rn(v[k] - __bfloat162float(hi[k]));
+    }
+    const size_t o = static_cast<size_t>(p) * channels + c0 + q;
+    if (cvec) {
+      *reinterpret_cast<uint2*>(dst + o) = *reinterpret_cast<const uint2*>(hi);
+      if (dst_lo) *reinterpret_cast<uint2*>(dst_lo + o) = *reinterpret_cast<const uint2*>(lo);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (c0 + q + k < channels) {
+          dst[o + k] = hi[k];
+          if (dst_lo) dst_lo[o + k] = lo[k];
+        }
     }
   }
 }
@@ -188,18 +225,18 @@ int ctk_pack_first_weight(const float* w, const float* scale, int cout, int cin,
 int ctk_pack_fc1_weight_bf16(const float* w, int out_features, int channels, int hw, void* w_packed_bf16,
                              void* stream) {
   CTK_REQUIRE(w && w_packed_bf16 && out_features > 0 && out_features <= 65535 && channels > 0 && hw > 0);
-  dim3 grid((hw + 31) / 32, (channels + 31) / 32, out_features);
-  pack_fc1_kernel<<<grid, dim3(32, 8), 0, ctk::as_stream(stream)>>>(w, channels, hw,
-                                                                    static_cast<__nv_bfloat16*>(w_packed_bf16), nullptr);
+  dim3 grid((hw + 63) / 64, (channels + 63) / 64, out_features);
+  pack_fc1_kernel<<<grid, 256, 0, ctk::as_stream(stream)>>>(w, channels, hw, static_cast<__nv_bfloat16*>(w_packed_bf16),
+                                                            nullptr);
   return ctk::check_launch();
 }
 
 int ctk_pack_fc1_weight_split_bf16(const float* w, int out_features, int channels, int hw, void* w_hi_bf16,
                                    void* w_lo_bf16, void* stream) {
   CTK_REQUIRE(w && w_hi_bf16 && w_lo_bf16 && out_features > 0 && out_features <= 65535 && channels > 0 && hw > 0);
-  dim3 grid((hw + 31) / 32, (channels + 31) / 32, out_features);
-  pack_fc1_kernel<<<grid, dim3(32, 8), 0, ctk::as_stream(stream)>>>(
-      w, channels, hw, static_cast<__nv_bfloat16*>(w_hi_bf16), static_cast<__nv_bfloat16*>(w_lo_bf16));
+  dim3 grid((hw + 63) / 64, (channels + 63) / 64, out_features);
+  pack_fc1_kernel<<<grid, 256, 0, ctk::as_stream(stream)>>>(w, channels, hw, static_cast<__nv_bfloat16*>(w_hi_bf16),
+                                                            static_cast<__nv_bfloat16*>(w_lo_bf16));
   return ctk::check_launch();
 }
 

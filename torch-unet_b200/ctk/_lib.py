@@ -90,6 +90,7 @@ _SIGNATURES = {
     "ctk_feat_transpose_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     "ctk_pack_fc1_weight_t_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "ctk_gemm_bf16_out_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "ctk_gemm_bf16_bt_out_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "ctk_colstat": (c_int, [c_void_p, c_int, c_longlong, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "ctk_bn1d_act_drop_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_int, c_int, c_void_p,
                                       c_void_p]),
@@ -149,7 +150,7 @@ KERNELS_PER_CALL = {"ctk_pearson_f32": 2, "ctk_tile_metrics_f32": 4, "ctk_tile_n
                     "ctk_bn_finalize": 1, "ctk_bn_finalize_moments": 1, "ctk_first_patch_gram": 1,
                     "ctk_first_moments": 1, "ctk_first_wgrad_codes": 1, "ctk_first_wgrad_finalize": 1, "ctk_bn_act_pool_fwd": 1, "ctk_bn_bwd_reduce": 1, "ctk_bn_bwd_reduce_pooled": 1, "ctk_bn_bwd_apply": 1,
                     "ctk_conv3x3_wgrad_tc": 1, "ctk_conv_first_wgrad": 1, "ctk_feat_transpose_bf16": 1,
-                    "ctk_pack_fc1_weight_t_bf16": 1, "ctk_gemm_bf16_out_bf16": 1, "ctk_colstat": 1,
+                    "ctk_pack_fc1_weight_t_bf16": 1, "ctk_gemm_bf16_out_bf16": 1, "ctk_gemm_bf16_bt_out_bf16": 1, "ctk_colstat": 1,
                     "ctk_bn1d_act_drop_fwd": 1, "ctk_sgemm_strided": 1, "ctk_head_out_fwd": 1, "ctk_head_out_bwd": 1,
                     "ctk_bn1d_bwd_reduce": 1, "ctk_bn1d_bwd_apply": 1}
 launch_count = 0

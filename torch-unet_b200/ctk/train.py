@@ -207,7 +207,7 @@ class TrainEngine:
         out = self._new((n, 1), torch.float32, dev)
         call("ctk_head_out_fwd", ptr(a2), ptr(fc3.weight), ptr(fc3.bias), c_int(n), c_int(f2), c_int(self.sigmoid_half),
              ptr(out), stream())
-        sv.update(z1=z1, bn1=bn1, a1=a1, z2=z2, bn2=bn2, a2=a2, out=out, masks=masks)
+        sv.update(z1=z1, bn1=bn1, a1=a1, z2=z2, bn2=bn2, a2=a2, out=out, masks=masks, w1p=w1p)
         self._saved = sv
         return out
 
@@ -298,12 +298,10 @@ class TrainEngine:
              meta={"flops": 2.0 * f1 * K * k_pad})
         done(fc1.weight, dw1)
         del featT
-        w1t = self._new((K, f1), torch.bfloat16, dev)
-        call("ctk_pack_fc1_weight_t_bf16", ptr(fc1.weight), c_int(f1), c_int(self.feat_channels), c_int(hw), ptr(w1t), stream())
+        # dfeat = dZ1 * W1 with the forward pass's packed weight [f1][HW*C] as an MN-major operand (no transposed copy)
         dfeat = self._new((m_pad, hf, wf, self.feat_channels), torch.bfloat16, dev)
-        call("ctk_gemm_bf16_out_bf16", ptr(dz1_bf), ptr(w1t), c_int(m_pad), c_int(K), c_int(f1), ptr(dfeat), stream(),
+        call("ctk_gemm_bf16_bt_out_bf16", ptr(dz1_bf), ptr(sv["w1p"]), c_int(m_pad), c_int(K), c_int(f1), ptr(dfeat), stream(),
              meta={"flops": 2.0 * m_pad * f1 * K})
-        del w1t
         # ---- conv stacks, last block first
         x = sv["x"]
         for entry in sv["blocks"]:
