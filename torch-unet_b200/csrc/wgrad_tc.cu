@@ -1,15 +1,21 @@
 // Weight gradient of the 3x3 convolutions on tcgen05 (replaces the wgrad half of aten::convolution_backward for
 // nn.Conv2d at /root/reference/regression_model.py:23 and two_branch_regression.py:16,22,28):
 //   dW[co][ci][ky][kx] = sum_{n,y,x} dY[n,y,x,co] * X[n, y+ky-1, x+kx-1, ci]
-// GEMM view per CTA: D[co (M=128), ci (N<=128)] for the three taps of one kernel row ky, reduced over K = pixels.
-// Both operands are NHWC, i.e. contiguous along their M/N dimension: they are consumed as MN-major 128B-swizzled
-// tiles exactly as TMA lands them (one 128-byte row of 64 channels per pixel, 8-pixel swizzle atoms):
+// GEMM view per CTA: D[co (M = 128), (ky, ci) (N = 3 x 64 = 192)] for one or two kernel columns kx, reduced over
+// K = pixels.  Both operands are NHWC, i.e. contiguous along their M/N dimension: they are consumed as MN-major
+// 128B-swizzled tiles exactly as TMA lands them (one 128-byte row of 64 channels per pixel, 8-pixel swizzle atoms):
 //   A = dY patch  : 16x8 pixels x 128 co  -> two boxes {64 co, 8, 16}; K atom = one image row of the patch (SBO 1024),
 //                   second 64-co block at LBO = 16 KiB
-//   B = X halo    : 16 rows x 10 columns x nci ci for row offset ky; the three taps kx are three shifted views of
-//                   it (start (2*ks*10 + kx) rows in, SBO = 1280 = one halo row), second ci block at LBO = 20 KiB
-// A CTA owns (co block, ci block, ky, slice) and walks every `slices`-th patch, accumulating 3 x nci fp32 columns in
-// TMEM with no epilogue in between; at the end the accumulators are added to dW (reference layout) with atomics.
+//   B = X halo    : 18 rows x 10 columns x 64 ci, loaded ONCE per patch.  The tap (ky, kx) is the view that starts
+//                   (ky*10 + kx) halo pixels in; consecutive K atoms (image rows) are SBO = 1280 B apart, and so are the
+//                   three ky views -- which makes them the three 64-element "N blocks" of one operand with LBO = 1280:
+//                   a single MMA covers all three kernel rows (N = 192).
+// With N = 192 an MMA reads 4 KB of A and 6 KB of B from shared memory per 96 clocks (107 B/clk against the 128 B/clk
+// port; the previous N = 64 / 128 tiles needed 192 / 128 B/clk plus the TMA writes and sat at 44 / 64 % tensor activity),
+// and a patch costs 55 KB of L2 traffic for 9 taps instead of 52-72 KB for 3.
+// A CTA owns (co block, 64-ci block, kx group, slice): kx group 0 = columns {0, 1} (384 TMEM columns), group 1 = column 2
+// (192 columns, half the work, so it gets half as many slices); it walks every `slices`-th patch, accumulating in TMEM
+// with no epilogue in between; at the end the accumulators are added to dW (reference layout) with atomics.
 #include "ctk_common.h"
 #include "ctk_ptx.cuh"
 
@@ -19,21 +25,24 @@ namespace {
 
 using namespace ctk;
 
-constexpr int kTileH = 16, kTileW = 8, kHaloW = 10;
+constexpr int kTileH = 16, kTileW = 8, kHaloW = 10, kHaloH = kTileH + 2;
 constexpr int kThreads = 192;                 // warp 0 = TMA producer, warp 1 = MMA issuer + TMEM, warps 2-5 = epilogue
 constexpr int kABlockBytes = 128 * 128;       // one 64-channel block of the dY patch
-constexpr int kBBlockBytes = kTileH * kHaloW * 128;   // one 64-channel block of the X halo rows (20480)
+constexpr int kBBytes = kHaloH * kHaloW * 128;                       // 23040: the 64-channel X halo
+constexpr int kStageBytes = 2 * kABlockBytes + (kBBytes + 1023) / 1024 * 1024;   // 56320
+constexpr int kStages = 3;
 constexpr int kTmemCols = 512;
+constexpr int kN = 192;                       // (ky, ci) columns per kernel column kx
 
 struct WgradParams {
-  int n_img, H, W, cin, cout, nci;            // nci = ci columns per CTA (64 or 128)
+  int n_img, H, W, cin, cout;
   int tiles_x, tiles_y, total_tiles;
-  int co_blocks, ci_blocks, slices;
+  int co_blocks, ci_blocks, slices_a, slices_b;   // slices of kx group 0 / 1
   float* dw;                                  // [cout][cin][3][3] fp32, pre-zeroed
 };
 
 struct WgradSmem {
-  uint64_t full[4], empty[4], done;
+  uint64_t full[kStages], empty[kStages], done;
   uint32_t tmem_base;
 };
 
@@ -52,23 +61,24 @@ __device__ __forceinline__ uint64_t desc_mn_sw128(uint32_t addr, uint32_t lbo, u
   return d;
 }
 
-template <int kStages>
 __global__ void __launch_bounds__(kThreads, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ CUtensorMap tm_x,
                 const WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int b_blocks = p.nci / 64;
-  const int stage_bytes = 2 * kABlockBytes + b_blocks * kBBlockBytes;       // multiple of 1024
-  WgradSmem* sl = reinterpret_cast<WgradSmem*>(smem + kStages * stage_bytes);
+  WgradSmem* sl = reinterpret_cast<WgradSmem*>(smem + kStages * kStageBytes);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  // unit decode: blockIdx.x = ((co_blk * ci_blocks + ci_blk) * 3 + ky) * slices + slice
-  int u = blockIdx.x;
-  const int slice = u % p.slices; u /= p.slices;
-  const int ky = u % 3; u /= 3;
-  const int ci_blk = u % p.ci_blocks;
-  const int co_blk = u / p.ci_blocks;
+  // unit decode: blockIdx.x = (co_blk * ci_blocks + ci_blk) * (slices_a + slices_b) + s;  s < slices_a -> kx group 0
+  const int per_pair = p.slices_a + p.slices_b;
+  const int pair = blockIdx.x / per_pair;
+  const int s_idx = blockIdx.x - pair * per_pair;
+  const int group = s_idx < p.slices_a ? 0 : 1;
+  const int slice = group == 0 ? s_idx : s_idx - p.slices_a;
+  const int slices = group == 0 ? p.slices_a : p.slices_b;
+  const int kx0 = group == 0 ? 0 : 2, nkx = group == 0 ? 2 : 1;
+  const int ci_blk = pair % p.ci_blocks;
+  const int co_blk = pair / p.ci_blocks;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStages; ++i) { mbar_init(&sl->full[i], 1); mbar_init(&sl->empty[i], 1); }
@@ -85,43 +95,40 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant
 
   if (warp == 0) {
     int stage = 0, phase = 0;
-    for (int tile = slice; tile < p.total_tiles; tile += p.slices) {
+    for (int tile = slice; tile < p.total_tiles; tile += slices) {
       const int tx = tile % p.tiles_x;
       const int ty = (tile / p.tiles_x) % p.tiles_y;
       const int img = tile / (p.tiles_x * p.tiles_y);
       mbar_wait(&sl->empty[stage], phase ^ 1);
       if (elect_one()) {
-        uint8_t* dst = smem + stage * stage_bytes;
-        mbar_arrive_expect_tx(&sl->full[stage], static_cast<uint32_t>(stage_bytes));
+        uint8_t* dst = smem + stage * kStageBytes;
+        mbar_arrive_expect_tx(&sl->full[stage], static_cast<uint32_t>(2 * kABlockBytes + kBBytes));
         for (int b = 0; b < 2; ++b)
           tma_load_4d(dst + b * kABlockBytes, &tm_dy, &sl->full[stage], co_blk * 128 + b * 64, tx * kTileW,
                       ty * kTileH, img);
-        for (int b = 0; b < b_blocks; ++b)
-          tma_load_4d(dst + 2 * kABlockBytes + b * kBBlockBytes, &tm_x, &sl->full[stage], ci_blk * p.nci + b * 64,
-                      tx * kTileW - 1, ty * kTileH + ky - 1, img);
+        tma_load_4d(dst + 2 * kABlockBytes, &tm_x, &sl->full[stage], ci_blk * 64, tx * kTileW - 1, ty * kTileH - 1, img);
       }
       __syncwarp();
       if (++stage == kStages) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1) {
-    const uint32_t idesc = idesc_mn(128, static_cast<uint32_t>(p.nci));
+    constexpr uint32_t idesc = idesc_mn(128, kN);
     const uint64_t adesc0 = desc_mn_sw128(0, kABlockBytes, 1024);
-    const uint64_t bdesc0 = desc_mn_sw128(0, kBBlockBytes, kHaloW * 128);
+    const uint64_t bdesc0 = desc_mn_sw128(0, kHaloW * 128, kHaloW * 128);   // N blocks = ky views, K atoms = image rows
     int stage = 0, phase = 0;
     bool first = true;
-    for (int tile = slice; tile < p.total_tiles; tile += p.slices) {
+    for (int tile = slice; tile < p.total_tiles; tile += slices) {
       mbar_wait(&sl->full[stage], phase);
       tc_fence_after();
-      const uint32_t a_base = smem_u32(smem + stage * stage_bytes);
-      const uint32_t b_base = a_base + 2 * kABlockBytes;
+      const uint32_t a_base = smem_u32(smem + stage * kStageBytes);
+      const uint64_t adesc_s = adesc0 | static_cast<uint64_t>(a_base >> 4);
+      const uint64_t bdesc_s = bdesc0 | static_cast<uint64_t>((a_base + 2 * kABlockBytes + kx0 * 128) >> 4);
       if (elect_one()) {
-#pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
+        for (int j = 0; j < nkx; ++j) {
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks) {                       // 16 pixels = image rows 2ks, 2ks+1 of the patch
-            const uint64_t adesc = adesc0 | static_cast<uint64_t>((a_base + ks * 2048) >> 4);
-            const uint64_t bdesc = bdesc0 | static_cast<uint64_t>((b_base + (ks * 2 * kHaloW + kx) * 128) >> 4);
-            umma_bf16(tmem_base + static_cast<uint32_t>(kx * p.nci), adesc, bdesc, idesc, (first && ks == 0) ? 0u : 1u);
+            umma_bf16(tmem_base + static_cast<uint32_t>(j * kN), adesc_s + (ks * 2048) / 16,
+                      bdesc_s + ((ks * 2 * kHaloW + j) * 128) / 16, idesc, (first && ks == 0) ? 0u : 1u);
           }
         }
         umma_commit(&sl->empty[stage]);
@@ -140,12 +147,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant
     if (any) {
       mbar_wait(&sl->done, 0);
       tc_fence_after();
-      for (int kx = 0; kx < 3; ++kx) {
-        for (int cb = 0; cb < p.nci / 32; ++cb) {
+      for (int j = 0; j < nkx; ++j) {
+        for (int cb = 0; cb < kN / 32; ++cb) {                   // column cb*32 + i = (ky = cb / 2, ci = (cb % 2) * 32 + i)
           uint32_t v[32];
-          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + kx * p.nci + cb * 32, v);
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + j * kN + cb * 32, v);
           tmem_ld_wait();
-          float* dst = p.dw + (static_cast<size_t>(co) * p.cin + ci_blk * p.nci + cb * 32) * 9 + ky * 3 + kx;
+          const int ky = cb >> 1;
+          float* dst = p.dw + (static_cast<size_t>(co) * p.cin + ci_blk * 64 + (cb & 1) * 32) * 9 + ky * 3 + kx0 + j;
 #pragma unroll
           for (int i = 0; i < 32; ++i) atomicAdd(dst + i * 9, __uint_as_float(v[i]));
         }
@@ -245,16 +253,18 @@ int ctk_conv3x3_wgrad_tc(const void* dy_bf16, const void* x_bf16, int n, int H, 
   CTK_CUDA_TRY(cudaMemsetAsync(dw, 0, sizeof(float) * 9 * cin * cout, s));
   WgradParams p = {};
   p.n_img = n; p.H = H; p.W = W; p.cin = cin; p.cout = cout;
-  p.nci = cin % 128 == 0 ? 128 : 64;
   p.tiles_x = W / kTileW;
   p.tiles_y = (H + kTileH - 1) / kTileH;
   const long long tiles = static_cast<long long>(n) * p.tiles_x * p.tiles_y;
   CTK_REQUIRE(tiles < (1ll << 30));
   p.total_tiles = static_cast<int>(tiles);
   p.co_blocks = cout / 128;
-  p.ci_blocks = cin / p.nci;
-  const int units = p.co_blocks * p.ci_blocks * 3;
-  p.slices = std::max(1, std::min(p.total_tiles, (2 * ctk::num_sms()) / units));
+  p.ci_blocks = cin / 64;
+  const int pairs = p.co_blocks * p.ci_blocks;
+  // kx group 0 does two kernel columns per patch, group 1 one: twice as many slices for group 0 balances the CTAs
+  const int s_unit = std::max(1, std::min(p.total_tiles / 2, (2 * ctk::num_sms()) / (3 * pairs)));
+  p.slices_a = std::min(p.total_tiles, 2 * s_unit);
+  p.slices_b = std::min(p.total_tiles, s_unit);
   p.dw = dw;
 
   CUtensorMap tm_dy, tm_x;
@@ -272,23 +282,14 @@ int ctk_conv3x3_wgrad_tc(const void* dy_bf16, const void* x_bf16, int n, int H, 
                               static_cast<uint64_t>(n)};
     const uint64_t strides[3] = {static_cast<uint64_t>(cin) * 2, static_cast<uint64_t>(W) * cin * 2,
                                  static_cast<uint64_t>(H) * W * cin * 2};
-    const uint32_t box[4] = {64, kHaloW, kTileH, 1};
+    const uint32_t box[4] = {64, kHaloW, kHaloH, 1};
     int st = ctk::encode_tmap_bf16_sw128(&tm_x, x_bf16, 4, dims, strides, box);
     if (st != CTK_OK) return st;
   }
-  const int stage_bytes = 2 * kABlockBytes + (p.nci / 64) * kBBlockBytes;
-  const int grid = units * p.slices;
-  if (p.nci == 128) {
-    constexpr int kStages = 2;
-    const int smem_bytes = 1024 + kStages * stage_bytes + 256;
-    CTK_CUDA_TRY(cudaFuncSetAttribute(wgrad_tc_kernel<kStages>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    wgrad_tc_kernel<kStages><<<grid, kThreads, smem_bytes, s>>>(tm_dy, tm_x, p);
-  } else {
-    constexpr int kStages = 3;
-    const int smem_bytes = 1024 + kStages * stage_bytes + 256;
-    CTK_CUDA_TRY(cudaFuncSetAttribute(wgrad_tc_kernel<kStages>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    wgrad_tc_kernel<kStages><<<grid, kThreads, smem_bytes, s>>>(tm_dy, tm_x, p);
-  }
+  const int grid = pairs * (p.slices_a + p.slices_b);
+  const int smem_bytes = 1024 + kStages * kStageBytes + 256;
+  CTK_CUDA_TRY(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+  wgrad_tc_kernel<<<grid, kThreads, smem_bytes, s>>>(tm_dy, tm_x, p);
   return ctk::check_launch();
 }
 
