@@ -13,17 +13,21 @@ It restates, as plain functional PyTorch-on-CPU / NumPy code over a
 * MSE loss                    -- /root/reference/train_model.py:636,421
 * Adam(weight_decay) update   -- /root/reference/train_model.py:637,424
 * per-image Pearson r         -- /root/reference/test-cross-talk-model.py:59-64
-* per-plane min-max normalise -- /root/reference/train_model.py:211-216
+* RMSE, 256-bin histogram correlation, NMI of the digitised planes
+                              -- /root/reference/test-cross-talk-model.py:65-79,84
+* per-plane min-max normalise, cast and flips of the input pipeline
+                              -- /root/reference/train_model.py:166-167,211-232
 
 The arithmetic itself lives in third-party libraries that are not vendored in
-the reference (PyTorch -- unpinned in requirements.txt:2 -- and SciPy, which is
-not listed at all).  The versions this oracle was pinned against are
-torch 2.11.0 and scipy 1.18.1.  The reference ships no tests and no golden
+the reference (PyTorch and NumPy -- unpinned in requirements.txt:1-2 -- and SciPy /
+scikit-learn, which are not listed at all).  The versions this oracle was pinned
+against are torch 2.11.0, numpy 2.3.5, scipy 1.18.1 and scikit-learn 1.9.0.  The reference ships no tests and no golden
 vectors, so the pins are created by ``tests/golden/make_golden.py``, which
 imports the *unmodified* reference modules from /root/reference, runs them on
 the reference's own ``Training_Data`` fixtures and records their outputs in
-``tests/golden/golden.json``; ``tests/test_oracle_golden.py`` holds the oracle
-to those numbers.  Parity status: pinned against reference outputs generated
+``tests/golden/golden.json`` (``make_loss_curve.py``: 200 steps of the reference's
+training loop; ``make_metrics_golden.py``: the reference's metric expressions
+verbatim); ``tests/test_oracle_golden.py`` holds the oracle to those numbers.  Parity status: pinned against reference outputs generated
 in the build container (not against reference-owned tests, which do not exist).
 """
 from __future__ import annotations
