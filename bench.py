@@ -117,8 +117,11 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": "images/sec", "n_gpus": args.gpus,
             "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "double-branch inference, 256 synthetic 2ch 256x256 tiles + Pearson",
-                       "bounded_sample_tiles": n_tiles},
+            "config": {"workload": "double-branch inference, batch 256 synthetic 2ch 256x256 tiles per GPU + Pearson "
+                                   "(BASELINE.json configs[1])",
+                       "per_gpu_batch": BATCH, "global_batch": BATCH, "parallelism": "host CPU cores, rank 0 only",
+                       "bounded_sample_tiles": n_tiles,
+                       "weights": "seed-0 random init"},
             "cpu_baseline": {"value": rate, "unit": "images/sec", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": rate, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)

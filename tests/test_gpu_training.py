@@ -166,16 +166,20 @@ def test_200_step_loss_curve_against_reference_golden():
     -- tests/golden/loss_curve_single.json, written by tests/golden/make_loss_curve.py -- against the same 200 steps on the
     GPU path with identical data order, initial weights and Dropout draws.
 
-    north_star asks for the curve within 1 % relative.  With bf16 operands that is not attainable on this problem: the CPU
-    oracle with nothing but the GPU path's bf16 roundings applied (recorded beside the reference curve) already moves the
-    per-step loss by 5-60 % -- random-init BatchNorm over 16 tiles amplifies a 1e-6 input perturbation 1000x in fp32 itself
-    (Precision).  What is asserted: step 0 within the forward-pass bf16 bound, every 25-step window's
-    geometric-mean loss within the factor the bf16 emulation itself strays (x1.5 margin), and the same plateau."""
+    north_star asks for the curve within 1 % relative.  That is not attainable on this problem by anything, the reference
+    included: the SAME reference loop run with 5 instead of 8 CPU threads (loss_curve_single_threads5.json; only ATen's
+    reduction order changes) leaves the 1 % band at step 3, differs by 18 % per step in the median and by a factor
+    0.93-1.23 per 25-step window -- random-init train-mode BatchNorm over 16 tiles amplifies fp32 rounding noise.  The CPU
+    oracle with the GPU path's bf16 roundings applied strays the same way.  What is asserted: step 0 within the
+    forward-pass bf16 bound, every 25-step window's geometric-mean loss within 1.5x the factor by which the reference
+    strays from itself / the bf16 emulation strays from it, and the same plateau."""
     import json
     import torch.nn.functional as F
     import ctk
     g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "loss_curve_single.json")))
     ref, emu = np.array(g["reference_fp32"]), np.array(g["oracle_bf16_emulation"])
+    self5 = np.array(json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden",
+                                                   "loss_curve_single_threads5.json")))["reference_fp32"])
     steps, pool, batch = g["steps"], g["pool"], g["batch"]
     x, y = orc.synthetic_batch(pool, seed=g["data_seed"])
     model = _build("single").cuda().train()
@@ -199,12 +203,13 @@ def test_200_step_loss_curve_against_reference_golden():
     assert np.isfinite(gpu).all()
     print("step-0 loss: reference %.6f  bf16-emulation %.6f  gpu %.6f" % (ref[0], emu[0], gpu[0]))
     assert abs(gpu[0] - ref[0]) / ref[0] <= 0.10
-    print("window  reference  bf16-emu   gpu      gpu/ref  emu/ref   (geometric means over 25 steps)")
+    print("window  reference  bf16-emu   gpu      gpu/ref  emu/ref  ref(5 threads)/ref   (geometric means over 25 steps)")
     for a in range(0, steps, 25):
         gm = lambda v: float(np.exp(np.log(v[a:a + 25]).mean()))
         r_, e_, g_ = gm(ref), gm(emu), gm(gpu)
-        print(f"{a:4d}    {r_:.5f}   {e_:.5f}   {g_:.5f}   {g_ / r_:.3f}   {e_ / r_:.3f}")
-        band = 1.5 * max(e_ / r_, r_ / e_, 1.15)
+        s_ = gm(self5) if a + 25 <= len(self5) else r_
+        print(f"{a:4d}    {r_:.5f}   {e_:.5f}   {g_:.5f}   {g_ / r_:.3f}   {e_ / r_:.3f}   {s_ / r_:.3f}")
+        band = 1.5 * max(e_ / r_, r_ / e_, s_ / r_, r_ / s_, 1.15)
         assert 1.0 / band <= g_ / r_ <= band, (a, g_, r_, e_)
     tail_ref, tail_gpu = ref[steps // 2:].mean(), gpu[steps // 2:].mean()
     print("mean loss over the last 100 steps: reference %.5f gpu %.5f" % (tail_ref, tail_gpu))
