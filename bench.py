@@ -225,10 +225,13 @@ def run_train(args, shared_pg=False):
     # end to end: the batch starts in pinned host memory every step (the DataLoader's pin_memory=True path, :607-614)
     barrier()
     t0 = time.perf_counter()
-    e2e_steps = max(2, steps // 2)
-    for i in range(e2e_steps):
-        xb = host[i % 2][0].to(dev, non_blocking=True)
-        yb = host[i % 2][1].to(dev, non_blocking=True)
+    e2e_steps = max(4, steps)
+    pre = ctk.DevicePrefetcher(device=str(dev))
+    for xb, yb in pre.iterate(host[i % 2] for i in range(2)):                 # staging buffers allocated, copies warm
+        step(xb, yb).item()
+    barrier()
+    t0 = time.perf_counter()
+    for xb, yb in pre.iterate(host[i % 2] for i in range(e2e_steps)):
         step(xb, yb).item()
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - t0) * 1e3
@@ -270,7 +273,9 @@ def run_train(args, shared_pg=False):
                 "clocks": clocks, "gpu_launches": launches, "last_loss": last,
                 "e2e": {"value": world * batch * e2e_steps / (e2e_ms / 1e3), "unit": "images/sec",
                         "h2d_bytes_per_step": batch * (2 * 256 * 256 + 1) * 4, "d2h_bytes_per_step": 4, "steps": e2e_steps,
-                        "ms_per_step": e2e_ms / e2e_steps, "api": "model(x); MSELoss; backward; ctk.Adam.step; loss.item()"}}
+                        "ms_per_step": e2e_ms / e2e_steps,
+                        "api": "for x, y in ctk.DevicePrefetcher().iterate(pinned host batches): model(x); MSELoss; backward; "
+                               "ctk.Adam.step; loss.item()  (every step's H2D and loss read-back inside the timed region)"}}
         if sync is not None:
             line["allreduce"] = {"collectives_per_step": sync.collectives / (warmup + steps + e2e_steps),
                                  "bytes_per_step": sync.bytes_reduced / (warmup + steps + e2e_steps)}

@@ -262,3 +262,26 @@ def test_lr_schedulers_and_checkpoint_resume_drive_ctk_adam():
     for _ in range(6):
         plateau.step(1.0)
     assert abs(opt.param_groups[0]["lr"] - 5e-4 * 0.3) < 1e-12
+
+
+def test_prefetch_to_device_orders_and_overlaps_safely():
+    """ctk.prefetch_to_device: batches arrive on the device in order and intact even when the consumer's kernels are
+    still running while the next copies are issued (slot reuse waits for the consumer's stream)."""
+    import ctk
+    torch.manual_seed(3)
+    host = [(torch.randn(64, 2, 64, 64).pin_memory(), torch.full((64, 1), float(i)).pin_memory()) for i in range(7)]
+    seen = []
+    big = torch.randn(4096, 4096, device="cuda")
+    for i, (x, y) in enumerate(ctk.prefetch_to_device(iter(host))):
+        for _ in range(3):
+            big = big @ big * 1e-4                      # keep the stream busy while the generator issues the next copy
+        seen.append((x.sum().clone(), y.mean().clone(), x.clone()))
+    torch.cuda.synchronize()
+    assert len(seen) == len(host)
+    for i, (sx, my, xc) in enumerate(seen):
+        assert torch.equal(xc.cpu(), host[i][0]) and my.item() == float(i)
+    # single tensors and ragged last batch
+    singles = [torch.arange(10.0).pin_memory(), torch.arange(3.0).pin_memory()]
+    got = [t.cpu() for t in ctk.prefetch_to_device(iter(singles))]
+    assert torch.equal(got[0], singles[0]) and torch.equal(got[1], singles[1])
+    assert list(ctk.prefetch_to_device(iter([]))) == []

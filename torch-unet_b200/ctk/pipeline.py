@@ -139,3 +139,85 @@ class HostScorer:
             pending = job
         if pending is not None:
             yield self._finish(pending)
+
+
+class DevicePrefetcher:
+    """Host batches -> device with the copy of batch k+1 running on a side stream while the caller's kernels work on
+    batch k.  The training-loop counterpart of ``HostScorer.score_stream``; staging buffers persist across ``iterate``
+    calls (epochs).  Batches are a tensor or a tuple of tensors, ideally pinned (the reference's DataLoader uses
+    ``pin_memory=True``, train_model.py:607-614):
+
+        pre = ctk.DevicePrefetcher()
+        for inputs, labels in pre.iterate(train_loader):        # train_model.py:415-417 without the .to(device)
+            ...
+    """
+
+    def __init__(self, device: str = "cuda", depth: int = 2):
+        self.dev = torch.device(device)
+        self.depth = depth
+        self.copy_stream = torch.cuda.Stream(device=self.dev)
+        self.slots = [None] * depth        # device tensors, ready event, released event
+
+    def _issue(self, batch, i):
+        single = torch.is_tensor(batch)
+        items = (batch,) if single else tuple(batch)
+        slot = self.slots[i]
+        if slot is None or len(slot["t"]) != len(items) or any(a.shape != b.shape or a.dtype != b.dtype
+                                                               for a, b in zip(slot["t"], items)):
+            if slot is not None and slot["released"] is not None:
+                slot["released"].synchronize()
+            slot = {"t": [torch.empty(t.shape, dtype=t.dtype, device=self.dev) for t in items], "released": None}
+            self.slots[i] = slot
+        if slot["released"] is not None:
+            self.copy_stream.wait_event(slot["released"])      # the kernels that read this slot's previous batch are enqueued
+        with torch.cuda.stream(self.copy_stream):
+            for d, h in zip(slot["t"], items):
+                n = h.shape[0] if h.dim() > 0 else 0
+                if h.dim() > 0 and h.numel() * h.element_size() > (64 << 20) and n >= 4:
+                    # large copies in four pieces: a single 134 MB cudaMemcpyAsync runs at 30-38 GB/s on these boxes,
+                    # the same bytes in four back-to-back copies at 54.8 GB/s (tools/probe_h2d.py)
+                    step = (n + 3) // 4
+                    for a in range(0, n, step):
+                        d[a:a + step].copy_(h[a:a + step], non_blocking=True)
+                else:
+                    d.copy_(h, non_blocking=True)
+            slot["ready"] = torch.cuda.Event()
+            slot["ready"].record(self.copy_stream)
+        slot["single"] = single
+
+    def _hand_out(self, i):
+        slot = self.slots[i]
+        torch.cuda.current_stream(self.dev).wait_event(slot["ready"])
+        return slot, (slot["t"][0] if slot["single"] else tuple(slot["t"]))
+
+    def iterate(self, batches: Iterable):
+        pending = []                       # slot indices in flight, oldest first
+        turn = 0
+        last = None
+
+        def release(slot):
+            # the generator was resumed: the consumer has enqueued all its work on the batch handed out last, so an
+            # event recorded now on its stream marks the point after which that slot may be overwritten
+            if slot is not None:
+                slot["released"] = torch.cuda.Event()
+                slot["released"].record(torch.cuda.current_stream(self.dev))
+
+        for batch in batches:
+            release(last)
+            last = None
+            self._issue(batch, turn)
+            pending.append(turn)
+            turn = (turn + 1) % self.depth
+            if len(pending) == self.depth:
+                last, out = self._hand_out(pending.pop(0))
+                yield out
+        while pending:
+            release(last)
+            last, out = self._hand_out(pending.pop(0))
+            yield out
+        release(last)
+
+
+def prefetch_to_device(batches: Iterable, device: str = "cuda", depth: int = 2):
+    """One-off form of ``DevicePrefetcher(device, depth).iterate(batches)``."""
+    return DevicePrefetcher(device, depth).iterate(batches)
