@@ -42,6 +42,26 @@ def peaks():
 NOMINAL_BF16_TFLOPS = 2250.0     # B200 dense bf16 (B200_PROFILING.md)
 
 
+def ncu_dram_traffic(kernel_substr, csv_name="r1c_infer_full_raw.csv"):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of a kernel, averaged over the launches of the committed
+    `ncu --set full` capture under profiles/ (None if the file is absent)."""
+    import csv
+    path = os.path.join(ROOT, "profiles", csv_name)
+    if not os.path.exists(path):
+        return None, None
+    rows = list(csv.reader(open(path)))
+    hdr, units = rows[0], rows[1]
+    idx = {h: i for i, h in enumerate(hdr)}
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot, n = 0.0, 0
+    for r in rows[2:]:
+        if kernel_substr in r[idx["Kernel Name"]]:
+            for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                tot += float(r[idx[key]].replace(",", "")) * scale.get(units[idx[key]], 1.0)
+            n += 1
+    return (tot / n if n else None), os.path.join("profiles", csv_name)
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
 
@@ -409,8 +429,13 @@ def main():
             d["flops"] += (meta or {}).get("flops", 0.0)
         conv = per.get("ctk_conv3x3_tc_eval", {"ms": 0.0, "n": 1, "flops": 0.0})
         conv_tf = conv["flops"] / (conv["ms"] / 1e3) / 1e12 if conv["ms"] > 0 else 0.0
+        traffic, traffic_src = ncu_dram_traffic("conv3x3_tc_kernel")
         roof = {"kernel": "conv3x3_tc_kernel", "bound": "tensor", "achieved": conv_tf, "peak": pk["bf16_tflops"],
-                "unit": "TFLOP/s", "frac": conv_tf / pk["bf16_tflops"], "traffic": None,
+                "unit": "TFLOP/s", "frac": conv_tf / pk["bf16_tflops"], "traffic": traffic,
+                "traffic_unit": "DRAM bytes per launch (ncu --set full, mean of the 6 launches of a step)",
+                "traffic_source": traffic_src,
+                "algorithmic_bytes_per_launch": (537e6 + 268e6 + 268e6 + 134e6 + 134e6 + 67e6) / 3,
+                "algorithmic_flop_per_launch": 618.5e9,
                 "peak_source": pk["src"] + " (sustained cuBLAS bf16: the kernel is timed inside a long step)",
                 "frac_of_burst_cublas": conv_tf / pk["bf16_tflops_burst"], "frac_of_nominal_dense": conv_tf / NOMINAL_BF16_TFLOPS,
                 "avg_launch_ms": conv["ms"] / max(1, conv["n"]), "launches": conv["n"],
