@@ -69,12 +69,21 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant
   WgradSmem* sl = reinterpret_cast<WgradSmem*>(smem + kStages * kStageBytes);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  // unit decode: blockIdx.x = (co_blk * ci_blocks + ci_blk) * (slices_a + slices_b) + s;  s < slices_a -> kx group 0
+  // unit decode: blockIdx.x = (co_blk * ci_blocks + ci_blk) * (slices_a + slices_b) + r.  Inside a pair the CTAs come in
+  // triplets (A, A, B): group-0 slices 2j and 2j+1 and group-1 slice j walk the SAME patches at the same time (the B CTA
+  // does two patches while each A CTA does one), so the second read of every dY / X tile is an L2 hit -- provided the
+  // whole grid is resident at once (grid <= SM count, see the launch code).
   const int per_pair = p.slices_a + p.slices_b;
   const int pair = blockIdx.x / per_pair;
-  const int s_idx = blockIdx.x - pair * per_pair;
-  const int group = s_idx < p.slices_a ? 0 : 1;
-  const int slice = group == 0 ? s_idx : s_idx - p.slices_a;
+  const int r = blockIdx.x - pair * per_pair;
+  int group, slice;
+  if (p.slices_a == 2 * p.slices_b) {
+    group = (r % 3) < 2 ? 0 : 1;
+    slice = group == 0 ? (r / 3) * 2 + (r % 3) : r / 3;
+  } else {                                            // tiny problems: plain split
+    group = r < p.slices_a ? 0 : 1;
+    slice = group == 0 ? r : r - p.slices_a;
+  }
   const int slices = group == 0 ? p.slices_a : p.slices_b;
   const int kx0 = group == 0 ? 0 : 2, nkx = group == 0 ? 2 : 1;
   const int ci_blk = pair % p.ci_blocks;
@@ -261,8 +270,9 @@ int ctk_conv3x3_wgrad_tc(const void* dy_bf16, const void* x_bf16, int n, int H, 
   p.co_blocks = cout / 128;
   p.ci_blocks = cin / 64;
   const int pairs = p.co_blocks * p.ci_blocks;
-  // kx group 0 does two kernel columns per patch, group 1 one: twice as many slices for group 0 balances the CTAs
-  const int s_unit = std::max(1, std::min(p.total_tiles / 2, (2 * ctk::num_sms()) / (3 * pairs)));
+  // kx group 0 does two kernel columns per patch, group 1 one: twice as many slices for group 0 balances the CTAs.
+  // One wave (grid <= SMs): all CTAs of a triplet run together, which is what makes their shared tiles L2 hits.
+  const int s_unit = std::max(1, std::min(p.total_tiles / 2, ctk::num_sms() / (3 * pairs)));
   p.slices_a = std::min(p.total_tiles, 2 * s_unit);
   p.slices_b = std::min(p.total_tiles, s_unit);
   p.dw = dw;
