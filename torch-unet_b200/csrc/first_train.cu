@@ -101,15 +101,23 @@ __device__ __forceinline__ void gram_role(const float* __restrict__ x, int n_img
         if (sr[k] < TH + 2) s_in[c][sr[k]][sq[k]] = pf[c][k];
     __syncthreads();
     if (tile + gridDim.x < total) fetch(tile + gridDim.x);
+    // explicit shared-space loads with immediate offsets: through the generic pointer every one of the 9*CIN loads of a
+    // row cost an extra shared-window address computation (ncu: 525 M instructions for 198 M FFMAs at CIN = 2)
+    const uint32_t s_base = static_cast<uint32_t>(__cvta_generic_to_shared(&s_in[0][0][0])) + static_cast<uint32_t>(lane * 4);
 #pragma unroll 2
     for (int py = rowg; py < TH; py += C::ROWG) {
       const int gy = ty * TH + py, gx = tx * TW + lane;
       float v[T];
       const bool in = gy < H && gx < W;
+      const uint32_t row_addr = s_base + static_cast<uint32_t>(py * 35 * 4);
 #pragma unroll
       for (int c = 0; c < CIN; ++c)
 #pragma unroll
-        for (int k = 0; k < 9; ++k) v[c * 9 + k] = in ? s_in[c][py + k / 3][lane + k % 3] : 0.f;
+        for (int k = 0; k < 9; ++k) {
+          float t;
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t) : "r"(row_addr + static_cast<uint32_t>((c * (TH + 2) * 35 + (k / 3) * 35 + (k % 3)) * 4)));
+          v[c * 9 + k] = in ? t : 0.f;
+        }
       gram_accumulate<CIN, ROLE>(v, acc);
     }
 #pragma unroll
