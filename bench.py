@@ -321,6 +321,8 @@ def main():
     ap.add_argument("--impl", default="ctk", choices=["ctk", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="default mode: skip the attached training measurement")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"],
+                    help="inference arithmetic: bf16 operands (default, the headline) or the fp32-class split-bf16 path")
     ap.add_argument("--sync-bn", action="store_true", help="train mode, N > 1: BatchNorm statistics over the global batch")
     ap.add_argument("--mode", default="infer", choices=["infer", "train"],
                     help="infer = BASELINE configs[1] (default, the headline line); train = configs[2]/[3] training step")
@@ -353,6 +355,8 @@ def main():
     model = ctk.SimplifiedTwoBranchRegressionModel(initial_filters_per_branch=64)
     model.load_state_dict(orc.randomize_bn(model.state_dict(), seed=7))
     model = model.to(dev).eval()
+    if args.precision != "bf16":
+        ctk.set_precision(model, args.precision)
     base, _ = orc.synthetic_batch(32, seed=1234 + rank)
     n_rot = 3                                   # rotate distinct 134 MB input batches (> 126 MB L2 each)
     host_batches = [base.roll(shifts=i, dims=0).repeat(BATCH // 32, 1, 1, 1).contiguous().pin_memory() for i in range(n_rot)]
@@ -427,7 +431,7 @@ def main():
             d["ms"] += a.elapsed_time(b)
             d["n"] += 1
             d["flops"] += (meta or {}).get("flops", 0.0)
-        conv = per.get("ctk_conv3x3_tc_eval", {"ms": 0.0, "n": 1, "flops": 0.0})
+        conv = per.get("ctk_conv3x3_tc_eval") or per.get("ctk_conv3x3_tc_eval_split") or {"ms": 0.0, "n": 1, "flops": 0.0}
         conv_tf = conv["flops"] / (conv["ms"] / 1e3) / 1e12 if conv["ms"] > 0 else 0.0
         traffic, traffic_src = ncu_dram_traffic("conv3x3_tc_kernel")
         roof = {"kernel": "conv3x3_tc_kernel", "bound": "tensor", "achieved": conv_tf, "peak": pk["bf16_tflops"],
@@ -443,7 +447,8 @@ def main():
                 "per_call_ms_per_step": {k: v["ms"] / steps for k, v in per.items()}}
         line = {"metric": METRIC, "value": value, "unit": "images/sec", "n_gpus": world, "steps": steps, "warmup": warmup,
                 "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "bf16", "data": "synthetic",
+                "dtype": "bf16" if args.precision == "bf16" else "bf16x3 (fp32-class: hi/lo operand pairs, fp32 accumulate)",
+                "data": "synthetic",
                 "config": {"workload": "double-branch inference, batch 256 synthetic 2ch 256x256 tiles per GPU + Pearson "
                                        "(BASELINE.json configs[1])",
                            "per_gpu_batch": BATCH, "global_batch": BATCH * world, "parallelism": f"tiles sharded x{world}, no collective",
