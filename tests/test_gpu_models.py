@@ -248,3 +248,28 @@ def test_fp32_class_mode_matches_oracle(golden, kind, weights):
     with torch.no_grad():
         out_bf16 = model(x.cuda()).flatten().cpu()
     assert not torch.equal(out_bf16, out)
+
+
+def test_other_tile_size_and_train_step(golden):
+    """The models take ``input_image_size`` (two_branch_regression.py:60,72-80): 128 x 128 tiles through the eval path
+    (against the oracle) and one train-mode step (finite loss, every parameter receives a gradient)."""
+    import ctk
+    torch.manual_seed(0)
+    model = ctk.SimplifiedTwoBranchRegressionModel(initial_filters_per_branch=64, input_image_size=(128, 128))
+    sd = orc.randomize_bn(model.state_dict(), seed=11)
+    model.load_state_dict(sd)
+    x, y = orc.synthetic_batch(5, seed=21, size=128)
+    with torch.no_grad():
+        ref = orc.FORWARD["double"](sd, x).flatten()
+    model = model.cuda()
+    with torch.no_grad():
+        out = model.eval()(x.cuda()).flatten().cpu()
+    assert (out - ref).abs().max().item() <= TOL_BF16
+    model.train()
+    loss = torch.nn.functional.mse_loss(model(x.cuda()), y.cuda())
+    loss.backward()
+    assert np.isfinite(loss.item())
+    for name, p in model.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all(), name
+    with pytest.raises(ctk.CtkError):
+        model.eval()(torch.zeros(1, 2, 100, 100, device="cuda"))          # not a multiple of 32: rejected loudly
