@@ -60,13 +60,19 @@ template <int kCtaGroup, int kBlockN, int kEpi>
 struct Cfg {
   static constexpr int kBRows = kBlockN / kCtaGroup;          // weight rows this CTA loads per (chunk, tap)
   static constexpr int kBStageBytes = kBRows * 128;
-  static constexpr int kExtra = kEpi == kEpiRawStats ? kScratchBytes : 0;
+  // raw modes with >= 64 channels per epilogue warp: the bf16 tile is staged per warp (32 pixels x 128 B, 128B-swizzled) and
+  // written by TMA -- a lane's 64-byte direct stores kept their source registers busy until the store path drained
+  // (ncu: the next tcgen05.ld / register clears stalled on them) and touched 32 half-lines per instruction
+  static constexpr bool kStage = (kEpi == kEpiRaw || kEpi == kEpiRawStats) && kBlockN >= 128;
+  static constexpr int kStageBytes = kStage ? kEpiWarps * 4096 : 0;
+  static constexpr int kExtra = kStageBytes + (kEpi == kEpiRawStats ? kScratchBytes : 0);
+  static constexpr int kAStg = (kStage && kEpi == kEpiRawStats) ? 3 : kAStages;     // activation halo stages
   // ring of weight stages; when the whole layer's share (chunks x 9 stages) fits, the weights are loaded ONCE and stay
   // resident (b_resident): 64-channel layers otherwise re-stream 74 KB per tile per CTA from L2 and stall on it
   static constexpr int kBStages =
-      std::min(18, (227 * 1024 - 1024 - kCtrlBytes - kExtra - kAStages * kAStageBytes) / kBStageBytes);
+      std::min(18, (227 * 1024 - 1024 - kCtrlBytes - kExtra - kAStg * kAStageBytes) / kBStageBytes);
   static constexpr int kTmemCols = kAccStages * kBlockN;
-  static constexpr int kSmemBytes = 1024 + kAStages * kAStageBytes + kBStages * kBStageBytes + kCtrlBytes + kExtra;
+  static constexpr int kSmemBytes = 1024 + kAStg * kAStageBytes + kBStages * kBStageBytes + kCtrlBytes + kExtra;
 };
 
 struct ConvParams {
@@ -145,6 +151,8 @@ struct EpiCtx {
   bool valid;
   uint32_t sc_addr, sh_addr;      // shared-space addresses of ch_a / ch_b
   uint32_t scratch_addr;          // this warp's transpose tile (statistics)
+  uint32_t stage_addr;            // this warp's 32-pixel x 128-byte output staging tile (raw modes, TMA store)
+  int stage_slot;                 // which 64-byte half of the staged rows the current block fills
   __nv_bfloat162 slope2;
 };
 
@@ -182,7 +190,17 @@ __device__ __forceinline__ void epilogue_block(const ConvParams& p, const EpiCtx
     }
 #pragma unroll
     for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
-    if (e.valid) {
+    if (e.stage_addr != 0) {
+      // row = this lane's pixel (128 B = 64 channels of two consecutive blocks), 16-byte chunks XOR-swizzled like TMA's
+      const uint32_t row = e.stage_addr + static_cast<uint32_t>(lane * 128);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t chunk = static_cast<uint32_t>(((e.stage_slot * 4 + i) ^ (lane & 7)) * 16);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + chunk), "r"(pk[4 * i]), "r"(pk[4 * i + 1]),
+                     "r"(pk[4 * i + 2]), "r"(pk[4 * i + 3])
+                     : "memory");
+      }
+    } else if (e.valid) {
       __nv_bfloat16* dst = p.out +
           (static_cast<size_t>(t.img) * p.H * p.W + static_cast<size_t>(e.y) * p.W + e.x) * p.out_cstride +
           p.out_coffset + t.n0 + ch0;
@@ -287,7 +305,7 @@ __device__ __forceinline__ void epilogue_block(const ConvParams& p, const EpiCtx
 template <int kCtaGroup, int kBlockN, int kEpi>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-                  const ConvParams p) {
+                  const __grid_constant__ CUtensorMap tm_out, const ConvParams p) {
   using C = Cfg<kCtaGroup, kBlockN, kEpi>;
   using SL = SmemLayout<kCtaGroup, kBlockN, kEpi>;
   static_assert(sizeof(SL) <= kCtrlBytes, "barrier block too large");
@@ -295,7 +313,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* a_smem = smem;
-  uint8_t* b_smem = smem + kAStages * kAStageBytes;
+  uint8_t* b_smem = smem + C::kAStg * kAStageBytes;
   SL* sl = reinterpret_cast<SL*>(b_smem + C::kBStages * C::kBStageBytes);
 
   const int warp = threadIdx.x >> 5;
@@ -306,7 +324,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
   const int work_stride = gridDim.x / kCtaGroup;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kAStages; ++i) { mbar_init(&sl->a_full[i], 1); mbar_init(&sl->a_empty[i], 1); }
+    for (int i = 0; i < C::kAStg; ++i) { mbar_init(&sl->a_full[i], 1); mbar_init(&sl->a_empty[i], 1); }
     for (int i = 0; i < C::kBStages; ++i) { mbar_init(&sl->b_full[i], 1); mbar_init(&sl->b_empty[i], 1); }
     for (int i = 0; i < kAccStages; ++i) { mbar_init(&sl->acc_full[i], 1); mbar_init(&sl->acc_empty[i], kEpiWarps * kCtaGroup); }
     fence_mbar_init();
@@ -353,7 +371,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
           }
         }
         __syncwarp();
-        if (++stage == kAStages) { stage = 0; phase ^= 1; }
+        if (++stage == C::kAStg) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 0) {
@@ -468,7 +486,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
             __syncwarp();
           }
         }
-        if (++as == kAStages) { as = 0; aphase ^= 1; }
+        if (++as == C::kAStg) { as = 0; aphase ^= 1; }
       }
     }
   } else if (warp >= 4) {
@@ -489,7 +507,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     e.Wp = p.W >> 1;
     e.sc_addr = smem_u32(sl->ch_a);
     e.sh_addr = smem_u32(sl->ch_b);
-    e.scratch_addr = smem_u32(reinterpret_cast<uint8_t*>(sl) + kCtrlBytes) + static_cast<uint32_t>((warp - 4) * 32 * kScratchPitch * 4);
+    e.scratch_addr = smem_u32(reinterpret_cast<uint8_t*>(sl) + kCtrlBytes) + static_cast<uint32_t>(C::kStageBytes) +
+                     static_cast<uint32_t>((warp - 4) * 32 * kScratchPitch * 4);
+    e.stage_addr = C::kStage ? smem_u32(reinterpret_cast<uint8_t*>(sl) + kCtrlBytes) + static_cast<uint32_t>((warp - 4) * 4096) : 0u;
+    e.stage_slot = 0;
+    // block i of this warp: consecutive PAIRS of 32-column blocks (64 channels = one 128-byte staged row)
+    auto block_of = [&](int i) { return kBlocks == 2 ? half : (i >> 1) * 4 + half * 2 + (i & 1); };
     e.slope2 = __float2bfloat162_rn(p.slope);
     int it = 0;
     for (int work = work0; work < p.total_work; work += work_stride, ++it) {
@@ -512,20 +535,42 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         }
       };
       uint32_t va[32], vb[32];
-      tmem_ld_32x32(taddr + half * 32, va);
+      tmem_ld_32x32(taddr + block_of(0) * 32, va);
 #pragma unroll
       for (int i = 0; i < kPerWarp; i += 2) {
         tmem_ld_wait();
-        if (i + 1 < kPerWarp) tmem_ld_32x32(taddr + (half + 2 * (i + 1)) * 32, vb);
+        if (i + 1 < kPerWarp) tmem_ld_32x32(taddr + block_of(i + 1) * 32, vb);
         else release();
-        epilogue_block<kEpi>(p, e, t, (half + 2 * i) * 32, va);
+        if constexpr (C::kStage) {
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous store read the tile
+          __syncwarp();
+          e.stage_slot = 0;
+        }
+        epilogue_block<kEpi>(p, e, t, block_of(i) * 32, va);
         if (i + 1 < kPerWarp) {
           tmem_ld_wait();
-          if (i + 2 < kPerWarp) tmem_ld_32x32(taddr + (half + 2 * (i + 2)) * 32, va);
+          if (i + 2 < kPerWarp) tmem_ld_32x32(taddr + block_of(i + 2) * 32, va);
           else release();
-          epilogue_block<kEpi>(p, e, t, (half + 2 * (i + 1)) * 32, vb);
+          e.stage_slot = 1;
+          epilogue_block<kEpi>(p, e, t, block_of(i + 1) * 32, vb);
+        }
+        if constexpr (C::kStage) {
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            asm volatile(
+                "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                    reinterpret_cast<uint64_t>(&tm_out)),
+                "r"(e.stage_addr), "r"(p.out_coffset + t.n0 + block_of(i) * 32), "r"(t.x0), "r"(t.y0 + ew * 4), "r"(t.img)
+                : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
         }
       }
+    }
+    if constexpr (C::kStage) {
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores must land before the CTA exits
+      __syncwarp();
     }
     if constexpr (kEpi == kEpiRawStats) {
       asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
@@ -573,6 +618,15 @@ int launch_conv(const void* x_bf16, const void* w_packed_bf16, ConvParams p, cud
     int st = ctk::encode_tmap_bf16_sw128(&tm_b, w_packed_bf16, 2, dims, strides, box);
     if (st != CTK_OK) return st;
   }
+  CUtensorMap tm_out = tm_a;          // only read by the staged raw epilogues
+  if constexpr (C::kStage) {
+    const uint64_t cs = static_cast<uint64_t>(p.out_cstride);
+    const uint64_t dims[4] = {cs, static_cast<uint64_t>(p.W), static_cast<uint64_t>(p.H), static_cast<uint64_t>(p.n_img)};
+    const uint64_t strides[3] = {cs * 2, static_cast<uint64_t>(p.W) * cs * 2, static_cast<uint64_t>(p.H) * p.W * cs * 2};
+    const uint32_t box[4] = {64, kTileW, 4, 1};
+    int st = ctk::encode_tmap_bf16_sw128(&tm_out, p.out, 4, dims, strides, box);
+    if (st != CTK_OK) return st;
+  }
   auto kernel = conv3x3_tc_kernel<kCtaGroup, kBlockN, kEpi>;
   CTK_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
   const int clusters = std::min(p.total_work, ctk::num_sms() / kCtaGroup);
@@ -588,7 +642,7 @@ int launch_conv(const void* x_bf16, const void* w_packed_bf16, ConvParams p, cud
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  CTK_CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, tm_a, tm_b, p));
+  CTK_CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, tm_a, tm_b, tm_out, p));
   return ctk::check_launch();
 }
 
