@@ -153,13 +153,14 @@ struct EpiCtx {
   uint32_t scratch_addr;          // this warp's transpose tile (statistics)
   uint32_t stage_addr;            // this warp's 32-pixel x 128-byte output staging tile (raw modes, TMA store)
   int stage_slot;                 // which 64-byte half of the staged rows the current block fills
+  bool stat_in_regs;              // raw+stats with one N tile: totals stay in the caller's registers until the end
   __nv_bfloat162 slope2;
 };
 
 // One 32-lane x 32-column block of fp32 accumulators (lane = output pixel, v[i] = channel ch0 + i of the tile).
 template <int kEpi>
 __device__ __forceinline__ void epilogue_block(const ConvParams& p, const EpiCtx& e, const TileCoord& t, int ch0,
-                                               const uint32_t (&v)[32]) {
+                                               const uint32_t (&v)[32], float& acc_s, float& acc_q) {
   const int lane = e.lane;
   uint32_t pk[16];
   if constexpr (kEpi == kEpiRaw || kEpi == kEpiRawStats) {
@@ -185,8 +186,13 @@ __device__ __forceinline__ void epilogue_block(const ConvParams& p, const EpiCtx
         s1 += x1; q1 = fmaf(x1, x1, q1);
       }
       __syncwarp();
-      red_shared_add(e.sc_addr + static_cast<uint32_t>((t.n0 + ch0 + lane) * 4), s0 + s1);
-      red_shared_add(e.sh_addr + static_cast<uint32_t>((t.n0 + ch0 + lane) * 4), q0 + q1);
+      if (e.stat_in_regs) {                 // same channel every tile: keep the totals in registers, flush once at the end
+        acc_s += s0 + s1;                   // (shared-memory float atomics are CAS loops on this architecture)
+        acc_q += q0 + q1;
+      } else {
+        red_shared_add(e.sc_addr + static_cast<uint32_t>((t.n0 + ch0 + lane) * 4), s0 + s1);
+        red_shared_add(e.sh_addr + static_cast<uint32_t>((t.n0 + ch0 + lane) * 4), q0 + q1);
+      }
     }
 #pragma unroll
     for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
@@ -511,6 +517,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                      static_cast<uint32_t>((warp - 4) * 32 * kScratchPitch * 4);
     e.stage_addr = C::kStage ? smem_u32(reinterpret_cast<uint8_t*>(sl) + kCtrlBytes) + static_cast<uint32_t>((warp - 4) * 4096) : 0u;
     e.stage_slot = 0;
+    float stat_s[kPerWarp], stat_q[kPerWarp];
+#pragma unroll
+    for (int i = 0; i < kPerWarp; ++i) { stat_s[i] = 0.f; stat_q[i] = 0.f; }
+    e.stat_in_regs = kEpi == kEpiRawStats && p.tiles_n == 1;
     // block i of this warp: consecutive PAIRS of 32-column blocks (64 channels = one 128-byte staged row)
     auto block_of = [&](int i) { return kBlocks == 2 ? half : (i >> 1) * 4 + half * 2 + (i & 1); };
     e.slope2 = __float2bfloat162_rn(p.slope);
@@ -546,13 +556,14 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
           __syncwarp();
           e.stage_slot = 0;
         }
-        epilogue_block<kEpi>(p, e, t, block_of(i) * 32, va);
+        epilogue_block<kEpi>(p, e, t, block_of(i) * 32, va, stat_s[i], stat_q[i]);
         if (i + 1 < kPerWarp) {
           tmem_ld_wait();
           if (i + 2 < kPerWarp) tmem_ld_32x32(taddr + block_of(i + 2) * 32, va);
           else release();
           e.stage_slot = 1;
-          epilogue_block<kEpi>(p, e, t, block_of(i + 1) * 32, vb);
+          epilogue_block<kEpi>(p, e, t, block_of(i + 1) * 32, vb, stat_s[i + 1 < kPerWarp ? i + 1 : 0],
+                               stat_q[i + 1 < kPerWarp ? i + 1 : 0]);
         }
         if constexpr (C::kStage) {
           fence_proxy_async_smem();
@@ -573,6 +584,13 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       __syncwarp();
     }
     if constexpr (kEpi == kEpiRawStats) {
+      if (e.stat_in_regs) {
+#pragma unroll
+        for (int i = 0; i < kPerWarp; ++i) {
+          red_shared_add(e.sc_addr + static_cast<uint32_t>((block_of(i) * 32 + lane) * 4), stat_s[i]);
+          red_shared_add(e.sh_addr + static_cast<uint32_t>((block_of(i) * 32 + lane) * 4), stat_q[i]);
+        }
+      }
       asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
       for (int i = et; i < p.cout; i += 32 * kEpiWarps) {
         atomicAdd(p.stats + i, sl->ch_a[i]);
