@@ -42,7 +42,7 @@ def peaks():
 NOMINAL_BF16_TFLOPS = 2250.0     # B200 dense bf16 (B200_PROFILING.md)
 
 
-def ncu_dram_traffic(kernel_substr, csv_name="r1c_infer_full_raw.csv"):
+def ncu_dram_traffic(kernel_substr, csv_name="r1d_infer_full_raw.csv"):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of a kernel, averaged over the launches of the committed
     `ncu --set full` capture under profiles/ (None if the file is absent)."""
     import csv
