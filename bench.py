@@ -4,8 +4,12 @@
 Workload at every N: BASELINE.json configs[1] -- double-branch (-o double) inference of a batch of 256 synthetic
 2-channel 256x256 tiles per GPU plus the per-tile Pearson baseline.  One "step" = Pearson + eval forward over
 one 256-tile batch.  Tiles are independent, so N GPUs shard tiles with no collective ("weak" scaling).
+The metric is "train & infer images/sec": the double-branch training step (batch 256 per GPU, gradients averaged by the
+bucketed NCCL all-reduce at N > 1) is measured in the same run and attached under "train".
 
-    python bench.py [--gpus N] [--steps K] [--warmup W]           # our arm
+    python bench.py [--gpus N] [--steps K] [--warmup W]           # our arm (inference headline + "train")
+    python bench.py --mode train [--model single|double] [--sync-bn]   # the training step as its own line
+    python bench.py --precision fp32                               # fp32-class inference path
     python bench.py --impl reference [...]                         # the reference's CPU path (oracle port)
 
 Under torchrun (N > 1) each rank drives one GPU; rank 0 prints the line.
