@@ -19,9 +19,14 @@
 // bytes each SM has to read per MMA -- with one CTA and N = 128 the operand reads alone are 128 B/clk/SM.
 //
 // Warp roles (384 threads): warp 0 = B producer, warp 3 = A producer (one lane each), warp 1 = MMA issuer
-// (one lane, pair leader only), warp 2 = TMEM allocator, warps 4-11 = epilogue (TMEM -> registers ->
-// scale/shift -> 2x2 max via two butterfly shuffle stages -> LeakyReLU -> 16-byte NHWC stores), compiled per
-// epilogue flavour (eval / raw / raw + batch statistics).
+// (one lane, pair leader only; fully unrolled taps, a whole chunk per elect when the weights are resident),
+// warp 2 = TMEM allocator, warps 4-11 = epilogue, compiled per flavour:
+//   eval        TMEM -> registers -> scale/shift -> 2x2 max via two butterfly shuffle stages -> LeakyReLU -> 16-byte
+//               NHWC stores of the pooled tile
+//   raw(+stats) bf16 pack -> per-warp 128B-swizzled staging tile (32 pixels x 64 channels) -> one TMA store; with stats
+//               also per-channel sum / sum of squares through a per-warp shared-memory transpose, totals in registers
+//   eval split  fp32-class: pool and LeakyReLU in fp32, (hi, lo) bf16 pair stores
+// Each epilogue warp owns a TMEM lane quadrant (warp % 4) and consecutive pairs of 32-column blocks.
 // Accumulators are double buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include "ctk_common.h"
 #include "ctk_ptx.cuh"
@@ -497,8 +502,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     }
   } else if (warp >= 4) {
     // ---------------- epilogue: thread <-> TMEM lane <-> output pixel of this CTA's tile; the two warps that share a
-    // lane quadrant (warp % 4) take alternate 32-column blocks.  TMEM loads are software pipelined: the block after the
-    // one being processed is already in flight, and the accumulator stage is released as soon as the last load landed.
+    // lane quadrant (warp % 4) take alternate PAIRS of 32-column blocks.  TMEM loads are software pipelined: the block
+    // after the one being processed is already in flight, and the accumulator stage is released as soon as the last load
+    // landed.
     const int ew = warp & 3;
     const int half = (warp - 4) >> 2;
     const int m = ew * 32 + lane;
