@@ -155,12 +155,13 @@ KERNELS_PER_CALL = {"ctk_pearson_f32": 2, "ctk_tile_metrics_f32": 4, "ctk_tile_n
                     "ctk_bn1d_bwd_reduce": 1, "ctk_bn1d_bwd_apply": 1}
 launch_count = 0
 _timeline = None      # when a list: (name, start_event, end_event, meta) per call, for per-kernel timing in bench.py
+_timeline_only = None # optional set of entry points to instrument (events around every call cost ~2 us each)
 
 
 def call(name: str, *args, meta=None) -> None:
     global launch_count
     fn = getattr(load(), name)
-    if _timeline is not None and name in KERNELS_PER_CALL:
+    if _timeline is not None and name in KERNELS_PER_CALL and (_timeline_only is None or name in _timeline_only):
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -172,9 +173,10 @@ def call(name: str, *args, meta=None) -> None:
     launch_count += KERNELS_PER_CALL.get(name, 0)
 
 
-def start_timeline() -> list:
-    global _timeline
+def start_timeline(only=None) -> list:
+    global _timeline, _timeline_only
     _timeline = []
+    _timeline_only = set(only) if only is not None else None
     return _timeline
 
 
