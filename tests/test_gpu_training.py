@@ -294,3 +294,37 @@ def test_prefetch_to_device_orders_and_overlaps_safely():
     got = [t.cpu() for t in ctk.prefetch_to_device(iter(singles))]
     assert torch.equal(got[0], singles[0]) and torch.equal(got[1], singles[1])
     assert list(ctk.prefetch_to_device(iter([]))) == []
+
+
+def test_first_block_gram_and_stored_paths_agree(golden):
+    """Two independent algorithms for the first block in training -- "gram" (patch Gram matrix + arg-max codes, no
+    full-resolution activation, the default) and "stored" (raw conv output kept, generic BN backward and wgrad) -- must
+    give the same step: identical loss up to bf16 flips, gradients within the run-to-run noise of these problems."""
+    import ctk
+    x, y = _data(golden)
+    n = x.shape[0]
+    masks = tuple(m.cuda() for m in orc.dropout_masks(n, 0.5, seed=5))
+    res = {}
+    for mode in ("gram", "stored"):
+        model = _build("double").cuda().train()
+        eng = ctk.models.get_train_engine(model)
+        eng.first_block_mode = mode
+        eng.forced_masks = masks
+        loss = torch.nn.functional.mse_loss(model(x.cuda()), y.cuda())
+        loss.backward()
+        res[mode] = (loss.item(), {k: p.grad.detach().clone() for k, p in model.named_parameters()},
+                     {k: v.detach().clone() for k, v in model.state_dict().items() if "running_" in k})
+    (lg, gg, sg), (ls, gs, ss) = res["gram"], res["stored"]
+    num = sum(((gg[k] - gs[k]).float() ** 2).sum().item() for k in gs)
+    den = sum((gs[k].float() ** 2).sum().item() for k in gs)
+    whole = (num / den) ** 0.5
+    first = [k for k in gs if k.endswith("conv_blocks.0.weight")]
+    rel_first = max(((gg[k] - gs[k]).norm() / gs[k].norm()).item() for k in first)
+    print("gram vs stored: loss", lg, ls, "whole-gradient rel L2", whole, "first conv weight rel L2", rel_first)
+    # the stored path rounds the full-resolution raw conv output to bf16 before BatchNorm, the gram path never materialises
+    # it: a 1e-3 difference at the first block that random-init train-mode BN amplifies to ~1.5 % of the loss (measured)
+    assert abs(lg - ls) <= 3e-2 * abs(ls), (lg, ls)
+    # measured 0.16 / 0.29 (run-to-run floor of this problem: 0.05-0.15, dist_check_syncbn.py); a wrong path gives >= 1
+    assert whole <= 0.4 and rel_first <= 0.6
+    for k in ss:
+        np.testing.assert_allclose(sg[k].cpu().numpy(), ss[k].cpu().numpy(), rtol=2e-2, atol=2e-3, err_msg=k)
