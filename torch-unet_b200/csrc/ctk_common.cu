@@ -23,8 +23,8 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
   return fn;
 }
 
-int encode_tmap_bf16_sw128(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
-                           const uint64_t* strides_bytes, const uint32_t* box) {
+static int encode_tmap_sw128(CUtensorMap* map, CUtensorMapDataType dtype, const void* base, int rank, const uint64_t* dims,
+                             const uint64_t* strides_bytes, const uint32_t* box) {
   auto fn = get_encode_fn();
   if (!fn) return CTK_ERR_NO_DEVICE;
   cuuint64_t gdim[5];
@@ -37,7 +37,7 @@ int encode_tmap_bf16_sw128(CUtensorMap* map, const void* base, int rank, const u
     es[i] = 1;
     if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
   }
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim,
+  CUresult r = fn(map, dtype, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim,
                   gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -45,6 +45,16 @@ int encode_tmap_bf16_sw128(CUtensorMap* map, const void* base, int rank, const u
     return CTK_ERR_CUDA;
   }
   return CTK_OK;
+}
+
+int encode_tmap_bf16_sw128(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                           const uint64_t* strides_bytes, const uint32_t* box) {
+  return encode_tmap_sw128(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, rank, dims, strides_bytes, box);
+}
+
+int encode_tmap_f32_sw128(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                          const uint64_t* strides_bytes, const uint32_t* box) {
+  return encode_tmap_sw128(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base, rank, dims, strides_bytes, box);
 }
 
 int num_sms() {

@@ -40,6 +40,9 @@ inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s
 // rank <= 4 bf16 tensor map, 128-byte swizzle.  dims/strides innermost first; strides in bytes for dims 1..rank-1.
 int encode_tmap_bf16_sw128(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
                            const uint64_t* strides_bytes, const uint32_t* box);
+// same for fp32 elements (box[0] <= 32)
+int encode_tmap_f32_sw128(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                          const uint64_t* strides_bytes, const uint32_t* box);
 
 int num_sms();
 

@@ -45,8 +45,8 @@ __device__ __forceinline__ uint64_t gemm_desc_mn_sw128(uint32_t addr, uint32_t l
 
 template <int kStages, bool kBMn>
 __global__ void __launch_bounds__(kThreads, kStages <= 2 ? 3 : 1)
-gemm_splitk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, int M, int N,
-                   int k_per_split, float* __restrict__ partial, __nv_bfloat16* __restrict__ out_bf16) {
+gemm_splitk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                   const __grid_constant__ CUtensorMap tm_out, int M, int k_per_split, int out_is_bf16) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   GemmSmem<kStages>* sl = reinterpret_cast<GemmSmem<kStages>*>(smem + kStages * kStageBytes);
@@ -61,6 +61,7 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
     fence_mbar_init();
     tma_prefetch_desc(&tm_a);
     tma_prefetch_desc(&tm_b);
+    tma_prefetch_desc(&tm_out);
   }
   if (warp == 1) tmem_alloc(&sl->tmem_base, kBN);
   tc_fence_before();
@@ -102,31 +103,65 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
     }
     umma_commit(&sl->acc_full);
   } else if (warp >= 2) {
+    // The accumulator barrier fires after the last MMA has completed, i.e. after every pipeline stage has been consumed:
+    // the stage buffers are free and become the output staging area.  Each warp owns 16 KiB of it = its 32 rows x 128
+    // columns as 128-byte rows in TMA's 128B-swizzled box layout (4 boxes of 32 fp32 columns, or 2 boxes of 64 bf16
+    // columns), written with conflict-free 16-byte shared stores and drained by TMA bulk tensor stores: full 128-byte
+    // lines to HBM instead of 32 scattered 16-byte pieces per store instruction.
     const int q = warp & 3;                       // TMEM lane quadrant this warp may read
-    const int row = m0 + q * 32 + lane;
+    const int row0 = split * M + m0 + q * 32;     // first output row of this warp (split-major partials)
     mbar_wait(&sl->acc_full, 0);
     tc_fence_after();
-    float* dst = partial ? partial + (static_cast<size_t>(split) * M + row) * N + n0 : nullptr;
-    __nv_bfloat16* dst16 = out_bf16 ? out_bf16 + static_cast<size_t>(row) * N + n0 : nullptr;
+    const uint32_t stage_base = smem_u32(smem) + static_cast<uint32_t>(q) * 16384u;
+    const uint32_t row_off = static_cast<uint32_t>(lane) * 128u;
+    const uint32_t sw = static_cast<uint32_t>(lane & 7);
 #pragma unroll 1
     for (int cb = 0; cb < kBN / 32; ++cb) {
       uint32_t v[32];
       tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + cb * 32, v);
       tmem_ld_wait();
-      if (dst) {
+      if (!out_is_bf16) {
+        const uint32_t box = stage_base + static_cast<uint32_t>(cb) * 4096u;
 #pragma unroll
         for (int i = 0; i < 8; ++i)
-          reinterpret_cast<uint4*>(dst + cb * 32)[i] = make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(box + row_off + ((static_cast<uint32_t>(i) ^ sw) << 4)),
+                       "r"(v[4 * i]), "r"(v[4 * i + 1]), "r"(v[4 * i + 2]), "r"(v[4 * i + 3])
+                       : "memory");
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                           reinterpret_cast<uint64_t>(&tm_out)),
+                       "r"(box), "r"(n0 + cb * 32), "r"(row0)
+                       : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
       } else {
+        const uint32_t box = stage_base + static_cast<uint32_t>(cb >> 1) * 4096u;
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-          reinterpret_cast<uint4*>(dst16 + cb * 32)[i] =
-              make_uint4(pack_bf16x2(__uint_as_float(v[8 * i]), __uint_as_float(v[8 * i + 1])),
-                         pack_bf16x2(__uint_as_float(v[8 * i + 2]), __uint_as_float(v[8 * i + 3])),
-                         pack_bf16x2(__uint_as_float(v[8 * i + 4]), __uint_as_float(v[8 * i + 5])),
-                         pack_bf16x2(__uint_as_float(v[8 * i + 6]), __uint_as_float(v[8 * i + 7])));
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(
+                           box + row_off + ((static_cast<uint32_t>((cb & 1) * 4 + i) ^ sw) << 4)),
+                       "r"(pack_bf16x2(__uint_as_float(v[8 * i]), __uint_as_float(v[8 * i + 1]))),
+                       "r"(pack_bf16x2(__uint_as_float(v[8 * i + 2]), __uint_as_float(v[8 * i + 3]))),
+                       "r"(pack_bf16x2(__uint_as_float(v[8 * i + 4]), __uint_as_float(v[8 * i + 5]))),
+                       "r"(pack_bf16x2(__uint_as_float(v[8 * i + 6]), __uint_as_float(v[8 * i + 7])))
+                       : "memory");
+        if (cb & 1) {
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                             reinterpret_cast<uint64_t>(&tm_out)),
+                         "r"(box), "r"(n0 + (cb >> 1) * 64), "r"(row0)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
       }
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores must land before the CTA exits
+    __syncwarp();
   }
   __syncwarp();
   tc_fence_before();
@@ -140,12 +175,12 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
 }  // namespace
 
 template <int kStages, bool kBMn>
-static int gemm_run(const CUtensorMap& tm_a, const CUtensorMap& tm_b, dim3 grid, int M, int N, int k_per_split, float* partial,
-                    void* out_bf16, void* stream) {
+static int gemm_run(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const CUtensorMap& tm_out, dim3 grid, int M,
+                    int k_per_split, bool out_is_bf16, void* stream) {
   auto kernel = gemm_splitk_kernel<kStages, kBMn>;
   CTK_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<kStages>()));
-  kernel<<<grid, kThreads, smem_bytes<kStages>(), ctk::as_stream(stream)>>>(tm_a, tm_b, M, N, k_per_split, partial,
-                                                                           static_cast<__nv_bfloat16*>(out_bf16));
+  kernel<<<grid, kThreads, smem_bytes<kStages>(), ctk::as_stream(stream)>>>(tm_a, tm_b, tm_out, M, k_per_split,
+                                                                           out_is_bf16 ? 1 : 0);
   return ctk::check_launch();
 }
 
@@ -176,12 +211,24 @@ static int gemm_launch(const void* a_bf16, const void* b_bf16, int M, int N, int
     int st = ctk::encode_tmap_bf16_sw128(&tm_b, b_bf16, 2, dims, strides, box);
     if (st != CTK_OK) return st;
   }
+  // output: [splits * M rows][N] fp32 partials in boxes of 32 rows x 32 columns, or [M][N] bf16 in boxes of 32 x 64
+  CUtensorMap tm_out;
+  {
+    const bool bf = out_bf16 != nullptr;
+    const uint64_t dims[2] = {static_cast<uint64_t>(N), static_cast<uint64_t>(M) * (bf ? 1 : splits)};
+    const uint64_t strides[1] = {static_cast<uint64_t>(N) * (bf ? 2 : 4)};
+    const uint32_t box_out[2] = {bf ? 64u : 32u, 32u};
+    int st = bf ? ctk::encode_tmap_bf16_sw128(&tm_out, out_bf16, 2, dims, strides, box_out)
+                : ctk::encode_tmap_f32_sw128(&tm_out, partial, 2, dims, strides, box_out);
+    if (st != CTK_OK) return st;
+  }
   dim3 grid(M / kBM, N / kBN, splits);
   const bool short_k = K / splits / kBK <= 8;
-  if (b_mn) return short_k ? gemm_run<2, true>(tm_a, tm_b, grid, M, N, K / splits, partial, out_bf16, stream)
-                           : gemm_run<6, true>(tm_a, tm_b, grid, M, N, K / splits, partial, out_bf16, stream);
-  return short_k ? gemm_run<2, false>(tm_a, tm_b, grid, M, N, K / splits, partial, out_bf16, stream)
-                 : gemm_run<6, false>(tm_a, tm_b, grid, M, N, K / splits, partial, out_bf16, stream);
+  const bool bf = out_bf16 != nullptr;
+  if (b_mn) return short_k ? gemm_run<2, true>(tm_a, tm_b, tm_out, grid, M, K / splits, bf, stream)
+                           : gemm_run<6, true>(tm_a, tm_b, tm_out, grid, M, K / splits, bf, stream);
+  return short_k ? gemm_run<2, false>(tm_a, tm_b, tm_out, grid, M, K / splits, bf, stream)
+                 : gemm_run<6, false>(tm_a, tm_b, tm_out, grid, M, K / splits, bf, stream);
 }
 
 extern "C" int ctk_gemm_bf16_splitk(const void* a_bf16, const void* b_bf16, int M, int N, int K, int splits,
