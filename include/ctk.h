@@ -71,6 +71,12 @@ int ctk_tile_metrics_f32(const float* tiles, int n_tiles, int plane_elems, doubl
 size_t ctk_tile_nmi_workspace_bytes(int n_tiles);
 int ctk_tile_nmi_f32(const float* tiles, int n_tiles, int plane_elems, double* nmi_out, void* workspace,
                      size_t workspace_bytes, void* stream);
+/* ssim_out[n] f64 = skimage.metrics.structural_similarity(img0, img1, data_range=max(both) - min(both)) with its defaults
+ * (7x7 uniform window, K1 0.01, K2 0.03, sample covariance, float32 arithmetic, mean over the tile cropped by 3 pixels)
+ * -- test-cross-talk-model.py:80-82.  tiles: [n][2][H][W] float32, H, W >= 7, H * W even, W <= 588, n <= 65535. */
+size_t ctk_tile_ssim_workspace_bytes(int n_tiles);
+int ctk_tile_ssim_f32(const float* tiles, int n_tiles, int H, int W, double* ssim_out, void* workspace,
+                      size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Parameter re-packing (derived cache; redo after every optimizer step / load_state_dict).

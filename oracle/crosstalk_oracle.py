@@ -15,6 +15,8 @@ It restates, as plain functional PyTorch-on-CPU / NumPy code over a
 * per-image Pearson r         -- /root/reference/test-cross-talk-model.py:59-64
 * RMSE, 256-bin histogram correlation, NMI of the digitised planes
                               -- /root/reference/test-cross-talk-model.py:65-79,84
+* structural similarity (scikit-image's algorithm; PARITY UNPINNED, see ssim_f32)
+                              -- /root/reference/test-cross-talk-model.py:80-82
 * per-plane min-max normalise, cast and flips of the input pipeline
                               -- /root/reference/train_model.py:166-167,211-232
 
@@ -485,6 +487,60 @@ def nmi_digitized(a: np.ndarray, b: np.ndarray) -> float:
     return nmi_from_joint(joint)
 
 
+def ssim_f32(a: np.ndarray, b: np.ndarray) -> float:
+    """Mean structural similarity as the reference calls it -- test-cross-talk-model.py:80-82:
+    ``ssim(img0, img1, data_range=max(img0.max(), img1.max()) - min(img0.min(), img1.min()))`` with scikit-image's
+    defaults (7x7 uniform window, K1 = 0.01, K2 = 0.03, sample covariance, float32 arithmetic for float32 images,
+    mean over the image cropped by 3 pixels, accumulated in float64).
+
+    PARITY UNPINNED for this function: scikit-image is neither vendored in /root/reference nor installed in the build
+    image, so no reference output could be recorded.  This is a restatement of the published algorithm of
+    ``skimage.metrics.structural_similarity`` (scikit-image 0.19-0.25, metrics/_structural_similarity.py) on top of the
+    one third-party routine it delegates to, ``scipy.ndimage.uniform_filter`` (scipy 1.18.1, installed here).
+    """
+    from scipy.ndimage import uniform_filter
+    a = np.asarray(a, dtype=np.float32)
+    b = np.asarray(b, dtype=np.float32)
+    data_range = np.max([a.max(), b.max()]) - np.min([a.min(), b.min()])       # np.float32, as at the call site
+    win, k1, k2 = 7, 0.01, 0.03
+    npix = win ** a.ndim
+    cov_norm = npix / (npix - 1)                                              # use_sample_covariance=True
+    ux = uniform_filter(a, size=win)
+    uy = uniform_filter(b, size=win)
+    uxx = uniform_filter(a * a, size=win)
+    uyy = uniform_filter(b * b, size=win)
+    uxy = uniform_filter(a * b, size=win)
+    vx = cov_norm * (uxx - ux * ux)
+    vy = cov_norm * (uyy - uy * uy)
+    vxy = cov_norm * (uxy - ux * uy)
+    c1 = (k1 * data_range) ** 2
+    c2 = (k2 * data_range) ** 2
+    a1, a2, b1, b2 = (2 * ux * uy + c1, 2 * vxy + c2, ux ** 2 + uy ** 2 + c1, vx + vy + c2)
+    smap = (a1 * a2) / (b1 * b2)
+    pad = (win - 1) // 2
+    return float(smap[pad:-pad, pad:-pad].mean(dtype=np.float64))
+
+
+def ssim_f64(a: np.ndarray, b: np.ndarray) -> float:
+    """The same definition evaluated in float64 with direct window sums (no float32 rounding anywhere): the yardstick
+    for how much of a difference is float32 noise of the definition itself."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    data_range = max(a.max(), b.max()) - min(a.min(), b.min())
+    win = 7
+
+    def box(img):
+        v = np.lib.stride_tricks.sliding_window_view(img, (win, win))
+        return v.mean(axis=(2, 3))
+
+    ux, uy, uxx, uyy, uxy = box(a), box(b), box(a * a), box(b * b), box(a * b)
+    cov_norm = 49.0 / 48.0
+    vx, vy, vxy = cov_norm * (uxx - ux * ux), cov_norm * (uyy - uy * uy), cov_norm * (uxy - ux * uy)
+    c1, c2 = (0.01 * data_range) ** 2, (0.03 * data_range) ** 2
+    smap = ((2 * ux * uy + c1) * (2 * vxy + c2)) / ((ux * ux + uy * uy + c1) * (vx + vy + c2))
+    return float(smap.mean())
+
+
 def tile_metrics_batch(x: torch.Tensor) -> Dict[str, np.ndarray]:
     """Per-image Pearson r, RMSE and histogram correlation of channel 0 vs channel 1 of an [N,2,H,W] float32 batch."""
     xs = x.detach().cpu().numpy()
@@ -493,6 +549,7 @@ def tile_metrics_batch(x: torch.Tensor) -> Dict[str, np.ndarray]:
             "rmse": np.array([rmse_f32(xs[i, 0], xs[i, 1]) for i in range(n)]),
             "hist_corr": np.array([hist_correlation(xs[i, 0], xs[i, 1]) for i in range(n)]),
             "nmi": np.array([nmi_digitized(xs[i, 0], xs[i, 1]) for i in range(n)]),
+            "ssim": np.array([ssim_f32(xs[i, 0], xs[i, 1]) for i in range(n)]),
             "hist": np.stack([np.stack([histogram256_f32(xs[i, 0]), histogram256_f32(xs[i, 1])]) for i in range(n)])
             if n else np.zeros((0, 2, 256), dtype=np.int64)}
 

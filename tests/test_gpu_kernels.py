@@ -98,6 +98,51 @@ def test_prepare_tiles_bit_exact(ctk, golden):
         ctk.prepare_tiles(torch.zeros(1, 2, 8, 8, dtype=torch.float64))      # host tensor: no CPU fallback
 
 
+def test_tile_ssim(ctk, golden):
+    """Structural similarity (test-cross-talk-model.py:80-82) against the oracle's restatement of
+    scikit-image's algorithm on scipy.ndimage.uniform_filter: the kernel follows the library's float32 / float64 operation
+    order, so the agreement is at float64 summation order (1e-9 absolute asked here), not at float32 noise (~1e-7).
+    Fixture tiles (normalised and raw intensities), synthetic tiles, a constant plane, both planes constant (0/0 -> NaN
+    like the library), a ragged tile size, and the exact properties ssim(x, x) == 1 and symmetry on a full 256-tile batch."""
+    tiles = torch.from_numpy(golden["tiles"].astype(np.float32))
+    xn = torch.stack([torch.stack([torch.from_numpy(orc.normalize_image(t[0].numpy())),
+                                   torch.from_numpy(orc.normalize_image(t[1].numpy()))]) for t in tiles])
+    xs, _ = orc.synthetic_batch(3, seed=5)
+    const = xs[:1].clone()
+    const[0, 1] = 0.25
+    quant = torch.round(xs[:1] * 6) / 6                      # large flat areas: variances cancel to exactly 0
+    x = torch.cat([xn, tiles, xs, const, quant], dim=0).contiguous()
+    got = ctk.ssim_per_image(x.cuda()).cpu().numpy()
+    ref = np.array([orc.ssim_f32(t[0].numpy(), t[1].numpy()) for t in x])
+    ref64 = np.array([orc.ssim_f64(t[0].numpy(), t[1].numpy()) for t in x])
+    print("ssim gpu", got, "\n  max |gpu - oracle|", np.abs(got - ref).max(), " max |oracle f32 - f64 definition|", np.abs(ref - ref64).max())
+    np.testing.assert_allclose(got, ref, atol=1e-9, rtol=0)
+    np.testing.assert_allclose(got[:5], ref64[:5], atol=1e-6, rtol=0)         # normalised tiles: float32 noise of the definition
+    with np.errstate(all="ignore"):
+        both = torch.full((1, 2, 16, 16), 0.5)
+        assert np.isnan(orc.ssim_f32(both[0, 0].numpy(), both[0, 1].numpy())) and np.isnan(ctk.ssim_per_image(both.cuda()).item())
+    rag = torch.rand(3, 2, 40, 72)
+    np.testing.assert_allclose(ctk.ssim_per_image(rag.cuda()).cpu().numpy(),
+                               [orc.ssim_f32(t[0].numpy(), t[1].numpy()) for t in rag], atol=1e-9, rtol=0)
+    small = torch.rand(2, 2, 7, 8)                            # a single window row
+    np.testing.assert_allclose(ctk.ssim_per_image(small.cuda()).cpu().numpy(),
+                               [orc.ssim_f32(t[0].numpy(), t[1].numpy()) for t in small], atol=1e-9, rtol=0)
+    assert ctk.ssim_per_image(torch.empty(0, 2, 32, 32).cuda()).numel() == 0
+    # full-size properties: identical planes give exactly 1, swapping the planes changes nothing
+    big, _ = orc.synthetic_batch(256, seed=11)
+    big = big.cuda()
+    same = big.clone()
+    same[:, 1] = same[:, 0]
+    assert torch.equal(ctk.ssim_per_image(same), torch.ones(256, dtype=torch.float64, device="cuda"))
+    a, b = ctk.ssim_per_image(big), ctk.ssim_per_image(big.flip(1).contiguous())
+    assert torch.allclose(a, b, rtol=0, atol=1e-13)
+    np.testing.assert_allclose(a[:4].cpu().numpy(), [orc.ssim_f32(t[0].numpy(), t[1].numpy()) for t in big[:4].cpu()], atol=1e-9, rtol=0)
+    with pytest.raises(ctk.CtkError):
+        ctk.ssim_per_image(torch.zeros(1, 2, 6, 32).cuda())   # smaller than the window
+    with pytest.raises(ctk.CtkError):
+        ctk.ssim_per_image(torch.zeros(1, 2, 32, 32))         # host tensor: no CPU fallback
+
+
 def test_tile_metrics_fused(ctk, golden):
     """Pearson + RMSE + 256-bin histograms + histogram correlation in one fused pass against the oracle
     restatement, the reference-call goldens, and np.histogram bit for bit -- on fixture tiles (normalised and raw),

@@ -195,6 +195,7 @@ def test_host_scorer_one_shot_and_stream(golden):
     np.testing.assert_allclose(m_all["rmse"].numpy(), ref_m["rmse"], rtol=2e-6)
     np.testing.assert_allclose(m_all["hist_corr"].numpy(), ref_m["hist_corr"], atol=1e-12, equal_nan=True)
     np.testing.assert_allclose(m_all["nmi"].numpy(), ref_m["nmi"], atol=1e-12)
+    np.testing.assert_allclose(m_all["ssim"].numpy(), ref_m["ssim"], atol=1e-9)
     with pytest.raises(ctk.CtkError):
         scorer.score(x.cuda())
     model.train()

@@ -125,3 +125,58 @@ def test_metrics_restatement_matches_reference_calls(golden):
         assert np.array_equal(orc.digitize256_f32(a), np.digitize(a, bins=np.linspace(a.min(), a.max(), 256)))
     const = np.full(1024, 0.5, np.float32)
     assert orc.nmi_digitized(const, const) == 1.0 and orc.nmi_digitized(const, awkward[1][:1024]) == 0.0
+
+
+def _ssim_device_model(a, b):
+    """NumPy model of the arithmetic ctk_tile_ssim_f32 performs (csrc/ssim.cu): direct 7-tap float64 sums, float32 rounding
+    after each 1-D pass, the SSIM map in float32 in the library's operation order, float64 mean."""
+    a = a.astype(np.float32)
+    b = b.astype(np.float32)
+    rng = np.float32(max(a.max(), b.max())) - np.float32(min(a.min(), b.min()))
+
+    def pass1d(img, axis):
+        v = np.lib.stride_tricks.sliding_window_view(img.astype(np.float64), 7, axis=axis)
+        s = np.zeros(v.shape[:-1])
+        for k in range(7):
+            s = s + v[..., k]
+        return (s / 7.0).astype(np.float32)
+
+    def box(img):
+        return pass1d(pass1d(img, 0), 1)
+
+    ux, uy, uxx, uyy, uxy = box(a), box(b), box(a * a), box(b * b), box(a * b)
+    cn = np.float32(49 / 48)
+    vx, vy, vxy = cn * (uxx - ux * ux), cn * (uyy - uy * uy), cn * (uxy - ux * uy)
+    t1, t2 = np.float32(0.01) * rng, np.float32(0.03) * rng
+    c1, c2 = t1 * t1, t2 * t2
+    with np.errstate(all="ignore"):
+        smap = (((np.float32(2) * ux) * uy + c1) * (np.float32(2) * vxy + c2)) / (((ux * ux + uy * uy) + c1) * ((vx + vy) + c2))
+    assert smap.dtype == np.float32
+    return float(smap.astype(np.float64).sum() / smap.size)
+
+
+def test_ssim_restatement(golden):
+    """SSIM (test-cross-talk-model.py:80-82).  scikit-image is not installed here, so the restatement cannot be pinned to
+    a reference output ("parity unpinned", oracle header); what can be checked on the CPU: known answers (identical
+    planes -> exactly 1, symmetry), agreement with an independent float64 evaluation of the definition up to float32 noise,
+    and that the operation-order model the CUDA kernel implements reproduces the scipy-based restatement."""
+    tiles = golden["tiles"].astype(np.float32)
+    cases = [(orc.normalize_image(t[0]), orc.normalize_image(t[1])) for t in tiles[:3]] + [(t[0], t[1]) for t in tiles[:3]]
+    xs, _ = orc.synthetic_batch(2, seed=5)
+    xs = xs.numpy()
+    cases += [(xs[0, 0], xs[0, 1]), (xs[1, 0], np.full_like(xs[1, 1], 0.25)), (np.round(xs[1, 0] * 6) / 6, np.round(xs[1, 1] * 6) / 6)]
+    r = np.random.default_rng(3)
+    cases += [(r.random((40, 72), dtype=np.float32), r.random((40, 72), dtype=np.float32)),
+              (r.random((7, 8), dtype=np.float32), r.random((7, 8), dtype=np.float32))]
+    for a, b in cases:
+        a, b = np.ascontiguousarray(a, dtype=np.float32), np.ascontiguousarray(b, dtype=np.float32)
+        v = orc.ssim_f32(a, b)
+        assert -1.0 <= v <= 1.0
+        assert v == orc.ssim_f32(b, a)                                      # symmetric, bit for bit
+        assert orc.ssim_f32(a, a) == 1.0                                    # identical planes
+        scale = max(1.0, float(max(a.max(), b.max()) - min(a.min(), b.min())))
+        assert abs(v - orc.ssim_f64(a, b)) <= (1e-6 if scale == 1.0 else 1e-3), (v, orc.ssim_f64(a, b))
+        assert abs(v - _ssim_device_model(a, b)) <= 1e-12, (v, _ssim_device_model(a, b))
+    with np.errstate(all="ignore"):
+        both = np.full((16, 16), 0.5, dtype=np.float32)
+        assert np.isnan(orc.ssim_f32(both, both.copy())) and np.isnan(_ssim_device_model(both, both.copy()))

@@ -7,7 +7,7 @@ Everything here drives hand-written sm_100a kernels in libctk.so through the C A
 """
 from ._lib import CtkError, EXPORTED_SYMBOLS, LIB_PATH, load
 from .engine import InferenceEngine
-from .metrics import nmi_per_image, pearson_per_image, tile_metrics
+from .metrics import nmi_per_image, pearson_per_image, ssim_per_image, tile_metrics
 from .models import (AdvancedRegressionModel, SimplifiedFeatureExtractionBranch, SimplifiedRegressionHead,
                      SimplifiedTwoBranchRegressionModel, accelerate, set_precision)
 from .optim import Adam, mse_loss
@@ -15,6 +15,6 @@ from .pipeline import DevicePrefetcher, HostScorer, prefetch_to_device
 from . import io, parallel
 from .io import prepare_tiles
 
-__all__ = ["CtkError", "EXPORTED_SYMBOLS", "LIB_PATH", "load", "InferenceEngine", "pearson_per_image", "tile_metrics", "nmi_per_image",
+__all__ = ["CtkError", "EXPORTED_SYMBOLS", "LIB_PATH", "load", "InferenceEngine", "pearson_per_image", "tile_metrics", "nmi_per_image", "ssim_per_image",
            "AdvancedRegressionModel", "SimplifiedFeatureExtractionBranch", "SimplifiedRegressionHead",
            "SimplifiedTwoBranchRegressionModel", "accelerate", "set_precision", "Adam", "mse_loss", "HostScorer", "DevicePrefetcher", "prefetch_to_device", "parallel", "io", "prepare_tiles"]

@@ -35,6 +35,8 @@ _SIGNATURES = {
     "ctk_prepare_tiles": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "ctk_tile_nmi_workspace_bytes": (c_size_t, [c_int]),
     "ctk_tile_nmi_f32": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "ctk_tile_ssim_workspace_bytes": (c_size_t, [c_int]),
+    "ctk_tile_ssim_f32": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "ctk_tile_metrics_workspace_bytes": (c_size_t, [c_int]),
     "ctk_tile_metrics_f32": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                                      c_void_p]),
@@ -142,7 +144,7 @@ def stream() -> c_void_p:
 
 
 # kernels launched per successful call (bench.py reports the sum as "gpu_launches")
-KERNELS_PER_CALL = {"ctk_pearson_f32": 2, "ctk_tile_metrics_f32": 4, "ctk_tile_nmi_f32": 4, "ctk_prepare_tiles": 1, "ctk_fold_bn_eval": 1, "ctk_pack_conv_weight_bf16": 1, "ctk_pack_first_weight": 1,
+KERNELS_PER_CALL = {"ctk_pearson_f32": 2, "ctk_tile_metrics_f32": 4, "ctk_tile_nmi_f32": 4, "ctk_tile_ssim_f32": 3, "ctk_prepare_tiles": 1, "ctk_fold_bn_eval": 1, "ctk_pack_conv_weight_bf16": 1, "ctk_pack_first_weight": 1,
                     "ctk_pack_fc1_weight_bf16": 1, "ctk_conv_first_eval": 1, "ctk_conv_first_pool_codes": 1, "ctk_pack_conv_weight_split_bf16": 1,
                     "ctk_pack_fc1_weight_split_bf16": 1, "ctk_conv_first_eval_split": 1, "ctk_conv3x3_tc_eval_split": 1, "ctk_conv3x3_tc_eval": 1,
                     "ctk_gemm_bf16_splitk": 1, "ctk_head_eval": 1, "ctk_mse_loss": 1, "ctk_adam_multi": 1,

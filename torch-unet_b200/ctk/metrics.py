@@ -53,6 +53,26 @@ def nmi_per_image(inputs: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def ssim_per_image(inputs: torch.Tensor) -> torch.Tensor:
+    """Mean structural similarity of channel 0 vs channel 1 of every tile, as the reference's evaluation loop calls
+    scikit-image (test-cross-talk-model.py:80-82: default 7x7 uniform window, ``data_range`` = max - min over both
+    planes).  ``inputs``: [N,2,H,W] float32 CUDA, H, W >= 7; returns float64 [N]."""
+    _lib.require_device(inputs, torch.float32, "inputs")
+    if inputs.dim() != 4 or inputs.shape[1] != 2:
+        raise _lib.CtkError(f"inputs must be [N,2,H,W], got {tuple(inputs.shape)}")
+    if not inputs.is_contiguous():
+        raise _lib.CtkError("inputs must be contiguous")
+    n, _, h, w = inputs.shape
+    out = torch.empty(n, device=inputs.device, dtype=torch.float64)
+    if n == 0:
+        return out
+    lib = _lib.load()
+    ws_bytes = lib.ctk_tile_ssim_workspace_bytes(c_int(n))
+    ws = torch.empty((ws_bytes + 7) // 8, device=inputs.device, dtype=torch.float64)
+    call("ctk_tile_ssim_f32", ptr(inputs), c_int(n), c_int(h), c_int(w), ptr(out), ptr(ws), c_size_t(ws_bytes), stream())
+    return out
+
+
 def tile_metrics(inputs: torch.Tensor, histograms: bool = True) -> dict:
     """Pearson r, RMSE and 256-bin histogram correlation of channel 0 vs channel 1 for every tile of ``inputs``
     ([N,2,H,W] float32, CUDA) in one fused pass -- test-cross-talk-model.py:59-70,79 without the device->host copy of the

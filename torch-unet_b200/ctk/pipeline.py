@@ -20,14 +20,14 @@ from typing import Iterable, Iterator, Tuple
 import torch
 
 from . import _lib
-from .metrics import nmi_per_image, pearson_per_image, tile_metrics
+from .metrics import nmi_per_image, pearson_per_image, ssim_per_image, tile_metrics
 from .models import get_engine
 
 
 class HostScorer:
     def __init__(self, model: torch.nn.Module, slice_tiles: int = 64, device: str = "cuda", metrics: str = "pearson"):
-        """``metrics``: "pearson" -> results are (scores, r);  "all" -> (scores, {"pearson", "rmse", "hist_corr", "nmi"}),
-        the device-computable comparison metrics of test-cross-talk-model.py:59-84 for every tile."""
+        """``metrics``: "pearson" -> results are (scores, r);  "all" -> (scores, {"pearson", "rmse", "ssim", "hist_corr",
+        "nmi"}), every comparison metric of test-cross-talk-model.py:59-85 for every tile."""
         if metrics not in ("pearson", "all"):
             raise _lib.CtkError("metrics must be 'pearson' or 'all'")
         self.metrics = metrics
@@ -54,10 +54,10 @@ class HostScorer:
                   "x": torch.empty((n, *tiles_host.shape[1:]), device=self.dev, dtype=tiles_host.dtype),
                   "scores": torch.empty(n, 1, device=self.dev, dtype=torch.float32),
                   "r": torch.empty(n, device=self.dev, dtype=torch.float64),
-                  "extra": torch.empty(3, n, device=self.dev, dtype=torch.float64),      # rmse, hist_corr, nmi
+                  "extra": torch.empty(4, n, device=self.dev, dtype=torch.float64),      # rmse, hist_corr, nmi, ssim
                   "scores_h": torch.empty(n, dtype=torch.float32, pin_memory=True),
                   "r_h": torch.empty(n, dtype=torch.float64, pin_memory=True),
-                  "extra_h": torch.empty(3, n, dtype=torch.float64, pin_memory=True),
+                  "extra_h": torch.empty(4, n, dtype=torch.float64, pin_memory=True),
                   "free": None, "done": None}
             self._slots[i] = sl
         return sl
@@ -97,6 +97,7 @@ class HostScorer:
                 sl["extra"][0, done_to:e] = m["rmse"].double()
                 sl["extra"][1, done_to:e] = m["hist_corr"]
                 sl["extra"][2, done_to:e] = nmi_per_image(part)
+                sl["extra"][3, done_to:e] = ssim_per_image(part)
             else:
                 pearson_per_image(part, out=sl["r"][done_to:e])
             engine.forward(part, out=sl["scores"][done_to:e])
@@ -111,7 +112,7 @@ class HostScorer:
         sl["done"] = torch.cuda.Event()
         sl["done"].record(main)
         self.h2d_bytes = tiles_host.numel() * tiles_host.element_size()
-        self.d2h_bytes = n * 4 + n * 8 + (3 * n * 8 if self.metrics == "all" else 0)
+        self.d2h_bytes = n * 4 + n * 8 + (4 * n * 8 if self.metrics == "all" else 0)
         return sl
 
     @staticmethod
@@ -119,7 +120,7 @@ class HostScorer:
         sl["done"].synchronize()
         if sl["all"]:
             ex = sl["extra_h"].clone()
-            return sl["scores_h"].clone(), {"pearson": sl["r_h"].clone(), "rmse": ex[0].float(), "hist_corr": ex[1], "nmi": ex[2]}
+            return sl["scores_h"].clone(), {"pearson": sl["r_h"].clone(), "rmse": ex[0].float(), "hist_corr": ex[1], "nmi": ex[2], "ssim": ex[3]}
         return sl["scores_h"].clone(), sl["r_h"].clone()
 
     # ------------------------------------------------------------------ public API
