@@ -436,18 +436,16 @@ def hist_correlation(a: np.ndarray, b: np.ndarray) -> float:
 def digitize256_f32(a: np.ndarray) -> np.ndarray:
     """``np.digitize(plane.flatten(), bins=np.linspace(plane.min(), plane.max(), 256))`` restated for a float32 plane
     (test-cross-talk-model.py:71-74): label = number of float32 edges ``k * step + min`` (last edge = max) that are <= x,
-    i.e. 1..256.  NumPy >= 2 keeps the edges in float32 (step = float32((max - min) / 255))."""
+    i.e. 1..256.  NumPy >= 2 keeps the edges in float32 (step = float32((max - min) / 255), one multiply and one add per
+    edge).  Planes whose range spans fewer than 256 float32 values get runs of equal edges; counting (rather than
+    guessing a bin from (x - min) / step) stays exact there.  Not restated: NumPy's denormal special case
+    (max - min != 0 but step == 0)."""
     x = np.asarray(a, dtype=np.float32).ravel()
     lo, hi = x.min(), x.max()
     step = np.float32((hi - lo) / np.float32(255))
     edges = (np.arange(256, dtype=np.float32) * step + lo).astype(np.float32)
     edges[-1] = hi
-    k = np.clip(((x - lo) / step).astype(np.int64) if step > 0 else np.full(x.shape, 255, np.int64), 0, 255)
-    k[edges[k] > x] -= 1
-    up = (k < 255)
-    up[up] &= edges[k[up] + 1] <= x[up]
-    k[up] += 1
-    return k + 1
+    return np.searchsorted(edges, x, side="right").astype(np.int64)
 
 
 def nmi_from_joint(joint: np.ndarray) -> float:

@@ -188,6 +188,11 @@ def test_tile_metrics_fused(ctk, golden):
     both_const = torch.full((1, 2, 32, 32), 0.5)
     assert ctk.nmi_per_image(both_const.cuda()).item() == 1.0
     np.testing.assert_allclose(ctk.nmi_per_image(rag.cuda()).cpu().numpy(), r2["nmi"], atol=1e-12)
+    # a range spanning fewer than 256 float32 values: runs of equal linspace edges (np.histogram refuses such planes,
+    # np.digitize does not)
+    narrow = (1000.0 + torch.rand(2, 2, 64, 64) * 1e-3).float().contiguous()
+    np.testing.assert_allclose(ctk.nmi_per_image(narrow.cuda()).cpu().numpy(),
+                               [orc.nmi_digitized(t[0].numpy(), t[1].numpy()) for t in narrow], atol=1e-12)
     # same Pearson as the stand-alone kernel
     np.testing.assert_allclose(got["pearson"].cpu().numpy(), ctk.pearson_per_image(x.cuda()).cpu().numpy(), atol=1e-12, equal_nan=True)
 

@@ -180,3 +180,37 @@ def test_ssim_restatement(golden):
     with np.errstate(all="ignore"):
         both = np.full((16, 16), 0.5, dtype=np.float32)
         assert np.isnan(orc.ssim_f32(both, both.copy())) and np.isnan(_ssim_device_model(both, both.copy()))
+
+
+def _adversarial_planes():
+    """float32 planes that stress the bin rules: values exactly on edges, tiny and huge ranges, negative offsets, denormal
+    steps, two-valued planes, heavy ties."""
+    r = np.random.default_rng(11)
+    out = [r.random(4096, dtype=np.float32),
+           (r.random(4096, dtype=np.float32) * np.float32(1e-30)),
+           (r.random(4096, dtype=np.float32) * np.float32(3e4) - np.float32(1.5e4)),
+           np.float32(1000.0) + r.random(4096, dtype=np.float32) * np.float32(1e-3),
+           (r.integers(0, 256, 4096) / np.float32(255)).astype(np.float32),          # every value an exact linspace edge
+           (r.integers(0, 257, 4096) / np.float32(256)).astype(np.float32),          # every value an exact histogram edge
+           (r.integers(0, 7, 4096) / np.float32(6)).astype(np.float32),
+           np.where(r.random(4096) < 0.5, np.float32(-2.5), np.float32(7.25)).astype(np.float32),
+           np.linspace(-1, 1, 4096, dtype=np.float32) ** 3,
+           np.nextafter(np.float32(0.5), np.float32(1), dtype=np.float32) * np.ones(4096, np.float32) + (r.integers(0, 3, 4096) * np.float32(6e-8)).astype(np.float32)]
+    for k in range(6):                                                                # random affine maps of random edges
+        lo, span = np.float32(r.normal() * 10), np.float32(abs(r.normal()) * 10.0 ** int(r.integers(-3, 4)))
+        out.append((lo + span * (r.integers(0, 256, 4096) / np.float32(255)).astype(np.float32)).astype(np.float32))
+    return out
+
+
+def test_bin_rules_match_numpy_on_adversarial_planes():
+    """The histogram and digitisation restatements (which the CUDA kernels follow operation by operation) against NumPy
+    itself on planes built to sit on bin edges (test-cross-talk-model.py:65-66, 71-74)."""
+    for x in _adversarial_planes():
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        try:
+            want = np.histogram(x, bins=256)[0]
+        except ValueError:               # range too narrow for 256 float32 bins: the reference's loop raises here too
+            want = None
+        if want is not None:
+            assert np.array_equal(orc.histogram256_f32(x), want)
+        assert np.array_equal(orc.digitize256_f32(x), np.digitize(x, bins=np.linspace(x.min(), x.max(), 256)))

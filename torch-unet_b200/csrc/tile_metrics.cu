@@ -252,8 +252,10 @@ __device__ __forceinline__ int digit_of(const DigitRule& d, float x) {      // 0
     k = static_cast<int>(__fdiv_rn(__fsub_rn(x, d.lo), d.step));
     k = min(max(k, 0), 255);
   }
-  if (digit_edge(d, k) > x) k -= 1;
-  if (k < 255 && digit_edge(d, k + 1) <= x) k += 1;
+  // largest k with edge_k <= x.  One step each way for ordinary planes; planes whose range spans fewer than 256 float32
+  // values have runs of equal edges, which the guess can miss by more than one.
+  while (k > 0 && digit_edge(d, k) > x) k -= 1;
+  while (k < 255 && digit_edge(d, k + 1) <= x) k += 1;
   return k;
 }
 
