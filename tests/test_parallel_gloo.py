@@ -38,6 +38,19 @@ def _worker(rank, world, port, q):
         w = lin.weight.detach().clone()
         dist.broadcast(w, src=0)
         ok &= torch.equal(w, lin.weight.detach())
+        # shard helpers: contiguous, disjoint, covering; mask rows follow the same split as the batch rows
+        from ctk.parallel import shard, shard_dropout_masks, shard_range
+        g = torch.Generator().manual_seed(7)
+        xb = torch.rand(9, 2, 4, 4, generator=g)                 # 9 images over 2 ranks: 5 + 4
+        masks = (torch.rand(9, 512, generator=g) > 0.5, torch.rand(9, 128, generator=g) > 0.5)
+        b, e = shard_range(9)
+        mine = shard(xb)
+        m1, m2 = shard_dropout_masks(masks)
+        ok &= (b, e) == ((0, 5) if rank == 0 else (5, 9)) and torch.equal(mine, xb[b:e])
+        ok &= torch.equal(m1, masks[0][b:e]) and torch.equal(m2, masks[1][b:e])
+        sizes = torch.tensor([e - b])
+        dist.all_reduce(sizes)
+        ok &= int(sizes) == 9
         q.put((rank, bool(ok), sync.collectives, sync.bytes_reduced))
     finally:
         dist.destroy_process_group()
@@ -59,3 +72,17 @@ def test_grad_synchronizer_world2_gloo():
         # one big tensor (512x700 fp32 = 1.4 MB) reduced in place + buckets for the rest
         assert ncoll >= 2
         assert nbytes == sum(n * 4 for n in (3, 128 * 64, 1, 512 * 700, 17 * 5 * 9, 64))
+
+
+def test_shard_range_covers_every_unit_once():
+    sys.path.insert(0, os.path.join(ROOT, "torch-unet_b200"))
+    from ctk.parallel import shard_range
+    for n in (0, 1, 7, 8, 255, 256, 2048, 1_000_000):
+        for world in (1, 2, 3, 4, 8):
+            spans = [shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [e - b for b, e in spans]
+            assert max(sizes) - min(sizes) <= 1 and sizes == sorted(sizes, reverse=True)
+    with pytest.raises(ValueError):
+        shard_range(4, 2, 2)

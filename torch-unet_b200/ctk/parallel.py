@@ -105,3 +105,28 @@ def broadcast_parameters(model: torch.nn.Module, src: int = 0, process_group=Non
     """All ranks start from rank ``src``'s parameters and buffers (what DDP does at construction)."""
     for t in list(model.parameters()) + list(model.buffers()):
         dist.broadcast(t.data, src=src, group=process_group)
+
+
+def shard_range(n: int, rank: Optional[int] = None, world: Optional[int] = None) -> Tuple[int, int]:
+    """[begin, end) of this rank's contiguous share of ``n`` units (tiles of an inference sweep, images of a global
+    training batch).  Ranks differ by at most one unit; the first ``n % world`` ranks get the extra one."""
+    rank = dist.get_rank() if rank is None else rank
+    world = dist.get_world_size() if world is None else world
+    if not (0 <= rank < world) or n < 0:
+        raise ValueError("need 0 <= rank < world and n >= 0")
+    base, extra = divmod(n, world)
+    begin = rank * base + min(rank, extra)
+    return begin, begin + base + (1 if rank < extra else 0)
+
+
+def shard(t: torch.Tensor, rank: Optional[int] = None, world: Optional[int] = None) -> torch.Tensor:
+    """This rank's rows of a tensor laid out over the GLOBAL batch (inputs, labels)."""
+    b, e = shard_range(t.shape[0], rank, world)
+    return t[b:e]
+
+
+def shard_dropout_masks(masks, rank: Optional[int] = None, world: Optional[int] = None):
+    """Parity mode: every rank draws (or is handed) the Dropout keep-masks of the GLOBAL batch and uses its
+    own rows, so that N ranks x B/N images reproduce the single-process step on B images mask for mask.
+    ``masks``: the (m1 [B,512], m2 [B,128]) pair ``TrainEngine.forced_masks`` takes."""
+    return tuple(shard(m, rank, world) for m in masks)
