@@ -328,3 +328,35 @@ def test_first_block_gram_and_stored_paths_agree(golden):
     assert whole <= 0.4 and rel_first <= 0.6
     for k in ss:
         np.testing.assert_allclose(sg[k].cpu().numpy(), ss[k].cpu().numpy(), rtol=2e-2, atol=2e-3, err_msg=k)
+
+
+@pytest.mark.parametrize("kind", ["single", "double"])
+def test_stream_overlap_gives_the_same_step(golden, kind):
+    """EXPERIMENTAL TrainEngine.overlap_streams (branches and weight gradients on side streams): the schedule changes,
+    the arithmetic does not -- loss identical, gradients within the run-to-run floor of the atomics-based statistics."""
+    import ctk
+    x, y = _data(golden)
+    n = x.shape[0]
+    masks = tuple(m.cuda() for m in orc.dropout_masks(n, 0.1 if kind == "single" else 0.5, seed=5))
+    res = {}
+    for overlap in (False, True):
+        model = _build(kind).cuda().train()
+        eng = ctk.models.get_train_engine(model)
+        eng.overlap_streams = overlap
+        eng.forced_masks = masks
+        opt = ctk.Adam(model.parameters(), lr=5e-4, weight_decay=1e-4)
+        losses = []
+        for _ in range(3):
+            opt.zero_grad()
+            loss = torch.nn.functional.mse_loss(model(x.cuda()), y.cuda())
+            loss.backward()
+            opt.step()
+            losses.append(loss.item())
+        torch.cuda.synchronize()
+        res[overlap] = (losses, {k: p.grad.detach().clone() for k, p in model.named_parameters()})
+    (l0, g0), (l1, g1) = res[False], res[True]
+    print(kind, "losses plain", l0, "overlap", l1)
+    assert abs(l0[0] - l1[0]) <= 2e-3 * abs(l0[0])
+    num = sum(((g0[k] - g1[k]).float() ** 2).sum().item() for k in g0)
+    den = sum((g0[k].float() ** 2).sum().item() for k in g0)
+    assert (num / den) ** 0.5 <= 0.5
