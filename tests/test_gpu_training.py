@@ -360,3 +360,44 @@ def test_stream_overlap_gives_the_same_step(golden, kind):
     num = sum(((g0[k] - g1[k]).float() ** 2).sum().item() for k in g0)
     den = sum((g0[k].float() ** 2).sum().item() for k in g0)
     assert (num / den) ** 0.5 <= 0.5
+
+
+def test_200_step_loss_curve_double_branch_against_reference_golden():
+    """Same as test_200_step_loss_curve_against_reference_golden for the double-branch model
+    (tests/golden/loss_curve_double.json; Dropout p = 0.5).  No second-thread-count curve exists for this model, so the
+    band comes from the bf16 emulation alone (it tracks the reference within 0.91-1.06 per window)."""
+    import json
+    import torch.nn.functional as F
+    import ctk
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "loss_curve_double.json")))
+    ref, emu = np.array(g["reference_fp32"]), np.array(g["oracle_bf16_emulation"])
+    steps, pool, batch = g["steps"], g["pool"], g["batch"]
+    x, y = orc.synthetic_batch(pool, seed=g["data_seed"])
+    model = _build("double").cuda().train()
+    eng = ctk.models.get_train_engine(model)
+    opt = ctk.Adam(model.parameters(), lr=g["lr"], weight_decay=g["weight_decay"])
+    crit = torch.nn.MSELoss()
+    xd, yd = x.cuda(), y.cuda()
+    losses = []
+    for t in range(steps):
+        s = (t * batch) % pool
+        torch.manual_seed(g["seed0"] + t)
+        m1 = (F.dropout(torch.ones(batch, 512), 0.5, True) != 0).float().cuda()
+        m2 = (F.dropout(torch.ones(batch, 128), 0.5, True) != 0).float().cuda()
+        eng.forced_masks = (m1, m2)
+        opt.zero_grad()
+        loss = crit(model(xd[s:s + batch]), yd[s:s + batch])
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    gpu = np.array(losses)
+    assert np.isfinite(gpu).all()
+    print("step-0 loss: reference %.6f  bf16-emulation %.6f  gpu %.6f" % (ref[0], emu[0], gpu[0]))
+    assert abs(gpu[0] - ref[0]) / ref[0] <= 0.02
+    for a in range(0, steps, 25):
+        gm = lambda v: float(np.exp(np.log(v[a:a + 25]).mean()))
+        r_, e_, g_ = gm(ref), gm(emu), gm(gpu)
+        print(f"{a:4d}    {r_:.5f}   {e_:.5f}   {g_:.5f}   {g_ / r_:.3f}   {e_ / r_:.3f}")
+        band = 1.5 * max(e_ / r_, r_ / e_, 1.15)
+        assert 1.0 / band <= g_ / r_ <= band, (a, g_, r_, e_)
+    assert abs(gpu[steps // 2:].mean() - ref[steps // 2:].mean()) / ref[steps // 2:].mean() <= 0.25
