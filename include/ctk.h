@@ -86,9 +86,11 @@ int ctk_tile_ssim_f32(const float* tiles, int n_tiles, int H, int W, double* ssi
  * Replaces: nn.BatchNorm2d/1d in eval(), regression_model.py:15,24,37,42; two_branch_regression.py:11,17,23,29,43,48. */
 int ctk_fold_bn_eval(const float* bias, const float* gamma, const float* beta, const float* rmean,
                      const float* rvar, float eps, int channels, float* scale, float* shift, void* stream);
-/* conv weight [Cout,Cin,3,3] fp32 -> [9][Cout][Cin] bf16 (tap-major, Cin contiguous = K-major GEMM B operand). */
+/* conv weight [Cout,Cin,3,3] fp32 (nn.Conv2d.weight of regression_model.py:23, two_branch_regression.py:16,22,28)
+ * -> [9][Cout][Cin] bf16 (tap-major, Cin contiguous = K-major GEMM B operand). */
 int ctk_pack_conv_weight_bf16(const float* w, int cout, int cin, void* w_packed_bf16, void* stream);
-/* first-layer weight [Cout,Cin,3,3] fp32 times per-channel scale -> fp32 [Cout][Cin*9] (BN folded into the taps). */
+/* first-layer weight [Cout,Cin,3,3] fp32 (regression_model.py:14, two_branch_regression.py:10) times per-channel scale
+ * -> fp32 [Cout][Cin*9] (BN folded into the taps). */
 int ctk_pack_first_weight(const float* w, const float* scale, int cout, int cin, float* w_folded, void* stream);
 /* FC1 weight [out, C*HW] fp32 (columns in NCHW-flatten order c*HW+p, nn.Flatten of regression_model.py:35 /
  * two_branch_regression.py:41) -> [out, HW*C] bf16 (columns in NHWC order p*C+c). */
@@ -264,7 +266,9 @@ int ctk_bn_act_pool_fwd(const void* y_bf16, int n, int H, int W, int channels, c
                         float slope, void* out_bf16, int out_cstride, int out_coffset, void* stream);
 /* Backward of MaxPool2d + LeakyReLU + BatchNorm2d(train).  dp = gradient of the pooled output (bf16 NHWC with channel
  * stride/offset).  reduce: sums[c] = sum(dA) (= dbeta), sums[C+c] = sum(dA*xhat) (= dgamma).  apply: dy (bf16 NHWC,
- * dense) = gamma*invstd*(dA - mean(dA) - xhat*mean(dA*xhat)).  The pool's argmax is recomputed (first maximum wins). */
+ * dense) = gamma*invstd*(dA - mean(dA) - xhat*mean(dA*xhat)).  The pool's argmax is recomputed (first maximum wins).
+ * Replaces: the autograd backward (train_model.py:422) of regression_model.py:15-17,24-26 and
+ * two_branch_regression.py:11-13,17-19,23-25,29-31. */
 int ctk_bn_bwd_reduce(const void* y_bf16, const void* dp_bf16, int dp_cstride, int dp_coffset, int n, int H, int W,
                       int channels, const float* scale, const float* shift, const float* mean, const float* invstd,
                       float slope, float* sums, void* stream);
@@ -281,7 +285,8 @@ int ctk_bn_bwd_apply(const void* y_bf16, const void* dp_bf16, int dp_cstride, in
 /* Weight gradients.  dw is fp32 in the reference layout [Cout,Cin,3,3] and is overwritten.
  * ctk_conv3x3_wgrad_tc: tcgen05 GEMM over pixels with MN-major NHWC operands (cin % 64 == 0, cout % 128 == 0).
  * ctk_conv_first_wgrad: first layer (cin 1 or 2), x = fp32 NCHW input planes.
- * Replaces: aten::convolution_backward (weight gradient). */
+ * Replaces: aten::convolution_backward (weight gradient) of the nn.Conv2d layers at regression_model.py:14,23 and
+ * two_branch_regression.py:10,16,22,28, reached through loss.backward() (train_model.py:422). */
 int ctk_conv3x3_wgrad_tc(const void* dy_bf16, const void* x_bf16, int n, int H, int W, int cin, int cout, float* dw,
                          void* stream);
 int ctk_conv_first_wgrad(const void* dy_bf16, const float* x, int n, int c_total, int c_offset, int cin, int H, int W,

@@ -67,9 +67,13 @@ def ssim_per_image(inputs: torch.Tensor) -> torch.Tensor:
     if n == 0:
         return out
     lib = _lib.load()
-    ws_bytes = lib.ctk_tile_ssim_workspace_bytes(c_int(n))
+    chunk = 65535                                   # one grid row per tile: the entry point takes at most 65535 tiles
+    ws_bytes = lib.ctk_tile_ssim_workspace_bytes(c_int(min(n, chunk)))
     ws = torch.empty((ws_bytes + 7) // 8, device=inputs.device, dtype=torch.float64)
-    call("ctk_tile_ssim_f32", ptr(inputs), c_int(n), c_int(h), c_int(w), ptr(out), ptr(ws), c_size_t(ws_bytes), stream())
+    for s in range(0, n, chunk):
+        e = min(n, s + chunk)
+        call("ctk_tile_ssim_f32", ptr(inputs[s:e]), c_int(e - s), c_int(h), c_int(w), ptr(out[s:e]), ptr(ws),
+             c_size_t(ws_bytes), stream())
     return out
 
 
