@@ -202,6 +202,7 @@ def run_train(args, shared_pg=False):
     torch.manual_seed(0)
     model = (ctk.SimplifiedTwoBranchRegressionModel(initial_filters_per_branch=64) if kind == "double"
              else ctk.AdvancedRegressionModel(initial_filters=128, num_conv_blocks=6)).to(dev).train()
+    ctk.models.get_train_engine(model).overlap_streams = bool(getattr(args, "overlap_streams", False))
     sync = None
     if world > 1:
         ctk.parallel.broadcast_parameters(model)
@@ -345,6 +346,8 @@ def main():
     ap.add_argument("--mode", default="infer", choices=["infer", "train"],
                     help="infer = BASELINE configs[1] (default, the headline line); train = configs[2]/[3] training step")
     ap.add_argument("--model", default="double", choices=["double", "single"])
+    ap.add_argument("--overlap-streams", action="store_true",
+                    help="train mode, EXPERIMENTAL: branches and weight gradients on side streams (TrainEngine.overlap_streams)")
     ap.add_argument("--batch", type=int, default=BATCH, help="per-GPU batch (train mode)")
     args = ap.parse_args()
     if args.mode == "train":

@@ -328,3 +328,79 @@ def test_first_block_gram_and_stored_paths_agree(golden):
     assert whole <= 0.4 and rel_first <= 0.6
     for k in ss:
         np.testing.assert_allclose(sg[k].cpu().numpy(), ss[k].cpu().numpy(), rtol=2e-2, atol=2e-3, err_msg=k)
+
+
+@pytest.mark.parametrize("kind", ["single", "double"])
+def test_stream_overlap_gives_the_same_step(golden, kind):
+    """EXPERIMENTAL TrainEngine.overlap_streams (branches and weight gradients on side streams): the schedule changes,
+    the arithmetic does not -- loss identical, gradients within the run-to-run floor of the atomics-based statistics."""
+    import ctk
+    x, y = _data(golden)
+    n = x.shape[0]
+    masks = tuple(m.cuda() for m in orc.dropout_masks(n, 0.1 if kind == "single" else 0.5, seed=5))
+    res = {}
+    for overlap in (False, True):
+        model = _build(kind).cuda().train()
+        eng = ctk.models.get_train_engine(model)
+        eng.overlap_streams = overlap
+        eng.forced_masks = masks
+        opt = ctk.Adam(model.parameters(), lr=5e-4, weight_decay=1e-4)
+        losses = []
+        for _ in range(3):
+            opt.zero_grad()
+            loss = torch.nn.functional.mse_loss(model(x.cuda()), y.cuda())
+            loss.backward()
+            opt.step()
+            losses.append(loss.item())
+        torch.cuda.synchronize()
+        res[overlap] = (losses, {k: p.grad.detach().clone() for k, p in model.named_parameters()})
+    (l0, g0), (l1, g1) = res[False], res[True]
+    print(kind, "losses plain", l0, "overlap", l1)
+    assert abs(l0[0] - l1[0]) <= 2e-3 * abs(l0[0])
+    num = sum(((g0[k] - g1[k]).float() ** 2).sum().item() for k in g0)
+    den = sum((g0[k].float() ** 2).sum().item() for k in g0)
+    assert (num / den) ** 0.5 <= 0.5
+
+
+def test_200_step_loss_curve_double_branch_against_reference_golden():
+    """Same as test_200_step_loss_curve_against_reference_golden for the double-branch model
+    (tests/golden/loss_curve_double.json; Dropout p = 0.5).  The band comes from the bf16 emulation (0.91-1.06 per window) and the
+    reference's own 5-thread re-run (0.97-1.01)."""
+    import json
+    import torch.nn.functional as F
+    import ctk
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "loss_curve_double.json")))
+    ref, emu = np.array(g["reference_fp32"]), np.array(g["oracle_bf16_emulation"])
+    self5 = np.array(json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden",
+                                                   "loss_curve_double_threads5.json")))["reference_fp32"])
+    steps, pool, batch = g["steps"], g["pool"], g["batch"]
+    x, y = orc.synthetic_batch(pool, seed=g["data_seed"])
+    model = _build("double").cuda().train()
+    eng = ctk.models.get_train_engine(model)
+    opt = ctk.Adam(model.parameters(), lr=g["lr"], weight_decay=g["weight_decay"])
+    crit = torch.nn.MSELoss()
+    xd, yd = x.cuda(), y.cuda()
+    losses = []
+    for t in range(steps):
+        s = (t * batch) % pool
+        torch.manual_seed(g["seed0"] + t)
+        m1 = (F.dropout(torch.ones(batch, 512), 0.5, True) != 0).float().cuda()
+        m2 = (F.dropout(torch.ones(batch, 128), 0.5, True) != 0).float().cuda()
+        eng.forced_masks = (m1, m2)
+        opt.zero_grad()
+        loss = crit(model(xd[s:s + batch]), yd[s:s + batch])
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    gpu = np.array(losses)
+    assert np.isfinite(gpu).all()
+    print("step-0 loss: reference %.6f  bf16-emulation %.6f  gpu %.6f" % (ref[0], emu[0], gpu[0]))
+    assert abs(gpu[0] - ref[0]) / ref[0] <= 0.02
+    for a in range(0, steps, 25):
+        gm = lambda v: float(np.exp(np.log(v[a:a + 25]).mean()))
+        r_, e_, g_ = gm(ref), gm(emu), gm(gpu)
+        print(f"{a:4d}    {r_:.5f}   {e_:.5f}   {g_:.5f}   {g_ / r_:.3f}   {e_ / r_:.3f}")
+        s_ = gm(self5)
+        band = 1.5 * max(e_ / r_, r_ / e_, s_ / r_, r_ / s_, 1.15)
+        assert 1.0 / band <= g_ / r_ <= band, (a, g_, r_, e_)
+    assert abs(gpu[steps // 2:].mean() - ref[steps // 2:].mean()) / ref[steps // 2:].mean() <= 0.25

@@ -10,6 +10,8 @@
 //   forward : 2 B/elem read + 0.5 B/elem written
 //   reduce  : 2 B/elem + 0.5 B/elem (dP) read
 //   apply   : 2 B/elem + 0.5 B/elem read, 2 B/elem written
+#include <cstdlib>
+
 #include "ctk_common.h"
 #include "ctk_ptx.cuh"
 
@@ -333,6 +335,17 @@ bn_bwd_apply_kernel(const uint4* __restrict__ y, const __nv_bfloat16* __restrict
   }
 }
 
+// EXPERIMENTAL (branch wip/overlap-streams): CTK_BN_BLOCK=128 launches the streaming BatchNorm passes with 128-thread CTAs
+// so that one of them fits beside a resident tensor-core conv CTA (register budget).  Default 256.
+inline int bn_block_threads() {
+  static const int v = [] {
+    const char* e = getenv("CTK_BN_BLOCK");
+    const int t = e ? atoi(e) : 256;
+    return (t == 64 || t == 128 || t == 256) ? t : 256;
+  }();
+  return v;
+}
+
 // grid for the pooled-pixel walks: `slots` pooled pixels per CTA pass, a few CTAs per SM
 inline int grid_for_pixels(long long pooled_pixels, int slots, int per_iter) {
   const long long blocks = (pooled_pixels + static_cast<long long>(slots) * per_iter - 1) / (static_cast<long long>(slots) * per_iter);
@@ -379,7 +392,7 @@ int ctk_bn_act_pool_fwd(const void* y_bf16, int n, int H, int W, int channels, c
               out_coffset + channels <= out_cstride);
   CTK_REQUIRE(channels <= 2048);
   const int c8 = channels / 8;
-  const int threads = (256 / c8) * c8;                 // a whole number of channel groups per CTA
+  const int threads = ((bn_block_threads() >= c8 ? bn_block_threads() : 256) / c8) * c8;   // whole channel groups per CTA
   const long long pooled = static_cast<long long>(n) * (H / 2) * (W / 2);
   bn_act_pool_fwd_kernel<<<grid_for_pixels(pooled, threads / c8, 2), threads, 0, ctk::as_stream(stream)>>>(
       static_cast<const uint4*>(y_bf16), H, W, c8, scale, shift, slope, static_cast<__nv_bfloat16*>(out_bf16),
@@ -437,7 +450,7 @@ int ctk_bn_bwd_apply(const void* y_bf16, const void* dp_bf16, int dp_cstride, in
               dp_coffset + channels <= dp_cstride);
   CTK_REQUIRE(channels <= 2048);
   const int c8 = channels / 8;
-  const int threads = (256 / c8) * c8;
+  const int threads = ((bn_block_threads() >= c8 ? bn_block_threads() : 256) / c8) * c8;
   const long long pooled = static_cast<long long>(n) * (H / 2) * (W / 2);
   const float inv_count = 1.f / (static_cast<float>(n) * H * W);
   bn_bwd_apply_kernel<<<grid_for_pixels(pooled, threads / c8, 2), threads, 0, ctk::as_stream(stream)>>>(

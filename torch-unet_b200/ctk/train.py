@@ -8,6 +8,7 @@ runs unchanged; PyTorch only owns the tensors and the graph edge.
 """
 from __future__ import annotations
 
+import contextlib
 from ctypes import c_double, c_float, c_int, c_longlong
 from typing import Callable, Dict, List, Optional, Tuple
 
@@ -56,8 +57,28 @@ class TrainEngine:
         self.stat_allreduce: Optional[Callable[[torch.Tensor], None]] = None
         self.stat_world: int = 1
         self._saved: Optional[dict] = None
+        # EXPERIMENTAL (not yet measured on a GPU): run every branch's conv stack on its own stream and every wgrad on a
+        # further side stream, so that the HBM-bound BatchNorm passes of one branch / layer overlap the tensor-bound conv
+        # kernels of the other.  Off by default; see DESIGN.md section 8.
+        self.overlap_streams: bool = False
+        self._streams: Dict[Tuple[str, int, int], torch.cuda.Stream] = {}
 
     # ------------------------------------------------------------------ helpers
+    def _side_stream(self, kind: str, index: int, dev) -> torch.cuda.Stream:
+        key = (kind, index, dev.index if dev.index is not None else torch.cuda.current_device())
+        st = self._streams.get(key)
+        if st is None:
+            st = self._streams[key] = torch.cuda.Stream(device=dev)
+        return st
+
+    @staticmethod
+    def _join(main: torch.cuda.Stream, side_streams) -> None:
+        """``main`` waits for everything enqueued so far on every side stream."""
+        for st in side_streams:
+            ev = torch.cuda.Event()
+            ev.record(st)
+            main.wait_event(ev)
+
     @staticmethod
     def _new(shape, dtype, dev):
         return torch.empty(shape, device=dev, dtype=dtype)
@@ -93,6 +114,65 @@ class TrainEngine:
         call("ctk_colstat", ptr(t), c_int(1), c_longlong(0), c_int(f), ptr(None), c_int(n), c_int(f), ptr(None), ptr(st), stream())
         return st[:f]
 
+    def _forward_branch(self, br, x: torch.Tensor, feat: torch.Tensor, c_off: int) -> List[dict]:
+        """Conv stack of one branch on the CURRENT stream; the last block writes its channel range of ``feat``."""
+        n, c_total, H, W = x.shape
+        dev = x.device
+        h, w = H, W
+        cur = None
+        blocks = []
+        for li, (conv, bn) in enumerate(br.pairs):
+            cout, cin = conv.out_channels, conv.in_channels
+            last = li == len(br.pairs) - 1
+            if last:
+                dst, cstride, coff = feat, self.feat_channels, c_off
+            else:
+                dst, cstride, coff = self._new((n, h // 2, w // 2, cout), torch.bfloat16, dev), cout, 0
+            if li == 0 and self.first_block_mode == "gram":
+                # first block: statistics from the input's patch Gram matrix, then the fused eval-style kernel;
+                # the full-resolution conv output is never written
+                T = 9 * cin
+                gram = self._new((T + T * T,), torch.float64, dev)
+                call("ctk_first_patch_gram", ptr(x), c_int(n), c_int(c_total), c_int(br.c_offset), c_int(cin), c_int(h),
+                     c_int(w), ptr(gram), stream())
+                self._sync_stats(gram)
+                count = float(n) * h * w * self.stat_world
+                mom = self._new((2 * cout,), torch.float32, dev)
+                call("ctk_first_moments", ptr(gram), ptr(conv.weight), c_int(cout), c_int(cin), c_double(count),
+                     ptr(mom), stream())
+                scale, shift, mean, invstd = self._bn_finalize(mom, count, conv.bias, bn, dev, moments=True)
+                wfold = self._new((cout, T), torch.float32, dev)
+                call("ctk_pack_first_weight", ptr(conv.weight), ptr(scale), c_int(cout), c_int(cin), ptr(wfold), stream())
+                codes = self._new((n, h // 2, w // 2, cout // 8), torch.int32, dev)
+                call("ctk_conv_first_pool_codes", ptr(x), c_int(n), c_int(c_total), c_int(br.c_offset), c_int(cin), c_int(h),
+                     c_int(w), ptr(wfold), ptr(shift), c_int(cout), c_float(LEAKY_SLOPE), ptr(dst), c_int(cstride),
+                     c_int(coff), ptr(codes), stream())
+                blocks.append({"y": None, "x_in": None, "pooled": (dst, cstride, coff), "scale": scale, "shift": shift,
+                               "mean": mean, "invstd": invstd, "h": h, "w": w, "conv": conv, "bn": bn, "gram": gram,
+                               "codes": codes})
+                cur = dst
+                h, w = h // 2, w // 2
+                continue
+            y = self._new((n, h, w, cout), torch.bfloat16, dev)
+            stats = self._new((2 * cout,), torch.float32, dev)
+            if li == 0:
+                call("ctk_conv_first_raw", ptr(x), c_int(n), c_int(c_total), c_int(br.c_offset), c_int(cin), c_int(h),
+                     c_int(w), ptr(conv.weight), c_int(cout), ptr(y), ptr(stats), stream())
+            else:
+                wp = self._new((9, cout, cin), torch.bfloat16, dev)
+                call("ctk_pack_conv_weight_bf16", ptr(conv.weight), c_int(cout), c_int(cin), ptr(wp), stream())
+                call("ctk_conv3x3_tc_raw", ptr(cur), c_int(n), c_int(h), c_int(w), c_int(cin), ptr(wp), c_int(cout),
+                     ptr(y), ptr(stats), stream(), meta={"flops": 2.0 * n * h * w * cout * 9 * cin})
+            self._sync_stats(stats)
+            scale, shift, mean, invstd = self._bn_finalize(stats, float(n) * h * w * self.stat_world, conv.bias, bn, dev)
+            call("ctk_bn_act_pool_fwd", ptr(y), c_int(n), c_int(h), c_int(w), c_int(cout), ptr(scale), ptr(shift),
+                 c_float(LEAKY_SLOPE), ptr(dst), c_int(cstride), c_int(coff), stream())
+            blocks.append({"y": y, "x_in": cur, "pooled": (dst, cstride, coff), "scale": scale, "shift": shift, "mean": mean, "invstd": invstd,
+                           "h": h, "w": w, "conv": conv, "bn": bn})
+            cur = dst
+            h, w = h // 2, w // 2
+        return blocks
+
     # ------------------------------------------------------------------ forward
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         _lib.require_device(x, torch.float32, "input batch")
@@ -113,62 +193,25 @@ class TrainEngine:
         sv = {"x": x, "n": n, "H": H, "W": W, "m_pad": m_pad, "blocks": []}
         feat = torch.zeros((m_pad, hf, wf, self.feat_channels), device=dev, dtype=torch.bfloat16)
         c_off = 0
-        for br in self.branches:
-            h, w = H, W
-            cur = None
-            blocks = []
-            for li, (conv, bn) in enumerate(br.pairs):
-                cout, cin = conv.out_channels, conv.in_channels
-                last = li == len(br.pairs) - 1
-                if last:
-                    dst, cstride, coff = feat, self.feat_channels, c_off
-                else:
-                    dst, cstride, coff = self._new((n, h // 2, w // 2, cout), torch.bfloat16, dev), cout, 0
-                if li == 0 and self.first_block_mode == "gram":
-                    # first block: statistics from the input's patch Gram matrix, then the fused eval-style kernel;
-                    # the full-resolution conv output is never written
-                    T = 9 * cin
-                    gram = self._new((T + T * T,), torch.float64, dev)
-                    call("ctk_first_patch_gram", ptr(x), c_int(n), c_int(c_total), c_int(br.c_offset), c_int(cin), c_int(h),
-                         c_int(w), ptr(gram), stream())
-                    self._sync_stats(gram)
-                    count = float(n) * h * w * self.stat_world
-                    mom = self._new((2 * cout,), torch.float32, dev)
-                    call("ctk_first_moments", ptr(gram), ptr(conv.weight), c_int(cout), c_int(cin), c_double(count),
-                         ptr(mom), stream())
-                    scale, shift, mean, invstd = self._bn_finalize(mom, count, conv.bias, bn, dev, moments=True)
-                    wfold = self._new((cout, T), torch.float32, dev)
-                    call("ctk_pack_first_weight", ptr(conv.weight), ptr(scale), c_int(cout), c_int(cin), ptr(wfold), stream())
-                    codes = self._new((n, h // 2, w // 2, cout // 8), torch.int32, dev)
-                    call("ctk_conv_first_pool_codes", ptr(x), c_int(n), c_int(c_total), c_int(br.c_offset), c_int(cin), c_int(h),
-                         c_int(w), ptr(wfold), ptr(shift), c_int(cout), c_float(LEAKY_SLOPE), ptr(dst), c_int(cstride),
-                         c_int(coff), ptr(codes), stream())
-                    blocks.append({"y": None, "x_in": None, "pooled": (dst, cstride, coff), "scale": scale, "shift": shift,
-                                   "mean": mean, "invstd": invstd, "h": h, "w": w, "conv": conv, "bn": bn, "gram": gram,
-                                   "codes": codes})
-                    cur = dst
-                    h, w = h // 2, w // 2
-                    continue
-                y = self._new((n, h, w, cout), torch.bfloat16, dev)
-                stats = self._new((2 * cout,), torch.float32, dev)
-                if li == 0:
-                    call("ctk_conv_first_raw", ptr(x), c_int(n), c_int(c_total), c_int(br.c_offset), c_int(cin), c_int(h),
-                         c_int(w), ptr(conv.weight), c_int(cout), ptr(y), ptr(stats), stream())
-                else:
-                    wp = self._new((9, cout, cin), torch.bfloat16, dev)
-                    call("ctk_pack_conv_weight_bf16", ptr(conv.weight), c_int(cout), c_int(cin), ptr(wp), stream())
-                    call("ctk_conv3x3_tc_raw", ptr(cur), c_int(n), c_int(h), c_int(w), c_int(cin), ptr(wp), c_int(cout),
-                         ptr(y), ptr(stats), stream(), meta={"flops": 2.0 * n * h * w * cout * 9 * cin})
-                self._sync_stats(stats)
-                scale, shift, mean, invstd = self._bn_finalize(stats, float(n) * h * w * self.stat_world, conv.bias, bn, dev)
-                call("ctk_bn_act_pool_fwd", ptr(y), c_int(n), c_int(h), c_int(w), c_int(cout), ptr(scale), ptr(shift),
-                     c_float(LEAKY_SLOPE), ptr(dst), c_int(cstride), c_int(coff), stream())
-                blocks.append({"y": y, "x_in": cur, "pooled": (dst, cstride, coff), "scale": scale, "shift": shift, "mean": mean, "invstd": invstd,
-                               "h": h, "w": w, "conv": conv, "bn": bn})
-                cur = dst
-                h, w = h // 2, w // 2
+        main = torch.cuda.current_stream(dev)
+        overlap = self.overlap_streams and len(self.branches) > 1
+        used_streams = []
+        if overlap:
+            fork = torch.cuda.Event()
+            fork.record(main)                   # feat is zero-filled and x is ready behind this point
+        for bi, br in enumerate(self.branches):
+            if overlap:
+                side = self._side_stream("branch", bi, dev)
+                side.wait_event(fork)
+                used_streams.append(side)
+                with torch.cuda.stream(side):
+                    blocks = self._forward_branch(br, x, feat, c_off)
+            else:
+                blocks = self._forward_branch(br, x, feat, c_off)
             sv["blocks"].append({"branch": br, "blocks": blocks, "c_off": c_off})
             c_off += br.channels[-1]
+        if overlap:
+            self._join(main, used_streams)
         sv["feat"], sv["hf"], sv["wf"] = feat, hf, wf
 
         # ---- FC1 (tcgen05 split-K) + fp32 head
@@ -226,6 +269,83 @@ class TrainEngine:
             out.append(None if p == 0.0 else (torch.rand(n, f, device=dev) >= p).float())
         return tuple(out)
 
+    def _backward_branch(self, entry: dict, sv: dict, dfeat: torch.Tensor, done, wgrad_stream=None) -> None:
+        """Backward of one branch's conv stack (last block first) on the CURRENT stream."""
+        x, n = sv["x"], sv["n"]
+        dev = x.device
+        br, blocks = entry["branch"], entry["blocks"]
+        dp, dp_cstride, dp_coff = dfeat, self.feat_channels, entry["c_off"]
+        for li in range(len(blocks) - 1, -1, -1):
+            b = blocks[li]
+            conv, bn, h, w = b["conv"], b["bn"], b["h"], b["w"]
+            cout, cin = conv.out_channels, conv.in_channels
+            sums = self._new((2 * cout,), torch.float32, dev)
+            if b.get("gram") is not None:
+                # first block: the forward pass stored arg-max / sign codes, so the data term of the weight gradient and
+                # sum(dA) are one gather over the input; sum(dA * xhat) follows from them in the finalize kernel
+                if dp_cstride != cout or dp_coff != 0:
+                    raise _lib.CtkError("the first block's output gradient must be dense")
+                T = 9 * cin
+                t1 = self._new((cout, T), torch.float32, dev)
+                call("ctk_first_wgrad_codes", ptr(x), c_int(n), c_int(x.shape[1]), c_int(br.c_offset), c_int(cin), c_int(h),
+                     c_int(w), ptr(b["codes"]), ptr(dp), c_int(cout), c_float(LEAKY_SLOPE), ptr(t1), ptr(sums), stream())
+                dw = self._new(tuple(conv.weight.shape), torch.float32, dev)
+                # SyncBN: the saved Gram matrix is already the global one, so reduce t1 / sum(dA) too and form the
+                # global gradient on every rank; dividing by the world size makes the exchange's mean leave it as is
+                self._sync_stats(t1)
+                self._sync_stats(sums)
+                call("ctk_first_wgrad_finalize", ptr(t1), ptr(b["gram"]), ptr(conv.weight), ptr(b["scale"]), ptr(b["mean"]),
+                     ptr(b["invstd"]), ptr(sums), c_double(float(n) * h * w * self.stat_world), c_int(cout), c_int(cin),
+                     ptr(dw), stream())
+                if self.stat_world > 1:
+                    dw.div_(self.stat_world)
+                    sums.div_(self.stat_world)
+                done(bn.bias, sums[:cout])
+                done(bn.weight, sums[cout:])
+                done(conv.weight, dw)
+                done(conv.bias, torch.zeros_like(conv.bias))
+                continue
+            pooled, p_cstride, p_coff = b["pooled"]
+            call("ctk_bn_bwd_reduce_pooled", ptr(pooled), c_int(p_cstride), c_int(p_coff), ptr(dp), c_int(dp_cstride),
+                 c_int(dp_coff), c_longlong(n * (h // 2) * (w // 2)), c_int(cout), ptr(bn.weight), ptr(bn.bias),
+                 c_float(LEAKY_SLOPE), ptr(sums), stream())
+            done(bn.bias, sums[:cout])
+            done(bn.weight, sums[cout:])
+            dy = self._new((n, h, w, cout), torch.bfloat16, dev)
+            call("ctk_bn_bwd_apply", ptr(b["y"]), ptr(dp), c_int(dp_cstride), c_int(dp_coff), c_int(n), c_int(h), c_int(w),
+                 c_int(cout), ptr(b["scale"]), ptr(b["shift"]), ptr(b["mean"]), ptr(b["invstd"]), ptr(self._global_sums(sums)),
+                 c_float(LEAKY_SLOPE), ptr(dy), stream())
+            b["y"] = None
+            if wgrad_stream is not None:
+                # the weight gradient is off the critical path (nothing in this backward reads it): a side stream lets the
+                # tensor-bound wgrad run under the HBM-bound BatchNorm passes of the next layer down
+                ready = torch.cuda.Event()
+                ready.record()
+                wgrad_stream.wait_event(ready)
+                dy.record_stream(wgrad_stream)
+                wg_ctx = torch.cuda.stream(wgrad_stream)
+            else:
+                wg_ctx = contextlib.nullcontext()
+            with wg_ctx:
+                dw = self._new(tuple(conv.weight.shape), torch.float32, dev)
+                if li == 0:
+                    call("ctk_conv_first_wgrad", ptr(dy), ptr(x), c_int(n), c_int(x.shape[1]), c_int(br.c_offset), c_int(cin),
+                         c_int(h), c_int(w), c_int(cout), ptr(dw), stream())
+                else:
+                    call("ctk_conv3x3_wgrad_tc", ptr(dy), ptr(b["x_in"]), c_int(n), c_int(h), c_int(w), c_int(cin), c_int(cout),
+                         ptr(dw), stream(), meta={"flops": 2.0 * n * h * w * cout * 9 * cin})
+                done(conv.weight, dw)
+            # the conv bias feeds a train-mode BatchNorm, so its gradient is sum(dY) = 0 identically
+            done(conv.bias, torch.zeros_like(conv.bias))
+            if li > 0:
+                wg = self._new((9, cin, cout), torch.bfloat16, dev)
+                call("ctk_pack_conv_weight_dgrad_bf16", ptr(conv.weight), c_int(cout), c_int(cin), ptr(wg), stream())
+                dx = self._new((n, h, w, cin), torch.bfloat16, dev)
+                call("ctk_conv3x3_tc_raw", ptr(dy), c_int(n), c_int(h), c_int(w), c_int(cout), ptr(wg), c_int(cin), ptr(dx),
+                     ptr(None), stream(), meta={"flops": 2.0 * n * h * w * cout * 9 * cin})
+                dp, dp_cstride, dp_coff = dx, cin, 0
+            del dy
+
     # ------------------------------------------------------------------ backward
     def backward(self, dout: torch.Tensor) -> Dict[torch.nn.Parameter, torch.Tensor]:
         sv = self._saved
@@ -236,12 +356,26 @@ class TrainEngine:
         _lib.require_device(dout, torch.float32, "output gradient")
         grads: Dict[torch.nn.Parameter, torch.Tensor] = {}
 
+        n, dev = sv["n"], dout.device
+        overlap = self.overlap_streams
+        comm = self._side_stream("comm", 0, dev) if overlap and self.on_grad_ready is not None else None
+
         def done(p, g):
             grads[p] = g
-            if self.on_grad_ready is not None:
+            if self.on_grad_ready is None:
+                return
+            if comm is None:
+                self.on_grad_ready(p, g)
+                return
+            # gradients are produced on several streams: hand them to the exchange from ONE stream that has waited for
+            # each producer, so that a bucket flushed under it never contains a tensor that is still being written
+            ev = torch.cuda.Event()
+            ev.record()
+            comm.wait_event(ev)
+            g.record_stream(comm)
+            with torch.cuda.stream(comm):
                 self.on_grad_ready(p, g)
 
-        n, dev = sv["n"], dout.device
         fc1, fc2, fc3 = self.lin
         f1, f2 = fc1.out_features, fc2.out_features
         K = fc1.in_features
@@ -303,69 +437,29 @@ class TrainEngine:
         call("ctk_gemm_bf16_bt_out_bf16", ptr(dz1_bf), ptr(sv["w1p"]), c_int(m_pad), c_int(K), c_int(f1), ptr(dfeat), stream(),
              meta={"flops": 2.0 * m_pad * f1 * K})
         # ---- conv stacks, last block first
-        x = sv["x"]
-        for entry in sv["blocks"]:
-            br, blocks = entry["branch"], entry["blocks"]
-            dp, dp_cstride, dp_coff = dfeat, self.feat_channels, entry["c_off"]
-            for li in range(len(blocks) - 1, -1, -1):
-                b = blocks[li]
-                conv, bn, h, w = b["conv"], b["bn"], b["h"], b["w"]
-                cout, cin = conv.out_channels, conv.in_channels
-                sums = self._new((2 * cout,), torch.float32, dev)
-                if b.get("gram") is not None:
-                    # first block: the forward pass stored arg-max / sign codes, so the data term of the weight gradient and
-                    # sum(dA) are one gather over the input; sum(dA * xhat) follows from them in the finalize kernel
-                    if dp_cstride != cout or dp_coff != 0:
-                        raise _lib.CtkError("the first block's output gradient must be dense")
-                    T = 9 * cin
-                    t1 = self._new((cout, T), torch.float32, dev)
-                    call("ctk_first_wgrad_codes", ptr(x), c_int(n), c_int(x.shape[1]), c_int(br.c_offset), c_int(cin), c_int(h),
-                         c_int(w), ptr(b["codes"]), ptr(dp), c_int(cout), c_float(LEAKY_SLOPE), ptr(t1), ptr(sums), stream())
-                    dw = self._new(tuple(conv.weight.shape), torch.float32, dev)
-                    # SyncBN: the saved Gram matrix is already the global one, so reduce t1 / sum(dA) too and form the
-                    # global gradient on every rank; dividing by the world size makes the exchange's mean leave it as is
-                    self._sync_stats(t1)
-                    self._sync_stats(sums)
-                    call("ctk_first_wgrad_finalize", ptr(t1), ptr(b["gram"]), ptr(conv.weight), ptr(b["scale"]), ptr(b["mean"]),
-                         ptr(b["invstd"]), ptr(sums), c_double(float(n) * h * w * self.stat_world), c_int(cout), c_int(cin),
-                         ptr(dw), stream())
-                    if self.stat_world > 1:
-                        dw.div_(self.stat_world)
-                        sums.div_(self.stat_world)
-                    done(bn.bias, sums[:cout])
-                    done(bn.weight, sums[cout:])
-                    done(conv.weight, dw)
-                    done(conv.bias, torch.zeros_like(conv.bias))
-                    continue
-                pooled, p_cstride, p_coff = b["pooled"]
-                call("ctk_bn_bwd_reduce_pooled", ptr(pooled), c_int(p_cstride), c_int(p_coff), ptr(dp), c_int(dp_cstride),
-                     c_int(dp_coff), c_longlong(n * (h // 2) * (w // 2)), c_int(cout), ptr(bn.weight), ptr(bn.bias),
-                     c_float(LEAKY_SLOPE), ptr(sums), stream())
-                done(bn.bias, sums[:cout])
-                done(bn.weight, sums[cout:])
-                dy = self._new((n, h, w, cout), torch.bfloat16, dev)
-                call("ctk_bn_bwd_apply", ptr(b["y"]), ptr(dp), c_int(dp_cstride), c_int(dp_coff), c_int(n), c_int(h), c_int(w),
-                     c_int(cout), ptr(b["scale"]), ptr(b["shift"]), ptr(b["mean"]), ptr(b["invstd"]), ptr(self._global_sums(sums)),
-                     c_float(LEAKY_SLOPE), ptr(dy), stream())
-                b["y"] = None
-                dw = self._new(tuple(conv.weight.shape), torch.float32, dev)
-                if li == 0:
-                    call("ctk_conv_first_wgrad", ptr(dy), ptr(x), c_int(n), c_int(x.shape[1]), c_int(br.c_offset), c_int(cin),
-                         c_int(h), c_int(w), c_int(cout), ptr(dw), stream())
+        main = torch.cuda.current_stream(dev)
+        used_streams = [comm] if comm is not None else []
+        if overlap:
+            fork = torch.cuda.Event()
+            fork.record(main)                   # dfeat is complete behind this point
+        for bi, entry in enumerate(sv["blocks"]):
+            if overlap:
+                wg = self._side_stream("wgrad", bi, dev)
+                used_streams.append(wg)
+                if len(sv["blocks"]) > 1:
+                    side = self._side_stream("branch", bi, dev)
+                    side.wait_event(fork)
+                    used_streams.append(side)
+                    with torch.cuda.stream(side):
+                        self._backward_branch(entry, sv, dfeat, done, wg)
                 else:
-                    call("ctk_conv3x3_wgrad_tc", ptr(dy), ptr(b["x_in"]), c_int(n), c_int(h), c_int(w), c_int(cin), c_int(cout),
-                         ptr(dw), stream(), meta={"flops": 2.0 * n * h * w * cout * 9 * cin})
-                done(conv.weight, dw)
-                # the conv bias feeds a train-mode BatchNorm, so its gradient is sum(dY) = 0 identically
-                done(conv.bias, torch.zeros_like(conv.bias))
-                if li > 0:
-                    wg = self._new((9, cin, cout), torch.bfloat16, dev)
-                    call("ctk_pack_conv_weight_dgrad_bf16", ptr(conv.weight), c_int(cout), c_int(cin), ptr(wg), stream())
-                    dx = self._new((n, h, w, cin), torch.bfloat16, dev)
-                    call("ctk_conv3x3_tc_raw", ptr(dy), c_int(n), c_int(h), c_int(w), c_int(cout), ptr(wg), c_int(cin), ptr(dx),
-                         ptr(None), stream(), meta={"flops": 2.0 * n * h * w * cout * 9 * cin})
-                    dp, dp_cstride, dp_coff = dx, cin, 0
-                del dy
+                    self._backward_branch(entry, sv, dfeat, done, wg)
+            else:
+                self._backward_branch(entry, sv, dfeat, done)
+        if overlap:
+            self._join(main, used_streams)
+            for g in grads.values():            # produced on side streams, consumed (optimizer, NCCL, user) on this one
+                g.record_stream(main)
         if self.finalize_grads is not None:
             grads = self.finalize_grads(grads)
         return grads
