@@ -219,10 +219,14 @@ int ctk_adam_multi(void* const* params, void* const* grads, void* const* exp_avg
  * fed ctk_pack_conv_weight_dgrad_bf16 weights: dX = conv(dY, rot180(W)^T)).
  * Replaces: nn.Conv2d forward / aten::convolution_backward (input gradient), regression_model.py:14,23;
  * two_branch_regression.py:10,16,22,28. */
+size_t ctk_conv_first_raw_workspace_bytes(int cout);
 int ctk_conv_first_raw(const float* x, int n, int c_total, int c_offset, int cin, int H, int W, const float* w,
-                       int cout, void* y_bf16, float* stats, void* stream);
+                       int cout, void* y_bf16, float* stats, void* workspace, size_t workspace_bytes, void* stream);
+/* Statistics are deterministic: each CTA stores one row of partial sums in the workspace (needed only when stats != NULL:
+ * ctk_*_raw_workspace_bytes(cout) bytes, 16-byte aligned) and the rows are added in a fixed order -- no float atomics. */
+size_t ctk_conv3x3_tc_raw_workspace_bytes(int cout);
 int ctk_conv3x3_tc_raw(const void* x_bf16, int n, int H, int W, int cin, const void* w_packed_bf16, int cout,
-                       void* y_bf16, float* stats, void* stream);
+                       void* y_bf16, float* stats, void* workspace, size_t workspace_bytes, void* stream);
 /* conv weight [Cout,Cin,3,3] fp32 -> [9][Cin][Cout] bf16 with the taps rotated by 180 degrees (dgrad operand). */
 int ctk_pack_conv_weight_dgrad_bf16(const float* w, int cout, int cin, void* w_packed_bf16, void* stream);
 
@@ -251,11 +255,16 @@ int ctk_bn_finalize_moments(const float* moments, double count, const float* bia
  *                            m1 = sums[c]/count, m2 = sums[cout+c]/count, count = n*H*W
  * Replaces (train mode): nn.Conv2d + nn.BatchNorm2d statistics and their backward for regression_model.py:14-15,
  * two_branch_regression.py:10-11. */
+/* (Gram matrix and gather are two-stage and deterministic: per-CTA partial sums in the workspace -- *_workspace_bytes()
+ * bytes, 16-byte aligned -- added in a fixed order; no floating-point atomics.) */
+size_t ctk_first_patch_gram_workspace_bytes(int cin);
 int ctk_first_patch_gram(const float* x, int n, int c_total, int c_offset, int cin, int H, int W, double* gram,
-                         void* stream);
+                         void* workspace, size_t workspace_bytes, void* stream);
 int ctk_first_moments(const double* gram, const float* w, int cout, int cin, double count, float* moments, void* stream);
+size_t ctk_first_wgrad_codes_workspace_bytes(int cin, int cout);
 int ctk_first_wgrad_codes(const float* x, int n, int c_total, int c_offset, int cin, int H, int W, const void* codes_u32,
-                          const void* dp_bf16, int cout, float slope, float* t1, float* sums, void* stream);
+                          const void* dp_bf16, int cout, float slope, float* t1, float* sums, void* workspace,
+                          size_t workspace_bytes, void* stream);
 int ctk_first_wgrad_finalize(const float* t1, const double* gram, const float* w, const float* scale, const float* mean,
                              const float* invstd, float* sums, double count, int cout, int cin, float* dw,
                              void* stream);
@@ -269,15 +278,29 @@ int ctk_bn_act_pool_fwd(const void* y_bf16, int n, int H, int W, int channels, c
  * dense) = gamma*invstd*(dA - mean(dA) - xhat*mean(dA*xhat)).  The pool's argmax is recomputed (first maximum wins).
  * Replaces: the autograd backward (train_model.py:422) of regression_model.py:15-17,24-26 and
  * two_branch_regression.py:11-13,17-19,23-25,29-31. */
+/* All three reductions are two-stage and deterministic: every CTA stores one row of partial sums into the workspace
+ * (ctk_bn_bwd_reduce_workspace_bytes(channels) bytes, 16-byte aligned) and the rows are added in a fixed order with fp64
+ * accumulation -- no floating-point atomics, identical launches give bit-identical sums. */
+size_t ctk_bn_bwd_reduce_workspace_bytes(int channels);
 int ctk_bn_bwd_reduce(const void* y_bf16, const void* dp_bf16, int dp_cstride, int dp_coffset, int n, int H, int W,
                       int channels, const float* scale, const float* shift, const float* mean, const float* invstd,
-                      float slope, float* sums, void* stream);
+                      float slope, float* sums, void* workspace, size_t workspace_bytes, void* stream);
 /* Same sums from the pooled activation P (the block's stored output) and dP alone: dA lives only at each window's
  * argmax, where the activation equals P, so f'(P) and xhat(P) = (leaky^-1(P) - beta)/gamma are recoverable.  Reads
- * 1 B per element of Y instead of 2.5 B.  gamma == 0 channels get dgamma = 0. */
+ * 1 B per element of Y instead of 2.5 B.  One bf16 ulp of P moves xhat by ~|beta/gamma| 2^-8 and gamma == 0 makes it
+ * unrecoverable (dgamma = 0 then): use ctk_bn_bwd_reduce_guarded unless the parameters are known to be benign. */
 int ctk_bn_bwd_reduce_pooled(const void* pooled_bf16, int p_cstride, int p_coffset, const void* dp_bf16, int dp_cstride,
                              int dp_coffset, long long pooled_pixels, int channels, const float* gamma,
-                             const float* beta, float slope, float* sums, void* stream);
+                             const float* beta, float slope, float* sums, void* workspace, size_t workspace_bytes,
+                             void* stream);
+/* The pooled reduction with a per-channel-group guard evaluated on the device (no host read of the parameters): a group of
+ * 8 channels containing gamma == 0 or |beta| > 8 |gamma| is reduced from the raw conv output y like ctk_bn_bwd_reduce,
+ * every other group from the pooled tensors.  This is the entry point the training path uses. */
+int ctk_bn_bwd_reduce_guarded(const void* y_bf16, int n, int H, int W, const float* scale, const float* shift,
+                              const float* mean, const float* invstd, const void* pooled_bf16, int p_cstride,
+                              int p_coffset, const void* dp_bf16, int dp_cstride, int dp_coffset, int channels,
+                              const float* gamma, const float* beta, float slope, float* sums, void* workspace,
+                              size_t workspace_bytes, void* stream);
 int ctk_bn_bwd_apply(const void* y_bf16, const void* dp_bf16, int dp_cstride, int dp_coffset, int n, int H, int W,
                      int channels, const float* scale, const float* shift, const float* mean, const float* invstd,
                      const float* sums, float slope, void* dy_bf16, void* stream);
@@ -287,10 +310,14 @@ int ctk_bn_bwd_apply(const void* y_bf16, const void* dp_bf16, int dp_cstride, in
  * ctk_conv_first_wgrad: first layer (cin 1 or 2), x = fp32 NCHW input planes.
  * Replaces: aten::convolution_backward (weight gradient) of the nn.Conv2d layers at regression_model.py:14,23 and
  * two_branch_regression.py:10,16,22,28, reached through loss.backward() (train_model.py:422). */
+/* Both are two-stage and deterministic: every CTA stores its partial sums in the workspace (*_workspace_bytes(cin, cout)
+ * bytes, 16-byte aligned) and a second kernel adds them in a fixed order -- no floating-point atomics. */
+size_t ctk_conv3x3_wgrad_tc_workspace_bytes(int cin, int cout);
 int ctk_conv3x3_wgrad_tc(const void* dy_bf16, const void* x_bf16, int n, int H, int W, int cin, int cout, float* dw,
-                         void* stream);
+                         void* workspace, size_t workspace_bytes, void* stream);
+size_t ctk_conv_first_wgrad_workspace_bytes(int cin, int cout);
 int ctk_conv_first_wgrad(const void* dy_bf16, const float* x, int n, int c_total, int c_offset, int cin, int H, int W,
-                         int cout, float* dw, void* stream);
+                         int cout, float* dw, void* workspace, size_t workspace_bytes, void* stream);
 
 /* FC1 in training: feature-map transpose out[(c*HW+p)][n] = feat[n][p][c] (zero padded to ld columns), FC1 weight
  * transposed + permuted w_t[p*C+c][o] = w[o][c*HW+p], and a plain bf16-output GEMM C[M,N] = A[M,K] * B[N,K]^T

@@ -39,7 +39,7 @@ def test_every_declared_symbol_is_exported(lib):
 
 
 def test_status_strings_and_no_compute_paths(lib):
-    assert lib.ctk_abi_version() == 1
+    assert lib.ctk_abi_version() == 2
     assert lib.ctk_status_string(0) == b"ok"
     assert b"argument" in lib.ctk_status_string(-1)
     assert lib.ctk_pearson_workspace_bytes(0) == 0
@@ -51,6 +51,14 @@ def test_status_strings_and_no_compute_paths(lib):
     assert lib.ctk_tile_ssim_f32(None, 4, 256, 256, None, None, 0, None) == -1           # null pointers
     assert lib.ctk_tile_ssim_f32(None, 0, 256, 256, None, None, 0, None) == 0            # empty batch: nothing to do
     assert lib.ctk_gemm_bf16_splitk(None, None, 128, 128, 64, 1, None, None) == -1
+    # the deterministic two-stage reductions take caller-owned workspaces: sizes are queries, null pointers are refused
+    assert lib.ctk_bn_bwd_reduce_workspace_bytes(0) == 0 and lib.ctk_bn_bwd_reduce_workspace_bytes(64) % (2 * 64 * 4) == 0
+    assert lib.ctk_conv3x3_tc_raw_workspace_bytes(256) % (2 * 256 * 4) == 0
+    assert lib.ctk_conv3x3_wgrad_tc_workspace_bytes(64, 128) >= 3 * 12 * 32 * 128 * 4
+    assert lib.ctk_first_patch_gram_workspace_bytes(2) % ((18 + 171) * 8) == 0
+    assert lib.ctk_conv3x3_wgrad_tc(None, None, 1, 16, 16, 64, 128, None, None, 0, None) == -1
+    assert lib.ctk_bn_bwd_reduce_guarded(None, 1, 16, 16, None, None, None, None, None, 64, 0, None, 64, 0, 64, None, None,
+                                         0.01, None, None, 0, None) == -1
 
 
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):

@@ -3,7 +3,7 @@
 Operands are rounded to bf16 up front so the only differences are accumulation order and the final bf16 store:
 tolerances are a few bf16 ulps for bf16 outputs and ~1e-3 relative for fp32 reductions over bf16 products.
 """
-from ctypes import c_double, c_float, c_int, c_longlong
+from ctypes import c_double, c_float, c_int, c_longlong, c_size_t
 
 import numpy as np
 import pytest
@@ -40,9 +40,15 @@ def test_conv_raw_and_stats(L, n, H, W, cin, cout):
     L.call("ctk_pack_conv_weight_bf16", L.ptr(wd), c_int(cout), c_int(cin), L.ptr(wp), L.stream())
     y = torch.zeros(n, H, W, cout, device="cuda", dtype=torch.bfloat16)
     stats = torch.empty(2 * cout, device="cuda")
+    ws = L.workspace("ctk_conv3x3_tc_raw_workspace_bytes", cout)
     L.call("ctk_conv3x3_tc_raw", L.ptr(xd), c_int(n), c_int(H), c_int(W), c_int(cin), L.ptr(wp), c_int(cout), L.ptr(y),
-           L.ptr(stats), L.stream())
+           L.ptr(stats), ws[1], ws[2], L.stream())
+    # the statistics are a fixed-order two-stage reduction: a second launch must reproduce them bit for bit
+    stats2 = torch.empty_like(stats)
+    L.call("ctk_conv3x3_tc_raw", L.ptr(xd), c_int(n), c_int(H), c_int(W), c_int(cin), L.ptr(wp), c_int(cout), L.ptr(y),
+           L.ptr(stats2), ws[1], ws[2], L.stream())
     torch.cuda.synchronize()
+    assert torch.equal(stats, stats2)
     assert rel_l2(y.float().cpu(), ref) < 4e-3
     s = stats.cpu()
     np.testing.assert_allclose(s[:cout].numpy(), ref.sum((0, 1, 2)).numpy(), rtol=2e-3, atol=2e-2)
@@ -59,9 +65,13 @@ def test_conv_first_raw_and_stats(L, cin, cout, coff):
     xd, wd = x.cuda(), w.cuda()
     y = torch.zeros(n, H, W, cout, device="cuda", dtype=torch.bfloat16)
     stats = torch.empty(2 * cout, device="cuda")
-    L.call("ctk_conv_first_raw", L.ptr(xd), c_int(n), c_int(2), c_int(coff), c_int(cin), c_int(H), c_int(W), L.ptr(wd),
-           c_int(cout), L.ptr(y), L.ptr(stats), L.stream())
+    ws = L.workspace("ctk_conv_first_raw_workspace_bytes", cout)
+    stats2 = torch.empty_like(stats)
+    for st in (stats, stats2):
+        L.call("ctk_conv_first_raw", L.ptr(xd), c_int(n), c_int(2), c_int(coff), c_int(cin), c_int(H), c_int(W), L.ptr(wd),
+               c_int(cout), L.ptr(y), L.ptr(st), ws[1], ws[2], L.stream())
     torch.cuda.synchronize()
+    assert torch.equal(stats, stats2)                    # deterministic reduction
     assert rel_l2(y.float().cpu(), ref) < 3e-3          # bf16 store of an fp32-class result
     s = stats.cpu()
     np.testing.assert_allclose(s[:cout].numpy(), ref.sum((0, 1, 2)).numpy(), rtol=1e-4, atol=1e-2)
@@ -77,9 +87,17 @@ def _bn_setup(n, H, W, C, seed):
     return y, gamma, beta, bias
 
 
-def test_bn_finalize_act_pool_and_backward(L):
+@pytest.mark.parametrize("hard", [False, True])
+def test_bn_finalize_act_pool_and_backward(L, hard):
     n, H, W, C = 3, 16, 24, 64
     y, gamma, beta, bias = _bn_setup(n, H, W, C, 2)
+    if hard:
+        # the regime where rebuilding xhat from the bf16 pooled output loses everything: |beta| >> |gamma|, and gamma == 0
+        gamma[0:8] = 0.01 * torch.sign(gamma[0:8])
+        beta[0:8] = 1.0
+        gamma[19] = 0.0
+        beta[40:48] = -2.0
+        gamma[40:48] = 0.05
     dp = bf(torch.randn(n, H // 2, W // 2, C))
     # ---- reference: BatchNorm2d(train) on (y + bias) -> LeakyReLU -> MaxPool, autograd for dy / dgamma / dbeta
     yr = y.permute(0, 3, 1, 2).clone().requires_grad_(True)
@@ -105,11 +123,20 @@ def test_bn_finalize_act_pool_and_backward(L):
     dpd = torch.zeros(n, H // 2, W // 2, C + 8, device="cuda", dtype=torch.bfloat16)
     dpd[..., 8:] = dp.to(torch.bfloat16).cuda()
     bsum = torch.empty(2 * C, device="cuda")
-    L.call("ctk_bn_bwd_reduce", L.ptr(yd), L.ptr(dpd), c_int(C + 8), c_int(8), c_int(n), c_int(H), c_int(W), c_int(C),
-           L.ptr(scale), L.ptr(shift), L.ptr(mean), L.ptr(invstd), c_float(0.01), L.ptr(bsum), L.stream())
+    ws = L.workspace("ctk_bn_bwd_reduce_workspace_bytes", C)
+    bsum_again = torch.empty(2 * C, device="cuda")
+    for dst in (bsum, bsum_again):
+        L.call("ctk_bn_bwd_reduce", L.ptr(yd), L.ptr(dpd), c_int(C + 8), c_int(8), c_int(n), c_int(H), c_int(W), c_int(C),
+               L.ptr(scale), L.ptr(shift), L.ptr(mean), L.ptr(invstd), c_float(0.01), L.ptr(dst), ws[1], ws[2], L.stream())
+    assert torch.equal(bsum, bsum_again)                 # fixed-order two-stage reduction: bit-identical
     bsum_p = torch.empty(2 * C, device="cuda")
     L.call("ctk_bn_bwd_reduce_pooled", L.ptr(out), c_int(C + 8), c_int(8), L.ptr(dpd), c_int(C + 8), c_int(8),
-           c_longlong(n * (H // 2) * (W // 2)), c_int(C), L.ptr(gd), L.ptr(bd), c_float(0.01), L.ptr(bsum_p), L.stream())
+           c_longlong(n * (H // 2) * (W // 2)), c_int(C), L.ptr(gd), L.ptr(bd), c_float(0.01), L.ptr(bsum_p), ws[1], ws[2],
+           L.stream())
+    bsum_g = torch.empty(2 * C, device="cuda")
+    L.call("ctk_bn_bwd_reduce_guarded", L.ptr(yd), c_int(n), c_int(H), c_int(W), L.ptr(scale), L.ptr(shift), L.ptr(mean),
+           L.ptr(invstd), L.ptr(out), c_int(C + 8), c_int(8), L.ptr(dpd), c_int(C + 8), c_int(8), c_int(C), L.ptr(gd),
+           L.ptr(bd), c_float(0.01), L.ptr(bsum_g), ws[1], ws[2], L.stream())
     dy = torch.empty(n, H, W, C, device="cuda", dtype=torch.bfloat16)
     L.call("ctk_bn_bwd_apply", L.ptr(yd), L.ptr(dpd), c_int(C + 8), c_int(8), c_int(n), c_int(H), c_int(W), c_int(C),
            L.ptr(scale), L.ptr(shift), L.ptr(mean), L.ptr(invstd), L.ptr(bsum), c_float(0.01), L.ptr(dy), L.stream())
@@ -123,8 +150,19 @@ def test_bn_finalize_act_pool_and_backward(L):
     np.testing.assert_allclose(bsum[C:].cpu().numpy(), g.grad.numpy(), rtol=1e-3, atol=1e-3)     # dgamma
     # the pooled-tensor variant reconstructs xhat = (bf16(a) - beta) / gamma: each term carries an unbiased error of
     # |a| 2^-9 / |gamma|, which averages out over the real 10^7 pixels per channel but not over this test's 288
-    np.testing.assert_allclose(bsum_p[:C].cpu().numpy(), b.grad.numpy(), rtol=1e-3, atol=1e-3)
-    np.testing.assert_allclose(bsum_p[C:].cpu().numpy(), g.grad.numpy(), rtol=2e-2, atol=0.2)
+    if not hard:
+        np.testing.assert_allclose(bsum_p[:C].cpu().numpy(), b.grad.numpy(), rtol=1e-3, atol=1e-3)
+        np.testing.assert_allclose(bsum_p[C:].cpu().numpy(), g.grad.numpy(), rtol=2e-2, atol=0.2)
+    # the guarded entry point (what the training path calls): channel groups of 8 with gamma == 0 or |beta| > 8 |gamma|
+    # come from the raw conv output (equal to ctk_bn_bwd_reduce), the others from the pooled tensors
+    guarded = (~((gamma.abs() > 0) & (beta.abs() <= 8 * gamma.abs()))).view(C // 8, 8).any(1).repeat_interleave(8)
+    assert bool(guarded.any()) == hard or not hard
+    expect = torch.where(guarded.repeat(2).cuda(), bsum, bsum_p)
+    np.testing.assert_allclose(bsum_g.cpu().numpy(), expect.cpu().numpy(), rtol=1e-6, atol=1e-7)
+    if hard:
+        gm = guarded.numpy()
+        assert gm[0:8].all() and gm[16:24].all() and gm[40:48].all()
+        np.testing.assert_allclose(bsum_g[C:].cpu().numpy()[gm], g.grad.numpy()[gm], rtol=1e-3, atol=1e-3)
     assert rel_l2(dy.float().cpu(), yr.grad.permute(0, 2, 3, 1)) < 6e-3
 
 
@@ -143,11 +181,15 @@ def test_dgrad_and_wgrad(L, n, H, W, cin, cout):
     L.call("ctk_pack_conv_weight_dgrad_bf16", L.ptr(wd), c_int(cout), c_int(cin), L.ptr(wg), L.stream())
     dx = torch.zeros(n, H, W, cin, device="cuda", dtype=torch.bfloat16)
     L.call("ctk_conv3x3_tc_raw", L.ptr(dyd), c_int(n), c_int(H), c_int(W), c_int(cout), L.ptr(wg), c_int(cin), L.ptr(dx),
-           L.ptr(None), L.stream())
+           L.ptr(None), L.ptr(None), c_size_t(0), L.stream())
     dw = torch.empty(cout, cin, 3, 3, device="cuda")
-    L.call("ctk_conv3x3_wgrad_tc", L.ptr(dyd), L.ptr(xd), c_int(n), c_int(H), c_int(W), c_int(cin), c_int(cout),
-           L.ptr(dw), L.stream())
+    dw2 = torch.full_like(dw, float("nan"))
+    ws = L.workspace("ctk_conv3x3_wgrad_tc_workspace_bytes", cin, cout)
+    for dst in (dw, dw2):
+        L.call("ctk_conv3x3_wgrad_tc", L.ptr(dyd), L.ptr(xd), c_int(n), c_int(H), c_int(W), c_int(cin), c_int(cout),
+               L.ptr(dst), ws[1], ws[2], L.stream())
     torch.cuda.synchronize()
+    assert torch.equal(dw, dw2)                           # split-K slices are added in slice order: bit-identical
     assert rel_l2(dx.float().cpu(), x.grad.permute(0, 2, 3, 1)) < 4e-3
     assert rel_l2(dw.cpu(), w.grad) < 1e-3
 
@@ -162,9 +204,13 @@ def test_first_layer_wgrad(L, cin, cout, coff):
     F.conv2d(x[:, coff:coff + cin], w, padding=1).backward(dy.permute(0, 3, 1, 2))
     xd, dyd = x.cuda(), dy.to(torch.bfloat16).cuda()
     dw = torch.empty(cout, cin, 3, 3, device="cuda")
-    L.call("ctk_conv_first_wgrad", L.ptr(dyd), L.ptr(xd), c_int(n), c_int(2), c_int(coff), c_int(cin), c_int(H), c_int(W),
-           c_int(cout), L.ptr(dw), L.stream())
+    dw2 = torch.empty_like(dw)
+    ws = L.workspace("ctk_conv_first_wgrad_workspace_bytes", cin, cout)
+    for dst in (dw, dw2):
+        L.call("ctk_conv_first_wgrad", L.ptr(dyd), L.ptr(xd), c_int(n), c_int(2), c_int(coff), c_int(cin), c_int(H),
+               c_int(W), c_int(cout), L.ptr(dst), ws[1], ws[2], L.stream())
     torch.cuda.synchronize()
+    assert torch.equal(dw, dw2)
     assert rel_l2(dw.cpu(), w.grad) < 1e-5
 
 
@@ -241,8 +287,12 @@ def test_first_block_gram_path(L, cin, cout, coff):
     rmd, rvd = torch.zeros(cout).cuda(), torch.ones(cout).cuda()
     nbt = torch.zeros((), dtype=torch.int64, device="cuda")
     gram = torch.empty(T + T * T, device="cuda", dtype=torch.float64)
-    L.call("ctk_first_patch_gram", L.ptr(xd), c_int(n), c_int(2), c_int(coff), c_int(cin), c_int(H), c_int(W), L.ptr(gram),
-           L.stream())
+    ws = L.workspace("ctk_first_patch_gram_workspace_bytes", cin)
+    gram2 = torch.empty_like(gram)
+    for dst in (gram2, gram):
+        L.call("ctk_first_patch_gram", L.ptr(xd), c_int(n), c_int(2), c_int(coff), c_int(cin), c_int(H), c_int(W),
+               L.ptr(dst), ws[1], ws[2], L.stream())
+    assert torch.equal(gram, gram2)                       # per-CTA fp64 partial sums added in CTA order
     # Gram matrix against unfold
     cols = F.unfold(x[:, coff:coff + cin].double(), 3, padding=1).permute(0, 2, 1).reshape(-1, T)   # [pixels, T]
     np.testing.assert_allclose(gram[:T].cpu().numpy(), cols.sum(0).numpy(), rtol=1e-7)
@@ -266,8 +316,12 @@ def test_first_block_gram_path(L, cin, cout, coff):
     dpd = dp.to(torch.bfloat16).cuda()
     sums = torch.empty(2 * cout, device="cuda")
     t1 = torch.empty(cout, T, device="cuda")
-    L.call("ctk_first_wgrad_codes", L.ptr(xd), c_int(n), c_int(2), c_int(coff), c_int(cin), c_int(H), c_int(W),
-           L.ptr(codes), L.ptr(dpd), c_int(cout), c_float(0.01), L.ptr(t1), L.ptr(sums), L.stream())
+    ws = L.workspace("ctk_first_wgrad_codes_workspace_bytes", cin, cout)
+    t1b, sums_b = torch.empty_like(t1), torch.empty_like(sums)
+    for a, b in ((t1b, sums_b), (t1, sums)):
+        L.call("ctk_first_wgrad_codes", L.ptr(xd), c_int(n), c_int(2), c_int(coff), c_int(cin), c_int(H), c_int(W),
+               L.ptr(codes), L.ptr(dpd), c_int(cout), c_float(0.01), L.ptr(a), L.ptr(b), ws[1], ws[2], L.stream())
+    assert torch.equal(t1, t1b) and torch.equal(sums[:cout], sums_b[:cout])
     dw = torch.empty(cout, cin, 3, 3, device="cuda")
     L.call("ctk_first_wgrad_finalize", L.ptr(t1), L.ptr(gram), L.ptr(wd), L.ptr(scale), L.ptr(mean), L.ptr(invstd),
            L.ptr(sums), c_double(count), c_int(cout), c_int(cin), L.ptr(dw), L.stream())

@@ -141,17 +141,35 @@ __device__ __forceinline__ void window_grads(const uint4* __restrict__ y, long l
   window_grads_raw(raw, sc, sh, slope, dp, yv, da);
 }
 
+// The pooled-tensor reduction below rebuilds xhat from the bf16-rounded pooled activation as (leaky^-1(P) - beta) / gamma:
+// one bf16 ulp of P moves xhat by about |beta / gamma| * 2^-8, and gamma == 0 makes it unrecoverable.  A channel group
+// (8 channels, one thread) whose parameters leave that regime is "guarded": the pooled kernel skips it and the
+// kernel that reads the raw conv output handles it instead.  Both kernels evaluate this same predicate.
+constexpr float kPooledGuardRatio = 8.f;
+__device__ __forceinline__ bool pooled_guarded(const float* __restrict__ gamma, const float* __restrict__ beta, int cg) {
+  bool guarded = false;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float g = fabsf(__ldg(gamma + cg * 8 + i)), b = fabsf(__ldg(beta + cg * 8 + i));
+    guarded |= !(g > 0.f && b <= kPooledGuardRatio * g);      // also true for NaN parameters
+  }
+  return guarded;
+}
+
 // ---------------------------------------------------------------- backward pass 1: sum(dA), sum(dA * xhat) per channel
+// guard_gamma != nullptr: only the guarded channel groups are processed (the rest write zero partial sums)
 __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(const uint4* __restrict__ y, const __nv_bfloat16* __restrict__ dp, int dp_cstride, int dp_coffset,
                      int H, int W, int c8, const float* __restrict__ scale, const float* __restrict__ shift,
                      const float* __restrict__ mean, const float* __restrict__ invstd, float slope,
-                     float* __restrict__ sums, long long pooled_pixels) {
+                     const float* __restrict__ guard_gamma, const float* __restrict__ guard_beta,
+                     float* __restrict__ part, long long pooled_pixels) {
   extern __shared__ float red[];                       // [256][16]
   const int Hp = H >> 1, Wp = W >> 1;
   const int cg = threadIdx.x % c8;
   const int slot = threadIdx.x / c8;
   const int slots = blockDim.x / c8;
+  const bool active = guard_gamma == nullptr || pooled_guarded(guard_gamma, guard_beta, cg);
   float sc[8], sh[8], mu[8], is[8], s1[8], s2[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -159,7 +177,7 @@ bn_bwd_reduce_kernel(const uint4* __restrict__ y, const __nv_bfloat16* __restric
     mu[i] = __ldg(mean + cg * 8 + i); is[i] = __ldg(invstd + cg * 8 + i);
     s1[i] = 0.f; s2[i] = 0.f;
   }
-  for (long long pix = blockIdx.x * static_cast<long long>(slots) + slot; pix < pooled_pixels;
+  for (long long pix = blockIdx.x * static_cast<long long>(slots) + slot; active && pix < pooled_pixels;
        pix += static_cast<long long>(gridDim.x) * slots) {
     const int px = static_cast<int>(pix % Wp);
     const long long t = pix / Wp;
@@ -185,8 +203,9 @@ bn_bwd_reduce_kernel(const uint4* __restrict__ y, const __nv_bfloat16* __restric
     for (int i = 0; i < 8; ++i) {
       float a = 0.f, b = 0.f;
       for (int s = 0; s < slots; ++s) { a += red[(s * c8 + cg) * 16 + i]; b += red[(s * c8 + cg) * 16 + 8 + i]; }
-      atomicAdd(sums + cg * 8 + i, a);
-      atomicAdd(sums + c + cg * 8 + i, b);
+      // one row of partial sums per CTA; ctk::reduce_rows_f32 adds the rows in a fixed order (no atomics: deterministic)
+      part[static_cast<size_t>(blockIdx.x) * 2 * c + cg * 8 + i] = a;
+      part[static_cast<size_t>(blockIdx.x) * 2 * c + c + cg * 8 + i] = b;
     }
   }
 }
@@ -199,14 +218,15 @@ bn_bwd_reduce_kernel(const uint4* __restrict__ y, const __nv_bfloat16* __restric
 __global__ void __launch_bounds__(256)
 bn_bwd_reduce_pooled_kernel(const __nv_bfloat16* __restrict__ pooled, int p_cstride, int p_coffset,
                             const __nv_bfloat16* __restrict__ dp, int dp_cstride, int dp_coffset, int c8,
-                            const float* __restrict__ gamma, const float* __restrict__ beta, float slope,
-                            float* __restrict__ sums, long long pooled_pixels) {
+                            const float* __restrict__ gamma, const float* __restrict__ beta, float slope, int guard,
+                            float* __restrict__ part, long long pooled_pixels) {
   extern __shared__ float red[];                       // [256][16]
   const int cg = threadIdx.x % c8;
   const int slot = threadIdx.x / c8;
   const int slots = blockDim.x / c8;
   float ig[8], be[8], s1[8], s2[8];
   const float inv_slope = 1.f / slope;
+  const bool active = !(guard && pooled_guarded(gamma, beta, cg));
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const float g = __ldg(gamma + cg * 8 + i);
@@ -215,7 +235,8 @@ bn_bwd_reduce_pooled_kernel(const __nv_bfloat16* __restrict__ pooled, int p_cstr
     s1[i] = 0.f; s2[i] = 0.f;
   }
   const long long stride = static_cast<long long>(gridDim.x) * slots;
-  for (long long pix0 = blockIdx.x * static_cast<long long>(slots) + slot; pix0 < pooled_pixels; pix0 += 4 * stride) {
+  for (long long pix0 = blockIdx.x * static_cast<long long>(slots) + slot; active && pix0 < pooled_pixels;
+       pix0 += 4 * stride) {
     uint4 rp[4], rd[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {                      // eight independent 16-byte loads in flight per thread
@@ -249,8 +270,9 @@ bn_bwd_reduce_pooled_kernel(const __nv_bfloat16* __restrict__ pooled, int p_cstr
     for (int i = 0; i < 8; ++i) {
       float a = 0.f, b = 0.f;
       for (int s = 0; s < slots; ++s) { a += red[(s * c8 + cg) * 16 + i]; b += red[(s * c8 + cg) * 16 + 8 + i]; }
-      atomicAdd(sums + cg * 8 + i, a);
-      atomicAdd(sums + c + cg * 8 + i, b);
+      // one row of partial sums per CTA; ctk::reduce_rows_f32 adds the rows in a fixed order (no atomics: deterministic)
+      part[static_cast<size_t>(blockIdx.x) * 2 * c + cg * 8 + i] = a;
+      part[static_cast<size_t>(blockIdx.x) * 2 * c + c + cg * 8 + i] = b;
     }
   }
 }
@@ -400,44 +422,97 @@ int ctk_bn_act_pool_fwd(const void* y_bf16, int n, int H, int W, int channels, c
   return ctk::check_launch();
 }
 
+// rows of partial sums: the exact kernel's grid plus the pooled kernel's grid (the guarded entry point runs both)
+static int bn_reduce_grid_exact(long long pooled, int channels) {
+  const int slots = 256 / (channels / 8);
+  const long long blocks = (pooled + slots - 1) / slots;
+  const long long cap = static_cast<long long>(ctk::num_sms()) * 4;
+  return static_cast<int>(blocks < 1 ? 1 : (blocks < cap ? blocks : cap));
+}
+static int bn_reduce_grid_pooled(long long pooled, int channels) {
+  const int slots = 256 / (channels / 8);
+  // every CTA ends with one row of 2 * channels partial sums: few, long-running CTAs (>= 64 pixels per slot)
+  const long long blocks = (pooled + static_cast<long long>(slots) * 64 - 1) / (static_cast<long long>(slots) * 64);
+  const long long cap = static_cast<long long>(ctk::num_sms()) * 3;
+  return static_cast<int>(blocks < 1 ? 1 : (blocks < cap ? blocks : cap));
+}
+
+size_t ctk_bn_bwd_reduce_workspace_bytes(int channels) {
+  return channels > 0 ? static_cast<size_t>(ctk::num_sms()) * 7 * 2 * channels * sizeof(float) : 0;
+}
+
 int ctk_bn_bwd_reduce(const void* y_bf16, const void* dp_bf16, int dp_cstride, int dp_coffset, int n, int H, int W,
                       int channels, const float* scale, const float* shift, const float* mean, const float* invstd,
-                      float slope, float* sums, void* stream) {
+                      float slope, float* sums, void* workspace, size_t workspace_bytes, void* stream) {
   if (n == 0) return CTK_OK;
   CTK_REQUIRE(y_bf16 && dp_bf16 && scale && shift && mean && invstd && sums && n > 0 && H % 2 == 0 && W % 2 == 0);
   CTK_REQUIRE(channels > 0 && channels % 8 == 0 && channels <= 2048 && 256 % (channels / 8) == 0 &&
               dp_cstride % 8 == 0 && dp_coffset % 8 == 0 && dp_coffset + channels <= dp_cstride);
   cudaStream_t s = ctk::as_stream(stream);
-  CTK_CUDA_TRY(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * channels, s));
   const long long pooled = static_cast<long long>(n) * (H / 2) * (W / 2);
-  const int slots = 256 / (channels / 8);
-  const long long blocks = (pooled + slots - 1) / slots;
-  const int grid = static_cast<int>(blocks < ctk::num_sms() * 8 ? blocks : ctk::num_sms() * 8);
+  const int grid = bn_reduce_grid_exact(pooled, channels);
+  CTK_REQUIRE_WORKSPACE(workspace, workspace_bytes, static_cast<size_t>(grid) * 2 * channels * sizeof(float));
+  float* part = static_cast<float*>(workspace);
   bn_bwd_reduce_kernel<<<grid, 256, 256 * 16 * sizeof(float), s>>>(
       static_cast<const uint4*>(y_bf16), static_cast<const __nv_bfloat16*>(dp_bf16), dp_cstride, dp_coffset, H, W,
-      channels / 8, scale, shift, mean, invstd, slope, sums, pooled);
-  return ctk::check_launch();
+      channels / 8, scale, shift, mean, invstd, slope, nullptr, nullptr, part, pooled);
+  int st = ctk::check_launch();
+  if (st != CTK_OK) return st;
+  return ctk::reduce_rows_f32(part, grid, 2 * channels, 2 * channels, sums, s);
 }
 
-int ctk_bn_bwd_reduce_pooled(const void* pooled_bf16, int p_cstride, int p_coffset, const void* dp_bf16, int dp_cstride,
-                             int dp_coffset, long long pooled_pixels, int channels, const float* gamma,
-                             const float* beta, float slope, float* sums, void* stream) {
+static int bn_reduce_pooled_impl(const void* y_bf16, int H, int W, const float* scale, const float* shift,
+                                 const float* mean, const float* invstd, const void* pooled_bf16, int p_cstride,
+                                 int p_coffset, const void* dp_bf16, int dp_cstride, int dp_coffset,
+                                 long long pooled_pixels, int channels, const float* gamma, const float* beta,
+                                 float slope, float* sums, void* workspace, size_t workspace_bytes, void* stream) {
   if (pooled_pixels == 0) return CTK_OK;
   CTK_REQUIRE(pooled_bf16 && dp_bf16 && gamma && beta && sums && pooled_pixels > 0 && slope > 0.f);
   CTK_REQUIRE(channels > 0 && channels % 8 == 0 && channels <= 2048 && 256 % (channels / 8) == 0);
   CTK_REQUIRE(dp_cstride % 8 == 0 && dp_coffset % 8 == 0 && dp_coffset + channels <= dp_cstride && p_cstride % 8 == 0 &&
               p_coffset % 8 == 0 && p_coffset + channels <= p_cstride);
   cudaStream_t s = ctk::as_stream(stream);
-  CTK_CUDA_TRY(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * channels, s));
-  const int slots = 256 / (channels / 8);
-  // every CTA ends with 2 * channels global atomics on the same addresses: few, long-running CTAs (>= 64 pixels per slot)
-  const long long blocks = (pooled_pixels + static_cast<long long>(slots) * 64 - 1) / (static_cast<long long>(slots) * 64);
-  const long long cap = static_cast<long long>(ctk::num_sms()) * 3;
-  const int grid = static_cast<int>(blocks < 1 ? 1 : (blocks < cap ? blocks : cap));
-  bn_bwd_reduce_pooled_kernel<<<grid, 256, 256 * 16 * sizeof(float), s>>>(
+  const bool guard = y_bf16 != nullptr;
+  const int grid_p = bn_reduce_grid_pooled(pooled_pixels, channels);
+  const int grid_e = guard ? bn_reduce_grid_exact(pooled_pixels, channels) : 0;
+  CTK_REQUIRE_WORKSPACE(workspace, workspace_bytes, static_cast<size_t>(grid_p + grid_e) * 2 * channels * sizeof(float));
+  float* part = static_cast<float*>(workspace);
+  bn_bwd_reduce_pooled_kernel<<<grid_p, 256, 256 * 16 * sizeof(float), s>>>(
       static_cast<const __nv_bfloat16*>(pooled_bf16), p_cstride, p_coffset, static_cast<const __nv_bfloat16*>(dp_bf16),
-      dp_cstride, dp_coffset, channels / 8, gamma, beta, slope, sums, pooled_pixels);
-  return ctk::check_launch();
+      dp_cstride, dp_coffset, channels / 8, gamma, beta, slope, guard ? 1 : 0, part, pooled_pixels);
+  int st = ctk::check_launch();
+  if (st != CTK_OK) return st;
+  if (guard) {
+    // guarded channel groups (none for freshly initialised or moderately trained BatchNorms: the CTAs then exit at once)
+    bn_bwd_reduce_kernel<<<grid_e, 256, 256 * 16 * sizeof(float), s>>>(
+        static_cast<const uint4*>(y_bf16), static_cast<const __nv_bfloat16*>(dp_bf16), dp_cstride, dp_coffset, H, W,
+        channels / 8, scale, shift, mean, invstd, slope, gamma, beta,
+        part + static_cast<size_t>(grid_p) * 2 * channels, pooled_pixels);
+    st = ctk::check_launch();
+    if (st != CTK_OK) return st;
+  }
+  return ctk::reduce_rows_f32(part, grid_p + grid_e, 2 * channels, 2 * channels, sums, s);
+}
+
+int ctk_bn_bwd_reduce_pooled(const void* pooled_bf16, int p_cstride, int p_coffset, const void* dp_bf16, int dp_cstride,
+                             int dp_coffset, long long pooled_pixels, int channels, const float* gamma,
+                             const float* beta, float slope, float* sums, void* workspace, size_t workspace_bytes,
+                             void* stream) {
+  return bn_reduce_pooled_impl(nullptr, 0, 0, nullptr, nullptr, nullptr, nullptr, pooled_bf16, p_cstride, p_coffset, dp_bf16,
+                               dp_cstride, dp_coffset, pooled_pixels, channels, gamma, beta, slope, sums, workspace,
+                               workspace_bytes, stream);
+}
+
+int ctk_bn_bwd_reduce_guarded(const void* y_bf16, int n, int H, int W, const float* scale, const float* shift,
+                              const float* mean, const float* invstd, const void* pooled_bf16, int p_cstride,
+                              int p_coffset, const void* dp_bf16, int dp_cstride, int dp_coffset, int channels,
+                              const float* gamma, const float* beta, float slope, float* sums, void* workspace,
+                              size_t workspace_bytes, void* stream) {
+  if (n == 0) return CTK_OK;
+  CTK_REQUIRE(y_bf16 && scale && shift && mean && invstd && n > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0);
+  return bn_reduce_pooled_impl(y_bf16, H, W, scale, shift, mean, invstd, pooled_bf16, p_cstride, p_coffset, dp_bf16,
+                               dp_cstride, dp_coffset, static_cast<long long>(n) * (H / 2) * (W / 2), channels, gamma,
+                               beta, slope, sums, workspace, workspace_bytes, stream);
 }
 
 int ctk_bn_bwd_apply(const void* y_bf16, const void* dp_bf16, int dp_cstride, int dp_coffset, int n, int H, int W,

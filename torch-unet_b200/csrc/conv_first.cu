@@ -74,9 +74,12 @@ conv_first_tc_kernel(const float* __restrict__ x, int n_img, int c_total, int c_
                      __nv_bfloat16* __restrict__ out, int out_cstride, int out_coffset, int regions_x, int regions_y,
                      int total_regions, float* __restrict__ stats) {
   using C = FirstCfg<CIN, COUT>;
-  __shared__ float s_stat[kTrain ? 2 * COUT : 1];
+  // statistics: one private row per warp (plain read-modify-write by the owning lane), combined in warp order at the end
+  // and stored as this CTA's row of partial sums -- no shared or global floating-point atomics (deterministic)
+  constexpr int kWarps = kThreads / 32;
+  __shared__ float s_stat[kTrain ? kWarps * 2 * COUT : 1];
   if constexpr (kTrain)
-    for (int i = threadIdx.x; i < 2 * COUT; i += kThreads) s_stat[i] = 0.f;
+    for (int i = threadIdx.x; i < kWarps * 2 * COUT; i += kThreads) s_stat[i] = 0.f;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* b_smem = smem;
@@ -248,8 +251,8 @@ conv_first_tc_kernel(const float* __restrict__ x, int n_img, int c_total, int c_
           }
           const float tot = warp_transpose_sum32(f, lane);
           const float tot2 = warp_transpose_sum32(sq, lane);
-          atomicAdd(&s_stat[cb * 32 + lane], tot);
-          atomicAdd(&s_stat[COUT + cb * 32 + lane], tot2);
+          s_stat[warp * 2 * COUT + cb * 32 + lane] += tot;
+          s_stat[warp * 2 * COUT + COUT + cb * 32 + lane] += tot2;
           if (valid) {
             __nv_bfloat16* dst = out + (static_cast<size_t>(img) * H * W + static_cast<size_t>(y) * W + xg) * out_cstride +
                                  out_coffset + cb * 32;
@@ -271,7 +274,11 @@ conv_first_tc_kernel(const float* __restrict__ x, int n_img, int c_total, int c_
   tc_fence_before();
   __syncthreads();
   if constexpr (kTrain)
-    for (int i = threadIdx.x; i < 2 * COUT; i += kThreads) atomicAdd(stats + i, s_stat[i]);
+    for (int i = threadIdx.x; i < 2 * COUT; i += kThreads) {
+      float tot = 0.f;
+      for (int w = 0; w < kWarps; ++w) tot += s_stat[w * 2 * COUT + i];
+      stats[static_cast<size_t>(blockIdx.x) * 2 * COUT + i] = tot;
+    }
   if (warp == 0) {
     tc_fence_after();
     tmem_dealloc<1>(tmem_base, kTmemCols);
@@ -659,20 +666,26 @@ int launch_first_win(const float* x, int n, int c_total, int c_offset, int H, in
 template <int CIN, int COUT, bool kTrain>
 int launch_first(const float* x, int n, int c_total, int c_offset, int H, int W, const float* w_folded,
                  const float* shift, float slope, __nv_bfloat16* out, int out_cstride, int out_coffset, float* stats,
-                 cudaStream_t stream) {
+                 cudaStream_t stream, void* workspace = nullptr, size_t workspace_bytes = 0) {
   using C = FirstCfg<CIN, COUT>;
   const int regions_x = (W + C::kRegionW - 1) / C::kRegionW;
   const int regions_y = (H + kTileH - 1) / kTileH;
   const long long total = static_cast<long long>(n) * regions_x * regions_y;
   if (total >= (1ll << 31)) return CTK_ERR_BAD_ARG;
   auto kernel = conv_first_tc_kernel<CIN, COUT, kTrain>;
-  if (kTrain) CTK_CUDA_TRY(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * COUT, stream));
   CTK_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
   const int grid = static_cast<int>(std::min<long long>((total + kGroups - 1) / kGroups, ctk::num_sms()));
+  float* part = nullptr;
+  if (kTrain) {
+    CTK_REQUIRE_WORKSPACE(workspace, workspace_bytes, static_cast<size_t>(grid) * 2 * COUT * sizeof(float));
+    part = static_cast<float*>(workspace);
+  }
   kernel<<<grid, kThreads, C::kSmemBytes, stream>>>(x, n, c_total, c_offset, H, W, w_folded, shift, slope, out,
                                                     out_cstride, out_coffset, regions_x, regions_y,
-                                                    static_cast<int>(total), stats);
-  return ctk::check_launch();
+                                                    static_cast<int>(total), kTrain ? part : stats);
+  int st = ctk::check_launch();
+  if (st != CTK_OK || !kTrain) return st;
+  return ctk::reduce_rows_f32(part, grid, 2 * COUT, 2 * COUT, stats, stream);
 }
 
 }  // namespace
@@ -733,16 +746,23 @@ extern "C" int ctk_conv_first_pool_codes(const float* x, int n, int c_total, int
                              out_coffset, codes_u32, nullptr, stream);
 }
 
+extern "C" size_t ctk_conv_first_raw_workspace_bytes(int cout) {
+  return cout > 0 ? static_cast<size_t>(ctk::num_sms()) * 2 * cout * sizeof(float) : 0;
+}
+
 extern "C" int ctk_conv_first_raw(const float* x, int n, int c_total, int c_offset, int cin, int H, int W,
-                                  const float* w, int cout, void* y_bf16, float* stats, void* stream) {
+                                  const float* w, int cout, void* y_bf16, float* stats, void* workspace,
+                                  size_t workspace_bytes, void* stream) {
   if (n == 0) return CTK_OK;
   CTK_REQUIRE(x && w && y_bf16 && stats && n > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0);
   CTK_REQUIRE(c_offset >= 0 && c_offset + cin <= c_total && (reinterpret_cast<uintptr_t>(y_bf16) & 15) == 0);
   cudaStream_t s = ctk::as_stream(stream);
   __nv_bfloat16* out = static_cast<__nv_bfloat16*>(y_bf16);
   if (cin == 1 && cout == 64)
-    return launch_first<1, 64, true>(x, n, c_total, c_offset, H, W, w, nullptr, 0.f, out, cout, 0, stats, s);
+    return launch_first<1, 64, true>(x, n, c_total, c_offset, H, W, w, nullptr, 0.f, out, cout, 0, stats, s, workspace,
+                                     workspace_bytes);
   if (cin == 2 && cout == 128)
-    return launch_first<2, 128, true>(x, n, c_total, c_offset, H, W, w, nullptr, 0.f, out, cout, 0, stats, s);
+    return launch_first<2, 128, true>(x, n, c_total, c_offset, H, W, w, nullptr, 0.f, out, cout, 0, stats, s, workspace,
+                                      workspace_bytes);
   return CTK_ERR_UNSUPPORTED;
 }

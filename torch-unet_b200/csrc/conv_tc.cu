@@ -88,7 +88,9 @@ struct ConvParams {
   float slope;
   const float* scale;   // nullptr = identity (raw conv output)
   const float* shift;
-  float* stats;         // nullptr, or [2*cout]: per-channel sum and sum of squares of the raw fp32 accumulators
+  float* stats;         // nullptr, or [gridDim.x][2*cout]: ONE ROW PER CTA of per-channel partial sum / sum of squares of
+                        // the raw fp32 accumulators (added up in a fixed order by ctk::reduce_rows_f32: deterministic)
+  float* stats_out;     // host side only: [2*cout] totals
   __nv_bfloat16* out;
   __nv_bfloat16* out_lo;   // kEpiEvalPoolSplit: low halves, same pixel / channel addressing as `out`
   int out_cstride, out_coffset;
@@ -147,10 +149,6 @@ __device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c,
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-__device__ __forceinline__ void red_shared_add(uint32_t addr, float v) {
-  asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
-}
-
 struct EpiCtx {
   int lane, y, x, Hp, Wp;
   bool valid;
@@ -158,7 +156,6 @@ struct EpiCtx {
   uint32_t scratch_addr;          // this warp's transpose tile (statistics)
   uint32_t stage_addr;            // this warp's 32-pixel x 128-byte output staging tile (raw modes, TMA store)
   int stage_slot;                 // which 64-byte half of the staged rows the current block fills
-  bool stat_in_regs;              // raw+stats with one N tile: totals stay in the caller's registers until the end
   __nv_bfloat162 slope2;
 };
 
@@ -191,13 +188,11 @@ __device__ __forceinline__ void epilogue_block(const ConvParams& p, const EpiCtx
         s1 += x1; q1 = fmaf(x1, x1, q1);
       }
       __syncwarp();
-      if (e.stat_in_regs) {                 // same channel every tile: keep the totals in registers, flush once at the end
-        acc_s += s0 + s1;                   // (shared-memory float atomics are CAS loops on this architecture)
-        acc_q += q0 + q1;
-      } else {
-        red_shared_add(e.sc_addr + static_cast<uint32_t>((t.n0 + ch0 + lane) * 4), s0 + s1);
-        red_shared_add(e.sh_addr + static_cast<uint32_t>((t.n0 + ch0 + lane) * 4), q0 + q1);
-      }
+      // a CTA keeps ONE N tile for all its work items (launch_conv makes the work stride a multiple of tiles_n), so a
+      // warp meets the same channels every tile: the totals stay in registers and are combined once, in a fixed order,
+      // at the end of the kernel -- no shared or global floating-point atomics anywhere in the statistics
+      acc_s += s0 + s1;
+      acc_q += q0 + q1;
     }
 #pragma unroll
     for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
@@ -526,7 +521,6 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     float stat_s[kPerWarp], stat_q[kPerWarp];
 #pragma unroll
     for (int i = 0; i < kPerWarp; ++i) { stat_s[i] = 0.f; stat_q[i] = 0.f; }
-    e.stat_in_regs = kEpi == kEpiRawStats && p.tiles_n == 1;
     // block i of this warp: consecutive PAIRS of 32-column blocks (64 channels = one 128-byte staged row)
     auto block_of = [&](int i) { return kBlocks == 2 ? half : (i >> 1) * 4 + half * 2 + (i & 1); };
     e.slope2 = __float2bfloat162_rn(p.slope);
@@ -590,17 +584,29 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       __syncwarp();
     }
     if constexpr (kEpi == kEpiRawStats) {
-      if (e.stat_in_regs) {
+      // the four lane quadrants (warp % 4) of a channel are added in quadrant order through the (now idle) transpose
+      // scratch: quad[ew][moment][kBlockN]; then this CTA's row of the partial-sum matrix is written with plain stores
+      const uint32_t quad = smem_u32(reinterpret_cast<uint8_t*>(sl) + kCtrlBytes) + static_cast<uint32_t>(C::kStageBytes);
+      static_assert(4 * 2 * kBlockN * 4 <= kScratchBytes, "quadrant totals must fit the scratch region");
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
 #pragma unroll
-        for (int i = 0; i < kPerWarp; ++i) {
-          red_shared_add(e.sc_addr + static_cast<uint32_t>((block_of(i) * 32 + lane) * 4), stat_s[i]);
-          red_shared_add(e.sh_addr + static_cast<uint32_t>((block_of(i) * 32 + lane) * 4), stat_q[i]);
-        }
+      for (int i = 0; i < kPerWarp; ++i) {
+        const uint32_t ch = static_cast<uint32_t>(block_of(i) * 32 + lane);
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(quad + ((ew * 2 + 0) * kBlockN + ch) * 4), "f"(stat_s[i]) : "memory");
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(quad + ((ew * 2 + 1) * kBlockN + ch) * 4), "f"(stat_q[i]) : "memory");
       }
       asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
-      for (int i = et; i < p.cout; i += 32 * kEpiWarps) {
-        atomicAdd(p.stats + i, sl->ch_a[i]);
-        atomicAdd(p.stats + p.cout + i, sl->ch_b[i]);
+      const int n0 = decode_work<kCtaGroup, kBlockN>(p, work0, rank).n0;
+      float* row = p.stats + static_cast<size_t>(blockIdx.x) * 2 * p.cout;
+      for (int i = et; i < 2 * p.cout; i += 32 * kEpiWarps) {
+        const int mom = i >= p.cout ? 1 : 0;
+        const int c = i - mom * p.cout - n0;
+        float v = 0.f;
+        if (c >= 0 && c < kBlockN) {
+          const uint32_t a = quad + static_cast<uint32_t>((mom * kBlockN + c) * 4);
+          v = ((lds32(a) + lds32(a + 2 * kBlockN * 4)) + lds32(a + 4 * kBlockN * 4)) + lds32(a + 6 * kBlockN * 4);
+        }
+        row[i] = v;
       }
     }
   }
@@ -653,7 +659,9 @@ int launch_conv(const void* x_bf16, const void* w_packed_bf16, ConvParams p, cud
   }
   auto kernel = conv3x3_tc_kernel<kCtaGroup, kBlockN, kEpi>;
   CTK_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
-  const int clusters = std::min(p.total_work, ctk::num_sms() / kCtaGroup);
+  int clusters = std::min(p.total_work, ctk::num_sms() / kCtaGroup);
+  // statistics: every CTA must keep one N tile (register-resident totals), i.e. the work stride is a multiple of tiles_n
+  if (kEpi == kEpiRawStats && clusters > p.tiles_n) clusters -= clusters % p.tiles_n;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(clusters * kCtaGroup);
   cfg.blockDim = dim3(kThreads);
@@ -667,14 +675,22 @@ int launch_conv(const void* x_bf16, const void* w_packed_bf16, ConvParams p, cud
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   CTK_CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, tm_a, tm_b, tm_out, p));
-  return ctk::check_launch();
+  int st = ctk::check_launch();
+  if (st != CTK_OK || kEpi != kEpiRawStats) return st;
+  return ctk::reduce_rows_f32(p.stats, clusters * kCtaGroup, 2 * p.cout, 2 * p.cout, p.stats_out, stream);
 }
 
 }  // namespace
 
+// one row of 2 * cout partial sums per CTA of the persistent grid (<= one CTA per SM)
+extern "C" size_t ctk_conv3x3_tc_raw_workspace_bytes(int cout) {
+  return cout > 0 ? static_cast<size_t>(ctk::num_sms()) * 2 * cout * sizeof(float) : 0;
+}
+
 static int conv_dispatch(const void* x_bf16, int n, int H, int W, int cin, const void* w_packed_bf16, int cout,
                          const float* scale, const float* shift, float* stats, float slope, void* out_bf16,
-                         int out_cstride, int out_coffset, int flags, void* stream, void* out_lo_bf16 = nullptr) {
+                         int out_cstride, int out_coffset, int flags, void* stream, void* out_lo_bf16 = nullptr,
+                         void* workspace = nullptr, size_t workspace_bytes = 0) {
   if (n == 0) return CTK_OK;
   CTK_REQUIRE(x_bf16 && w_packed_bf16 && out_bf16 && (scale == nullptr) == (shift == nullptr));
   CTK_REQUIRE(n > 0 && H > 0 && W > 0 && H % 2 == 0 && W % kTileW == 0 && cin > 0 && cin % kKC == 0 && cout > 0 &&
@@ -693,7 +709,12 @@ static int conv_dispatch(const void* x_bf16, int n, int H, int W, int cin, const
   p.pool = (flags & CTK_CONV_NO_POOL) ? 0 : 1;
   p.act = (flags & CTK_CONV_NO_ACT) ? 0 : 1;
   p.slope = slope;
-  p.scale = scale; p.shift = shift; p.stats = stats;
+  p.scale = scale; p.shift = shift;
+  p.stats = nullptr; p.stats_out = stats;
+  if (stats != nullptr) {
+    CTK_REQUIRE_WORKSPACE(workspace, workspace_bytes, ctk_conv3x3_tc_raw_workspace_bytes(cout));
+    p.stats = static_cast<float*>(workspace);
+  }
   p.out = static_cast<__nv_bfloat16*>(out_bf16);
   p.out_lo = static_cast<__nv_bfloat16*>(out_lo_bf16);
   p.out_cstride = out_cstride; p.out_coffset = out_coffset;
@@ -708,7 +729,6 @@ static int conv_dispatch(const void* x_bf16, int n, int H, int W, int cin, const
     if (cout % 128 == 0) return launch_conv<2, 128, kEpiEvalPoolSplit>(x_bf16, w_packed_bf16, p, s);
     return CTK_ERR_UNSUPPORTED;
   }
-  if (stats != nullptr) CTK_CUDA_TRY(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * cout, s));
   const int epi = scale == nullptr ? (stats != nullptr ? kEpiRawStats : kEpiRaw)
                                    : (p.pool && p.act ? kEpiEvalPool : kEpiEvalAny);
 #define CTK_CONV_LAUNCH(G, N)                                                                             \
@@ -743,7 +763,8 @@ extern "C" int ctk_conv3x3_tc_eval_split(const void* x_split_bf16, int n, int H,
 }
 
 extern "C" int ctk_conv3x3_tc_raw(const void* x_bf16, int n, int H, int W, int cin, const void* w_packed_bf16,
-                                  int cout, void* y_bf16, float* stats, void* stream) {
+                                  int cout, void* y_bf16, float* stats, void* workspace, size_t workspace_bytes,
+                                  void* stream) {
   return conv_dispatch(x_bf16, n, H, W, cin, w_packed_bf16, cout, nullptr, nullptr, stats, 0.f, y_bf16, cout, 0,
-                       CTK_CONV_NO_POOL | CTK_CONV_NO_ACT, stream);
+                       CTK_CONV_NO_POOL | CTK_CONV_NO_ACT, stream, nullptr, workspace, workspace_bytes);
 }

@@ -73,7 +73,7 @@ int num_sms() {
 
 extern "C" {
 
-int ctk_abi_version(void) { return 1; }
+int ctk_abi_version(void) { return 2; }
 
 const char* ctk_status_string(int status) {
   switch (status) {

@@ -46,6 +46,17 @@ int encode_tmap_f32_sw128(CUtensorMap* map, const void* base, int rank, const ui
 
 int num_sms();
 
+// Second stage of the cross-CTA reductions (reduce.cu): out[c] = sum_{r < rows} part[r * stride + c], rows added in a
+// fixed order with fp64 accumulation, so the result is independent of CTA scheduling.
+int reduce_rows_f32(const float* part, int rows, long long stride, int cols, float* out, cudaStream_t s);
+int reduce_rows_f64(const double* part, int rows, long long stride, int cols, double* out, cudaStream_t s);
+
+#define CTK_REQUIRE_WORKSPACE(ptr, have, need)                                         \
+  do {                                                                                 \
+    if ((ptr) == nullptr || (have) < (need)) return CTK_ERR_WORKSPACE;                 \
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) return CTK_ERR_BAD_ARG;          \
+  } while (0)
+
 // n / d for 0 <= n < 2^31 by multiply-high (Granlund-Montgomery, 31-bit dividend): the role loops decode a work index
 // per tile, and a run-time integer division costs ~45 instructions each in every one of the 11 warps
 struct FastDiv {

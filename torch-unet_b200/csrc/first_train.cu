@@ -50,7 +50,7 @@ __device__ __forceinline__ void gram_accumulate(const float (&v)[9 * CIN], float
 
 template <int CIN, int ROLE>
 __device__ __forceinline__ void gram_role(const float* __restrict__ x, int n_img, int c_total, int c_offset, int H, int W,
-                                          double* __restrict__ gram, float (*s_in)[GramCfg<CIN>::TH + 2][35],
+                                          double* __restrict__ part, float (*s_in)[GramCfg<CIN>::TH + 2][35],
                                           double* s_red) {
   using C = GramCfg<CIN>;
   constexpr int T = C::T, TW = C::TW, TH = C::TH, SLOTS = C::SLOTS;
@@ -123,7 +123,7 @@ __device__ __forceinline__ void gram_role(const float* __restrict__ x, int n_img
 #pragma unroll
     for (int i = 0; i < C::PER; ++i) { dacc[i] += static_cast<double>(acc[i]); acc[i] = 0.f; }
   }
-  // lanes -> warp total, the ROWG warps of a role -> CTA total (shared memory), one fp64 atomic per item per CTA
+  // lanes -> warp total, the ROWG warps of a role -> CTA total (shared memory), one fp64 partial per item per CTA
 #pragma unroll
   for (int i = 0; i < C::PER; ++i) {
     double sres = dacc[i];
@@ -138,16 +138,7 @@ __device__ __forceinline__ void gram_role(const float* __restrict__ x, int n_img
       if (item >= C::ITEMS) continue;
       double tot = 0.0;
       for (int g = 0; g < C::ROWG; ++g) tot += s_red[(g * C::ROLES + ROLE) * C::PER + i];
-      if (item < T) {
-        atomicAdd(gram + item, tot);
-      } else {
-        // upper-triangle index -> (a, b), a <= b
-        int rem = item - T, a = 0;
-        while (rem >= T - a) { rem -= T - a; ++a; }
-        const int b = a + rem;
-        atomicAdd(gram + T + a * T + b, tot);
-        if (a != b) atomicAdd(gram + T + b * T + a, tot);
-      }
+      part[static_cast<size_t>(blockIdx.x) * C::ITEMS + item] = tot;      // one row per CTA, added up by gram_reduce_kernel
     }
   }
 }
@@ -155,20 +146,43 @@ __device__ __forceinline__ void gram_role(const float* __restrict__ x, int n_img
 template <int CIN>
 __global__ void __launch_bounds__(256)
 patch_gram_kernel(const float* __restrict__ x, int n_img, int c_total, int c_offset, int H, int W,
-                  double* __restrict__ gram) {
+                  double* __restrict__ part) {
   using C = GramCfg<CIN>;
   __shared__ float s_in[CIN][C::TH + 2][35];
   __shared__ double s_red[8 * C::PER];
   const int role = (threadIdx.x >> 5) % C::ROLES;
   if constexpr (C::ROLES == 1) {
-    gram_role<CIN, 0>(x, n_img, c_total, c_offset, H, W, gram, s_in, s_red);
+    gram_role<CIN, 0>(x, n_img, c_total, c_offset, H, W, part, s_in, s_red);
   } else {
     switch (role) {          // warp-uniform
-      case 0: gram_role<CIN, 0>(x, n_img, c_total, c_offset, H, W, gram, s_in, s_red); break;
-      case 1: gram_role<CIN, 1>(x, n_img, c_total, c_offset, H, W, gram, s_in, s_red); break;
-      case 2: gram_role<CIN, 2>(x, n_img, c_total, c_offset, H, W, gram, s_in, s_red); break;
-      default: gram_role<CIN, 3>(x, n_img, c_total, c_offset, H, W, gram, s_in, s_red); break;
+      case 0: gram_role<CIN, 0>(x, n_img, c_total, c_offset, H, W, part, s_in, s_red); break;
+      case 1: gram_role<CIN, 1>(x, n_img, c_total, c_offset, H, W, part, s_in, s_red); break;
+      case 2: gram_role<CIN, 2>(x, n_img, c_total, c_offset, H, W, part, s_in, s_red); break;
+      default: gram_role<CIN, 3>(x, n_img, c_total, c_offset, H, W, part, s_in, s_red); break;
     }
+  }
+}
+
+// Second stage: item totals over the CTA rows in row order (one warp per item: lane l adds rows l, l+32, ..., then a
+// fixed butterfly), expanded from the upper triangle to the full symmetric matrix.  Deterministic: no atomics.
+__global__ void gram_reduce_kernel(const double* __restrict__ part, int rows, int T, double* __restrict__ gram) {
+  const int items = T + T * (T + 1) / 2;
+  const int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (item >= items) return;
+  double acc = 0.0;
+  for (int r = lane; r < rows; r += 32) acc += part[static_cast<size_t>(r) * items + item];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane != 0) return;
+  if (item < T) {
+    gram[item] = acc;
+  } else {
+    int rem = item - T, a = 0;                 // upper-triangle index -> (a, b), a <= b
+    while (rem >= T - a) { rem -= T - a; ++a; }
+    const int b = a + rem;
+    gram[T + a * T + b] = acc;
+    gram[T + b * T + a] = acc;
   }
 }
 
@@ -204,7 +218,7 @@ template <int CIN, int COUT>
 __global__ void __launch_bounds__(256)
 first_wgrad_codes_kernel(const float* __restrict__ x, int n_img, int c_total, int c_offset, int H, int W,
                          const uint32_t* __restrict__ codes, const __nv_bfloat16* __restrict__ dp, float slope,
-                         float* __restrict__ t1, float* __restrict__ s1_out) {
+                         float* __restrict__ part) {
   constexpr int T = 9 * CIN;
   constexpr int G = COUT / 4;                  // channel groups of 4
   constexpr int SLOTS = 256 / G;               // windows processed concurrently
@@ -314,8 +328,10 @@ first_wgrad_codes_kernel(const float* __restrict__ x, int n_img, int c_total, in
       if (slot == 0) {
         float s = 0.f;
         for (int t = 0; t < SLOTS; ++t) s += s_red[t * G + cg];
-        if (k < T) atomicAdd(t1 + (cg * 4 + j) * T + k, s);
-        else atomicAdd(s1_out + cg * 4 + j, s);
+        // one row [COUT * T (t1) | COUT (s1)] of partial sums per CTA
+        float* row = part + static_cast<size_t>(blockIdx.x) * (COUT * T + COUT);
+        if (k < T) row[(cg * 4 + j) * T + k] = s;
+        else row[COUT * T + cg * 4 + j] = s;
       }
     }
 }
@@ -350,16 +366,26 @@ __global__ void first_wgrad_finalize_kernel(const float* __restrict__ t1, const 
 
 extern "C" {
 
-int ctk_first_patch_gram(const float* x, int n, int c_total, int c_offset, int cin, int H, int W, double* gram,
-                         void* stream) {
-  CTK_REQUIRE(x && gram && n > 0 && H > 0 && W > 0 && c_offset >= 0 && c_offset + cin <= c_total);
+size_t ctk_first_patch_gram_workspace_bytes(int cin) {
   const int T = 9 * cin;
+  return cin > 0 ? static_cast<size_t>(ctk::num_sms()) * (T + T * (T + 1) / 2) * sizeof(double) : 0;
+}
+
+int ctk_first_patch_gram(const float* x, int n, int c_total, int c_offset, int cin, int H, int W, double* gram,
+                         void* workspace, size_t workspace_bytes, void* stream) {
+  CTK_REQUIRE(x && gram && n > 0 && H > 0 && W > 0 && c_offset >= 0 && c_offset + cin <= c_total);
+  CTK_REQUIRE(cin == 1 || cin == 2);
+  const int T = 9 * cin;
+  const int items = T + T * (T + 1) / 2;
   cudaStream_t s = ctk::as_stream(stream);
-  CTK_CUDA_TRY(cudaMemsetAsync(gram, 0, sizeof(double) * (T + T * T), s));
   const int grid = ctk::num_sms();          // ~240 registers per thread: one resident CTA per SM
-  if (cin == 1) patch_gram_kernel<1><<<grid, 256, 0, s>>>(x, n, c_total, c_offset, H, W, gram);
-  else if (cin == 2) patch_gram_kernel<2><<<grid, 256, 0, s>>>(x, n, c_total, c_offset, H, W, gram);
-  else return CTK_ERR_UNSUPPORTED;
+  CTK_REQUIRE_WORKSPACE(workspace, workspace_bytes, static_cast<size_t>(grid) * items * sizeof(double));
+  double* part = static_cast<double*>(workspace);
+  if (cin == 1) patch_gram_kernel<1><<<grid, 256, 0, s>>>(x, n, c_total, c_offset, H, W, part);
+  else patch_gram_kernel<2><<<grid, 256, 0, s>>>(x, n, c_total, c_offset, H, W, part);
+  int st = ctk::check_launch();
+  if (st != CTK_OK) return st;
+  gram_reduce_kernel<<<(items + 7) / 8, 256, 0, s>>>(part, grid, T, gram);
   return ctk::check_launch();
 }
 
@@ -370,23 +396,36 @@ int ctk_first_moments(const double* gram, const float* w, int cout, int cin, dou
   return ctk::check_launch();
 }
 
+size_t ctk_first_wgrad_codes_workspace_bytes(int cin, int cout) {
+  return cin > 0 && cout > 0 ? static_cast<size_t>(ctk::num_sms()) * 2 * (9 * cin + 1) * cout * sizeof(float) : 0;
+}
+
 int ctk_first_wgrad_codes(const float* x, int n, int c_total, int c_offset, int cin, int H, int W, const void* codes_u32,
-                          const void* dp_bf16, int cout, float slope, float* t1, float* sums, void* stream) {
+                          const void* dp_bf16, int cout, float slope, float* t1, float* sums, void* workspace,
+                          size_t workspace_bytes, void* stream) {
   CTK_REQUIRE(x && codes_u32 && dp_bf16 && t1 && sums && n > 0 && H % 2 == 0 && W % 2 == 0);
   CTK_REQUIRE(c_offset >= 0 && c_offset + cin <= c_total);
   cudaStream_t s = ctk::as_stream(stream);
-  CTK_CUDA_TRY(cudaMemsetAsync(t1, 0, sizeof(float) * 9 * cin * cout, s));
-  CTK_CUDA_TRY(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * cout, s));
   const int grid = ctk::num_sms() * 2;
+  const int T = 9 * cin;
+  const int cols = (T + 1) * cout;
+  CTK_REQUIRE_WORKSPACE(workspace, workspace_bytes, static_cast<size_t>(grid) * cols * sizeof(float));
+  float* part = static_cast<float*>(workspace);
   const __nv_bfloat16* dp = static_cast<const __nv_bfloat16*>(dp_bf16);
   const uint32_t* cd = static_cast<const uint32_t*>(codes_u32);
   if (cin == 1 && cout == 64)
-    first_wgrad_codes_kernel<1, 64><<<grid, 256, 0, s>>>(x, n, c_total, c_offset, H, W, cd, dp, slope, t1, sums);
+    first_wgrad_codes_kernel<1, 64><<<grid, 256, 0, s>>>(x, n, c_total, c_offset, H, W, cd, dp, slope, part);
   else if (cin == 2 && cout == 128)
-    first_wgrad_codes_kernel<2, 128><<<grid, 256, 0, s>>>(x, n, c_total, c_offset, H, W, cd, dp, slope, t1, sums);
+    first_wgrad_codes_kernel<2, 128><<<grid, 256, 0, s>>>(x, n, c_total, c_offset, H, W, cd, dp, slope, part);
   else
     return CTK_ERR_UNSUPPORTED;
-  return ctk::check_launch();
+  int st = ctk::check_launch();
+  if (st != CTK_OK) return st;
+  st = ctk::reduce_rows_f32(part, grid, cols, T * cout, t1, s);
+  if (st != CTK_OK) return st;
+  // sums = [d beta (this pass) | d gamma (ctk_first_wgrad_finalize)]
+  CTK_CUDA_TRY(cudaMemsetAsync(sums + cout, 0, sizeof(float) * cout, s));
+  return ctk::reduce_rows_f32(part + T * cout, grid, cols, cout, sums, s);
 }
 
 int ctk_first_wgrad_finalize(const float* t1, const double* gram, const float* w, const float* scale, const float* mean,

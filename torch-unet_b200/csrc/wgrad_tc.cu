@@ -15,7 +15,9 @@
 // and a patch costs 55 KB of L2 traffic for 9 taps instead of 52-72 KB for 3.
 // A CTA owns (co block, 64-ci block, kx group, slice): kx group 0 = columns {0, 1} (384 TMEM columns), group 1 = column 2
 // (192 columns, half the work, so it gets half as many slices); it walks every `slices`-th patch, accumulating in TMEM
-// with no epilogue in between; at the end the accumulators are added to dW (reference layout) with atomics.
+// with no epilogue in between; at the end every CTA stores its accumulators as one slice of partial sums in the workspace
+// (plain coalesced stores) and wgrad_reduce_kernel adds the slices of each (co block, ci block) in slice order into dW
+// (reference layout).  No floating-point atomics: two identical launches give bit-identical gradients.
 #include "ctk_common.h"
 #include "ctk_ptx.cuh"
 
@@ -38,8 +40,14 @@ struct WgradParams {
   int n_img, H, W, cin, cout;
   int tiles_x, tiles_y, total_tiles;
   int co_blocks, ci_blocks, slices_a, slices_b;   // slices of kx group 0 / 1
-  float* dw;                                  // [cout][cin][3][3] fp32, pre-zeroed
+  float* part;                                // workspace: per pair [slices_a][2][6][32][128] then [slices_b][6][32][128] fp32
+  float* dw;                                  // [cout][cin][3][3] fp32
 };
+constexpr int kColBlock = 32 * 128;           // one 32-column TMEM block of a CTA: [i (ci)][co] floats
+// floats of partial sums per (co block, ci block) pair
+__host__ __device__ inline size_t pair_part_floats(int slices_a, int slices_b) {
+  return static_cast<size_t>(slices_a) * 12 * kColBlock + static_cast<size_t>(slices_b) * 6 * kColBlock;
+}
 
 struct WgradSmem {
   uint64_t full[kStages], empty[kStages], done;
@@ -151,21 +159,29 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant
   } else {
     // epilogue: lane quadrant q of TMEM = co rows q*32 .. q*32+31 of this CTA's co block
     const int q = warp & 3;
-    const int co = co_blk * 128 + q * 32 + lane;
     const bool any = slice < p.total_tiles;
+    // this CTA's slice of the pair's partial sums: [j (kx)][cb][i][co in block], co fastest -> 128-byte warp stores
+    float* mine = p.part + static_cast<size_t>(pair) * pair_part_floats(p.slices_a, p.slices_b) +
+                  (group == 0 ? static_cast<size_t>(slice) * 12 * kColBlock
+                              : static_cast<size_t>(p.slices_a) * 12 * kColBlock + static_cast<size_t>(slice) * 6 * kColBlock) +
+                  q * 32 + lane;
     if (any) {
       mbar_wait(&sl->done, 0);
       tc_fence_after();
-      for (int j = 0; j < nkx; ++j) {
-        for (int cb = 0; cb < kN / 32; ++cb) {                   // column cb*32 + i = (ky = cb / 2, ci = (cb % 2) * 32 + i)
-          uint32_t v[32];
+    }
+    for (int j = 0; j < nkx; ++j) {
+      for (int cb = 0; cb < kN / 32; ++cb) {                   // column cb*32 + i = (ky = cb / 2, ci = (cb % 2) * 32 + i)
+        uint32_t v[32];
+        if (any) {
           tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + j * kN + cb * 32, v);
           tmem_ld_wait();
-          const int ky = cb >> 1;
-          float* dst = p.dw + (static_cast<size_t>(co) * p.cin + ci_blk * 64 + (cb & 1) * 32) * 9 + ky * 3 + kx0 + j;
+        } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) atomicAdd(dst + i * 9, __uint_as_float(v[i]));
+          for (int i = 0; i < 32; ++i) v[i] = 0u;              // a slice without patches still owns (zero) partial sums
         }
+        float* dst = mine + static_cast<size_t>(j * 6 + cb) * kColBlock;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) dst[i * 128] = __uint_as_float(v[i]);
       }
     }
   }
@@ -178,6 +194,36 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant
   }
 }
 
+// Second stage: dW[co][ci][ky][kx] = sum over the slices of its (co block, ci block) pair, in slice order.
+// grid = (pairs * 18, 1): one CTA per 32-column block of the pair's 18 = 3 kx x 6 (ky, ci half); thread = (i, co quarter).
+__global__ void __launch_bounds__(1024) wgrad_reduce_kernel(const WgradParams p) {
+  const int pair = blockIdx.x / 18, blk = blockIdx.x % 18;
+  const int kx = blk / 6, cb = blk % 6;
+  const int ci_blk = pair % p.ci_blocks, co_blk = pair / p.ci_blocks;
+  const int co_l = threadIdx.x & 127, i0 = threadIdx.x >> 7;      // 8 values of i per pass
+  const float* base = p.part + static_cast<size_t>(pair) * pair_part_floats(p.slices_a, p.slices_b);
+  const int slices = kx < 2 ? p.slices_a : p.slices_b;
+  const size_t slice_stride = kx < 2 ? 12 * kColBlock : 6 * kColBlock;
+  const float* src = base + (kx < 2 ? static_cast<size_t>(kx * 6 + cb) * kColBlock
+                                    : static_cast<size_t>(p.slices_a) * 12 * kColBlock + static_cast<size_t>(cb) * kColBlock);
+  const int ky = cb >> 1;
+#pragma unroll
+  for (int pass = 0; pass < 4; ++pass) {
+    const int i = pass * 8 + i0;
+    const float* col = src + i * 128 + co_l;
+    float acc = 0.f;
+    int s = 0;
+    for (; s + 4 <= slices; s += 4) {
+      const float a = col[static_cast<size_t>(s) * slice_stride], b = col[static_cast<size_t>(s + 1) * slice_stride];
+      const float c = col[static_cast<size_t>(s + 2) * slice_stride], d = col[static_cast<size_t>(s + 3) * slice_stride];
+      acc = (((acc + a) + b) + c) + d;
+    }
+    for (; s < slices; ++s) acc += col[static_cast<size_t>(s) * slice_stride];
+    const int co = co_blk * 128 + co_l, ci = ci_blk * 64 + (cb & 1) * 32 + i;
+    p.dw[(static_cast<size_t>(co) * p.cin + ci) * 9 + ky * 3 + kx] = acc;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // First layer (Cin = 1 or 2): K = pixels, N = 9*Cin is too narrow for the tensor cores -> fp32 CUDA-core reduction.
 // dW[co][ci][tap] = sum dY[n,y,x,co] * x[n,ci,y+ky-1,x+kx-1];  x is the fp32 NCHW input, dY is bf16 NHWC.
@@ -185,7 +231,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant
 template <int CIN, int COUT>
 __global__ void __launch_bounds__(256)
 wgrad_first_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x, int n_img, int c_total,
-                   int c_offset, int H, int W, float* __restrict__ dw) {
+                   int c_offset, int H, int W, float* __restrict__ part) {
   constexpr int G = COUT / 4;                  // channel groups
   constexpr int SLOTS = 256 / G;               // pixels processed concurrently
   constexpr int TW = 32, TH = 8;               // pixel tile per iteration
@@ -244,7 +290,7 @@ wgrad_first_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict
       if (slot == 0) {
         float s = 0.f;
         for (int t = 0; t < SLOTS; ++t) s += s_red[t * G + cg];
-        atomicAdd(dw + (cg * 4 + j) * (CIN * 9) + k, s);
+        part[static_cast<size_t>(blockIdx.x) * (COUT * CIN * 9) + (cg * 4 + j) * (CIN * 9) + k] = s;   // one row per CTA
       }
     }
 }
@@ -253,13 +299,20 @@ wgrad_first_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict
 
 extern "C" {
 
+// the grid is one resident wave (<= one CTA per SM), every CTA stores at most 12 column blocks of 32 x 128 floats
+size_t ctk_conv3x3_wgrad_tc_workspace_bytes(int cin, int cout) {
+  if (cin <= 0 || cout <= 0) return 0;
+  const size_t pairs = static_cast<size_t>((cout + 127) / 128) * ((cin + 63) / 64);
+  const size_t ctas = std::max(static_cast<size_t>(ctk::num_sms()), 3 * pairs);
+  return ctas * 12 * kColBlock * sizeof(float);
+}
+
 int ctk_conv3x3_wgrad_tc(const void* dy_bf16, const void* x_bf16, int n, int H, int W, int cin, int cout, float* dw,
-                         void* stream) {
+                         void* workspace, size_t workspace_bytes, void* stream) {
   if (n == 0) return CTK_OK;
   CTK_REQUIRE(dy_bf16 && x_bf16 && dw && n > 0 && H > 0 && W > 0 && W % kTileW == 0 && cin % 64 == 0 && cout % 128 == 0);
   CTK_REQUIRE((reinterpret_cast<uintptr_t>(dy_bf16) & 15) == 0 && (reinterpret_cast<uintptr_t>(x_bf16) & 15) == 0);
   cudaStream_t s = ctk::as_stream(stream);
-  CTK_CUDA_TRY(cudaMemsetAsync(dw, 0, sizeof(float) * 9 * cin * cout, s));
   WgradParams p = {};
   p.n_img = n; p.H = H; p.W = W; p.cin = cin; p.cout = cout;
   p.tiles_x = W / kTileW;
@@ -276,6 +329,8 @@ int ctk_conv3x3_wgrad_tc(const void* dy_bf16, const void* x_bf16, int n, int H, 
   p.slices_a = std::min(p.total_tiles, 2 * s_unit);
   p.slices_b = std::min(p.total_tiles, s_unit);
   p.dw = dw;
+  CTK_REQUIRE_WORKSPACE(workspace, workspace_bytes, pairs * pair_part_floats(p.slices_a, p.slices_b) * sizeof(float));
+  p.part = static_cast<float*>(workspace);
 
   CUtensorMap tm_dy, tm_x;
   {
@@ -300,25 +355,36 @@ int ctk_conv3x3_wgrad_tc(const void* dy_bf16, const void* x_bf16, int n, int H, 
   const int smem_bytes = 1024 + kStages * kStageBytes + 256;
   CTK_CUDA_TRY(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   wgrad_tc_kernel<<<grid, kThreads, smem_bytes, s>>>(tm_dy, tm_x, p);
+  int st = ctk::check_launch();
+  if (st != CTK_OK) return st;
+  wgrad_reduce_kernel<<<pairs * 18, 1024, 0, s>>>(p);
   return ctk::check_launch();
 }
 
+size_t ctk_conv_first_wgrad_workspace_bytes(int cin, int cout) {
+  return cin > 0 && cout > 0 ? static_cast<size_t>(ctk::num_sms()) * 4 * 9 * cin * cout * sizeof(float) : 0;
+}
+
 int ctk_conv_first_wgrad(const void* dy_bf16, const float* x, int n, int c_total, int c_offset, int cin, int H, int W,
-                         int cout, float* dw, void* stream) {
+                         int cout, float* dw, void* workspace, size_t workspace_bytes, void* stream) {
   if (n == 0) return CTK_OK;
   CTK_REQUIRE(dy_bf16 && x && dw && n > 0 && H > 0 && W > 0 && c_offset >= 0 && c_offset + cin <= c_total);
   cudaStream_t s = ctk::as_stream(stream);
-  CTK_CUDA_TRY(cudaMemsetAsync(dw, 0, sizeof(float) * 9 * cin * cout, s));
   const int grid = ctk::num_sms() * 4;
+  const int cols = 9 * cin * cout;
+  CTK_REQUIRE_WORKSPACE(workspace, workspace_bytes, static_cast<size_t>(grid) * cols * sizeof(float));
+  float* part = static_cast<float*>(workspace);
   const __nv_bfloat16* dy = static_cast<const __nv_bfloat16*>(dy_bf16);
   if (cin == 1 && cout == 64) {
-    wgrad_first_kernel<1, 64><<<grid, 256, 0, s>>>(dy, x, n, c_total, c_offset, H, W, dw);
+    wgrad_first_kernel<1, 64><<<grid, 256, 0, s>>>(dy, x, n, c_total, c_offset, H, W, part);
   } else if (cin == 2 && cout == 128) {
-    wgrad_first_kernel<2, 128><<<grid, 256, 0, s>>>(dy, x, n, c_total, c_offset, H, W, dw);
+    wgrad_first_kernel<2, 128><<<grid, 256, 0, s>>>(dy, x, n, c_total, c_offset, H, W, part);
   } else {
     return CTK_ERR_UNSUPPORTED;
   }
-  return ctk::check_launch();
+  int st = ctk::check_launch();
+  if (st != CTK_OK) return st;
+  return ctk::reduce_rows_f32(part, grid, cols, cols, dw, s);
 }
 
 }  // extern "C"

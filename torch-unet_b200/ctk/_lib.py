@@ -64,31 +64,44 @@ _SIGNATURES = {
     "ctk_adam_multi": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float,
                                c_float, c_float, c_float, c_float, c_int, c_float, c_void_p]),
     # ---- training path
+    "ctk_conv_first_raw_workspace_bytes": (c_size_t, [c_int]),
     "ctk_conv_first_raw": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p,
-                                   c_void_p, c_void_p]),
-    "ctk_conv3x3_tc_raw": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+                                   c_void_p, c_void_p, c_size_t, c_void_p]),
+    "ctk_conv3x3_tc_raw_workspace_bytes": (c_size_t, [c_int]),
+    "ctk_conv3x3_tc_raw": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                                   c_size_t, c_void_p]),
     "ctk_pack_conv_weight_dgrad_bf16": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "ctk_bn_finalize": (c_int, [c_void_p, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
                                 c_float, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "ctk_bn_finalize_moments": (c_int, [c_void_p, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                         c_float, c_float, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "ctk_first_patch_gram": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "ctk_first_patch_gram_workspace_bytes": (c_size_t, [c_int]),
+    "ctk_first_patch_gram": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t,
+                                     c_void_p]),
     "ctk_first_moments": (c_int, [c_void_p, c_void_p, c_int, c_int, c_double, c_void_p, c_void_p]),
+    "ctk_first_wgrad_codes_workspace_bytes": (c_size_t, [c_int, c_int]),
     "ctk_first_wgrad_codes": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
-                                      c_float, c_void_p, c_void_p, c_void_p]),
+                                      c_float, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "ctk_first_wgrad_finalize": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_double,
                                          c_int, c_int, c_void_p, c_void_p]),
     "ctk_bn_act_pool_fwd": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p, c_int,
                                     c_int, c_void_p]),
+    "ctk_bn_bwd_reduce_workspace_bytes": (c_size_t, [c_int]),
     "ctk_bn_bwd_reduce": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
-                                  c_void_p, c_void_p, c_float, c_void_p, c_void_p]),
+                                  c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_size_t, c_void_p]),
     "ctk_bn_bwd_reduce_pooled": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_longlong, c_int, c_void_p,
-                                         c_void_p, c_float, c_void_p, c_void_p]),
+                                         c_void_p, c_float, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "ctk_bn_bwd_reduce_guarded": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                          c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_float,
+                                          c_void_p, c_void_p, c_size_t, c_void_p]),
     "ctk_bn_bwd_apply": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                  c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p]),
-    "ctk_conv3x3_wgrad_tc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
-    "ctk_conv_first_wgrad": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
+    "ctk_conv3x3_wgrad_tc_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "ctk_conv3x3_wgrad_tc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t,
                                      c_void_p]),
+    "ctk_conv_first_wgrad_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "ctk_conv_first_wgrad": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                                     c_void_p, c_size_t, c_void_p]),
     "ctk_feat_transpose_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     "ctk_pack_fc1_weight_t_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "ctk_gemm_bf16_out_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
@@ -143,15 +156,23 @@ def stream() -> c_void_p:
     return c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def workspace(query: str, *args, device=None):
+    """(tensor, pointer, byte count) of a caller-owned workspace sized by the entry point's ``*_workspace_bytes`` query.
+    Allocated through torch's caching allocator on the current stream, so it is recycled like any other temporary."""
+    nbytes = int(getattr(load(), query)(*args))
+    t = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=device if device is not None else torch.cuda.current_device())
+    return t, c_void_p(t.data_ptr()), c_size_t(nbytes)
+
+
 # kernels launched per successful call (bench.py reports the sum as "gpu_launches")
 KERNELS_PER_CALL = {"ctk_pearson_f32": 2, "ctk_tile_metrics_f32": 4, "ctk_tile_nmi_f32": 4, "ctk_tile_ssim_f32": 3, "ctk_prepare_tiles": 1, "ctk_fold_bn_eval": 1, "ctk_pack_conv_weight_bf16": 1, "ctk_pack_first_weight": 1,
                     "ctk_pack_fc1_weight_bf16": 1, "ctk_conv_first_eval": 1, "ctk_conv_first_pool_codes": 1, "ctk_pack_conv_weight_split_bf16": 1,
                     "ctk_pack_fc1_weight_split_bf16": 1, "ctk_conv_first_eval_split": 1, "ctk_conv3x3_tc_eval_split": 1, "ctk_conv3x3_tc_eval": 1,
                     "ctk_gemm_bf16_splitk": 1, "ctk_head_eval": 1, "ctk_mse_loss": 1, "ctk_adam_multi": 1,
-                    "ctk_conv_first_raw": 1, "ctk_conv3x3_tc_raw": 1, "ctk_pack_conv_weight_dgrad_bf16": 1,
-                    "ctk_bn_finalize": 1, "ctk_bn_finalize_moments": 1, "ctk_first_patch_gram": 1,
-                    "ctk_first_moments": 1, "ctk_first_wgrad_codes": 1, "ctk_first_wgrad_finalize": 1, "ctk_bn_act_pool_fwd": 1, "ctk_bn_bwd_reduce": 1, "ctk_bn_bwd_reduce_pooled": 1, "ctk_bn_bwd_apply": 1,
-                    "ctk_conv3x3_wgrad_tc": 1, "ctk_conv_first_wgrad": 1, "ctk_feat_transpose_bf16": 1,
+                    "ctk_conv_first_raw": 2, "ctk_conv3x3_tc_raw": 1, "ctk_pack_conv_weight_dgrad_bf16": 1,
+                    "ctk_bn_finalize": 1, "ctk_bn_finalize_moments": 1, "ctk_first_patch_gram": 2,
+                    "ctk_first_moments": 1, "ctk_first_wgrad_codes": 3, "ctk_first_wgrad_finalize": 1, "ctk_bn_act_pool_fwd": 1, "ctk_bn_bwd_reduce": 2, "ctk_bn_bwd_reduce_pooled": 2, "ctk_bn_bwd_reduce_guarded": 3, "ctk_bn_bwd_apply": 1,
+                    "ctk_conv3x3_wgrad_tc": 2, "ctk_conv_first_wgrad": 2, "ctk_feat_transpose_bf16": 1,
                     "ctk_pack_fc1_weight_t_bf16": 1, "ctk_gemm_bf16_out_bf16": 1, "ctk_gemm_bf16_bt_out_bf16": 1, "ctk_colstat": 1,
                     "ctk_bn1d_act_drop_fwd": 1, "ctk_sgemm_strided": 1, "ctk_head_out_fwd": 1, "ctk_head_out_bwd": 1,
                     "ctk_bn1d_bwd_reduce": 1, "ctk_bn1d_bwd_apply": 1}
@@ -172,7 +193,7 @@ def call(name: str, *args, meta=None) -> None:
         _timeline.append((name, e0, e1, meta))
     else:
         check(fn(*args), name)
-    launch_count += KERNELS_PER_CALL.get(name, 0)
+    launch_count += (meta or {}).get("kernels", KERNELS_PER_CALL.get(name, 0))
 
 
 def start_timeline(only=None) -> list:

@@ -44,11 +44,33 @@ def _head_layers(seq):
 class _Branch:
     """One conv stack: first block on the fp32 pipe (cin 1 or 2), the rest on tcgen05."""
 
-    def __init__(self, pairs, c_offset: int):
+    def __init__(self, pairs, c_offset: int, training: bool = False):
         self.pairs = pairs
         self.c_offset = c_offset
         self.cin = pairs[0][0].in_channels
         self.channels = [p[0].out_channels for p in pairs]
+        self._validate(training)
+
+    def _validate(self, training: bool) -> None:
+        """The kernels cover the widths the reference instantiates (train_model.py:535,537: 64 filters per branch, or 128
+        filters x 6 blocks) and anything built from the same pieces; say so at construction instead of failing inside
+        a kernel launch with an opaque status."""
+        supported = ("supported: first Conv2d 1->64 or 2->128 channels; later Conv2d layers with in_channels a multiple of 64 "
+                     "and out_channels a multiple of 64 (128 for training) up to 512 -- e.g. "
+                     "AdvancedRegressionModel(2, 128, 6) and SimplifiedTwoBranchRegressionModel(64)")
+        for li, (conv, bn) in enumerate(self.pairs):
+            cin, cout = conv.in_channels, conv.out_channels
+            if li == 0:
+                ok = (cin, cout) in ((1, 64), (2, 128))
+            else:
+                ok = cin % 64 == 0 and cout % (128 if training else 64) == 0 and cout <= 512
+            if not ok:
+                raise _lib.CtkError(f"conv block {li} ({cin}->{cout} channels) has no libctk kernel; {supported}")
+            if bn.num_features != cout or not bn.affine or not bn.track_running_stats:
+                raise _lib.CtkError(f"conv block {li}: BatchNorm2d must be affine, track running statistics and match the conv")
+            if training and bn.momentum is None:
+                raise _lib.CtkError("BatchNorm momentum=None (cumulative average) is not supported by the ctk training path; "
+                                    "the reference uses the default momentum 0.1")
 
 
 class InferenceEngine:

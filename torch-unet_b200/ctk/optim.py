@@ -86,4 +86,7 @@ class Adam(torch.optim.Optimizer):
                  c_float(group["eps"]), c_float(group["weight_decay"]), c_int(t), c_float(grad_scale), stream())
             for p in plist:
                 self.state[p]["step"] += 1
+            # the kernel updated the parameters through raw pointers: bump their version counters so that derived caches
+            # keyed on them (InferenceEngine's packed weights / folded BatchNorm) are rebuilt at the next eval forward
+            torch.autograd.graph.increment_version(plist)
         return loss

@@ -16,6 +16,8 @@ from typing import Dict, List, Optional, Tuple
 import torch
 import torch.distributed as dist
 
+from ._lib import CtkError
+
 BIG_TENSOR_BYTES = 8 << 20
 BUCKET_BYTES = 25 << 20
 
@@ -98,6 +100,18 @@ def attach(model: torch.nn.Module, process_group=None, sync_bn: bool = False, **
         pg = process_group
         eng.stat_allreduce = lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM, group=pg)
         eng.stat_world = sync.world
+
+        def check_equal_batch(n: int, dev) -> None:
+            # global statistics are formed with count = n * world: ragged shards (shard_range on a batch that does not
+            # divide, a ragged last DataLoader batch) would be normalised with the wrong count -- refuse them
+            t = torch.tensor([float(n), -float(n)], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=pg)
+            hi, neg_lo = t.tolist()
+            if hi != -neg_lo:
+                raise CtkError(f"sync_bn=True needs the same number of tiles on every rank (this rank {n}, "
+                               f"min {int(-neg_lo)}, max {int(hi)}): pad or drop the ragged batch")
+
+        eng.stat_check_equal_batch = check_equal_batch
     return sync
 
 

@@ -9,13 +9,13 @@ runs unchanged; PyTorch only owns the tensors and the graph edge.
 from __future__ import annotations
 
 import contextlib
-from ctypes import c_double, c_float, c_int, c_longlong
+from ctypes import c_double, c_float, c_int, c_longlong, c_size_t
 from typing import Callable, Dict, List, Optional, Tuple
 
 import torch
 
 from . import _lib
-from ._lib import call, ptr, stream
+from ._lib import call, ptr, stream, workspace
 from .engine import LEAKY_SLOPE, _Branch, _conv_bn_pairs, _head_layers
 
 
@@ -28,18 +28,20 @@ class TrainEngine:
         self.model = model
         if hasattr(model, "conv_layers") and hasattr(model, "fc_layers"):
             self.kind = "single"
-            self.branches = [_Branch(_conv_bn_pairs(model.conv_layers), 0)]
+            self.branches = [_Branch(_conv_bn_pairs(model.conv_layers), 0, training=True)]
             seq = model.fc_layers
             self.sigmoid_half = 0
         elif hasattr(model, "bleed_branch") and hasattr(model, "source_branch"):
             self.kind = "double"
-            self.branches = [_Branch(_conv_bn_pairs(model.bleed_branch.conv_blocks), 0),
-                             _Branch(_conv_bn_pairs(model.source_branch.conv_blocks), 1)]
+            self.branches = [_Branch(_conv_bn_pairs(model.bleed_branch.conv_blocks), 0, training=True),
+                             _Branch(_conv_bn_pairs(model.source_branch.conv_blocks), 1, training=True)]
             seq = model.regression_head.fc_layers
             self.sigmoid_half = 1
         else:
             raise _lib.CtkError(f"{type(model).__name__} is not one of the two crosstalk regression models")
         self.lin, self.bns = _head_layers(seq)
+        if any(bn.momentum is None for bn in self.bns):
+            raise _lib.CtkError("BatchNorm momentum=None (cumulative average) is not supported by the ctk training path")
         self.drop_p = [m.p for m in seq if isinstance(m, torch.nn.Dropout)]
         if len(self.drop_p) != 2:
             raise _lib.CtkError("head layout differs from the reference (2 Dropout layers expected)")
@@ -56,7 +58,10 @@ class TrainEngine:
         # hook the data-parallel path reproduces that instead of per-rank statistics.
         self.stat_allreduce: Optional[Callable[[torch.Tensor], None]] = None
         self.stat_world: int = 1
-        self._saved: Optional[dict] = None
+        # SyncBN forms global statistics as (sum over ranks) / (n * world): every rank must hold the same number of tiles.
+        # parallel.attach installs a check (one 16-byte all-reduce per forward) that raises instead of silently normalising
+        # with the wrong count when shards are ragged.
+        self.stat_check_equal_batch: Optional[Callable[[int, torch.device], None]] = None
         # EXPERIMENTAL (not yet measured on a GPU): run every branch's conv stack on its own stream and every wgrad on a
         # further side stream, so that the HBM-bound BatchNorm passes of one branch / layer overlap the tensor-bound conv
         # kernels of the other.  Off by default; see DESIGN.md section 8.
@@ -86,7 +91,7 @@ class TrainEngine:
     def _bn_finalize(self, sums, count, bias, bn, dev, moments=False):
         c = bn.num_features
         scale, shift, mean, invstd = (self._new((c,), torch.float32, dev) for _ in range(4))
-        mom = 0.1 if bn.momentum is None else bn.momentum
+        mom = bn.momentum
         track = bn.track_running_stats and bn.running_mean is not None
         call("ctk_bn_finalize_moments" if moments else "ctk_bn_finalize", ptr(sums), c_double(count), ptr(bias), ptr(bn.weight), ptr(bn.bias),
              ptr(bn.running_mean if track else None), ptr(bn.running_var if track else None),
@@ -133,8 +138,9 @@ class TrainEngine:
                 # the full-resolution conv output is never written
                 T = 9 * cin
                 gram = self._new((T + T * T,), torch.float64, dev)
+                ws = workspace("ctk_first_patch_gram_workspace_bytes", cin, device=dev)
                 call("ctk_first_patch_gram", ptr(x), c_int(n), c_int(c_total), c_int(br.c_offset), c_int(cin), c_int(h),
-                     c_int(w), ptr(gram), stream())
+                     c_int(w), ptr(gram), ws[1], ws[2], stream())
                 self._sync_stats(gram)
                 count = float(n) * h * w * self.stat_world
                 mom = self._new((2 * cout,), torch.float32, dev)
@@ -156,13 +162,16 @@ class TrainEngine:
             y = self._new((n, h, w, cout), torch.bfloat16, dev)
             stats = self._new((2 * cout,), torch.float32, dev)
             if li == 0:
+                ws = workspace("ctk_conv_first_raw_workspace_bytes", cout, device=dev)
                 call("ctk_conv_first_raw", ptr(x), c_int(n), c_int(c_total), c_int(br.c_offset), c_int(cin), c_int(h),
-                     c_int(w), ptr(conv.weight), c_int(cout), ptr(y), ptr(stats), stream())
+                     c_int(w), ptr(conv.weight), c_int(cout), ptr(y), ptr(stats), ws[1], ws[2], stream())
             else:
                 wp = self._new((9, cout, cin), torch.bfloat16, dev)
                 call("ctk_pack_conv_weight_bf16", ptr(conv.weight), c_int(cout), c_int(cin), ptr(wp), stream())
+                ws = workspace("ctk_conv3x3_tc_raw_workspace_bytes", cout, device=dev)
                 call("ctk_conv3x3_tc_raw", ptr(cur), c_int(n), c_int(h), c_int(w), c_int(cin), ptr(wp), c_int(cout),
-                     ptr(y), ptr(stats), stream(), meta={"flops": 2.0 * n * h * w * cout * 9 * cin})
+                     ptr(y), ptr(stats), ws[1], ws[2], stream(),
+                     meta={"flops": 2.0 * n * h * w * cout * 9 * cin, "kernels": 2})
             self._sync_stats(stats)
             scale, shift, mean, invstd = self._bn_finalize(stats, float(n) * h * w * self.stat_world, conv.bias, bn, dev)
             call("ctk_bn_act_pool_fwd", ptr(y), c_int(n), c_int(h), c_int(w), c_int(cout), ptr(scale), ptr(shift),
@@ -174,7 +183,10 @@ class TrainEngine:
         return blocks
 
     # ------------------------------------------------------------------ forward
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
+    def forward(self, x: torch.Tensor) -> Tuple[torch.Tensor, dict]:
+        """Returns (scores [n,1], saved state).  The saved state belongs to THIS forward pass (the autograd edge keeps it
+        on its ctx), so several forwards may be in flight before their backwards run -- gradient accumulation over
+        micro-batches, two losses, a train-mode forward under no_grad in between."""
         _lib.require_device(x, torch.float32, "input batch")
         if x.dim() != 4 or x.shape[1] != 2 or x.shape[2] % 32 or x.shape[3] % 32:
             raise _lib.CtkError(f"input must be [N,2,H,W] float32 with H, W multiples of 32, got {tuple(x.shape)}")
@@ -190,6 +202,8 @@ class TrainEngine:
         if K != hf * wf * self.feat_channels:
             raise _lib.CtkError("input size does not match the model's first Linear layer")
         m_pad = _pad(n, 128)
+        if self.stat_check_equal_batch is not None:
+            self.stat_check_equal_batch(n, dev)
         sv = {"x": x, "n": n, "H": H, "W": W, "m_pad": m_pad, "blocks": []}
         feat = torch.zeros((m_pad, hf, wf, self.feat_channels), device=dev, dtype=torch.bfloat16)
         c_off = 0
@@ -251,8 +265,10 @@ class TrainEngine:
         call("ctk_head_out_fwd", ptr(a2), ptr(fc3.weight), ptr(fc3.bias), c_int(n), c_int(f2), c_int(self.sigmoid_half),
              ptr(out), stream())
         sv.update(z1=z1, bn1=bn1, a1=a1, z2=z2, bn2=bn2, a2=a2, out=out, masks=masks, w1p=w1p)
-        self._saved = sv
-        return out
+        # ctk_bn_finalize wrote the running statistics through raw pointers: bump the tensors' version counters so that
+        # anything keyed on them (the eval engine's derived-parameter cache) sees the change
+        torch.autograd.graph.increment_version([b for b in self.model.buffers()])
+        return out, sv
 
     def _masks(self, n, f1, f2, dev):
         if self.forced_masks is not None:
@@ -287,8 +303,10 @@ class TrainEngine:
                     raise _lib.CtkError("the first block's output gradient must be dense")
                 T = 9 * cin
                 t1 = self._new((cout, T), torch.float32, dev)
+                ws = workspace("ctk_first_wgrad_codes_workspace_bytes", cin, cout, device=dev)
                 call("ctk_first_wgrad_codes", ptr(x), c_int(n), c_int(x.shape[1]), c_int(br.c_offset), c_int(cin), c_int(h),
-                     c_int(w), ptr(b["codes"]), ptr(dp), c_int(cout), c_float(LEAKY_SLOPE), ptr(t1), ptr(sums), stream())
+                     c_int(w), ptr(b["codes"]), ptr(dp), c_int(cout), c_float(LEAKY_SLOPE), ptr(t1), ptr(sums), ws[1], ws[2],
+                     stream())
                 dw = self._new(tuple(conv.weight.shape), torch.float32, dev)
                 # SyncBN: the saved Gram matrix is already the global one, so reduce t1 / sum(dA) too and form the
                 # global gradient on every rank; dividing by the world size makes the exchange's mean leave it as is
@@ -306,9 +324,13 @@ class TrainEngine:
                 done(conv.bias, torch.zeros_like(conv.bias))
                 continue
             pooled, p_cstride, p_coff = b["pooled"]
-            call("ctk_bn_bwd_reduce_pooled", ptr(pooled), c_int(p_cstride), c_int(p_coff), ptr(dp), c_int(dp_cstride),
-                 c_int(dp_coff), c_longlong(n * (h // 2) * (w // 2)), c_int(cout), ptr(bn.weight), ptr(bn.bias),
-                 c_float(LEAKY_SLOPE), ptr(sums), stream())
+            # sums from the pooled tensors; channel groups whose BatchNorm parameters make that reconstruction lossy
+            # (gamma == 0 or |beta| > 8 |gamma|) are reduced from the raw conv output instead -- decided on the device
+            ws = workspace("ctk_bn_bwd_reduce_workspace_bytes", cout, device=dev)
+            call("ctk_bn_bwd_reduce_guarded", ptr(b["y"]), c_int(n), c_int(h), c_int(w), ptr(b["scale"]), ptr(b["shift"]),
+                 ptr(b["mean"]), ptr(b["invstd"]), ptr(pooled), c_int(p_cstride), c_int(p_coff), ptr(dp), c_int(dp_cstride),
+                 c_int(dp_coff), c_int(cout), ptr(bn.weight), ptr(bn.bias), c_float(LEAKY_SLOPE), ptr(sums), ws[1], ws[2],
+                 stream())
             done(bn.bias, sums[:cout])
             done(bn.weight, sums[cout:])
             dy = self._new((n, h, w, cout), torch.bfloat16, dev)
@@ -329,11 +351,13 @@ class TrainEngine:
             with wg_ctx:
                 dw = self._new(tuple(conv.weight.shape), torch.float32, dev)
                 if li == 0:
+                    ws = workspace("ctk_conv_first_wgrad_workspace_bytes", cin, cout, device=dev)
                     call("ctk_conv_first_wgrad", ptr(dy), ptr(x), c_int(n), c_int(x.shape[1]), c_int(br.c_offset), c_int(cin),
-                         c_int(h), c_int(w), c_int(cout), ptr(dw), stream())
+                         c_int(h), c_int(w), c_int(cout), ptr(dw), ws[1], ws[2], stream())
                 else:
+                    ws = workspace("ctk_conv3x3_wgrad_tc_workspace_bytes", cin, cout, device=dev)
                     call("ctk_conv3x3_wgrad_tc", ptr(dy), ptr(b["x_in"]), c_int(n), c_int(h), c_int(w), c_int(cin), c_int(cout),
-                         ptr(dw), stream(), meta={"flops": 2.0 * n * h * w * cout * 9 * cin})
+                         ptr(dw), ws[1], ws[2], stream(), meta={"flops": 2.0 * n * h * w * cout * 9 * cin})
                 done(conv.weight, dw)
             # the conv bias feeds a train-mode BatchNorm, so its gradient is sum(dY) = 0 identically
             done(conv.bias, torch.zeros_like(conv.bias))
@@ -342,16 +366,17 @@ class TrainEngine:
                 call("ctk_pack_conv_weight_dgrad_bf16", ptr(conv.weight), c_int(cout), c_int(cin), ptr(wg), stream())
                 dx = self._new((n, h, w, cin), torch.bfloat16, dev)
                 call("ctk_conv3x3_tc_raw", ptr(dy), c_int(n), c_int(h), c_int(w), c_int(cout), ptr(wg), c_int(cin), ptr(dx),
-                     ptr(None), stream(), meta={"flops": 2.0 * n * h * w * cout * 9 * cin})
+                     ptr(None), ptr(None), c_size_t(0), stream(), meta={"flops": 2.0 * n * h * w * cout * 9 * cin})
                 dp, dp_cstride, dp_coff = dx, cin, 0
             del dy
 
     # ------------------------------------------------------------------ backward
-    def backward(self, dout: torch.Tensor) -> Dict[torch.nn.Parameter, torch.Tensor]:
-        sv = self._saved
-        if sv is None:
-            raise _lib.CtkError("backward called without a matching train-mode forward")
-        self._saved = None
+    def backward(self, sv: dict, dout: torch.Tensor) -> Dict[torch.nn.Parameter, torch.Tensor]:
+        """Gradients of every parameter for the forward pass that produced ``sv`` (consumed: a second backward through the
+        same pass raises, like autograd without retain_graph)."""
+        if sv.get("consumed"):
+            raise _lib.CtkError("backward called twice for the same train-mode forward (activations already released)")
+        sv["consumed"] = True
         dout = dout.contiguous().float()
         _lib.require_device(dout, torch.float32, "output gradient")
         grads: Dict[torch.nn.Parameter, torch.Tensor] = {}
@@ -471,12 +496,14 @@ class _CtkTrainFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, engine, x, *params):
         ctx.engine = engine
-        return engine.forward(x)
+        out, ctx.sv = engine.forward(x)
+        return out
 
     @staticmethod
     def backward(ctx, dout):
-        engine = ctx.engine
-        grads = engine.backward(dout)
+        engine, sv = ctx.engine, ctx.sv
+        ctx.sv = None
+        grads = engine.backward(sv, dout)
         return (None, None) + tuple(grads.get(p) for p in engine.params)
 
 
