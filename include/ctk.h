@@ -193,6 +193,9 @@ int ctk_prepare_tiles(const void* raw, int raw_is_f64, const unsigned char* flip
  * loss_out: [1] fp32; grad_out (may be NULL): [n] fp32 = 2*(out-target)/n.
  * ------------------------------------------------------------------------------------------ */
 int ctk_mse_loss(const float* out, const float* target, int n, float* loss_out, float* grad_out, void* stream);
+/* out[i] = in[i] * scalar[0] (scalar on the device): the backward of the MSE loss scales the gradient ctk_mse_loss
+ * already produced by the incoming d(loss), which loss.backward() seeds with 1 (train_model.py:422). */
+int ctk_scale_by_scalar(const float* in, const float* scalar, int n, float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Multi-tensor Adam with coupled L2 (torch.optim.Adam(lr, weight_decay) semantics).
@@ -342,6 +345,12 @@ int ctk_colstat(const float* in, int splits, long long split_stride, int row_str
                 int features, float* z, float* stats, void* stream);
 int ctk_bn1d_act_drop_fwd(const float* z, const float* scale, const float* shift, const float* mask, float drop_p,
                           float slope, int n_rows, int features, float* a, void* stream);
+/* Keep-masks (1.0 keep / 0.0 drop) of the head's two nn.Dropout layers (regression_model.py:39,44;
+ * two_branch_regression.py:45,50) drawn on the device in one launch: Philox-4x32-10 keyed by `seed`, counter =
+ * (element / 4, offset); element kept when its uniform draw >= p.  Callers advance `offset` every step.  This is not
+ * torch's generator stream -- parity runs hand their own masks to ctk_bn1d_act_drop_fwd instead. */
+int ctk_dropout_masks(float* mask1, long long n1, float p1, float* mask2, long long n2, float p2, unsigned long long seed,
+                      unsigned long long offset, void* stream);
 int ctk_sgemm_strided(const float* a, long long a_i, long long a_k, const float* b, long long b_j, long long b_k,
                       const float* bias, int M, int N, int K, float* c, int ldc, void* stream);
 int ctk_head_out_fwd(const float* a2, const float* w3, const float* b3, int n_rows, int features, int sigmoid_half,

@@ -63,3 +63,18 @@ def test_prepare_tiles_restatement(golden):
                 ref = np.flip(ref, axis=-2)
             assert np.array_equal(out[i, c], ref)
             assert out[i, c].min() == 0.0 and out[i, c].max() == 1.0
+
+
+def test_product_synthetic_generator_matches_the_oracle_copy():
+    """bench.py's GPU arm draws its tiles from ctk.synthetic (product code, no oracle import); the oracle keeps its own copy
+    of the SURVEY 8d generator for the tests.  The two must stay bit-identical, and so must randomize_bn."""
+    import torch
+    import crosstalk_oracle as orc
+    from ctk import synthetic
+    xa, ya = synthetic.synthetic_batch(5, seed=1234)
+    xb, yb = orc.synthetic_batch(5, seed=1234)
+    assert torch.equal(xa, xb) and torch.equal(ya, yb)
+    assert xa.shape == (5, 2, 256, 256) and float(xa.amin()) == 0.0 and float(xa.amax()) == 1.0
+    sd = orc.init_double_state_dict(0)
+    ra, rb = synthetic.randomize_bn(sd, seed=7), orc.randomize_bn(sd, seed=7)
+    assert ra.keys() == rb.keys() and all(torch.equal(ra[k], rb[k]) for k in ra)

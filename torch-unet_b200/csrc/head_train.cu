@@ -52,6 +52,38 @@ __global__ void bn1d_act_drop_fwd_kernel(const float* __restrict__ z, const floa
   a[i] = v;
 }
 
+// Keep-masks of nn.Dropout drawn on the device: Philox-4x32-10 keyed by (seed), counter = (element index / 4, stream
+// offset); element i is kept when its uniform draw in [0, 1) is >= p.  One launch covers both Dropout layers of the
+// head (mask1 [n1] then mask2 [n2] elements).  Not PyTorch's generator stream: parity runs inject their masks instead.
+__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+  const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+  const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+  const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+  c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+}
+__global__ void dropout_masks_kernel(float* __restrict__ mask1, long long n1, float p1, float* __restrict__ mask2,
+                                     long long n2, float p2, unsigned long long seed, unsigned long long offset) {
+  const long long q = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;      // one Philox block = 4 elements
+  const long long q1 = (n1 + 3) / 4, q2 = (n2 + 3) / 4;
+  if (q >= q1 + q2) return;
+  uint32_t c[4] = {static_cast<uint32_t>(q), static_cast<uint32_t>(q >> 32), static_cast<uint32_t>(offset),
+                   static_cast<uint32_t>(offset >> 32)};
+  uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    philox_round(c, k0, k1);
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  const bool second = q >= q1;
+  float* dst = second ? mask2 : mask1;
+  const long long base = (second ? q - q1 : q) * 4, n = second ? n2 : n1;
+  const float p = second ? p2 : p1;
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    if (base + j < n) dst[base + j] = (static_cast<float>(c[j] >> 8) * (1.f / 16777216.f)) >= p ? 1.f : 0.f;
+}
+
 // C[i][j] = sum_k A[i*a_i + k*a_k] * B[j*b_j + k*b_k] (+ bias[j]); 32x32 tiles, K staged through shared memory
 __global__ void __launch_bounds__(256)
 sgemm_strided_kernel(const float* __restrict__ A, long long a_i, long long a_k, const float* __restrict__ B,
@@ -201,6 +233,17 @@ int ctk_bn1d_act_drop_fwd(const float* z, const float* scale, const float* shift
   const long long total = static_cast<long long>(n_rows) * features;
   bn1d_act_drop_fwd_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, ctk::as_stream(stream)>>>(
       z, scale, shift, mask, 1.f / (1.f - drop_p), slope, features, total, a);
+  return ctk::check_launch();
+}
+
+int ctk_dropout_masks(float* mask1, long long n1, float p1, float* mask2, long long n2, float p2, unsigned long long seed,
+                      unsigned long long offset, void* stream) {
+  CTK_REQUIRE((mask1 || n1 == 0) && (mask2 || n2 == 0) && n1 >= 0 && n2 >= 0 && p1 >= 0.f && p1 < 1.f && p2 >= 0.f &&
+              p2 < 1.f);
+  const long long blocks4 = (n1 + 3) / 4 + (n2 + 3) / 4;
+  if (blocks4 == 0) return CTK_OK;
+  dropout_masks_kernel<<<static_cast<unsigned>((blocks4 + 255) / 256), 256, 0, ctk::as_stream(stream)>>>(
+      mask1, n1, p1, mask2, n2, p2, seed, offset);
   return ctk::check_launch();
 }
 

@@ -31,6 +31,12 @@ __global__ void mse_kernel(const float* __restrict__ out, const float* __restric
   }
 }
 
+__global__ void scale_by_scalar_kernel(const float* __restrict__ in, const float* __restrict__ scalar, int n,
+                                       float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[i] * scalar[0];
+}
+
 struct AdamConsts {
   float beta1, beta2, one_minus_beta1, one_minus_beta2, eps, weight_decay, step_size, inv_sqrt_bc2, grad_scale;
 };
@@ -91,6 +97,12 @@ extern "C" {
 int ctk_mse_loss(const float* out, const float* target, int n, float* loss_out, float* grad_out, void* stream) {
   CTK_REQUIRE(out && target && loss_out && n > 0);
   mse_kernel<<<1, 256, 0, ctk::as_stream(stream)>>>(out, target, n, loss_out, grad_out);
+  return ctk::check_launch();
+}
+
+int ctk_scale_by_scalar(const float* in, const float* scalar, int n, float* out, void* stream) {
+  CTK_REQUIRE(in && scalar && out && n > 0);
+  scale_by_scalar_kernel<<<(n + 255) / 256, 256, 0, ctk::as_stream(stream)>>>(in, scalar, n, out);
   return ctk::check_launch();
 }
 

@@ -10,12 +10,12 @@ from .engine import InferenceEngine
 from .metrics import nmi_per_image, pearson_per_image, ssim_per_image, tile_metrics
 from .models import (AdvancedRegressionModel, SimplifiedFeatureExtractionBranch, SimplifiedRegressionHead,
                      SimplifiedTwoBranchRegressionModel, accelerate, set_precision)
-from .optim import Adam, mse_loss
+from .optim import Adam, MSELoss, mse_loss
 from .schedulers import CosineWarmupLR
 from .pipeline import DevicePrefetcher, HostScorer, prefetch_to_device
-from . import io, parallel
+from . import io, parallel, synthetic
 from .io import prepare_tiles
 
 __all__ = ["CtkError", "EXPORTED_SYMBOLS", "LIB_PATH", "load", "InferenceEngine", "pearson_per_image", "tile_metrics", "nmi_per_image", "ssim_per_image",
            "AdvancedRegressionModel", "SimplifiedFeatureExtractionBranch", "SimplifiedRegressionHead",
-           "SimplifiedTwoBranchRegressionModel", "accelerate", "set_precision", "Adam", "mse_loss", "CosineWarmupLR", "HostScorer", "DevicePrefetcher", "prefetch_to_device", "parallel", "io", "prepare_tiles"]
+           "SimplifiedTwoBranchRegressionModel", "accelerate", "set_precision", "Adam", "MSELoss", "mse_loss", "CosineWarmupLR", "HostScorer", "DevicePrefetcher", "prefetch_to_device", "parallel", "io", "prepare_tiles"]

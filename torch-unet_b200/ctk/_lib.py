@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_longlong, c_size_t, c_void_p
+from ctypes import c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_longlong, c_size_t, c_ulonglong, c_void_p
 
 import torch
 
@@ -61,6 +61,7 @@ _SIGNATURES = {
     "ctk_head_eval": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                               c_void_p, c_void_p, c_void_p, c_float, c_int, c_void_p, c_void_p]),
     "ctk_mse_loss": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "ctk_scale_by_scalar": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "ctk_adam_multi": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float,
                                c_float, c_float, c_float, c_float, c_int, c_float, c_void_p]),
     # ---- training path
@@ -109,6 +110,8 @@ _SIGNATURES = {
     "ctk_colstat": (c_int, [c_void_p, c_int, c_longlong, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "ctk_bn1d_act_drop_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_int, c_int, c_void_p,
                                       c_void_p]),
+    "ctk_dropout_masks": (c_int, [c_void_p, c_longlong, c_float, c_void_p, c_longlong, c_float, c_ulonglong, c_ulonglong,
+                                  c_void_p]),
     "ctk_sgemm_strided": (c_int, [c_void_p, c_longlong, c_longlong, c_void_p, c_longlong, c_longlong, c_void_p, c_int,
                                   c_int, c_int, c_void_p, c_int, c_void_p]),
     "ctk_head_out_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
@@ -168,13 +171,13 @@ def workspace(query: str, *args, device=None):
 KERNELS_PER_CALL = {"ctk_pearson_f32": 2, "ctk_tile_metrics_f32": 4, "ctk_tile_nmi_f32": 4, "ctk_tile_ssim_f32": 3, "ctk_prepare_tiles": 1, "ctk_fold_bn_eval": 1, "ctk_pack_conv_weight_bf16": 1, "ctk_pack_first_weight": 1,
                     "ctk_pack_fc1_weight_bf16": 1, "ctk_conv_first_eval": 1, "ctk_conv_first_pool_codes": 1, "ctk_pack_conv_weight_split_bf16": 1,
                     "ctk_pack_fc1_weight_split_bf16": 1, "ctk_conv_first_eval_split": 1, "ctk_conv3x3_tc_eval_split": 1, "ctk_conv3x3_tc_eval": 1,
-                    "ctk_gemm_bf16_splitk": 1, "ctk_head_eval": 1, "ctk_mse_loss": 1, "ctk_adam_multi": 1,
+                    "ctk_gemm_bf16_splitk": 1, "ctk_head_eval": 1, "ctk_mse_loss": 1, "ctk_scale_by_scalar": 1, "ctk_adam_multi": 1,
                     "ctk_conv_first_raw": 2, "ctk_conv3x3_tc_raw": 1, "ctk_pack_conv_weight_dgrad_bf16": 1,
                     "ctk_bn_finalize": 1, "ctk_bn_finalize_moments": 1, "ctk_first_patch_gram": 2,
                     "ctk_first_moments": 1, "ctk_first_wgrad_codes": 3, "ctk_first_wgrad_finalize": 1, "ctk_bn_act_pool_fwd": 1, "ctk_bn_bwd_reduce": 2, "ctk_bn_bwd_reduce_pooled": 2, "ctk_bn_bwd_reduce_guarded": 3, "ctk_bn_bwd_apply": 1,
                     "ctk_conv3x3_wgrad_tc": 2, "ctk_conv_first_wgrad": 2, "ctk_feat_transpose_bf16": 1,
                     "ctk_pack_fc1_weight_t_bf16": 1, "ctk_gemm_bf16_out_bf16": 1, "ctk_gemm_bf16_bt_out_bf16": 1, "ctk_colstat": 1,
-                    "ctk_bn1d_act_drop_fwd": 1, "ctk_sgemm_strided": 1, "ctk_head_out_fwd": 1, "ctk_head_out_bwd": 1,
+                    "ctk_bn1d_act_drop_fwd": 1, "ctk_dropout_masks": 1, "ctk_sgemm_strided": 1, "ctk_head_out_fwd": 1, "ctk_head_out_bwd": 1,
                     "ctk_bn1d_bwd_reduce": 1, "ctk_bn1d_bwd_apply": 1}
 launch_count = 0
 _timeline = None      # when a list: (name, start_event, end_event, meta) per call, for per-kernel timing in bench.py

@@ -23,6 +23,33 @@ def mse_loss(outputs: torch.Tensor, targets: torch.Tensor, want_grad: bool = Fal
     return (loss, grad) if want_grad else loss
 
 
+class _MseFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, outputs, targets):
+        loss, grad = mse_loss(outputs.contiguous(), targets.contiguous(), want_grad=True)
+        ctx.save_for_backward(grad)
+        ctx.shape = outputs.shape
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, dloss):
+        (grad,) = ctx.saved_tensors
+        dloss = dloss.reshape(1).contiguous().float()
+        _lib.require_device(dloss, torch.float32, "loss gradient")
+        out = torch.empty_like(grad)
+        call("ctk_scale_by_scalar", ptr(grad), ptr(dloss), c_int(grad.numel()), ptr(out), stream())
+        return out.view(ctx.shape), None
+
+
+class MSELoss(torch.nn.Module):
+    """``torch.nn.MSELoss()`` (reduction='mean', train_model.py:636) as ONE libctk launch: the loss value and
+    dL/d outputs come out of the same kernel, the backward just hands the stored gradient on (scaled by the incoming
+    gradient, which ``loss.backward()`` seeds with 1)."""
+
+    def forward(self, outputs: torch.Tensor, targets: torch.Tensor) -> torch.Tensor:
+        return _MseFunction.apply(outputs, targets)
+
+
 class Adam(torch.optim.Optimizer):
     """Drop-in for ``optim.Adam(params, lr, weight_decay=1e-4)`` (train_model.py:637): coupled L2, betas
     (0.9, 0.999), eps 1e-8 -- one multi-tensor kernel launch per step over every parameter of the group.

@@ -9,7 +9,7 @@ runs unchanged; PyTorch only owns the tensors and the graph edge.
 from __future__ import annotations
 
 import contextlib
-from ctypes import c_double, c_float, c_int, c_longlong, c_size_t
+from ctypes import c_double, c_float, c_int, c_longlong, c_size_t, c_ulonglong
 from typing import Callable, Dict, List, Optional, Tuple
 
 import torch
@@ -66,6 +66,9 @@ class TrainEngine:
         # further side stream, so that the HBM-bound BatchNorm passes of one branch / layer overlap the tensor-bound conv
         # kernels of the other.  Off by default; see DESIGN.md section 8.
         self.overlap_streams: bool = False
+        self._zero_grads: Dict[torch.nn.Parameter, torch.Tensor] = {}
+        self.dropout_seed: int = torch.initial_seed() & 0xFFFFFFFFFFFFFFFF
+        self._dropout_calls: int = 0
         self._streams: Dict[Tuple[str, int, int], torch.cuda.Stream] = {}
 
     # ------------------------------------------------------------------ helpers
@@ -87,6 +90,20 @@ class TrainEngine:
     @staticmethod
     def _new(shape, dtype, dev):
         return torch.empty(shape, device=dev, dtype=dtype)
+
+    @staticmethod
+    def _padded(shape, used, padded, dev, dtype=torch.bfloat16):
+        """A GEMM operand whose leading / trailing extent is padded from ``used`` to ``padded``: zero-filled only when
+        there is padding to zero (the kernels overwrite the used part)."""
+        return torch.empty(shape, device=dev, dtype=dtype) if used == padded else torch.zeros(shape, device=dev, dtype=dtype)
+
+    def _zero_grad_of(self, p: torch.nn.Parameter) -> torch.Tensor:
+        """The (identically zero) gradient of a conv bias that feeds a train-mode BatchNorm: one cached tensor per bias
+        instead of a fill kernel per layer and step."""
+        z = self._zero_grads.get(p)
+        if z is None or z.device != p.device:
+            z = self._zero_grads[p] = torch.zeros_like(p)
+        return z
 
     def _bn_finalize(self, sums, count, bias, bn, dev, moments=False):
         c = bn.num_features
@@ -205,7 +222,7 @@ class TrainEngine:
         if self.stat_check_equal_batch is not None:
             self.stat_check_equal_batch(n, dev)
         sv = {"x": x, "n": n, "H": H, "W": W, "m_pad": m_pad, "blocks": []}
-        feat = torch.zeros((m_pad, hf, wf, self.feat_channels), device=dev, dtype=torch.bfloat16)
+        feat = self._padded((m_pad, hf, wf, self.feat_channels), n, m_pad, dev)
         c_off = 0
         main = torch.cuda.current_stream(dev)
         overlap = self.overlap_streams and len(self.branches) > 1
@@ -280,10 +297,18 @@ class TrainEngine:
                         raise _lib.CtkError("dropout mask has the wrong shape")
                 ms.append(m)
             return tuple(ms)
-        out = []
-        for p, f in zip(self.drop_p, (f1, f2)):
-            out.append(None if p == 0.0 else (torch.rand(n, f, device=dev) >= p).float())
-        return tuple(out)
+        # keep-masks drawn by libctk's Philox kernel (one launch for both layers): seeded from torch's seed at engine
+        # creation, one counter offset per forward pass -- reproducible under torch.manual_seed, no ATen kernel in the step
+        p1, p2 = self.drop_p
+        if p1 == 0.0 and p2 == 0.0:
+            return (None, None)
+        m1 = self._new((n, f1), torch.float32, dev) if p1 > 0.0 else None
+        m2 = self._new((n, f2), torch.float32, dev) if p2 > 0.0 else None
+        call("ctk_dropout_masks", ptr(m1), c_longlong(n * f1 if m1 is not None else 0), c_float(p1), ptr(m2),
+             c_longlong(n * f2 if m2 is not None else 0), c_float(p2), c_ulonglong(self.dropout_seed),
+             c_ulonglong(self._dropout_calls), stream())
+        self._dropout_calls += 1
+        return (m1, m2)
 
     def _backward_branch(self, entry: dict, sv: dict, dfeat: torch.Tensor, done, wgrad_stream=None) -> None:
         """Backward of one branch's conv stack (last block first) on the CURRENT stream."""
@@ -321,7 +346,7 @@ class TrainEngine:
                 done(bn.bias, sums[:cout])
                 done(bn.weight, sums[cout:])
                 done(conv.weight, dw)
-                done(conv.bias, torch.zeros_like(conv.bias))
+                done(conv.bias, self._zero_grad_of(conv.bias))
                 continue
             pooled, p_cstride, p_coff = b["pooled"]
             # sums from the pooled tensors; channel groups whose BatchNorm parameters make that reconstruction lossy
@@ -360,7 +385,7 @@ class TrainEngine:
                          ptr(dw), ws[1], ws[2], stream(), meta={"flops": 2.0 * n * h * w * cout * 9 * cin})
                 done(conv.weight, dw)
             # the conv bias feeds a train-mode BatchNorm, so its gradient is sum(dY) = 0 identically
-            done(conv.bias, torch.zeros_like(conv.bias))
+            done(conv.bias, self._zero_grad_of(conv.bias))
             if li > 0:
                 wg = self._new((9, cin, cout), torch.bfloat16, dev)
                 call("ctk_pack_conv_weight_dgrad_bf16", ptr(conv.weight), c_int(cout), c_int(cin), ptr(wg), stream())
@@ -441,8 +466,8 @@ class TrainEngine:
         done(self.bns[0].bias, sums1[:f1])
         done(self.bns[0].weight, sums1[f1:])
         dz1 = self._new((n, f1), torch.float32, dev)
-        dz1_bf = torch.zeros((m_pad, f1), device=dev, dtype=torch.bfloat16)
-        dz1t_bf = torch.zeros((f1, k_pad), device=dev, dtype=torch.bfloat16)
+        dz1_bf = self._padded((m_pad, f1), n, m_pad, dev)
+        dz1t_bf = self._padded((f1, k_pad), n, k_pad, dev)
         call("ctk_bn1d_bwd_apply", ptr(dact1), ptr(sv["z1"]), ptr(sc1), ptr(mu1), ptr(is1), ptr(self._global_sums(sums1)),
              c_int(n), c_int(f1), ptr(dz1), ptr(dz1_bf), ptr(dz1t_bf), c_int(k_pad), stream())
         done(fc1.bias, self._colsum(dz1, n, f1))
