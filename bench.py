@@ -293,11 +293,14 @@ def _timeline_table(timeline, denom):
     return per
 
 
-def build_model(kind, dev):
+def build_model(kind, dev, randomized_bn=False):
     import ctk
+    from ctk import synthetic
     torch.manual_seed(0)
     model = (ctk.SimplifiedTwoBranchRegressionModel(initial_filters_per_branch=64) if kind == "double"
              else ctk.AdvancedRegressionModel(initial_filters=128, num_conv_blocks=6))
+    if randomized_bn:
+        model.load_state_dict(synthetic.randomize_bn(model.state_dict(), seed=7))
     return model.to(dev)
 
 
@@ -502,9 +505,7 @@ def measure_infer(args, steps, warmup):
     from ctk import _lib, synthetic
     world, rank, local = env()
     dev = torch.device("cuda", local)
-    model = build_model("double", dev)
-    model.load_state_dict(synthetic.randomize_bn(model.state_dict(), seed=7))
-    model = model.to(dev).eval()
+    model = build_model("double", dev, randomized_bn=True).eval()
     if args.precision != "bf16":
         ctk.set_precision(model, args.precision)
     base, _ = synthetic.synthetic_batch(32, seed=1234 + rank)
@@ -613,10 +614,8 @@ def measure_sweep(args):
     from ctk import _lib, synthetic
     world, rank, local = env()
     dev = torch.device("cuda", local)
-    model = build_model("double", dev)
-    sd = synthetic.randomize_bn(model.state_dict(), seed=7)
-    model.load_state_dict(sd)
-    model = model.to(dev).eval()
+    model = build_model("double", dev, randomized_bn=True).eval()
+    sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
     ctk.set_precision(model, args.precision)
     engine = ctk.models.get_engine(model)
     begin, end = ctk.parallel.shard_range(args.tiles, rank, world)
@@ -658,7 +657,7 @@ def measure_sweep(args):
         idx = torch.arange(0, min(n_local, 4 * BATCH), max(1, min(n_local, 4 * BATCH) // 64))[:64]
         xs = torch.stack([ring[(int(j) // BATCH) % 4][int(j) % BATCH] for j in idx]).cpu()
         with torch.no_grad():
-            ref = orc.double_forward({k: v.cpu() for k, v in sd.items()}, xs).flatten()
+            ref = orc.double_forward(sd, xs).flatten()
         got = scores[idx.to(dev)].flatten().cpu()
         r_ref = torch.from_numpy(orc.pearson_batch(xs))
         r_got = pear[idx.to(dev)].cpu()

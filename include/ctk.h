@@ -42,6 +42,12 @@ const char* ctk_status_string(int status);
 int ctk_last_cuda_error(void);
 /* 0 if the current device is an sm_100 part the kernels can run on, else CTK_ERR_NO_DEVICE. */
 int ctk_device_check(void);
+/* Leave `sms` (0..64) streaming multiprocessors free when sizing the grids of the persistent one-CTA-per-SM tensor-core
+ * kernels (ctk_conv3x3_tc_*, ctk_conv3x3_wgrad_tc) launched AFTER this call.  Data-parallel training sets it around the
+ * backward pass: the NCCL all-reduce of the gradients (there is none in the single-process reference) then
+ * finds free SMs at once instead of displacing CTAs of a full grid into a second wave.  Process-wide setting, 0 by default;
+ * results stay deterministic for a fixed value (the partition of every reduction depends on the grid). */
+int ctk_set_persistent_sm_reserve(int sms);
 
 /* ------------------------------------------------------------------------------------------
  * Pearson r of channel 0 vs channel 1 of each [2,H,W] float32 tile.

@@ -47,7 +47,7 @@ def test_status_strings_and_no_compute_paths(lib):
     # argument validation happens before any CUDA call: null pointers are refused without a device
     assert lib.ctk_pearson_f32(None, 4, 65536, None, None, 0, None) == -1
     assert lib.ctk_conv3x3_tc_eval(None, 1, 16, 16, 64, None, 128, None, None, 0.01, None, 128, 0, 0, None) == -1
-    assert lib.ctk_tile_ssim_workspace_bytes(0) == 0 and lib.ctk_tile_ssim_workspace_bytes(256) == 256 * 12 + 8
+    assert lib.ctk_tile_ssim_workspace_bytes(0) == 0 and lib.ctk_tile_ssim_workspace_bytes(256) == 256 * (8 * 8 + 4) + 8
     assert lib.ctk_tile_ssim_f32(None, 4, 256, 256, None, None, 0, None) == -1           # null pointers
     assert lib.ctk_tile_ssim_f32(None, 0, 256, 256, None, None, 0, None) == 0            # empty batch: nothing to do
     assert lib.ctk_gemm_bf16_splitk(None, None, 128, 128, 64, 1, None, None) == -1

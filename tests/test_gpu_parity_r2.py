@@ -174,22 +174,48 @@ def test_philox_dropout_masks_and_mse_module():
     assert torch.allclose(g, o.grad, rtol=1e-6, atol=1e-8)
 
 
+# ------------------------------------------------------------------------------------------------ CPU-warmed weights
+@pytest.fixture(scope="module")
+def warmed():
+    """SURVEY 8c fallback weight set (ii): seed-0 init + 20 oracle Adam steps (lr 5e-4, wd 1e-4) at batch 16 on a 64-tile
+    pool -- BatchNorm running statistics and the head have moved off their initial values and eval outputs have real
+    spread.  Built once per test session on the host (about a minute per model on 16 cores)."""
+    cache = {}
+
+    def get(kind):
+        if kind not in cache:
+            torch.set_num_threads(os.cpu_count() or 1)
+            x, y = orc.synthetic_batch(64, seed=4321)
+            tr = orc.OracleTrainer(kind, orc.INIT[kind](0), lr=5e-4, weight_decay=1e-4)
+            for t in range(20):
+                s = (t * 16) % 64
+                tr.step(x[s:s + 16], y[s:s + 16], dropout_masks=orc.dropout_masks(16, P_DROP[kind], 1000 + t))
+            cache[kind] = {k: v.detach().clone() for k, v in tr.sd.items()}
+        return cache[kind]
+    return get
+
+
 # ------------------------------------------------------------------------------------------------ gradients at batch 64
-# measured on B200 (round 2): whole-gradient relative L2 distance to the fp32 oracle, bf16 operand storage
-WHOLE_GRAD_BOUND = {"single": 6e-2, "double": 3e-2}
-TENSOR_GRAD_BOUND = {"single": 1.5e-1, "double": 8e-2}
+# Whole-gradient relative L2 distance to the fp32 oracle with bf16 operand storage.  Conditioning of this problem, measured
+# on the CPU in pure fp32 (double-branch): a 1e-6 relative perturbation of the INPUT moves the whole gradient by 6e-4 on the
+# warmed weights and 9e-4 at seed-0 init (x600-900 through train-mode BatchNorm); the oracle with bf16-rounded operands is
+# 3.4e-2 from fp32 on the warmed weights and 1.7e-1 at init.  The bounds are ~1.7x the bf16 rounding model on the warmed set.
+WHOLE_GRAD_BOUND = {"single": 1.2e-1, "double": 6e-2}
+TENSOR_GRAD_BOUND = {"single": 4e-1, "double": 2e-1}
 
 
 @pytest.mark.parametrize("kind", ["double", "single"])
-def test_gradients_at_batch_64_against_fp32_oracle(kind):
-    """One training step on 64 tiles of a 256-tile pool: loss within 1 %, whole-gradient and per-tensor relative L2 against
-    the fp32 oracle asserted directly, BatchNorm running statistics within 2e-3."""
+def test_gradients_at_batch_64_against_fp32_oracle(warmed, kind):
+    """One training step from the CPU-warmed weights on 64 tiles of a 256-tile pool: loss within 1 %, whole-gradient and
+    per-tensor relative L2 against the fp32 oracle asserted directly (no bf16-emulation yardstick), BatchNorm running
+    statistics within 2e-3."""
     import ctk
     pool_x, pool_y = orc.synthetic_batch(256, seed=4321)
     idx = torch.arange(0, 256, 4)
     x, y = pool_x[idx].contiguous(), pool_y[idx].contiguous()
     n = x.shape[0]
     model = _build(kind)
+    model.load_state_dict(warmed(kind))
     sd = {k: v.clone() for k, v in model.state_dict().items()}
     masks = orc.dropout_masks(n, P_DROP[kind], seed=5)
     torch.set_num_threads(os.cpu_count() or 1)
@@ -208,8 +234,10 @@ def test_gradients_at_batch_64_against_fp32_oracle(kind):
     worst, worst_name = 0.0, ""
     for name, p in model.named_parameters():
         g, r = p.grad.detach().cpu(), grads_ref[name]
-        if name.endswith("bias") and r.norm().item() < 1e-6 * (1 + p.detach().norm().item()):
-            assert g.abs().max().item() <= 1e-5, name         # bias in front of a train-mode BatchNorm: exactly zero
+        if name.endswith("bias") and p.dim() == 1 and (".conv_blocks." in name or name.startswith("conv_layers.")) and \
+                int(name.split(".")[-2]) % 4 == 0:
+            # conv bias in front of a train-mode BatchNorm: the exact gradient is 0 (autograd leaves fp32 cancellation noise)
+            assert g.abs().max().item() == 0.0 and r.norm().item() <= 1e-3 * grads_ref[name[:-4] + "weight"].norm().item(), name
             continue
         if name.endswith("fc_layers.9.bias"):
             scale = (2.0 * (out_ref - y).abs() / n).sum().item()      # a sum that cancels: bound by the size of its terms
@@ -231,27 +259,6 @@ def test_gradients_at_batch_64_against_fp32_oracle(kind):
             np.testing.assert_allclose(msd[k].cpu().numpy(), v.numpy(), rtol=2e-3, atol=2e-4, err_msg=k)
         if k.endswith("num_batches_tracked"):
             assert int(msd[k]) == int(v), k
-
-
-# ------------------------------------------------------------------------------------------------ CPU-warmed weights
-@pytest.fixture(scope="module")
-def warmed():
-    """SURVEY 8c fallback weight set (ii): seed-0 init + 20 oracle Adam steps (lr 5e-4, wd 1e-4) at batch 16 on a 64-tile
-    pool -- BatchNorm running statistics and the head have moved off their initial values and eval outputs have real
-    spread.  Built once per test session on the host (about a minute per model on 16 cores)."""
-    cache = {}
-
-    def get(kind):
-        if kind not in cache:
-            torch.set_num_threads(os.cpu_count() or 1)
-            x, y = orc.synthetic_batch(64, seed=4321)
-            tr = orc.OracleTrainer(kind, orc.INIT[kind](0), lr=5e-4, weight_decay=1e-4)
-            for t in range(20):
-                s = (t * 16) % 64
-                tr.step(x[s:s + 16], y[s:s + 16], dropout_masks=orc.dropout_masks(16, P_DROP[kind], 1000 + t))
-            cache[kind] = {k: v.detach().clone() for k, v in tr.sd.items()}
-        return cache[kind]
-    return get
 
 
 @pytest.mark.parametrize("kind", ["single", "double"])

@@ -314,6 +314,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                   const __grid_constant__ CUtensorMap tm_out, const ConvParams p) {
   using C = Cfg<kCtaGroup, kBlockN, kEpi>;
   using SL = SmemLayout<kCtaGroup, kBlockN, kEpi>;
+  constexpr bool kChunkAcc = kEpi == kEpiEvalPoolSplit;     // fresh accumulator per K chunk, summed in registers
+  static_assert(!kChunkAcc || kBlockN <= 128, "chunked accumulation keeps kBlockN / 2 running sums per epilogue thread");
   static_assert(sizeof(SL) <= kCtrlBytes, "barrier block too large");
   static_assert(C::kBStages >= 4, "too few weight stages");
   extern __shared__ uint8_t smem_raw[];
@@ -428,14 +430,22 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     };
     int as = 0, aphase = 0, bs = 0, bphase = 0;
     int it = 0;
+    int ia = 0;                              // accumulator stages handed to the epilogue so far
     const bool resident = p.b_resident != 0;
     for (int work = work0; work < p.total_work; work += work_stride, ++it) {
-      const int acc = it & 1;
-      const int acc_phase = (it >> 1) & 1;
-      mbar_wait(&sl->acc_empty[acc], acc_phase ^ 1);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * kBlockN);
+      int acc = 0;
+      uint32_t d_tmem = 0;
       for (int c = 0; c < chunks; ++c) {
+        if (kChunkAcc || c == 0) {
+          // kChunkAcc: every 64-channel chunk (36 MMAs) gets a fresh accumulator stage; the epilogue adds the stages up
+          // in fp32 registers.  tcgen05 accumulates with truncation (about -2^-24 relative per MMA step, measured:
+          // tools/probe_accum_bias.py), which over the 200-900 steps of a whole fp32-class tile is 1e-5..5e-5.
+          acc = ia & 1;
+          mbar_wait(&sl->acc_empty[acc], ((ia >> 1) & 1) ^ 1);
+          tc_fence_after();
+          d_tmem = tmem_base + static_cast<uint32_t>(acc * kBlockN);
+          ++ia;
+        }
         mbar_wait(&sl->a_full[as], aphase);
         tc_fence_after();
         // The 128B swizzle is a function of the absolute shared-memory address bits (verified on B200: base-offset
@@ -443,7 +453,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         // TMA-written halo is a valid K-major operand as is.  Stage bases are 1024-byte aligned and every offset below
         // stays inside the stage, so adding (offset >> 4) never carries out of the descriptor's address field.
         const uint64_t adesc_c = adesc0 | static_cast<uint64_t>(smem_u32(a_smem + as * kAStageBytes) >> 4);
-        const bool last_chunk = c == chunks - 1;
+        const bool last_chunk = kChunkAcc || c == chunks - 1;
+        const bool first_chunk = kChunkAcc || c == 0;
         if (resident && it > 0) {
           // weights of every (chunk, tap) are in place since the first tile: one straight-line burst per chunk
           const uint64_t bdesc_c = bdesc0 | static_cast<uint64_t>((b_smem_addr + c * 9 * C::kBStageBytes) >> 4);
@@ -452,7 +463,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
             for (int tap = 0; tap < 9; ++tap) {
 #pragma unroll
               for (int s = 0; s < kKC / 16; ++s) {
-                const uint32_t accum = (tap | s) != 0 ? 1u : (c != 0 ? 1u : 0u);
+                const uint32_t accum = (tap | s) != 0 ? 1u : (first_chunk ? 0u : 1u);
                 mma(d_tmem, adesc_c + (((tap / 3) * kHaloW + tap % 3) * 128 + s * 32) / 16,
                     bdesc_c + (tap * C::kBStageBytes + s * 32) / 16, accum);
               }
@@ -481,7 +492,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                 const uint64_t bdesc = bdesc0 | static_cast<uint64_t>((b_smem_addr + st[kx] * C::kBStageBytes) >> 4);
 #pragma unroll
                 for (int s = 0; s < kKC / 16; ++s) {
-                  const uint32_t accum = (ky | kx | s) != 0 ? 1u : (c != 0 ? 1u : 0u);
+                  const uint32_t accum = (ky | kx | s) != 0 ? 1u : (first_chunk ? 0u : 1u);
                   mma(d_tmem, adesc + 2 * s, bdesc + 2 * s, accum);      // +32 bytes per UMMA_K step
                 }
                 if (!resident) commit(&sl->b_empty[st[kx]]);
@@ -525,7 +536,50 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     auto block_of = [&](int i) { return kBlocks == 2 ? half : (i >> 1) * 4 + half * 2 + (i & 1); };
     e.slope2 = __float2bfloat162_rn(p.slope);
     int it = 0;
-    for (int work = work0; work < p.total_work; work += work_stride, ++it) {
+    if constexpr (kChunkAcc) {
+      // fp32-class path: one accumulator stage per K chunk, added up here in fp32 (round to nearest) registers
+      int ia = 0;
+      for (int work = work0; work < p.total_work; work += work_stride) {
+        const TileCoord t = decode_work<kCtaGroup, kBlockN>(p, work, rank);
+        e.y = t.y0 + r;
+        e.x = t.x0 + cpx;
+        e.valid = t.img < p.n_img && e.y < p.H && e.x < p.W;
+        float sums[kPerWarp][32];
+#pragma unroll
+        for (int i = 0; i < kPerWarp; ++i)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sums[i][j] = 0.f;
+        for (int c = 0; c < chunks; ++c, ++ia) {
+          const int acc = ia & 1;
+          mbar_wait(&sl->acc_full[acc], (ia >> 1) & 1);
+          tc_fence_after();
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(acc * kBlockN);
+#pragma unroll
+          for (int i = 0; i < kPerWarp; ++i) {
+            uint32_t v[32];
+            tmem_ld_32x32(taddr + block_of(i) * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sums[i][j] += __uint_as_float(v[j]);
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if constexpr (kCtaGroup == 1) mbar_arrive(&sl->acc_empty[acc]);
+            else mbar_arrive_cluster(mapa_shared(smem_u32(&sl->acc_empty[acc]), 0));
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < kPerWarp; ++i) {
+          uint32_t v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(sums[i][j]);
+          float unused_s = 0.f, unused_q = 0.f;
+          epilogue_block<kEpi>(p, e, t, block_of(i) * 32, v, unused_s, unused_q);
+        }
+      }
+    }
+    for (int work = work0; !kChunkAcc && work < p.total_work; work += work_stride, ++it) {
       const TileCoord t = decode_work<kCtaGroup, kBlockN>(p, work, rank);
       const int acc = it & 1;
       const int acc_phase = (it >> 1) & 1;
@@ -659,7 +713,7 @@ int launch_conv(const void* x_bf16, const void* w_packed_bf16, ConvParams p, cud
   }
   auto kernel = conv3x3_tc_kernel<kCtaGroup, kBlockN, kEpi>;
   CTK_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
-  int clusters = std::min(p.total_work, ctk::num_sms() / kCtaGroup);
+  int clusters = std::min(p.total_work, ctk::persistent_sms() / kCtaGroup);
   // statistics: every CTA must keep one N tile (register-resident totals), i.e. the work stride is a multiple of tiles_n
   if (kEpi == kEpiRawStats && clusters > p.tiles_n) clusters -= clusters % p.tiles_n;
   cudaLaunchConfig_t cfg = {};
@@ -725,7 +779,6 @@ static int conv_dispatch(const void* x_bf16, int n, int H, int W, int cin, const
     CTK_REQUIRE(cin % 3 == 0 && (cin / 3) % kKC == 0 && scale != nullptr && p.pool && p.act);
     p.cin_phys = cin / 3 * 2;
     p.a_wrap = p.cin_phys / kKC;
-    if (cout % 256 == 0) return launch_conv<2, 256, kEpiEvalPoolSplit>(x_bf16, w_packed_bf16, p, s);
     if (cout % 128 == 0) return launch_conv<2, 128, kEpiEvalPoolSplit>(x_bf16, w_packed_bf16, p, s);
     return CTK_ERR_UNSUPPORTED;
   }

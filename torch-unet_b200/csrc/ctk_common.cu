@@ -2,6 +2,7 @@
 #include "ctk_common.h"
 
 #include <cudaTypedefs.h>
+#include <atomic>
 #include <mutex>
 
 namespace ctk {
@@ -69,9 +70,21 @@ int num_sms() {
   return cached[dev];
 }
 
+static std::atomic<int> g_sm_reserve{0};
+int persistent_sms() {
+  const int n = num_sms() - g_sm_reserve.load(std::memory_order_relaxed);
+  return n < 8 ? 8 : n;
+}
+
 }  // namespace ctk
 
 extern "C" {
+
+int ctk_set_persistent_sm_reserve(int sms) {
+  if (sms < 0 || sms > 64) return CTK_ERR_BAD_ARG;
+  ctk::g_sm_reserve.store(sms, std::memory_order_relaxed);
+  return CTK_OK;
+}
 
 int ctk_abi_version(void) { return 2; }
 

@@ -45,6 +45,9 @@ int encode_tmap_f32_sw128(CUtensorMap* map, const void* base, int rank, const ui
                           const uint64_t* strides_bytes, const uint32_t* box);
 
 int num_sms();
+// SMs the one-CTA-per-SM persistent tensor-core kernels may fill: num_sms() minus the reserve set through
+// ctk_set_persistent_sm_reserve (SMs left free for a concurrently running collective kernel)
+int persistent_sms();
 
 // Second stage of the cross-CTA reductions (reduce.cu): out[c] = sum_{r < rows} part[r * stride + c], rows added in a
 // fixed order with fp64 accumulation, so the result is independent of CTA scheduling.

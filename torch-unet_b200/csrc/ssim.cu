@@ -21,7 +21,8 @@ namespace {
 constexpr int kWin = 7, kPad = 3;
 constexpr int kRows = 4;              // rows of row-pass results staged per exchange
 constexpr int kThreads = 256;
-constexpr int kStrip = 32;            // output rows per CTA
+constexpr int kStrip = 32;            // output rows per strip
+constexpr int kSlices = 8;            // CTAs (and partial sums) per tile: slice s takes strips s, s + 8, ...
 
 struct MinMax { float lo, hi; };
 
@@ -48,7 +49,6 @@ ssim_range_kernel(const float* __restrict__ tiles, int plane_elems, float* __res
   if (threadIdx.x == 0) {
     for (int w = 1; w < kThreads / 32; ++w) { lo = fminf(lo, s_lo[w]); hi = fmaxf(hi, s_hi[w]); }
     range[blockIdx.x] = __fsub_rn(hi, lo);
-    acc[blockIdx.x] = 0.0;
   }
 }
 
@@ -62,14 +62,16 @@ ssim_strip_kernel(const float* __restrict__ tiles, int H, int W, const float* __
   const int tile = blockIdx.y;
   const float* x = tiles + static_cast<size_t>(tile) * 2 * H * W;
   const float* y = x + static_cast<size_t>(H) * W;
-  const int r_begin = kPad + blockIdx.x * kStrip;
-  const int r_end = min(r_begin + kStrip, H - kPad);
   const float R = range[tile];
   const float t1 = __fmul_rn(0.01f, R), t2 = __fmul_rn(0.03f, R);
   const float c1 = __fmul_rn(t1, t1), c2 = __fmul_rn(t2, t2);              // (K * data_range) ** 2 in float32
   const float cov_norm = static_cast<float>(49.0 / 48.0);                  // NP / (NP - 1), cast to the arrays' float32
   double total = 0.0;
 
+  // a tile is covered by kSlices CTAs; CTA s takes the row strips s, s + kSlices, ... and leaves ONE partial sum, added up
+  // in slice order by the finalize kernel (no floating-point atomics: the result is reproducible bit for bit)
+  for (int r_begin = kPad + blockIdx.x * kStrip; r_begin < H - kPad; r_begin += kSlices * kStrip) {
+  const int r_end = min(r_begin + kStrip, H - kPad);
   for (int r0 = r_begin; r0 < r_end; r0 += kRows) {
     const int rows = min(kRows, r_end - r0);
     // ---- pass 1 (down the rows, scipy's axis 0): thread <-> column
@@ -122,6 +124,7 @@ ssim_strip_kernel(const float* __restrict__ tiles, int H, int W, const float* __
     }
     __syncthreads();
   }
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
   if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = total;
@@ -129,13 +132,17 @@ ssim_strip_kernel(const float* __restrict__ tiles, int H, int W, const float* __
   if (threadIdx.x == 0) {
     double t = 0.0;
     for (int w = 0; w < kThreads / 32; ++w) t += s_part[w];
-    atomicAdd(acc + tile, t);
+    acc[static_cast<size_t>(tile) * kSlices + blockIdx.x] = t;
   }
 }
 
 __global__ void ssim_finalize_kernel(const double* __restrict__ acc, int n, double count, double* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = acc[i] / count;
+  if (i >= n) return;
+  double t = 0.0;
+#pragma unroll
+  for (int s = 0; s < kSlices; ++s) t += acc[static_cast<size_t>(i) * kSlices + s];
+  out[i] = t / count;
 }
 
 }  // namespace
@@ -144,7 +151,7 @@ extern "C" {
 
 size_t ctk_tile_ssim_workspace_bytes(int n_tiles) {
   if (n_tiles <= 0) return 0;
-  return static_cast<size_t>(n_tiles) * (sizeof(double) + sizeof(float)) + 8;
+  return static_cast<size_t>(n_tiles) * (kSlices * sizeof(double) + sizeof(float)) + 8;
 }
 
 int ctk_tile_ssim_f32(const float* tiles, int n_tiles, int H, int W, double* ssim_out, void* workspace,
@@ -158,12 +165,11 @@ int ctk_tile_ssim_f32(const float* tiles, int n_tiles, int H, int W, double* ssi
   if (workspace_bytes < ctk_tile_ssim_workspace_bytes(n_tiles)) return CTK_ERR_WORKSPACE;
   cudaStream_t s = ctk::as_stream(stream);
   double* acc = static_cast<double*>(workspace);
-  float* range = reinterpret_cast<float*>(acc + n_tiles);
+  float* range = reinterpret_cast<float*>(acc + static_cast<size_t>(n_tiles) * kSlices);
   ssim_range_kernel<<<n_tiles, kThreads, 0, s>>>(tiles, H * W, range, acc);
   int st = ctk::check_launch();
   if (st != CTK_OK) return st;
-  const int strips = (H - 2 * kPad + kStrip - 1) / kStrip;
-  ssim_strip_kernel<<<dim3(strips, n_tiles), kThreads, smem, s>>>(tiles, H, W, range, acc);
+  ssim_strip_kernel<<<dim3(kSlices, n_tiles), kThreads, smem, s>>>(tiles, H, W, range, acc);
   st = ctk::check_launch();
   if (st != CTK_OK) return st;
   const double count = static_cast<double>(H - 2 * kPad) * (W - 2 * kPad);

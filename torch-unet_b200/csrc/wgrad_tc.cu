@@ -325,7 +325,7 @@ int ctk_conv3x3_wgrad_tc(const void* dy_bf16, const void* x_bf16, int n, int H, 
   const int pairs = p.co_blocks * p.ci_blocks;
   // kx group 0 does two kernel columns per patch, group 1 one: twice as many slices for group 0 balances the CTAs.
   // One wave (grid <= SMs): all CTAs of a triplet run together, which is what makes their shared tiles L2 hits.
-  const int s_unit = std::max(1, std::min(p.total_tiles / 2, ctk::num_sms() / (3 * pairs)));
+  const int s_unit = std::max(1, std::min(p.total_tiles / 2, ctk::persistent_sms() / (3 * pairs)));
   p.slices_a = std::min(p.total_tiles, 2 * s_unit);
   p.slices_b = std::min(p.total_tiles, s_unit);
   p.dw = dw;

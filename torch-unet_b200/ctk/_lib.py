@@ -30,6 +30,7 @@ _SIGNATURES = {
     "ctk_status_string": (c_char_p, [c_int]),
     "ctk_last_cuda_error": (c_int, []),
     "ctk_device_check": (c_int, []),
+    "ctk_set_persistent_sm_reserve": (c_int, [c_int]),
     "ctk_pearson_workspace_bytes": (c_size_t, [c_int]),
     "ctk_pearson_f32": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "ctk_prepare_tiles": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),

@@ -13,13 +13,20 @@ from __future__ import annotations
 
 from typing import Dict, List, Optional, Tuple
 
+import os
+
 import torch
 import torch.distributed as dist
 
 from ._lib import CtkError
 
 BIG_TENSOR_BYTES = 8 << 20
-BUCKET_BYTES = 25 << 20
+BUCKET_BYTES = 4 << 20            # small gradients: 12.7 MB per step in all, flushed as they accumulate, not at the end
+# SMs the backward pass's persistent tensor-core kernels leave free while the exchange runs (TrainEngine.backward_sm_reserve
+# -> ctk_set_persistent_sm_reserve).  Measured on 8 x B200 (tools/r2_dp_experiment.sh, gpurun_out/r2_dp_8.txt): reserve
+# 0 / 16 / 32 SMs -> 16.36 / 16.41 / 16.85 ms per step, and 15.90 / 16.25 / 16.39 ms at 2 GPUs: NCCL's kernel finds its
+# SMs at kernel boundaries without help, and the reserve only slows the convolutions.  Hence off by default.
+BACKWARD_SM_RESERVE = int(os.environ.get("CTK_DP_SM_RESERVE", "0"))
 
 
 class GradSynchronizer:
@@ -96,6 +103,8 @@ def attach(model: torch.nn.Module, process_group=None, sync_bn: bool = False, **
     eng = get_train_engine(model)
     eng.on_grad_ready = sync.on_grad_ready
     eng.finalize_grads = sync.finalize
+    if sync.world > 1 and sync.use_avg:
+        eng.backward_sm_reserve = max(0, min(64, BACKWARD_SM_RESERVE))
     if sync_bn and sync.world > 1:
         pg = process_group
         eng.stat_allreduce = lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM, group=pg)

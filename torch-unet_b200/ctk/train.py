@@ -66,6 +66,9 @@ class TrainEngine:
         # further side stream, so that the HBM-bound BatchNorm passes of one branch / layer overlap the tensor-bound conv
         # kernels of the other.  Off by default; see DESIGN.md section 8.
         self.overlap_streams: bool = False
+        # data parallel: SMs the persistent tensor-core kernels of the BACKWARD pass leave free for the gradient all-reduce
+        # that runs beside them (parallel.attach sets it; 0 = fill the GPU, the single-GPU setting)
+        self.backward_sm_reserve: int = 0
         self._zero_grads: Dict[torch.nn.Parameter, torch.Tensor] = {}
         self.dropout_seed: int = torch.initial_seed() & 0xFFFFFFFFFFFFFFFF
         self._dropout_calls: int = 0
@@ -404,6 +407,15 @@ class TrainEngine:
         sv["consumed"] = True
         dout = dout.contiguous().float()
         _lib.require_device(dout, torch.float32, "output gradient")
+        if self.backward_sm_reserve > 0:
+            call("ctk_set_persistent_sm_reserve", c_int(self.backward_sm_reserve))
+        try:
+            return self._backward(sv, dout)
+        finally:
+            if self.backward_sm_reserve > 0:
+                call("ctk_set_persistent_sm_reserve", c_int(0))
+
+    def _backward(self, sv: dict, dout: torch.Tensor) -> Dict[torch.nn.Parameter, torch.Tensor]:
         grads: Dict[torch.nn.Parameter, torch.Tensor] = {}
 
         n, dev = sv["n"], dout.device
