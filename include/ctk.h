@@ -370,6 +370,53 @@ int ctk_bn1d_bwd_apply(const float* dact, const float* z, const float* scale, co
                        const float* sums, int n_rows, int features, float* dz, void* dz_bf16, void* dzT_bf16, int ldt,
                        void* stream);
 
+/* ==========================================================================================
+ * fp32 training path (ctk.set_precision(model, "fp32")): the reference's own arithmetic -- float32 operands, products
+ * and stored tensors (train_model.py:419-424 runs the nn.Modules in fp32) -- on the CUDA cores, for parity runs.  FFMA
+ * products, fp32 partial sums over 16 terms folded into fp64 running sums, fp64 batch statistics, fixed-order two-stage
+ * cross-CTA reductions (bit-reproducible).  Activations are NHWC float32; `sn, sy, sx, sc` are ELEMENT strides of the
+ * input read as [n][y][x][c], so the reference's NCHW input planes are consumed in place.
+ * ========================================================================================== */
+/* [Cout,Cin,3,3] -> [(tap*cin + ci)][cout] (rotate 0: forward operand) or [((8-tap)*cout + co)][cin] (rotate 1: the
+ * operand that makes ctk_conv3x3_f32 compute the input gradient from dY). */
+int ctk_pack_conv_weight_f32(const float* w, int cout, int cin, int rotate, float* out, void* stream);
+/* y[n,H,W,cout] = conv3x3(x, w) without bias, stride 1, zero padding 1.  cout % 64 == 0, n*H*W % 128 == 0.
+ * Replaces: nn.Conv2d forward / input gradient, regression_model.py:14,23; two_branch_regression.py:10,16,22,28. */
+int ctk_conv3x3_f32(const float* x, long long sn, long long sy, long long sx, long long sc, int n, int H, int W, int cin,
+                    const float* w_packed, int cout, float* y, void* stream);
+/* dw[Cout,Cin,3,3] = sum_pixels dY[p,co] * x[p+tap,ci]; split over pixel slices with fp64 partial sums in the workspace,
+ * added in slice order.  n*H*W % 16 == 0, cout % 64 == 0.  Replaces: aten::convolution_backward (weight gradient). */
+size_t ctk_conv3x3_wgrad_f32_workspace_bytes(int n, int H, int W, int cin, int cout);
+int ctk_conv3x3_wgrad_f32(const float* dy, const float* x, long long sn, long long sy, long long sx, long long sc, int n,
+                          int H, int W, int cin, int cout, float* dw, void* workspace, size_t workspace_bytes,
+                          void* stream);
+/* sums[c] = sum_p y[p,c], sums[C+c] = sum_p y[p,c]^2 in fp64 (workspace: ctk_channel_sums_f64_workspace_bytes(C)), and
+ * the BatchNorm constants from them (ctk_bn_finalize with fp64 sums).  Replaces: aten::native_batch_norm(training). */
+size_t ctk_channel_sums_f64_workspace_bytes(int channels);
+int ctk_channel_stats_f32(const float* y, long long pixels, int channels, double* sums, void* workspace,
+                          size_t workspace_bytes, void* stream);
+int ctk_bn_finalize_f64(const double* sums, double count, const float* bias, const float* gamma, const float* beta,
+                        float* running_mean, float* running_var, long long* num_batches_tracked, float momentum,
+                        float eps, int channels, float* scale, float* shift, float* mean, float* invstd, void* stream);
+/* out[img*out_sn + (py*Wp+px)*out_sp + c*out_sc] = maxpool2x2(leaky((y-mean)*invstd*gamma + beta)): NHWC output with
+ * (Hp*Wp*C, C, 1), or the NCHW-flatten order nn.Flatten hands to FC1 with (features, 1, Hp*Wp) (two_branch_regression.py:96). */
+int ctk_bn_act_pool_fwd_f32(const float* y, int n, int H, int W, int channels, const float* mean, const float* invstd,
+                            const float* gamma, const float* beta, float slope, float* out, long long out_sn,
+                            long long out_sp, long long out_sc, void* stream);
+/* Backward of MaxPool2d + LeakyReLU + BatchNorm2d(train) in fp32: sums (fp64; optional float copy = [d beta | d gamma]),
+ * then the dense dY.  dp is read through the same three strides as the forward output. */
+int ctk_bn_bwd_reduce_f32(const float* y, const float* dp, long long dp_sn, long long dp_sp, long long dp_sc, int n, int H,
+                          int W, int channels, const float* mean, const float* invstd, const float* gamma,
+                          const float* beta, float slope, double* sums, float* sums_f32, void* workspace,
+                          size_t workspace_bytes, void* stream);
+int ctk_bn_bwd_apply_f32(const float* y, const float* dp, long long dp_sn, long long dp_sp, long long dp_sc, int n, int H,
+                         int W, int channels, const float* mean, const float* invstd, const float* gamma,
+                         const float* beta, const double* sums, double count, float slope, float* dy, void* stream);
+/* c[i*ldc + j] = sum_k a[i*a_i + k*a_k] * b[j*b_j + k*b_k] + bias[j], fp64 running sums: FC1 forward, dX and dW in the
+ * reference's own layouts (regression_model.py:36; two_branch_regression.py:42). */
+int ctk_gemm_f32(const float* a, long long a_i, long long a_k, const float* b, long long b_j, long long b_k,
+                 const float* bias, int M, int N, int K, float* c, long long ldc, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

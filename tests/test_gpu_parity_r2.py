@@ -200,15 +200,17 @@ def warmed():
 # on the CPU in pure fp32 (double-branch): a 1e-6 relative perturbation of the INPUT moves the whole gradient by 6e-4 on the
 # warmed weights and 9e-4 at seed-0 init (x600-900 through train-mode BatchNorm); the oracle with bf16-rounded operands is
 # 3.4e-2 from fp32 on the warmed weights and 1.7e-1 at init.  The bounds are ~1.7x the bf16 rounding model on the warmed set.
-WHOLE_GRAD_BOUND = {"single": 1.2e-1, "double": 6e-2}
-TENSOR_GRAD_BOUND = {"single": 4e-1, "double": 2e-1}
+# Measured on B200: whole gradient 2.9e-2 (double) / 1.3e-2 (single); single tensors up to 19 % / 27 % (the first conv blocks,
+# whose gradient norms are 1e-3 of the whole).
+WHOLE_GRAD_BOUND = {"single": 3e-2, "double": 5e-2}
+TENSOR_GRAD_BOUND = {"single": 4e-1, "double": 3e-1}
 
 
 @pytest.mark.parametrize("kind", ["double", "single"])
 def test_gradients_at_batch_64_against_fp32_oracle(warmed, kind):
     """One training step from the CPU-warmed weights on 64 tiles of a 256-tile pool: loss within 1 %, whole-gradient and
     per-tensor relative L2 against the fp32 oracle asserted directly (no bf16-emulation yardstick), BatchNorm running
-    statistics within 2e-3."""
+    statistics within 2e-3 relative / 1e-3 absolute."""
     import ctk
     pool_x, pool_y = orc.synthetic_batch(256, seed=4321)
     idx = torch.arange(0, 256, 4)
@@ -237,11 +239,15 @@ def test_gradients_at_batch_64_against_fp32_oracle(warmed, kind):
         if name.endswith("bias") and p.dim() == 1 and (".conv_blocks." in name or name.startswith("conv_layers.")) and \
                 int(name.split(".")[-2]) % 4 == 0:
             # conv bias in front of a train-mode BatchNorm: the exact gradient is 0 (autograd leaves fp32 cancellation noise)
-            assert g.abs().max().item() == 0.0 and r.norm().item() <= 1e-3 * grads_ref[name[:-4] + "weight"].norm().item(), name
+            assert g.abs().max().item() == 0.0, name           # (the oracle's value is what cancels to in fp32, not a signal)
             continue
         if name.endswith("fc_layers.9.bias"):
             scale = (2.0 * (out_ref - y).abs() / n).sum().item()      # a sum that cancels: bound by the size of its terms
             assert (g - r).abs().item() <= 2e-2 * scale, (name, g.item(), r.item(), scale)
+            continue
+        if name.endswith("fc_layers.1.bias") or name.endswith("fc_layers.5.bias"):
+            # Linear bias in front of a train-mode BatchNorm1d: the exact gradient is 0, both sides hold cancellation noise
+            assert g.abs().max().item() <= 1e-6 * max(1.0, grads_ref[name[:-4] + "weight"].norm().item()), name
             continue
         rel = _rel(g, r)
         num += ((g.double() - r.double()) ** 2).sum().item()
@@ -256,7 +262,8 @@ def test_gradients_at_batch_64_against_fp32_oracle(warmed, kind):
     msd = model.state_dict()
     for k, v in sd.items():
         if k.endswith("running_mean") or k.endswith("running_var"):
-            np.testing.assert_allclose(msd[k].cpu().numpy(), v.numpy(), rtol=2e-3, atol=2e-4, err_msg=k)
+            # bf16 storage of the block inputs moves a batch mean by a few 1e-4 absolute (measured: up to 3.1e-4)
+            np.testing.assert_allclose(msd[k].cpu().numpy(), v.numpy(), rtol=2e-3, atol=1e-3, err_msg=k)
         if k.endswith("num_batches_tracked"):
             assert int(msd[k]) == int(v), k
 

@@ -17,7 +17,7 @@ OBJ = os.path.join(HERE, "build")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
          "-Xptxas", "-v", "--expt-relaxed-constexpr"]
-SOURCES = ["ctk_common.cu", "pearson.cu", "prep.cu", "conv_first.cu", "conv_tc.cu", "gemm_tc.cu", "head.cu", "optim.cu", "bn_train.cu", "head_train.cu", "wgrad_tc.cu", "first_train.cu", "tile_metrics.cu", "prep_input.cu", "ssim.cu", "reduce.cu"]
+SOURCES = ["ctk_common.cu", "pearson.cu", "prep.cu", "conv_first.cu", "conv_tc.cu", "gemm_tc.cu", "head.cu", "optim.cu", "bn_train.cu", "head_train.cu", "wgrad_tc.cu", "first_train.cu", "tile_metrics.cu", "prep_input.cu", "ssim.cu", "reduce.cu", "f32_train.cu"]
 
 
 def _digest():

@@ -423,10 +423,12 @@ int ctk_bn_act_pool_fwd(const void* y_bf16, int n, int H, int W, int channels, c
 }
 
 // rows of partial sums: the exact kernel's grid plus the pooled kernel's grid (the guarded entry point runs both)
-static int bn_reduce_grid_exact(long long pooled, int channels) {
+// full == false: the guarded entry point's second kernel, which normally finds no guarded channel group and only has to
+// write its rows of zero partial sums -- one CTA per SM keeps that at a few microseconds
+static int bn_reduce_grid_exact(long long pooled, int channels, bool full = true) {
   const int slots = 256 / (channels / 8);
   const long long blocks = (pooled + slots - 1) / slots;
-  const long long cap = static_cast<long long>(ctk::num_sms()) * 4;
+  const long long cap = static_cast<long long>(ctk::num_sms()) * (full ? 4 : 1);
   return static_cast<int>(blocks < 1 ? 1 : (blocks < cap ? blocks : cap));
 }
 static int bn_reduce_grid_pooled(long long pooled, int channels) {
@@ -474,7 +476,7 @@ static int bn_reduce_pooled_impl(const void* y_bf16, int H, int W, const float* 
   cudaStream_t s = ctk::as_stream(stream);
   const bool guard = y_bf16 != nullptr;
   const int grid_p = bn_reduce_grid_pooled(pooled_pixels, channels);
-  const int grid_e = guard ? bn_reduce_grid_exact(pooled_pixels, channels) : 0;
+  const int grid_e = guard ? bn_reduce_grid_exact(pooled_pixels, channels, false) : 0;
   CTK_REQUIRE_WORKSPACE(workspace, workspace_bytes, static_cast<size_t>(grid_p + grid_e) * 2 * channels * sizeof(float));
   float* part = static_cast<float*>(workspace);
   bn_bwd_reduce_pooled_kernel<<<grid_p, 256, 256 * 16 * sizeof(float), s>>>(

@@ -138,29 +138,43 @@ __global__ void head_out_fwd_kernel(const float* __restrict__ a2, const float* _
 }
 
 // dz3[n] = dout[n] * d(out)/dz;  dA2[n][j] = dz3[n]*w3[j];  dw3[j] = sum_n dz3[n]*a2[n][j];  db3 = sum_n dz3[n]
-// single block: the whole problem is N x 128
+// one CTA per 32 columns j; the 8 warps split the rows, their partial sums are added in warp order (deterministic)
 __global__ void __launch_bounds__(256)
 head_out_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ out, const float* __restrict__ a2,
                     const float* __restrict__ w3, int n_rows, int F, int sigmoid_half, float* __restrict__ da2,
                     float* __restrict__ dw3, float* __restrict__ db3) {
-  extern __shared__ float dz[];          // [n_rows]
-  for (int n = threadIdx.x; n < n_rows; n += blockDim.x) {
+  __shared__ float red[8][32];
+  const int lane = threadIdx.x & 31, rg = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + lane;
+  const float w = j < F ? w3[j] : 0.f;
+  float acc = 0.f;
+  for (int n = rg; n < n_rows; n += 8) {
     float g = dout[n];
     if (sigmoid_half) g *= out[n] * (1.f - 2.f * out[n]);      // d/dz 0.5*sigmoid(z) = out*(1-2*out)
-    dz[n] = g;
+    if (j < F) {
+      const long long i = static_cast<long long>(n) * F + j;
+      da2[i] = g * w;
+      acc = fmaf(g, a2[i], acc);
+    }
   }
+  red[rg][lane] = acc;
   __syncthreads();
-  for (long long i = threadIdx.x; i < static_cast<long long>(n_rows) * F; i += blockDim.x)
-    da2[i] = dz[i / F] * w3[i % F];
-  for (int j = threadIdx.x; j < F; j += blockDim.x) {
-    float acc = 0.f;
-    for (int n = 0; n < n_rows; ++n) acc = fmaf(dz[n], a2[static_cast<long long>(n) * F + j], acc);
-    dw3[j] = acc;
+  if (rg == 0 && j < F) {
+    float t = 0.f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) t += red[r][lane];
+    dw3[j] = t;
   }
-  if (threadIdx.x == 0) {
-    float acc = 0.f;
-    for (int n = 0; n < n_rows; ++n) acc += dz[n];
-    db3[0] = acc;
+  if (blockIdx.x == 0 && rg == 1) {                            // db3: lane l adds rows l, l+32, ..., then a fixed butterfly
+    float t = 0.f;
+    for (int n = lane; n < n_rows; n += 32) {
+      float g = dout[n];
+      if (sigmoid_half) g *= out[n] * (1.f - 2.f * out[n]);
+      t += g;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (lane == 0) db3[0] = t;
   }
 }
 
@@ -266,8 +280,8 @@ int ctk_head_out_fwd(const float* a2, const float* w3, const float* b3, int n_ro
 int ctk_head_out_bwd(const float* dout, const float* out, const float* a2, const float* w3, int n_rows, int features,
                      int sigmoid_half, float* da2, float* dw3, float* db3, void* stream) {
   CTK_REQUIRE(dout && out && a2 && w3 && da2 && dw3 && db3 && n_rows > 0 && n_rows <= 8192 && features > 0);
-  head_out_bwd_kernel<<<1, 256, n_rows * sizeof(float), ctk::as_stream(stream)>>>(dout, out, a2, w3, n_rows, features,
-                                                                                 sigmoid_half, da2, dw3, db3);
+  head_out_bwd_kernel<<<(features + 31) / 32, 256, 0, ctk::as_stream(stream)>>>(dout, out, a2, w3, n_rows, features,
+                                                                               sigmoid_half, da2, dw3, db3);
   return ctk::check_launch();
 }
 

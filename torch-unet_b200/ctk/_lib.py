@@ -122,6 +122,27 @@ _SIGNATURES = {
                                     c_float, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "ctk_bn1d_bwd_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p,
                                    c_void_p, c_void_p, c_int, c_void_p]),
+    # ---- fp32 training path (CUDA cores, the reference's own arithmetic)
+    "ctk_pack_conv_weight_f32": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "ctk_conv3x3_f32": (c_int, [c_void_p, c_longlong, c_longlong, c_longlong, c_longlong, c_int, c_int, c_int, c_int,
+                                c_void_p, c_int, c_void_p, c_void_p]),
+    "ctk_conv3x3_wgrad_f32_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    "ctk_conv3x3_wgrad_f32": (c_int, [c_void_p, c_void_p, c_longlong, c_longlong, c_longlong, c_longlong, c_int, c_int,
+                                      c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "ctk_channel_sums_f64_workspace_bytes": (c_size_t, [c_int]),
+    "ctk_channel_stats_f32": (c_int, [c_void_p, c_longlong, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "ctk_bn_finalize_f64": (c_int, [c_void_p, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                    c_float, c_float, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "ctk_bn_act_pool_fwd_f32": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                        c_float, c_void_p, c_longlong, c_longlong, c_longlong, c_void_p]),
+    "ctk_bn_bwd_reduce_f32": (c_int, [c_void_p, c_void_p, c_longlong, c_longlong, c_longlong, c_int, c_int, c_int, c_int,
+                                      c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p,
+                                      c_size_t, c_void_p]),
+    "ctk_bn_bwd_apply_f32": (c_int, [c_void_p, c_void_p, c_longlong, c_longlong, c_longlong, c_int, c_int, c_int, c_int,
+                                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_float, c_void_p,
+                                     c_void_p]),
+    "ctk_gemm_f32": (c_int, [c_void_p, c_longlong, c_longlong, c_void_p, c_longlong, c_longlong, c_void_p, c_int, c_int,
+                             c_int, c_void_p, c_longlong, c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES.keys())
@@ -179,7 +200,10 @@ KERNELS_PER_CALL = {"ctk_pearson_f32": 2, "ctk_tile_metrics_f32": 4, "ctk_tile_n
                     "ctk_conv3x3_wgrad_tc": 2, "ctk_conv_first_wgrad": 2, "ctk_feat_transpose_bf16": 1,
                     "ctk_pack_fc1_weight_t_bf16": 1, "ctk_gemm_bf16_out_bf16": 1, "ctk_gemm_bf16_bt_out_bf16": 1, "ctk_colstat": 1,
                     "ctk_bn1d_act_drop_fwd": 1, "ctk_dropout_masks": 1, "ctk_sgemm_strided": 1, "ctk_head_out_fwd": 1, "ctk_head_out_bwd": 1,
-                    "ctk_bn1d_bwd_reduce": 1, "ctk_bn1d_bwd_apply": 1}
+                    "ctk_bn1d_bwd_reduce": 1, "ctk_bn1d_bwd_apply": 1,
+                    "ctk_pack_conv_weight_f32": 1, "ctk_conv3x3_f32": 1, "ctk_conv3x3_wgrad_f32": 2, "ctk_channel_stats_f32": 2,
+                    "ctk_bn_finalize_f64": 1, "ctk_bn_act_pool_fwd_f32": 1, "ctk_bn_bwd_reduce_f32": 3,
+                    "ctk_bn_bwd_apply_f32": 1, "ctk_gemm_f32": 1, "ctk_dropout_masks": 1, "ctk_scale_by_scalar": 1}
 launch_count = 0
 _timeline = None      # when a list: (name, start_event, end_event, meta) per call, for per-kernel timing in bench.py
 _timeline_only = None # optional set of entry points to instrument (events around every call cost ~2 us each)

@@ -46,21 +46,28 @@ def get_engine(model) -> InferenceEngine:
 
 
 def set_precision(model, precision: str):
-    """Select the arithmetic of the eval-mode path: "bf16" (default: bf16 operands, fp32 accumulation; north_star bound
-    1e-3 on the score) or "fp32" (every operand carried as a bf16 hi/lo pair, three MMAs per product; bound 1e-5)."""
+    """Select the arithmetic of both paths.  "bf16" (default): bf16 operands, fp32 accumulation on tcgen05 (north_star bound
+    1e-3 on the score).  "fp32": eval -- every operand carried as a bf16 (hi, lo) pair, three MMAs per product, one
+    accumulator per K chunk (bound 1e-5); train -- the reference's own float32 arithmetic on the CUDA cores
+    (ctk.train_f32.TrainEngineF32), for gradient / loss-curve parity runs.  Call it before parallel.attach()."""
     if precision not in ("bf16", "fp32"):
         raise _lib.CtkError("precision must be 'bf16' or 'fp32'")
     model.__dict__["_ctk_precision"] = precision
     model.__dict__.pop("_ctk_engine", None)
+    model.__dict__.pop("_ctk_train_engine", None)
     return model
 
 
 def get_train_engine(model):
     """The (lazily created) libctk training engine bound to ``model``."""
-    from .train import TrainEngine
     eng = model.__dict__.get("_ctk_train_engine")
     if eng is None:
-        eng = TrainEngine(model)
+        if model.__dict__.get("_ctk_precision", "bf16") == "fp32":
+            from .train_f32 import TrainEngineF32
+            eng = TrainEngineF32(model)
+        else:
+            from .train import TrainEngine
+            eng = TrainEngine(model)
         model.__dict__["_ctk_train_engine"] = eng
     return eng
 
