@@ -37,3 +37,18 @@ def golden():
     g["tiles"] = z["tiles"]
     g["labels_np"] = z["labels"]
     return g
+
+
+@pytest.fixture(scope="session")
+def golden32():
+    """32 of the reference's Training_Data pairs + what the unmodified reference computes for them
+    (tests/golden/make_fixtures32.py).  ``x`` is the normalised input batch the reference's dataset would yield."""
+    import json
+    import numpy as np
+    import torch
+    import crosstalk_oracle as orc
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "golden32.json")))
+    tiles = np.load(os.path.join(ROOT, "tests", "golden", "tiles32.npz"))["tiles"]
+    g["tiles"] = tiles
+    g["x"] = torch.from_numpy(np.stack([np.stack([orc.normalize_image(t[0]), orc.normalize_image(t[1])]) for t in tiles]))
+    return g

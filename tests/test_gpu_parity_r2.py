@@ -321,3 +321,26 @@ def test_bench_configuration_spot_check():
     assert (s_host.flatten() - scores).abs().max().item() <= 1e-5
     assert torch.equal(r_host.flatten().double(), r.double())
     assert (s_host.flatten()[idx] - ref).abs().max().item() <= 1e-3
+
+
+def test_32_reference_fixture_pairs_against_the_reference_outputs(golden32):
+    """Config 1 of BASELINE.json widened to 32 of the reference's own Training_Data pairs: scores of both models in both
+    precisions and the comparison metrics against the values the UNMODIFIED reference computed (tests/golden/golden32.json)."""
+    import ctk
+    x = golden32["x"].cuda()
+    m = ctk.tile_metrics(x)
+    np.testing.assert_allclose(m["pearson"].cpu().numpy(), np.array(golden32["pearson_f32"]), rtol=0, atol=1e-6)
+    np.testing.assert_allclose(ctk.pearson_per_image(x).cpu().numpy(), np.array(golden32["pearson_f32"]), rtol=0, atol=1e-6)
+    np.testing.assert_allclose(m["rmse"].cpu().numpy(), np.array(golden32["rmse"]), rtol=0, atol=1e-6)
+    np.testing.assert_allclose(m["hist_corr"].cpu().numpy(), np.array(golden32["hist_corr"]), rtol=0, atol=1e-9)
+    for kind in ("single", "double"):
+        model = _build(kind)
+        model.load_state_dict(orc.randomize_bn(model.state_dict(), seed=7))
+        model = model.cuda().eval()
+        ref = torch.tensor(golden32[f"{kind}_eval_randomized_bn"])
+        with torch.no_grad():
+            e16 = (model(x).flatten().cpu() - ref).abs().max().item()
+            ctk.set_precision(model, "fp32")
+            e32 = (model(x).flatten().cpu() - ref).abs().max().item()
+        print(kind, "32 fixture pairs: max abs err vs the reference's scores: bf16 %.2e, fp32-class %.2e" % (e16, e32))
+        assert e16 <= 1e-3 and e32 <= 1e-5

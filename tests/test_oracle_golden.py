@@ -214,3 +214,21 @@ def test_bin_rules_match_numpy_on_adversarial_planes():
         if want is not None:
             assert np.array_equal(orc.histogram256_f32(x), want)
         assert np.array_equal(orc.digitize256_f32(x), np.digitize(x, bins=np.linspace(x.min(), x.max(), 256)))
+
+
+def test_oracle_on_32_reference_fixture_pairs(golden32):
+    """The wider fixture set (32 Training_Data pairs): Pearson r (float32, like scipy), RMSE, histogram correlation and the
+    eval-mode scores of both models (randomised BatchNorm) against the unmodified reference's values."""
+    x = golden32["x"]
+    xn = x.numpy()
+    r = orc.pearson_batch(x, f64=False)
+    np.testing.assert_allclose(r, np.array(golden32["pearson_f32"]), rtol=0, atol=1e-6)
+    np.testing.assert_allclose(orc.pearson_batch(x, f64=True), np.array(golden32["pearson_f32"]), rtol=0, atol=1e-6)
+    for j in range(x.shape[0]):
+        assert abs(orc.rmse_f32(xn[j, 0], xn[j, 1]) - golden32["rmse"][j]) <= 1e-7
+        assert abs(orc.hist_correlation(xn[j, 0], xn[j, 1]) - golden32["hist_corr"][j]) <= 1e-9
+    for kind in ("single", "double"):
+        sd = orc.randomize_bn(orc.INIT[kind](0), seed=7)
+        with torch.no_grad():
+            out = orc.FORWARD[kind](sd, x).flatten().numpy()
+        np.testing.assert_allclose(out, np.array(golden32[f"{kind}_eval_randomized_bn"]), rtol=0, atol=2e-6)
