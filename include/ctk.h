@@ -380,12 +380,12 @@ int ctk_bn1d_bwd_apply(const float* dact, const float* z, const float* scale, co
 /* [Cout,Cin,3,3] -> [(tap*cin + ci)][cout] (rotate 0: forward operand) or [((8-tap)*cout + co)][cin] (rotate 1: the
  * operand that makes ctk_conv3x3_f32 compute the input gradient from dY). */
 int ctk_pack_conv_weight_f32(const float* w, int cout, int cin, int rotate, float* out, void* stream);
-/* y[n,H,W,cout] = conv3x3(x, w) without bias, stride 1, zero padding 1.  cout % 64 == 0, n*H*W % 128 == 0.
+/* y[n,H,W,cout] = conv3x3(x, w) without bias, stride 1, zero padding 1.  cout % 64 == 0.
  * Replaces: nn.Conv2d forward / input gradient, regression_model.py:14,23; two_branch_regression.py:10,16,22,28. */
 int ctk_conv3x3_f32(const float* x, long long sn, long long sy, long long sx, long long sc, int n, int H, int W, int cin,
                     const float* w_packed, int cout, float* y, void* stream);
 /* dw[Cout,Cin,3,3] = sum_pixels dY[p,co] * x[p+tap,ci]; split over pixel slices with fp64 partial sums in the workspace,
- * added in slice order.  n*H*W % 16 == 0, cout % 64 == 0.  Replaces: aten::convolution_backward (weight gradient). */
+ * added in slice order.  cout % 64 == 0.  Replaces: aten::convolution_backward (weight gradient). */
 size_t ctk_conv3x3_wgrad_f32_workspace_bytes(int n, int H, int W, int cin, int cout);
 int ctk_conv3x3_wgrad_f32(const float* dy, const float* x, long long sn, long long sy, long long sx, long long sc, int n,
                           int H, int W, int cin, int cout, float* dw, void* workspace, size_t workspace_bytes,

@@ -48,7 +48,7 @@ def _build(kind):
 # ------------------------------------------------------------------------------------------------ kernels
 @pytest.mark.parametrize("n,H,W,cin,cout,layout", [(2, 32, 32, 64, 128, "nhwc"), (1, 16, 32, 128, 64, "nhwc"),
                                                    (2, 32, 64, 1, 64, "plane1"), (2, 32, 32, 2, 128, "nchw"),
-                                                   (4, 8, 8, 128, 128, "nhwc")])
+                                                   (4, 8, 8, 128, 128, "nhwc"), (3, 8, 8, 64, 64, "nhwc")])
 def test_conv_forward_dgrad_and_wgrad_f32(L, n, H, W, cin, cout, layout):
     torch.manual_seed(0)
     w = (torch.randn(cout, cin, 3, 3) / (3 * cin ** 0.5)).requires_grad_(True)

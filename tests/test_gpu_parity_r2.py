@@ -344,3 +344,42 @@ def test_32_reference_fixture_pairs_against_the_reference_outputs(golden32):
             e32 = (model(x).flatten().cpu() - ref).abs().max().item()
         print(kind, "32 fixture pairs: max abs err vs the reference's scores: bf16 %.2e, fp32-class %.2e" % (e16, e32))
         assert e16 <= 1e-3 and e32 <= 1e-5
+
+
+def test_edge_cases_empty_ragged_and_single_sample_batches():
+    """Empty and ragged batches through the eval path (FC1 pads its M to 128, batches above 256 tiles run in slices), the
+    smallest training batch, and the reference's own refusal of a 1-sample training batch (nn.BatchNorm1d raises ValueError)."""
+    import ctk
+    x, y = orc.synthetic_batch(5, seed=8)
+    model = _build("double")
+    sd = orc.randomize_bn(model.state_dict(), seed=7)
+    model.load_state_dict(sd)
+    model = model.cuda().eval()
+    with torch.no_grad():
+        ref = orc.double_forward(sd, x).flatten()
+        assert tuple(model(x[:0].cuda()).shape) == (0, 1)
+        assert ctk.pearson_per_image(x[:0].cuda()).numel() == 0
+        for n in (1, 3, 5):
+            assert (model(x[:n].cuda()).flatten().cpu() - ref[:n]).abs().max().item() <= 1e-3
+        big = x.repeat(52, 1, 1, 1)[:257].contiguous()                 # 256 + 1: two slices
+        out = model(big.cuda()).flatten().cpu()
+        assert (out - ref.repeat(52)[:257]).abs().max().item() <= 1e-3
+    with pytest.raises(ctk.CtkError):
+        model(x.cuda().permute(0, 1, 3, 2))                            # non-contiguous input
+    with pytest.raises(ctk.CtkError):
+        model(x[:, :1].contiguous().cuda())                            # one channel
+    model.train()
+    for precision in ("bf16", "fp32"):
+        ctk.set_precision(model, precision)
+        loss = ctk.MSELoss()(model(x[:2].cuda()), y[:2].cuda())        # the smallest batch BatchNorm accepts
+        loss.backward()
+        assert np.isfinite(loss.item()) and all(torch.isfinite(p.grad).all() for p in model.parameters())
+        with pytest.raises(ValueError):
+            model(x[:1].cuda())
+    # an odd batch through the single-branch model (its deepest conv sees 3 x 8 x 8 = 192 pixels: a ragged last tile)
+    single = _build("single").cuda().train()
+    for precision in ("bf16", "fp32"):
+        ctk.set_precision(single, precision)
+        loss = ctk.MSELoss()(single(x[:3].cuda()), y[:3].cuda())
+        loss.backward()
+        assert np.isfinite(loss.item()) and all(torch.isfinite(p.grad).all() for p in single.parameters())

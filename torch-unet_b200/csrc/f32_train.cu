@@ -38,8 +38,8 @@ __device__ __forceinline__ float leaky_f(float v, float slope) { return v > 0.f 
 constexpr int kBM = 128, kBN = 64, kBK = 16, kAPitch = kBM + 2;
 
 __global__ void __launch_bounds__(256)
-conv3x3_f32_kernel(const float* __restrict__ x, TensorView xv, int H, int W, int cin, const float* __restrict__ wk,
-                   int cout, float* __restrict__ y) {
+conv3x3_f32_kernel(const float* __restrict__ x, TensorView xv, long long pixels, int H, int W, int cin,
+                   const float* __restrict__ wk, int cout, float* __restrict__ y) {
   __shared__ float As[kBK][kAPitch];
   __shared__ __align__(16) float Bs[kBK][kBN];
   const int tid = threadIdx.x;
@@ -56,7 +56,7 @@ conv3x3_f32_kernel(const float* __restrict__ x, TensorView xv, int H, int W, int
     const int w = static_cast<int>(p % W);
     const long long t = p / W;
     const int h = static_cast<int>(t % H);
-    ph[j] = h; pw[j] = w;
+    ph[j] = p < pixels ? h : -4; pw[j] = w;                 // rows past the end (ragged last tile) read as padding
     pix_off[j] = (t / H) * xv.sn + h * xv.sy + w * xv.sx;
   }
   const int nl = tid & 63, kq = tid >> 6;                 // B loads
@@ -107,7 +107,8 @@ conv3x3_f32_kernel(const float* __restrict__ x, TensorView xv, int H, int W, int
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const long long p = p0 + i * 16 + tm;
-    *reinterpret_cast<float4*>(y + p * cout + n0 + tn * 4) =
+    if (p < pixels)
+      *reinterpret_cast<float4*>(y + p * cout + n0 + tn * 4) =
         make_float4(static_cast<float>(sum[i][0]), static_cast<float>(sum[i][1]), static_cast<float>(sum[i][2]),
                     static_cast<float>(sum[i][3]));
   }
@@ -117,8 +118,9 @@ conv3x3_f32_kernel(const float* __restrict__ x, TensorView xv, int H, int W, int
 // dW partial[s][co][nn] = sum_{p in slice s} dY[p][co] * X[p + tap(nn)][ci(nn)],  nn = tap * cin + ci
 // CTA: 64 co x 64 nn, K = pixels in chunks of 16 (one image row segment); thread: 4 co x 4 nn; fp64 running sums.
 __global__ void __launch_bounds__(256)
-conv3x3_wgrad_f32_kernel(const float* __restrict__ dy, const float* __restrict__ x, TensorView xv, int H, int W, int cin,
-                         int cout, long long chunks_total, int chunks_per_slice, double* __restrict__ part) {
+conv3x3_wgrad_f32_kernel(const float* __restrict__ dy, const float* __restrict__ x, TensorView xv, long long pixels, int H,
+                         int W, int cin, int cout, long long chunks_total, int chunks_per_slice,
+                         double* __restrict__ part) {
   __shared__ __align__(16) float As[kBK][64];
   __shared__ __align__(16) float Bs[kBK][64];
   const int tid = threadIdx.x;
@@ -144,14 +146,15 @@ conv3x3_wgrad_f32_kernel(const float* __restrict__ dy, const float* __restrict__
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int pk = pq + 4 * j;
-      As[pk][cl] = __ldg(dy + (p0 + pk) * cout + co0 + cl);
       const long long p = p0 + pk;
+      const bool pin = p < pixels;
+      As[pk][cl] = pin ? __ldg(dy + p * cout + co0 + cl) : 0.f;
       const int w = static_cast<int>(p % W);
       const long long t = p / W;
       const int h = static_cast<int>(t % H);
       const long long img = t / H;
       const int hh = h + ddy, ww = w + ddx;
-      const bool ok = nin && hh >= 0 && hh < H && ww >= 0 && ww < W;
+      const bool ok = pin && nin && hh >= 0 && hh < H && ww >= 0 && ww < W;
       Bs[pk][cl] = ok ? __ldg(x + img * xv.sn + hh * xv.sy + ww * xv.sx + ci * xv.sc) : 0.f;
     }
     __syncthreads();
@@ -471,10 +474,10 @@ int ctk_conv3x3_f32(const float* x, long long sn, long long sy, long long sx, lo
   if (n == 0) return CTK_OK;
   CTK_REQUIRE(x && w_packed && y && n > 0 && H > 0 && W > 0 && cin > 0 && cout > 0 && cout % kBN == 0);
   const long long pixels = static_cast<long long>(n) * H * W;
-  CTK_REQUIRE(pixels % kBM == 0 && pixels / kBM < (1ll << 31) && (reinterpret_cast<uintptr_t>(y) & 15) == 0);
+  CTK_REQUIRE((pixels + kBM - 1) / kBM < (1ll << 31) && (reinterpret_cast<uintptr_t>(y) & 15) == 0);
   const TensorView xv = {sn, sy, sx, sc};
-  conv3x3_f32_kernel<<<dim3(static_cast<unsigned>(pixels / kBM), cout / kBN), 256, 0, ctk::as_stream(stream)>>>(
-      x, xv, H, W, cin, w_packed, cout, y);
+  conv3x3_f32_kernel<<<dim3(static_cast<unsigned>((pixels + kBM - 1) / kBM), cout / kBN), 256, 0, ctk::as_stream(stream)>>>(
+      x, xv, pixels, H, W, cin, w_packed, cout, y);
   return ctk::check_launch();
 }
 
@@ -487,7 +490,7 @@ static int wgrad_f32_slices(long long chunks, int cout, int cin) {
 
 size_t ctk_conv3x3_wgrad_f32_workspace_bytes(int n, int H, int W, int cin, int cout) {
   if (n <= 0 || H <= 0 || W <= 0 || cin <= 0 || cout <= 0) return 0;
-  const long long chunks = static_cast<long long>(n) * H * W / kBK;
+  const long long chunks = (static_cast<long long>(n) * H * W + kBK - 1) / kBK;
   return static_cast<size_t>(wgrad_f32_slices(chunks, cout, cin)) * cout * 9 * cin * sizeof(double);
 }
 
@@ -496,16 +499,16 @@ int ctk_conv3x3_wgrad_f32(const float* dy, const float* x, long long sn, long lo
                           void* stream) {
   if (n == 0) return CTK_OK;
   CTK_REQUIRE(dy && x && dw && n > 0 && H > 0 && W > 0 && cin > 0 && cout > 0 && cout % 64 == 0);
-  CTK_REQUIRE((static_cast<long long>(n) * H * W) % kBK == 0);
-  const long long chunks = static_cast<long long>(n) * H * W / kBK;
+  const long long pixels = static_cast<long long>(n) * H * W;
+  const long long chunks = (pixels + kBK - 1) / kBK;
   const int slices = wgrad_f32_slices(chunks, cout, cin);
   CTK_REQUIRE_WORKSPACE(workspace, workspace_bytes, static_cast<size_t>(slices) * cout * 9 * cin * sizeof(double));
   const int per = static_cast<int>((chunks + slices - 1) / slices);
   const TensorView xv = {sn, sy, sx, sc};
   cudaStream_t s = ctk::as_stream(stream);
   double* part = static_cast<double*>(workspace);
-  conv3x3_wgrad_f32_kernel<<<dim3(cout / 64, (9 * cin + 63) / 64, slices), 256, 0, s>>>(dy, x, xv, H, W, cin, cout, chunks, per,
-                                                                                      part);
+  conv3x3_wgrad_f32_kernel<<<dim3(cout / 64, (9 * cin + 63) / 64, slices), 256, 0, s>>>(dy, x, xv, pixels, H, W, cin, cout,
+                                                                                      chunks, per, part);
   int st = ctk::check_launch();
   if (st != CTK_OK) return st;
   const int total = cout * 9 * cin;

@@ -214,6 +214,10 @@ class TrainEngine:
         for p in self.params:
             _lib.require_device(p, torch.float32, "parameter")
         n, c_total, H, W = x.shape
+        if n < 2:
+            # nn.BatchNorm1d in train() refuses a single sample (torch.nn.functional._verify_batch_size); so does this path
+            raise ValueError(f"Expected more than 1 value per channel when training, got input size torch.Size([{n}, "
+                             f"{self.lin[0].out_features}])")
         dev = x.device
         depth = len(self.branches[0].pairs)
         hf, wf = H >> depth, W >> depth

@@ -60,6 +60,10 @@ class TrainEngineF32(TrainEngine):
         if self.stat_allreduce is not None:
             raise _lib.CtkError("sync_bn is not wired into the fp32 training path (single-process parity mode)")
         n, c_total, H, W = x.shape
+        if n < 2:
+            # nn.BatchNorm1d in train() refuses a single sample (torch.nn.functional._verify_batch_size); so does this path
+            raise ValueError(f"Expected more than 1 value per channel when training, got input size torch.Size([{n}, "
+                             f"{self.lin[0].out_features}])")
         dev = x.device
         depth = len(self.branches[0].pairs)
         hf, wf = H >> depth, W >> depth
