@@ -288,7 +288,9 @@ class TrainEngine:
         out = self._new((n, 1), torch.float32, dev)
         call("ctk_head_out_fwd", ptr(a2), ptr(fc3.weight), ptr(fc3.bias), c_int(n), c_int(f2), c_int(self.sigmoid_half),
              ptr(out), stream())
-        sv.update(z1=z1, bn1=bn1, a1=a1, z2=z2, bn2=bn2, a2=a2, out=out, masks=masks, w1p=w1p)
+        # (a detached alias of the output: the returned tensor will own the autograd node that owns this dict -- saving the
+        #  tensor itself would make a reference cycle that keeps a whole step's activations alive until the garbage collector runs)
+        sv.update(z1=z1, bn1=bn1, a1=a1, z2=z2, bn2=bn2, a2=a2, out=out.detach(), masks=masks, w1p=w1p)
         # ctk_bn_finalize wrote the running statistics through raw pointers: bump the tensors' version counters so that
         # anything keyed on them (the eval engine's derived-parameter cache) sees the change
         torch.autograd.graph.increment_version([b for b in self.model.buffers()])

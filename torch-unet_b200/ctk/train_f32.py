@@ -135,7 +135,7 @@ class TrainEngineF32(TrainEngine):
         out = self._new((n, 1), torch.float32, dev)
         call("ctk_head_out_fwd", ptr(a2), ptr(fc3.weight), ptr(fc3.bias), c_int(n), c_int(f2), c_int(self.sigmoid_half),
              ptr(out), stream())
-        sv.update(z1=z1, bn1=bn1, a1=a1, z2=z2, bn2=bn2, a2=a2, out=out, masks=masks)
+        sv.update(z1=z1, bn1=bn1, a1=a1, z2=z2, bn2=bn2, a2=a2, out=out.detach(), masks=masks)
         torch.autograd.graph.increment_version([b for b in self.model.buffers()])
         return out, sv
 
