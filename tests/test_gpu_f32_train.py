@@ -301,8 +301,8 @@ def test_200_step_loss_curve_at_batch_64(kind):
     (unmodified model class + torch.optim.Adam + MSELoss on the CPU, tests/golden/make_loss_curve.py) at batch 64 from a
     256-tile pool is the golden; the same loop re-run with another thread count (only ATen's reduction order changes) tells
     for how many steps the reference reproduces ITSELF to 1 %.  Asserted:
-      fp32 path : every step within 1 % for as long as the reference's two runs agree to 1 % (at least steps 0 and 1),
-                  and every 25-step window's geometric-mean loss within 1.5 x the band the reference keeps to itself;
+      fp32 path : over the first 12 steps each step within max(1 %, 4 x the distance between the reference's two runs at that
+                  step), and every 25-step window's geometric-mean loss within 1.5 x the band the reference keeps to itself;
       bf16 path : step 0 within 1 %, every window within the same band widened to at least 25 % -- bf16 operand rounding
                   is a 2^-9 perturbation where a thread count is a 2^-24 one."""
     g = _curve(f"loss_curve_{kind}_b64.json")
@@ -327,7 +327,15 @@ def test_200_step_loss_curve_at_batch_64(kind):
         print(f"{kind} {precision}: step-0 loss gpu {gpu[0]:.6f} reference {ref[0]:.6f}; within 1 % for the first {first_bad} steps; "
               f"median rel {np.median(rel):.2e}, max {rel.max():.2e}")
         assert rel[0] <= 1e-2
-        if precision == "fp32":
+        if other is not None:
+            m = min(len(other), steps, 12)
+            own_rel = np.abs(other[:m] - ref[:m]) / ref[:m]
+            print("   step: gpu-vs-reference / reference-vs-itself  " + "  ".join(f"{t}: {rel[t]:.1e}/{own_rel[t]:.1e}" for t in range(m)))
+            if precision == "fp32":
+                # step by step the fp32 path may stray from the reference run no further than a small multiple of what the
+                # reference's second run does (both are fp32 summation-order perturbations of the same chaotic trajectory)
+                assert all(rel[t] <= max(1e-2, 4.0 * own_rel[t]) for t in range(m)), (rel[:m], own_rel[:m])
+        elif precision == "fp32":
             assert first_bad >= min(agree, steps), (first_bad, agree)
         for a in range(0, steps - 24, 25):
             r_, g_ = gm(ref, a), gm(gpu, a)

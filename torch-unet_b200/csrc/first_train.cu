@@ -12,6 +12,8 @@
 // arg-max / sign codes the forward kernel stored per pooled element.
 // Replaces (train mode) nn.Conv2d + nn.BatchNorm2d statistics + their backward for the first block:
 // /root/reference/regression_model.py:14-15 and two_branch_regression.py:10-11.
+#include <cstdlib>
+
 #include "ctk_common.h"
 #include "ctk_ptx.cuh"
 
@@ -336,6 +338,360 @@ first_wgrad_codes_kernel(const float* __restrict__ x, int n_img, int c_total, in
     }
 }
 
+// ------------------------------------------------------------------------------------------------ the same gather on tcgen05
+// t1[c][t] = sum_w g[w,c] x[p*(w,c) + t] is a GEMM over K = windows once the arg-max position is folded into the A operand:
+//   D[c][n] = sum_q sum_w A_q[c][w] * B_q[w][n],   A_q[c][w] = g[w,c] if position(w,c) == q else 0   (bf16: dP is bf16),
+//   B_q[w][n] = the 9*CIN taps of window w's patch shifted by q, every fp32 value carried as three bf16 terms
+//   (hi, mid, lo planes: exact to fp32), plus a column of ones that yields s1[c] = sum_w g[w,c].
+// Both operands are MN-major (the K index -- the window -- selects a 128-byte row), built by hand in the 128B-swizzled
+// layout TMA would produce: A builders mask one 16-byte chunk (8 channels of one window) per variant with two PRMT look-ups
+// of the packed 2-bit positions, B builders (one thread per window) expand the 4x4 patch.  One (region of 16x8 windows,
+// position) pair is one pipeline stage of 8 MMAs (M = 128 channels, N = 64 columns, K = 16 windows each).  tcgen05
+// accumulates with truncation (-2^-24 per step), so the TMEM accumulator is drained into fp32 shared-memory totals every
+// four regions (128 steps) instead of once per kernel (~28 000 steps).  Per-CTA partial rows as in the CUDA-core kernel.
+namespace wtc {
+constexpr int kWinH = 16, kWinW = 8;                 // windows per region: K = 128 per stage
+constexpr int kStages = 3;
+constexpr int kABytes = 32768, kBBytes = 16384, kStageBytes = kABytes + kBBytes;
+constexpr int kAccPitch = 65;                        // fp32 totals [128 channels][64 columns], conflict-free rows
+constexpr int kInRows = 2 * kWinH + 2, kInCols = 2 * kWinW + 2, kInPitch = 24;
+constexpr int kThreads = 13 * 32;                    // warps 0-3 B builders + drain, 4 MMA, 5-12 A builders
+constexpr int kDrainEvery = 4;                       // regions per accumulation period
+constexpr int smem_bytes(int cin) {
+  return 1024 + kStages * kStageBytes + 128 * kAccPitch * 4 + cin * kInRows * kInPitch * 4 + 256;
+}
+__device__ __forceinline__ uint64_t mn_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {   // MN-major, SWIZZLE_128B
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((addr >> 4) & 0x3fff);
+  d |= static_cast<uint64_t>((lbo >> 4) & 0x3fff) << 16;
+  d |= static_cast<uint64_t>((sbo >> 4) & 0x3fff) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+__host__ __device__ constexpr uint32_t mn_idesc(uint32_t M, uint32_t N) {                    // bf16 x bf16 -> f32, A and B MN-major
+  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+__device__ __forceinline__ uint32_t bf16_bits(float v) { return __bfloat16_as_ushort(__float2bfloat16_rn(v)); }
+// Bounded wait without the %globaltimer read of ctk::mbar_wait: the roles of this kernel hand stages to one another four
+// times per region and usually find the barrier not yet flipped; a protocol bug still traps (try_wait itself suspends the
+// warp for a hardware-bounded time, so 2^26 failed polls are seconds, not an endless spin).
+__device__ __forceinline__ void wait(uint32_t bar_addr, uint32_t parity) {
+  uint32_t n = 0;
+  for (;;) {
+    uint32_t ok;
+    // the suspend-time hint keeps a waiting warp parked instead of polling: the builder and MMA warps share schedulers
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar_addr), "r"(parity), "r"(0x989680u)
+        : "memory");
+    if (ok) return;
+    if (++n > (1u << 22)) __trap();
+  }
+}
+__device__ __forceinline__ void arrive(uint32_t bar_addr) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_addr) : "memory");
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+}  // namespace wtc
+
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(wtc::kThreads, 1)
+first_wgrad_tc_kernel(const float* __restrict__ x, int n_img, int c_total, int c_offset, int H, int W,
+                      const uint32_t* __restrict__ codes, const __nv_bfloat16* __restrict__ dp, float slope,
+                      float* __restrict__ part) {
+  using namespace wtc;
+  constexpr int T = 9 * CIN;
+  constexpr int TP = CIN == 1 ? 10 : 18;              // plane stride inside a B row (even: planes start on a word)
+  constexpr int ONES = 3 * TP;                        // the column of ones
+  constexpr int BWORDS = ONES / 2 + 1;                // 32-bit words of a B row that are ever non-zero
+  constexpr int BCHUNKS = (BWORDS + 3) / 4;
+  constexpr int CH = COUT / 8;                        // 16-byte chunks (8 channels) per window
+  constexpr int AIT = 128 * CH / 256;                 // chunks per A-builder thread and variant
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* stages = smem;
+  float* acc_s = reinterpret_cast<float*>(smem + kStages * kStageBytes);
+  float* s_in = acc_s + 128 * kAccPitch;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_in + CIN * kInRows * kInPitch);
+  uint64_t* full = bars;                    // [kStages]: 12 builder-warp arrivals
+  uint64_t* empty = bars + kStages;         // [kStages]: one MMA commit
+  uint64_t* acc_full = empty + kStages;     // [2]: one MMA commit
+  uint64_t* acc_empty = acc_full + 2;       // [2]: 4 drain-warp arrivals
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 12); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    fence_mbar_init();
+  }
+  if (warp == 4) tmem_alloc<1>(tmem_slot, 128);
+  // stage memory starts zeroed: channel block 1 of A (COUT == 64) and the unused tail of every B row stay zero for good
+  for (int i = threadIdx.x; i < kStages * kStageBytes / 16; i += kThreads)
+    reinterpret_cast<uint4*>(stages)[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = threadIdx.x; i < 128 * kAccPitch; i += kThreads) acc_s[i] = 0.f;
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t stages_a = smem_u32(stages);
+  const uint32_t full_a = smem_u32(full), empty_a = smem_u32(empty), acc_full_a = smem_u32(acc_full),
+                 acc_empty_a = smem_u32(acc_empty);
+
+  const int Hp = H >> 1, Wp = W >> 1;
+  const int regions_x = (Wp + kWinW - 1) / kWinW, regions_y = (Hp + kWinH - 1) / kWinH;
+  const long long total = static_cast<long long>(n_img) * regions_x * regions_y;
+  const int my_regions = blockIdx.x < total ? static_cast<int>((total - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+  auto decode = [&](long long region, int& img, int& ry, int& rx) {
+    rx = static_cast<int>(region % regions_x);
+    ry = static_cast<int>((region / regions_x) % regions_y);
+    img = static_cast<int>(region / (static_cast<long long>(regions_x) * regions_y));
+  };
+
+  if (warp >= 5) {
+    // ------------------------------------------------------------------ A builders: masked gradient tiles
+    const int tp = threadIdx.x - 160;
+    const int cc = tp % CH, ws = tp / CH;
+    const uint32_t one_b = 0x3f80u, slope_b = bf16_bits(slope);
+    // chunk j of this thread: window ws + j * (256 / CH); its byte offset inside an A tile never changes
+    uint32_t a_off[AIT];
+#pragma unroll
+    for (int j = 0; j < AIT; ++j) {
+      const int w = ws + j * (256 / CH), row = w & 7;
+      a_off[j] = static_cast<uint32_t>((cc >> 3) * 16384 + (w >> 3) * 1024 + row * 128 + (((cc & 7) ^ row) << 4));
+    }
+    uint4 raw[AIT];
+    uint32_t cw[AIT];
+    auto load_region = [&](long long region) {
+      int img, ry, rx;
+      decode(region, img, ry, rx);
+      const int py0 = ry * kWinH + (ws >> 3), px = rx * kWinW + (ws & 7);     // 256 / CH is a multiple of 8: px is shared
+      const size_t pix0 = (static_cast<size_t>(img) * Hp + py0) * Wp + px;
+#pragma unroll
+      for (int j = 0; j < AIT; ++j) {
+        const int py = py0 + j * (32 / CH);
+        const bool ok = py < Hp && px < Wp;
+        const size_t pix = ok ? pix0 + static_cast<size_t>(j * (32 / CH)) * Wp : 0;
+        raw[j] = ok ? __ldcs(reinterpret_cast<const uint4*>(dp + pix * COUT + cc * 8)) : make_uint4(0u, 0u, 0u, 0u);
+        cw[j] = ok ? __ldcs(codes + pix * CH + cc) : 0u;
+      }
+    };
+    if (my_regions > 0) load_region(blockIdx.x);
+    int slot = 0;
+    uint32_t phase = 1;                     // parity the empty barrier of `slot` must have completed
+    for (int k = 0; k < my_regions; ++k) {
+      // g = dP * (slope where the pre-activation was negative), in bf16 like dP itself; positions as PRMT selectors
+      uint32_t g[AIT][4], sel_lo[AIT], sel_hi[AIT];
+#pragma unroll
+      for (int j = 0; j < AIT; ++j) {
+        const uint32_t rw[4] = {raw[j].x, raw[j].y, raw[j].z, raw[j].w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          // elements 2i / 2i+1 of the chunk: sign bits at 8i + 2 / 8i + 6 of the code word
+          const uint32_t f = (((cw[j] >> (8 * i + 2)) & 1u) ? slope_b : one_b) |
+                             ((((cw[j] >> (8 * i + 6)) & 1u) ? slope_b : one_b) << 16);
+          const __nv_bfloat162 v = __hmul2(*reinterpret_cast<const __nv_bfloat162*>(&rw[i]),
+                                           *reinterpret_cast<const __nv_bfloat162*>(&f));
+          g[j][i] = *reinterpret_cast<const uint32_t*>(&v);
+        }
+        sel_lo[j] = cw[j] & 0x3333u;
+        sel_hi[j] = (cw[j] >> 16) & 0x3333u;
+      }
+      if (k + 1 < my_regions) load_region(blockIdx.x + static_cast<long long>(k + 1) * gridDim.x);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        wait(empty_a + slot * 8, phase);
+        const uint32_t a_tile = stages_a + slot * kStageBytes;
+        const uint32_t lut = 0xffu << (8 * q);
+#pragma unroll
+        for (int j = 0; j < AIT; ++j) {
+          const uint32_t m_lo = __byte_perm(lut, 0u, sel_lo[j]);      // byte e = 0xff where element e sits at position q
+          const uint32_t m_hi = __byte_perm(lut, 0u, sel_hi[j]);
+          sts128(a_tile + a_off[j], g[j][0] & __byte_perm(m_lo, 0u, 0x1100), g[j][1] & __byte_perm(m_lo, 0u, 0x3322),
+                 g[j][2] & __byte_perm(m_hi, 0u, 0x1100), g[j][3] & __byte_perm(m_hi, 0u, 0x3322));
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) arrive(full_a + slot * 8);
+        if (++slot == kStages) { slot = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 4) {
+    // ------------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = mn_idesc(128, 64);
+    uint64_t adesc[kStages], bdesc[kStages];
+#pragma unroll
+    for (int i = 0; i < kStages; ++i) {
+      adesc[i] = mn_desc(stages_a + i * kStageBytes, 16384, 1024);
+      bdesc[i] = mn_desc(stages_a + i * kStageBytes + kABytes, 16384, 1024);
+    }
+    int slot = 0, periods = 0, in_period = 0;
+    uint32_t phase = 0;
+    for (int k = 0; k < my_regions; ++k) {
+      const int buf = periods & 1;
+      if (in_period == 0) {
+        wait(acc_empty_a + buf * 8, ((periods >> 1) & 1) ^ 1);
+        tc_fence_after();
+      }
+      const bool last_of_period = in_period == kDrainEvery - 1 || k + 1 == my_regions;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        wait(full_a + slot * 8, phase);
+        tc_fence_after();
+        const uint64_t ad = slot == 0 ? adesc[0] : slot == 1 ? adesc[1] : adesc[2];
+        const uint64_t bd = slot == 0 ? bdesc[0] : slot == 1 ? bdesc[1] : bdesc[2];
+        if (elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks)
+            umma_bf16(tmem_base + buf * 64, ad + (ks * 2048) / 16, bd + (ks * 2048) / 16, idesc,
+                      (in_period == 0 && q == 0 && ks == 0) ? 0u : 1u);
+          umma_commit(&empty[slot]);
+          if (q == 3 && last_of_period) umma_commit(&acc_full[buf]);
+        }
+        __syncwarp();
+        if (++slot == kStages) { slot = 0; phase ^= 1u; }
+      }
+      if (++in_period == kDrainEvery) { in_period = 0; ++periods; }
+    }
+  } else {
+    // ------------------------------------------------------------------ B builders (thread = window) + accumulator drain
+    const int w = threadIdx.x, wy = w >> 3, wx = w & 7;
+    constexpr int PRE = (kInRows * kInCols + 127) / 128;
+    int sr[PRE], sq[PRE];
+#pragma unroll
+    for (int j = 0; j < PRE; ++j) {
+      const int i = w + 128 * j;
+      sr[j] = i < kInRows * kInCols ? i / kInCols : -1000000;
+      sq[j] = i - (i / kInCols) * kInCols;
+    }
+    float pf[CIN][PRE];
+    auto fetch = [&](long long region) {
+      int img, ry, rx;
+      decode(region, img, ry, rx);
+#pragma unroll
+      for (int c = 0; c < CIN; ++c) {
+        const float* plane = x + (static_cast<size_t>(img) * c_total + c_offset + c) * H * W;
+#pragma unroll
+        for (int j = 0; j < PRE; ++j) {
+          const int gy = 2 * ry * kWinH - 1 + sr[j], gx = 2 * rx * kWinW - 1 + sq[j];
+          pf[c][j] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? __ldg(plane + static_cast<size_t>(gy) * W + gx) : 0.f;
+        }
+      }
+    };
+    auto drain = [&](int period) {       // TMEM accumulator of `period` -> fp32 totals owned by this thread's channel
+      const int buf = period & 1;
+      wait(acc_full_a + buf * 8, (period >> 1) & 1);
+      tc_fence_after();
+      float* mine = acc_s + w * kAccPitch;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + buf * 64 + h * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mine[h * 32 + i] += __uint_as_float(v[i]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) arrive(acc_empty_a + buf * 8);
+    };
+    if (my_regions > 0) fetch(blockIdx.x);
+    int slot = 0, drained = 0, in_period = 0, periods_done = 0;
+    uint32_t phase = 1;
+    const uint32_t b_row_off = static_cast<uint32_t>(kABytes + (w >> 3) * 1024 + (w & 7) * 128);
+    const uint32_t s_in_a = smem_u32(s_in);
+    for (int k = 0; k < my_regions; ++k) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");                 // everybody has read the previous region's patches
+#pragma unroll
+      for (int c = 0; c < CIN; ++c)
+#pragma unroll
+        for (int j = 0; j < PRE; ++j)
+          if (sr[j] >= 0)
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(s_in_a + static_cast<uint32_t>(((c * kInRows + sr[j]) * kInPitch + sq[j]) * 4)),
+                         "f"(pf[c][j]) : "memory");
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (k + 1 < my_regions) fetch(blockIdx.x + static_cast<long long>(k + 1) * gridDim.x);
+      // this window's 4 x 4 patch per channel as three bf16 terms (bit patterns in the UPPER halves): hi = the top 8
+      // significant bits (truncation), mid = the next 8, lo = the last 8 -- x = hi + mid + lo exactly, four ALU ops per value
+      uint32_t ph[CIN][4][4], pm[CIN][4][4], pl[CIN][4][4];
+#pragma unroll
+      for (int c = 0; c < CIN; ++c)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          float vals[4];
+          const uint32_t ra = s_in_a + static_cast<uint32_t>(((c * kInRows + 2 * wy + r) * kInPitch + 2 * wx) * 4);
+          asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(vals[0]), "=f"(vals[1]) : "r"(ra));
+          asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(vals[2]), "=f"(vals[3]) : "r"(ra + 8));
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint32_t hb = __float_as_uint(vals[i]) & 0xffff0000u;
+            const float r1 = vals[i] - __uint_as_float(hb);
+            const uint32_t mb = __float_as_uint(r1) & 0xffff0000u;
+            ph[c][r][i] = hb; pm[c][r][i] = mb; pl[c][r][i] = __float_as_uint(r1 - __uint_as_float(mb));
+          }
+        }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int dy = q >> 1, dx = q & 1;
+        // row of window w for position q: three planes of T taps (plane stride TP, two taps per 32-bit word), then 1.0
+        uint32_t words[BCHUNKS * 4];
+#pragma unroll
+        for (int i = 0; i < BCHUNKS * 4; ++i) words[i] = 0u;
+#pragma unroll
+        for (int pln = 0; pln < 3; ++pln)
+#pragma unroll
+          for (int t = 0; t < T; t += 2) {
+            auto tap = [&](int tt) -> uint32_t {
+              const int c = tt / 9, ky = (tt % 9) / 3, kx = tt % 3;
+              return pln == 0 ? ph[c][dy + ky][dx + kx] : pln == 1 ? pm[c][dy + ky][dx + kx] : pl[c][dy + ky][dx + kx];
+            };
+            words[(pln * TP + t) >> 1] = t + 1 < T ? __byte_perm(tap(t), tap(t + 1), 0x7632) : (tap(t) >> 16);
+          }
+        words[ONES >> 1] = 0x3f80u;                                      // bf16 1.0 at column ONES (even)
+        wait(empty_a + slot * 8, phase);
+        const uint32_t b_row = stages_a + slot * kStageBytes + b_row_off;
+#pragma unroll
+        for (int ch = 0; ch < BCHUNKS; ++ch)
+          sts128(b_row + ((ch ^ (w & 7)) << 4), words[4 * ch], words[4 * ch + 1], words[4 * ch + 2], words[4 * ch + 3]);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) arrive(full_a + slot * 8);
+        if (++slot == kStages) { slot = 0; phase ^= 1u; }
+      }
+      // one period behind the MMA warp: the accumulator drained here was committed four regions ago
+      if (++in_period == kDrainEvery) {
+        in_period = 0;
+        if (++periods_done >= 2) drain(drained++);
+      }
+    }
+    const int periods_total = (my_regions + kDrainEvery - 1) / kDrainEvery;
+    while (drained < periods_total) drain(drained++);
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    // hi + mid + lo planes -> t1, the ones column -> s1; this CTA's row [COUT * T | COUT] of partial sums
+    if (w < COUT) {
+      float* row = part + static_cast<size_t>(blockIdx.x) * (COUT * T + COUT);
+      const float* mine = acc_s + w * kAccPitch;
+#pragma unroll
+      for (int t = 0; t < T; ++t) row[w * T + t] = (mine[t] + mine[TP + t]) + mine[2 * TP + t];
+      row[COUT * T + w] = mine[ONES];
+    }
+  }
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc<1>(tmem_base, 128);
+  }
+}
+
 // dW[c,t] = scale_c [ T1 - m1 S_t - m2 invstd ((G w_c)[t] - mu S_t) ],  m1 = s1 / count,  m2 = s2 / count with
 // s2[c] = sum dA * xhat = invstd_c (sum_t w[c][t] T1[c][t] - mu_c s1[c]);  sums = [s1 (in) | s2 (out)] = [d beta | d gamma]
 __global__ void first_wgrad_finalize_kernel(const float* __restrict__ t1, const double* __restrict__ gram,
@@ -406,19 +762,36 @@ int ctk_first_wgrad_codes(const float* x, int n, int c_total, int c_offset, int 
   CTK_REQUIRE(x && codes_u32 && dp_bf16 && t1 && sums && n > 0 && H % 2 == 0 && W % 2 == 0);
   CTK_REQUIRE(c_offset >= 0 && c_offset + cin <= c_total);
   cudaStream_t s = ctk::as_stream(stream);
-  const int grid = ctk::num_sms() * 2;
+  // CTK_FIRST_WGRAD=cuda selects the CUDA-core gather (one shared-memory load and one FMA per window, channel and tap);
+  // the default is the tcgen05 formulation (masked-gradient tiles x patch tiles over K = windows)
+  static const bool use_tc = [] { const char* e = getenv("CTK_FIRST_WGRAD"); return !(e && e[0] == 'c'); }();
+  const int grid = use_tc ? ctk::num_sms() : ctk::num_sms() * 2;
   const int T = 9 * cin;
   const int cols = (T + 1) * cout;
   CTK_REQUIRE_WORKSPACE(workspace, workspace_bytes, static_cast<size_t>(grid) * cols * sizeof(float));
+  CTK_REQUIRE((reinterpret_cast<uintptr_t>(dp_bf16) & 15) == 0 && (reinterpret_cast<uintptr_t>(codes_u32) & 3) == 0);
   float* part = static_cast<float*>(workspace);
   const __nv_bfloat16* dp = static_cast<const __nv_bfloat16*>(dp_bf16);
   const uint32_t* cd = static_cast<const uint32_t*>(codes_u32);
-  if (cin == 1 && cout == 64)
-    first_wgrad_codes_kernel<1, 64><<<grid, 256, 0, s>>>(x, n, c_total, c_offset, H, W, cd, dp, slope, part);
-  else if (cin == 2 && cout == 128)
-    first_wgrad_codes_kernel<2, 128><<<grid, 256, 0, s>>>(x, n, c_total, c_offset, H, W, cd, dp, slope, part);
-  else
+  if (cin == 1 && cout == 64) {
+    if (use_tc) {
+      auto kernel = first_wgrad_tc_kernel<1, 64>;
+      CTK_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wtc::smem_bytes(1)));
+      kernel<<<grid, wtc::kThreads, wtc::smem_bytes(1), s>>>(x, n, c_total, c_offset, H, W, cd, dp, slope, part);
+    } else {
+      first_wgrad_codes_kernel<1, 64><<<grid, 256, 0, s>>>(x, n, c_total, c_offset, H, W, cd, dp, slope, part);
+    }
+  } else if (cin == 2 && cout == 128) {
+    if (use_tc) {
+      auto kernel = first_wgrad_tc_kernel<2, 128>;
+      CTK_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wtc::smem_bytes(2)));
+      kernel<<<grid, wtc::kThreads, wtc::smem_bytes(2), s>>>(x, n, c_total, c_offset, H, W, cd, dp, slope, part);
+    } else {
+      first_wgrad_codes_kernel<2, 128><<<grid, 256, 0, s>>>(x, n, c_total, c_offset, H, W, cd, dp, slope, part);
+    }
+  } else {
     return CTK_ERR_UNSUPPORTED;
+  }
   int st = ctk::check_launch();
   if (st != CTK_OK) return st;
   st = ctk::reduce_rows_f32(part, grid, cols, T * cout, t1, s);
