@@ -474,13 +474,14 @@ first_wgrad_tc_kernel(const float* __restrict__ x, int n_img, int c_total, int c
       decode(region, img, ry, rx);
       const int py0 = ry * kWinH + (ws >> 3), px = rx * kWinW + (ws & 7);     // 256 / CH is a multiple of 8: px is shared
       const size_t pix0 = (static_cast<size_t>(img) * Hp + py0) * Wp + px;
+      const uint4* dp_j = reinterpret_cast<const uint4*>(dp + pix0 * COUT + cc * 8);
+      const uint32_t* cd_j = codes + pix0 * CH + cc;
+      const size_t row_step = static_cast<size_t>(32 / CH) * Wp;                  // pooled pixels between this thread's windows
 #pragma unroll
       for (int j = 0; j < AIT; ++j) {
-        const int py = py0 + j * (32 / CH);
-        const bool ok = py < Hp && px < Wp;
-        const size_t pix = ok ? pix0 + static_cast<size_t>(j * (32 / CH)) * Wp : 0;
-        raw[j] = ok ? __ldcs(reinterpret_cast<const uint4*>(dp + pix * COUT + cc * 8)) : make_uint4(0u, 0u, 0u, 0u);
-        cw[j] = ok ? __ldcs(codes + pix * CH + cc) : 0u;
+        const bool ok = py0 + j * (32 / CH) < Hp && px < Wp;
+        raw[j] = ok ? __ldcs(dp_j + j * row_step * (COUT / 8)) : make_uint4(0u, 0u, 0u, 0u);
+        cw[j] = ok ? __ldcs(cd_j + j * row_step * CH) : 0u;
       }
     };
     if (my_regions > 0) load_region(blockIdx.x);
