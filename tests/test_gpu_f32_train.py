@@ -301,8 +301,9 @@ def test_200_step_loss_curve_at_batch_64(kind):
     (unmodified model class + torch.optim.Adam + MSELoss on the CPU, tests/golden/make_loss_curve.py) at batch 64 from a
     256-tile pool is the golden; the same loop re-run with another thread count (only ATen's reduction order changes) tells
     for how many steps the reference reproduces ITSELF to 1 %.  Asserted:
-      fp32 path : over the first 12 steps each step within max(1 %, 4 x the distance between the reference's two runs at that
-                  step), and every 25-step window's geometric-mean loss within 1.5 x the band the reference keeps to itself;
+      fp32 path : every step within 1 % while the reference's two runs agree to 1e-3; over the first 50 steps the distance
+                  to the reference run at most 2 x (median) / 3 x (maximum) the distance between the reference's own two
+                  runs; every 25-step window's geometric-mean loss within 1.5 x the band the reference keeps to itself;
       bf16 path : step 0 within 1 %, every window within the same band widened to at least 25 % -- bf16 operand rounding
                   is a 2^-9 perturbation where a thread count is a 2^-24 one."""
     g = _curve(f"loss_curve_{kind}_b64.json")
@@ -328,13 +329,19 @@ def test_200_step_loss_curve_at_batch_64(kind):
               f"median rel {np.median(rel):.2e}, max {rel.max():.2e}")
         assert rel[0] <= 1e-2
         if other is not None:
-            m = min(len(other), steps, 12)
+            m = min(len(other), steps, 50)
             own_rel = np.abs(other[:m] - ref[:m]) / ref[:m]
-            print("   step: gpu-vs-reference / reference-vs-itself  " + "  ".join(f"{t}: {rel[t]:.1e}/{own_rel[t]:.1e}" for t in range(m)))
+            print("   step: gpu-vs-reference / reference-vs-itself  " +
+                  "  ".join(f"{t}: {rel[t]:.1e}/{own_rel[t]:.1e}" for t in range(min(m, 12))))
+            print(f"   first {m} steps: median {np.median(rel[:m]):.2e} / {np.median(own_rel):.2e}, max {rel[:m].max():.2e} / {own_rel.max():.2e}")
             if precision == "fp32":
-                # step by step the fp32 path may stray from the reference run no further than a small multiple of what the
-                # reference's second run does (both are fp32 summation-order perturbations of the same chaotic trajectory)
-                assert all(rel[t] <= max(1e-2, 4.0 * own_rel[t]) for t in range(m)), (rel[:m], own_rel[:m])
+                # Both the fp32 path and the reference's second run are fp32 summation-order perturbations of the same
+                # trajectory.  Where the reference reproduces itself (to 1e-3) the GPU must be within 1 %; once the
+                # trajectory has gone chaotic, its distance from the reference run may not exceed the reference's own
+                # (2 x the median, 3 x the maximum over the compared steps).
+                assert all(rel[t] <= 1e-2 for t in range(m) if own_rel[t] <= 1e-3), (rel[:m], own_rel[:m])
+                assert np.median(rel[:m]) <= 2.0 * np.median(own_rel) + 1e-2, (np.median(rel[:m]), np.median(own_rel))
+                assert rel[:m].max() <= 3.0 * own_rel.max() + 1e-2, (rel[:m].max(), own_rel.max())
         elif precision == "fp32":
             assert first_bad >= min(agree, steps), (first_bad, agree)
         for a in range(0, steps - 24, 25):
