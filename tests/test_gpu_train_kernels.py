@@ -255,13 +255,15 @@ def test_fc1_training_gemms(L):
     assert rel_l2(dw[0].cpu(), dw_ref) < 1e-3
 
 
+@pytest.mark.parametrize("n,H,W", [(3, 32, 64), (2, 40, 24), (10, 256, 256)])
 @pytest.mark.parametrize("cin,cout,coff", [(1, 64, 1), (1, 64, 0), (2, 128, 0)])
-def test_first_block_gram_path(L, cin, cout, coff):
+def test_first_block_gram_path(L, cin, cout, coff, n, H, W):
     """First block in training without its full-resolution output: patch Gram matrix -> batch moments -> fused
     conv/BN/LeakyReLU/pool, and dW from the recomputed arg-max taps + Gram corrections, against fp32 autograd of
     Conv2d -> BatchNorm2d(train) -> LeakyReLU -> MaxPool2d (regression_model.py:14-17, two_branch_regression.py:10-13)."""
+    # (2, 40, 24): ragged 16 x 8-window regions; (10, 256, 256): nine regions per CTA, i.e. three accumulator periods of the
+    # tcgen05 weight-gradient kernel (its TMEM totals are drained one period behind the MMA warp)
     torch.manual_seed(6)
-    n, H, W = 3, 32, 64
     T = 9 * cin
     x = torch.rand(n, 2, H, W)
     w = (torch.randn(cout, cin, 3, 3) / 3).requires_grad_(True)

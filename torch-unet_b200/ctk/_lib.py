@@ -203,7 +203,7 @@ KERNELS_PER_CALL = {"ctk_pearson_f32": 2, "ctk_tile_metrics_f32": 4, "ctk_tile_n
                     "ctk_bn1d_bwd_reduce": 1, "ctk_bn1d_bwd_apply": 1,
                     "ctk_pack_conv_weight_f32": 1, "ctk_conv3x3_f32": 1, "ctk_conv3x3_wgrad_f32": 2, "ctk_channel_stats_f32": 2,
                     "ctk_bn_finalize_f64": 1, "ctk_bn_act_pool_fwd_f32": 1, "ctk_bn_bwd_reduce_f32": 3,
-                    "ctk_bn_bwd_apply_f32": 1, "ctk_gemm_f32": 1, "ctk_dropout_masks": 1, "ctk_scale_by_scalar": 1}
+                    "ctk_bn_bwd_apply_f32": 1, "ctk_gemm_f32": 1}
 launch_count = 0
 _timeline = None      # when a list: (name, start_event, end_event, meta) per call, for per-kernel timing in bench.py
 _timeline_only = None # optional set of entry points to instrument (events around every call cost ~2 us each)

@@ -12,7 +12,7 @@ identical steps are bit-identical.  About 1/20 of the tensor-core path's through
 from __future__ import annotations
 
 from ctypes import c_double, c_float, c_int, c_longlong
-from typing import Dict, List, Tuple
+from typing import Dict, Tuple
 
 import torch
 
