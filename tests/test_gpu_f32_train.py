@@ -301,7 +301,7 @@ def test_200_step_loss_curve_at_batch_64(kind):
     (unmodified model class + torch.optim.Adam + MSELoss on the CPU, tests/golden/make_loss_curve.py) at batch 64 from a
     256-tile pool is the golden; the same loop re-run with another thread count (only ATen's reduction order changes) tells
     for how many steps the reference reproduces ITSELF to 1 %.  Asserted:
-      fp32 path : every step within 1 % while the reference's two runs agree to 1e-3; over the first 50 steps the distance
+      fp32 path : every step within 1 % until the reference's two runs first differ by 1e-3; over the first 50 steps the distance
                   to the reference run at most 2 x (median) / 3 x (maximum) the distance between the reference's own two
                   runs; every 25-step window's geometric-mean loss within 1.5 x the band the reference keeps to itself;
       bf16 path : step 0 within 1 %, every window within the same band widened to at least 25 % -- bf16 operand rounding
@@ -339,7 +339,8 @@ def test_200_step_loss_curve_at_batch_64(kind):
                 # trajectory.  Where the reference reproduces itself (to 1e-3) the GPU must be within 1 %; once the
                 # trajectory has gone chaotic, its distance from the reference run may not exceed the reference's own
                 # (2 x the median, 3 x the maximum over the compared steps).
-                assert all(rel[t] <= 1e-2 for t in range(m) if own_rel[t] <= 1e-3), (rel[:m], own_rel[:m])
+                prefix = int(np.argmax(own_rel > 1e-3)) if (own_rel > 1e-3).any() else m      # steps before the reference first strays
+                assert (rel[:prefix] <= 1e-2).all(), (prefix, rel[:prefix], own_rel[:prefix])
                 assert np.median(rel[:m]) <= 2.0 * np.median(own_rel) + 1e-2, (np.median(rel[:m]), np.median(own_rel))
                 assert rel[:m].max() <= 3.0 * own_rel.max() + 1e-2, (rel[:m].max(), own_rel.max())
         elif precision == "fp32":

@@ -332,7 +332,10 @@ def test_first_block_gram_path(L, cin, cout, coff, n, H, W):
     np.testing.assert_allclose(rmd.cpu().numpy(), rm.numpy(), rtol=1e-4, atol=1e-6)
     np.testing.assert_allclose(rvd.cpu().numpy(), rv.numpy(), rtol=1e-4, atol=1e-6)
     assert rel_l2(out.float().cpu(), pooled.detach().permute(0, 2, 3, 1)) < 4e-3
-    np.testing.assert_allclose(sums[:cout].cpu().numpy(), beta.grad.numpy(), rtol=1e-3, atol=1e-3)
-    np.testing.assert_allclose(sums[cout:].cpu().numpy(), gamma.grad.numpy(), rtol=1e-3, atol=2e-3)
+    # sums of n*Hp*Wp random terms: the negative-side gradients are slope * dP rounded to bf16 (2^-9 of 1 % of the terms),
+    # an absolute error that grows like the square root of the window count
+    noise = 2e-5 * float(n * (H // 2) * (W // 2)) ** 0.5
+    np.testing.assert_allclose(sums[:cout].cpu().numpy(), beta.grad.numpy(), rtol=1e-3, atol=1e-3 + noise)
+    np.testing.assert_allclose(sums[cout:].cpu().numpy(), gamma.grad.numpy(), rtol=1e-3, atol=2e-3 + 2 * noise)
     # dW is a small difference of large terms (BN removes the mean and the xhat component of the gradient)
     assert rel_l2(dw.cpu(), w.grad) < 2e-3

@@ -352,7 +352,7 @@ bn_bwd_apply_kernel(const uint4* __restrict__ y, const __nv_bfloat16* __restrict
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        dy[base[u] + ((j >> 1) * W + (j & 1)) * static_cast<long long>(c8)] = make_uint4(o[j][0], o[j][1], o[j][2], o[j][3]);
+        __stcs(dy + base[u] + ((j >> 1) * W + (j & 1)) * static_cast<long long>(c8), make_uint4(o[j][0], o[j][1], o[j][2], o[j][3]));
     }
   }
 }
