@@ -355,7 +355,11 @@ constexpr int kStages = 3;
 constexpr int kABytes = 32768, kBBytes = 16384, kStageBytes = kABytes + kBBytes;
 constexpr int kAccPitch = 65;                        // fp32 totals [128 channels][64 columns], conflict-free rows
 constexpr int kInRows = 2 * kWinH + 2, kInCols = 2 * kWinW + 2, kInPitch = 24;
-constexpr int kThreads = 13 * 32;                    // warps 0-3 B builders + drain, 4 MMA, 5-12 A builders
+// warps 0-3 B builders + drain, warp 4 MMA, then 8 A-builder warps.  (16 A-builder warps for Cout = 64 -- two chunks per
+// thread, 80 registers -- were measured SLOWER: 1.49 ms against 1.02 ms per step; the builders are bound by issue slots, not
+// by the number of warps hiding latency.)
+constexpr int a_warps(int) { return 8; }
+constexpr int threads(int cout) { return (5 + a_warps(cout)) * 32; }
 constexpr int kDrainEvery = 4;                       // regions per accumulation period
 constexpr int smem_bytes(int cin) {
   return 1024 + kStages * kStageBytes + 128 * kAccPitch * 4 + cin * kInRows * kInPitch * 4 + 256;
@@ -401,7 +405,7 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, ui
 }  // namespace wtc
 
 template <int CIN, int COUT>
-__global__ void __launch_bounds__(wtc::kThreads, 1)
+__global__ void __launch_bounds__(wtc::threads(COUT), 1)
 first_wgrad_tc_kernel(const float* __restrict__ x, int n_img, int c_total, int c_offset, int H, int W,
                       const uint32_t* __restrict__ codes, const __nv_bfloat16* __restrict__ dp, float slope,
                       float* __restrict__ part) {
@@ -412,7 +416,10 @@ first_wgrad_tc_kernel(const float* __restrict__ x, int n_img, int c_total, int c
   constexpr int BWORDS = ONES / 2 + 1;                // 32-bit words of a B row that are ever non-zero
   constexpr int BCHUNKS = (BWORDS + 3) / 4;
   constexpr int CH = COUT / 8;                        // 16-byte chunks (8 channels) per window
-  constexpr int AIT = 128 * CH / 256;                 // chunks per A-builder thread and variant
+  constexpr int NAT = a_warps(COUT) * 32;             // A-builder threads
+  constexpr int kThreads = threads(COUT);
+  constexpr int AIT = 128 * CH / NAT;                 // chunks per A-builder thread and variant
+  constexpr int WSTEP = NAT / CH;                     // windows between a thread's chunks (a multiple of 8: whole rows)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stages = smem;
@@ -427,7 +434,7 @@ first_wgrad_tc_kernel(const float* __restrict__ x, int n_img, int c_total, int c
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 12); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], a_warps(COUT) + 4); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
     fence_mbar_init();
   }
@@ -460,11 +467,11 @@ first_wgrad_tc_kernel(const float* __restrict__ x, int n_img, int c_total, int c
     const int tp = threadIdx.x - 160;
     const int cc = tp % CH, ws = tp / CH;
     const uint32_t one_b = 0x3f80u, slope_b = bf16_bits(slope);
-    // chunk j of this thread: window ws + j * (256 / CH); its byte offset inside an A tile never changes
+    // chunk j of this thread: window ws + j * WSTEP; its byte offset inside an A tile never changes
     uint32_t a_off[AIT];
 #pragma unroll
     for (int j = 0; j < AIT; ++j) {
-      const int w = ws + j * (256 / CH), row = w & 7;
+      const int w = ws + j * WSTEP, row = w & 7;
       a_off[j] = static_cast<uint32_t>((cc >> 3) * 16384 + (w >> 3) * 1024 + row * 128 + (((cc & 7) ^ row) << 4));
     }
     uint4 raw[AIT];
@@ -472,14 +479,14 @@ first_wgrad_tc_kernel(const float* __restrict__ x, int n_img, int c_total, int c
     auto load_region = [&](long long region) {
       int img, ry, rx;
       decode(region, img, ry, rx);
-      const int py0 = ry * kWinH + (ws >> 3), px = rx * kWinW + (ws & 7);     // 256 / CH is a multiple of 8: px is shared
+      const int py0 = ry * kWinH + (ws >> 3), px = rx * kWinW + (ws & 7);     // WSTEP is a multiple of 8: px is shared
       const size_t pix0 = (static_cast<size_t>(img) * Hp + py0) * Wp + px;
       const uint4* dp_j = reinterpret_cast<const uint4*>(dp + pix0 * COUT + cc * 8);
       const uint32_t* cd_j = codes + pix0 * CH + cc;
-      const size_t row_step = static_cast<size_t>(32 / CH) * Wp;                  // pooled pixels between this thread's windows
+      const size_t row_step = static_cast<size_t>(WSTEP / 8) * Wp;                // pooled pixels between this thread's windows
 #pragma unroll
       for (int j = 0; j < AIT; ++j) {
-        const bool ok = py0 + j * (32 / CH) < Hp && px < Wp;
+        const bool ok = py0 + j * (WSTEP / 8) < Hp && px < Wp;
         raw[j] = ok ? __ldcs(dp_j + j * row_step * (COUT / 8)) : make_uint4(0u, 0u, 0u, 0u);
         cw[j] = ok ? __ldcs(cd_j + j * row_step * CH) : 0u;
       }
@@ -778,7 +785,7 @@ int ctk_first_wgrad_codes(const float* x, int n, int c_total, int c_offset, int 
     if (use_tc) {
       auto kernel = first_wgrad_tc_kernel<1, 64>;
       CTK_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wtc::smem_bytes(1)));
-      kernel<<<grid, wtc::kThreads, wtc::smem_bytes(1), s>>>(x, n, c_total, c_offset, H, W, cd, dp, slope, part);
+      kernel<<<grid, wtc::threads(64), wtc::smem_bytes(1), s>>>(x, n, c_total, c_offset, H, W, cd, dp, slope, part);
     } else {
       first_wgrad_codes_kernel<1, 64><<<grid, 256, 0, s>>>(x, n, c_total, c_offset, H, W, cd, dp, slope, part);
     }
@@ -786,7 +793,7 @@ int ctk_first_wgrad_codes(const float* x, int n, int c_total, int c_offset, int 
     if (use_tc) {
       auto kernel = first_wgrad_tc_kernel<2, 128>;
       CTK_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wtc::smem_bytes(2)));
-      kernel<<<grid, wtc::kThreads, wtc::smem_bytes(2), s>>>(x, n, c_total, c_offset, H, W, cd, dp, slope, part);
+      kernel<<<grid, wtc::threads(128), wtc::smem_bytes(2), s>>>(x, n, c_total, c_offset, H, W, cd, dp, slope, part);
     } else {
       first_wgrad_codes_kernel<2, 128><<<grid, 256, 0, s>>>(x, n, c_total, c_offset, H, W, cd, dp, slope, part);
     }
