@@ -295,6 +295,12 @@ def _run_curve(kind, g, precision, steps):
     return np.array(losses)
 
 
+# 25-step geometric-mean windows, gpu / reference.  Measured on B200: double-branch 0.990 - 1.002 (fp32 path) and 0.975 - 0.987
+# (bf16 path); the single-branch trajectory is chaotic from step 2 on (its loss jumps from 0.16 to 1.43 at step 1, and the
+# reference's own second run differs from its first by 25 % at single steps), so its floor is wider.
+WINDOW_BAND = {"double": {"fp32": 1.03, "bf16": 1.08}, "single": {"fp32": 1.10, "bf16": 1.25}}
+
+
 @pytest.mark.parametrize("kind", ["double", "single"])
 def test_200_step_loss_curve_at_batch_64(kind):
     """north_star: "the loss curve over the first 200 steps matching within 1 % relative".  The reference's own loop
@@ -303,9 +309,10 @@ def test_200_step_loss_curve_at_batch_64(kind):
     for how many steps the reference reproduces ITSELF to 1 %.  Asserted:
       fp32 path : every step within 1 % until the reference's two runs first differ by 1e-3; over the first 50 steps the distance
                   to the reference run at most 2 x (median) / 3 x (maximum) the distance between the reference's own two
-                  runs; every 25-step window's geometric-mean loss within 1.5 x the band the reference keeps to itself;
-      bf16 path : step 0 within 1 %, every window within the same band widened to at least 25 % -- bf16 operand rounding
-                  is a 2^-9 perturbation where a thread count is a 2^-24 one."""
+                  runs; every 25-step window's geometric-mean loss within WINDOW_BAND (3 % double-branch, 10 % single) or
+                  1.5 x the band the reference keeps to itself, whichever is wider;
+      bf16 path : step 0 within 1 %, every window within 8 % (double) / 25 % (single) or that same reference band --
+                  bf16 operand rounding is a 2^-9 perturbation where a thread count is a 2^-24 one."""
     g = _curve(f"loss_curve_{kind}_b64.json")
     if g is None:
         pytest.skip("golden curve not generated")
@@ -320,7 +327,11 @@ def test_200_step_loss_curve_at_batch_64(kind):
         agree = max(2, int(bad[0]) if len(bad) else m)
     print(f"{kind}: golden has {steps} steps; the reference's two runs agree to 1 % for {agree} steps")
     gm = lambda v, a: float(np.exp(np.log(v[a:a + 25]).mean()))         # noqa: E731
+    all_steps, all_ref = steps, ref
     for precision in ("fp32", "bf16"):
+        # the fp32 path (CUDA cores, ~0.4 s per batch-64 step) is run for the first 100 steps, the bf16 path for all of them
+        steps = min(all_steps, 100) if precision == "fp32" else all_steps
+        ref = all_ref[:steps]
         gpu = _run_curve(kind, g, precision, steps)
         assert np.isfinite(gpu).all()
         rel = np.abs(gpu - ref) / ref
@@ -348,7 +359,7 @@ def test_200_step_loss_curve_at_batch_64(kind):
         for a in range(0, steps - 24, 25):
             r_, g_ = gm(ref, a), gm(gpu, a)
             own = max(gm(other, a) / r_, r_ / gm(other, a)) if other is not None and a + 25 <= len(other) else 1.0
-            band = max(1.10 if precision == "fp32" else 1.25, 1.0 + 1.5 * (own - 1.0))
+            band = max(WINDOW_BAND[kind][precision], 1.0 + 1.5 * (own - 1.0))
             print(f"   window {a:3d}: reference {r_:.5f} gpu {g_:.5f} ratio {g_ / r_:.4f} (reference vs itself {own:.4f}, band {band:.3f})")
             assert 1.0 / band <= g_ / r_ <= band, (precision, a, g_, r_, band)
         assert gpu[-10:].mean() < 0.5 * gpu[0]                  # and it trained
