@@ -599,6 +599,14 @@ def measure_infer(args, steps, warmup):
                         "ms_per_step": e2e_ms / e2e_steps,
                         "api": "ctk.HostScorer.score_stream(pinned host batches) -> host scores + Pearson r per batch "
                                "(one batch of look-ahead; every step's H2D and D2H inside the timed region)"}}
+        # the host's measured pinned-H2D ceiling with `world` ranks copying at once (tools/probe_h2d_ranks.py), if committed
+        ceil_path = os.path.join(ROOT, "profiles", f"r2_h2d_ranks_{world}.json")
+        if os.path.exists(ceil_path):
+            ceiling = json.load(open(ceil_path)).get("tiles_per_s_ceiling_together")
+            if ceiling:
+                line["e2e"]["host_h2d_ceiling_tiles_per_s"] = ceiling
+                line["e2e"]["fraction_of_host_h2d_ceiling"] = line["e2e"]["value"] / ceiling
+                line["e2e"]["host_h2d_ceiling_source"] = os.path.join("profiles", f"r2_h2d_ranks_{world}.json")
     del model, engine, dev_batches, scorer
     torch.cuda.empty_cache()
     return line
