@@ -281,10 +281,12 @@ def _max_over_ranks(vals, dev, world):
     return t.tolist()
 
 
-def _timeline_table(timeline, denom):
+def _timeline_table(timeline, denom, by_role=False):
+    """Per entry point (by_role: per (entry point, meta['role'])): summed CUDA-event time, launches, algorithmic FLOP."""
     per = {}
     for name, a, b, meta in timeline:
-        d = per.setdefault(name, {"ms": 0.0, "n": 0, "flops": 0.0})
+        key = f"{name}:{(meta or {}).get('role', '')}" if by_role else name
+        d = per.setdefault(key, {"ms": 0.0, "n": 0, "flops": 0.0})
         d["ms"] += a.elapsed_time(b)
         d["n"] += 1
         d["flops"] += (meta or {}).get("flops", 0.0)
@@ -316,6 +318,10 @@ def measure_train(args, kind, steps, warmup, with_scheduler=False):
     model = build_model(kind, dev).train()
     eng = ctk.models.get_train_engine(model)
     eng.overlap_streams = bool(getattr(args, "overlap_streams", False))
+    if getattr(args, "no_overlap_wgrad", False):
+        eng.overlap_wgrad = False
+    concurrent_backward = eng.overlap_wgrad or eng.overlap_streams
+    eng_overlap_wgrad = eng.overlap_wgrad and not eng.overlap_streams
     sync = None
     if world > 1:
         ctk.parallel.broadcast_parameters(model)
@@ -384,9 +390,17 @@ def measure_train(args, kind, steps, warmup, with_scheduler=False):
         pk = peaks()
         per = _timeline_table(timeline, steps)
         per_all = _timeline_table(detail, 2)
-        conv = per.get("ctk_conv3x3_tc_raw", {"ms": 0.0, "n": 0, "flops": 0.0})
-        wg = per.get("ctk_conv3x3_wgrad_tc", {"ms": 0.0, "n": 0, "flops": 0.0})
+        zero = {"ms": 0.0, "n": 0, "flops": 0.0}
+        roles = _timeline_table(timeline, steps, by_role=True)
+        conv_fwd, conv_dg = roles.get("ctk_conv3x3_tc_raw:fwd", zero), roles.get("ctk_conv3x3_tc_raw:dgrad", zero)
+        # With the weight gradients on their own stream the dgrad launches share the GPU with them: CUDA events around such a
+        # launch also count the time its CTAs wait for SMs the previous wgrad still holds.  The kernel's roofline is then taken
+        # from the launches that own the GPU while they run -- the train-mode forward ones (same kernel template, the heavier
+        # raw+stats epilogue); the dgrad launches are reported beside it as measured.
+        conv = conv_fwd if concurrent_backward else per.get("ctk_conv3x3_tc_raw", zero)
+        wg = per.get("ctk_conv3x3_wgrad_tc", zero)
         conv_tf = conv["flops"] / (conv["ms"] / 1e3) / 1e12 if conv["ms"] > 0 else 0.0
+        dg_tf = conv_dg["flops"] / (conv_dg["ms"] / 1e3) / 1e12 if conv_dg["ms"] > 0 else 0.0
         wg_tf = wg["flops"] / (wg["ms"] / 1e3) / 1e12 if wg["ms"] > 0 else 0.0
         traffic, traffic_src = ncu_dram_traffic("conv3x3_tc_kernel", ("r2_train_full_raw.csv",))
         value = world * batch * steps / (ms / 1e3)
@@ -403,7 +417,9 @@ def measure_train(args, kind, steps, warmup, with_scheduler=False):
                        "lr_schedule": f"ctk.CosineWarmupLR, epoch 0 (lr {opt.param_groups[0]['lr']:.1e})" if sched is not None else "constant 5e-4 (what the reference's cosine_warmup amounts to, SURVEY D6)",
                        "weights": "seed-0 random init", "dropout": "libctk Philox keep-masks", "loss": "ctk.MSELoss"},
             "whole_net_tflops": value * GFLOP_TRAIN[kind] / 1e3,
-            "roofline": {"kernel": "conv3x3_tc_kernel (raw+stats forward and dgrad launches)", "bound": "tensor",
+            "roofline": {"kernel": ("conv3x3_tc_kernel (raw+stats forward launches; the dgrad launches run beside the weight "
+                                    "gradients and are listed under dgrad_launches)") if concurrent_backward
+                                   else "conv3x3_tc_kernel (raw+stats forward and dgrad launches)", "bound": "tensor",
                          "achieved": conv_tf, "peak": pk["bf16_tflops_burst"], "unit": "TFLOP/s",
                          "frac": conv_tf / pk["bf16_tflops_burst"], "traffic": traffic,
                          "traffic_unit": "DRAM bytes per launch (ncu --set full, mean over the launches of a step)",
@@ -414,6 +430,12 @@ def measure_train(args, kind, steps, warmup, with_scheduler=False):
                          "algorithmic_flop_per_launch": conv["flops"] / max(1, conv["n"]),
                          "avg_launch_ms": conv["ms"] / max(1, conv["n"]), "launches": conv["n"],
                          "share_of_step": conv["ms"] / ms if ms > 0 else None,
+                         "dgrad_launches": {"achieved": dg_tf, "avg_launch_ms": conv_dg["ms"] / max(1, conv_dg["n"]),
+                                            "launches": conv_dg["n"],
+                                            "concurrent_with": "wgrad_tc_kernel on the weight-gradient stream" if concurrent_backward else None},
+                         "backward_schedule": ("weight gradients on a high-priority side stream behind each layer's dgrad, "
+                                               "beside the next layer's BatchNorm-backward passes (TrainEngine.overlap_wgrad)")
+                                              if eng_overlap_wgrad else "single stream",
                          "wgrad_tc_kernel": {"achieved": wg_tf, "frac": wg_tf / pk["bf16_tflops_burst"],
                                              "avg_launch_ms": wg["ms"] / max(1, wg["n"]), "launches": wg["n"],
                                              "share_of_step": wg["ms"] / ms if ms > 0 else None},
@@ -707,6 +729,8 @@ def main():
     ap.add_argument("--model", default="double", choices=["double", "single"])
     ap.add_argument("--overlap-streams", action="store_true",
                     help="training, EXPERIMENTAL: branches and weight gradients on side streams (measured: no gain)")
+    ap.add_argument("--no-overlap-wgrad", action="store_true",
+                    help="training: single-stream backward (A/B against the default deferred weight-gradient stream)")
     ap.add_argument("--batch", type=int, default=BATCH, help="per-GPU batch (training)")
     ap.add_argument("--tiles", type=int, default=1_000_000, help="sweep mode: total tiles over all ranks")
     args = ap.parse_args()

@@ -9,6 +9,7 @@ runs unchanged; PyTorch only owns the tensors and the graph edge.
 from __future__ import annotations
 
 import contextlib
+import os
 from ctypes import c_double, c_float, c_int, c_longlong, c_size_t, c_ulonglong
 from typing import Callable, Dict, List, Optional, Tuple
 
@@ -66,6 +67,12 @@ class TrainEngine:
         # further side stream, so that the HBM-bound BatchNorm passes of one branch / layer overlap the tensor-bound conv
         # kernels of the other.  Off by default; see DESIGN.md section 8.
         self.overlap_streams: bool = False
+        # Weight gradients on ONE high-priority side stream, each started when the input gradient of ITS layer has been
+        # enqueued: wgrad_tc_kernel (192 threads x 48 registers, 166 KB of shared memory, one CTA per SM) leaves most of an
+        # SM's register file free, so the HBM-bound BatchNorm-backward passes of the next layer down -- the critical path --
+        # run on the same SMs at the same time instead of after it.  Nothing in backward reads a weight gradient, so only
+        # the end of backward waits for the side stream.  CTK_OVERLAP_WGRAD=0 restores the single-stream schedule.
+        self.overlap_wgrad: bool = os.environ.get("CTK_OVERLAP_WGRAD", "1") != "0"
         # data parallel: SMs the persistent tensor-core kernels of the BACKWARD pass leave free for the gradient all-reduce
         # that runs beside them (parallel.attach sets it; 0 = fill the GPU, the single-GPU setting)
         self.backward_sm_reserve: int = 0
@@ -79,7 +86,9 @@ class TrainEngine:
         key = (kind, index, dev.index if dev.index is not None else torch.cuda.current_device())
         st = self._streams.get(key)
         if st is None:
-            st = self._streams[key] = torch.cuda.Stream(device=dev)
+            # the weight-gradient stream outranks the default stream: its one-CTA-per-SM kernels take their SMs first and the
+            # streaming passes fill in beside them
+            st = self._streams[key] = torch.cuda.Stream(device=dev, priority=-1 if kind == "wgrad" else 0)
         return st
 
     @staticmethod
@@ -139,7 +148,49 @@ class TrainEngine:
         call("ctk_colstat", ptr(t), c_int(1), c_longlong(0), c_int(f), ptr(None), c_int(n), c_int(f), ptr(None), ptr(st), stream())
         return st[:f]
 
-    def _forward_branch(self, br, x: torch.Tensor, feat: torch.Tensor, c_off: int) -> List[dict]:
+    def _pack_weights(self, dev, main: torch.cuda.Stream) -> dict:
+        """bf16 operand copies of the weights for this step -- every tensor-core conv's forward and input-gradient layouts
+        and FC1's column-permuted matrix -- built on a side stream at the start of the forward pass, so that the 0.3 ms
+        they take (FC1: 805 MB of traffic) run beside the first block instead of on the critical path.  The compute stream
+        waits for ``conv_ready`` before its first tensor-core conv and for ``fc1_ready`` before the FC1 GEMM."""
+        side = self._side_stream("pack", 0, dev) if self.overlap_wgrad else None
+        packs = {"conv": {}, "conv_ready": None, "fc1_ready": None}
+        if side is not None:
+            start = torch.cuda.Event()
+            start.record(main)                  # the parameters are final behind this point (e.g. the optimizer's update)
+            side.wait_event(start)
+        with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
+            for br in self.branches:
+                for li, (conv, _) in enumerate(br.pairs):
+                    if li == 0:
+                        continue
+                    cout, cin = conv.out_channels, conv.in_channels
+                    wp = self._new((9, cout, cin), torch.bfloat16, dev)
+                    call("ctk_pack_conv_weight_bf16", ptr(conv.weight), c_int(cout), c_int(cin), ptr(wp), stream())
+                    wg = self._new((9, cin, cout), torch.bfloat16, dev)
+                    call("ctk_pack_conv_weight_dgrad_bf16", ptr(conv.weight), c_int(cout), c_int(cin), ptr(wg), stream())
+                    packs["conv"][conv] = (wp, wg)
+            if side is not None:
+                packs["conv_ready"] = torch.cuda.Event()
+                packs["conv_ready"].record(side)
+            fc1 = self.lin[0]
+            hw = fc1.in_features // self.feat_channels
+            w1p = self._new((fc1.out_features, fc1.in_features), torch.bfloat16, dev)
+            call("ctk_pack_fc1_weight_bf16", ptr(fc1.weight), c_int(fc1.out_features), c_int(self.feat_channels), c_int(hw),
+                 ptr(w1p), stream())
+            packs["w1p"] = w1p
+            if side is not None:
+                packs["fc1_ready"] = torch.cuda.Event()
+                packs["fc1_ready"].record(side)
+        if side is not None:
+            # allocated on the side stream, read on the compute stream until the end of backward
+            for wp, wg in packs["conv"].values():
+                wp.record_stream(main)
+                wg.record_stream(main)
+            packs["w1p"].record_stream(main)
+        return packs
+
+    def _forward_branch(self, br, x: torch.Tensor, feat: torch.Tensor, c_off: int, packs: dict) -> List[dict]:
         """Conv stack of one branch on the CURRENT stream; the last block writes its channel range of ``feat``."""
         n, c_total, H, W = x.shape
         dev = x.device
@@ -186,18 +237,19 @@ class TrainEngine:
                 call("ctk_conv_first_raw", ptr(x), c_int(n), c_int(c_total), c_int(br.c_offset), c_int(cin), c_int(h),
                      c_int(w), ptr(conv.weight), c_int(cout), ptr(y), ptr(stats), ws[1], ws[2], stream())
             else:
-                wp = self._new((9, cout, cin), torch.bfloat16, dev)
-                call("ctk_pack_conv_weight_bf16", ptr(conv.weight), c_int(cout), c_int(cin), ptr(wp), stream())
+                wp = packs["conv"][conv][0]
+                if packs["conv_ready"] is not None:
+                    torch.cuda.current_stream(dev).wait_event(packs["conv_ready"])
                 ws = workspace("ctk_conv3x3_tc_raw_workspace_bytes", cout, device=dev)
                 call("ctk_conv3x3_tc_raw", ptr(cur), c_int(n), c_int(h), c_int(w), c_int(cin), ptr(wp), c_int(cout),
                      ptr(y), ptr(stats), ws[1], ws[2], stream(),
-                     meta={"flops": 2.0 * n * h * w * cout * 9 * cin, "kernels": 2})
+                     meta={"flops": 2.0 * n * h * w * cout * 9 * cin, "kernels": 2, "role": "fwd"})
             self._sync_stats(stats)
             scale, shift, mean, invstd = self._bn_finalize(stats, float(n) * h * w * self.stat_world, conv.bias, bn, dev)
             call("ctk_bn_act_pool_fwd", ptr(y), c_int(n), c_int(h), c_int(w), c_int(cout), ptr(scale), ptr(shift),
                  c_float(LEAKY_SLOPE), ptr(dst), c_int(cstride), c_int(coff), stream())
             blocks.append({"y": y, "x_in": cur, "pooled": (dst, cstride, coff), "scale": scale, "shift": shift, "mean": mean, "invstd": invstd,
-                           "h": h, "w": w, "conv": conv, "bn": bn})
+                           "h": h, "w": w, "conv": conv, "bn": bn, "w_dgrad": packs["conv"][conv][1] if li > 0 else None})
             cur = dst
             h, w = h // 2, w // 2
         return blocks
@@ -232,6 +284,7 @@ class TrainEngine:
         feat = self._padded((m_pad, hf, wf, self.feat_channels), n, m_pad, dev)
         c_off = 0
         main = torch.cuda.current_stream(dev)
+        packs = self._pack_weights(dev, main)
         overlap = self.overlap_streams and len(self.branches) > 1
         used_streams = []
         if overlap:
@@ -243,9 +296,9 @@ class TrainEngine:
                 side.wait_event(fork)
                 used_streams.append(side)
                 with torch.cuda.stream(side):
-                    blocks = self._forward_branch(br, x, feat, c_off)
+                    blocks = self._forward_branch(br, x, feat, c_off, packs)
             else:
-                blocks = self._forward_branch(br, x, feat, c_off)
+                blocks = self._forward_branch(br, x, feat, c_off, packs)
             sv["blocks"].append({"branch": br, "blocks": blocks, "c_off": c_off})
             c_off += br.channels[-1]
         if overlap:
@@ -255,8 +308,9 @@ class TrainEngine:
         # ---- FC1 (tcgen05 split-K) + fp32 head
         f1, f2 = fc1.out_features, fc2.out_features
         hw = hf * wf
-        w1p = self._new((f1, K), torch.bfloat16, dev)
-        call("ctk_pack_fc1_weight_bf16", ptr(fc1.weight), c_int(f1), c_int(self.feat_channels), c_int(hw), ptr(w1p), stream())
+        w1p = packs["w1p"]
+        if packs["fc1_ready"] is not None:
+            main.wait_event(packs["fc1_ready"])
         tiles = (m_pad // 128) * (f1 // 128)
         splits = 1
         while splits * 2 * tiles <= 160 and (K // 64) % (splits * 2) == 0 and K // (splits * 2) >= 512:
@@ -319,44 +373,71 @@ class TrainEngine:
         self._dropout_calls += 1
         return (m1, m2)
 
-    def _backward_branch(self, entry: dict, sv: dict, dfeat: torch.Tensor, done, wgrad_stream=None) -> None:
-        """Backward of one branch's conv stack (last block first) on the CURRENT stream."""
+    def _backward_branch(self, entry: dict, sv: dict, dfeat: torch.Tensor, done, wgrad_stream=None,
+                         defer_wgrad: bool = False) -> None:
+        """Backward of one branch's conv stack (last block first) on the CURRENT stream.
+
+        ``wgrad_stream``: weight gradients go to that stream.  ``defer_wgrad`` picks the order: False (the
+        ``overlap_streams`` experiment) forks right behind the BatchNorm backward of the layer, True (``overlap_wgrad``)
+        forks behind the layer's INPUT gradient, so that the weight gradient runs beside the next layer's BatchNorm passes
+        instead of competing with the dgrad kernel for whole SMs."""
         x, n = sv["x"], sv["n"]
         dev = x.device
         br, blocks = entry["branch"], entry["blocks"]
         dp, dp_cstride, dp_coff = dfeat, self.feat_channels, entry["c_off"]
+
+        def fork(*read_on_side):
+            """Context of the weight-gradient stream, ordered behind everything enqueued so far on the current one; the
+            tensors it reads were allocated on the current stream, so the allocator must not recycle them before the side
+            stream is done with them."""
+            if wgrad_stream is None:
+                return contextlib.nullcontext()
+            ready = torch.cuda.Event()
+            ready.record()
+            wgrad_stream.wait_event(ready)
+            for t in read_on_side:
+                if t is not None:
+                    t.record_stream(wgrad_stream)
+            return torch.cuda.stream(wgrad_stream)
+
         for li in range(len(blocks) - 1, -1, -1):
             b = blocks[li]
             conv, bn, h, w = b["conv"], b["bn"], b["h"], b["w"]
             cout, cin = conv.out_channels, conv.in_channels
-            sums = self._new((2 * cout,), torch.float32, dev)
             if b.get("gram") is not None:
                 # first block: the forward pass stored arg-max / sign codes, so the data term of the weight gradient and
                 # sum(dA) are one gather over the input; sum(dA * xhat) follows from them in the finalize kernel
                 if dp_cstride != cout or dp_coff != 0:
                     raise _lib.CtkError("the first block's output gradient must be dense")
                 T = 9 * cin
-                t1 = self._new((cout, T), torch.float32, dev)
-                ws = workspace("ctk_first_wgrad_codes_workspace_bytes", cin, cout, device=dev)
-                call("ctk_first_wgrad_codes", ptr(x), c_int(n), c_int(x.shape[1]), c_int(br.c_offset), c_int(cin), c_int(h),
-                     c_int(w), ptr(b["codes"]), ptr(dp), c_int(cout), c_float(LEAKY_SLOPE), ptr(t1), ptr(sums), ws[1], ws[2],
-                     stream())
-                dw = self._new(tuple(conv.weight.shape), torch.float32, dev)
-                # SyncBN: the saved Gram matrix is already the global one, so reduce t1 / sum(dA) too and form the
-                # global gradient on every rank; dividing by the world size makes the exchange's mean leave it as is
-                self._sync_stats(t1)
-                self._sync_stats(sums)
-                call("ctk_first_wgrad_finalize", ptr(t1), ptr(b["gram"]), ptr(conv.weight), ptr(b["scale"]), ptr(b["mean"]),
-                     ptr(b["invstd"]), ptr(sums), c_double(float(n) * h * w * self.stat_world), c_int(cout), c_int(cin),
-                     ptr(dw), stream())
-                if self.stat_world > 1:
-                    dw.div_(self.stat_world)
-                    sums.div_(self.stat_world)
-                done(bn.bias, sums[:cout])
-                done(bn.weight, sums[cout:])
-                done(conv.weight, dw)
+                # nothing downstream reads these gradients: with deferred weight gradients the whole first block goes to
+                # the side stream (not under SyncBN, whose blocking statistics all-reduces belong on the compute stream)
+                side = defer_wgrad and self.stat_allreduce is None
+                with (fork(dp, b["codes"], b["gram"], b["scale"], b["mean"], b["invstd"]) if side
+                      else contextlib.nullcontext()):
+                    sums = self._new((2 * cout,), torch.float32, dev)
+                    t1 = self._new((cout, T), torch.float32, dev)
+                    ws = workspace("ctk_first_wgrad_codes_workspace_bytes", cin, cout, device=dev)
+                    call("ctk_first_wgrad_codes", ptr(x), c_int(n), c_int(x.shape[1]), c_int(br.c_offset), c_int(cin),
+                         c_int(h), c_int(w), ptr(b["codes"]), ptr(dp), c_int(cout), c_float(LEAKY_SLOPE), ptr(t1), ptr(sums),
+                         ws[1], ws[2], stream())
+                    dw = self._new(tuple(conv.weight.shape), torch.float32, dev)
+                    # SyncBN: the saved Gram matrix is already the global one, so reduce t1 / sum(dA) too and form the
+                    # global gradient on every rank; dividing by the world size makes the exchange's mean leave it as is
+                    self._sync_stats(t1)
+                    self._sync_stats(sums)
+                    call("ctk_first_wgrad_finalize", ptr(t1), ptr(b["gram"]), ptr(conv.weight), ptr(b["scale"]),
+                         ptr(b["mean"]), ptr(b["invstd"]), ptr(sums), c_double(float(n) * h * w * self.stat_world),
+                         c_int(cout), c_int(cin), ptr(dw), stream())
+                    if self.stat_world > 1:
+                        dw.div_(self.stat_world)
+                        sums.div_(self.stat_world)
+                    done(bn.bias, sums[:cout])
+                    done(bn.weight, sums[cout:])
+                    done(conv.weight, dw)
                 done(conv.bias, self._zero_grad_of(conv.bias))
                 continue
+            sums = self._new((2 * cout,), torch.float32, dev)
             pooled, p_cstride, p_coff = b["pooled"]
             # sums from the pooled tensors; channel groups whose BatchNorm parameters make that reconstruction lossy
             # (gamma == 0 or |beta| > 8 |gamma|) are reduced from the raw conv output instead -- decided on the device
@@ -372,36 +453,34 @@ class TrainEngine:
                  c_int(cout), ptr(b["scale"]), ptr(b["shift"]), ptr(b["mean"]), ptr(b["invstd"]), ptr(self._global_sums(sums)),
                  c_float(LEAKY_SLOPE), ptr(dy), stream())
             b["y"] = None
-            if wgrad_stream is not None:
-                # the weight gradient is off the critical path (nothing in this backward reads it): a side stream lets the
-                # tensor-bound wgrad run under the HBM-bound BatchNorm passes of the next layer down
-                ready = torch.cuda.Event()
-                ready.record()
-                wgrad_stream.wait_event(ready)
-                dy.record_stream(wgrad_stream)
-                wg_ctx = torch.cuda.stream(wgrad_stream)
-            else:
-                wg_ctx = contextlib.nullcontext()
-            with wg_ctx:
-                dw = self._new(tuple(conv.weight.shape), torch.float32, dev)
-                if li == 0:
-                    ws = workspace("ctk_conv_first_wgrad_workspace_bytes", cin, cout, device=dev)
-                    call("ctk_conv_first_wgrad", ptr(dy), ptr(x), c_int(n), c_int(x.shape[1]), c_int(br.c_offset), c_int(cin),
-                         c_int(h), c_int(w), c_int(cout), ptr(dw), ws[1], ws[2], stream())
-                else:
-                    ws = workspace("ctk_conv3x3_wgrad_tc_workspace_bytes", cin, cout, device=dev)
-                    call("ctk_conv3x3_wgrad_tc", ptr(dy), ptr(b["x_in"]), c_int(n), c_int(h), c_int(w), c_int(cin), c_int(cout),
-                         ptr(dw), ws[1], ws[2], stream(), meta={"flops": 2.0 * n * h * w * cout * 9 * cin})
-                done(conv.weight, dw)
+
+            def weight_gradient():
+                # off the critical path (nothing in this backward reads it)
+                with fork(dy, b["x_in"]):
+                    dw = self._new(tuple(conv.weight.shape), torch.float32, dev)
+                    if li == 0:
+                        ws = workspace("ctk_conv_first_wgrad_workspace_bytes", cin, cout, device=dev)
+                        call("ctk_conv_first_wgrad", ptr(dy), ptr(x), c_int(n), c_int(x.shape[1]), c_int(br.c_offset),
+                             c_int(cin), c_int(h), c_int(w), c_int(cout), ptr(dw), ws[1], ws[2], stream())
+                    else:
+                        ws = workspace("ctk_conv3x3_wgrad_tc_workspace_bytes", cin, cout, device=dev)
+                        call("ctk_conv3x3_wgrad_tc", ptr(dy), ptr(b["x_in"]), c_int(n), c_int(h), c_int(w), c_int(cin),
+                             c_int(cout), ptr(dw), ws[1], ws[2], stream(), meta={"flops": 2.0 * n * h * w * cout * 9 * cin})
+                    done(conv.weight, dw)
+
+            if not defer_wgrad:
+                weight_gradient()
             # the conv bias feeds a train-mode BatchNorm, so its gradient is sum(dY) = 0 identically
             done(conv.bias, self._zero_grad_of(conv.bias))
             if li > 0:
-                wg = self._new((9, cin, cout), torch.bfloat16, dev)
-                call("ctk_pack_conv_weight_dgrad_bf16", ptr(conv.weight), c_int(cout), c_int(cin), ptr(wg), stream())
+                wg = b["w_dgrad"]
                 dx = self._new((n, h, w, cin), torch.bfloat16, dev)
                 call("ctk_conv3x3_tc_raw", ptr(dy), c_int(n), c_int(h), c_int(w), c_int(cout), ptr(wg), c_int(cin), ptr(dx),
-                     ptr(None), ptr(None), c_size_t(0), stream(), meta={"flops": 2.0 * n * h * w * cout * 9 * cin})
+                     ptr(None), ptr(None), c_size_t(0), stream(),
+                     meta={"flops": 2.0 * n * h * w * cout * 9 * cin, "role": "dgrad"})
                 dp, dp_cstride, dp_coff = dx, cin, 0
+            if defer_wgrad:
+                weight_gradient()
             del dy
 
     # ------------------------------------------------------------------ backward
@@ -425,8 +504,9 @@ class TrainEngine:
         grads: Dict[torch.nn.Parameter, torch.Tensor] = {}
 
         n, dev = sv["n"], dout.device
-        overlap = self.overlap_streams
-        comm = self._side_stream("comm", 0, dev) if overlap and self.on_grad_ready is not None else None
+        overlap = self.overlap_streams                        # experiment: branches and weight gradients on side streams
+        defer = self.overlap_wgrad and not overlap            # weight gradients beside the next layer's BatchNorm passes
+        comm = self._side_stream("comm", 0, dev) if (overlap or defer) and self.on_grad_ready is not None else None
 
         def done(p, g):
             grads[p] = g
@@ -522,9 +602,14 @@ class TrainEngine:
                         self._backward_branch(entry, sv, dfeat, done, wg)
                 else:
                     self._backward_branch(entry, sv, dfeat, done, wg)
+            elif defer:
+                wg = self._side_stream("wgrad", 0, dev)
+                if wg not in used_streams:
+                    used_streams.append(wg)
+                self._backward_branch(entry, sv, dfeat, done, wg, defer_wgrad=True)
             else:
                 self._backward_branch(entry, sv, dfeat, done)
-        if overlap:
+        if overlap or defer:
             self._join(main, used_streams)
             for g in grads.values():            # produced on side streams, consumed (optimizer, NCCL, user) on this one
                 g.record_stream(main)
