@@ -88,7 +88,7 @@ class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
 
     FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw,power.limit")
 
     def __init__(self, index):
         self.index = index
@@ -112,7 +112,7 @@ class ClockSampler:
         except subprocess.TimeoutExpired:
             self.proc.kill()
             out, _ = self.proc.communicate()
-        sm, mx, reasons = [], [], set()
+        sm, mx, reasons, watts, limit = [], [], set(), [], []
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
         for line in out.strip().splitlines():
             parts = [p.strip() for p in line.split(",")]
@@ -126,8 +126,14 @@ class ClockSampler:
             for nm, v in zip(names, parts[2:6]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
+            try:
+                watts.append(float(parts[6]))
+                limit.append(float(parts[7]))
+            except (IndexError, ValueError):
+                pass
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm),
+                "power_w": statistics.median(watts) if watts else None, "power_limit_w": max(limit) if limit else None}
 
 
 # ------------------------------------------------------------------------------------------------ the reference's CPU path
@@ -319,7 +325,7 @@ def measure_train(args, kind, steps, warmup, with_scheduler=False):
     eng = ctk.models.get_train_engine(model)
     eng.overlap_streams = bool(getattr(args, "overlap_streams", False))
     if getattr(args, "no_overlap_wgrad", False):
-        eng.overlap_wgrad = False
+        eng.overlap_wgrad = eng.overlap_pack = False
     concurrent_backward = eng.overlap_wgrad or eng.overlap_streams
     eng_overlap_wgrad = eng.overlap_wgrad and not eng.overlap_streams
     sync = None

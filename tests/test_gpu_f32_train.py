@@ -307,10 +307,11 @@ def test_200_step_loss_curve_at_batch_64(kind):
     (unmodified model class + torch.optim.Adam + MSELoss on the CPU, tests/golden/make_loss_curve.py) at batch 64 from a
     256-tile pool is the golden; the same loop re-run with another thread count (only ATen's reduction order changes) tells
     for how many steps the reference reproduces ITSELF to 1 %.  Asserted:
-      fp32 path : every step within 1 % until the reference's two runs first differ by 1e-3; over the first 50 steps the distance
-                  to the reference run at most 2 x (median) / 3 x (maximum) the distance between the reference's own two
-                  runs; every 25-step window's geometric-mean loss within WINDOW_BAND (3 % double-branch, 10 % single) or
-                  1.5 x the band the reference keeps to itself, whichever is wider;
+      fp32 path : every step within 1 % until the reference's two runs first differ by 1e-4; over the compared steps (100) the
+                  distance to the reference run at most 2 x (median) / 3 x (maximum) the distance between the reference's own
+                  two runs; every 25-step window's geometric-mean loss within WINDOW_BAND (3 % double-branch, 10 % single) or
+                  1.5 x the band the reference keeps to itself (double-branch: 0.3 / 1.0 / 2.6 / 6.8 % per window), whichever is
+                  wider;
       bf16 path : step 0 within 1 %, every window within 8 % (double) / 25 % (single) or that same reference band --
                   bf16 operand rounding is a 2^-9 perturbation where a thread count is a 2^-24 one."""
     g = _curve(f"loss_curve_{kind}_b64.json")
@@ -340,17 +341,20 @@ def test_200_step_loss_curve_at_batch_64(kind):
               f"median rel {np.median(rel):.2e}, max {rel.max():.2e}")
         assert rel[0] <= 1e-2
         if other is not None:
-            m = min(len(other), steps, 50)
+            m = min(len(other), steps)
             own_rel = np.abs(other[:m] - ref[:m]) / ref[:m]
             print("   step: gpu-vs-reference / reference-vs-itself  " +
                   "  ".join(f"{t}: {rel[t]:.1e}/{own_rel[t]:.1e}" for t in range(min(m, 12))))
             print(f"   first {m} steps: median {np.median(rel[:m]):.2e} / {np.median(own_rel):.2e}, max {rel[:m].max():.2e} / {own_rel.max():.2e}")
             if precision == "fp32":
                 # Both the fp32 path and the reference's second run are fp32 summation-order perturbations of the same
-                # trajectory.  Where the reference reproduces itself (to 1e-3) the GPU must be within 1 %; once the
-                # trajectory has gone chaotic, its distance from the reference run may not exceed the reference's own
-                # (2 x the median, 3 x the maximum over the compared steps).
-                prefix = int(np.argmax(own_rel > 1e-3)) if (own_rel > 1e-3).any() else m      # steps before the reference first strays
+                # trajectory, of different size: another thread count reorders the threaded reductions only (step-1 loss
+                # moves by 1e-6), the CUDA path reorders every sum and keeps fp64 partials (gradient 2.6e-4 away in relative
+                # L2, which Adam's first sign-like update turns into 5e-5 on the step-1 loss) -- about two of the trajectory's
+                # x10 - x30 per-step amplifications ahead.  So: while the reference reproduces itself to 1e-4 the GPU must be
+                # within 1 %; once the trajectory has gone chaotic, its distance from the reference run may not exceed the
+                # reference's own (2 x the median, 3 x the maximum over the compared steps).
+                prefix = int(np.argmax(own_rel > 1e-4)) if (own_rel > 1e-4).any() else m      # steps before the reference first strays
                 assert (rel[:prefix] <= 1e-2).all(), (prefix, rel[:prefix], own_rel[:prefix])
                 assert np.median(rel[:m]) <= 2.0 * np.median(own_rel) + 1e-2, (np.median(rel[:m]), np.median(own_rel))
                 assert rel[:m].max() <= 3.0 * own_rel.max() + 1e-2, (rel[:m].max(), own_rel.max())

@@ -339,6 +339,30 @@ def test_gemm_splitk(ctk):
     assert (part[0].double().cpu() - ref0).abs().max().item() <= 1e-3
 
 
+def test_gemm_splitk_ragged_splits(ctk):
+    """The split count follows the SM count, not the divisors of K / 64: 64 K blocks over 18 splits = 10 splits of 4 blocks and
+    8 of 3, each split the partial sum over its own contiguous K range."""
+    from ctk._lib import call, ptr, stream
+    torch.manual_seed(6)
+    M, N, K, splits = 128, 256, 4096, 18
+    a = torch.randn(M, K).to(torch.bfloat16)
+    b = (torch.randn(N, K) / K ** 0.5).to(torch.bfloat16)
+    part = torch.full((splits, M, N), float("nan"), device="cuda")
+    ad, bd = a.cuda(), b.cuda()
+    call("ctk_gemm_bf16_splitk", ptr(ad), ptr(bd), c_int(M), c_int(N), c_int(K), c_int(splits), ptr(part), stream())
+    torch.cuda.synchronize()
+    base, extra = divmod(K // 64, splits)
+    k0 = 0
+    for s_ in range(splits):
+        k1 = k0 + 64 * (base + (1 if s_ < extra else 0))
+        ref = a[:, k0:k1].double() @ b[:, k0:k1].double().t()
+        assert (part[s_].double().cpu() - ref).abs().max().item() <= 1e-3, s_
+        k0 = k1
+    assert k0 == K
+    ref = a.double() @ b.double().t()
+    assert (part.double().sum(0).cpu() - ref).abs().max().item() <= 1e-3
+
+
 def test_head_eval(ctk):
     from ctk._lib import call, ptr, stream
     torch.manual_seed(5)

@@ -280,7 +280,8 @@ bn_bwd_reduce_pooled_kernel(const __nv_bfloat16* __restrict__ pooled, int p_cstr
 // ---------------------------------------------------------------- backward pass 2: dense gradient of the raw conv output
 // dY = sc (dA - m1 - xhat m2) with xhat = (y - mu) invstd  ==  sc dA + A y + B,  A = -sc invstd m2,  B = -sc m1 - A mu.
 // Same thread <-> channel-group mapping as the forward pass: constants live in registers for the whole walk.
-__global__ void __launch_bounds__(256, 2)
+template <int kU, int kMinBlocks>          // pooled pixels per thread and iteration, resident CTAs the register budget allows
+__global__ void __launch_bounds__(256, kMinBlocks)
 bn_bwd_apply_kernel(const uint4* __restrict__ y, const __nv_bfloat16* __restrict__ dp, int dp_cstride, int dp_coffset,
                     int H, int W, int c8, const float* __restrict__ scale, const float* __restrict__ shift,
                     const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ sums,
@@ -299,12 +300,12 @@ bn_bwd_apply_kernel(const uint4* __restrict__ y, const __nv_bfloat16* __restrict
     cb[i] = -sc[i] * m1 - ca[i] * mu;
   }
   const long long stride = static_cast<long long>(gridDim.x) * slots;
-  for (long long pix0 = blockIdx.x * static_cast<long long>(slots) + slot; pix0 < pooled_pixels; pix0 += 2 * stride) {
-    uint4 raw[2][4], rdp[2];
-    long long base[2];
-    bool on[2];
+  for (long long pix0 = blockIdx.x * static_cast<long long>(slots) + slot; pix0 < pooled_pixels; pix0 += kU * stride) {
+    uint4 raw[kU][4], rdp[kU];
+    long long base[kU];
+    bool on[kU];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < kU; ++u) {
       const long long pix = pix0 + u * stride;
       on[u] = pix < pooled_pixels;
       const long long q = on[u] ? pix : pix0;
@@ -318,7 +319,7 @@ bn_bwd_apply_kernel(const uint4* __restrict__ y, const __nv_bfloat16* __restrict
       for (int j = 0; j < 4; ++j) raw[u][j] = __ldcs(y + base[u] + ((j >> 1) * W + (j & 1)) * static_cast<long long>(c8));
     }
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < kU; ++u) {
       if (!on[u]) break;
       // one 32-bit word (two channels) of the four window positions at a time keeps the live set small
       uint32_t o[4][4];
@@ -530,9 +531,18 @@ int ctk_bn_bwd_apply(const void* y_bf16, const void* dp_bf16, int dp_cstride, in
   const int threads = ((bn_block_threads() >= c8 ? bn_block_threads() : 256) / c8) * c8;
   const long long pooled = static_cast<long long>(n) * (H / 2) * (W / 2);
   const float inv_count = 1.f / (static_cast<float>(n) * H * W);
-  bn_bwd_apply_kernel<<<grid_for_pixels(pooled, threads / c8, 2), threads, 0, ctk::as_stream(stream)>>>(
-      static_cast<const uint4*>(y_bf16), static_cast<const __nv_bfloat16*>(dp_bf16), dp_cstride, dp_coffset, H, W,
-      c8, scale, shift, mean, invstd, sums, inv_count, slope, static_cast<uint4*>(dy_bf16), pooled);
+  // CTK_BN_APPLY_VARIANT: 0 = two pooled pixels per iteration, 2 CTAs per SM (128 registers); 1 / 2 = one pixel, 3 / 4 CTAs;
+  // 3 = two pixels, 3 CTAs
+  static const int variant = [] { const char* e = getenv("CTK_BN_APPLY_VARIANT"); return e ? atoi(e) : 1; }();
+#define CTK_BN_APPLY(U, B)                                                                                              \
+  bn_bwd_apply_kernel<U, B><<<grid_for_pixels(pooled, threads / c8, U), threads, 0, ctk::as_stream(stream)>>>(        \
+      static_cast<const uint4*>(y_bf16), static_cast<const __nv_bfloat16*>(dp_bf16), dp_cstride, dp_coffset, H, W, c8, \
+      scale, shift, mean, invstd, sums, inv_count, slope, static_cast<uint4*>(dy_bf16), pooled)
+  if (variant == 1) CTK_BN_APPLY(1, 3);
+  else if (variant == 2) CTK_BN_APPLY(1, 4);
+  else if (variant == 3) CTK_BN_APPLY(2, 3);
+  else CTK_BN_APPLY(2, 2);
+#undef CTK_BN_APPLY
   return ctk::check_launch();
 }
 

@@ -534,70 +534,79 @@ conv_first_ws_kernel(const __grid_constant__ CUtensorMap tm_out, const float* __
         mbar_wait(&acc_full[eg], (u >> 1) & 1);
         tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + eg * 256;
+        // Eight channels (x the four window positions) per step, TMEM loads one step ahead of the arithmetic: the loads of
+        // step h + 1 are in flight while step h is reduced, packed and staged (ncu, round 2: the epilogue warps sat on the
+        // TMEM scoreboard for most of a unit when every 16-channel load was waited for before anything else was issued).
+        uint32_t va[4][8], vb[4][8];
+        auto load8 = [&](uint32_t (&v)[4][8], int h8) {
 #pragma unroll
-        for (int hf = 0; hf < 4; ++hf) {
-          uint32_t v[4][16];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) tmem_ld_32x16(taddr + q * 64 + hf * 16, v[q]);
-          tmem_ld_wait();
-          if (hf == 3) {                          // all TMEM reads of this unit are done: hand the buffer back
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[eg]);
-          }
-          float best[16];
-          const int ch = p * 64 + hf * 16;
+          for (int q = 0; q < 4; ++q) tmem_ld_32x8(taddr + q * 64 + h8 * 8, v[q]);
+        };
+        auto release = [&]() {                    // all TMEM reads of this unit are done: hand the buffer back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[eg]);
+        };
+        auto step8 = [&](const uint32_t (&v)[4][8], int h8) {
+          float best[8];
+          const int ch = p * 64 + h8 * 8;
           if constexpr (kCodes) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
+            for (int i = 0; i < 8; ++i) {
               float m = __uint_as_float((v[0][i] & ~3u) | 3u);
               m = fmaxf(m, __uint_as_float((v[1][i] & ~3u) | 2u));
               m = fmaxf(m, __uint_as_float((v[2][i] & ~3u) | 1u));
               best[i] = fmaxf(m, __uint_as_float(v[3][i] & ~3u));
             }
-            uint32_t cw[2] = {0u, 0u};
+            uint32_t cw = 0u;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
+            for (int i = 0; i < 8; ++i) {
               const uint32_t b = __float_as_uint(best[i]);
               const uint32_t nib = (3u - (b & 3u)) | ((b >> 29) & 4u);      // arg-max position | sign << 2
-              cw[i >> 3] |= nib << (4 * (i & 7));
+              cw |= nib << (4 * i);
             }
-            code_words[2 * hf] = cw[0];
-            code_words[2 * hf + 1] = cw[1];
+            code_words[h8] = cw;
           } else {
 #pragma unroll
-            for (int i = 0; i < 16; ++i)
+            for (int i = 0; i < 8; ++i)
               best[i] = fmaxf(fmaxf(__uint_as_float(v[0][i]), __uint_as_float(v[1][i])),
                               fmaxf(__uint_as_float(v[2][i]), __uint_as_float(v[3][i])));
           }
           if constexpr (kMode == 2) {
-            uint32_t oh[8], ol[8];
+            uint32_t oh[4], ol[4];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
+            for (int i = 0; i < 4; ++i) {
               const uint32_t s0 = split_hi_lo(leaky(best[2 * i], slope)), s1 = split_hi_lo(leaky(best[2 * i + 1], slope));
               oh[i] = (s0 & 0xffffu) | (s1 << 16);
               ol[i] = (s0 >> 16) | (s1 & 0xffff0000u);
             }
             if (valid) {
               const size_t off = pooled_pix * out_cstride + out_coffset + ch;
-              reinterpret_cast<uint4*>(out + off)[0] = make_uint4(oh[0], oh[1], oh[2], oh[3]);
-              reinterpret_cast<uint4*>(out + off)[1] = make_uint4(oh[4], oh[5], oh[6], oh[7]);
-              reinterpret_cast<uint4*>(out_lo + off)[0] = make_uint4(ol[0], ol[1], ol[2], ol[3]);
-              reinterpret_cast<uint4*>(out_lo + off)[1] = make_uint4(ol[4], ol[5], ol[6], ol[7]);
+              *reinterpret_cast<uint4*>(out + off) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+              *reinterpret_cast<uint4*>(out_lo + off) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
             }
           } else {
             // pooled bf16 output: staged as a 128B-swizzled [32 windows][64 channels] tile, stored by one TMA instruction
             // per warp and pass -- registers are free again after the shared-memory store, every global write is a full
             // 128-byte line, and ragged edges are clipped by the tensor map
-            uint32_t o[8];
+            uint32_t o[4];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = leaky_bf16x2(pack_bf16x2(best[2 * i], best[2 * i + 1]), slope2);
+            for (int i = 0; i < 4; ++i) o[i] = leaky_bf16x2(pack_bf16x2(best[2 * i], best[2 * i + 1]), slope2);
             const uint32_t row = stage_addr + static_cast<uint32_t>(lane * 128);
-            const uint32_t c0 = static_cast<uint32_t>(((2 * hf) ^ (lane & 7)) * 16);
-            const uint32_t c1 = static_cast<uint32_t>(((2 * hf + 1) ^ (lane & 7)) * 16);
+            const uint32_t c0 = static_cast<uint32_t>((h8 ^ (lane & 7)) * 16);
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + c0), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + c1), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]) : "memory");
           }
+        };
+        load8(va, 0);
+#pragma unroll
+        for (int h8 = 0; h8 < 8; h8 += 2) {
+          tmem_ld_wait();
+          load8(vb, h8 + 1);
+          step8(va, h8);
+          tmem_ld_wait();
+          if (h8 + 2 < 8) load8(va, h8 + 2);
+          else release();
+          step8(vb, h8 + 1);
         }
         if constexpr (kCodes) {
           if (valid) {                                      // the window's 64 codes of this pass: one full 32-byte sector

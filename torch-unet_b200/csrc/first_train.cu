@@ -25,20 +25,20 @@ using namespace ctk;
 // gram layout (double): [0, T) = S, [T, T + T*T) = G row-major (full, symmetric).
 // Items = T sums + T(T+1)/2 upper-triangle products.  A warp owns one row of a 32 x 8 pixel tile at a time (lane = pixel)
 // and a compile-time slice ("role") of the items, so every FFMA is unconditional: 9*CIN LDS feed ITEMS/ROLES FFMAs.
-template <int CIN>
+template <int CIN, int kRoles>
 struct GramCfg {
   static constexpr int T = 9 * CIN;
   static constexpr int ITEMS = T + T * (T + 1) / 2;
-  static constexpr int ROLES = CIN == 1 ? 1 : 4;
+  static constexpr int ROLES = kRoles;
   static constexpr int PER = (ITEMS + ROLES - 1) / ROLES;
   static constexpr int ROWG = 8 / ROLES;             // warps that share a role split the tile's rows
   static constexpr int TW = 32, TH = 64;             // pixel tile per iteration: long enough to hide the next tile's loads
   static constexpr int SLOTS = ((TH + 2) * (TW + 2) + 255) / 256;   // staging elements per thread and channel
 };
 
-template <int CIN, int ROLE>
-__device__ __forceinline__ void gram_accumulate(const float (&v)[9 * CIN], float (&acc)[GramCfg<CIN>::PER]) {
-  using C = GramCfg<CIN>;
+template <int CIN, int kRoles, int ROLE>
+__device__ __forceinline__ void gram_accumulate(const float (&v)[9 * CIN], float (&acc)[GramCfg<CIN, kRoles>::PER]) {
+  using C = GramCfg<CIN, kRoles>;
   int item = 0;
 #pragma unroll
   for (int a = 0; a < C::T; ++a, ++item)
@@ -50,11 +50,11 @@ __device__ __forceinline__ void gram_accumulate(const float (&v)[9 * CIN], float
       if (item % C::ROLES == ROLE) acc[item / C::ROLES] = fmaf(v[a], v[b], acc[item / C::ROLES]);
 }
 
-template <int CIN, int ROLE>
+template <int CIN, int kRoles, int ROLE>
 __device__ __forceinline__ void gram_role(const float* __restrict__ x, int n_img, int c_total, int c_offset, int H, int W,
-                                          double* __restrict__ part, float (*s_in)[GramCfg<CIN>::TH + 2][35],
+                                          double* __restrict__ part, float (*s_in)[GramCfg<CIN, kRoles>::TH + 2][35],
                                           double* s_red) {
-  using C = GramCfg<CIN>;
+  using C = GramCfg<CIN, kRoles>;
   constexpr int T = C::T, TW = C::TW, TH = C::TH, SLOTS = C::SLOTS;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int rowg = warp / C::ROLES;
@@ -120,7 +120,7 @@ __device__ __forceinline__ void gram_role(const float* __restrict__ x, int n_img
           asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t) : "r"(row_addr + static_cast<uint32_t>((c * (TH + 2) * 35 + (k / 3) * 35 + (k % 3)) * 4)));
           v[c * 9 + k] = in ? t : 0.f;
         }
-      gram_accumulate<CIN, ROLE>(v, acc);
+      gram_accumulate<CIN, kRoles, ROLE>(v, acc);
     }
 #pragma unroll
     for (int i = 0; i < C::PER; ++i) { dacc[i] += static_cast<double>(acc[i]); acc[i] = 0.f; }
@@ -145,22 +145,30 @@ __device__ __forceinline__ void gram_role(const float* __restrict__ x, int n_img
   }
 }
 
-template <int CIN>
-__global__ void __launch_bounds__(256)
+// kRoles splits the items over the warps of a CTA: fewer accumulators (and fp64 running sums) per thread buy resident
+// CTAs.  With one role the Cin = 1 kernel needs ~240 registers (54 fp32 + 54 fp64 sums): 8 warps per SM, and the 9 shared-
+// memory loads + 54 FFMAs of a row wait on each other with nothing else to issue; kMinBlocks tells the compiler the
+// register budget of the split variants.
+template <int CIN, int kRoles, int kMinBlocks>
+__global__ void __launch_bounds__(256, kMinBlocks)
 patch_gram_kernel(const float* __restrict__ x, int n_img, int c_total, int c_offset, int H, int W,
                   double* __restrict__ part) {
-  using C = GramCfg<CIN>;
+  using C = GramCfg<CIN, kRoles>;
+  static_assert(kRoles == 1 || kRoles == 2 || kRoles == 4, "roles must divide the 8 warps");
   __shared__ float s_in[CIN][C::TH + 2][35];
   __shared__ double s_red[8 * C::PER];
   const int role = (threadIdx.x >> 5) % C::ROLES;
   if constexpr (C::ROLES == 1) {
-    gram_role<CIN, 0>(x, n_img, c_total, c_offset, H, W, part, s_in, s_red);
+    gram_role<CIN, kRoles, 0>(x, n_img, c_total, c_offset, H, W, part, s_in, s_red);
+  } else if constexpr (C::ROLES == 2) {
+    if (role == 0) gram_role<CIN, kRoles, 0>(x, n_img, c_total, c_offset, H, W, part, s_in, s_red);   // warp-uniform
+    else gram_role<CIN, kRoles, 1>(x, n_img, c_total, c_offset, H, W, part, s_in, s_red);
   } else {
     switch (role) {          // warp-uniform
-      case 0: gram_role<CIN, 0>(x, n_img, c_total, c_offset, H, W, part, s_in, s_red); break;
-      case 1: gram_role<CIN, 1>(x, n_img, c_total, c_offset, H, W, part, s_in, s_red); break;
-      case 2: gram_role<CIN, 2>(x, n_img, c_total, c_offset, H, W, part, s_in, s_red); break;
-      default: gram_role<CIN, 3>(x, n_img, c_total, c_offset, H, W, part, s_in, s_red); break;
+      case 0: gram_role<CIN, kRoles, 0>(x, n_img, c_total, c_offset, H, W, part, s_in, s_red); break;
+      case 1: gram_role<CIN, kRoles, 1>(x, n_img, c_total, c_offset, H, W, part, s_in, s_red); break;
+      case 2: gram_role<CIN, kRoles, 2>(x, n_img, c_total, c_offset, H, W, part, s_in, s_red); break;
+      default: gram_role<CIN, kRoles, 3>(x, n_img, c_total, c_offset, H, W, part, s_in, s_red); break;
     }
   }
 }
@@ -732,7 +740,7 @@ extern "C" {
 
 size_t ctk_first_patch_gram_workspace_bytes(int cin) {
   const int T = 9 * cin;
-  return cin > 0 ? static_cast<size_t>(ctk::num_sms()) * (T + T * (T + 1) / 2) * sizeof(double) : 0;
+  return cin > 0 ? static_cast<size_t>(ctk::num_sms()) * 4 * (T + T * (T + 1) / 2) * sizeof(double) : 0;   // <= 4 CTAs per SM
 }
 
 int ctk_first_patch_gram(const float* x, int n, int c_total, int c_offset, int cin, int H, int W, double* gram,
@@ -742,11 +750,19 @@ int ctk_first_patch_gram(const float* x, int n, int c_total, int c_offset, int c
   const int T = 9 * cin;
   const int items = T + T * (T + 1) / 2;
   cudaStream_t s = ctk::as_stream(stream);
-  const int grid = ctk::num_sms();          // ~240 registers per thread: one resident CTA per SM
+  // Cin = 1 variants (CTK_GRAM_VARIANT): 0 = one role, one CTA per SM; 1 = two roles, two CTAs per SM; 2 = four roles, three
+  static const int variant = [] { const char* e = getenv("CTK_GRAM_VARIANT"); return e ? atoi(e) : 1; }();
+  const int per_sm = cin == 1 ? (variant == 2 ? 3 : variant == 1 ? 2 : 1) : 1;
+  const int grid = ctk::num_sms() * per_sm;
   CTK_REQUIRE_WORKSPACE(workspace, workspace_bytes, static_cast<size_t>(grid) * items * sizeof(double));
   double* part = static_cast<double*>(workspace);
-  if (cin == 1) patch_gram_kernel<1><<<grid, 256, 0, s>>>(x, n, c_total, c_offset, H, W, part);
-  else patch_gram_kernel<2><<<grid, 256, 0, s>>>(x, n, c_total, c_offset, H, W, part);
+  if (cin == 1) {
+    if (variant == 2) patch_gram_kernel<1, 4, 3><<<grid, 256, 0, s>>>(x, n, c_total, c_offset, H, W, part);
+    else if (variant == 1) patch_gram_kernel<1, 2, 2><<<grid, 256, 0, s>>>(x, n, c_total, c_offset, H, W, part);
+    else patch_gram_kernel<1, 1, 1><<<grid, 256, 0, s>>>(x, n, c_total, c_offset, H, W, part);
+  } else {
+    patch_gram_kernel<2, 4, 1><<<grid, 256, 0, s>>>(x, n, c_total, c_offset, H, W, part);
+  }
   int st = ctk::check_launch();
   if (st != CTK_OK) return st;
   gram_reduce_kernel<<<(items + 7) / 8, 256, 0, s>>>(part, grid, T, gram);

@@ -46,14 +46,16 @@ __device__ __forceinline__ uint64_t gemm_desc_mn_sw128(uint32_t addr, uint32_t l
 template <int kStages, bool kBMn>
 __global__ void __launch_bounds__(kThreads, kStages <= 2 ? 3 : 1)
 gemm_splitk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-                   const __grid_constant__ CUtensorMap tm_out, int M, int k_per_split, int out_is_bf16) {
+                   const __grid_constant__ CUtensorMap tm_out, int M, int kb_base, int kb_extra, int out_is_bf16) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   GemmSmem<kStages>* sl = reinterpret_cast<GemmSmem<kStages>*>(smem + kStages * kStageBytes);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * kBM, n0 = blockIdx.y * kBN, split = blockIdx.z;
-  const int k_begin = split * k_per_split;
-  const int k_iters = k_per_split / kBK;
+  // K blocks (64 elements) are dealt out as evenly as they go: the first kb_extra splits take one more than the others, so
+  // the split count can follow the SM count (18 x 8 tiles = 144 CTAs for FC1) instead of the divisors of K / 64
+  const int k_begin = (split * kb_base + (split < kb_extra ? split : kb_extra)) * kBK;
+  const int k_iters = kb_base + (split < kb_extra ? 1 : 0);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStages; ++i) { mbar_init(&sl->full[i], 1); mbar_init(&sl->empty[i], 1); }
@@ -176,18 +178,19 @@ gemm_splitk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
 
 template <int kStages, bool kBMn>
 static int gemm_run(const CUtensorMap& tm_a, const CUtensorMap& tm_b, const CUtensorMap& tm_out, dim3 grid, int M,
-                    int k_per_split, bool out_is_bf16, void* stream) {
+                    int k_blocks, bool out_is_bf16, void* stream) {
   auto kernel = gemm_splitk_kernel<kStages, kBMn>;
   CTK_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<kStages>()));
-  kernel<<<grid, kThreads, smem_bytes<kStages>(), ctk::as_stream(stream)>>>(tm_a, tm_b, tm_out, M, k_per_split,
-                                                                           out_is_bf16 ? 1 : 0);
+  const int splits = static_cast<int>(grid.z);
+  kernel<<<grid, kThreads, smem_bytes<kStages>(), ctk::as_stream(stream)>>>(tm_a, tm_b, tm_out, M, k_blocks / splits,
+                                                                           k_blocks % splits, out_is_bf16 ? 1 : 0);
   return ctk::check_launch();
 }
 
 static int gemm_launch(const void* a_bf16, const void* b_bf16, int M, int N, int K, int splits, float* partial,
                        void* out_bf16, void* stream, bool b_mn = false) {
   CTK_REQUIRE(a_bf16 && b_bf16 && (partial != nullptr) != (out_bf16 != nullptr) && M > 0 && N > 0 && K > 0 && splits > 0);
-  CTK_REQUIRE(M % kBM == 0 && N % kBN == 0 && K % (kBK * splits) == 0 && splits <= 65535 && N / kBN <= 65535);
+  CTK_REQUIRE(M % kBM == 0 && N % kBN == 0 && K % kBK == 0 && splits <= K / kBK && splits <= 65535 && N / kBN <= 65535);
   CTK_REQUIRE(out_bf16 == nullptr || splits == 1);
   CTK_REQUIRE((reinterpret_cast<uintptr_t>(a_bf16) & 15) == 0 && (reinterpret_cast<uintptr_t>(b_bf16) & 15) == 0 &&
               (reinterpret_cast<uintptr_t>(partial) & 15) == 0 && (reinterpret_cast<uintptr_t>(out_bf16) & 15) == 0);
@@ -223,12 +226,12 @@ static int gemm_launch(const void* a_bf16, const void* b_bf16, int M, int N, int
     if (st != CTK_OK) return st;
   }
   dim3 grid(M / kBM, N / kBN, splits);
-  const bool short_k = K / splits / kBK <= 8;
+  const bool short_k = K / kBK / splits <= 8;
   const bool bf = out_bf16 != nullptr;
-  if (b_mn) return short_k ? gemm_run<2, true>(tm_a, tm_b, tm_out, grid, M, K / splits, bf, stream)
-                           : gemm_run<6, true>(tm_a, tm_b, tm_out, grid, M, K / splits, bf, stream);
-  return short_k ? gemm_run<2, false>(tm_a, tm_b, tm_out, grid, M, K / splits, bf, stream)
-                 : gemm_run<6, false>(tm_a, tm_b, tm_out, grid, M, K / splits, bf, stream);
+  if (b_mn) return short_k ? gemm_run<2, true>(tm_a, tm_b, tm_out, grid, M, K / kBK, bf, stream)
+                           : gemm_run<6, true>(tm_a, tm_b, tm_out, grid, M, K / kBK, bf, stream);
+  return short_k ? gemm_run<2, false>(tm_a, tm_b, tm_out, grid, M, K / kBK, bf, stream)
+                 : gemm_run<6, false>(tm_a, tm_b, tm_out, grid, M, K / kBK, bf, stream);
 }
 
 extern "C" int ctk_gemm_bf16_splitk(const void* a_bf16, const void* b_bf16, int M, int N, int K, int splits,

@@ -12,7 +12,8 @@ from ctypes import c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_longl
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libctk.so")
+# CTK_LIB: another build of the same C ABI (tools/build_alt_lib.py), for same-box A/B measurements of a kernel change
+LIB_PATH = os.environ.get("CTK_LIB") or os.path.join(_HERE, "libctk.so")
 
 CONV_NO_POOL = 1
 CONV_NO_ACT = 2

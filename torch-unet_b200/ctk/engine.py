@@ -10,12 +10,33 @@ from __future__ import annotations
 from ctypes import c_float, c_int
 from typing import Dict, List, Optional, Tuple
 
+import os
+
 import torch
 
 from . import _lib
 from ._lib import call, ptr, stream
 
 LEAKY_SLOPE = 0.01     # nn.LeakyReLU(0.01): regression_model.py:16,25,38,43; two_branch_regression.py:12,18,24,30,44,49
+
+
+_SM_COUNT = {}
+
+
+def fc1_splits(tiles: int, K: int, dev) -> int:
+    """Split-K factor of the FC1 GEMM: as many K ranges as there are SMs per output tile (18 x 8 tiles = 144 CTAs on a B200
+    for a 256-tile batch), at least eight 64-element K blocks each.  The kernel deals the K blocks out raggedly, so the
+    count need not divide K / 64."""
+    if os.environ.get("CTK_FC1_SPLITS") == "pow2":      # round 1's rule (a power of two that divides K / 64), for A/B runs
+        splits = 1
+        while splits * 2 * tiles <= 160 and (K // 64) % (splits * 2) == 0 and K // (splits * 2) >= 512:
+            splits *= 2
+        return splits
+    idx = dev.index if getattr(dev, "index", None) is not None else torch.cuda.current_device()
+    sms = _SM_COUNT.get(idx)
+    if sms is None:
+        sms = _SM_COUNT[idx] = torch.cuda.get_device_properties(idx).multi_processor_count
+    return max(1, min(sms // tiles if tiles <= sms else 1, (K // 64) // 8))
 MAX_SUB_BATCH = 256    # images per pass; larger batches are processed in slices (eval BN is batch-independent)
 
 
@@ -204,9 +225,7 @@ class InferenceEngine:
         fc1, fc2, fc3 = self.lin
         K = fc1.in_features
         tiles = (m_pad // 128) * (fc1.out_features // 128)
-        splits = 1
-        while splits * 2 * tiles <= 160 and (K // 64) % (splits * 2) == 0 and K // (splits * 2) >= 512:
-            splits *= 2
+        splits = fc1_splits(tiles, K, dev)
         partial = self._buf("fc1p_split", (3 * splits, m_pad, fc1.out_features), torch.float32, dev)
         for j, (a, b) in enumerate(((feat[0], pk["fc1.w"]), (feat[1], pk["fc1.w"]), (feat[0], pk["fc1.w_lo"]))):
             call("ctk_gemm_bf16_splitk", ptr(a), ptr(b), c_int(m_pad), c_int(fc1.out_features), c_int(K), c_int(splits),
@@ -257,9 +276,7 @@ class InferenceEngine:
         fc1, fc2, fc3 = self.lin
         K = fc1.in_features
         tiles = (m_pad // 128) * (fc1.out_features // 128)
-        splits = 1
-        while splits * 2 * tiles <= 160 and (K // 64) % (splits * 2) == 0 and K // (splits * 2) >= 512:
-            splits *= 2
+        splits = fc1_splits(tiles, K, dev)
         partial = self._buf("fc1p", (splits, m_pad, fc1.out_features), torch.float32, dev)
         call("ctk_gemm_bf16_splitk", ptr(feat), ptr(pk["fc1.w"]), c_int(m_pad), c_int(fc1.out_features), c_int(K),
              c_int(splits), ptr(partial), stream())

@@ -17,7 +17,7 @@ import torch
 
 from . import _lib
 from ._lib import call, ptr, stream, workspace
-from .engine import LEAKY_SLOPE, _Branch, _conv_bn_pairs, _head_layers
+from .engine import LEAKY_SLOPE, _Branch, _conv_bn_pairs, _head_layers, fc1_splits
 
 
 def _pad(n: int, m: int) -> int:
@@ -67,12 +67,20 @@ class TrainEngine:
         # further side stream, so that the HBM-bound BatchNorm passes of one branch / layer overlap the tensor-bound conv
         # kernels of the other.  Off by default; see DESIGN.md section 8.
         self.overlap_streams: bool = False
-        # Weight gradients on ONE high-priority side stream, each started when the input gradient of ITS layer has been
-        # enqueued: wgrad_tc_kernel (192 threads x 48 registers, 166 KB of shared memory, one CTA per SM) leaves most of an
-        # SM's register file free, so the HBM-bound BatchNorm-backward passes of the next layer down -- the critical path --
-        # run on the same SMs at the same time instead of after it.  Nothing in backward reads a weight gradient, so only
-        # the end of backward waits for the side stream.  CTK_OVERLAP_WGRAD=0 restores the single-stream schedule.
-        self.overlap_wgrad: bool = os.environ.get("CTK_OVERLAP_WGRAD", "1") != "0"
+        # Side-stream schedules (CTK_OVERLAP_WGRAD = "pack" (default) / "0" / "1" / "wgrad"):
+        #  * overlap_pack  -- the step's bf16 weight copies (conv forward / dgrad layouts, FC1: 0.3 ms, 805 MB of traffic) are
+        #    built on a side stream at the start of forward, beside the issue-bound first block.  On by default.
+        #  * overlap_wgrad -- weight gradients on ONE high-priority side stream, each started behind the input gradient of
+        #    its layer, so that wgrad_tc_kernel (192 threads x 48 registers, 166 KB of shared memory, one CTA per SM) could
+        #    share its SMs with the HBM-bound BatchNorm-backward passes of the next layer down.  MEASURED (B200, round 2,
+        #    tools/r2_run21.sh / r2_run22.sh): the two then take exactly the SUM of their solo times (wgrad 2.8 -> 5.0 ms of
+        #    event time per step, BatchNorm passes 2.3 -> 4.1 ms; step 15.2 - 15.3 ms against 15.3 - 15.4 ms plain, within
+        #    run-to-run noise), with or without stream priority, 128-thread BatchNorm CTAs or a maximum shared-memory
+        #    carve-out on the streaming kernels: wgrad_tc_kernel itself keeps 50 - 65 % of the DRAM bandwidth busy and the
+        #    pair is bound by it.  Bit-identical results either way (test_stream_overlap_gives_the_same_step); off by default.
+        mode = os.environ.get("CTK_OVERLAP_WGRAD", "pack")
+        self.overlap_wgrad: bool = mode in ("1", "wgrad")
+        self.overlap_pack: bool = mode in ("1", "pack")
         # data parallel: SMs the persistent tensor-core kernels of the BACKWARD pass leave free for the gradient all-reduce
         # that runs beside them (parallel.attach sets it; 0 = fill the GPU, the single-GPU setting)
         self.backward_sm_reserve: int = 0
@@ -88,7 +96,7 @@ class TrainEngine:
         if st is None:
             # the weight-gradient stream outranks the default stream: its one-CTA-per-SM kernels take their SMs first and the
             # streaming passes fill in beside them
-            st = self._streams[key] = torch.cuda.Stream(device=dev, priority=-1 if kind == "wgrad" else 0)
+            st = self._streams[key] = torch.cuda.Stream(device=dev, priority=-1 if kind == "wgrad" and os.environ.get("CTK_WGRAD_PRIORITY", "1") != "0" else 0)
         return st
 
     @staticmethod
@@ -153,7 +161,7 @@ class TrainEngine:
         and FC1's column-permuted matrix -- built on a side stream at the start of the forward pass, so that the 0.3 ms
         they take (FC1: 805 MB of traffic) run beside the first block instead of on the critical path.  The compute stream
         waits for ``conv_ready`` before its first tensor-core conv and for ``fc1_ready`` before the FC1 GEMM."""
-        side = self._side_stream("pack", 0, dev) if self.overlap_wgrad else None
+        side = self._side_stream("pack", 0, dev) if self.overlap_pack else None
         packs = {"conv": {}, "conv_ready": None, "fc1_ready": None}
         if side is not None:
             start = torch.cuda.Event()
@@ -312,9 +320,7 @@ class TrainEngine:
         if packs["fc1_ready"] is not None:
             main.wait_event(packs["fc1_ready"])
         tiles = (m_pad // 128) * (f1 // 128)
-        splits = 1
-        while splits * 2 * tiles <= 160 and (K // 64) % (splits * 2) == 0 and K // (splits * 2) >= 512:
-            splits *= 2
+        splits = fc1_splits(tiles, K, dev)
         partial = self._new((splits, m_pad, f1), torch.float32, dev)
         call("ctk_gemm_bf16_splitk", ptr(feat), ptr(w1p), c_int(m_pad), c_int(f1), c_int(K), c_int(splits), ptr(partial),
              stream(), meta={"flops": 2.0 * m_pad * f1 * K})
