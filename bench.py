@@ -324,8 +324,8 @@ def measure_train(args, kind, steps, warmup, with_scheduler=False):
     model = build_model(kind, dev).train()
     eng = ctk.models.get_train_engine(model)
     eng.overlap_streams = bool(getattr(args, "overlap_streams", False))
-    if getattr(args, "no_overlap_wgrad", False):
-        eng.overlap_wgrad = eng.overlap_pack = False
+    if getattr(args, "overlap_wgrad", False):
+        eng.overlap_wgrad = eng.overlap_pack = True
     concurrent_backward = eng.overlap_wgrad or eng.overlap_streams
     eng_overlap_wgrad = eng.overlap_wgrad and not eng.overlap_streams
     sync = None
@@ -735,8 +735,8 @@ def main():
     ap.add_argument("--model", default="double", choices=["double", "single"])
     ap.add_argument("--overlap-streams", action="store_true",
                     help="training, EXPERIMENTAL: branches and weight gradients on side streams (measured: no gain)")
-    ap.add_argument("--no-overlap-wgrad", action="store_true",
-                    help="training: single-stream backward (A/B against the default deferred weight-gradient stream)")
+    ap.add_argument("--overlap-wgrad", action="store_true",
+                    help="training, experiment: weight packing and deferred weight gradients on side streams (measured: no gain)")
     ap.add_argument("--batch", type=int, default=BATCH, help="per-GPU batch (training)")
     ap.add_argument("--tiles", type=int, default=1_000_000, help="sweep mode: total tiles over all ranks")
     args = ap.parse_args()

@@ -334,8 +334,9 @@ def test_first_block_gram_and_stored_paths_agree(golden):
 
 @pytest.mark.parametrize("kind", ["single", "double"])
 def test_stream_overlap_gives_the_same_step(golden, kind):
-    """The three backward schedules -- one stream, weight gradients deferred to a high-priority side stream (the default,
-    TrainEngine.overlap_wgrad) and the overlap_streams experiment (branches and weight gradients on side streams) -- change
+    """The three schedules -- one stream (the default), weight packing and deferred weight gradients on side streams
+    (TrainEngine.overlap_pack / overlap_wgrad) and the overlap_streams experiment (branches and weight gradients on side
+    streams) -- change
     WHEN kernels run, not what they compute: every reduction is a fixed-order sum of per-CTA partials, so losses,
     gradients and the parameters after three Adam steps are bit-identical."""
     import ctk
@@ -346,7 +347,7 @@ def test_stream_overlap_gives_the_same_step(golden, kind):
     for mode in ("plain", "wgrad", "streams"):
         model = _build(kind).cuda().train()
         eng = ctk.models.get_train_engine(model)
-        eng.overlap_wgrad = mode == "wgrad"
+        eng.overlap_wgrad = eng.overlap_pack = mode == "wgrad"
         eng.overlap_streams = mode == "streams"
         eng.forced_masks = masks
         opt = ctk.Adam(model.parameters(), lr=5e-4, weight_decay=1e-4)

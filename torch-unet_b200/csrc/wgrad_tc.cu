@@ -32,7 +32,7 @@ constexpr int kThreads = 192;                 // warp 0 = TMA producer, warp 1 =
 constexpr int kABlockBytes = 128 * 128;       // one 64-channel block of the dY patch
 constexpr int kBBytes = kHaloH * kHaloW * 128;                       // 23040: the 64-channel X halo
 constexpr int kStageBytes = 2 * kABlockBytes + (kBBytes + 1023) / 1024 * 1024;   // 56320
-constexpr int kStages = 3;
+constexpr int kStages = 4;                    // 4 x 55 KB: one more patch in flight than round 1 (the 64 -> 128 layer is 66 % DRAM-bound)
 constexpr int kTmemCols = 512;
 constexpr int kN = 192;                       // (ky, ci) columns per kernel column kx
 

@@ -63,22 +63,26 @@ class TrainEngine:
         # parallel.attach installs a check (one 16-byte all-reduce per forward) that raises instead of silently normalising
         # with the wrong count when shards are ragged.
         self.stat_check_equal_batch: Optional[Callable[[int, torch.device], None]] = None
-        # EXPERIMENTAL (not yet measured on a GPU): run every branch's conv stack on its own stream and every wgrad on a
-        # further side stream, so that the HBM-bound BatchNorm passes of one branch / layer overlap the tensor-bound conv
-        # kernels of the other.  Off by default; see DESIGN.md section 8.
+        # Experiment: every branch's conv stack on its own stream and every wgrad on a further side stream, so that the
+        # HBM-bound BatchNorm passes of one branch / layer could overlap the tensor-bound conv kernels of the other.
+        # Measured (gpurun_out/ab_overlap.txt, round 2): 15.08 ms per step against 14.94 ms -- one persistent CTA per SM with
+        # 210 - 227 KB of shared memory leaves no room for a second kernel.  Off by default; see DESIGN.md section 4.8.
         self.overlap_streams: bool = False
-        # Side-stream schedules (CTK_OVERLAP_WGRAD = "pack" (default) / "0" / "1" / "wgrad"):
-        #  * overlap_pack  -- the step's bf16 weight copies (conv forward / dgrad layouts, FC1: 0.3 ms, 805 MB of traffic) are
-        #    built on a side stream at the start of forward, beside the issue-bound first block.  On by default.
+        # Side-stream schedules, both OFF by default (CTK_OVERLAP_WGRAD = "0" (default) / "pack" / "wgrad" / "1" = both).
+        # Measured on B200 in round 2 (tools/r2_run21.sh, r2_run22.sh, r2_run26.sh; same box, 20 - 30 steps each):
+        #  * overlap_pack  -- the step's bf16 weight copies (conv forward / dgrad layouts, FC1: 0.35 ms, 805 MB of traffic)
+        #    built on a side stream beside the first block: 15.00 / 15.24 ms per step against 14.93 / 15.05 ms single-stream.
+        #    The Gram and first-conv kernels it runs beside hold the whole register file of an SM, so the packing kernels
+        #    mostly wait for them anyway.
         #  * overlap_wgrad -- weight gradients on ONE high-priority side stream, each started behind the input gradient of
         #    its layer, so that wgrad_tc_kernel (192 threads x 48 registers, 166 KB of shared memory, one CTA per SM) could
-        #    share its SMs with the HBM-bound BatchNorm-backward passes of the next layer down.  MEASURED (B200, round 2,
-        #    tools/r2_run21.sh / r2_run22.sh): the two then take exactly the SUM of their solo times (wgrad 2.8 -> 5.0 ms of
-        #    event time per step, BatchNorm passes 2.3 -> 4.1 ms; step 15.2 - 15.3 ms against 15.3 - 15.4 ms plain, within
-        #    run-to-run noise), with or without stream priority, 128-thread BatchNorm CTAs or a maximum shared-memory
-        #    carve-out on the streaming kernels: wgrad_tc_kernel itself keeps 50 - 65 % of the DRAM bandwidth busy and the
-        #    pair is bound by it.  Bit-identical results either way (test_stream_overlap_gives_the_same_step); off by default.
-        mode = os.environ.get("CTK_OVERLAP_WGRAD", "pack")
+        #    share its SMs with the HBM-bound BatchNorm-backward passes of the next layer down.  The two then take exactly
+        #    the SUM of their solo times (wgrad 2.8 -> 5.0 ms of event time per step, BatchNorm passes 2.3 -> 4.1 ms; step
+        #    15.2 - 15.3 ms against 15.3 - 15.4 ms), with or without stream priority, 128-thread BatchNorm CTAs or a maximum
+        #    shared-memory carve-out on the streaming kernels: wgrad_tc_kernel itself keeps 50 - 65 % of the DRAM bandwidth
+        #    busy and the pair is bound by it.
+        # Results are bit-identical under every schedule (test_stream_overlap_gives_the_same_step).
+        mode = os.environ.get("CTK_OVERLAP_WGRAD", "0")
         self.overlap_wgrad: bool = mode in ("1", "wgrad")
         self.overlap_pack: bool = mode in ("1", "pack")
         # data parallel: SMs the persistent tensor-core kernels of the BACKWARD pass leave free for the gradient all-reduce
@@ -156,7 +160,7 @@ class TrainEngine:
         call("ctk_colstat", ptr(t), c_int(1), c_longlong(0), c_int(f), ptr(None), c_int(n), c_int(f), ptr(None), ptr(st), stream())
         return st[:f]
 
-    def _pack_weights(self, dev, main: torch.cuda.Stream) -> dict:
+    def _pack_weights(self, dev, main: torch.cuda.Stream, params_ready: Optional[torch.cuda.Event] = None) -> dict:
         """bf16 operand copies of the weights for this step -- every tensor-core conv's forward and input-gradient layouts
         and FC1's column-permuted matrix -- built on a side stream at the start of the forward pass, so that the 0.3 ms
         they take (FC1: 805 MB of traffic) run beside the first block instead of on the critical path.  The compute stream
@@ -164,9 +168,10 @@ class TrainEngine:
         side = self._side_stream("pack", 0, dev) if self.overlap_pack else None
         packs = {"conv": {}, "conv_ready": None, "fc1_ready": None}
         if side is not None:
-            start = torch.cuda.Event()
-            start.record(main)                  # the parameters are final behind this point (e.g. the optimizer's update)
-            side.wait_event(start)
+            if params_ready is None:
+                params_ready = torch.cuda.Event()
+                params_ready.record(main)
+            side.wait_event(params_ready)       # the parameters are final behind this point (e.g. the optimizer's update)
         with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
             for br in self.branches:
                 for li, (conv, _) in enumerate(br.pairs):
@@ -198,8 +203,12 @@ class TrainEngine:
             packs["w1p"].record_stream(main)
         return packs
 
-    def _forward_branch(self, br, x: torch.Tensor, feat: torch.Tensor, c_off: int, packs: dict) -> List[dict]:
-        """Conv stack of one branch on the CURRENT stream; the last block writes its channel range of ``feat``."""
+    def _forward_branch(self, br, x: torch.Tensor, feat: torch.Tensor, c_off: int, get_packs) -> List[dict]:
+        """Conv stack of one branch on the CURRENT stream; the last block writes its channel range of ``feat``.
+        ``get_packs()`` returns the step's packed weights, building them at the first call -- which comes right after the
+        first block's kernels have been enqueued, so the host launches the ~13 packing kernels while the GPU is busy (at the
+        very start of forward the GPU has just been drained by the previous step's ``loss.item()`` and would sit idle for the
+        0.3 ms those launches take on the host)."""
         n, c_total, H, W = x.shape
         dev = x.device
         h, w = H, W
@@ -245,6 +254,7 @@ class TrainEngine:
                 call("ctk_conv_first_raw", ptr(x), c_int(n), c_int(c_total), c_int(br.c_offset), c_int(cin), c_int(h),
                      c_int(w), ptr(conv.weight), c_int(cout), ptr(y), ptr(stats), ws[1], ws[2], stream())
             else:
+                packs = get_packs()
                 wp = packs["conv"][conv][0]
                 if packs["conv_ready"] is not None:
                     torch.cuda.current_stream(dev).wait_event(packs["conv_ready"])
@@ -257,7 +267,7 @@ class TrainEngine:
             call("ctk_bn_act_pool_fwd", ptr(y), c_int(n), c_int(h), c_int(w), c_int(cout), ptr(scale), ptr(shift),
                  c_float(LEAKY_SLOPE), ptr(dst), c_int(cstride), c_int(coff), stream())
             blocks.append({"y": y, "x_in": cur, "pooled": (dst, cstride, coff), "scale": scale, "shift": shift, "mean": mean, "invstd": invstd,
-                           "h": h, "w": w, "conv": conv, "bn": bn, "w_dgrad": packs["conv"][conv][1] if li > 0 else None})
+                           "h": h, "w": w, "conv": conv, "bn": bn, "w_dgrad": get_packs()["conv"][conv][1] if li > 0 else None})
             cur = dst
             h, w = h // 2, w // 2
         return blocks
@@ -292,8 +302,20 @@ class TrainEngine:
         feat = self._padded((m_pad, hf, wf, self.feat_channels), n, m_pad, dev)
         c_off = 0
         main = torch.cuda.current_stream(dev)
-        packs = self._pack_weights(dev, main)
+        pack_box: list = []
+        params_ready = None
+        if self.overlap_pack:
+            params_ready = torch.cuda.Event()
+            params_ready.record(main)           # recorded before this step's first kernel: the side stream need not wait for it
+
+        def get_packs() -> dict:
+            if not pack_box:
+                pack_box.append(self._pack_weights(dev, main, params_ready))
+            return pack_box[0]
+
         overlap = self.overlap_streams and len(self.branches) > 1
+        if overlap:
+            get_packs()                         # the branch streams fork below: build the packs on the main stream's timeline
         used_streams = []
         if overlap:
             fork = torch.cuda.Event()
@@ -304,9 +326,9 @@ class TrainEngine:
                 side.wait_event(fork)
                 used_streams.append(side)
                 with torch.cuda.stream(side):
-                    blocks = self._forward_branch(br, x, feat, c_off, packs)
+                    blocks = self._forward_branch(br, x, feat, c_off, get_packs)
             else:
-                blocks = self._forward_branch(br, x, feat, c_off, packs)
+                blocks = self._forward_branch(br, x, feat, c_off, get_packs)
             sv["blocks"].append({"branch": br, "blocks": blocks, "c_off": c_off})
             c_off += br.channels[-1]
         if overlap:
@@ -316,6 +338,7 @@ class TrainEngine:
         # ---- FC1 (tcgen05 split-K) + fp32 head
         f1, f2 = fc1.out_features, fc2.out_features
         hw = hf * wf
+        packs = get_packs()
         w1p = packs["w1p"]
         if packs["fc1_ready"] is not None:
             main.wait_event(packs["fc1_ready"])
