@@ -197,20 +197,25 @@ __global__ void gram_reduce_kernel(const double* __restrict__ part, int rows, in
 }
 
 // ------------------------------------------------------------------------------------------------ moments from the Gram matrix
+// The CTA first forms s = S / M and the patch covariance C = G / M - s s^T in shared memory (T <= 18), then a thread per
+// channel evaluates w.s and w^T C w: 2 T^2 fp64 FMAs.  (Dividing inside the T^2 loop -- three fp64 divisions per term and
+// thread, straight from global memory -- made this 25 us per launch.)
 __global__ void first_moments_kernel(const double* __restrict__ gram, const float* __restrict__ w, int cout, int T,
                                      double count, float* __restrict__ moments) {
+  __shared__ double s_mean[18], s_cov[18 * 18];
+  const double inv = 1.0 / count;
+  for (int i = threadIdx.x; i < T; i += blockDim.x) s_mean[i] = gram[i] * inv;
+  __syncthreads();
+  for (int i = threadIdx.x; i < T * T; i += blockDim.x) s_cov[i] = gram[T + i] * inv - s_mean[i / T] * s_mean[i % T];
+  __syncthreads();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= cout) return;
-  const double* S = gram;
-  const double* G = gram + T;
   double mean = 0.0;
-  for (int t = 0; t < T; ++t) mean += static_cast<double>(w[c * T + t]) * S[t];
-  mean /= count;
+  for (int t = 0; t < T; ++t) mean += static_cast<double>(w[c * T + t]) * s_mean[t];
   double var = 0.0;
   for (int a = 0; a < T; ++a) {
     double row = 0.0;
-    for (int b = 0; b < T; ++b)
-      row += static_cast<double>(w[c * T + b]) * (G[a * T + b] / count - (S[a] / count) * (S[b] / count));
+    for (int b = 0; b < T; ++b) row += static_cast<double>(w[c * T + b]) * s_cov[a * T + b];
     var += static_cast<double>(w[c * T + a]) * row;
   }
   moments[c] = static_cast<float>(mean);
@@ -771,7 +776,7 @@ int ctk_first_patch_gram(const float* x, int n, int c_total, int c_offset, int c
 
 int ctk_first_moments(const double* gram, const float* w, int cout, int cin, double count, float* moments,
                       void* stream) {
-  CTK_REQUIRE(gram && w && moments && cout > 0 && cin > 0 && count >= 1.0);
+  CTK_REQUIRE(gram && w && moments && cout > 0 && cin > 0 && cin <= 2 && count >= 1.0);
   first_moments_kernel<<<(cout + 63) / 64, 64, 0, ctk::as_stream(stream)>>>(gram, w, cout, 9 * cin, count, moments);
   return ctk::check_launch();
 }

@@ -12,18 +12,32 @@ namespace {
 using namespace ctk;
 
 // Z[n][f] = sum_s in[s*split_stride + n*row_stride + f] + bias[f];  stats[f] = sum_n Z, stats[F+f] = sum_n Z^2
-__global__ void __launch_bounds__(256)
+// One CTA per 32 columns, 32 row groups (1024 threads): a thread owns rows rg, rg + 32, ... of one column and adds the
+// split-K partials of a row in split order with four loads in flight.  (With 8 row groups and one load at a time the FC1
+// call -- 18 splits x 256 rows -- was a 39 us chain of dependent L2 reads on 16 SMs.)  Row-group totals are combined in a
+// fixed order: deterministic.
+constexpr int kColstatGroups = 32;
+__global__ void __launch_bounds__(32 * kColstatGroups)
 colstat_kernel(const float* __restrict__ in, int splits, long long split_stride, int row_stride,
                const float* __restrict__ bias, int n_rows, int F, float* __restrict__ z, float* __restrict__ stats) {
-  __shared__ float r1[8][32], r2[8][32];
+  __shared__ float r1[kColstatGroups][32], r2[kColstatGroups][32];
   const int col = blockIdx.x * 32 + (threadIdx.x & 31);
   const int rg = threadIdx.x >> 5;
   float s1 = 0.f, s2 = 0.f;
   if (col < F) {
     const float b = bias ? __ldg(bias + col) : 0.f;
-    for (int n = rg; n < n_rows; n += 8) {
+    for (int n = rg; n < n_rows; n += kColstatGroups) {
+      const float* src = in + static_cast<long long>(n) * row_stride + col;
       float v = b;
-      for (int s = 0; s < splits; ++s) v += in[s * split_stride + static_cast<long long>(n) * row_stride + col];
+      int s = 0;
+      for (; s + 4 <= splits; s += 4) {
+        float t[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) t[u] = src[(s + u) * split_stride];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v += t[u];
+      }
+      for (; s < splits; ++s) v += src[s * split_stride];
       if (z) z[static_cast<long long>(n) * F + col] = v;
       s1 += v;
       s2 = fmaf(v, v, s2);
@@ -34,7 +48,7 @@ colstat_kernel(const float* __restrict__ in, int splits, long long split_stride,
   __syncthreads();
   if (rg == 0 && col < F && stats) {
     float a = 0.f, b = 0.f;
-    for (int i = 0; i < 8; ++i) { a += r1[i][threadIdx.x]; b += r2[i][threadIdx.x]; }
+    for (int i = 0; i < kColstatGroups; ++i) { a += r1[i][threadIdx.x]; b += r2[i][threadIdx.x]; }
     stats[col] = a;
     stats[F + col] = b;
   }
@@ -93,13 +107,26 @@ sgemm_strided_kernel(const float* __restrict__ A, long long a_i, long long a_k, 
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // ty 0..7
   const int i0 = blockIdx.y * 32, j0 = blockIdx.x * 32;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  // the next K tile is fetched into registers while the current one is multiplied (the loop used to be a chain of exposed
+  // L2 round trips: 50 us for the 256 x 128 x 512 product)
+  float pa[4], pb[4];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int r = ty + 8 * q, i = i0 + r, j = j0 + r, k = k0 + tx;
+      pa[q] = (i < M && k < K) ? A[i * a_i + k * a_k] : 0.f;
+      pb[q] = (j < N && k < K) ? B[j * b_j + k * b_k] : 0.f;
+    }
+  };
+  fetch(0);
   for (int k0 = 0; k0 < K; k0 += 32) {
-    for (int r = ty; r < 32; r += 8) {
-      const int i = i0 + r, j = j0 + r, k = k0 + tx;
-      sa[r][tx] = (i < M && k < K) ? A[i * a_i + k * a_k] : 0.f;
-      sb[r][tx] = (j < N && k < K) ? B[j * b_j + k * b_k] : 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      sa[ty + 8 * q][tx] = pa[q];
+      sb[ty + 8 * q][tx] = pb[q];
     }
     __syncthreads();
+    if (k0 + 32 < K) fetch(k0 + 32);
 #pragma unroll 8
     for (int k = 0; k < 32; ++k) {
       const float bv = sb[tx][k];
@@ -179,18 +206,18 @@ head_out_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ ou
 }
 
 // backward of dropout + LeakyReLU + BN1d, pass 1: dact = dA*mask*keep_scale*leaky'(zn); sums[f] = sum dact, sums[F+f] = sum dact*xhat
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(32 * kColstatGroups)      // 32 row groups like colstat_kernel: 8 rows per thread
 bn1d_bwd_reduce_kernel(const float* __restrict__ da, const float* __restrict__ mask, float keep_scale,
                        const float* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ shift,
                        const float* __restrict__ mean, const float* __restrict__ invstd, float slope, int n_rows, int F,
                        float* __restrict__ dact, float* __restrict__ sums) {
-  __shared__ float r1[8][32], r2[8][32];
+  __shared__ float r1[kColstatGroups][32], r2[kColstatGroups][32];
   const int col = blockIdx.x * 32 + (threadIdx.x & 31);
   const int rg = threadIdx.x >> 5;
   float s1 = 0.f, s2 = 0.f;
   if (col < F) {
     const float sc = scale[col], sh = shift[col], mu = mean[col], is = invstd[col];
-    for (int n = rg; n < n_rows; n += 8) {
+    for (int n = rg; n < n_rows; n += kColstatGroups) {
       const long long i = static_cast<long long>(n) * F + col;
       const float zn = fmaf(z[i], sc, sh);
       float g = da[i] * (zn > 0.f ? 1.f : slope);
@@ -205,7 +232,7 @@ bn1d_bwd_reduce_kernel(const float* __restrict__ da, const float* __restrict__ m
   __syncthreads();
   if (rg == 0 && col < F) {
     float a = 0.f, b = 0.f;
-    for (int i = 0; i < 8; ++i) { a += r1[i][threadIdx.x]; b += r2[i][threadIdx.x]; }
+    for (int i = 0; i < kColstatGroups; ++i) { a += r1[i][threadIdx.x]; b += r2[i][threadIdx.x]; }
     sums[col] = a;
     sums[F + col] = b;
   }
@@ -236,7 +263,7 @@ extern "C" {
 int ctk_colstat(const float* in, int splits, long long split_stride, int row_stride, const float* bias, int n_rows,
                 int features, float* z, float* stats, void* stream) {
   CTK_REQUIRE(in && n_rows > 0 && features > 0 && splits > 0 && (z || stats));
-  colstat_kernel<<<(features + 31) / 32, 256, 0, ctk::as_stream(stream)>>>(in, splits, split_stride, row_stride, bias,
+  colstat_kernel<<<(features + 31) / 32, 32 * kColstatGroups, 0, ctk::as_stream(stream)>>>(in, splits, split_stride, row_stride, bias,
                                                                            n_rows, features, z, stats);
   return ctk::check_launch();
 }
@@ -289,7 +316,7 @@ int ctk_bn1d_bwd_reduce(const float* da, const float* mask, float drop_p, const 
                         const float* shift, const float* mean, const float* invstd, float slope, int n_rows,
                         int features, float* dact, float* sums, void* stream) {
   CTK_REQUIRE(da && z && scale && shift && mean && invstd && dact && sums && n_rows > 0 && features > 0);
-  bn1d_bwd_reduce_kernel<<<(features + 31) / 32, 256, 0, ctk::as_stream(stream)>>>(
+  bn1d_bwd_reduce_kernel<<<(features + 31) / 32, 32 * kColstatGroups, 0, ctk::as_stream(stream)>>>(
       da, mask, 1.f / (1.f - drop_p), z, scale, shift, mean, invstd, slope, n_rows, features, dact, sums);
   return ctk::check_launch();
 }
