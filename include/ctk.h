@@ -142,7 +142,8 @@ int ctk_conv3x3_tc_eval(const void* x_bf16, int n, int H, int W, int cin,
  * Replaces: the first nn.Linear of each head (aten::addmm), regression_model.py:36 and
  * two_branch_regression.py:42; the bias is added by ctk_head_eval, which also sums the splits.
  * A: [M,K] bf16 row-major, B: [N,K] bf16 row-major, M % 128 == 0 (pad the batch), N % 128 == 0,
- * K % (64*splits) == 0.
+ * K % 64 == 0, 1 <= splits <= K / 64.  The K / 64 blocks are dealt out contiguously and as evenly as they go: split s covers
+ * blocks [s*q + min(s, r), ...) with q = (K/64) / splits, r = (K/64) % splits, the first r splits one block more.
  * ------------------------------------------------------------------------------------------ */
 int ctk_gemm_bf16_splitk(const void* a_bf16, const void* b_bf16, int M, int N, int K, int splits,
                          float* partial, void* stream);

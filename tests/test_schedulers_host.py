@@ -67,3 +67,19 @@ def test_cosine_warmup_checkpoint_resume_and_validation():
     for bad in ({"warmup_epochs": 40}, {"warmup_epochs": -1}, {"max_lr": 0.0}, {"final_lr": 1.0}):
         with pytest.raises(ValueError):
             _make(**bad)
+
+
+def test_fc1_split_factor_follows_the_sm_count():
+    """Host logic of the FC1 split-K GEMM (ctk.engine.fc1_splits): as many K ranges as SMs per output tile, at least eight
+    64-element K blocks each; the kernel deals the blocks out raggedly (tests/test_gpu_kernels.py checks the ranges)."""
+    from ctk.engine import fc1_splits
+    assert fc1_splits(8, 262144, None, sms=148) == 18          # double-branch, 256-tile batch: 8 tiles x 18 = 144 CTAs
+    assert fc1_splits(4, 262144, None, sms=148) == 37          # HostScorer's 64-tile slices (m_pad 128): 148 CTAs
+    assert fc1_splits(8, 8192, None, sms=148) == 16            # single-branch: K / 64 = 128 blocks, eight per split
+    assert fc1_splits(200, 262144, None, sms=148) == 1         # more tiles than SMs: no split
+    assert fc1_splits(1, 64, None, sms=148) == 1
+    for tiles, K in ((8, 262144), (4, 262144), (8, 8192), (3, 4096)):
+        s = fc1_splits(tiles, K, None, sms=148)
+        q, r = divmod(K // 64, s)
+        assert q >= 8 or s == 1
+        assert r * (q + 1) + (s - r) * q == K // 64             # the ragged ranges cover every K block exactly once

@@ -23,7 +23,7 @@ LEAKY_SLOPE = 0.01     # nn.LeakyReLU(0.01): regression_model.py:16,25,38,43; tw
 _SM_COUNT = {}
 
 
-def fc1_splits(tiles: int, K: int, dev) -> int:
+def fc1_splits(tiles: int, K: int, dev, sms: Optional[int] = None) -> int:
     """Split-K factor of the FC1 GEMM: as many K ranges as there are SMs per output tile (18 x 8 tiles = 144 CTAs on a B200
     for a 256-tile batch), at least eight 64-element K blocks each.  The kernel deals the K blocks out raggedly, so the
     count need not divide K / 64."""
@@ -32,10 +32,11 @@ def fc1_splits(tiles: int, K: int, dev) -> int:
         while splits * 2 * tiles <= 160 and (K // 64) % (splits * 2) == 0 and K // (splits * 2) >= 512:
             splits *= 2
         return splits
-    idx = dev.index if getattr(dev, "index", None) is not None else torch.cuda.current_device()
-    sms = _SM_COUNT.get(idx)
     if sms is None:
-        sms = _SM_COUNT[idx] = torch.cuda.get_device_properties(idx).multi_processor_count
+        idx = dev.index if getattr(dev, "index", None) is not None else torch.cuda.current_device()
+        sms = _SM_COUNT.get(idx)
+        if sms is None:
+            sms = _SM_COUNT[idx] = torch.cuda.get_device_properties(idx).multi_processor_count
     return max(1, min(sms // tiles if tiles <= sms else 1, (K // 64) // 8))
 MAX_SUB_BATCH = 256    # images per pass; larger batches are processed in slices (eval BN is batch-independent)
 
