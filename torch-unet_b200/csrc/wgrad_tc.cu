@@ -22,6 +22,7 @@
 #include "ctk_ptx.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace {
 
@@ -328,6 +329,18 @@ int ctk_conv3x3_wgrad_tc(const void* dy_bf16, const void* x_bf16, int n, int H, 
   const int s_unit = std::max(1, std::min(p.total_tiles / 2, ctk::persistent_sms() / (3 * pairs)));
   p.slices_a = std::min(p.total_tiles, 2 * s_unit);
   p.slices_b = std::min(p.total_tiles, s_unit);
+  // Share of a pair's CTAs given to kx group 1 (CTK_WGRAD_B_PERMILLE, 0 = the 2 : 1 triplets above).  The B CTAs load the same
+  // 55 KB per patch for half the MMA work: they are load-bound (~860 clocks per patch against 1 536 for an A CTA), so the
+  // balanced split is 95 : 53, not 98 : 49.  That gives up the triplet lock-step (the second read of a tile is no longer a
+  // guaranteed L2 hit); measured on one box, wgrad per step: 300 permille 3.23 ms, 333 (triplets) 2.64 - 2.68, 360 2.56,
+  // 400 2.69.  Applied where a pair has at least 12 CTAs to split (pairs <= 12: the 64 -> 128 and 128 -> 256 layers).
+  static const int b_permille = [] { const char* e = getenv("CTK_WGRAD_B_PERMILLE"); return e ? atoi(e) : 360; }();
+  const int per_pair = ctk::persistent_sms() / pairs;
+  if (b_permille > 0 && b_permille < 1000 && per_pair >= 12 && p.total_tiles >= ctk::persistent_sms()) {
+    const int sb = std::max(1, std::min(per_pair - 1, per_pair * b_permille / 1000));
+    p.slices_a = per_pair - sb;
+    p.slices_b = sb;
+  }
   p.dw = dw;
   CTK_REQUIRE_WORKSPACE(workspace, workspace_bytes, pairs * pair_part_floats(p.slices_a, p.slices_b) * sizeof(float));
   p.part = static_cast<float*>(workspace);
