@@ -408,7 +408,7 @@ def measure_train(args, kind, steps, warmup, with_scheduler=False):
         conv_tf = conv["flops"] / (conv["ms"] / 1e3) / 1e12 if conv["ms"] > 0 else 0.0
         dg_tf = conv_dg["flops"] / (conv_dg["ms"] / 1e3) / 1e12 if conv_dg["ms"] > 0 else 0.0
         wg_tf = wg["flops"] / (wg["ms"] / 1e3) / 1e12 if wg["ms"] > 0 else 0.0
-        traffic, traffic_src = ncu_dram_traffic("conv3x3_tc_kernel", ("r2_train_full_raw.csv",))
+        traffic, traffic_src = ncu_dram_traffic("conv3x3_tc_kernel", ("r2b_train_full_raw.csv", "r2_train_full_raw.csv"))
         value = world * batch * steps / (ms / 1e3)
         cfg_idx = 3 if kind == "double" else 2
         line = {
@@ -595,7 +595,7 @@ def measure_infer(args, steps, warmup):
         per_all = _timeline_table(detail, 3)
         conv = per.get("ctk_conv3x3_tc_eval") or per.get("ctk_conv3x3_tc_eval_split") or {"ms": 0.0, "n": 1, "flops": 0.0}
         conv_tf = conv["flops"] / (conv["ms"] / 1e3) / 1e12 if conv["ms"] > 0 else 0.0
-        traffic, traffic_src = ncu_dram_traffic("conv3x3_tc_kernel", ("r2_infer_full_raw.csv", "r1d_infer_full_raw.csv"))
+        traffic, traffic_src = ncu_dram_traffic("conv3x3_tc_kernel", ("r2b_infer_full_raw.csv", "r2_infer_full_raw.csv", "r1d_infer_full_raw.csv"))
         value = world * BATCH * steps / (ms / 1e3)
         line = {"metric": "infer images/sec (double-branch, 2ch 256x256, batch 256/GPU, + Pearson)", "value": value,
                 "unit": "images/sec", "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms / steps,
