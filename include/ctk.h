@@ -239,6 +239,11 @@ int ctk_conv3x3_tc_raw(const void* x_bf16, int n, int H, int W, int cin, const v
                        void* y_bf16, float* stats, void* workspace, size_t workspace_bytes, void* stream);
 /* conv weight [Cout,Cin,3,3] fp32 -> [9][Cin][Cout] bf16 with the taps rotated by 180 degrees (dgrad operand). */
 int ctk_pack_conv_weight_dgrad_bf16(const float* w, int cout, int cin, void* w_packed_bf16, void* stream);
+/* Both copies (ctk_pack_conv_weight_bf16 and ..._dgrad_bf16 layouts) of up to 8 conv weights in one launch: what a training
+ * step needs of every tensor-core conv layer (nn.Conv2d weights, regression_model.py:23; two_branch_regression.py:16,22,28).
+ * w / cout / cin / w_fwd_bf16 / w_dgrad_bf16 are HOST arrays of n_layers entries (device pointers inside). */
+int ctk_pack_conv_weights_train(int n_layers, const float* const* w, const int* cout, const int* cin,
+                                void* const* w_fwd_bf16, void* const* w_dgrad_bf16, void* stream);
 
 /* Batch statistics -> normalisation constants; updates running_mean/var (momentum, unbiased variance, conv bias added
  * to the mean) and num_batches_tracked like nn.BatchNorm in train().  running_* / num_batches_tracked may be NULL.

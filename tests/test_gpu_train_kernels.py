@@ -339,3 +339,30 @@ def test_first_block_gram_path(L, cin, cout, coff, n, H, W):
     np.testing.assert_allclose(sums[cout:].cpu().numpy(), gamma.grad.numpy(), rtol=1e-3, atol=2e-3 + 2 * noise)
     # dW is a small difference of large terms (BN removes the mean and the xhat component of the gradient)
     assert rel_l2(dw.cpu(), w.grad) < 2e-3
+
+
+def test_pack_conv_weights_train_matches_the_single_layer_packers(L):
+    """ctk_pack_conv_weights_train writes, in one launch, exactly what ctk_pack_conv_weight_bf16 and
+    ctk_pack_conv_weight_dgrad_bf16 write layer by layer (the six tensor-core conv layers of the double-branch model)."""
+    from ctypes import c_void_p
+    torch.manual_seed(11)
+    shapes = [(128, 64), (256, 128), (512, 256), (128, 64), (256, 128), (512, 256)]
+    ws = [torch.randn(co, ci, 3, 3, device="cuda") for co, ci in shapes]
+    fwd = [torch.full((9, co, ci), float("nan"), device="cuda", dtype=torch.bfloat16) for co, ci in shapes]
+    dg = [torch.full((9, ci, co), float("nan"), device="cuda", dtype=torch.bfloat16) for co, ci in shapes]
+    k = len(shapes)
+    L.call("ctk_pack_conv_weights_train", c_int(k), (c_void_p * k)(*[w.data_ptr() for w in ws]),
+           (c_int * k)(*[s[0] for s in shapes]), (c_int * k)(*[s[1] for s in shapes]),
+           (c_void_p * k)(*[t.data_ptr() for t in fwd]), (c_void_p * k)(*[t.data_ptr() for t in dg]), L.stream())
+    for w, (co, ci), f, d in zip(ws, shapes, fwd, dg):
+        f1 = torch.empty_like(f)
+        d1 = torch.empty_like(d)
+        L.call("ctk_pack_conv_weight_bf16", L.ptr(w), c_int(co), c_int(ci), L.ptr(f1), L.stream())
+        L.call("ctk_pack_conv_weight_dgrad_bf16", L.ptr(w), c_int(co), c_int(ci), L.ptr(d1), L.stream())
+        torch.cuda.synchronize()
+        assert torch.equal(f.view(torch.int16), f1.view(torch.int16))
+        assert torch.equal(d.view(torch.int16), d1.view(torch.int16))
+        # and against the definition: fwd[tap][co][ci] = w[co][ci][tap], dgrad[tap][ci][co] = w[co][ci][8 - tap]
+        ref = w.reshape(co, ci, 9).to(torch.bfloat16)
+        assert torch.equal(f, ref.permute(2, 0, 1).contiguous())
+        assert torch.equal(d, ref.flip(2).permute(2, 1, 0).contiguous())

@@ -64,6 +64,34 @@ __global__ void pack_conv_dgrad_kernel(const float* __restrict__ w, int cout, in
   }
 }
 
+// Both operand layouts of up to eight conv weights in ONE launch (the training step packs every tensor-core conv's forward
+// and dgrad copy once per step: twelve 5-us launches otherwise).  Same values as pack_conv_kernel / pack_conv_dgrad_kernel.
+constexpr int kPackMulti = 8;
+struct PackMulti {
+  const float* w[kPackMulti];
+  __nv_bfloat16* fwd[kPackMulti];
+  __nv_bfloat16* dgrad[kPackMulti];
+  int cout[kPackMulti], cin[kPackMulti];
+  long long begin[kPackMulti + 1];
+  int n;
+};
+__global__ void pack_conv_multi_kernel(const PackMulti p) {
+  const long long total = p.begin[p.n];
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    int t = 0;
+    while (t + 1 < p.n && i >= p.begin[t + 1]) ++t;
+    const long long j = i - p.begin[t];
+    const int cin = p.cin[t], cout = p.cout[t];
+    const int ci = static_cast<int>(j % cin);
+    const int co = static_cast<int>((j / cin) % cout);
+    const int tap = static_cast<int>(j / (static_cast<long long>(cin) * cout));
+    const __nv_bfloat16 v = __float2bfloat16_rn(p.w[t][(static_cast<size_t>(co) * cin + ci) * 9 + tap]);
+    p.fwd[t][j] = v;                                                                       // [tap][co][ci]
+    p.dgrad[t][(static_cast<size_t>(8 - tap) * cin + ci) * cout + co] = v;                 // [8 - tap][ci][co]
+  }
+}
+
 // out[(c*HW + p)][n] = feat[n][p*cstride + c]   (NHWC activations -> NCHW-flatten rows, batch contiguous, zero padded to ld)
 __global__ void feat_transpose_kernel(const __nv_bfloat16* __restrict__ feat, int n, int hw, int channels,
                                       __nv_bfloat16* __restrict__ out, int ld) {
@@ -241,6 +269,27 @@ int ctk_pack_conv_weight_dgrad_bf16(const float* w, int cout, int cin, void* w_p
   const int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, 4096));
   pack_conv_dgrad_kernel<<<blocks, 256, 0, ctk::as_stream(stream)>>>(w, cout, cin,
                                                                      static_cast<__nv_bfloat16*>(w_packed_bf16));
+  return ctk::check_launch();
+}
+
+int ctk_pack_conv_weights_train(int n_layers, const float* const* w, const int* cout, const int* cin,
+                                void* const* w_fwd_bf16, void* const* w_dgrad_bf16, void* stream) {
+  if (n_layers == 0) return CTK_OK;
+  CTK_REQUIRE(n_layers > 0 && n_layers <= kPackMulti && w && cout && cin && w_fwd_bf16 && w_dgrad_bf16);
+  PackMulti p = {};
+  p.n = n_layers;
+  for (int t = 0; t < n_layers; ++t) {
+    CTK_REQUIRE(w[t] && w_fwd_bf16[t] && w_dgrad_bf16[t] && cout[t] > 0 && cin[t] > 0);
+    p.w[t] = w[t];
+    p.fwd[t] = static_cast<__nv_bfloat16*>(w_fwd_bf16[t]);
+    p.dgrad[t] = static_cast<__nv_bfloat16*>(w_dgrad_bf16[t]);
+    p.cout[t] = cout[t];
+    p.cin[t] = cin[t];
+    p.begin[t + 1] = p.begin[t] + 9ll * cout[t] * cin[t];
+  }
+  const long long total = p.begin[n_layers];
+  const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 16));
+  pack_conv_multi_kernel<<<blocks, 256, 0, ctk::as_stream(stream)>>>(p);
   return ctk::check_launch();
 }
 

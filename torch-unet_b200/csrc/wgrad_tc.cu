@@ -196,7 +196,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant
 }
 
 // Second stage: dW[co][ci][ky][kx] = sum over the slices of its (co block, ci block) pair, in slice order.
-// grid = (pairs * 18, 1): one CTA per 32-column block of the pair's 18 = 3 kx x 6 (ky, ci half); thread = (i, co quarter).
+// grid = (pairs * 18, 4): one CTA per 32-column block of the pair's 18 = 3 kx x 6 (ky, ci half) and per quarter of its 32
+// rows i; thread = (i, co).  (One CTA for all four quarters left the single-pair layers with 18 CTAs on 148 SMs: 19 us.)
 __global__ void __launch_bounds__(1024) wgrad_reduce_kernel(const WgradParams p) {
   const int pair = blockIdx.x / 18, blk = blockIdx.x % 18;
   const int kx = blk / 6, cb = blk % 6;
@@ -208,8 +209,8 @@ __global__ void __launch_bounds__(1024) wgrad_reduce_kernel(const WgradParams p)
   const float* src = base + (kx < 2 ? static_cast<size_t>(kx * 6 + cb) * kColBlock
                                     : static_cast<size_t>(p.slices_a) * 12 * kColBlock + static_cast<size_t>(cb) * kColBlock);
   const int ky = cb >> 1;
-#pragma unroll
-  for (int pass = 0; pass < 4; ++pass) {
+  {
+    const int pass = blockIdx.y;
     const int i = pass * 8 + i0;
     const float* col = src + i * 128 + co_l;
     float acc = 0.f;
@@ -370,7 +371,7 @@ int ctk_conv3x3_wgrad_tc(const void* dy_bf16, const void* x_bf16, int n, int H, 
   wgrad_tc_kernel<<<grid, kThreads, smem_bytes, s>>>(tm_dy, tm_x, p);
   int st = ctk::check_launch();
   if (st != CTK_OK) return st;
-  wgrad_reduce_kernel<<<pairs * 18, 1024, 0, s>>>(p);
+  wgrad_reduce_kernel<<<dim3(pairs * 18, 4), 1024, 0, s>>>(p);
   return ctk::check_launch();
 }
 

@@ -74,6 +74,7 @@ _SIGNATURES = {
     "ctk_conv3x3_tc_raw": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                                    c_size_t, c_void_p]),
     "ctk_pack_conv_weight_dgrad_bf16": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "ctk_pack_conv_weights_train": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "ctk_bn_finalize": (c_int, [c_void_p, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
                                 c_float, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "ctk_bn_finalize_moments": (c_int, [c_void_p, c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
@@ -195,7 +196,7 @@ KERNELS_PER_CALL = {"ctk_pearson_f32": 2, "ctk_tile_metrics_f32": 4, "ctk_tile_n
                     "ctk_pack_fc1_weight_bf16": 1, "ctk_conv_first_eval": 1, "ctk_conv_first_pool_codes": 1, "ctk_pack_conv_weight_split_bf16": 1,
                     "ctk_pack_fc1_weight_split_bf16": 1, "ctk_conv_first_eval_split": 1, "ctk_conv3x3_tc_eval_split": 1, "ctk_conv3x3_tc_eval": 1,
                     "ctk_gemm_bf16_splitk": 1, "ctk_head_eval": 1, "ctk_mse_loss": 1, "ctk_scale_by_scalar": 1, "ctk_adam_multi": 1,
-                    "ctk_conv_first_raw": 2, "ctk_conv3x3_tc_raw": 1, "ctk_pack_conv_weight_dgrad_bf16": 1,
+                    "ctk_conv_first_raw": 2, "ctk_conv3x3_tc_raw": 1, "ctk_pack_conv_weight_dgrad_bf16": 1, "ctk_pack_conv_weights_train": 1,
                     "ctk_bn_finalize": 1, "ctk_bn_finalize_moments": 1, "ctk_first_patch_gram": 2,
                     "ctk_first_moments": 1, "ctk_first_wgrad_codes": 3, "ctk_first_wgrad_finalize": 1, "ctk_bn_act_pool_fwd": 1, "ctk_bn_bwd_reduce": 2, "ctk_bn_bwd_reduce_pooled": 2, "ctk_bn_bwd_reduce_guarded": 3, "ctk_bn_bwd_apply": 1,
                     "ctk_conv3x3_wgrad_tc": 2, "ctk_conv_first_wgrad": 2, "ctk_feat_transpose_bf16": 1,

@@ -10,7 +10,7 @@ from __future__ import annotations
 
 import contextlib
 import os
-from ctypes import c_double, c_float, c_int, c_longlong, c_size_t, c_ulonglong
+from ctypes import c_double, c_float, c_int, c_longlong, c_size_t, c_ulonglong, c_void_p
 from typing import Callable, Dict, List, Optional, Tuple
 
 import torch
@@ -173,16 +173,18 @@ class TrainEngine:
                 params_ready.record(main)
             side.wait_event(params_ready)       # the parameters are final behind this point (e.g. the optimizer's update)
         with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
-            for br in self.branches:
-                for li, (conv, _) in enumerate(br.pairs):
-                    if li == 0:
-                        continue
-                    cout, cin = conv.out_channels, conv.in_channels
-                    wp = self._new((9, cout, cin), torch.bfloat16, dev)
-                    call("ctk_pack_conv_weight_bf16", ptr(conv.weight), c_int(cout), c_int(cin), ptr(wp), stream())
-                    wg = self._new((9, cin, cout), torch.bfloat16, dev)
-                    call("ctk_pack_conv_weight_dgrad_bf16", ptr(conv.weight), c_int(cout), c_int(cin), ptr(wg), stream())
-                    packs["conv"][conv] = (wp, wg)
+            convs = [conv for br in self.branches for li, (conv, _) in enumerate(br.pairs) if li > 0]
+            for conv in convs:
+                cout, cin = conv.out_channels, conv.in_channels
+                packs["conv"][conv] = (self._new((9, cout, cin), torch.bfloat16, dev), self._new((9, cin, cout), torch.bfloat16, dev))
+            for g0 in range(0, len(convs), 8):                  # forward and dgrad layouts of eight layers per launch
+                grp = convs[g0:g0 + 8]
+                k = len(grp)
+                call("ctk_pack_conv_weights_train", c_int(k),
+                     (c_void_p * k)(*[conv.weight.data_ptr() for conv in grp]),
+                     (c_int * k)(*[conv.out_channels for conv in grp]), (c_int * k)(*[conv.in_channels for conv in grp]),
+                     (c_void_p * k)(*[packs["conv"][conv][0].data_ptr() for conv in grp]),
+                     (c_void_p * k)(*[packs["conv"][conv][1].data_ptr() for conv in grp]), stream())
             if side is not None:
                 packs["conv_ready"] = torch.cuda.Event()
                 packs["conv_ready"].record(side)
