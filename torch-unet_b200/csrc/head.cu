@@ -2,14 +2,15 @@
 // two_branch_regression.py:43-53,100): split-K reduce + bias/BN1d fold + LeakyReLU + Linear(f1,f2) + BN1d fold
 // + LeakyReLU + Linear(f2,1) [+ Sigmoid * 0.5].  Everything stays fp32.  Tiny (256 images x 66 kFLOP) and latency-bound:
 // a CTA takes kImg images, so every row of FC2's weight is fetched once per four images and the loads of four dot
-// products are in flight together (one CTA per image spent 57 us walking 128 dependent row fetches; this is ~10 us).
+// products are in flight together (one CTA per image spent 57 us walking 128 dependent row fetches); 512 threads keep the
+// chain of split-K partial loads (18 per value, six in flight) to four values per thread.
 // Per image the arithmetic order is the one-image-per-CTA kernel's: results are bit-identical to round 1's.
 #include "ctk_common.h"
 #include "ctk_ptx.cuh"
 
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 512;
 constexpr int kImg = 4;
 constexpr int kMaxF1 = 512;
 constexpr int kMaxF2 = 128;
@@ -32,9 +33,12 @@ head_eval_kernel(const float* __restrict__ partial, int splits, int m_stride, in
       const float* src = partial + static_cast<size_t>(img0 + im) * f1 + f;
       float acc = 0.f;
       int s = 0;
-      for (; s + 4 <= splits; s += 4) {                    // four independent loads in flight, same order of additions
-        const float a0 = src[s * sstride], a1 = src[(s + 1) * sstride], a2 = src[(s + 2) * sstride], a3 = src[(s + 3) * sstride];
-        acc = (((acc + a0) + a1) + a2) + a3;
+      for (; s + 6 <= splits; s += 6) {                    // six independent loads in flight, same order of additions
+        float a[6];
+#pragma unroll
+        for (int u = 0; u < 6; ++u) a[u] = src[(s + u) * sstride];
+#pragma unroll
+        for (int u = 0; u < 6; ++u) acc += a[u];
       }
       for (; s < splits; ++s) acc += src[s * sstride];
       v = ctk::leaky(fmaf(acc, scale1[f], shift1[f]), slope);
